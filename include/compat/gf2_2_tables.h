@@ -1,0 +1,3 @@
+/* include/compat/gf2_2_tables.h -- drop-in for the reference header of the same name:
+ * everything it declared is provided by liboblas_b200.so through oblas_compat.h. */
+#include "../oblas_compat.h"

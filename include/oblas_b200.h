@@ -1,0 +1,156 @@
+/*
+ * oblas_b200.h -- C ABI of liboblas_b200.so, the B200 (sm_100a) implementation of
+ * the oblas hot path.  Plain pointers and sizes only; no CUDA or torch types.
+ *
+ * Two layers are exported by the same shared library:
+ *
+ *  (1) the reference's own API, unchanged (include/oblas_compat.h and the shim
+ *      headers include/compat/{oblas,octmat,gfmat,binmat}.h): the 39 functions of
+ *      liboblas.a with identical signatures and struct layouts, plus *_batch forms.
+ *      A C program written against /root/reference/{oblas,octmat,gfmat,binmat}.h
+ *      recompiles against include/compat and links -loblas_b200 without edits.
+ *
+ *  (2) this file: the device-resident / batched entry points the throughput
+ *      numbers are measured on.  Every pointer named "device-visible" may be a
+ *      cudaMalloc pointer, a managed pointer (what octmat_new & co. return) or
+ *      host memory registered with CUDA; plain host memory is staged through the
+ *      device where the function says so.
+ *
+ * All functions return 0 on success and a negative code on error unless stated;
+ * oblas_b200_last_error() gives the text.  There is NO CPU fallback: without a
+ * usable CUDA device every entry point fails (the drop-in void functions print to
+ * stderr and exit(EIO), mirroring the reference's exit(ENOMEM) convention,
+ * oblas.c:16-17).
+ */
+#ifndef OBLAS_B200_H
+#define OBLAS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* field ids = gfmat_type of the reference (gfmat.h:6) */
+#define OBLAS_B200_GF2 0
+#define OBLAS_B200_GF4 1
+#define OBLAS_B200_GF16 2
+#define OBLAS_B200_GF256 3
+
+/* table variant: 0 = split-nibble tables exactly as the reference ships them
+ * (gf2_2_tables.h:27-33 carries a defect in GF2_2_SHUF_HI), 1 = corrected GF(4)
+ * table (HI = LO << 4).  Identical for GF(16)/GF(256). */
+#define OBLAS_B200_TABLES_SHIPPED 0
+#define OBLAS_B200_TABLES_FIXED 1
+
+/* row-operation kinds of oblas_b200_rowops() */
+#define OBLAS_B200_OP_AXPY 0     /* oaxpy      octmat.c:32-46 / gfmat_axpy gfmat.c:133-145 */
+#define OBLAS_B200_OP_ADD 1      /* oaddrow    octmat.c:48-52 / gfmat_add / binmat_add      */
+#define OBLAS_B200_OP_SCAL 2     /* oscal      octmat.c:54-63 / gfmat_scal gfmat.c:147-156  */
+#define OBLAS_B200_OP_SWAP 3     /* oswaprow   octmat.c:24-30 / gfmat_swaprow / binmat_swaprow */
+#define OBLAS_B200_OP_ZERO 4     /* gfmat_zero gfmat.c:158-161 / binmat_zero binmat.c:59-62 */
+#define OBLAS_B200_OP_AXPY_B32 5 /* oaxpy_b32  octmat.c:65-68 -> oblas_ref.c:19-28          */
+
+/* multiply back-end of AXPY/SCAL: -1 = pick (linear bit-plane path when the table
+ * set is GF(2)-linear, PRMT nibble look-up otherwise), 0 = force bit-plane,
+ * 1 = force PRMT look-up (always valid). */
+#define OBLAS_B200_MUL_AUTO (-1)
+#define OBLAS_B200_MUL_LIN 0
+#define OBLAS_B200_MUL_LUT 1
+
+/* ---- context ------------------------------------------------------------ */
+int oblas_b200_init(int device);          /* idempotent; device < 0: keep current */
+void oblas_b200_shutdown(void);
+int oblas_b200_device(void);
+int oblas_b200_sm_count(void);
+const char *oblas_b200_last_error(void);
+/* all launches go to this stream (a cudaStream_t passed as void*); NULL selects
+ * the library's own non-blocking stream */
+void oblas_b200_set_stream(void *cuda_stream);
+void *oblas_b200_get_stream(void);
+int oblas_b200_sync(void);                /* wait for the current stream */
+/* drop-in (layer 1) calls synchronise before returning unless async != 0, in
+ * which case they only enqueue and the caller must oblas_b200_sync() before
+ * touching `bits` from the host */
+void oblas_b200_set_async(int async);
+/* number of kernels this library has launched so far */
+uint64_t oblas_b200_launch_count(void);
+
+/* ---- memory ------------------------------------------------------------- */
+void *oblas_b200_dev_alloc(size_t bytes);
+void oblas_b200_dev_free(void *p);
+void *oblas_b200_host_alloc(size_t bytes); /* pinned */
+void oblas_b200_host_free(void *p);
+void *oblas_b200_managed_alloc(size_t bytes, size_t align);
+void oblas_b200_free(void *p);             /* any of the above, or malloc memory */
+int oblas_b200_copy(void *dst, const void *src, size_t bytes); /* async on the stream */
+int oblas_b200_memset(void *dst, int value, size_t bytes);
+/* synthetic data: byte n of the splitmix64 counter stream `seed` (same generator
+ * as oracle/oblas_oracle.c:orc_fill_random), written by a kernel */
+int oblas_b200_fill_random(void *dst_dev, size_t bytes, uint64_t seed, uint64_t byte_offset);
+
+/* ---- batched row operations (rows a-2 .. a-8) ----------------------------- */
+/* nops independent operations of kind `op` on rows of `row_bytes` bytes
+ * (row_bytes % 16 == 0, base pointers 16-byte aligned, strides % 16 == 0):
+ *     a[dst_rows[k]]  op=  u[k] (x) b[src_rows[k]]
+ * a, b: device-visible matrix bases; strides in bytes; b may equal a.
+ * dst_rows/src_rows/u: nops entries each, device-visible OR plain host memory
+ * (host arrays are copied to the device first).  src_rows may be NULL for
+ * SCAL/ZERO, u may be NULL for ADD/SWAP/ZERO.  For OP_AXPY_B32, b is a matrix of
+ * uint32 mask words (row_bytes/32 words per row, oblas_ref.c:19-28).
+ * Destination rows must be pairwise distinct and disjoint from source rows of
+ * other operations in the same call (the operations are unordered). */
+int oblas_b200_rowops(int field, int variant, int op, int mul_mode,
+                      void *a, size_t a_stride, const void *b, size_t b_stride,
+                      size_t row_bytes, const uint32_t *dst_rows,
+                      const uint32_t *src_rows, const uint8_t *u, size_t nops);
+
+/* ---- batched elimination + RHS update (rows a-9 .. a-11) ------------------- */
+/* For every system s < nsys, in place:
+ *   A_s (rows x cols field elements, row stride a_row_stride, a_row_bytes bytes of
+ *   each row are processed = the padded stride of the reference container) and
+ *   optionally B_s (rows x b_row_bytes bytes) go through the column-skipping
+ *   Gauss-Jordan loop of DESIGN.md / oracle/ref_driver.c: rank_out[s] = rank,
+ *   pivcols_out[s*rows + t] = column of pivot t (t < rank), A_s = RREF(A_s) with
+ *   pivot rows on top, B_s transformed by the same row operations.  For a full
+ *   rank square system A_s = I and B_s = A_s^-1 B_s.
+ * A, B, rank_out, pivcols_out are device-visible.  B and pivcols_out may be NULL.
+ * GF(4) always uses true field arithmetic (the corrected table). */
+int oblas_b200_solve_batch(int field, void *A, size_t a_row_stride, size_t a_sys_stride,
+                           uint32_t rows, uint32_t cols, size_t a_row_bytes,
+                           void *B, size_t b_row_stride, size_t b_sys_stride,
+                           size_t b_row_bytes, int32_t *rank_out,
+                           uint32_t *pivcols_out, size_t nsys);
+
+/* Same job with HOST buffers (pinned for full speed, pageable works): systems are
+ * streamed host -> device -> host in chunks, copies overlapped with the
+ * elimination of the neighbouring chunks.  rank_out/pivcols_out are host arrays.
+ * chunk_systems = 0 picks a default. */
+int oblas_b200_solve_batch_host(int field, void *A_host, size_t a_row_stride, size_t a_sys_stride,
+                                uint32_t rows, uint32_t cols, size_t a_row_bytes,
+                                void *B_host, size_t b_row_stride, size_t b_sys_stride,
+                                size_t b_row_bytes, int32_t *rank_out,
+                                uint32_t *pivcols_out, size_t nsys, size_t chunk_systems);
+
+/* ---- dense apply (row a-12) ---------------------------------------------- */
+/* Y (M x nbytes) = C (M x Kc GF(256) coefficients) * D (Kc x nbytes), i.e. the
+ * loop  for i,j: oaxpy(Y, D, i, j, C[i][j])  on a zeroed Y; accumulate != 0 keeps
+ * Y's previous contents (Y ^= C*D).  nbytes % 16 == 0; device-visible pointers. */
+int oblas_b200_gf256_apply(const void *C, size_t c_stride, uint32_t M, uint32_t Kc,
+                           const void *D, size_t d_stride, void *Y, size_t y_stride,
+                           size_t nbytes, int accumulate);
+
+/* ---- row-degree kernels ("next" row f-1) ---------------------------------- */
+/* out[k] = number of non-zero elements of row rows_idx[k] in columns [s, e) with
+ * CORRECT counting (the reference's gfmat_nnz/binmat_nnz are only right for s==0,
+ * gfmat.c:193-195; the drop-in gfmat_nnz/binmat_nnz symbols mirror the reference
+ * bug-for-bug on the host).  bits: device-visible packed matrix. */
+int oblas_b200_nnz_batch(int field, const void *bits, size_t row_stride, uint32_t cols,
+                         const uint32_t *rows_idx, size_t nrows, uint32_t s, uint32_t e,
+                         uint32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

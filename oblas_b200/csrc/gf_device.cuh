@@ -1,0 +1,87 @@
+// gf_device.cuh -- register-level GF(2^e) arithmetic on packed 32-bit words.
+//
+// Three ways to apply "multiply every byte by the constant described by the
+// split-nibble tables (lo,hi)" -- the operation oblas_axpy/oblas_scal perform per
+// byte (oblas_ref.c:3-7, :12-16):
+//   * mul_lin : the tables are GF(2)-linear in the input nibble (true for the
+//               GF(256), GF(16) and corrected GF(4) tables), so
+//               out = XOR_i spread(bit_i(in)) & basis_i  -- 1 shift + 1 PRMT
+//               (sign-replicate) + 1 LOP3 per input bit, no table look-ups.
+//   * mul_lut : arbitrary 16-entry tables held in 4+4 registers, looked up with
+//               PRMT byte permutes (the GPU analogue of pshufb, oblas_avx.c:15-16).
+//               Needed for the shipped GF(4) HI table, which is not linear.
+//   * (shared-memory Four-Russians tables for whole rows live in solve.cuh)
+#pragma once
+#include "ob2_platform.h"
+
+namespace ob2 {
+
+// 0xFF in every byte of w whose bit 7 is set (PRMT sign-replicate mode).
+OB2_D uint32_t spread_msb(uint32_t w) { return __byte_perm(w, 0u, 0xba98u); }
+
+struct Basis8 {  // basis_i replicated into the 4 bytes of a word
+  uint32_t b[8];
+};
+
+OB2_D uint32_t mul_lin(uint32_t w, const Basis8 &u) {
+  uint32_t y = spread_msb(w) & u.b[7];
+#pragma unroll
+  for (int i = 0; i < 7; i++) y ^= spread_msb(w << (7 - i)) & u.b[i];
+  return y;
+}
+
+struct Lut16x2 {  // lo[16], hi[16] as 4 little-endian words each
+  uint32_t lo[4], hi[4];
+};
+
+// 16-entry byte table look-up for four indices at once; idx bytes are 0..15.
+OB2_D uint32_t lut16(uint32_t idx, const uint32_t t[4]) {
+  uint32_t x = idx & 0x07070707u;
+  uint32_t p = x | (x >> 4);                   // byte0 = i0|i1<<4, byte2 = i2|i3<<4
+  uint32_t sel = __byte_perm(p, 0u, 0x4420u);  // 16-bit selector, nibble n = idx_n & 7
+  uint32_t a = __byte_perm(t[0], t[1], sel);   // entries 0..7
+  uint32_t b = __byte_perm(t[2], t[3], sel);   // entries 8..15
+  uint32_t m = spread_msb(idx << 4);           // 0xFF where idx bit 3 set
+  return (a & ~m) | (b & m);
+}
+
+OB2_D uint32_t mul_lut(uint32_t w, const Lut16x2 &t) {
+  uint32_t lo = w & 0x0f0f0f0fu;
+  uint32_t hi = (w >> 4) & 0x0f0f0f0fu;
+  return lut16(lo, t.lo) ^ lut16(hi, t.hi);
+}
+
+// ---- multiply every packed element of a word by x (the field generator) ------
+// EXP = bits per element; elements are packed little-endian (gfmat.c:88).
+template <int EXP>
+OB2_D uint32_t xtime(uint32_t w) {
+  if (EXP == 8) {  // poly 285: x^8 = x^4+x^3+x^2+1 = 0x1d
+    uint32_t m = spread_msb(w);
+    return ((w & 0x7f7f7f7fu) << 1) ^ (m & 0x1d1d1d1du);
+  } else if (EXP == 4) {  // poly 19: x^4 = x+1 = 3
+    uint32_t top = (w >> 3) & 0x11111111u;
+    return ((w & 0x77777777u) << 1) ^ (top * 3u);
+  } else if (EXP == 2) {  // poly 7: x^2 = x+1 = 3
+    uint32_t top = (w >> 1) & 0x55555555u;
+    return ((w & 0x55555555u) << 1) ^ (top * 3u);
+  } else {
+    return w;
+  }
+}
+
+// scalar field helpers on single elements (used by the panel factorisation)
+template <int EXP>
+OB2_D uint32_t gf_mul_scalar(uint32_t a, uint32_t b) {
+  if (EXP == 1) return a & b;
+  constexpr uint32_t poly = (EXP == 2) ? 7u : (EXP == 4) ? 19u : 285u;
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < EXP; i++) {
+    acc ^= (0u - ((b >> i) & 1u)) & a;
+    a <<= 1;
+    a ^= (0u - ((a >> EXP) & 1u)) & poly;
+  }
+  return acc;
+}
+
+}  // namespace ob2

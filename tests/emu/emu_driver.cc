@@ -1,0 +1,139 @@
+// tests/emu/emu_driver.cc -- TEST INFRASTRUCTURE ONLY.
+// Compiles the product's kernel sources (rowops.cuh, solve.cuh, apply.cuh) for the
+// host-thread emulation of cuda_emu.h and exposes them through a small C ABI so
+// that tests/test_emu.py can compare kernel LOGIC with the oracle without a GPU.
+#include "cuda_emu.h"
+
+#include "apply.cuh"
+#include "rowops.cuh"
+#include "solve.cuh"
+#include "tables_host.h"
+
+using namespace ob2;
+
+static DevTableSet g_sets[TS_COUNT];
+static bool g_sets_ready = false;
+static void ensure_sets() {
+  if (!g_sets_ready) {
+    fill_all_table_sets(g_sets);
+    g_sets_ready = true;
+  }
+}
+
+extern "C" {
+
+const uint8_t *emu_table(int ts, int which, unsigned *len) {
+  ensure_sets();
+  switch (which) {
+  case 3: *len = 4096; return g_sets[ts].lo;
+  case 4: *len = 4096; return g_sets[ts].hi;
+  case 2: *len = 256; return g_sets[ts].inv;
+  }
+  *len = 0;
+  return nullptr;
+}
+int emu_table_linear(int ts) {
+  ensure_sets();
+  return g_sets[ts].linear;
+}
+
+int emu_rowops(int op, int mode, int ts, uint8_t *a, size_t a_stride, const uint8_t *b,
+               size_t b_stride, uint32_t row_bytes, const uint32_t *dst_rows,
+               const uint32_t *src_rows, const uint8_t *u, uint32_t u0, uint32_t nops) {
+  ensure_sets();
+  if (row_bytes & 15) return -1;
+  RowOpArgs p;
+  memset(&p, 0, sizeof p);
+  p.a = a;
+  p.b = b;
+  p.a_stride = a_stride;
+  p.b_stride = b_stride;
+  p.chunks_per_row = row_bytes / 16;
+  FastDiv fd = make_fastdiv(p.chunks_per_row);
+  p.div_mul = fd.mul;
+  p.div_shift = fd.shift;
+  p.total_chunks = nops * p.chunks_per_row;
+  p.dst_rows = dst_rows;
+  p.src_rows = src_rows;
+  p.u = u;
+  p.u0 = u0;
+  p.ts = ts >= 0 ? &g_sets[ts] : nullptr;
+  launch_rowops(op, mode, p, nullptr);
+  return 0;
+}
+
+int emu_rowop_explicit(int op, int mode, uint8_t *a, const uint8_t *b, uint32_t row_bytes,
+                       const uint8_t *lo16, const uint8_t *hi16) {
+  RowOpArgs p;
+  memset(&p, 0, sizeof p);
+  static const uint32_t zero = 0;
+  p.a = a;
+  p.b = b;
+  p.chunks_per_row = row_bytes / 16;
+  FastDiv fd = make_fastdiv(p.chunks_per_row);
+  p.div_mul = fd.mul;
+  p.div_shift = fd.shift;
+  p.total_chunks = p.chunks_per_row;
+  p.dst_rows = &zero;
+  p.src_rows = &zero;
+  p.u0 = 2;
+  p.use_explicit = 1;
+  make_lut(p.lut, lo16, hi16);
+  make_basis(p.basis, lo16, hi16);
+  launch_rowops(op, mode, p, nullptr);
+  return 0;
+}
+
+int emu_rowop_bytes(int op, uint8_t *a, const uint8_t *b, size_t k, const uint8_t *lo16,
+                    const uint8_t *hi16, uint32_t u) {
+  Lut16x2 lt;
+  memset(&lt, 0, sizeof lt);
+  if (lo16) make_lut(lt, lo16, hi16);
+  launch_rowop_bytes(op, a, b, k, lt, u, nullptr);
+  return 0;
+}
+
+int emu_fastdiv_check(uint32_t d, uint32_t nmax, uint32_t step) {
+  FastDiv fd = make_fastdiv(d);
+  for (uint64_t n = 0; n <= nmax; n += step)
+    if (fastdiv((uint32_t)n, fd.mul, fd.shift) != (uint32_t)n / d) return 0;
+  uint32_t edge[] = {0x7fffffffu, 0x7ffffffeu, d - 1, d, d + 1, 2 * d - 1, 2 * d};
+  for (uint32_t n : edge)
+    if (n < 0x80000000u && fastdiv(n, fd.mul, fd.shift) != n / d) return 0;
+  return 1;
+}
+
+int emu_solve(int field, uint8_t *A, size_t a_rs, size_t a_ss, uint32_t rows, uint32_t cols,
+              uint32_t a_bytes, uint8_t *B, size_t b_rs, size_t b_ss, uint32_t b_bytes,
+              int32_t *rank, uint32_t *pivcols, uint32_t nsys, uint32_t grid, uint32_t threads,
+              size_t smem_limit, int force_nbw) {
+  ensure_sets();
+  SolveArgs p;
+  memset(&p, 0, sizeof p);
+  p.A = A; p.a_rs = a_rs; p.a_ss = a_ss; p.rows = rows; p.cols = cols; p.a_bytes = a_bytes;
+  p.B = B; p.b_rs = b_rs; p.b_ss = b_ss; p.b_bytes = B ? b_bytes : 0;
+  p.rank = rank; p.pivcols = pivcols; p.nsys = nsys;
+  int ts = table_set_id(field, 1);
+  p.inv = ts >= 0 ? g_sets[ts].inv : nullptr;
+  if (force_nbw == 2) {
+    switch (field) {
+    case OB2_GF256: return launch_solve_t<8, 2>(p, grid, threads, smem_limit, nullptr);
+    case OB2_GF16: return launch_solve_t<4, 2>(p, grid, threads, smem_limit, nullptr);
+    case OB2_GF4: return launch_solve_t<2, 2>(p, grid, threads, smem_limit, nullptr);
+    case OB2_GF2: return launch_solve_t<1, 2>(p, grid, threads, smem_limit, nullptr);
+    }
+  }
+  return launch_solve(field, p, grid, threads, smem_limit, nullptr);
+}
+
+int emu_apply(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, const uint8_t *D,
+              size_t d_stride, uint8_t *Y, size_t y_stride, uint32_t nbytes, int accumulate,
+              uint32_t threads) {
+  ApplyArgs p;
+  memset(&p, 0, sizeof p);
+  p.C = C; p.c_stride = c_stride; p.M = M; p.Kc = Kc; p.D = D; p.d_stride = d_stride;
+  p.Y = Y; p.y_stride = y_stride; p.nbytes = nbytes; p.accumulate = accumulate;
+  return launch_apply(p, threads, nullptr);
+}
+
+}  // extern "C"
