@@ -1,0 +1,1093 @@
+// oblas_b200.cu -- liboblas_b200.so: context, memory model and every exported entry
+// point (include/oblas_b200.h, include/oblas_compat.h).  Kernels live in
+// rowops.cuh / solve.cuh / apply.cuh.  sm_100a only; no CPU path: every compute
+// entry point ends in a kernel launch or fails.
+#define OBLAS_B200_BUILDING 1
+#include <cuda_runtime.h>
+#include <errno.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "apply.cuh"
+#include "rowops.cuh"
+#include "solve.cuh"
+#include "tables_host.h"
+
+#include "../../include/oblas_b200.h"
+
+using namespace ob2;
+
+// ============================================================================
+// context
+// ============================================================================
+namespace {
+
+struct Ctx {
+  bool ready = false;
+  int device = -1;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  bool async = false;
+  DevTableSet *d_sets = nullptr;  // [TS_COUNT] in device memory
+  DevTableSet h_sets[TS_COUNT];
+  // device scratch for index arrays handed over from plain host memory
+  void *scratch = nullptr;
+  size_t scratch_bytes = 0;
+  std::mutex mu;
+  std::atomic<uint64_t> launches{0};
+};
+Ctx g;
+thread_local char tl_err[512] = "";
+
+int fail(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(tl_err, sizeof tl_err, fmt, ap);
+  va_end(ap);
+  return -1;
+}
+#define CK(call)                                                                   \
+  do {                                                                             \
+    cudaError_t e_ = (call);                                                       \
+    if (e_ != cudaSuccess)                                                         \
+      return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+int ensure_init() {
+  if (g.ready) return 0;
+  return oblas_b200_init(-1);
+}
+
+// The void functions of the reference API cannot report errors; like the
+// reference's exit(ENOMEM) (oblas.c:16-17) they terminate loudly.
+[[noreturn]] void die(const char *what) {
+  fprintf(stderr, "liboblas_b200: %s: %s\n", what, tl_err);
+  exit(EIO);
+}
+#define MUST(expr, what)                                                           \
+  do {                                                                             \
+    if ((expr) != 0) die(what);                                                    \
+  } while (0)
+
+enum PtrKind { PK_HOST = 0, PK_DEVVIS = 1 };
+PtrKind classify(const void *p) {
+  if (!p) return PK_HOST;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return PK_HOST;
+  }
+  if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged ||
+      at.type == cudaMemoryTypeHost)
+    return PK_DEVVIS;
+  return PK_HOST;
+}
+
+int scratch_reserve(size_t bytes) {
+  if (bytes <= g.scratch_bytes) return 0;
+  if (g.scratch) {
+    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaFree(g.scratch));
+    g.scratch = nullptr;
+    g.scratch_bytes = 0;
+  }
+  size_t want = bytes < (1u << 20) ? (1u << 20) : bytes * 2;
+  CK(cudaMalloc(&g.scratch, want));
+  g.scratch_bytes = want;
+  return 0;
+}
+
+int after_launch(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("%s launch failed: %s", what, cudaGetErrorString(e));
+  g.launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int finish_dropin() {
+  if (g.async) return 0;
+  CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+__global__ void fill_random_kernel(uint64_t *dst, size_t nwords, uint64_t seed, uint64_t word0) {
+  for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < nwords;
+       n += (size_t)gridDim.x * blockDim.x) {
+    uint64_t z = seed + (word0 + n + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    dst[n] = z ^ (z >> 31);
+  }
+}
+
+// one warp per requested row: count non-zero elements in columns [s, e)
+template <int EXP>
+__global__ void nnz_kernel(const uint8_t *bits, size_t row_stride, const uint32_t *rows_idx,
+                           uint32_t nrows, uint32_t s, uint32_t e, uint32_t *out) {
+  constexpr uint32_t VPW = 32 / EXP;
+  uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= nrows) return;
+  const uint32_t *row = reinterpret_cast<const uint32_t *>(bits + (size_t)rows_idx[warp] * row_stride);
+  uint32_t w0 = s / VPW, w1 = (e + VPW - 1) / VPW, cnt = 0;
+  for (uint32_t w = w0 + lane; w < w1; w += 32) {
+    uint32_t x = row[w], z = x;
+    // fold every element onto its lowest bit
+    if (EXP >= 2) z |= z >> 1;
+    if (EXP >= 4) z |= z >> 2;
+    if (EXP >= 8) z |= z >> 4;
+    z &= (EXP == 1) ? 0xffffffffu : (EXP == 2) ? 0x55555555u : (EXP == 4) ? 0x11111111u : 0x01010101u;
+    // keep elements with index in [s, e)
+    uint32_t first = w * VPW;
+    for (uint32_t k = 0; k < VPW; k++) {
+      uint32_t col = first + k;
+      if (col < s || col >= e) z &= ~(1u << (k * EXP));
+    }
+    cnt += __popc(z);
+  }
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) out[warp] = cnt;
+}
+
+}  // namespace
+
+// ============================================================================
+// layer 2: oblas_b200_* C ABI
+// ============================================================================
+extern "C" {
+
+int oblas_b200_init(int device) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  if (g.ready) {
+    if (device >= 0 && device != g.device) return fail("already initialised on device %d", g.device);
+    return 0;
+  }
+  int n = 0;
+  CK(cudaGetDeviceCount(&n));
+  if (n <= 0) return fail("no CUDA device");
+  if (device < 0) {
+    CK(cudaGetDevice(&device));
+  }
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  g.device = device;
+  g.sm_count = prop.multiProcessorCount;
+  g.smem_optin = prop.sharedMemPerBlockOptin;
+  CK(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
+  g.stream = g.own_stream;
+  fill_all_table_sets(g.h_sets);
+  CK(cudaMalloc(&g.d_sets, sizeof(DevTableSet) * TS_COUNT));
+  CK(cudaMemcpy(g.d_sets, g.h_sets, sizeof(DevTableSet) * TS_COUNT, cudaMemcpyHostToDevice));
+  g.ready = true;
+  return 0;
+}
+
+void oblas_b200_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  if (!g.ready) return;
+  cudaStreamSynchronize(g.stream);
+  if (g.scratch) cudaFree(g.scratch);
+  g.scratch = nullptr;
+  g.scratch_bytes = 0;
+  cudaFree(g.d_sets);
+  g.d_sets = nullptr;
+  cudaStreamDestroy(g.own_stream);
+  g.own_stream = g.stream = nullptr;
+  g.ready = false;
+}
+
+int oblas_b200_device(void) { return g.ready ? g.device : -1; }
+int oblas_b200_sm_count(void) { return ensure_init() ? -1 : g.sm_count; }
+const char *oblas_b200_last_error(void) { return tl_err; }
+void oblas_b200_set_stream(void *s) {
+  if (ensure_init()) return;
+  g.stream = s ? (cudaStream_t)s : g.own_stream;
+}
+void *oblas_b200_get_stream(void) { return ensure_init() ? nullptr : (void *)g.stream; }
+int oblas_b200_sync(void) {
+  if (ensure_init()) return -1;
+  CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+void oblas_b200_set_async(int async) { g.async = async != 0; }
+uint64_t oblas_b200_launch_count(void) { return g.launches.load(); }
+
+// ---- memory -----------------------------------------------------------------
+void *oblas_b200_dev_alloc(size_t bytes) {
+  if (ensure_init()) return nullptr;
+  void *p = nullptr;
+  if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
+    fail("cudaMalloc(%zu) failed", bytes);
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void oblas_b200_dev_free(void *p) {
+  if (p) cudaFree(p);
+}
+void *oblas_b200_host_alloc(size_t bytes) {
+  if (ensure_init()) return nullptr;
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    fail("cudaHostAlloc(%zu) failed", bytes);
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void oblas_b200_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+void *oblas_b200_managed_alloc(size_t bytes, size_t align) {
+  if (ensure_init()) return nullptr;
+  (void)align;  // cudaMallocManaged returns >= 256-byte aligned blocks
+  void *p = nullptr;
+  if (cudaMallocManaged(&p, bytes ? bytes : 1, cudaMemAttachGlobal) != cudaSuccess) {
+    fail("cudaMallocManaged(%zu) failed", bytes);
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void oblas_b200_free(void *p) {
+  if (!p) return;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    free(p);
+    return;
+  }
+  switch (at.type) {
+  case cudaMemoryTypeDevice:
+  case cudaMemoryTypeManaged:
+    if (g.ready) cudaStreamSynchronize(g.stream);
+    cudaFree(p);
+    break;
+  case cudaMemoryTypeHost:
+    cudaFreeHost(p);
+    break;
+  default:
+    free(p);
+  }
+}
+int oblas_b200_copy(void *dst, const void *src, size_t bytes) {
+  if (ensure_init()) return -1;
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, g.stream));
+  return 0;
+}
+int oblas_b200_memset(void *dst, int value, size_t bytes) {
+  if (ensure_init()) return -1;
+  CK(cudaMemsetAsync(dst, value, bytes, g.stream));
+  return 0;
+}
+int oblas_b200_fill_random(void *dst, size_t bytes, uint64_t seed, uint64_t byte_offset) {
+  if (ensure_init()) return -1;
+  if ((bytes & 7) || (byte_offset & 7) || (reinterpret_cast<uintptr_t>(dst) & 7))
+    return fail("fill_random: dst, bytes and byte_offset must be multiples of 8");
+  size_t nwords = bytes / 8;
+  if (!nwords) return 0;
+  size_t blocks = (nwords + 255) / 256;
+  if (blocks > (size_t)g.sm_count * 16) blocks = (size_t)g.sm_count * 16;
+  fill_random_kernel<<<(unsigned)blocks, 256, 0, g.stream>>>((uint64_t *)dst, nwords, seed, byte_offset / 8);
+  return after_launch("fill_random");
+}
+
+// ---- row operations ------------------------------------------------------------
+// Bring an index/scalar array to the device if it lives in plain host memory.
+// `slot` is a byte offset inside the scratch block.
+static int stage_array(const void *src, size_t bytes, size_t slot, const void **out) {
+  if (!src) {
+    *out = nullptr;
+    return 0;
+  }
+  if (classify(src) == PK_DEVVIS) {
+    *out = src;
+    return 0;
+  }
+  void *dst = (char *)g.scratch + slot;
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g.stream));
+  *out = dst;
+  return 0;
+}
+
+int oblas_b200_rowops(int field, int variant, int op, int mul_mode, void *a, size_t a_stride,
+                      const void *b, size_t b_stride, size_t row_bytes,
+                      const uint32_t *dst_rows, const uint32_t *src_rows, const uint8_t *u,
+                      size_t nops) {
+  if (ensure_init()) return -1;
+  if (nops == 0 || row_bytes == 0) return 0;
+  if (op < OP_AXPY || op > OP_AXPY_B32) return fail("rowops: bad op %d", op);
+  if ((row_bytes & 15) || (a_stride & 15) || (reinterpret_cast<uintptr_t>(a) & 15))
+    return fail("rowops: a, a_stride and row_bytes must be multiples of 16");
+  const bool needs_b = (op == OP_AXPY || op == OP_ADD || op == OP_SWAP || op == OP_AXPY_B32);
+  if (needs_b) {
+    if (!b || !src_rows) return fail("rowops: op %d needs b and src_rows", op);
+    size_t balign = (op == OP_AXPY_B32) ? 3 : 15;
+    if ((b_stride & balign) || (reinterpret_cast<uintptr_t>(b) & balign))
+      return fail("rowops: b / b_stride misaligned");
+  }
+  const bool needs_u = (op == OP_AXPY || op == OP_SCAL || op == OP_AXPY_B32);
+  if (needs_u && !u) return fail("rowops: op %d needs u", op);
+  if (classify(a) != PK_DEVVIS || (needs_b && classify(b) != PK_DEVVIS))
+    return fail("rowops: matrix pointers must be device-visible (device, managed or pinned)");
+  const bool needs_tab = (op == OP_AXPY || op == OP_SCAL);
+  int ts = -1, mode = MUL_LIN;
+  if (needs_tab && field != OB2_GF2) {
+    ts = table_set_id(field, variant);
+    if (ts < 0) return fail("rowops: bad field %d", field);
+    bool linear = g.h_sets[ts].linear != 0;
+    if (mul_mode == OBLAS_B200_MUL_AUTO) mode = linear ? MUL_LIN : MUL_LUT;
+    else if (mul_mode == OBLAS_B200_MUL_LIN) {
+      if (!linear) return fail("rowops: table set %d is not GF(2)-linear, MUL_LIN is invalid", ts);
+      mode = MUL_LIN;
+    } else mode = MUL_LUT;
+  }
+  // GF(2) has no tables (gfmat.c:14-19): only u in {0,1} is meaningful (u==1 is XOR,
+  // the reference dereferences NULL for u>1); give the kernel a valid set anyway
+  if (needs_tab && field == OB2_GF2) ts = TS_GF4_FIXED;
+  std::lock_guard<std::mutex> lk(g.mu);
+  const size_t idx_bytes = nops * sizeof(uint32_t);
+  const size_t slot1 = (idx_bytes + 255) & ~(size_t)255, slot2 = 2 * slot1;
+  if (scratch_reserve(slot2 + nops + 256)) return -1;
+  const void *d_dst, *d_src, *d_u;
+  if (stage_array(dst_rows, idx_bytes, 0, &d_dst)) return -1;
+  if (stage_array(src_rows, idx_bytes, slot1, &d_src)) return -1;
+  if (stage_array(needs_u ? u : nullptr, nops, slot2, &d_u)) return -1;
+
+  const uint32_t cpr = (uint32_t)(row_bytes / 16);
+  const size_t max_ops = (size_t)0x7fffffffu / cpr;
+  for (size_t first = 0; first < nops; first += max_ops) {
+    size_t cnt = nops - first < max_ops ? nops - first : max_ops;
+    RowOpArgs p;
+    memset(&p, 0, sizeof p);
+    p.a = (uint8_t *)a;
+    p.b = (const uint8_t *)b;
+    p.a_stride = a_stride;
+    p.b_stride = b_stride;
+    p.chunks_per_row = cpr;
+    FastDiv fd = make_fastdiv(cpr);
+    p.div_mul = fd.mul;
+    p.div_shift = fd.shift;
+    p.total_chunks = (uint32_t)(cnt * cpr);
+    p.dst_rows = (const uint32_t *)d_dst + first;
+    p.src_rows = d_src ? (const uint32_t *)d_src + first : nullptr;
+    p.u = d_u ? (const uint8_t *)d_u + first : nullptr;
+    p.ts = ts >= 0 ? g.d_sets + ts : nullptr;
+    launch_rowops(op, mode, p, g.stream);
+    if (after_launch("rowops")) return -1;
+  }
+  return 0;
+}
+
+// ---- elimination -----------------------------------------------------------------
+static int solve_common(int field, SolveArgs &p, size_t nsys) {
+  if (field < OB2_GF2 || field > OB2_GF256) return fail("solve: bad field %d", field);
+  if (p.rows == 0 || p.cols == 0 || nsys == 0) return 0;
+  if ((p.a_bytes & 15) || (p.a_rs & 15)) return fail("solve: A row bytes / stride must be multiples of 16");
+  if (p.B && ((p.b_bytes & 15) || (p.b_rs & 15))) return fail("solve: B row bytes / stride must be multiples of 16");
+  uint32_t ebits = kBits[field];
+  if ((size_t)p.cols * ebits > (size_t)p.a_bytes * 8) return fail("solve: cols exceed a_row_bytes");
+  int ts = table_set_id(field, 1);
+  p.inv = ts >= 0 ? g.d_sets[ts].inv : nullptr;
+  p.nsys = (uint32_t)nsys;
+  uint32_t grid = nsys < (size_t)g.sm_count ? (uint32_t)nsys : (uint32_t)g.sm_count;
+  int rc = launch_solve(field, p, grid, 512, g.smem_optin, g.stream);
+  if (rc == -1)
+    return fail("solve: %u rows do not fit the shared-memory panel (limit %zu bytes); no fallback", p.rows, g.smem_optin);
+  if (rc) return fail("solve: cudaFuncSetAttribute failed");
+  return after_launch("solve");
+}
+
+int oblas_b200_solve_batch(int field, void *A, size_t a_row_stride, size_t a_sys_stride,
+                           uint32_t rows, uint32_t cols, size_t a_row_bytes, void *B,
+                           size_t b_row_stride, size_t b_sys_stride, size_t b_row_bytes,
+                           int32_t *rank_out, uint32_t *pivcols_out, size_t nsys) {
+  if (ensure_init()) return -1;
+  if (!A || !rank_out) return fail("solve: A and rank_out are required");
+  if (classify(A) != PK_DEVVIS || (B && classify(B) != PK_DEVVIS) || classify(rank_out) != PK_DEVVIS ||
+      (pivcols_out && classify(pivcols_out) != PK_DEVVIS))
+    return fail("solve_batch: pointers must be device-visible; use oblas_b200_solve_batch_host for host buffers");
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (a_sys_stride & 15) ||
+      (B && ((reinterpret_cast<uintptr_t>(B) & 15) || (b_sys_stride & 15))))
+    return fail("solve: base pointers / system strides must be multiples of 16");
+  SolveArgs p;
+  memset(&p, 0, sizeof p);
+  p.A = (uint8_t *)A; p.a_rs = a_row_stride; p.a_ss = a_sys_stride;
+  p.rows = rows; p.cols = cols; p.a_bytes = (uint32_t)a_row_bytes;
+  p.B = (uint8_t *)B; p.b_rs = b_row_stride; p.b_ss = b_sys_stride;
+  p.b_bytes = B ? (uint32_t)b_row_bytes : 0;
+  p.rank = rank_out; p.pivcols = pivcols_out;
+  std::lock_guard<std::mutex> lk(g.mu);
+  return solve_common(field, p, nsys);
+}
+
+int oblas_b200_solve_batch_host(int field, void *A_host, size_t a_row_stride, size_t a_sys_stride,
+                                uint32_t rows, uint32_t cols, size_t a_row_bytes, void *B_host,
+                                size_t b_row_stride, size_t b_sys_stride, size_t b_row_bytes,
+                                int32_t *rank_out, uint32_t *pivcols_out, size_t nsys,
+                                size_t chunk_systems) {
+  if (ensure_init()) return -1;
+  if (!A_host || !rank_out) return fail("solve_host: A and rank_out are required");
+  if (nsys == 0) return 0;
+  if ((a_sys_stride & 15) || (B_host && (b_sys_stride & 15)))
+    return fail("solve_host: system strides must be multiples of 16");
+  std::lock_guard<std::mutex> lk(g.mu);
+  const size_t per_sys = a_sys_stride + (B_host ? b_sys_stride : 0) + 4 + (pivcols_out ? (size_t)rows * 4 : 0);
+  if (chunk_systems == 0) {
+    // ~3 waves of the grid per chunk keeps the tail short and the copies overlapped
+    chunk_systems = (size_t)g.sm_count * 2;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    while (chunk_systems > 1 && chunk_systems * per_sys * 3 > free_b / 2) chunk_systems /= 2;
+  }
+  if (chunk_systems > nsys) chunk_systems = nsys;
+  const int NL = 3;  // lanes: chunk c runs on lane c % NL (own stream, own buffers)
+  struct Lane {
+    cudaStream_t s = nullptr;
+    uint8_t *A = nullptr, *B = nullptr;
+    int32_t *rank = nullptr;
+    uint32_t *piv = nullptr;
+  } lane[NL];
+  int rc = 0;
+  cudaStream_t saved = g.stream;
+  auto cleanup = [&]() {
+    for (int l = 0; l < NL; l++) {
+      if (lane[l].s) cudaStreamSynchronize(lane[l].s);
+      cudaFree(lane[l].A);
+      cudaFree(lane[l].B);
+      cudaFree(lane[l].rank);
+      cudaFree(lane[l].piv);
+      if (lane[l].s) cudaStreamDestroy(lane[l].s);
+    }
+    g.stream = saved;
+  };
+#define CKL(call)                                                                  \
+  do {                                                                             \
+    cudaError_t e_ = (call);                                                       \
+    if (e_ != cudaSuccess) {                                                       \
+      fail("%s failed: %s", #call, cudaGetErrorString(e_));                        \
+      cleanup();                                                                   \
+      return -1;                                                                   \
+    }                                                                              \
+  } while (0)
+  for (int l = 0; l < NL; l++) {
+    CKL(cudaStreamCreateWithFlags(&lane[l].s, cudaStreamNonBlocking));
+    CKL(cudaMalloc(&lane[l].A, chunk_systems * a_sys_stride));
+    if (B_host) CKL(cudaMalloc(&lane[l].B, chunk_systems * b_sys_stride));
+    CKL(cudaMalloc(&lane[l].rank, chunk_systems * 4));
+    if (pivcols_out) CKL(cudaMalloc(&lane[l].piv, chunk_systems * (size_t)rows * 4));
+  }
+  size_t c = 0;
+  for (size_t first = 0; first < nsys; first += chunk_systems, c++) {
+    Lane &L = lane[c % NL];
+    size_t cnt = nsys - first < chunk_systems ? nsys - first : chunk_systems;
+    CKL(cudaMemcpyAsync(L.A, (uint8_t *)A_host + first * a_sys_stride, cnt * a_sys_stride,
+                        cudaMemcpyHostToDevice, L.s));
+    if (B_host)
+      CKL(cudaMemcpyAsync(L.B, (uint8_t *)B_host + first * b_sys_stride, cnt * b_sys_stride,
+                          cudaMemcpyHostToDevice, L.s));
+    if (pivcols_out) CKL(cudaMemsetAsync(L.piv, 0xff, cnt * (size_t)rows * 4, L.s));
+    SolveArgs p;
+    memset(&p, 0, sizeof p);
+    p.A = L.A; p.a_rs = a_row_stride; p.a_ss = a_sys_stride;
+    p.rows = rows; p.cols = cols; p.a_bytes = (uint32_t)a_row_bytes;
+    p.B = L.B; p.b_rs = b_row_stride; p.b_ss = b_sys_stride;
+    p.b_bytes = B_host ? (uint32_t)b_row_bytes : 0;
+    p.rank = L.rank; p.pivcols = L.piv;
+    g.stream = L.s;
+    rc = solve_common(field, p, cnt);
+    g.stream = saved;
+    if (rc) {
+      cleanup();
+      return rc;
+    }
+    CKL(cudaMemcpyAsync((uint8_t *)A_host + first * a_sys_stride, L.A, cnt * a_sys_stride,
+                        cudaMemcpyDeviceToHost, L.s));
+    if (B_host)
+      CKL(cudaMemcpyAsync((uint8_t *)B_host + first * b_sys_stride, L.B, cnt * b_sys_stride,
+                          cudaMemcpyDeviceToHost, L.s));
+    CKL(cudaMemcpyAsync(rank_out + first, L.rank, cnt * 4, cudaMemcpyDeviceToHost, L.s));
+    if (pivcols_out)
+      CKL(cudaMemcpyAsync(pivcols_out + first * rows, L.piv, cnt * (size_t)rows * 4,
+                          cudaMemcpyDeviceToHost, L.s));
+  }
+  for (int l = 0; l < NL; l++) CKL(cudaStreamSynchronize(lane[l].s));
+#undef CKL
+  cleanup();
+  return 0;
+}
+
+// ---- apply ---------------------------------------------------------------------
+int oblas_b200_gf256_apply(const void *C, size_t c_stride, uint32_t M, uint32_t Kc, const void *D,
+                           size_t d_stride, void *Y, size_t y_stride, size_t nbytes, int accumulate) {
+  if (ensure_init()) return -1;
+  if (M == 0 || nbytes == 0) return 0;
+  if (!C || !D || !Y) return fail("apply: null pointer");
+  if ((nbytes & 15) || (d_stride & 15) || (y_stride & 15) || (reinterpret_cast<uintptr_t>(D) & 15) ||
+      (reinterpret_cast<uintptr_t>(Y) & 15))
+    return fail("apply: D, Y, their strides and nbytes must be multiples of 16");
+  if (classify(C) != PK_DEVVIS || classify(D) != PK_DEVVIS || classify(Y) != PK_DEVVIS)
+    return fail("apply: pointers must be device-visible");
+  ApplyArgs p;
+  memset(&p, 0, sizeof p);
+  p.C = (const uint8_t *)C; p.c_stride = c_stride; p.M = M; p.Kc = Kc;
+  p.D = (const uint8_t *)D; p.d_stride = d_stride;
+  p.Y = (uint8_t *)Y; p.y_stride = y_stride; p.nbytes = (uint32_t)nbytes; p.accumulate = accumulate;
+  std::lock_guard<std::mutex> lk(g.mu);
+  int rc = launch_apply(p, 512, g.stream);
+  if (rc) return fail("apply: launch configuration failed (%d)", rc);
+  return after_launch("apply");
+}
+
+// ---- row degree -------------------------------------------------------------------
+int oblas_b200_nnz_batch(int field, const void *bits, size_t row_stride, uint32_t cols,
+                         const uint32_t *rows_idx, size_t nrows, uint32_t s, uint32_t e, uint32_t *out) {
+  if (ensure_init()) return -1;
+  if (nrows == 0) return 0;
+  if (e > cols) e = cols;
+  if (s > e) s = e;
+  if (classify(bits) != PK_DEVVIS || classify(rows_idx) != PK_DEVVIS || classify(out) != PK_DEVVIS)
+    return fail("nnz_batch: pointers must be device-visible");
+  std::lock_guard<std::mutex> lk(g.mu);
+  unsigned blocks = (unsigned)((nrows * 32 + 255) / 256);
+  const uint8_t *p = (const uint8_t *)bits;
+  switch (field) {
+  case OB2_GF2: nnz_kernel<1><<<blocks, 256, 0, g.stream>>>(p, row_stride, rows_idx, (uint32_t)nrows, s, e, out); break;
+  case OB2_GF4: nnz_kernel<2><<<blocks, 256, 0, g.stream>>>(p, row_stride, rows_idx, (uint32_t)nrows, s, e, out); break;
+  case OB2_GF16: nnz_kernel<4><<<blocks, 256, 0, g.stream>>>(p, row_stride, rows_idx, (uint32_t)nrows, s, e, out); break;
+  case OB2_GF256: nnz_kernel<8><<<blocks, 256, 0, g.stream>>>(p, row_stride, rows_idx, (uint32_t)nrows, s, e, out); break;
+  default: return fail("nnz_batch: bad field %d", field);
+  }
+  return after_launch("nnz");
+}
+
+}  // extern "C"
+
+// ============================================================================
+// layer 1: the reference's API (include/oblas_compat.h)
+// ============================================================================
+#include "../../include/oblas_compat.h"
+
+namespace {
+
+unsigned round_up_u(unsigned k, unsigned a) { return (k + a - 1) / a * a; }
+
+// One-row operation through the batched kernel, explicit tables, operands that
+// are already device-visible and 16-byte friendly.
+int single_vec(int op, int mode, uint8_t *a, const uint8_t *b, size_t k, const uint8_t *lo,
+               const uint8_t *hi, uint32_t u) {
+  static uint32_t *d_zero = nullptr;  // a device word holding row index 0
+  if (!d_zero) {
+    CK(cudaMalloc(&d_zero, 4));
+    CK(cudaMemset(d_zero, 0, 4));
+  }
+  RowOpArgs p;
+  memset(&p, 0, sizeof p);
+  p.a = a;
+  p.b = b;
+  p.chunks_per_row = (uint32_t)(k / 16);
+  FastDiv fd = make_fastdiv(p.chunks_per_row);
+  p.div_mul = fd.mul;
+  p.div_shift = fd.shift;
+  p.total_chunks = p.chunks_per_row;
+  p.dst_rows = d_zero;
+  p.src_rows = d_zero;
+  p.u0 = u;
+  if (lo) {
+    p.use_explicit = 1;
+    make_lut(p.lut, lo, hi);
+    make_basis(p.basis, lo, hi);
+  }
+  launch_rowops(op, mode, p, g.stream);
+  return after_launch("row op");
+}
+
+// L1 entry: any pointers, any k.  u = 2 makes the kernels take the table path.
+int l1_op(int op, uint8_t *a, const uint8_t *b, size_t k, const uint8_t *lo, const uint8_t *hi, uint32_t u) {
+  if (ensure_init()) return -1;
+  if (k == 0) return 0;
+  std::lock_guard<std::mutex> lk(g.mu);
+  const bool has_b = (op == OP_AXPY || op == OP_ADD || op == OP_SWAP || op == OP_AXPY_B32);
+  const size_t b_bytes = (op == OP_AXPY_B32) ? ((k + 31) / 32) * 4 : k;
+  int mode = MUL_LUT;
+  if (lo && nibble_table_linear(lo) && nibble_table_linear(hi)) mode = MUL_LIN;
+  const bool a_dev = classify(a) == PK_DEVVIS, b_dev = !has_b || classify(b) == PK_DEVVIS;
+  uint8_t *da = a;
+  const uint8_t *db = b;
+  size_t ka = (k + 15) & ~(size_t)15, kb = (b_bytes + 15) & ~(size_t)15;
+  if (!a_dev || !b_dev) {  // stage plain host operands through device scratch
+    if (scratch_reserve(ka + kb + 64)) return -1;
+    if (!a_dev) {
+      da = (uint8_t *)g.scratch;
+      CK(cudaMemsetAsync(da + (ka - 16), 0, 16, g.stream));
+      CK(cudaMemcpyAsync(da, a, k, cudaMemcpyHostToDevice, g.stream));
+    }
+    if (has_b && !b_dev) {
+      uint8_t *t = (uint8_t *)g.scratch + ka;
+      CK(cudaMemsetAsync(t + (kb - 16), 0, 16, g.stream));
+      CK(cudaMemcpyAsync(t, b, b_bytes, cudaMemcpyHostToDevice, g.stream));
+      db = t;
+    }
+  }
+  const bool a_staged = !a_dev, b_staged = has_b && !b_dev;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(da) & 15) == 0) && (a_staged || (k & 15) == 0) &&
+                      (!has_b || (((reinterpret_cast<uintptr_t>(db) & (op == OP_AXPY_B32 ? 3 : 15)) == 0) &&
+                                  (b_staged || op == OP_AXPY_B32 || (k & 15) == 0)));
+  if (vec_ok) {
+    // staged buffers are padded to 16 bytes, so the vector kernel may run over ka
+    size_t kk = a_staged ? ka : k;
+    if (op == OP_AXPY_B32 && !b_staged && (k & 31)) {
+      // mask words beyond ceil(k/32) must not be read: fall through to bytes
+      Lut16x2 lt;
+      memset(&lt, 0, sizeof lt);
+      launch_rowop_bytes(op, da, db, k, lt, u, g.stream);
+      if (after_launch("row op (bytes)")) return -1;
+    } else if (single_vec(op, mode, da, db, kk, lo, hi, u)) {
+      return -1;
+    }
+  } else {
+    Lut16x2 lt;
+    memset(&lt, 0, sizeof lt);
+    if (lo) make_lut(lt, lo, hi);
+    launch_rowop_bytes(op, da, db, k, lt, u, g.stream);
+    if (after_launch("row op (bytes)")) return -1;
+  }
+  if (a_staged) CK(cudaMemcpyAsync(a, da, k, cudaMemcpyDeviceToHost, g.stream));
+  if (op == OP_SWAP && b_staged) CK(cudaMemcpyAsync(const_cast<uint8_t *>(b), db, k, cudaMemcpyDeviceToHost, g.stream));
+  if (a_staged || b_staged) CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+// matrix-level single row op on managed/device matrices: one launch, one row
+int mat_rowop(int field, int variant, int op, uint8_t *abits, size_t astride, const uint8_t *bbits,
+              size_t bstride, size_t row_bytes, unsigned i, unsigned j, uint8_t u) {
+  uint32_t di = i, dj = j;
+  return oblas_b200_rowops(field, variant, op, OBLAS_B200_MUL_AUTO, abits, astride, bbits, bstride,
+                           row_bytes, &di, &dj, &u, 1);
+}
+
+int batch_rowop(int field, int variant, int op, uint8_t *abits, size_t astride, const uint8_t *bbits,
+                size_t bstride, size_t row_bytes, const unsigned *i, const unsigned *j,
+                const uint8_t *u, size_t n) {
+  return oblas_b200_rowops(field, variant, op, OBLAS_B200_MUL_AUTO, abits, astride, bbits, bstride,
+                           row_bytes, (const uint32_t *)i, (const uint32_t *)j, u, n);
+}
+
+const unsigned kFieldBits[4] = {1, 2, 4, 8};
+
+// solve n systems given as separate allocations (struct API)
+int solve_ptrs(int field, uint8_t **abits, uint8_t **bbits, size_t a_rs, unsigned rows, unsigned cols,
+               size_t a_bytes, size_t b_rs, size_t b_bytes, unsigned *rank, unsigned *pivcols, size_t n) {
+  if (ensure_init()) return -1;
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(g.mu);
+  const size_t ptr_bytes = ((n * 8) + 255) & ~(size_t)255;
+  const size_t rank_bytes = ((n * 4) + 255) & ~(size_t)255;
+  const size_t piv_bytes = pivcols ? n * (size_t)rows * 4 : 0;
+  if (scratch_reserve(2 * ptr_bytes + rank_bytes + piv_bytes + 256)) return -1;
+  uint8_t *s = (uint8_t *)g.scratch;
+  unsigned long long *d_a = (unsigned long long *)s, *d_b = (unsigned long long *)(s + ptr_bytes);
+  int32_t *d_rank = (int32_t *)(s + 2 * ptr_bytes);
+  uint32_t *d_piv = pivcols ? (uint32_t *)(s + 2 * ptr_bytes + rank_bytes) : nullptr;
+  CK(cudaMemcpyAsync(d_a, abits, n * 8, cudaMemcpyHostToDevice, g.stream));
+  if (bbits) CK(cudaMemcpyAsync(d_b, bbits, n * 8, cudaMemcpyHostToDevice, g.stream));
+  if (d_piv) CK(cudaMemsetAsync(d_piv, 0xff, piv_bytes, g.stream));
+  SolveArgs p;
+  memset(&p, 0, sizeof p);
+  p.A = abits[0]; p.a_rs = a_rs; p.rows = rows; p.cols = cols; p.a_bytes = (uint32_t)a_bytes;
+  p.B = bbits ? bbits[0] : nullptr; p.b_rs = b_rs; p.b_bytes = bbits ? (uint32_t)b_bytes : 0;
+  p.rank = d_rank; p.pivcols = d_piv;
+  p.a_ptrs = d_a;
+  p.b_ptrs = bbits ? d_b : nullptr;
+  if (solve_common(field, p, n)) return -1;
+  CK(cudaMemcpyAsync(rank, d_rank, n * 4, cudaMemcpyDeviceToHost, g.stream));
+  if (pivcols) CK(cudaMemcpyAsync(pivcols, d_piv, piv_bytes, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- oblas.h ------------------------------------------------------------------
+// oblas.c:4-11
+uint32_t bfd_32(uint32_t word, uint8_t at, uint8_t len, uint8_t val) {
+  uint32_t mask = (uint32_t)((1 << len) - 1) << at;
+  return (word & ~mask) | ((uint32_t)val << at);
+}
+uint32_t bfx_32(uint32_t word, uint8_t at, uint8_t len) { return (word >> at) & (uint32_t)((1 << len) - 1); }
+
+// oblas.c:13-19: nmemb blocks of `size` rounded up to `align`; here CUDA managed
+void *oblas_alloc(size_t nmemb, size_t size, size_t align) {
+  size_t each = (size + align - 1) / align * align;
+  void *p = oblas_b200_managed_alloc(nmemb * each, align);
+  if (!p) {
+    fprintf(stderr, "liboblas_b200: oblas_alloc: %s\n", tl_err);
+    exit(ENOMEM);
+  }
+  return p;
+}
+
+void oblas_xor(uint8_t *a, uint8_t *b, size_t k) {
+  MUST(l1_op(OP_ADD, a, b, k, nullptr, nullptr, 1), "oblas_xor");
+  MUST(finish_dropin(), "oblas_xor");
+}
+void oblas_axpy(uint8_t *a, const uint8_t *b, size_t k, const uint8_t *u_lo, const uint8_t *u_hi) {
+  MUST(l1_op(OP_AXPY, a, b, k, u_lo, u_hi, 2), "oblas_axpy");
+  MUST(finish_dropin(), "oblas_axpy");
+}
+void oblas_scal(uint8_t *a, size_t k, const uint8_t *u_lo, const uint8_t *u_hi) {
+  MUST(l1_op(OP_SCAL, a, nullptr, k, u_lo, u_hi, 2), "oblas_scal");
+  MUST(finish_dropin(), "oblas_scal");
+}
+void oblas_swap(uint8_t *a, uint8_t *b, size_t k) {
+  MUST(l1_op(OP_SWAP, a, b, k, nullptr, nullptr, 1), "oblas_swap");
+  MUST(finish_dropin(), "oblas_swap");
+}
+void oblas_axpy_gf2_gf256_32(uint8_t *a, uint32_t *b, size_t k, uint8_t u) {
+  MUST(l1_op(OP_AXPY_B32, a, (const uint8_t *)b, k, nullptr, nullptr, u), "oblas_axpy_gf2_gf256_32");
+  MUST(finish_dropin(), "oblas_axpy_gf2_gf256_32");
+}
+
+// ---- octmat.h -------------------------------------------------------------------
+// octmat.c:7-15
+octmat *octmat_new_aligned(unsigned rows, unsigned cols, unsigned align) {
+  octmat *m = (octmat *)calloc(1, sizeof(octmat));
+  if (!m) exit(ENOMEM);
+  if (align < 16) align = 16;
+  m->rows = rows;
+  m->cols = cols;
+  m->stride = round_up_u(cols, align);
+  m->bits = (uint8_t *)oblas_alloc(rows, m->stride, align);
+  memset(m->bits, 0, (size_t)rows * m->stride);
+  return m;
+}
+octmat *octmat_new(unsigned rows, unsigned cols) { return octmat_new_aligned(rows, cols, 16); }
+// octmat.c:17-22
+void octmat_free(octmat *m) {
+  if (m && m->bits) oblas_b200_free(m->bits);
+  if (m) free(m);
+}
+void oswaprow(octmat *a, unsigned i, unsigned j) {
+  if (i == j) return;  // octmat.c:25-26
+  MUST(mat_rowop(OB2_GF256, 0, OP_SWAP, a->bits, a->stride, a->bits, a->stride, a->stride, i, j, 1), "oswaprow");
+  MUST(finish_dropin(), "oswaprow");
+}
+void oaxpy(octmat *a, octmat *b, unsigned i, unsigned j, uint8_t u) {
+  if (u == 0) return;  // octmat.c:36-37
+  MUST(mat_rowop(OB2_GF256, 0, OP_AXPY, a->bits, a->stride, b->bits, b->stride, a->stride, i, j, u), "oaxpy");
+  MUST(finish_dropin(), "oaxpy");
+}
+void oaddrow(octmat *a, octmat *b, unsigned i, unsigned j) {
+  MUST(mat_rowop(OB2_GF256, 0, OP_ADD, a->bits, a->stride, b->bits, b->stride, a->stride, i, j, 1), "oaddrow");
+  MUST(finish_dropin(), "oaddrow");
+}
+void oscal(octmat *a, unsigned i, uint8_t u) {
+  if (u < 2) return;  // octmat.c:57-58
+  MUST(mat_rowop(OB2_GF256, 0, OP_SCAL, a->bits, a->stride, nullptr, 0, a->stride, i, i, u), "oscal");
+  MUST(finish_dropin(), "oscal");
+}
+void oaxpy_b32(octmat *a, uint32_t *b, unsigned i, uint8_t u) {
+  // octmat.c:65-68: b is a caller-owned row of stride/32 mask words
+  MUST(l1_op(OP_AXPY_B32, a->bits + (size_t)i * a->stride, (const uint8_t *)b, a->stride, nullptr, nullptr, u), "oaxpy_b32");
+  MUST(finish_dropin(), "oaxpy_b32");
+}
+
+void oaxpy_batch(octmat *a, octmat *b, const unsigned *i, const unsigned *j, const uint8_t *u, size_t n) {
+  MUST(batch_rowop(OB2_GF256, 0, OP_AXPY, a->bits, a->stride, b->bits, b->stride, a->stride, i, j, u, n), "oaxpy_batch");
+  MUST(finish_dropin(), "oaxpy_batch");
+}
+void oaddrow_batch(octmat *a, octmat *b, const unsigned *i, const unsigned *j, size_t n) {
+  MUST(batch_rowop(OB2_GF256, 0, OP_ADD, a->bits, a->stride, b->bits, b->stride, a->stride, i, j, nullptr, n), "oaddrow_batch");
+  MUST(finish_dropin(), "oaddrow_batch");
+}
+void oscal_batch(octmat *a, const unsigned *i, const uint8_t *u, size_t n) {
+  MUST(batch_rowop(OB2_GF256, 0, OP_SCAL, a->bits, a->stride, nullptr, 0, a->stride, i, nullptr, u, n), "oscal_batch");
+  MUST(finish_dropin(), "oscal_batch");
+}
+void oswaprow_batch(octmat *a, const unsigned *i, const unsigned *j, size_t n) {
+  MUST(batch_rowop(OB2_GF256, 0, OP_SWAP, a->bits, a->stride, a->bits, a->stride, a->stride, i, j, nullptr, n), "oswaprow_batch");
+  MUST(finish_dropin(), "oswaprow_batch");
+}
+
+// ---- gfmat.h ---------------------------------------------------------------------
+// gfmat.c:48-60: stride in WORDS, ceil(cols/vpw) rounded up to `align` words,
+// align = sizeof(void*) for GF2_1 else OCTMAT_ALIGN
+gfmat *gfmat_new_aligned(gfmat_type field, unsigned rows, unsigned cols, unsigned align) {
+  gfmat *m = (gfmat *)calloc(1, sizeof(gfmat));
+  if (!m) exit(ENOMEM);
+  unsigned vpw = 32 / kFieldBits[field];
+  m->field = field;
+  m->rows = rows;
+  m->cols = cols;
+  m->align = (field == GF2_1) ? (unsigned)sizeof(void *) : (align < 16 ? 16 : align);
+  m->stride = round_up_u((cols + vpw - 1) / vpw, m->align);
+  m->bits = (oblas_word *)oblas_alloc(rows, (size_t)m->stride * sizeof(oblas_word), m->align);
+  memset(m->bits, 0, (size_t)rows * m->stride * sizeof(oblas_word));
+  return m;
+}
+gfmat *gfmat_new(gfmat_type field, unsigned rows, unsigned cols) { return gfmat_new_aligned(field, rows, cols, 16); }
+// gfmat.c:62-74.  The reference copies stride*cols words (line 72), which over- or
+// under-runs for non-square matrices; we copy the whole matrix (stride*rows).
+gfmat *gfmat_copy(gfmat *src) {
+  if (!src || !src->bits) return NULL;
+  MUST(oblas_b200_sync(), "gfmat_copy");
+  gfmat *m = (gfmat *)calloc(1, sizeof(gfmat));
+  if (!m) exit(ENOMEM);
+  *m = *src;
+  m->bits = (oblas_word *)oblas_alloc(m->rows, (size_t)m->stride * sizeof(oblas_word), m->align);
+  memcpy(m->bits, src->bits, sizeof(oblas_word) * (size_t)m->stride * m->rows);
+  return m;
+}
+void gfmat_free(gfmat *m) {
+  if (m && m->bits) oblas_b200_free(m->bits);
+  if (m) free(m);
+}
+// host-side element access on managed memory (gfmat.c:83-98)
+uint8_t gfmat_get(gfmat *m, unsigned i, unsigned j) {
+  if (i >= m->rows || j >= m->cols) return 0;
+  unsigned e = kFieldBits[m->field], vpw = 32 / e;
+  oblas_word *a = m->bits + (size_t)i * m->stride;
+  return (uint8_t)bfx_32(a[j / vpw], (uint8_t)((j % vpw) * e), (uint8_t)e);
+}
+void gfmat_set(gfmat *m, unsigned i, unsigned j, uint8_t b) {
+  if (i >= m->rows || j >= m->cols) return;
+  unsigned e = kFieldBits[m->field], vpw = 32 / e;
+  oblas_word *a = m->bits + (size_t)i * m->stride;
+  a[j / vpw] = bfd_32(a[j / vpw], (uint8_t)((j % vpw) * e), (uint8_t)e, (uint8_t)(b % (1u << e)));
+}
+// gfmat.c:100-116
+void gfmat_print(gfmat *m, FILE *stream) {
+  static const char *fn[] = {"gf2", "gf4", "gf16", "gf256"};
+  fprintf(stream, "%s [%ux%u]\n", fn[m->field], m->rows, m->cols);
+  fprintf(stream, "|     ");
+  for (unsigned j = 0; j < m->cols; j++) fprintf(stream, "| %03d ", j);
+  fprintf(stream, "|\n");
+  for (unsigned i = 0; i < m->rows; i++) {
+    fprintf(stream, "| %03d | %3d ", i, gfmat_get(m, i, 0));
+    for (unsigned j = 1; j < m->cols; j++) fprintf(stream, "| %3d ", gfmat_get(m, i, j));
+    fprintf(stream, "|\n");
+  }
+}
+void gfmat_add(gfmat *a, gfmat *b, unsigned i, unsigned j) {
+  MUST(mat_rowop(a->field, 0, OP_ADD, (uint8_t *)a->bits, (size_t)a->stride * 4, (uint8_t *)b->bits, (size_t)b->stride * 4, (size_t)a->stride * 4, i, j, 1), "gfmat_add");
+  MUST(finish_dropin(), "gfmat_add");
+}
+void gfmat_swaprow(gfmat *m, unsigned i, unsigned j) {
+  if (i == j) return;
+  MUST(mat_rowop(m->field, 0, OP_SWAP, (uint8_t *)m->bits, (size_t)m->stride * 4, (uint8_t *)m->bits, (size_t)m->stride * 4, (size_t)m->stride * 4, i, j, 1), "gfmat_swaprow");
+  MUST(finish_dropin(), "gfmat_swaprow");
+}
+void gfmat_axpy(gfmat *a, gfmat *b, unsigned i, unsigned j, uint8_t u) {
+  if (u == 0) return;
+  // GF2_1 has no tables (gfmat.c:14-19): only u==1 is defined; we treat u>1 as XOR-free no-op
+  if (a->field == GF2_1 && u > 1) return;
+  MUST(mat_rowop(a->field, 0, OP_AXPY, (uint8_t *)a->bits, (size_t)a->stride * 4, (uint8_t *)b->bits, (size_t)b->stride * 4, (size_t)a->stride * 4, i, j, u), "gfmat_axpy");
+  MUST(finish_dropin(), "gfmat_axpy");
+}
+void gfmat_scal(gfmat *a, unsigned i, uint8_t u) {
+  if (u < 2 || a->field == GF2_1) return;
+  MUST(mat_rowop(a->field, 0, OP_SCAL, (uint8_t *)a->bits, (size_t)a->stride * 4, nullptr, 0, (size_t)a->stride * 4, i, i, u), "gfmat_scal");
+  MUST(finish_dropin(), "gfmat_scal");
+}
+void gfmat_zero(gfmat *a, unsigned i) {
+  MUST(mat_rowop(a->field, 0, OP_ZERO, (uint8_t *)a->bits, (size_t)a->stride * 4, nullptr, 0, (size_t)a->stride * 4, i, i, 0), "gfmat_zero");
+  MUST(finish_dropin(), "gfmat_zero");
+}
+// gfmat.c:163-175, truncation into uint8_t kept
+void gfmat_fill(gfmat *m, unsigned i, uint8_t *dst) {
+  unsigned e = kFieldBits[m->field], vpw = 32 / e;
+  oblas_word *a = m->bits + (size_t)i * m->stride;
+  for (unsigned idx = 0; idx < m->stride; idx++)
+    for (unsigned tz = 0; tz < 32; tz++)
+      if ((a[idx] >> tz) & 1u) dst[tz / e + idx * vpw] |= (uint8_t)(1u << (tz % vpw));
+}
+static unsigned elem_flags_host(uint32_t w, unsigned e) {
+  unsigned z = 0;
+  for (unsigned bit = 0; bit < 32; bit++)
+    if ((w >> bit) & 1u) z |= 1u << (bit / e);
+  return z;
+}
+static unsigned nnz_compat(const oblas_word *a, unsigned e, unsigned s, unsigned en) {
+  // gfmat.c:183-212 / binmat.c:87-116 bug-for-bug: after a partial first word the
+  // element index s is bumped and reused as the word index of the middle loop
+  unsigned vpw = 32 / e, n = 0;
+  unsigned sq = s / vpw, eq = en / vpw, sr = s % vpw, er = en % vpw;
+  uint32_t m_first = ~((1u << sr) - 1u), m_last = (1u << er) - 1u;
+  if (sr) {
+    n += (unsigned)__builtin_popcount(elem_flags_host(a[sq], e) & m_first);
+    s++;
+  }
+  for (unsigned w = s; w < eq; w++) n += (unsigned)__builtin_popcount(elem_flags_host(a[w], e));
+  if (en > eq && m_last) n += (unsigned)__builtin_popcount(elem_flags_host(a[eq], e) & m_last);
+  return n;
+}
+unsigned gfmat_nnz(gfmat *m, unsigned i, unsigned s, unsigned e) {
+  if (i >= m->rows || s > e || e > (m->cols + 1)) return 0;
+  return nnz_compat(m->bits + (size_t)i * m->stride, kFieldBits[m->field], s, e);
+}
+// gfmat.c:215-231
+void gfmat_swapcol(gfmat *m, unsigned i, unsigned j) {
+  if (i == j) return;
+  unsigned e = kFieldBits[m->field], vpw = 32 / e;
+  for (unsigned r = 0; r < m->rows; r++) {
+    oblas_word *row = m->bits + (size_t)r * m->stride;
+    uint8_t vi = (uint8_t)bfx_32(row[i / vpw], (uint8_t)((i % vpw) * e), (uint8_t)e);
+    uint8_t vj = (uint8_t)bfx_32(row[j / vpw], (uint8_t)((j % vpw) * e), (uint8_t)e);
+    row[i / vpw] = bfd_32(row[i / vpw], (uint8_t)((i % vpw) * e), (uint8_t)e, vj);
+    row[j / vpw] = bfd_32(row[j / vpw], (uint8_t)((j % vpw) * e), (uint8_t)e, vi);
+  }
+}
+void gfmat_axpy_batch(gfmat *a, gfmat *b, const unsigned *i, const unsigned *j, const uint8_t *u, size_t n) {
+  MUST(batch_rowop(a->field, 0, OP_AXPY, (uint8_t *)a->bits, (size_t)a->stride * 4, (uint8_t *)b->bits, (size_t)b->stride * 4, (size_t)a->stride * 4, i, j, u, n), "gfmat_axpy_batch");
+  MUST(finish_dropin(), "gfmat_axpy_batch");
+}
+void gfmat_add_batch(gfmat *a, gfmat *b, const unsigned *i, const unsigned *j, size_t n) {
+  MUST(batch_rowop(a->field, 0, OP_ADD, (uint8_t *)a->bits, (size_t)a->stride * 4, (uint8_t *)b->bits, (size_t)b->stride * 4, (size_t)a->stride * 4, i, j, nullptr, n), "gfmat_add_batch");
+  MUST(finish_dropin(), "gfmat_add_batch");
+}
+void gfmat_scal_batch(gfmat *a, const unsigned *i, const uint8_t *u, size_t n) {
+  if (a->field == GF2_1) return;
+  MUST(batch_rowop(a->field, 0, OP_SCAL, (uint8_t *)a->bits, (size_t)a->stride * 4, nullptr, 0, (size_t)a->stride * 4, i, nullptr, u, n), "gfmat_scal_batch");
+  MUST(finish_dropin(), "gfmat_scal_batch");
+}
+void gfmat_swaprow_batch(gfmat *m, const unsigned *i, const unsigned *j, size_t n) {
+  MUST(batch_rowop(m->field, 0, OP_SWAP, (uint8_t *)m->bits, (size_t)m->stride * 4, (uint8_t *)m->bits, (size_t)m->stride * 4, (size_t)m->stride * 4, i, j, nullptr, n), "gfmat_swaprow_batch");
+  MUST(finish_dropin(), "gfmat_swaprow_batch");
+}
+
+// ---- binmat.h ---------------------------------------------------------------------
+// binmat.c:8-17
+binmat *binmat_new(unsigned rows, unsigned cols) {
+  binmat *m = (binmat *)calloc(1, sizeof(binmat));
+  if (!m) exit(ENOMEM);
+  m->rows = rows;
+  m->cols = cols;
+  m->stride = round_up_u((cols + 31) / 32, (unsigned)sizeof(void *));
+  m->bits = (oblas_word *)oblas_alloc(rows, (size_t)m->stride * sizeof(oblas_word), sizeof(void *));
+  memset(m->bits, 0, (size_t)rows * m->stride * sizeof(oblas_word));
+  return m;
+}
+void binmat_free(binmat *m) {
+  if (m && m->bits) oblas_b200_free(m->bits);
+  if (m) free(m);
+}
+uint8_t binmat_get(binmat *m, unsigned i, unsigned j) {
+  if (i >= m->rows || j >= m->cols) return 0;
+  return (uint8_t)((m->bits[(size_t)i * m->stride + j / 32] >> (j % 32)) & 1u);
+}
+// binmat.c:35-42: the bit is always set, `b` is ignored (line 41) -- kept
+void binmat_set(binmat *m, unsigned i, unsigned j, uint8_t b) {
+  (void)b;
+  if (i >= m->rows || j >= m->cols) return;
+  m->bits[(size_t)i * m->stride + j / 32] |= 1u << (j % 32);
+}
+void binmat_add(binmat *a, binmat *b, unsigned i, unsigned j) {
+  MUST(mat_rowop(OB2_GF2, 0, OP_ADD, (uint8_t *)a->bits, (size_t)a->stride * 4, (uint8_t *)b->bits, (size_t)b->stride * 4, (size_t)a->stride * 4, i, j, 1), "binmat_add");
+  MUST(finish_dropin(), "binmat_add");
+}
+void binmat_swaprow(binmat *m, unsigned i, unsigned j) {
+  if (i == j) return;
+  MUST(mat_rowop(OB2_GF2, 0, OP_SWAP, (uint8_t *)m->bits, (size_t)m->stride * 4, (uint8_t *)m->bits, (size_t)m->stride * 4, (size_t)m->stride * 4, i, j, 1), "binmat_swaprow");
+  MUST(finish_dropin(), "binmat_swaprow");
+}
+void binmat_zero(binmat *a, unsigned i) {
+  MUST(mat_rowop(OB2_GF2, 0, OP_ZERO, (uint8_t *)a->bits, (size_t)a->stride * 4, nullptr, 0, (size_t)a->stride * 4, i, i, 0), "binmat_zero");
+  MUST(finish_dropin(), "binmat_zero");
+}
+// binmat.c:64-75
+void binmat_fill(binmat *m, unsigned i, uint8_t *dst) {
+  oblas_word *a = m->bits + (size_t)i * m->stride;
+  for (unsigned idx = 0; idx < m->stride; idx++)
+    for (unsigned tz = 0; tz < 32; tz++)
+      if ((a[idx] >> tz) & 1u) dst[tz + idx * 32] |= (uint8_t)(1u << tz);
+}
+// binmat.c:77-80
+void binmat_expand(binmat *m, uint32_t *src, unsigned i, uint8_t u) {
+  MUST(l1_op(OP_AXPY_B32, (uint8_t *)(m->bits + (size_t)i * m->stride), (const uint8_t *)src, (size_t)m->stride * 4, nullptr, nullptr, u), "binmat_expand");
+  MUST(finish_dropin(), "binmat_expand");
+}
+unsigned binmat_nnz(binmat *m, unsigned i, unsigned s, unsigned e) {
+  if (i >= m->rows || s > e || e > (m->cols + 1)) return 0;
+  return nnz_compat(m->bits + (size_t)i * m->stride, 1, s, e);
+}
+void binmat_add_batch(binmat *a, binmat *b, const unsigned *i, const unsigned *j, size_t n) {
+  MUST(batch_rowop(OB2_GF2, 0, OP_ADD, (uint8_t *)a->bits, (size_t)a->stride * 4, (uint8_t *)b->bits, (size_t)b->stride * 4, (size_t)a->stride * 4, i, j, nullptr, n), "binmat_add_batch");
+  MUST(finish_dropin(), "binmat_add_batch");
+}
+void binmat_swaprow_batch(binmat *m, const unsigned *i, const unsigned *j, size_t n) {
+  MUST(batch_rowop(OB2_GF2, 0, OP_SWAP, (uint8_t *)m->bits, (size_t)m->stride * 4, (uint8_t *)m->bits, (size_t)m->stride * 4, (size_t)m->stride * 4, i, j, nullptr, n), "binmat_swaprow_batch");
+  MUST(finish_dropin(), "binmat_swaprow_batch");
+}
+
+// ---- caller-side loops as single calls ------------------------------------------------
+void octmat_solve_batch(octmat **A, octmat **B, unsigned *rank, size_t n) {
+  if (n == 0) return;
+  std::vector<uint8_t *> ab(n), bb(n);
+  for (size_t k = 0; k < n; k++) {
+    ab[k] = A[k]->bits;
+    if (B) bb[k] = B[k]->bits;
+  }
+  MUST(solve_ptrs(OB2_GF256, ab.data(), B ? bb.data() : nullptr, A[0]->stride, A[0]->rows, A[0]->cols,
+                  A[0]->stride, B ? B[0]->stride : 0, B ? B[0]->stride : 0, rank, nullptr, n), "octmat_solve_batch");
+}
+unsigned octmat_solve(octmat *A, octmat *B, unsigned *pivcols) {
+  unsigned rank = 0;
+  uint8_t *ab = A->bits, *bb = B ? B->bits : nullptr;
+  MUST(solve_ptrs(OB2_GF256, &ab, B ? &bb : nullptr, A->stride, A->rows, A->cols, A->stride,
+                  B ? B->stride : 0, B ? B->stride : 0, &rank, pivcols, 1), "octmat_solve");
+  return rank;
+}
+void gfmat_solve_batch(gfmat **A, gfmat **B, unsigned *rank, size_t n) {
+  if (n == 0) return;
+  std::vector<uint8_t *> ab(n), bb(n);
+  for (size_t k = 0; k < n; k++) {
+    ab[k] = (uint8_t *)A[k]->bits;
+    if (B) bb[k] = (uint8_t *)B[k]->bits;
+  }
+  MUST(solve_ptrs(A[0]->field, ab.data(), B ? bb.data() : nullptr, (size_t)A[0]->stride * 4, A[0]->rows, A[0]->cols,
+                  (size_t)A[0]->stride * 4, B ? (size_t)B[0]->stride * 4 : 0, B ? (size_t)B[0]->stride * 4 : 0, rank, nullptr, n), "gfmat_solve_batch");
+}
+unsigned gfmat_solve(gfmat *A, gfmat *B, unsigned *pivcols) {
+  unsigned rank = 0;
+  uint8_t *ab = (uint8_t *)A->bits, *bb = B ? (uint8_t *)B->bits : nullptr;
+  MUST(solve_ptrs(A->field, &ab, B ? &bb : nullptr, (size_t)A->stride * 4, A->rows, A->cols, (size_t)A->stride * 4,
+                  B ? (size_t)B->stride * 4 : 0, B ? (size_t)B->stride * 4 : 0, &rank, pivcols, 1), "gfmat_solve");
+  return rank;
+}
+void binmat_rref_batch(binmat **A, binmat **B, unsigned *rank, size_t n) {
+  if (n == 0) return;
+  std::vector<uint8_t *> ab(n), bb(n);
+  for (size_t k = 0; k < n; k++) {
+    ab[k] = (uint8_t *)A[k]->bits;
+    if (B) bb[k] = (uint8_t *)B[k]->bits;
+  }
+  MUST(solve_ptrs(OB2_GF2, ab.data(), B ? bb.data() : nullptr, (size_t)A[0]->stride * 4, A[0]->rows, A[0]->cols,
+                  (size_t)A[0]->stride * 4, B ? (size_t)B[0]->stride * 4 : 0, B ? (size_t)B[0]->stride * 4 : 0, rank, nullptr, n), "binmat_rref_batch");
+}
+unsigned binmat_rref(binmat *A, binmat *B, unsigned *pivcols) {
+  unsigned rank = 0;
+  uint8_t *ab = (uint8_t *)A->bits, *bb = B ? (uint8_t *)B->bits : nullptr;
+  MUST(solve_ptrs(OB2_GF2, &ab, B ? &bb : nullptr, (size_t)A->stride * 4, A->rows, A->cols, (size_t)A->stride * 4,
+                  B ? (size_t)B->stride * 4 : 0, B ? (size_t)B->stride * 4 : 0, &rank, pivcols, 1), "binmat_rref");
+  return rank;
+}
+void octmat_apply(octmat *C, octmat *D, octmat *Y) {
+  unsigned nbytes = D->stride < Y->stride ? D->stride : Y->stride;
+  MUST(oblas_b200_gf256_apply(C->bits, C->stride, C->rows, C->cols, D->bits, D->stride, Y->bits, Y->stride, nbytes, 0), "octmat_apply");
+  MUST(oblas_b200_sync(), "octmat_apply");
+}
+
+}  // extern "C"

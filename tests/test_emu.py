@@ -1,0 +1,175 @@
+"""Kernel LOGIC of the product's CUDA sources, executed on host threads
+(tests/emu): row ops, blocked elimination, apply -- bit-exact against the oracle.
+This is not the product path (the GPU tests are); it lets the GPU-less build
+container catch indexing / pivoting / table-build mistakes."""
+import numpy as np
+import pytest
+
+from helpers import (GF2, GF4, GF16, GF256, FIELD_BITS, MUL_LIN, MUL_LUT, OP_ADD, OP_AXPY, OP_AXPY_B32,
+                     OP_SCAL, OP_SWAP, OP_ZERO, TS_GF4_FIXED, TS_GF4_SHIPPED, TS_GF16, TS_GF256, emu,
+                     i32p, oracle, oracle_solve, ptr, random_matrix, splitmix_bytes, u32p)
+
+SMEM = 227 * 1024
+
+
+def test_fastdiv_exact():
+    e = emu()
+    for d in (1, 2, 3, 5, 16, 80, 81, 640, 1000, 4096, 65536, 12345, 0x7FFFFFF):
+        assert e.emu_fastdiv_check(d, 2_000_000, 7) == 1, d
+
+
+def test_table_linearity_flags():
+    e = emu()
+    assert [e.emu_table_linear(t) for t in range(4)] == [0, 1, 1, 1]
+
+
+@pytest.mark.parametrize("field,ts,variant", [(GF256, TS_GF256, 0), (GF16, TS_GF16, 0),
+                                              (GF4, TS_GF4_FIXED, 1), (GF4, TS_GF4_SHIPPED, 0)])
+@pytest.mark.parametrize("mode", [MUL_LIN, MUL_LUT])
+def test_rowops(field, ts, variant, mode):
+    if ts == TS_GF4_SHIPPED and mode == MUL_LIN:
+        pytest.skip("shipped GF(4) HI table is not linear")
+    o, e = oracle(), emu()
+    rng = np.random.default_rng(field * 10 + mode)
+    rows = 12
+    for op in (OP_AXPY, OP_ADD, OP_SCAL, OP_ZERO):
+        for stride in (16, 48, 1280):
+            nops = 9
+            A = splitmix_bytes(10 + op, rows * stride).reshape(rows, stride).copy()
+            Bm = splitmix_bytes(20 + op, rows * stride).reshape(rows, stride).copy()
+            dst = rng.permutation(rows)[:nops].astype(np.uint32)
+            src = rng.integers(0, rows, nops).astype(np.uint32)
+            u = rng.integers(0, 1 << FIELD_BITS[field], nops).astype(np.uint8)
+            u[0], u[1] = 0, 1
+            A0, A1 = A.copy(), A.copy()
+            for k in range(nops):
+                if op == OP_AXPY:
+                    o.orc_row_axpy(field, variant, ptr(A0), stride, ptr(Bm), stride, dst[k], src[k], u[k])
+                elif op == OP_ADD:
+                    o.orc_row_add(ptr(A0), stride, ptr(Bm), stride, dst[k], src[k])
+                elif op == OP_SCAL:
+                    o.orc_row_scal(field, variant, ptr(A0), stride, dst[k], u[k])
+                else:
+                    o.orc_row_zero(ptr(A0), stride, dst[k])
+            e.emu_rowops(op, mode, ts, ptr(A1), stride, ptr(Bm), stride, stride, ptr(dst, u32p),
+                         ptr(src, u32p), ptr(u), 0, nops)
+            assert np.array_equal(A0, A1), (op, stride)
+
+
+@pytest.mark.parametrize("mode", [MUL_LIN, MUL_LUT])
+def test_axpy_every_scalar_every_byte(mode):
+    o, e = oracle(), emu()
+    stride = rows = 256
+    A = splitmix_bytes(5, rows * stride).reshape(rows, stride).copy()
+    Bm = np.tile(np.arange(256, dtype=np.uint8), (rows, 1))
+    idx = np.arange(rows, dtype=np.uint32)
+    u = np.arange(256, dtype=np.uint8)
+    A0, A1 = A.copy(), A.copy()
+    for k in range(rows):
+        o.orc_row_axpy(GF256, 0, ptr(A0), stride, ptr(Bm), stride, k, k, k)
+    e.emu_rowops(OP_AXPY, mode, TS_GF256, ptr(A1), stride, ptr(Bm), stride, stride, ptr(idx, u32p),
+                 ptr(idx, u32p), ptr(u), 0, rows)
+    assert np.array_equal(A0, A1)
+
+
+def test_swap_and_b32():
+    o, e = oracle(), emu()
+    A = splitmix_bytes(7, 10 * 64).reshape(10, 64).copy()
+    A0, A1 = A.copy(), A.copy()
+    i = np.array([0, 2, 5, 7], dtype=np.uint32)
+    j = np.array([1, 2, 9, 3], dtype=np.uint32)
+    for k in range(4):
+        o.orc_row_swap(ptr(A0), 64, i[k], j[k])
+    e.emu_rowops(OP_SWAP, 0, -1, ptr(A1), 64, ptr(A1), 64, 64, ptr(i, u32p), ptr(j, u32p), None, 0, 4)
+    assert np.array_equal(A0, A1)
+    A = splitmix_bytes(8, 6 * 96).reshape(6, 96).copy()
+    A0, A1 = A.copy(), A.copy()
+    masks = splitmix_bytes(9, 6 * 12).view(np.uint32).reshape(6, 3).copy()
+    i = np.array([0, 3, 4], dtype=np.uint32)
+    j = np.array([5, 1, 1], dtype=np.uint32)
+    u = np.array([0x53, 1, 0xFF], dtype=np.uint8)
+    for k in range(3):
+        o.orc_row_axpy_b32(ptr(A0), 96, ptr(masks[j[k]], u32p), i[k], u[k])
+    e.emu_rowops(OP_AXPY_B32, 0, -1, ptr(A1), 96, ptr(masks.view(np.uint8)), 12, 96, ptr(i, u32p),
+                 ptr(j, u32p), ptr(u), 0, 3)
+    assert np.array_equal(A0, A1)
+
+
+def _solve(field, rows, cols, b_bytes, seed, nsys=1, deficient=0, threads=64, grid=1, nbw=0):
+    e = emu()
+    A = np.stack([random_matrix(field, rows, cols, seed + 2 * s, rank_deficient=deficient) for s in range(nsys)])
+    B = np.stack([splitmix_bytes(seed + 2 * s + 1, rows * b_bytes).reshape(rows, b_bytes)
+                  for s in range(nsys)]).copy() if b_bytes else None
+    A0, B0 = A.copy(), (B.copy() if B is not None else None)
+    want = [oracle_solve(field, A0[s], B0[s] if B0 is not None else None, cols) for s in range(nsys)]
+    rank = np.zeros(nsys, dtype=np.int32)
+    piv = np.full((nsys, rows), 0xFFFFFFFF, dtype=np.uint32)
+    rc = e.emu_solve(field, ptr(A), A.strides[1], A.strides[0], rows, cols, A.shape[2],
+                     ptr(B) if B is not None else None, B.strides[1] if B is not None else 0,
+                     B.strides[0] if B is not None else 0, B.shape[2] if B is not None else 0,
+                     ptr(rank, i32p), ptr(piv, u32p), nsys, grid, threads, SMEM, nbw)
+    assert rc == 0
+    assert [int(r) for r in rank] == [w[0] for w in want]
+    for s in range(nsys):
+        assert np.array_equal(piv[s][:want[s][0]], want[s][1][:want[s][0]])
+    assert np.array_equal(A, A0)
+    if B is not None:
+        assert np.array_equal(B, B0)
+    return [w[0] for w in want]
+
+
+@pytest.mark.parametrize("args", [
+    dict(field=GF256, rows=20, cols=20, b_bytes=48, seed=100),
+    dict(field=GF256, rows=40, cols=40, b_bytes=272, seed=101),
+    dict(field=GF256, rows=40, cols=40, b_bytes=0, seed=102),
+    dict(field=GF256, rows=40, cols=40, b_bytes=64, seed=103, deficient=1),
+    dict(field=GF256, rows=40, cols=40, b_bytes=64, seed=104, deficient=2),
+    dict(field=GF256, rows=33, cols=50, b_bytes=32, seed=105),
+    dict(field=GF256, rows=50, cols=33, b_bytes=32, seed=106),
+    dict(field=GF256, rows=40, cols=40, b_bytes=64, seed=107, nsys=3, grid=2),
+    dict(field=GF256, rows=40, cols=40, b_bytes=64, seed=108, nbw=2),
+    dict(field=GF256, rows=150, cols=150, b_bytes=528, seed=110, threads=128),
+    dict(field=GF16, rows=70, cols=70, b_bytes=48, seed=111),
+    dict(field=GF16, rows=70, cols=70, b_bytes=48, seed=112, deficient=2),
+    dict(field=GF4, rows=70, cols=70, b_bytes=32, seed=114),
+    dict(field=GF4, rows=150, cols=150, b_bytes=16, seed=115, deficient=1),
+    dict(field=GF4, rows=150, cols=150, b_bytes=16, seed=116, nbw=2),
+    dict(field=GF2, rows=70, cols=70, b_bytes=32, seed=117),
+    dict(field=GF2, rows=200, cols=200, b_bytes=32, seed=118, threads=128),
+    dict(field=GF2, rows=200, cols=200, b_bytes=0, seed=119, nbw=2, threads=128),
+    dict(field=GF2, rows=100, cols=300, b_bytes=16, seed=120),
+    dict(field=GF2, rows=300, cols=100, b_bytes=16, seed=121),
+    dict(field=GF256, rows=1, cols=1, b_bytes=16, seed=122),
+    dict(field=GF256, rows=5, cols=700, b_bytes=16, seed=123),
+])
+def test_solve(args):
+    _solve(**args)
+
+
+def test_solve_zero_and_identity():
+    e = emu()
+    for field in (GF256, GF2):
+        rows = cols = 40
+        A = random_matrix(field, rows, cols, 1) * 0
+        rank = np.zeros(1, dtype=np.int32)
+        rc = e.emu_solve(field, ptr(A), A.strides[0], A.nbytes, rows, cols, A.shape[1], None, 0, 0, 0,
+                         ptr(rank, i32p), None, 1, 1, 64, SMEM, 0)
+        assert rc == 0 and rank[0] == 0 and not A.any()
+
+
+def test_apply():
+    o, e = oracle(), emu()
+    for (M, Kc, nbytes, seed, threads, acc) in [(10, 10, 32, 1, 64, 0), (40, 37, 272, 2, 64, 0),
+                                               (70, 100, 512, 3, 128, 0), (5, 3, 16, 5, 64, 0),
+                                               (40, 37, 272, 6, 64, 1), (100, 50, 48, 7, 32, 0)]:
+        cs = (Kc + 15) // 16 * 16 if seed != 5 else 7
+        Cm = np.zeros((M, cs), dtype=np.uint8)
+        Cm[:, :Kc] = splitmix_bytes(seed, M * Kc).reshape(M, Kc)
+        D = splitmix_bytes(seed + 1, Kc * nbytes).reshape(Kc, nbytes).copy()
+        Y0 = splitmix_bytes(seed + 2, M * nbytes).reshape(M, nbytes).copy()
+        Y1, prev = Y0.copy(), Y0.copy()
+        o.orc_gf256_apply(ptr(Cm), cs, M, Kc, ptr(D), nbytes, ptr(Y0), nbytes, nbytes)
+        if acc:
+            Y0 ^= prev
+        assert e.emu_apply(ptr(Cm), cs, M, Kc, ptr(D), nbytes, ptr(Y1), nbytes, nbytes, acc, threads) == 0
+        assert np.array_equal(Y0, Y1)

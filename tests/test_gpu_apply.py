@@ -1,0 +1,73 @@
+"""Dense GF(256) apply Y = C*D and the row-degree kernel on the GPU."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_helpers import dev, gf256_vecmat, host
+from helpers import GF2, GF4, GF16, GF256, FIELD_BITS, oracle, ptr, splitmix_bytes
+from oblas_b200 import capi, device
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _bind(cuda_lib):
+    device.bind(0)
+
+
+@pytest.mark.parametrize("M,Kc,nbytes,cs", [(10, 10, 32, 16), (40, 37, 272, 48), (300, 100, 512, 112),
+                                            (33, 16, 256, 16), (5, 3, 16, 7), (257, 260, 1296, 260)])
+def test_apply_vs_oracle(M, Kc, nbytes, cs):
+    o = oracle()
+    Cm = np.zeros((M, cs), dtype=np.uint8)
+    Cm[:, :Kc] = splitmix_bytes(1, M * Kc).reshape(M, Kc)
+    D = splitmix_bytes(2, Kc * nbytes).reshape(Kc, nbytes).copy()
+    Y0 = np.zeros((M, nbytes), dtype=np.uint8)
+    o.orc_gf256_apply(ptr(Cm), cs, M, Kc, ptr(D), nbytes, ptr(Y0), nbytes, nbytes)
+    Y = device.apply(dev(Cm)[:, :], dev(D))
+    assert np.array_equal(host(Y), Y0)
+    Y2 = device.apply(dev(Cm), dev(D), Y=Y.clone(), accumulate=True)
+    assert not host(Y2).any()  # Y ^ Y == 0
+
+
+def test_apply_medium_linearity_and_spot_rows():
+    M = Kc = 1500
+    N = 4096
+    Cm = torch.empty((M, Kc), dtype=torch.uint8, device="cuda")
+    D1 = torch.empty((Kc, N), dtype=torch.uint8, device="cuda")
+    D2 = torch.empty((Kc, N), dtype=torch.uint8, device="cuda")
+    Cp = torch.zeros((M, 1504), dtype=torch.uint8, device="cuda")
+    tmp = torch.empty(M * 1504, dtype=torch.uint8, device="cuda")
+    device.fill_random(tmp, 11)
+    Cp[:, :Kc] = tmp.reshape(M, 1504)[:, :Kc]
+    device.fill_random(D1, 12)
+    device.fill_random(D2, 13)
+    Y1, Y2, Y12 = device.apply(Cp, D1), device.apply(Cp, D2), device.apply(Cp, D1 ^ D2)
+    assert torch.equal(Y1 ^ Y2, Y12)
+    Ch, Dh, Yh = host(Cp), host(D1), host(Y1)
+    rng = np.random.default_rng(0)
+    for r in rng.choice(M, 5, replace=False):
+        assert np.array_equal(gf256_vecmat(Ch[r][:Kc], Dh), Yh[r])
+
+
+@pytest.mark.parametrize("field", [GF2, GF4, GF16, GF256])
+def test_nnz_batch(field, cuda_lib):
+    import ctypes as C
+    bits = FIELD_BITS[field]
+    rows, cols = 50, 1000
+    st = ((cols * bits + 31) // 32 * 4 + 15) // 16 * 16
+    M = np.zeros((rows, st), dtype=np.uint8)
+    used = (cols * bits + 7) // 8
+    M[:, :used] = splitmix_bytes(20 + field, rows * used).reshape(rows, used)
+    M[::3] &= 0x11  # sparser rows
+    # element values on the CPU
+    w = np.unpackbits(M, axis=1, bitorder="little")[:, :cols * bits].reshape(rows, cols, bits)
+    nz = w.any(axis=2)
+    idx = np.arange(rows, dtype=np.int32)
+    for (s, e) in ((0, cols), (3, 20), (40, 100), (33, 999), (0, 0), (500, 5000)):
+        out = torch.zeros(rows, dtype=torch.int32, device="cuda")
+        dM, di = dev(M), dev(idx)
+        capi.check(cuda_lib.oblas_b200_nnz_batch(field, C.c_void_p(dM.data_ptr()), st, cols, C.c_void_p(di.data_ptr()),
+                                                 rows, s, e, C.c_void_p(out.data_ptr())))
+        want = nz[:, s:min(e, cols)].sum(axis=1)
+        assert np.array_equal(host(out), want.astype(np.int32)), (field, s, e)

@@ -1,0 +1,158 @@
+"""Device-resident batched row operations (oblas_b200_rowops) against the oracle:
+every op x field x multiply back-end x stride, every scalar, large batches."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_helpers import dev, host
+from helpers import (GF2, GF4, GF16, GF256, FIELD_BITS, MUL_LIN, MUL_LUT, OP_ADD, OP_AXPY, OP_AXPY_B32,
+                     OP_SCAL, OP_SWAP, OP_ZERO, oracle, ptr, splitmix_bytes, u32p)
+from oblas_b200 import capi, device
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _bind(cuda_lib):
+    device.bind(0)
+
+
+def _oracle_apply(field, variant, op, A0, Bm, dst, src, u):
+    o = oracle()
+    st, sb = A0.strides[0], Bm.strides[0]
+    for k in range(len(dst)):
+        if op == OP_AXPY:
+            o.orc_row_axpy(field, variant, ptr(A0), st, ptr(Bm), sb, dst[k], src[k], u[k])
+        elif op == OP_ADD:
+            o.orc_row_add(ptr(A0), st, ptr(Bm), sb, dst[k], src[k])
+        elif op == OP_SCAL:
+            o.orc_row_scal(field, variant, ptr(A0), st, dst[k], u[k])
+        elif op == OP_ZERO:
+            o.orc_row_zero(ptr(A0), st, dst[k])
+
+
+@pytest.mark.parametrize("field,variant", [(GF256, 0), (GF16, 0), (GF4, 0), (GF4, 1)])
+@pytest.mark.parametrize("mul", [capi.MUL_AUTO, capi.MUL_LIN, capi.MUL_LUT])
+@pytest.mark.parametrize("stride", [16, 48, 1280, 1296, 10000])
+def test_rowops_vs_oracle(field, variant, mul, stride):
+    if field == GF4 and variant == 0 and mul == capi.MUL_LIN:
+        pytest.skip("shipped GF(4) table is not GF(2)-linear; the library rejects MUL_LIN (checked below)")
+    rng = np.random.default_rng(stride + field)
+    rows, nops = 40, 31
+    for op in (OP_AXPY, OP_ADD, OP_SCAL, OP_ZERO):
+        A = splitmix_bytes(100 + op, rows * stride).reshape(rows, stride).copy()
+        Bm = splitmix_bytes(200 + op, rows * stride).reshape(rows, stride).copy()
+        dst = rng.permutation(rows)[:nops].astype(np.int32)
+        src = rng.integers(0, rows, nops).astype(np.int32)
+        u = rng.integers(0, 1 << FIELD_BITS[field], nops).astype(np.uint8)
+        u[0], u[1] = 0, 1
+        A0 = A.copy()
+        _oracle_apply(field, variant, op, A0, Bm, dst, src, u)
+        dA, dB = dev(A), dev(Bm)
+        device.rowops(field, op, dA, dB, dev(dst), dev(src), dev(u), variant=variant, mul=mul)
+        assert np.array_equal(host(dA), A0), (op, stride)
+
+
+def test_lin_mode_rejected_for_nonlinear_table(cuda_lib):
+    a = torch.zeros((2, 64), dtype=torch.uint8, device="cuda")
+    idx = torch.zeros(1, dtype=torch.int32, device="cuda")
+    u = torch.full((1,), 2, dtype=torch.uint8, device="cuda")
+    with pytest.raises(capi.OblasB200Error):
+        device.rowops(GF4, OP_AXPY, a, a, idx, idx, u, variant=0, mul=capi.MUL_LIN)
+
+
+@pytest.mark.parametrize("mul", [capi.MUL_LIN, capi.MUL_LUT])
+def test_every_scalar_every_byte(mul):
+    o = oracle()
+    A = splitmix_bytes(5, 256 * 256).reshape(256, 256).copy()
+    Bm = np.tile(np.arange(256, dtype=np.uint8), (256, 1))
+    idx = np.arange(256, dtype=np.int32)
+    u = np.arange(256, dtype=np.uint8)
+    A0 = A.copy()
+    for k in range(256):
+        o.orc_row_axpy(GF256, 0, ptr(A0), 256, ptr(Bm), 256, k, k, k)
+    dA = dev(A)
+    device.rowops(GF256, OP_AXPY, dA, dev(Bm), dev(idx), dev(idx), dev(u), mul=mul)
+    assert np.array_equal(host(dA), A0)
+
+
+def test_swap_and_b32_device():
+    o = oracle()
+    A = splitmix_bytes(7, 10 * 64).reshape(10, 64).copy()
+    A0 = A.copy()
+    i = np.array([0, 2, 5, 7], dtype=np.int32)
+    j = np.array([1, 2, 9, 3], dtype=np.int32)
+    for k in range(4):
+        o.orc_row_swap(ptr(A0), 64, i[k], j[k])
+    dA = dev(A)
+    device.rowops(GF256, OP_SWAP, dA, dA, dev(i), dev(j), None)
+    assert np.array_equal(host(dA), A0)
+    A = splitmix_bytes(8, 6 * 96).reshape(6, 96).copy()
+    A0 = A.copy()
+    masks = splitmix_bytes(9, 6 * 16).view(np.uint32).reshape(6, 4).copy()  # 16-byte rows, 3 words used
+    i = np.array([0, 3, 4], dtype=np.int32)
+    j = np.array([5, 1, 1], dtype=np.int32)
+    u = np.array([0x53, 1, 0xFF], dtype=np.uint8)
+    for k in range(3):
+        o.orc_row_axpy_b32(ptr(A0), 96, ptr(masks[j[k]], u32p), i[k], u[k])
+    dA = dev(A)
+    device.rowops(GF256, OP_AXPY_B32, dA, dev(masks.view(np.uint8)), dev(i), dev(j), dev(u), row_bytes=96)
+    assert np.array_equal(host(dA), A0)
+
+
+def test_config1_shape_and_large_batch():
+    """BASELINE.json configs[0]: 1024 rows x 1280-byte rows, one batched launch of 1024
+    row ops, every output byte checked; then a batch large enough for the 4-chunk kernel."""
+    o = oracle()
+    rng = np.random.default_rng(1)
+    for rows in (1024, 8192):
+        st = 1280
+        A = splitmix_bytes(300, rows * st).reshape(rows, st).copy()
+        Bm = splitmix_bytes(301, rows * st).reshape(rows, st).copy()
+        dst = rng.permutation(rows).astype(np.int32)
+        src = rng.integers(0, rows, rows).astype(np.int32)
+        u = rng.integers(2, 256, rows).astype(np.uint8)
+        for op in (OP_AXPY, OP_ADD, OP_SCAL):
+            A0 = A.copy()
+            _oracle_apply(GF256, 0, op, A0, Bm, dst, src, u)
+            dA = dev(A)
+            device.rowops(GF256, op, dA, dev(Bm), dev(dst), dev(src), dev(u))
+            assert np.array_equal(host(dA), A0), (rows, op)
+
+
+def test_binmat_and_gf2_paths():
+    o = oracle()
+    rows, st = 64, 1024
+    A = splitmix_bytes(400, rows * st).reshape(rows, st).copy()
+    A0 = A.copy()
+    dst = np.arange(0, 32, dtype=np.int32)
+    src = np.arange(32, 64, dtype=np.int32)
+    for k in range(32):
+        o.orc_row_add(ptr(A0), st, ptr(A0), st, dst[k], src[k])
+    dA = dev(A)
+    device.rowops(GF2, OP_ADD, dA, dA, dev(dst), dev(src), None)
+    assert np.array_equal(host(dA), A0)
+
+
+def test_fill_random_matches_splitmix():
+    t = torch.empty(1 << 16, dtype=torch.uint8, device="cuda")
+    device.fill_random(t, 77, 4096)
+    assert np.array_equal(host(t), splitmix_bytes(77, 1 << 16, 4096))
+
+
+def test_host_index_arrays_are_staged(cuda_lib):
+    """index/scalar arrays may live in plain host memory (the struct-level *_batch calls rely on it)"""
+    o = oracle()
+    A = splitmix_bytes(500, 8 * 64).reshape(8, 64).copy()
+    A0 = A.copy()
+    dst = np.array([1, 3], dtype=np.uint32)
+    src = np.array([0, 2], dtype=np.uint32)
+    u = np.array([9, 200], dtype=np.uint8)
+    for k in range(2):
+        o.orc_row_axpy(GF256, 0, ptr(A0), 64, ptr(A0), 64, dst[k], src[k], u[k])
+    dA = dev(A)
+    import ctypes as C
+    capi.check(cuda_lib.oblas_b200_rowops(GF256, 0, OP_AXPY, -1, C.c_void_p(dA.data_ptr()), 64,
+                                          C.c_void_p(dA.data_ptr()), 64, 64, dst.ctypes.data, src.ctypes.data,
+                                          u.ctypes.data, 2))
+    assert np.array_equal(host(dA), A0)

@@ -1,0 +1,171 @@
+"""Batched elimination + RHS update on the GPU (oblas_b200_solve_batch and the host
+streaming variant) against the oracle / the compiled reference, bit for bit, and at
+BASELINE.json's full size through properties that do not need the CPU to redo the
+work (A -> I, A_orig * X == B_orig on sampled rows)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from gpu_helpers import dev, gf256_vecmat, host
+from helpers import (GF2, GF4, GF16, GF256, FIELD_BITS, field_row_bytes, mat_view, oracle, oracle_solve, ptr,
+                     random_matrix, reference, splitmix_bytes, u32p)
+from oblas_b200 import capi, device
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _bind(cuda_lib):
+    device.bind(0)
+
+
+def _batch(field, rows, cols, b_bytes, seed, nsys, deficient_every=0):
+    A = np.stack([random_matrix(field, rows, cols, seed + 2 * s,
+                                rank_deficient=(1 + s % 2) if deficient_every and s % deficient_every == 0 else 0)
+                  for s in range(nsys)])
+    B = None
+    if b_bytes:
+        B = np.stack([splitmix_bytes(seed + 2 * s + 1, rows * b_bytes).reshape(rows, b_bytes) for s in range(nsys)]).copy()
+    return A, B
+
+
+def _check_vs_oracle(field, A, B, cols, rank, piv):
+    nsys = A.shape[0]
+    A0, B0 = A.copy(), (B.copy() if B is not None else None)
+    for s in range(nsys):
+        rk, pv = oracle_solve(field, A0[s], B0[s] if B0 is not None else None, cols)
+        assert rank[s] == rk, s
+        assert np.array_equal(piv[s][:rk].astype(np.uint32), pv[:rk]), s
+    return A0, B0
+
+
+@pytest.mark.parametrize("field,rows,cols,b_bytes,nsys,defe", [
+    (GF256, 64, 64, 272, 7, 3),
+    (GF256, 100, 100, 1280, 3, 0),
+    (GF256, 256, 256, 512, 4, 2),
+    (GF256, 33, 50, 32, 2, 0),
+    (GF256, 50, 33, 32, 2, 0),
+    (GF16, 128, 128, 64, 5, 2),
+    (GF16, 300, 300, 0, 2, 0),
+    (GF4, 128, 128, 32, 5, 2),
+    (GF4, 300, 300, 16, 2, 0),
+    (GF2, 128, 128, 32, 5, 0),
+    (GF2, 500, 500, 64, 3, 0),
+    (GF2, 100, 300, 16, 2, 0),
+])
+def test_solve_batch_vs_oracle(field, rows, cols, b_bytes, nsys, defe):
+    A, B = _batch(field, rows, cols, b_bytes, 3000 + rows + field, nsys, defe)
+    dA, dB = dev(A), (dev(B) if B is not None else None)
+    rank, piv = device.solve_batch(field, dA, cols, dB, want_pivcols=True)
+    rank, piv = host(rank), host(piv)
+    A0, B0 = _check_vs_oracle(field, A, B, cols, rank, piv)
+    assert np.array_equal(host(dA), A0)
+    if B is not None:
+        assert np.array_equal(host(dB), B0)
+
+
+def test_solve_more_systems_than_sms():
+    """persistent CTAs loop over the batch: 300 systems on 148 SMs"""
+    A, B = _batch(GF256, 48, 48, 64, 4000, 300, 7)
+    dA, dB = dev(A), dev(B)
+    rank, piv = device.solve_batch(GF256, dA, 48, dB, want_pivcols=True)
+    A0, B0 = _check_vs_oracle(GF256, A, B, 48, host(rank), host(piv))
+    assert np.array_equal(host(dA), A0) and np.array_equal(host(dB), B0)
+
+
+def test_zero_and_identity_systems():
+    K = 64
+    A = np.zeros((2, K, K), dtype=np.uint8)
+    A[1] = np.eye(K, dtype=np.uint8) * 7
+    B = splitmix_bytes(1, 2 * K * 32).reshape(2, K, 32).copy()
+    dA, dB = dev(A), dev(B)
+    rank, _ = device.solve_batch(GF256, dA, K, dB)
+    assert host(rank).tolist() == [0, K]
+    A0, B0 = A.copy(), B.copy()
+    for s in range(2):
+        oracle_solve(GF256, A0[s], B0[s], K)
+    assert np.array_equal(host(dA), A0) and np.array_equal(host(dB), B0)
+
+
+def test_config2_shape_vs_reference():
+    """K=1024, 1280-byte RHS symbols (BASELINE.json configs[1]) -- whole buffers against
+    the unmodified reference's AVX build driven by oracle/ref_driver.c (falls back to a
+    K=384 system on the scalar oracle when the host has no AVX2)."""
+    lib = reference("avx512") or reference("avx2")
+    K, L, nsys = (1024, 1280, 3) if lib is not None else (384, 1280, 2)
+    A, B = _batch(GF256, K, K, L, 5000, nsys, 0)
+    A[1, K // 2] = A[1, 3]  # one singular system in the batch
+    dA, dB = dev(A), dev(B)
+    rank, piv = device.solve_batch(GF256, dA, K, dB, want_pivcols=True)
+    rank, piv, gA, gB = host(rank), host(piv), host(dA), host(dB)
+    for s in range(nsys):
+        if lib is not None:
+            ma, mb = lib.octmat_new(K, K), lib.octmat_new(K, L)
+            assert ma.contents.stride == K and mb.contents.stride == L
+            mat_view(ma)[:] = A[s]
+            mat_view(mb)[:] = B[s]
+            pv = np.zeros(K, dtype=np.uint32)
+            rk = lib.refdrv_octmat_solve(ma, mb, ptr(pv, u32p))
+            wa, wb = mat_view(ma).copy(), mat_view(mb).copy()
+            lib.octmat_free(ma)
+            lib.octmat_free(mb)
+        else:
+            wa, wb = A[s].copy(), B[s].copy()
+            rk, pv = oracle_solve(GF256, wa, wb, K)
+        assert rank[s] == rk and np.array_equal(piv[s][:rk].astype(np.uint32), pv[:rk])
+        assert np.array_equal(gA[s], wa), s
+        assert np.array_equal(gB[s], wb), s
+    assert rank[1] == K - 1 and rank[0] == K
+
+
+def test_full_size_roundtrip_properties():
+    """A batch at full K=1024 / L=1280 generated on the device: every full-rank system
+    ends with A == I, and A_orig * X == B_orig on sampled rows (checked on the CPU)."""
+    K, L, nsys = 1024, 1280, 160
+    dA = torch.empty((nsys, K, K), dtype=torch.uint8, device="cuda")
+    dB = torch.empty((nsys, K, L), dtype=torch.uint8, device="cuda")
+    device.fill_random(dA, 6000)
+    device.fill_random(dB, 6001)
+    A_orig, B_orig = dA.clone(), dB.clone()
+    rank, _ = device.solve_batch(GF256, dA, K, dB)
+    rank = host(rank)
+    eye = torch.eye(K, dtype=torch.uint8, device="cuda")
+    full = np.nonzero(rank == K)[0]
+    assert len(full) >= nsys - 8  # P(singular) ~ 0.4 %
+    for s in full:
+        assert torch.equal(dA[s], eye), s
+    rng = np.random.default_rng(0)
+    for s in rng.choice(full, 6, replace=False):
+        X = host(dB[s])
+        Ao, Bo = host(A_orig[s]), host(B_orig[s])
+        for r in rng.choice(K, 4, replace=False):
+            assert np.array_equal(gf256_vecmat(Ao[r], X), Bo[r]), (s, r)
+
+
+def test_solve_batch_host_streaming(cuda_lib):
+    """host buffers in, host buffers out (the e2e entry point), several chunks"""
+    K, L, nsys = 96, 272, 37
+    A, B = _batch(GF256, K, K, L, 7000, nsys, 5)
+    A0, B0 = A.copy(), B.copy()
+    want = [oracle_solve(GF256, A0[s], B0[s], K) for s in range(nsys)]
+    rank = np.zeros(nsys, dtype=np.int32)
+    piv = np.zeros((nsys, K), dtype=np.uint32)
+    capi.check(cuda_lib.oblas_b200_solve_batch_host(
+        GF256, A.ctypes.data, A.strides[1], A.strides[0], K, K, K, B.ctypes.data, B.strides[1], B.strides[0], L,
+        rank.ctypes.data, piv.ctypes.data, nsys, 8))
+    assert rank.tolist() == [w[0] for w in want]
+    assert np.array_equal(A, A0) and np.array_equal(B, B0)
+    for s in range(nsys):
+        assert np.array_equal(piv[s][:want[s][0]], want[s][1][:want[s][0]])
+
+
+def test_rows_beyond_shared_memory_fail_loudly():
+    K = 40000  # u16 row map / shared-memory panel cannot hold it; there is no fallback path
+    dA = torch.zeros((1, 1, 16), dtype=torch.uint8, device="cuda")
+    rank = torch.zeros(1, dtype=torch.int32, device="cuda")
+    rc = capi.lib().oblas_b200_solve_batch(GF256, C.c_void_p(dA.data_ptr()), 16, 16, K, 16, 16, None, 0, 0, 0,
+                                           C.c_void_p(rank.data_ptr()), None, 1)
+    assert rc != 0 and b"no fallback" in capi.lib().oblas_b200_last_error()
