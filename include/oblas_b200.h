@@ -65,9 +65,11 @@ void oblas_b200_shutdown(void);
 int oblas_b200_device(void);
 int oblas_b200_sm_count(void);
 const char *oblas_b200_last_error(void);
-/* all launches go to this stream (a cudaStream_t passed as void*); NULL selects
- * the library's own non-blocking stream */
+/* all launches go to this stream (a cudaStream_t passed as void*; NULL is CUDA's
+ * legacy default stream).  After init the library uses its own non-blocking
+ * stream; oblas_b200_use_own_stream() goes back to it. */
 void oblas_b200_set_stream(void *cuda_stream);
+void oblas_b200_use_own_stream(void);
 void *oblas_b200_get_stream(void);
 int oblas_b200_sync(void);                /* wait for the current stream */
 /* drop-in (layer 1) calls synchronise before returning unless async != 0, in

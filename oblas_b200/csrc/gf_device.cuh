@@ -16,8 +16,22 @@
 
 namespace ob2 {
 
+// PRMT with the full 4-bit selectors of the hardware instruction (bit 3 of a
+// selector nibble = replicate the sign of the selected byte).  CUDA's
+// __byte_perm() intrinsic only honours 3 bits per selector, so the PTX
+// instruction is emitted directly.
+OB2_D uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+#ifdef OB2_EMU
+  return __byte_perm(a, b, sel);  // the emulation implements the 4-bit selectors
+#else
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+#endif
+}
+
 // 0xFF in every byte of w whose bit 7 is set (PRMT sign-replicate mode).
-OB2_D uint32_t spread_msb(uint32_t w) { return __byte_perm(w, 0u, 0xba98u); }
+OB2_D uint32_t spread_msb(uint32_t w) { return prmt(w, 0u, 0xba98u); }
 
 struct Basis8 {  // basis_i replicated into the 4 bytes of a word
   uint32_t b[8];
@@ -38,9 +52,9 @@ struct Lut16x2 {  // lo[16], hi[16] as 4 little-endian words each
 OB2_D uint32_t lut16(uint32_t idx, const uint32_t t[4]) {
   uint32_t x = idx & 0x07070707u;
   uint32_t p = x | (x >> 4);                   // byte0 = i0|i1<<4, byte2 = i2|i3<<4
-  uint32_t sel = __byte_perm(p, 0u, 0x4420u);  // 16-bit selector, nibble n = idx_n & 7
-  uint32_t a = __byte_perm(t[0], t[1], sel);   // entries 0..7
-  uint32_t b = __byte_perm(t[2], t[3], sel);   // entries 8..15
+  uint32_t sel = prmt(p, 0u, 0x4420u);  // 16-bit selector, nibble n = idx_n & 7
+  uint32_t a = prmt(t[0], t[1], sel);   // entries 0..7
+  uint32_t b = prmt(t[2], t[3], sel);   // entries 8..15
   uint32_t m = spread_msb(idx << 4);           // 0xFF where idx bit 3 set
   return (a & ~m) | (b & m);
 }

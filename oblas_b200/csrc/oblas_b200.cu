@@ -211,7 +211,11 @@ int oblas_b200_sm_count(void) { return ensure_init() ? -1 : g.sm_count; }
 const char *oblas_b200_last_error(void) { return tl_err; }
 void oblas_b200_set_stream(void *s) {
   if (ensure_init()) return;
-  g.stream = s ? (cudaStream_t)s : g.own_stream;
+  g.stream = (cudaStream_t)s;  // NULL is the legacy default stream
+}
+void oblas_b200_use_own_stream(void) {
+  if (ensure_init()) return;
+  g.stream = g.own_stream;
 }
 void *oblas_b200_get_stream(void) { return ensure_init() ? nullptr : (void *)g.stream; }
 int oblas_b200_sync(void) {

@@ -131,17 +131,8 @@ def oracle_table(field, which, variant=0):
 
 
 # ---- the compiled reference (oracle/_ref), struct API ---------------------------
-class Octmat(C.Structure):
-    _fields_ = [("rows", C.c_uint), ("cols", C.c_uint), ("stride", C.c_uint), ("bits", u8p)]
-
-
-class Gfmat(C.Structure):
-    _fields_ = [("field", C.c_int), ("rows", C.c_uint), ("cols", C.c_uint),
-                ("stride", C.c_uint), ("align", C.c_uint), ("bits", u32p)]
-
-
-class Binmat(C.Structure):
-    _fields_ = [("rows", C.c_uint), ("cols", C.c_uint), ("stride", C.c_uint), ("bits", u32p)]
+# struct layouts are the interface (octmat.h:19-24, gfmat.h:18-25, binmat.h:6-11): one definition
+from oblas_b200.capi import Binmat, Gfmat, Octmat  # noqa: E402
 
 
 def bind_struct_api(lib):
