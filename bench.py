@@ -256,8 +256,11 @@ def run_b200_arm(args):
     macs = nsys * (K ** 3 / 2.0 + K * K * L)         # Gauss-Jordan as executed (K^3/2 + K^2 L)
     macs_min = nsys * (K ** 3 / 3.0 + K * K * L)     # SURVEY 8d algorithmic minimum
     ach = algo_bytes / (kern_ms / 1e3) / 1e9
+    # DRAM bytes of this kernel from the committed ncu --set full capture (profiles/):
+    # dram__bytes_read.sum + dram__bytes_write.sum = 72.01 GB for a 296-system launch
+    traffic = 72.011960e9 / 296 * nsys if (K, L) == (K_DEFAULT, L_DEFAULT) else None
     roofline = {"kernel": "ob2::solve_kernel<8,4>", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "note": "by construction not HBM bound (arithmetic intensity ~460 MAC/B); see roofline_binding"}
     sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("clocks_under_load", {}).get("sm_mhz_median") or 1500.0
     sms = L_.oblas_b200_sm_count()

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256) rowop_kernel(const RowOpArgs p) {
       // the reference's short-circuits
       if (OP == OP_AXPY && u == 0) live[k] = false;          // octmat.c:36-37
       if (OP == OP_SCAL && u < 2) live[k] = false;           // octmat.c:57-58
-      if (OP == OP_SWAP && i == j) live[k] = false;          // octmat.c:25-26
+      if (OP == OP_SWAP && pa[k] == pb[k]) live[k] = false;  // octmat.c:25-26 (same row of the same matrix)
       if (OP == OP_AXPY_B32 && u == 0) live[k] = false;      // XOR with 0
     }
   }
