@@ -259,13 +259,18 @@ def run_b200_arm(args):
     # DRAM bytes of this kernel from the committed ncu --set full capture (profiles/):
     # dram__bytes_read.sum + dram__bytes_write.sum = 72.01 GB for a 296-system launch
     traffic = 72.011960e9 / 296 * nsys if (K, L) == (K_DEFAULT, L_DEFAULT) else None
-    roofline = {"kernel": "ob2::solve_kernel<8,4>", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+    roofline = {"kernel": "ob2::solve_kernel<8,4,6,128>", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "note": "by construction not HBM bound (arithmetic intensity ~460 MAC/B); see roofline_binding"}
     sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("clocks_under_load", {}).get("sm_mhz_median") or 1500.0
     sms = L_.oblas_b200_sm_count()
-    lut_peak = 64.0 * sms * sm_mhz * 1e6             # byte-MACs/s: 128 B/clk/SM of LDS, 2 table bytes per MAC
-    binding = {"kernel": "ob2::solve_kernel<8,4>", "bound": "shared-memory LUT bandwidth (64 GF(256) MAC/clk/SM)",
+    # shared-memory look-up ceiling of the kernel's table geometry: a row update of 16 bytes x
+    # 16 pivots (256 byte-MACs) costs 22 LDS.128 (6-bit groups of the 128 coefficient bits), the
+    # crossbar delivers 8 x 16 B per clk per SM  =>  256 * 8 / 22 = 93.1 byte-MACs/clk/SM
+    macs_per_clk_sm = 256.0 * 8.0 / 22.0
+    lut_peak = macs_per_clk_sm * sms * sm_mhz * 1e6
+    binding = {"kernel": "ob2::solve_kernel<8,4,6,128>",
+               "bound": "shared-memory LUT bandwidth (6-bit Four-Russians tables: %.1f GF(256) MAC/clk/SM)" % macs_per_clk_sm,
                "achieved": macs / (kern_ms / 1e3) / 1e12, "peak": lut_peak / 1e12, "unit": "T GF-MAC/s",
                "frac": macs / (kern_ms / 1e3) / lut_peak, "sm_mhz_used": sm_mhz,
                "algorithmic_min_gmacs_per_system": macs_min / nsys / 1e9,

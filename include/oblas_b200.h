@@ -76,6 +76,14 @@ int oblas_b200_sync(void);                /* wait for the current stream */
  * which case they only enqueue and the caller must oblas_b200_sync() before
  * touching `bits` from the host */
 void oblas_b200_set_async(int async);
+/* Four-Russians table geometry of the elimination / apply kernels (tuning knob for
+ * measurements): 0 = 4-bit groups, 256-byte tiles; 1 = 6-bit groups, 128-byte tiles;
+ * 2 = 7-bit groups, 64-byte tiles; -1 = library default.  Results are identical. */
+void oblas_b200_set_tuning(int solve_geo, int apply_geo);
+/* diagnostics: enable != 0 starts per-phase cycle counters of the elimination kernel
+ * (panel load, panel factorisation, trailing update, permutation; SM cycles summed
+ * over CTAs); out (may be NULL) receives the 4 counters collected so far */
+int oblas_b200_solve_phases(int enable, uint64_t *out);
 /* number of kernels this library has launched so far */
 uint64_t oblas_b200_launch_count(void);
 

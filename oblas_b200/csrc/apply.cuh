@@ -3,8 +3,8 @@
 // The caller-side loop this replaces is  for i, j: oaxpy(Y, D, i, j, C[i][j])
 // (octmat.c:32-46), i.e.  Y[i,:] = XOR_j C[i][j] (x) D[j,:]  over whole symbol rows.
 //
-// One CTA owns a Y tile of RM = 256 rows x 256 bytes held entirely in registers
-// (8 x 16 B per thread) and sweeps the Kc coefficient columns 16 at a time: for
+// One CTA owns a Y tile of rm rows x WT bytes held entirely in registers
+// (8 x 16 B per thread; 512 x 128 B at the default geometry) and sweeps the Kc coefficient columns 16 at a time: for
 // the 16 D rows of a step it builds the same Four-Russians tables as solve.cuh
 // (32 tables x 16 entries x 256 B = 128 KB of shared memory, one thread per table
 // column, straight from global memory), stages the 256 x 16 coefficient block in
@@ -29,24 +29,35 @@ struct ApplyArgs {
   int accumulate;         // 0: Y = C*D, 1: Y ^= C*D
 };
 
-constexpr int kApplyRM = 256;   // Y rows per CTA tile (512 threads x 8 chunks)
-constexpr int kApplyRU = 8;
-constexpr int kApplyStep = 16;  // coefficient columns per table build
-constexpr size_t kApplySmem = (size_t)32 * 16 * kSolveWT + (size_t)kApplyRM * 16;
+constexpr int kApplyRU = 8;     // Y chunks (16 B) per thread
+constexpr int kApplyStep = 16;  // coefficient columns per table build (128 coefficient bits)
 
+template <int KB, int WT>
+struct ApplyGeo {
+  using G = Geo<4, KB, WT>;
+  static constexpr size_t smem(uint32_t threads) {
+    return G::TAB_BYTES + (size_t)(threads / G::CW) * kApplyRU * 16;
+  }
+};
+
+template <int KB, int WT>
 __global__ void __launch_bounds__(512, 1) apply_kernel(const ApplyArgs p) {
+  using G = Geo<4, KB, WT>;
+  constexpr int CW = G::CW, NG = G::NG, LASTBITS = G::LASTBITS;
+  constexpr int PARTS = 1 << (KB - 4);
+  constexpr int LPARTS = LASTBITS > 4 ? (1 << (LASTBITS - 4)) : 1;
   OB2_DYN_SMEM(smem_raw);
   uint4 *tab = reinterpret_cast<uint4 *>(smem_raw);
-  uint4 *cpan = reinterpret_cast<uint4 *>(smem_raw + (size_t)32 * 16 * kSolveWT);  // [RM]
+  uint4 *cpan = reinterpret_cast<uint4 *>(smem_raw + G::TAB_BYTES);  // [rm]
   const uint32_t tid = threadIdx.x, T = blockDim.x;
-  const uint32_t rstep = T >> 4;          // rows covered by one sweep of the block
-  const uint32_t rm = rstep * kApplyRU;   // Y rows per CTA tile (256 at 512 threads)
+  const uint32_t rstep = T / CW;          // rows covered by one sweep of the block
+  const uint32_t rm = rstep * kApplyRU;   // Y rows per CTA tile
   const uint32_t rt = blockIdx.x / p.col_tiles, ct = blockIdx.x - rt * p.col_tiles;
-  const uint32_t r0 = rt * rm, off = ct * kSolveWT;
-  const uint32_t tile_bytes = (p.nbytes - off < (uint32_t)kSolveWT) ? (p.nbytes - off) : (uint32_t)kSolveWT;
+  const uint32_t r0 = rt * rm, off = ct * WT;
+  const uint32_t tile_bytes = (p.nbytes - off < (uint32_t)WT) ? (p.nbytes - off) : (uint32_t)WT;
   const uint32_t cwt = tile_bytes >> 4;
   const uint32_t rows_here = (p.M - r0 < rm) ? (p.M - r0) : rm;
-  const uint32_t ch = tid & 15, rl = tid >> 4;
+  const uint32_t ch = tid % CW, rl = tid / CW;
 
   uint4 acc[kApplyRU];
 #pragma unroll
@@ -76,16 +87,20 @@ __global__ void __launch_bounds__(512, 1) apply_kernel(const ApplyArgs p) {
       cpan[row] = c;
     }
     // tables for D rows j0 .. j0+nj-1
-    const uint32_t nbasis = nj * 8, ngrp = (nbasis + 3) >> 2;
-    for (uint32_t it = tid; it < ngrp * cwt; it += T) {
-      uint32_t g = it / cwt, c2 = it - g * cwt;
-      uint4 e[16];
-      build_table_column<8>(e, g, nbasis, [&](uint32_t s) {
+    const uint32_t nbasis = nj * 8;
+    for (uint32_t it = tid; it < (uint32_t)(NG - 1) * PARTS * cwt; it += T) {
+      uint32_t c2 = it % cwt, q = it / cwt;
+      uint32_t part = q % PARTS, g = q / PARTS;
+      build_table_part<8, KB>(tab + (size_t)(g << KB) * CW + c2, CW, g * KB, nbasis, part, [&](uint32_t s) {
         return __ldg(reinterpret_cast<const uint4 *>(p.D + (size_t)(j0 + s) * p.d_stride + off + c2 * 16));
       });
-      uint4 *tg = tab + (g * 16) * kSolveCW + c2;
-#pragma unroll
-      for (int v = 0; v < 16; v++) tg[v * kSolveCW] = e[v];
+    }
+    for (uint32_t it = tid; it < (uint32_t)LPARTS * cwt; it += T) {
+      uint32_t c2 = it % cwt, part = it / cwt;
+      build_table_part<8, LASTBITS>(tab + (size_t)((NG - 1) << KB) * CW + c2, CW, (NG - 1) * KB, nbasis, part,
+                                    [&](uint32_t s) {
+        return __ldg(reinterpret_cast<const uint4 *>(p.D + (size_t)(j0 + s) * p.d_stride + off + c2 * 16));
+      });
     }
     __syncthreads();
     if (ch < cwt) {
@@ -95,19 +110,13 @@ __global__ void __launch_bounds__(512, 1) apply_kernel(const ApplyArgs p) {
         uint32_t row = rl + k * rstep;
         uint4 c = cpan[row];
         if ((c.x | c.y | c.z | c.w) == 0) continue;
-        uint32_t cw[4] = {c.x, c.y, c.z, c.w};
-        if (ngrp == 32) {
+        PanelVec<4> cv;
+        cv.w[0] = c.x; cv.w[1] = c.y; cv.w[2] = c.z; cv.w[3] = c.w;
 #pragma unroll
-          for (int g = 0; g < 32; g++) {
-            uint32_t nib = (cw[g >> 3] >> (4 * (g & 7))) & 15u;
-            acc[k] = xor4(acc[k], tc[(g * 16 + nib) * kSolveCW]);
-          }
-        } else {
-          for (uint32_t g = 0; g < ngrp; g++) {
-            uint32_t word = (g >> 3) == 0 ? c.x : (g >> 3) == 1 ? c.y : (g >> 3) == 2 ? c.z : c.w;
-            uint32_t nib = (word >> (4 * (g & 7))) & 15u;
-            acc[k] = xor4(acc[k], tc[(g * 16 + nib) * kSolveCW]);
-          }
+        for (int g = 0; g < NG; g++) {
+          const int bits = (g == NG - 1) ? LASTBITS : KB;
+          uint32_t idx = get_bits<4>(cv, g * KB, bits);
+          acc[k] = xor4(acc[k], tc[(size_t)((g << KB) + idx) * CW]);
         }
       }
     }
@@ -121,21 +130,33 @@ __global__ void __launch_bounds__(512, 1) apply_kernel(const ApplyArgs p) {
   }
 }
 
-inline int launch_apply(const ApplyArgs &p0, uint32_t threads, cudaStream_t s) {
-  ApplyArgs p = p0;
-  if (p.M == 0 || p.nbytes == 0) return 0;
-  if (p.nbytes & 15) return -1;
-  p.col_tiles = (p.nbytes + kSolveWT - 1) / kSolveWT;
-  if (threads < 32 || threads > 512 || (threads & 31)) return -1;
-  uint32_t rm = (threads >> 4) * kApplyRU;
+template <int KB, int WT>
+inline int launch_apply_t(ApplyArgs p, uint32_t threads, cudaStream_t s) {
+  using G = Geo<4, KB, WT>;
+  if (threads < 32 || threads > 512 || (threads & 31) || threads % G::CW) return -1;
+  p.col_tiles = (p.nbytes + WT - 1) / WT;
+  uint32_t rm = (threads / G::CW) * kApplyRU;
   uint32_t row_tiles = (p.M + rm - 1) / rm;
-  auto k = apply_kernel;
+  size_t smem = ApplyGeo<KB, WT>::smem(threads);
+  auto k = apply_kernel<KB, WT>;
 #ifndef OB2_EMU
-  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kApplySmem) != cudaSuccess)
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return -2;
 #endif
-  OB2_LAUNCH(k, row_tiles * p.col_tiles, threads, kApplySmem, s, p);
+  OB2_LAUNCH(k, row_tiles * p.col_tiles, threads, smem, s, p);
   return 0;
+}
+
+// geo as in launch_solve: 0 = 4-bit groups / 256-byte tiles, 1 = 6-bit / 128, 2 = 7-bit / 64
+inline int launch_apply(const ApplyArgs &p, int geo, uint32_t threads, cudaStream_t s) {
+  if (p.M == 0 || p.nbytes == 0) return 0;
+  if (p.nbytes & 15) return -1;
+  if (geo < 0) geo = 1;
+  switch (geo) {
+  case 1: return launch_apply_t<6, 128>(p, threads, s);
+  case 2: return launch_apply_t<7, 64>(p, threads, s);
+  default: return launch_apply_t<4, 256>(p, threads, s);
+  }
 }
 
 }  // namespace ob2

@@ -36,6 +36,8 @@ struct Ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   bool async = false;
+  int solve_geo = -1, apply_geo = -1;  // table geometry overrides (-1 = default)
+  unsigned long long *d_phase = nullptr;  // solve-kernel phase counters (diagnostics)
   DevTableSet *d_sets = nullptr;  // [TS_COUNT] in device memory
   DevTableSet h_sets[TS_COUNT];
   // device scratch for index arrays handed over from plain host memory
@@ -46,6 +48,7 @@ struct Ctx {
 };
 Ctx g;
 thread_local char tl_err[512] = "";
+void lanes_release();  // host-streaming lanes, defined with oblas_b200_solve_batch_host
 
 int fail(const char *fmt, ...) {
   va_list ap;
@@ -199,6 +202,7 @@ void oblas_b200_shutdown(void) {
   if (g.scratch) cudaFree(g.scratch);
   g.scratch = nullptr;
   g.scratch_bytes = 0;
+  lanes_release();
   cudaFree(g.d_sets);
   g.d_sets = nullptr;
   cudaStreamDestroy(g.own_stream);
@@ -224,7 +228,29 @@ int oblas_b200_sync(void) {
   return 0;
 }
 void oblas_b200_set_async(int async) { g.async = async != 0; }
+void oblas_b200_set_tuning(int solve_geo, int apply_geo) {
+  g.solve_geo = solve_geo;
+  g.apply_geo = apply_geo;
+}
 uint64_t oblas_b200_launch_count(void) { return g.launches.load(); }
+// diagnostics: enable != 0 starts (and zeroes) per-phase cycle counters of the elimination
+// kernel; out (may be NULL) receives 4 counters: panel load, panel factorisation,
+// trailing update, permutation -- SM cycles of thread 0 summed over all CTAs
+int oblas_b200_solve_phases(int enable, uint64_t *out) {
+  if (ensure_init()) return -1;
+  if (out && g.d_phase) {
+    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaMemcpy(out, g.d_phase, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  }
+  if (enable) {
+    if (!g.d_phase) CK(cudaMalloc(&g.d_phase, 8 * sizeof(uint64_t)));
+    CK(cudaMemset(g.d_phase, 0, 8 * sizeof(uint64_t)));
+  } else if (g.d_phase) {
+    CK(cudaFree(g.d_phase));
+    g.d_phase = nullptr;
+  }
+  return 0;
+}
 
 // ---- memory -----------------------------------------------------------------
 void *oblas_b200_dev_alloc(size_t bytes) {
@@ -405,8 +431,9 @@ static int solve_common(int field, SolveArgs &p, size_t nsys) {
   int ts = table_set_id(field, 1);
   p.inv = ts >= 0 ? g.d_sets[ts].inv : nullptr;
   p.nsys = (uint32_t)nsys;
+  p.phase = g.d_phase;
   uint32_t grid = nsys < (size_t)g.sm_count ? (uint32_t)nsys : (uint32_t)g.sm_count;
-  int rc = launch_solve(field, p, grid, 512, g.smem_optin, g.stream);
+  int rc = launch_solve(field, g.solve_geo, p, grid, 512, g.smem_optin, g.stream);
   if (rc == -1)
     return fail("solve: %u rows do not fit the shared-memory panel (limit %zu bytes); no fallback", p.rows, g.smem_optin);
   if (rc) return fail("solve: cudaFuncSetAttribute failed");
@@ -436,6 +463,56 @@ int oblas_b200_solve_batch(int field, void *A, size_t a_row_stride, size_t a_sys
   return solve_common(field, p, nsys);
 }
 
+}  // extern "C"
+
+// Lanes of the host-streaming pipeline: chunk c runs on lane c % NL (own stream, own
+// device buffers).  Kept in the context between calls (cudaMalloc/cudaFree of GB-sized
+// blocks costs more than the elimination of a chunk).
+namespace {
+constexpr int kLanes = 3;
+struct HostLane {
+  cudaStream_t s = nullptr;
+  uint8_t *A = nullptr, *B = nullptr;
+  int32_t *rank = nullptr;
+  uint32_t *piv = nullptr;
+  size_t a_cap = 0, b_cap = 0, r_cap = 0, p_cap = 0;
+};
+HostLane g_lane[kLanes];
+void *g_pin = nullptr;  // pinned staging for rank / pivcols of the whole call
+size_t g_pin_cap = 0;
+
+int lane_reserve(HostLane &L, size_t a, size_t b, size_t r, size_t pv) {
+  if (!L.s) CK(cudaStreamCreateWithFlags(&L.s, cudaStreamNonBlocking));
+  auto grow = [&](void **p, size_t &cap, size_t want) -> int {
+    if (want <= cap) return 0;
+    if (*p) CK(cudaFree(*p));
+    *p = nullptr;
+    cap = 0;
+    CK(cudaMalloc(p, want));
+    cap = want;
+    return 0;
+  };
+  if (grow((void **)&L.A, L.a_cap, a)) return -1;
+  if (grow((void **)&L.B, L.b_cap, b)) return -1;
+  if (grow((void **)&L.rank, L.r_cap, r)) return -1;
+  if (grow((void **)&L.piv, L.p_cap, pv)) return -1;
+  return 0;
+}
+void lanes_release() {
+  for (auto &L : g_lane) {
+    if (L.s) cudaStreamSynchronize(L.s);
+    cudaFree(L.A); cudaFree(L.B); cudaFree(L.rank); cudaFree(L.piv);
+    if (L.s) cudaStreamDestroy(L.s);
+    L = HostLane();
+  }
+  if (g_pin) cudaFreeHost(g_pin);
+  g_pin = nullptr;
+  g_pin_cap = 0;
+}
+}  // namespace
+
+extern "C" {
+
 int oblas_b200_solve_batch_host(int field, void *A_host, size_t a_row_stride, size_t a_sys_stride,
                                 uint32_t rows, uint32_t cols, size_t a_row_bytes, void *B_host,
                                 size_t b_row_stride, size_t b_sys_stride, size_t b_row_bytes,
@@ -449,87 +526,105 @@ int oblas_b200_solve_batch_host(int field, void *A_host, size_t a_row_stride, si
   std::lock_guard<std::mutex> lk(g.mu);
   const size_t per_sys = a_sys_stride + (B_host ? b_sys_stride : 0) + 4 + (pivcols_out ? (size_t)rows * 4 : 0);
   if (chunk_systems == 0) {
-    // ~3 waves of the grid per chunk keeps the tail short and the copies overlapped
-    chunk_systems = (size_t)g.sm_count * 2;
+    // one wave of the persistent grid per chunk: no tail inside a chunk, fine-grained
+    // overlap of the copies with the neighbouring chunks' elimination (measured best)
+    chunk_systems = (size_t)g.sm_count;
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
-    while (chunk_systems > 1 && chunk_systems * per_sys * 3 > free_b / 2) chunk_systems /= 2;
+    size_t have = 0;
+    for (auto &L : g_lane) have += L.a_cap + L.b_cap;
+    while (chunk_systems > 1 && chunk_systems * per_sys * kLanes > (free_b + have) / 2) chunk_systems /= 2;
   }
   if (chunk_systems > nsys) chunk_systems = nsys;
-  const int NL = 3;  // lanes: chunk c runs on lane c % NL (own stream, own buffers)
-  struct Lane {
-    cudaStream_t s = nullptr;
-    uint8_t *A = nullptr, *B = nullptr;
-    int32_t *rank = nullptr;
-    uint32_t *piv = nullptr;
-  } lane[NL];
-  int rc = 0;
-  cudaStream_t saved = g.stream;
-  auto cleanup = [&]() {
-    for (int l = 0; l < NL; l++) {
-      if (lane[l].s) cudaStreamSynchronize(lane[l].s);
-      cudaFree(lane[l].A);
-      cudaFree(lane[l].B);
-      cudaFree(lane[l].rank);
-      cudaFree(lane[l].piv);
-      if (lane[l].s) cudaStreamDestroy(lane[l].s);
-    }
-    g.stream = saved;
-  };
-#define CKL(call)                                                                  \
-  do {                                                                             \
-    cudaError_t e_ = (call);                                                       \
-    if (e_ != cudaSuccess) {                                                       \
-      fail("%s failed: %s", #call, cudaGetErrorString(e_));                        \
-      cleanup();                                                                   \
-      return -1;                                                                   \
-    }                                                                              \
-  } while (0)
-  for (int l = 0; l < NL; l++) {
-    CKL(cudaStreamCreateWithFlags(&lane[l].s, cudaStreamNonBlocking));
-    CKL(cudaMalloc(&lane[l].A, chunk_systems * a_sys_stride));
-    if (B_host) CKL(cudaMalloc(&lane[l].B, chunk_systems * b_sys_stride));
-    CKL(cudaMalloc(&lane[l].rank, chunk_systems * 4));
-    if (pivcols_out) CKL(cudaMalloc(&lane[l].piv, chunk_systems * (size_t)rows * 4));
+  for (auto &L : g_lane)
+    if (lane_reserve(L, chunk_systems * a_sys_stride, B_host ? chunk_systems * b_sys_stride : 0,
+                     chunk_systems * 4, pivcols_out ? chunk_systems * (size_t)rows * 4 : 0))
+      return -1;
+  // results are staged in pinned memory: a device-to-host copy into the caller's
+  // (usually pageable) rank array would block the host and serialise the lanes
+  const size_t pin_rank = (nsys * 4 + 255) & ~(size_t)255;
+  const size_t pin_need = pin_rank + (pivcols_out ? nsys * (size_t)rows * 4 : 0);
+  if (pin_need > g_pin_cap) {
+    if (g_pin) CK(cudaFreeHost(g_pin));
+    g_pin = nullptr;
+    g_pin_cap = 0;
+    CK(cudaHostAlloc(&g_pin, pin_need, cudaHostAllocDefault));
+    g_pin_cap = pin_need;
   }
+  int32_t *pin_r = (int32_t *)g_pin;
+  uint32_t *pin_p = (uint32_t *)((uint8_t *)g_pin + pin_rank);
+
+  const bool trace = getenv("OBLAS_B200_TRACE") != nullptr;
+  std::vector<cudaEvent_t> ev;
+  cudaEvent_t ev_start = nullptr;
+  if (trace) {
+    cudaEventCreate(&ev_start);
+    cudaEventRecord(ev_start, g_lane[0].s);
+  }
+  auto mark = [&](cudaStream_t st) {
+    if (!trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev.push_back(e);
+  };
+  cudaStream_t saved = g.stream;
+  int rc = 0;
   size_t c = 0;
-  for (size_t first = 0; first < nsys; first += chunk_systems, c++) {
-    Lane &L = lane[c % NL];
+  for (size_t first = 0; first < nsys && rc == 0; first += chunk_systems, c++) {
+    HostLane &L = g_lane[c % kLanes];
     size_t cnt = nsys - first < chunk_systems ? nsys - first : chunk_systems;
-    CKL(cudaMemcpyAsync(L.A, (uint8_t *)A_host + first * a_sys_stride, cnt * a_sys_stride,
-                        cudaMemcpyHostToDevice, L.s));
-    if (B_host)
-      CKL(cudaMemcpyAsync(L.B, (uint8_t *)B_host + first * b_sys_stride, cnt * b_sys_stride,
-                          cudaMemcpyHostToDevice, L.s));
-    if (pivcols_out) CKL(cudaMemsetAsync(L.piv, 0xff, cnt * (size_t)rows * 4, L.s));
+    cudaError_t e = cudaMemcpyAsync(L.A, (uint8_t *)A_host + first * a_sys_stride, cnt * a_sys_stride,
+                                    cudaMemcpyHostToDevice, L.s);
+    if (e == cudaSuccess && B_host)
+      e = cudaMemcpyAsync(L.B, (uint8_t *)B_host + first * b_sys_stride, cnt * b_sys_stride,
+                          cudaMemcpyHostToDevice, L.s);
+    if (e == cudaSuccess && pivcols_out) e = cudaMemsetAsync(L.piv, 0xff, cnt * (size_t)rows * 4, L.s);
+    if (e != cudaSuccess) { rc = fail("solve_host: copy to device failed: %s", cudaGetErrorString(e)); break; }
+    mark(L.s);
     SolveArgs p;
     memset(&p, 0, sizeof p);
     p.A = L.A; p.a_rs = a_row_stride; p.a_ss = a_sys_stride;
     p.rows = rows; p.cols = cols; p.a_bytes = (uint32_t)a_row_bytes;
-    p.B = L.B; p.b_rs = b_row_stride; p.b_ss = b_sys_stride;
+    p.B = B_host ? L.B : nullptr; p.b_rs = b_row_stride; p.b_ss = b_sys_stride;
     p.b_bytes = B_host ? (uint32_t)b_row_bytes : 0;
-    p.rank = L.rank; p.pivcols = L.piv;
+    p.rank = L.rank; p.pivcols = pivcols_out ? L.piv : nullptr;
     g.stream = L.s;
     rc = solve_common(field, p, cnt);
     g.stream = saved;
-    if (rc) {
-      cleanup();
-      return rc;
-    }
-    CKL(cudaMemcpyAsync((uint8_t *)A_host + first * a_sys_stride, L.A, cnt * a_sys_stride,
-                        cudaMemcpyDeviceToHost, L.s));
-    if (B_host)
-      CKL(cudaMemcpyAsync((uint8_t *)B_host + first * b_sys_stride, L.B, cnt * b_sys_stride,
-                          cudaMemcpyDeviceToHost, L.s));
-    CKL(cudaMemcpyAsync(rank_out + first, L.rank, cnt * 4, cudaMemcpyDeviceToHost, L.s));
-    if (pivcols_out)
-      CKL(cudaMemcpyAsync(pivcols_out + first * rows, L.piv, cnt * (size_t)rows * 4,
-                          cudaMemcpyDeviceToHost, L.s));
+    if (rc) break;
+    mark(L.s);
+    e = cudaMemcpyAsync((uint8_t *)A_host + first * a_sys_stride, L.A, cnt * a_sys_stride,
+                        cudaMemcpyDeviceToHost, L.s);
+    if (e == cudaSuccess && B_host)
+      e = cudaMemcpyAsync((uint8_t *)B_host + first * b_sys_stride, L.B, cnt * b_sys_stride,
+                          cudaMemcpyDeviceToHost, L.s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pin_r + first, L.rank, cnt * 4, cudaMemcpyDeviceToHost, L.s);
+    if (e == cudaSuccess && pivcols_out)
+      e = cudaMemcpyAsync(pin_p + first * rows, L.piv, cnt * (size_t)rows * 4, cudaMemcpyDeviceToHost, L.s);
+    if (e != cudaSuccess) { rc = fail("solve_host: copy to host failed: %s", cudaGetErrorString(e)); break; }
+    mark(L.s);
   }
-  for (int l = 0; l < NL; l++) CKL(cudaStreamSynchronize(lane[l].s));
-#undef CKL
-  cleanup();
-  return 0;
+  for (auto &L : g_lane) {
+    cudaError_t e = cudaStreamSynchronize(L.s);
+    if (e != cudaSuccess && rc == 0) rc = fail("solve_host: %s", cudaGetErrorString(e));
+  }
+  if (rc == 0) {
+    memcpy(rank_out, pin_r, nsys * 4);
+    if (pivcols_out) memcpy(pivcols_out, pin_p, nsys * (size_t)rows * 4);
+  }
+  if (trace) {
+    for (size_t k = 0; k + 2 < ev.size() + 1; k += 3) {
+      float a = 0, b = 0, d = 0;
+      cudaEventElapsedTime(&a, ev_start, ev[k]);
+      cudaEventElapsedTime(&b, ev_start, ev[k + 1]);
+      cudaEventElapsedTime(&d, ev_start, ev[k + 2]);
+      fprintf(stderr, "chunk %zu: h2d done %.1f ms, kernel done %.1f ms, d2h done %.1f ms\n", k / 3, a, b, d);
+    }
+    for (auto e : ev) cudaEventDestroy(e);
+    cudaEventDestroy(ev_start);
+  }
+  return rc;
 }
 
 // ---- apply ---------------------------------------------------------------------
@@ -549,7 +644,7 @@ int oblas_b200_gf256_apply(const void *C, size_t c_stride, uint32_t M, uint32_t 
   p.D = (const uint8_t *)D; p.d_stride = d_stride;
   p.Y = (uint8_t *)Y; p.y_stride = y_stride; p.nbytes = (uint32_t)nbytes; p.accumulate = accumulate;
   std::lock_guard<std::mutex> lk(g.mu);
-  int rc = launch_apply(p, 512, g.stream);
+  int rc = launch_apply(p, g.apply_geo, 512, g.stream);
   if (rc) return fail("apply: launch configuration failed (%d)", rc);
   return after_launch("apply");
 }

@@ -54,24 +54,39 @@ struct SolveArgs {
   // optional per-system base pointers (device arrays of nsys addresses) for
   // batches whose systems are separate allocations; override A/a_ss, B/b_ss
   const unsigned long long *a_ptrs, *b_ptrs;
+  // optional diagnostics: cycles spent per phase, summed over CTAs (8 counters)
+  unsigned long long *phase;
 };
 
-constexpr int kSolveWT = 256;  // column tile width in bytes
-constexpr int kSolveCW = kSolveWT / 16;
+// Tile / table geometry.  NB = 32*NBW panel bits are cut into groups of KB bits
+// (the last group takes the remainder); group g owns a 2^bits-entry table of WT
+// bytes per entry.  Larger KB = fewer look-ups per row (NB/KB instead of NB/4)
+// against a bigger table build (2^KB entries) and a narrower tile (WT).
+template <int NBW, int KB, int WT>
+struct Geo {
+  static constexpr int NB = 32 * NBW;
+  static constexpr int NG = (NB + KB - 1) / KB;
+  static constexpr int LASTBITS = NB - (NG - 1) * KB;
+  static constexpr int ENTRIES = (NG - 1) * (1 << KB) + (1 << LASTBITS);
+  static constexpr int CW = WT / 16;                     // 16-byte chunks per tile row
+  static constexpr size_t TAB_BYTES = (size_t)ENTRIES * WT;
+  static_assert(KB >= 4 && KB <= 8, "group width");
+  static_assert(WT % 16 == 0 && (CW & (CW - 1)) == 0, "tile width");
+};
 
 template <int NBW>
 struct PanelVec {
   uint32_t w[NBW];
 };
 
-template <int EXP, int NBW>
+template <int EXP, int NBW, int KB, int WT>
 struct SolveSmem {
+  using G = Geo<NBW, KB, WT>;
   static constexpr int NB = 32 * NBW;          // panel width in bits
   static constexpr int NPIV = NB / EXP;        // max pivots per panel
-  static constexpr int NGRP = NB / 4;          // 16-entry tables per tile
   static size_t bytes(uint32_t rows) {
     size_t s = 0;
-    s += (size_t)NGRP * 16 * kSolveWT;         // tables
+    s += G::TAB_BYTES;                         // tables
     s += (size_t)rows * NBW * 4 * 2;           // panel + V
     s = (s + 15) / 16 * 16;
     s += ((size_t)rows * 2 + 15) / 16 * 16;    // pos2phys (u16)
@@ -123,116 +138,130 @@ OB2_D uint4 xtime4(uint4 v) {
   return make_uint4(xtime<EXP>(v.x), xtime<EXP>(v.y), xtime<EXP>(v.z), xtime<EXP>(v.w));
 }
 
-// All 16 entries of Four-Russians table g for one 16-byte chunk.  Basis vector
-// m = 4g+k is x^(m % EXP) * row(m / EXP); rows beyond nbasis contribute zero.
+// bits [pos, pos+len) of the NBW-word little-endian bit string w (compile-time pos/len
+// after unrolling, so everything stays in registers)
+template <int NBW>
+OB2_D uint32_t get_bits(const PanelVec<NBW> &w, int pos, int len) {
+  const int wi = pos >> 5, sh = pos & 31;
+  uint32_t v = w.w[wi] >> sh;
+  if (sh + len > 32 && wi + 1 < NBW) v |= w.w[wi + 1 < NBW ? wi + 1 : wi] << (32 - sh);
+  return v & ((1u << len) - 1u);
+}
+
+// basis vector m of the panel: x^(m % EXP) * row(m / EXP), zero beyond nbasis
 template <int EXP, typename LoadRow>
-OB2_D void build_table_column(uint4 e[16], uint32_t g, uint32_t nbasis, LoadRow load_row) {
-  uint4 bv[4];
+OB2_D uint4 basis_vector(uint32_t m, uint32_t nbasis, uint4 prev, bool have_prev, LoadRow load_row) {
+  if (m >= nbasis) return make_uint4(0, 0, 0, 0);
+  uint32_t b = m % EXP;
+  if (have_prev && b != 0) return xtime4<EXP>(prev);
+  uint4 cur = load_row(m / EXP);
+  for (uint32_t j = 0; j < b; j++) cur = xtime4<EXP>(cur);
+  return cur;
+}
+
+// One thread builds 16 consecutive-in-Gray-order entries of table g for one chunk:
+// the entries whose high (bits-4) index bits equal `part`.  4 low basis vectors are
+// walked in Gray-code order: one XOR + one STS.128 per entry, nothing read back.
+template <int EXP, int BITS, typename LoadRow>
+OB2_D void build_table_part(uint4 *tg /* entry 0 of table g, this chunk */, int cw_stride,
+                            uint32_t m0, uint32_t nbasis, uint32_t part, LoadRow load_row) {
+  constexpr int LOW = BITS < 4 ? BITS : 4;
+  uint4 bv[BITS];
+  uint4 prev = make_uint4(0, 0, 0, 0);
+#pragma unroll
+  for (int i = 0; i < BITS; i++) {
+    bv[i] = basis_vector<EXP>(m0 + i, nbasis, prev, i > 0 && (m0 + i - 1) < nbasis, load_row);
+    prev = bv[i];
+  }
   uint4 cur = make_uint4(0, 0, 0, 0);
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    uint32_t m = 4 * g + k;
-    if (m < nbasis) {
-      uint32_t b = m % EXP;
-      if (k == 0 || b == 0) {
-        cur = load_row(m / EXP);
-        if (EXP == 8 && b) {  // only (k == 0, g odd): start at x^4
-          cur = xtime4<EXP>(xtime4<EXP>(xtime4<EXP>(xtime4<EXP>(cur))));
-        }
-      } else {
-        cur = xtime4<EXP>(cur);
-      }
-      bv[k] = cur;
-    } else {
-      bv[k] = make_uint4(0, 0, 0, 0);
-    }
+  for (int j = 0; j < BITS - LOW; j++)
+    if ((part >> j) & 1u) cur = xor4(cur, bv[LOW + j]);
+  uint4 *tp = tg + (size_t)(part << LOW) * cw_stride;
+  tp[0] = cur;
+#pragma unroll
+  for (int i = 1; i < (1 << LOW); i++) {
+    // Gray code: entry index i ^ (i >> 1) differs from the previous one in bit ctz(i)
+    int bit = (i & 1) ? 0 : (i & 2) ? 1 : (i & 4) ? 2 : 3;
+    cur = xor4(cur, bv[bit]);
+    tp[(i ^ (i >> 1)) * cw_stride] = cur;
   }
-  e[0] = make_uint4(0, 0, 0, 0);
-  e[1] = bv[0];
-  e[2] = bv[1];
-  e[3] = xor4(bv[0], bv[1]);
-  e[4] = bv[2];
-#pragma unroll
-  for (int v = 1; v < 4; v++) e[4 + v] = xor4(e[4], e[v]);
-  e[8] = bv[3];
-#pragma unroll
-  for (int v = 1; v < 8; v++) e[8 + v] = xor4(e[8], e[v]);
 }
 
 // ---------------------------------------------------------------------------
-// trailing update of one column tile (tile_bytes <= kSolveWT) of A or B
+// trailing update of one column tile (tile_bytes <= WT) of A or B
 // ---------------------------------------------------------------------------
-template <int EXP, int NBW>
+template <int EXP, int NBW, int KB, int WT>
 OB2_D void update_tile(uint8_t *base, size_t rs, uint32_t rows, uint32_t tile_off,
                        uint32_t tile_bytes, uint32_t npiv, const uint16_t *piv_phys,
                        const uint32_t *V, uint4 *tab) {
-  constexpr int NGRP = 32 * NBW / 4;
+  using G = Geo<NBW, KB, WT>;
+  constexpr int CW = G::CW, NG = G::NG, LASTBITS = G::LASTBITS;
+  constexpr int PARTS = 1 << (KB - 4);                 // threads per (table, chunk)
+  constexpr int LPARTS = LASTBITS > 4 ? (1 << (LASTBITS - 4)) : 1;
   const uint32_t tid = threadIdx.x, T = blockDim.x;
-  const uint32_t cwt = tile_bytes >> 4;             // 16-byte chunks in this tile
-  const uint32_t nbasis = npiv * EXP;               // basis rows in use
-  const uint32_t ngrp = (nbasis + 3) >> 2;          // tables in use
+  const uint32_t cwt = tile_bytes >> 4;                // 16-byte chunks in this tile
+  const uint32_t nbasis = npiv * EXP;                  // basis rows in use
 
-  // (a)+(b) one thread builds one whole 16-entry table column (table g, chunk
-  // ch): its 4 basis vectors x^b * P_old[s] come straight from global memory
-  // (+ xtime in registers), the 11 XOR-combinations never leave registers, so a
-  // tile's tables cost 16 STS.128 per (g,ch) and no shared-memory reads.
-  for (uint32_t it = tid; it < ngrp * cwt; it += T) {
-    uint32_t g = it / cwt, ch = it - g * cwt;
-    uint4 e[16];
-    build_table_column<EXP>(e, g, nbasis, [&](uint32_t s) {
+  // (a) tables, straight from global memory, no shared-memory reads
+  for (uint32_t it = tid; it < (uint32_t)(NG - 1) * PARTS * cwt; it += T) {
+    uint32_t ch = it % cwt, q = it / cwt;
+    uint32_t part = q % PARTS, g = q / PARTS;
+    build_table_part<EXP, KB>(tab + (size_t)(g << KB) * CW + ch, CW, g * KB, nbasis, part, [&](uint32_t s) {
       return *reinterpret_cast<const uint4 *>(base + (size_t)piv_phys[s] * rs + tile_off + ch * 16);
     });
-    uint4 *tg = tab + (g * 16) * kSolveCW + ch;
-#pragma unroll
-    for (int v = 0; v < 16; v++) tg[v * kSolveCW] = e[v];
+  }
+  for (uint32_t it = tid; it < (uint32_t)LPARTS * cwt; it += T) {
+    uint32_t ch = it % cwt, part = it / cwt;
+    build_table_part<EXP, LASTBITS>(tab + (size_t)((NG - 1) << KB) * CW + ch, CW, (NG - 1) * KB, nbasis, part,
+                                    [&](uint32_t s) {
+      return *reinterpret_cast<const uint4 *>(base + (size_t)piv_phys[s] * rs + tile_off + ch * 16);
+    });
   }
   __syncthreads();
-  // (c) stream every row's tile:  row ^= XOR_g tab[g][nibble_g(V[row])]
-  const uint32_t items = rows * kSolveCW;
-  constexpr int RU = 4;
+  // (b) stream every row's tile:  row ^= XOR_g tab[g][bits_g(V[row])]
+  // Software pipelined in registers: the global loads (and V) of batch n+1 are in
+  // flight while batch n does its NG table look-ups.
+  const uint32_t items = rows * CW;
+  constexpr int RU = 2;
+  struct Item {
+    uint4 x;
+    PanelVec<NBW> v;
+    uint8_t *p;
+    bool live;
+  };
+  auto fetch = [&](uint32_t it) {
+    Item m;
+    uint32_t r = it / CW, ch = it % CW;
+    m.live = (it < items) && (ch < cwt);
+    m.v = ldv<NBW>(V + (m.live ? r : 0) * NBW);
+    uint32_t any = 0;
+#pragma unroll
+    for (int w = 0; w < NBW; w++) any |= m.v.w[w];
+    m.live = m.live && (any != 0);
+    m.p = base + (size_t)r * rs + tile_off + ch * 16;
+    m.x = make_uint4(0, 0, 0, 0);
+    if (m.live) m.x = *reinterpret_cast<const uint4 *>(m.p);
+    return m;
+  };
+  const uint4 *tc = tab + (tid % CW);  // T % CW == 0: every item of this thread has ch = tid % CW
+  auto apply = [&](Item &m) {
+    if (!m.live) return;
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+      const int bits = (g == NG - 1) ? LASTBITS : KB;
+      uint32_t idx = get_bits<NBW>(m.v, g * KB, bits);
+      m.x = xor4(m.x, tc[(size_t)((g << KB) + idx) * CW]);
+    }
+    *reinterpret_cast<uint4 *>(m.p) = m.x;
+  };
+  Item c0 = fetch(tid), c1 = fetch(tid + T);
   for (uint32_t it0 = tid; it0 < items; it0 += T * RU) {
-    uint4 x[RU];
-    uint8_t *ptr[RU];
-    PanelVec<NBW> vv[RU];
-    bool live[RU];
-#pragma unroll
-    for (int k = 0; k < RU; k++) {
-      uint32_t it = it0 + k * T;
-      uint32_t r = it >> 4, ch = it & 15;
-      live[k] = (it < items) && (ch < cwt);
-      uint32_t any = 0;
-      if (live[k]) {
-        vv[k] = ldv<NBW>(V + r * NBW);
-#pragma unroll
-        for (int w = 0; w < NBW; w++) any |= vv[k].w[w];
-      }
-      live[k] = live[k] && (any != 0);
-      ptr[k] = base + (size_t)r * rs + tile_off + ch * 16;
-      if (live[k]) x[k] = *reinterpret_cast<const uint4 *>(ptr[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < RU; k++) {
-      if (!live[k]) continue;
-      uint32_t ch = (it0 + k * T) & 15;
-      const uint4 *tc = tab + ch;
-      if (ngrp == NGRP) {
-#pragma unroll
-        for (int g = 0; g < NGRP; g++) {
-          uint32_t nib = (vv[k].w[g >> 3] >> (4 * (g & 7))) & 15u;
-          x[k] = xor4(x[k], tc[(g * 16 + nib) * kSolveCW]);
-        }
-      } else {
-        for (uint32_t g = 0; g < ngrp; g++) {
-          uint32_t word = vv[k].w[0];
-#pragma unroll
-          for (int w = 1; w < NBW; w++)
-            if ((g >> 3) == (uint32_t)w) word = vv[k].w[w];
-          uint32_t nib = (word >> (4 * (g & 7))) & 15u;
-          x[k] = xor4(x[k], tc[(g * 16 + nib) * kSolveCW]);
-        }
-      }
-      *reinterpret_cast<uint4 *>(ptr[k]) = x[k];
-    }
+    Item n0 = fetch(it0 + T * RU), n1 = fetch(it0 + T * RU + T);
+    apply(c0);
+    apply(c1);
+    c0 = n0;
+    c1 = n1;
   }
   __syncthreads();  // tables are rebuilt by the next tile
 }
@@ -264,17 +293,18 @@ OB2_D void permute_rows(uint8_t *base, size_t rs, uint32_t rows, uint32_t nbytes
   }
 }
 
-template <int EXP, int NBW>
+template <int EXP, int NBW, int KB, int WT>
 __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
-  using SM = SolveSmem<EXP, NBW>;
-  constexpr int NB = SM::NB, NPIV = SM::NPIV, NGRP = SM::NGRP;
+  using SM = SolveSmem<EXP, NBW, KB, WT>;
+  using G = Geo<NBW, KB, WT>;
+  constexpr int NB = SM::NB, NPIV = SM::NPIV;
   constexpr uint32_t EMASK = (1u << EXP) - 1u;
   const uint32_t tid = threadIdx.x, T = blockDim.x;
   const uint32_t rows = p.rows;
 
   OB2_DYN_SMEM(smem_raw);
   unsigned char *sp = smem_raw;
-  uint4 *tab = reinterpret_cast<uint4 *>(sp);              sp += (size_t)NGRP * 16 * kSolveWT;
+  uint4 *tab = reinterpret_cast<uint4 *>(sp);              sp += G::TAB_BYTES;
   uint32_t *pan = reinterpret_cast<uint32_t *>(sp);        sp += (size_t)rows * NBW * 4;
   uint32_t *V = reinterpret_cast<uint32_t *>(sp);          sp += (size_t)rows * NBW * 4;
   sp = smem_raw + (((size_t)(sp - smem_raw) + 15) & ~(size_t)15);
@@ -284,9 +314,25 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
   uint32_t *vrow = reinterpret_cast<uint32_t *>(sp);       sp += (size_t)EXP * NBW * 4;   // x^b * its V
   uint32_t *scal = reinterpret_cast<uint32_t *>(sp);       // [0] search result, [1] flag
 
+  // phase clock (diagnostics only): 0 panel load, 1 panel factorisation, 2 trailing update,
+  // 3 final permutation / bookkeeping
+  long long t_last = 0;
+  unsigned long long acc_phase[4] = {0, 0, 0, 0};
+  auto tick = [&](int ph) {
+#ifndef OB2_EMU
+    if (p.phase && tid == 0) {
+      long long now = clock64();
+      acc_phase[ph] += (unsigned long long)(now - t_last);
+      t_last = now;
+    }
+#endif
+  };
+#ifndef OB2_EMU
+  if (p.phase && tid == 0) t_last = clock64();
+#endif
   const uint32_t npanels = (p.cols * EXP + NB - 1) / NB;
   // staging area of the final row permutation: tables + panel + V (all dead then)
-  const uint32_t stage_bytes = (uint32_t)NGRP * 16 * kSolveWT + rows * NBW * 8;
+  const uint32_t stage_bytes = (uint32_t)G::TAB_BYTES + rows * NBW * 8;
 
   for (uint32_t sys = blockIdx.x; sys < p.nsys; sys += gridDim.x) {
     uint8_t *A = p.a_ptrs ? reinterpret_cast<uint8_t *>(p.a_ptrs[sys]) : p.A + (size_t)sys * p.a_ss;
@@ -309,6 +355,7 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
         }
       }
       __syncthreads();
+      tick(0);
       // ---- panel factorisation --------------------------------------------
       uint32_t n = 0;
       for (uint32_t j = 0; j < ncols_p && t < rows; j++) {
@@ -389,6 +436,7 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
         n++;
         t++;
       }
+      tick(1);
       if (n == 0) continue;  // no pivot in this panel: nothing to update
       // pivot rows: cancel their own base term (new = V*P_old, not old ^ V*P_old)
       for (uint32_t s = tid; s < n; s += T) {
@@ -400,15 +448,16 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
       // (rounded down to a 16-byte boundary; bytes left of the panel only see
       //  zeros of the pivot rows there, so touching them again changes nothing)
       const uint32_t a_from = (pi * (NBW * 4)) & ~15u;
-      for (uint32_t off = a_from; off < p.a_bytes; off += kSolveWT) {
-        uint32_t w = (p.a_bytes - off < (uint32_t)kSolveWT) ? (p.a_bytes - off) : (uint32_t)kSolveWT;
-        update_tile<EXP, NBW>(A, p.a_rs, rows, off, w, n, piv_phys, V, tab);
+      for (uint32_t off = a_from; off < p.a_bytes; off += WT) {
+        uint32_t w = (p.a_bytes - off < (uint32_t)WT) ? (p.a_bytes - off) : (uint32_t)WT;
+        update_tile<EXP, NBW, KB, WT>(A, p.a_rs, rows, off, w, n, piv_phys, V, tab);
       }
       if (B)
-        for (uint32_t off = 0; off < p.b_bytes; off += kSolveWT) {
-          uint32_t w = (p.b_bytes - off < (uint32_t)kSolveWT) ? (p.b_bytes - off) : (uint32_t)kSolveWT;
-          update_tile<EXP, NBW>(B, p.b_rs, rows, off, w, n, piv_phys, V, tab);
+        for (uint32_t off = 0; off < p.b_bytes; off += WT) {
+          uint32_t w = (p.b_bytes - off < (uint32_t)WT) ? (p.b_bytes - off) : (uint32_t)WT;
+          update_tile<EXP, NBW, KB, WT>(B, p.b_rs, rows, off, w, n, piv_phys, V, tab);
         }
+      tick(2);
     }
     // ---- results ------------------------------------------------------------
     if (tid == 0) {
@@ -425,17 +474,24 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
       if (B) permute_rows(B, p.b_rs, rows, p.b_bytes, pos2phys, tab, stage_bytes);
     }
     __syncthreads();
+    tick(3);
   }
+#ifndef OB2_EMU
+  if (p.phase && tid == 0)
+    for (int k = 0; k < 4; k++) atomicAdd(p.phase + k, acc_phase[k]);
+#endif
 }
 
 // rows limit: shared memory (SolveSmem::bytes <= 227 KB) and the u16 row map.
-template <int EXP, int NBW>
+template <int EXP, int NBW, int KB, int WT>
 inline int launch_solve_t(const SolveArgs &p, uint32_t grid, uint32_t threads,
                           size_t smem_limit, cudaStream_t s) {
-  size_t smem = SolveSmem<EXP, NBW>::bytes(p.rows);
-  size_t stage = (size_t)SolveSmem<EXP, NBW>::NGRP * 16 * kSolveWT + (size_t)p.rows * NBW * 8;
+  using SM = SolveSmem<EXP, NBW, KB, WT>;
+  size_t smem = SM::bytes(p.rows);
+  size_t stage = SM::G::TAB_BYTES + (size_t)p.rows * NBW * 8;
   if (smem > smem_limit || p.rows > 65535u || p.rows == 0 || stage / p.rows < 16) return -1;
-  auto k = solve_kernel<EXP, NBW>;
+  if (threads % SM::G::CW) return -3;
+  auto k = solve_kernel<EXP, NBW, KB, WT>;
 #ifndef OB2_EMU
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return -2;
@@ -444,28 +500,35 @@ inline int launch_solve_t(const SolveArgs &p, uint32_t grid, uint32_t threads,
   return 0;
 }
 
-// field = OB2_GF2 .. OB2_GF256.  Picks the widest panel that fits shared memory.
-inline int launch_solve(int field, const SolveArgs &p, uint32_t grid, uint32_t threads,
-                        size_t smem_limit, cudaStream_t s) {
-  int rc = -1;
-  switch (field) {
-  case OB2_GF256:
-    rc = launch_solve_t<8, 4>(p, grid, threads, smem_limit, s);
-    if (rc == -1) rc = launch_solve_t<8, 2>(p, grid, threads, smem_limit, s);
-    break;
-  case OB2_GF16:
-    rc = launch_solve_t<4, 4>(p, grid, threads, smem_limit, s);
-    if (rc == -1) rc = launch_solve_t<4, 2>(p, grid, threads, smem_limit, s);
-    break;
-  case OB2_GF4:
-    rc = launch_solve_t<2, 4>(p, grid, threads, smem_limit, s);
-    if (rc == -1) rc = launch_solve_t<2, 2>(p, grid, threads, smem_limit, s);
-    break;
-  case OB2_GF2:
-    rc = launch_solve_t<1, 4>(p, grid, threads, smem_limit, s);
-    if (rc == -1) rc = launch_solve_t<1, 2>(p, grid, threads, smem_limit, s);
-    break;
+// table geometry: 0 = 4-bit groups / 256-byte tiles, 1 = 6-bit / 128, 2 = 7-bit / 64
+template <int EXP, int NBW>
+inline int launch_solve_geo(int geo, const SolveArgs &p, uint32_t grid, uint32_t threads,
+                            size_t smem_limit, cudaStream_t s) {
+  switch (geo) {
+  case 1: return launch_solve_t<EXP, NBW, 6, 128>(p, grid, threads, smem_limit, s);
+  case 2: return launch_solve_t<EXP, NBW, 7, 64>(p, grid, threads, smem_limit, s);
+  default: return launch_solve_t<EXP, NBW, 4, 256>(p, grid, threads, smem_limit, s);
   }
+}
+
+// field = OB2_GF2 .. OB2_GF256.  geo < 0: default geometry for the field.  Picks the
+// widest panel that fits shared memory (128-bit panels, then 64-bit, then 4-bit groups).
+inline int launch_solve(int field, int geo, const SolveArgs &p, uint32_t grid, uint32_t threads,
+                        size_t smem_limit, cudaStream_t s) {
+  if (geo < 0) geo = 1;
+  int rc = -1;
+#define OB2_TRY(E)                                                                     \
+  rc = launch_solve_geo<E, 4>(geo, p, grid, threads, smem_limit, s);                   \
+  if (rc == -1) rc = launch_solve_geo<E, 2>(geo, p, grid, threads, smem_limit, s);     \
+  if (rc == -1 && geo != 0) rc = launch_solve_geo<E, 4>(0, p, grid, threads, smem_limit, s); \
+  if (rc == -1 && geo != 0) rc = launch_solve_geo<E, 2>(0, p, grid, threads, smem_limit, s);
+  switch (field) {
+  case OB2_GF256: OB2_TRY(8) break;
+  case OB2_GF16: OB2_TRY(4) break;
+  case OB2_GF4: OB2_TRY(2) break;
+  case OB2_GF2: OB2_TRY(1) break;
+  }
+#undef OB2_TRY
   return rc;
 }
 

@@ -106,7 +106,7 @@ int emu_fastdiv_check(uint32_t d, uint32_t nmax, uint32_t step) {
 int emu_solve(int field, uint8_t *A, size_t a_rs, size_t a_ss, uint32_t rows, uint32_t cols,
               uint32_t a_bytes, uint8_t *B, size_t b_rs, size_t b_ss, uint32_t b_bytes,
               int32_t *rank, uint32_t *pivcols, uint32_t nsys, uint32_t grid, uint32_t threads,
-              size_t smem_limit, int force_nbw) {
+              size_t smem_limit, int force_nbw, int geo) {
   ensure_sets();
   SolveArgs p;
   memset(&p, 0, sizeof p);
@@ -117,23 +117,23 @@ int emu_solve(int field, uint8_t *A, size_t a_rs, size_t a_ss, uint32_t rows, ui
   p.inv = ts >= 0 ? g_sets[ts].inv : nullptr;
   if (force_nbw == 2) {
     switch (field) {
-    case OB2_GF256: return launch_solve_t<8, 2>(p, grid, threads, smem_limit, nullptr);
-    case OB2_GF16: return launch_solve_t<4, 2>(p, grid, threads, smem_limit, nullptr);
-    case OB2_GF4: return launch_solve_t<2, 2>(p, grid, threads, smem_limit, nullptr);
-    case OB2_GF2: return launch_solve_t<1, 2>(p, grid, threads, smem_limit, nullptr);
+    case OB2_GF256: return launch_solve_geo<8, 2>(geo, p, grid, threads, smem_limit, nullptr);
+    case OB2_GF16: return launch_solve_geo<4, 2>(geo, p, grid, threads, smem_limit, nullptr);
+    case OB2_GF4: return launch_solve_geo<2, 2>(geo, p, grid, threads, smem_limit, nullptr);
+    case OB2_GF2: return launch_solve_geo<1, 2>(geo, p, grid, threads, smem_limit, nullptr);
     }
   }
-  return launch_solve(field, p, grid, threads, smem_limit, nullptr);
+  return launch_solve(field, geo, p, grid, threads, smem_limit, nullptr);
 }
 
 int emu_apply(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, const uint8_t *D,
               size_t d_stride, uint8_t *Y, size_t y_stride, uint32_t nbytes, int accumulate,
-              uint32_t threads) {
+              uint32_t threads, int geo) {
   ApplyArgs p;
   memset(&p, 0, sizeof p);
   p.C = C; p.c_stride = c_stride; p.M = M; p.Kc = Kc; p.D = D; p.d_stride = d_stride;
   p.Y = Y; p.y_stride = y_stride; p.nbytes = nbytes; p.accumulate = accumulate;
-  return launch_apply(p, threads, nullptr);
+  return launch_apply(p, geo, threads, nullptr);
 }
 
 }  // extern "C"

@@ -95,7 +95,7 @@ def test_swap_and_b32():
     assert np.array_equal(A0, A1)
 
 
-def _solve(field, rows, cols, b_bytes, seed, nsys=1, deficient=0, threads=64, grid=1, nbw=0):
+def _solve(field, rows, cols, b_bytes, seed, nsys=1, deficient=0, threads=64, grid=1, nbw=0, geo=-1):
     e = emu()
     A = np.stack([random_matrix(field, rows, cols, seed + 2 * s, rank_deficient=deficient) for s in range(nsys)])
     B = np.stack([splitmix_bytes(seed + 2 * s + 1, rows * b_bytes).reshape(rows, b_bytes)
@@ -107,7 +107,7 @@ def _solve(field, rows, cols, b_bytes, seed, nsys=1, deficient=0, threads=64, gr
     rc = e.emu_solve(field, ptr(A), A.strides[1], A.strides[0], rows, cols, A.shape[2],
                      ptr(B) if B is not None else None, B.strides[1] if B is not None else 0,
                      B.strides[0] if B is not None else 0, B.shape[2] if B is not None else 0,
-                     ptr(rank, i32p), ptr(piv, u32p), nsys, grid, threads, SMEM, nbw)
+                     ptr(rank, i32p), ptr(piv, u32p), nsys, grid, threads, SMEM, nbw, geo)
     assert rc == 0
     assert [int(r) for r in rank] == [w[0] for w in want]
     for s in range(nsys):
@@ -142,8 +142,9 @@ def _solve(field, rows, cols, b_bytes, seed, nsys=1, deficient=0, threads=64, gr
     dict(field=GF256, rows=1, cols=1, b_bytes=16, seed=122),
     dict(field=GF256, rows=5, cols=700, b_bytes=16, seed=123),
 ])
-def test_solve(args):
-    _solve(**args)
+@pytest.mark.parametrize("geo", [0, 1, 2])
+def test_solve(args, geo):
+    _solve(geo=geo, **args)
 
 
 def test_solve_zero_and_identity():
@@ -153,7 +154,7 @@ def test_solve_zero_and_identity():
         A = random_matrix(field, rows, cols, 1) * 0
         rank = np.zeros(1, dtype=np.int32)
         rc = e.emu_solve(field, ptr(A), A.strides[0], A.nbytes, rows, cols, A.shape[1], None, 0, 0, 0,
-                         ptr(rank, i32p), None, 1, 1, 64, SMEM, 0)
+                         ptr(rank, i32p), None, 1, 1, 64, SMEM, 0, -1)
         assert rc == 0 and rank[0] == 0 and not A.any()
 
 
@@ -171,5 +172,7 @@ def test_apply():
         o.orc_gf256_apply(ptr(Cm), cs, M, Kc, ptr(D), nbytes, ptr(Y0), nbytes, nbytes)
         if acc:
             Y0 ^= prev
-        assert e.emu_apply(ptr(Cm), cs, M, Kc, ptr(D), nbytes, ptr(Y1), nbytes, nbytes, acc, threads) == 0
-        assert np.array_equal(Y0, Y1)
+        for geo in (0, 1, 2):
+            Y2 = Y1.copy()
+            assert e.emu_apply(ptr(Cm), cs, M, Kc, ptr(D), nbytes, ptr(Y2), nbytes, nbytes, acc, threads, geo) == 0
+            assert np.array_equal(Y0, Y2), geo

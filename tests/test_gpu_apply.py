@@ -10,9 +10,13 @@ from oblas_b200 import capi, device
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", autouse=True)
-def _bind(cuda_lib):
+@pytest.fixture(scope="module", autouse=True, params=[-1, 0, 1, 2], ids=["geo_default", "geo4x256", "geo6x128", "geo7x64"])
+def _bind(cuda_lib, request):
+    """every test of this module runs once per Four-Russians table geometry"""
     device.bind(0)
+    cuda_lib.oblas_b200_set_tuning(request.param, request.param)
+    yield
+    cuda_lib.oblas_b200_set_tuning(-1, -1)
 
 
 @pytest.mark.parametrize("M,Kc,nbytes,cs", [(10, 10, 32, 16), (40, 37, 272, 48), (300, 100, 512, 112),

@@ -105,14 +105,17 @@ if __name__ == "__main__":
     out(gpu=torch.cuda.get_device_name(0), sms=capi.lib().oblas_b200_sm_count())
     if "rowops" in which:
         rowops()
-    if "solve" in which:
-        solve(GF256, 1024, 1280, 148)
-        solve(GF256, 1024, 1280, 592)
-        solve(GF256, 256, 1280, 592)
-        solve(GF16, 2048, 0, 148)
-        solve(GF4, 2048, 0, 148)
-        solve(GF2, 2048, 0, 148)
-        solve(GF2, 8192, 0, 37)
-    if "apply" in which:
-        apply(2048, 2048, 65536)
-        apply(10000, 10000, 8192)
+    geos = [int(x) for x in os.environ.get("GEOS", "0,1,2").split(",")]
+    for geo in geos:
+        capi.lib().oblas_b200_set_tuning(geo, geo)
+        out(geo=geo)
+        if "solve" in which:
+            solve(GF256, 1024, 1280, 592)
+            solve(GF256, 256, 1280, 592)
+            solve(GF16, 2048, 0, 148)
+            solve(GF4, 2048, 0, 148)
+            solve(GF2, 2048, 0, 148)
+            solve(GF2, 8192, 0, 37)
+        if "apply" in which:
+            apply(2048, 2048, 65536)
+            apply(10000, 10000, 8192)
