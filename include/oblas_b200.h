@@ -80,6 +80,9 @@ void oblas_b200_set_async(int async);
  * measurements): 0 = 4-bit groups, 256-byte tiles; 1 = 6-bit groups, 128-byte tiles;
  * 2 = 7-bit groups, 64-byte tiles; -1 = library default.  Results are identical. */
 void oblas_b200_set_tuning(int solve_geo, int apply_geo);
+/* diagnostics/tests: general_only != 0 disables the register-resident fast panel
+ * factorisation (identical results, slower) */
+void oblas_b200_set_panel_path(int general_only);
 /* diagnostics: enable != 0 starts per-phase cycle counters of the elimination kernel
  * (panel load, panel factorisation, trailing update, permutation; SM cycles summed
  * over CTAs); out (may be NULL) receives the 4 counters collected so far */

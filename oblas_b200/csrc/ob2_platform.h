@@ -19,6 +19,13 @@
   kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
 
+// barrier over the first `nthreads` threads of the block (multiple of 32), id 1..15
+#ifndef OB2_EMU
+#define OB2_NAMED_BAR(id, nthreads) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory")
+#else
+#define OB2_NAMED_BAR(id, nthreads) emu::named_bar((id), (nthreads))
+#endif
+
 #define OB2_HD __host__ __device__ __forceinline__
 #define OB2_D __device__ __forceinline__
 

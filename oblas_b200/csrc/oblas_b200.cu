@@ -37,6 +37,7 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   bool async = false;
   int solve_geo = -1, apply_geo = -1;  // table geometry overrides (-1 = default)
+  int no_fast_panel = 0;               // diagnostics: general panel path only
   unsigned long long *d_phase = nullptr;  // solve-kernel phase counters (diagnostics)
   DevTableSet *d_sets = nullptr;  // [TS_COUNT] in device memory
   DevTableSet h_sets[TS_COUNT];
@@ -228,6 +229,7 @@ int oblas_b200_sync(void) {
   return 0;
 }
 void oblas_b200_set_async(int async) { g.async = async != 0; }
+void oblas_b200_set_panel_path(int general_only) { g.no_fast_panel = general_only != 0; }
 void oblas_b200_set_tuning(int solve_geo, int apply_geo) {
   g.solve_geo = solve_geo;
   g.apply_geo = apply_geo;
@@ -432,6 +434,7 @@ static int solve_common(int field, SolveArgs &p, size_t nsys) {
   p.inv = ts >= 0 ? g.d_sets[ts].inv : nullptr;
   p.nsys = (uint32_t)nsys;
   p.phase = g.d_phase;
+  p.no_fast_panel = g.no_fast_panel;
   uint32_t grid = nsys < (size_t)g.sm_count ? (uint32_t)nsys : (uint32_t)g.sm_count;
   int rc = launch_solve(field, g.solve_geo, p, grid, 512, g.smem_optin, g.stream);
   if (rc == -1)

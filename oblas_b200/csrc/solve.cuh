@@ -56,6 +56,7 @@ struct SolveArgs {
   const unsigned long long *a_ptrs, *b_ptrs;
   // optional diagnostics: cycles spent per phase, summed over CTAs (8 counters)
   unsigned long long *phase;
+  int no_fast_panel;  // diagnostics/tests: always use the general column-by-column panel path
 };
 
 // Tile / table geometry.  NB = 32*NBW panel bits are cut into groups of KB bits
@@ -194,7 +195,7 @@ OB2_D void build_table_part(uint4 *tg /* entry 0 of table g, this chunk */, int 
 template <int EXP, int NBW, int KB, int WT>
 OB2_D void update_tile(uint8_t *base, size_t rs, uint32_t rows, uint32_t tile_off,
                        uint32_t tile_bytes, uint32_t npiv, const uint16_t *piv_phys,
-                       const uint32_t *V, uint4 *tab) {
+                       const uint32_t *V, uint4 *tab, uint32_t *pan_next, uint32_t pan_off) {
   using G = Geo<NBW, KB, WT>;
   constexpr int CW = G::CW, NG = G::NG, LASTBITS = G::LASTBITS;
   constexpr int PARTS = 1 << (KB - 4);                 // threads per (table, chunk)
@@ -228,32 +229,48 @@ OB2_D void update_tile(uint8_t *base, size_t rs, uint32_t rows, uint32_t tile_of
     uint4 x;
     PanelVec<NBW> v;
     uint8_t *p;
-    bool live;
+    uint32_t r;
+    bool live, upd;
   };
+  // T % CW == 0: every item of this thread has the same chunk ch = tid % CW.  The lane whose
+  // chunk holds the NEXT panel's bytes also writes the updated chunk into the shared-memory
+  // panel, so the next panel factorisation starts without a global gather.
+  const uint32_t my_ch = tid % CW;
+  const bool pan_lane = pan_next != nullptr && pan_off >= tile_off + my_ch * 16 &&
+                        pan_off < tile_off + my_ch * 16 + 16 && pan_off < tile_off + tile_bytes;
   auto fetch = [&](uint32_t it) {
     Item m;
-    uint32_t r = it / CW, ch = it % CW;
-    m.live = (it < items) && (ch < cwt);
-    m.v = ldv<NBW>(V + (m.live ? r : 0) * NBW);
+    m.r = it / CW;
+    m.live = (it < items) && (my_ch < cwt);
+    m.v = ldv<NBW>(V + (m.live ? m.r : 0) * NBW);
     uint32_t any = 0;
 #pragma unroll
     for (int w = 0; w < NBW; w++) any |= m.v.w[w];
-    m.live = m.live && (any != 0);
-    m.p = base + (size_t)r * rs + tile_off + ch * 16;
+    m.upd = m.live && (any != 0);
+    m.p = base + (size_t)m.r * rs + tile_off + my_ch * 16;
     m.x = make_uint4(0, 0, 0, 0);
-    if (m.live) m.x = *reinterpret_cast<const uint4 *>(m.p);
+    if (m.upd || (m.live && pan_lane)) m.x = *reinterpret_cast<const uint4 *>(m.p);
     return m;
   };
-  const uint4 *tc = tab + (tid % CW);  // T % CW == 0: every item of this thread has ch = tid % CW
+  const uint4 *tc = tab + my_ch;
   auto apply = [&](Item &m) {
-    if (!m.live) return;
+    if (m.upd) {
 #pragma unroll
-    for (int g = 0; g < NG; g++) {
-      const int bits = (g == NG - 1) ? LASTBITS : KB;
-      uint32_t idx = get_bits<NBW>(m.v, g * KB, bits);
-      m.x = xor4(m.x, tc[(size_t)((g << KB) + idx) * CW]);
+      for (int g = 0; g < NG; g++) {
+        const int bits = (g == NG - 1) ? LASTBITS : KB;
+        uint32_t idx = get_bits<NBW>(m.v, g * KB, bits);
+        m.x = xor4(m.x, tc[(size_t)((g << KB) + idx) * CW]);
+      }
+      *reinterpret_cast<uint4 *>(m.p) = m.x;
     }
-    *reinterpret_cast<uint4 *>(m.p) = m.x;
+    if (pan_lane && m.live) {
+      if (NBW == 4) {
+        *reinterpret_cast<uint4 *>(pan_next + m.r * NBW) = m.x;
+      } else {  // 8-byte panels: lower or upper half of the chunk
+        uint2 h = (pan_off & 8) ? make_uint2(m.x.z, m.x.w) : make_uint2(m.x.x, m.x.y);
+        *reinterpret_cast<uint2 *>(pan_next + m.r * NBW) = h;
+      }
+    }
   };
   Item c0 = fetch(tid), c1 = fetch(tid + T);
   for (uint32_t it0 = tid; it0 < items; it0 += T * RU) {
@@ -291,6 +308,173 @@ OB2_D void permute_rows(uint8_t *base, size_t rs, uint32_t rows, uint32_t nbytes
     }
     __syncthreads();
   }
+}
+
+// select word `wi` (run-time) of a register-resident panel vector without dynamic indexing
+template <int NBW>
+OB2_D uint32_t pick_word(const PanelVec<NBW> &v, uint32_t wi) {
+  uint32_t w = v.w[0];
+#pragma unroll
+  for (int k = 1; k < NBW; k++)
+    if (wi == (uint32_t)k) w = v.w[k];
+  return w;
+}
+
+// ---------------------------------------------------------------------------
+// Fast panel factorisation.  The canonical pivot of column j is the lowest row
+// position >= t+j with a non-zero entry; for all but a vanishing fraction of
+// panels every pivot lies among the first NPIV+32 positions.  Those candidate rows
+// are eliminated in REGISTERS by the first NBT threads (named barrier, the other
+// warps wait), which yields the pivots and their coefficient vectors; V of every
+// other row is then one GF(2) matrix-vector product  V[r] = pan[r] * M, done with
+// 4-bit Four-Russians tables built from the pivots' vectors.  Returns false (and
+// changes nothing but scratch) if some column has no pivot among the candidates;
+// the caller then runs the general column-by-column path.
+// ---------------------------------------------------------------------------
+template <int EXP, int NBW>
+OB2_D bool panel_fast(uint32_t *pan, uint32_t *V, uint16_t *pos2phys, uint16_t *piv_phys,
+                      uint32_t *prow, uint32_t *vrow, uint32_t *scal, uint32_t *scratch,
+                      uint32_t t, uint32_t rows, uint32_t c0, uint32_t *pivcols_sys,
+                      const uint8_t *inv_tab) {
+  constexpr int NB = 32 * NBW, NPIV = NB / EXP;
+  constexpr uint32_t EMASK = (1u << EXP) - 1u;
+  constexpr uint32_t NBT = (uint32_t)((NPIV + 32 + 31) / 32 * 32);  // threads in the candidate group
+  constexpr uint32_t NONE = 0xffffffffu;
+  const uint32_t tid = threadIdx.x, T = blockDim.x;
+  const uint32_t ncand = (rows - t < NBT) ? (rows - t) : NBT;      // candidate rows
+  uint32_t *Mb = scratch;                       // [NB][NBW]  x^b * (vector of the pivot of column m/EXP)
+  uint32_t *T2 = scratch + NB * NBW;            // [NB/4][16][NBW]
+  if (tid == 0) {
+    scal[0] = NONE;  // search slots, alternating per column
+    scal[1] = NONE;
+    scal[2] = 0;     // fail flag
+  }
+  __syncthreads();
+  const bool have = tid < ncand && tid < NBT;
+  uint32_t phys = 0;
+  int my_col = -1;  // column this row became the pivot of
+  PanelVec<NBW> E;
+#pragma unroll
+  for (int w = 0; w < NBW; w++) E.w[w] = 0;
+  if (tid < NBT) {
+    uint32_t mypos = tid;  // position offset inside the candidate set
+    phys = have ? pos2phys[t + tid] : 0;
+    PanelVec<NBW> blk;
+#pragma unroll
+    for (int w = 0; w < NBW; w++) blk.w[w] = have ? pan[phys * NBW + w] : 0;
+    bool failed = false;
+    for (uint32_t j = 0; j < (uint32_t)NPIV; j++) {
+      const uint32_t wj = (j * EXP) >> 5, sh = (j * EXP) & 31;
+      const uint32_t e = (pick_word<NBW>(blk, wj) >> sh) & EMASK;
+      if (have && mypos >= j && e) atomicMin(&scal[j & 1], mypos);
+      OB2_NAMED_BAR(1, NBT);
+      const uint32_t pv = scal[j & 1];
+      if (pv == NONE) {  // no pivot among the candidates (uniform over the group)
+        failed = true;
+        break;
+      }
+      const bool is_piv = have && mypos == pv;
+      if (have) {
+        if (is_piv) mypos = j;
+        else if (mypos == j) mypos = pv;
+      }
+      if (is_piv) {
+        my_col = (int)j;
+        const uint32_t inv = (EXP == 1) ? 1u : (uint32_t)__ldg(inv_tab + e);
+        // content = inv*(own old row) ^ inv*E*P_old : the own base moves into slot j
+#pragma unroll
+        for (int w = 0; w < NBW; w++) {
+          uint32_t unit = (((j * EXP) >> 5) == (uint32_t)w) ? (1u << ((j * EXP) & 31)) : 0u;
+          blk.w[w] = mul_scalar_word<EXP>(blk.w[w], inv);
+          E.w[w] = mul_scalar_word<EXP>(E.w[w] ^ unit, inv);
+          uint32_t a = blk.w[w], b = E.w[w];
+#pragma unroll
+          for (int q = 0; q < EXP; q++) {
+            prow[q * NBW + w] = a;
+            vrow[q * NBW + w] = b;
+            a = xtime<EXP>(a);
+            b = xtime<EXP>(b);
+          }
+        }
+        scal[(j + 1) & 1] = NONE;  // re-arm the slot of the next column
+      }
+      OB2_NAMED_BAR(1, NBT);
+      if (have && !is_piv) {
+        const uint32_t f = (pick_word<NBW>(blk, wj) >> sh) & EMASK;
+        if (f) {
+#pragma unroll
+          for (int q = 0; q < EXP; q++) {
+            uint32_t m = 0u - ((f >> q) & 1u);
+            PanelVec<NBW> pb = ldv<NBW>(prow + q * NBW), vb = ldv<NBW>(vrow + q * NBW);
+#pragma unroll
+            for (int w = 0; w < NBW; w++) {
+              blk.w[w] ^= m & pb.w[w];
+              E.w[w] ^= m & vb.w[w];
+            }
+          }
+        }
+      }
+    }
+    if (failed) {
+      if (tid == 0) scal[2] = 1;
+    } else if (have) {
+      pos2phys[t + mypos] = (uint16_t)phys;  // row map: the candidate window is permuted
+      if (my_col >= 0) {
+        piv_phys[my_col] = (uint16_t)phys;
+        if (pivcols_sys) pivcols_sys[t + my_col] = c0 + (uint32_t)my_col;
+        PanelVec<NBW> x = E;
+#pragma unroll
+        for (int q = 0; q < EXP; q++) {
+          stv<NBW>(Mb + ((uint32_t)my_col * EXP + q) * NBW, x);
+#pragma unroll
+          for (int w = 0; w < NBW; w++) x.w[w] = xtime<EXP>(x.w[w]);
+        }
+      }
+    }
+  }
+  __syncthreads();                        // fail flag, Mb, row map visible
+  if (scal[2]) return false;
+  // 4-bit Four-Russians tables of the bit matrix M
+  for (uint32_t it = tid; it < (uint32_t)(NB / 4) * 16; it += T) {
+    uint32_t g = it >> 4, v = it & 15;
+    PanelVec<NBW> acc;
+#pragma unroll
+    for (int w = 0; w < NBW; w++) acc.w[w] = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (v & (1u << k)) {
+        PanelVec<NBW> b = ldv<NBW>(Mb + (4 * g + k) * NBW);
+#pragma unroll
+        for (int w = 0; w < NBW; w++) acc.w[w] ^= b.w[w];
+      }
+    stv<NBW>(T2 + it * NBW, acc);
+  }
+  __syncthreads();
+  // V[r] = pan[r] * M for every row
+  for (uint32_t r = tid; r < rows; r += T) {
+    PanelVec<NBW> pr = ldv<NBW>(pan + r * NBW), acc;
+#pragma unroll
+    for (int w = 0; w < NBW; w++) acc.w[w] = 0;
+#pragma unroll
+    for (int g = 0; g < NB / 4; g++) {
+      uint32_t nib = (pr.w[g >> 3] >> (4 * (g & 7))) & 15u;
+      PanelVec<NBW> tv = ldv<NBW>(T2 + (g * 16 + nib) * NBW);
+#pragma unroll
+      for (int w = 0; w < NBW; w++) acc.w[w] ^= tv.w[w];
+    }
+    stv<NBW>(V + r * NBW, acc);
+  }
+  __syncthreads();
+  // pivot rows: new content = E * P_old, so cancel the own base term: V = E ^ e_col
+  if (my_col >= 0) {
+#pragma unroll
+    for (int w = 0; w < NBW; w++) {
+      uint32_t unit = ((((uint32_t)my_col * EXP) >> 5) == (uint32_t)w) ? (1u << (((uint32_t)my_col * EXP) & 31)) : 0u;
+      V[phys * NBW + w] = E.w[w] ^ unit;
+    }
+  }
+  __syncthreads();
+  return true;
 }
 
 template <int EXP, int NBW, int KB, int WT>
@@ -340,17 +524,18 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
                           : (p.B ? p.B + (size_t)sys * p.b_ss : nullptr);
     for (uint32_t r = tid; r < rows; r += T) pos2phys[r] = (uint16_t)r;
     uint32_t t = 0;  // pivots found so far == next pivot position (uniform)
+    bool pan_ready = false;  // panel already written into shared memory by the previous update
     __syncthreads();
 
     for (uint32_t pi = 0; pi < npanels && t < rows; pi++) {
       const uint32_t c0 = pi * NPIV;
       const uint32_t ncols_p = (p.cols - c0 < (uint32_t)NPIV) ? (p.cols - c0) : (uint32_t)NPIV;
-      // ---- load the panel, clear V ----------------------------------------
+      // ---- load the panel (unless the previous update wrote it through), clear V ----
       for (uint32_t r = tid; r < rows; r += T) {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(A + (size_t)r * p.a_rs + (size_t)pi * (NBW * 4));
 #pragma unroll
         for (int w = 0; w < NBW; w++) {
-          pan[r * NBW + w] = src[w];
+          if (!pan_ready) pan[r * NBW + w] = src[w];
           V[r * NBW + w] = 0;
         }
       }
@@ -358,7 +543,17 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
       tick(0);
       // ---- panel factorisation --------------------------------------------
       uint32_t n = 0;
-      for (uint32_t j = 0; j < ncols_p && t < rows; j++) {
+      constexpr uint32_t kFastThreads = (uint32_t)((NPIV + 32 + 31) / 32 * 32);
+      bool fast = false;
+      if (ncols_p == (uint32_t)NPIV && rows - t >= (uint32_t)NPIV && kFastThreads <= T && !p.no_fast_panel)
+        fast = panel_fast<EXP, NBW>(pan, V, pos2phys, piv_phys, prow, vrow, scal,
+                                    reinterpret_cast<uint32_t *>(tab), t, rows, c0,
+                                    p.pivcols ? p.pivcols + (size_t)sys * rows : nullptr, p.inv);
+      if (fast) {
+        n = NPIV;
+        t += NPIV;
+      }
+      for (uint32_t j = 0; !fast && j < ncols_p && t < rows; j++) {
         const uint32_t wj = (j * EXP) >> 5, sh = (j * EXP) & 31;
         uint32_t pos = t;
         uint32_t ph = pos2phys[t];
@@ -437,25 +632,31 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
         t++;
       }
       tick(1);
+      pan_ready = false;
       if (n == 0) continue;  // no pivot in this panel: nothing to update
       // pivot rows: cancel their own base term (new = V*P_old, not old ^ V*P_old)
-      for (uint32_t s = tid; s < n; s += T) {
-        uint32_t ph = piv_phys[s];
-        V[ph * NBW + ((s * EXP) >> 5)] ^= 1u << ((s * EXP) & 31);
+      if (!fast) {
+        for (uint32_t s = tid; s < n; s += T) {
+          uint32_t ph = piv_phys[s];
+          V[ph * NBW + ((s * EXP) >> 5)] ^= 1u << ((s * EXP) & 31);
+        }
+        __syncthreads();
       }
-      __syncthreads();
       // ---- trailing update: A from this panel's first byte, then all of B ----
       // (rounded down to a 16-byte boundary; bytes left of the panel only see
       //  zeros of the pivot rows there, so touching them again changes nothing)
       const uint32_t a_from = (pi * (NBW * 4)) & ~15u;
+      // the tile holding the next panel's bytes also refreshes the shared-memory panel
+      const uint32_t next_off = (pi + 1 < npanels) ? (pi + 1) * (NBW * 4) : 0xffffffffu;
       for (uint32_t off = a_from; off < p.a_bytes; off += WT) {
         uint32_t w = (p.a_bytes - off < (uint32_t)WT) ? (p.a_bytes - off) : (uint32_t)WT;
-        update_tile<EXP, NBW, KB, WT>(A, p.a_rs, rows, off, w, n, piv_phys, V, tab);
+        update_tile<EXP, NBW, KB, WT>(A, p.a_rs, rows, off, w, n, piv_phys, V, tab, pan, next_off);
       }
+      pan_ready = next_off != 0xffffffffu && next_off < p.a_bytes;
       if (B)
         for (uint32_t off = 0; off < p.b_bytes; off += WT) {
           uint32_t w = (p.b_bytes - off < (uint32_t)WT) ? (p.b_bytes - off) : (uint32_t)WT;
-          update_tile<EXP, NBW, KB, WT>(B, p.b_rs, rows, off, w, n, piv_phys, V, tab);
+          update_tile<EXP, NBW, KB, WT>(B, p.b_rs, rows, off, w, n, piv_phys, V, tab, nullptr, 0xffffffffu);
         }
       tick(2);
     }
@@ -467,7 +668,7 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
     __syncthreads();
     uint32_t moved = 0;
     for (uint32_t r = tid; r < rows; r += T) moved |= (pos2phys[r] != r);
-    if (moved) scal[1] = 1;
+    if (moved) atomicOr(&scal[1], 1u);
     __syncthreads();
     if (scal[1]) {
       permute_rows(A, p.a_rs, rows, p.a_bytes, pos2phys, tab, stage_bytes);

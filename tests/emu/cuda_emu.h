@@ -73,7 +73,13 @@ struct BlockState {
   Barrier bar;
   std::vector<WarpState *> warps;
   unsigned char *dyn_smem;
-  explicit BlockState(unsigned n) : bar(n), dyn_smem(nullptr) {}
+  std::mutex named_mu;
+  Barrier *named[16];
+  unsigned named_n[16];
+  explicit BlockState(unsigned n) : bar(n), dyn_smem(nullptr) {
+    for (int i = 0; i < 16; i++) { named[i] = nullptr; named_n[i] = 0; }
+  }
+  ~BlockState() { for (int i = 0; i < 16; i++) delete named[i]; }
 };
 
 extern thread_local BlockState *tl_block;
@@ -154,6 +160,22 @@ using std::min;
 
 namespace emu {
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body);
+// bar.sync id, nthreads : every participant passes the same nthreads
+static inline void named_bar(int id, unsigned nthreads) {
+  BlockState *b = tl_block;
+  Barrier *bar;
+  {
+    std::lock_guard<std::mutex> lk(b->named_mu);
+    if (!b->named[id] || b->named_n[id] != nthreads) {
+      // (a barrier is only re-created between uses, when no thread waits on it)
+      delete b->named[id];
+      b->named[id] = new Barrier(nthreads);
+      b->named_n[id] = nthreads;
+    }
+    bar = b->named[id];
+  }
+  bar->wait();
+}
 }
 
 #define OB2_LAUNCH(kernel, grid, block, smem, stream, ...)                      \

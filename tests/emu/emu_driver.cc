@@ -106,13 +106,14 @@ int emu_fastdiv_check(uint32_t d, uint32_t nmax, uint32_t step) {
 int emu_solve(int field, uint8_t *A, size_t a_rs, size_t a_ss, uint32_t rows, uint32_t cols,
               uint32_t a_bytes, uint8_t *B, size_t b_rs, size_t b_ss, uint32_t b_bytes,
               int32_t *rank, uint32_t *pivcols, uint32_t nsys, uint32_t grid, uint32_t threads,
-              size_t smem_limit, int force_nbw, int geo) {
+              size_t smem_limit, int force_nbw, int geo, int no_fast) {
   ensure_sets();
   SolveArgs p;
   memset(&p, 0, sizeof p);
   p.A = A; p.a_rs = a_rs; p.a_ss = a_ss; p.rows = rows; p.cols = cols; p.a_bytes = a_bytes;
   p.B = B; p.b_rs = b_rs; p.b_ss = b_ss; p.b_bytes = B ? b_bytes : 0;
   p.rank = rank; p.pivcols = pivcols; p.nsys = nsys;
+  p.no_fast_panel = no_fast;
   int ts = table_set_id(field, 1);
   p.inv = ts >= 0 ? g_sets[ts].inv : nullptr;
   if (force_nbw == 2) {

@@ -275,7 +275,7 @@ def emu():
         lib.emu_fastdiv_check.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
         lib.emu_solve.argtypes = [C.c_int, u8p, C.c_size_t, C.c_size_t, C.c_uint32, C.c_uint32,
                                   C.c_uint32, u8p, C.c_size_t, C.c_size_t, C.c_uint32, i32p,
-                                  u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_size_t, C.c_int, C.c_int]
+                                  u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_size_t, C.c_int, C.c_int, C.c_int]
         lib.emu_apply.argtypes = [u8p, C.c_size_t, C.c_uint32, C.c_uint32, u8p, C.c_size_t,
                                   u8p, C.c_size_t, C.c_uint32, C.c_int, C.c_uint32, C.c_int]
         _emu = lib

@@ -95,7 +95,7 @@ def test_swap_and_b32():
     assert np.array_equal(A0, A1)
 
 
-def _solve(field, rows, cols, b_bytes, seed, nsys=1, deficient=0, threads=64, grid=1, nbw=0, geo=-1):
+def _solve(field, rows, cols, b_bytes, seed, nsys=1, deficient=0, threads=64, grid=1, nbw=0, geo=-1, no_fast=0):
     e = emu()
     A = np.stack([random_matrix(field, rows, cols, seed + 2 * s, rank_deficient=deficient) for s in range(nsys)])
     B = np.stack([splitmix_bytes(seed + 2 * s + 1, rows * b_bytes).reshape(rows, b_bytes)
@@ -107,7 +107,7 @@ def _solve(field, rows, cols, b_bytes, seed, nsys=1, deficient=0, threads=64, gr
     rc = e.emu_solve(field, ptr(A), A.strides[1], A.strides[0], rows, cols, A.shape[2],
                      ptr(B) if B is not None else None, B.strides[1] if B is not None else 0,
                      B.strides[0] if B is not None else 0, B.shape[2] if B is not None else 0,
-                     ptr(rank, i32p), ptr(piv, u32p), nsys, grid, threads, SMEM, nbw, geo)
+                     ptr(rank, i32p), ptr(piv, u32p), nsys, grid, threads, SMEM, nbw, geo, no_fast)
     assert rc == 0
     assert [int(r) for r in rank] == [w[0] for w in want]
     for s in range(nsys):
@@ -147,6 +147,26 @@ def test_solve(args, geo):
     _solve(geo=geo, **args)
 
 
+@pytest.mark.parametrize("args", [
+    dict(field=GF256, rows=100, cols=100, b_bytes=272, seed=201, threads=64),
+    dict(field=GF256, rows=100, cols=100, b_bytes=64, seed=202, threads=64, deficient=1),
+    dict(field=GF256, rows=100, cols=100, b_bytes=64, seed=203, threads=64, deficient=2),
+    dict(field=GF256, rows=70, cols=120, b_bytes=32, seed=204, threads=64),
+    dict(field=GF16, rows=150, cols=150, b_bytes=48, seed=205, threads=64),
+    dict(field=GF16, rows=150, cols=150, b_bytes=48, seed=206, threads=64, nbw=2),
+    dict(field=GF4, rows=200, cols=200, b_bytes=32, seed=207, threads=96),
+    dict(field=GF4, rows=200, cols=200, b_bytes=32, seed=208, threads=64, nbw=2),
+    dict(field=GF2, rows=400, cols=400, b_bytes=32, seed=209, threads=160),
+    dict(field=GF2, rows=300, cols=300, b_bytes=0, seed=210, threads=96, nbw=2),
+    dict(field=GF2, rows=300, cols=500, b_bytes=16, seed=211, threads=160),
+])
+@pytest.mark.parametrize("no_fast", [0, 1])
+def test_solve_fast_and_general_panel_paths(args, no_fast):
+    """block sizes large enough for the register-resident fast panel path (NPIV+32 threads),
+    and the same systems forced through the general path"""
+    _solve(no_fast=no_fast, **args)
+
+
 def test_solve_zero_and_identity():
     e = emu()
     for field in (GF256, GF2):
@@ -154,7 +174,7 @@ def test_solve_zero_and_identity():
         A = random_matrix(field, rows, cols, 1) * 0
         rank = np.zeros(1, dtype=np.int32)
         rc = e.emu_solve(field, ptr(A), A.strides[0], A.nbytes, rows, cols, A.shape[1], None, 0, 0, 0,
-                         ptr(rank, i32p), None, 1, 1, 64, SMEM, 0, -1)
+                         ptr(rank, i32p), None, 1, 1, 64, SMEM, 0, -1, 0)
         assert rc == 0 and rank[0] == 0 and not A.any()
 
 

@@ -17,13 +17,18 @@ from oblas_b200 import capi, device
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", autouse=True, params=[-1, 0, 1, 2], ids=["geo_default", "geo4x256", "geo6x128", "geo7x64"])
+@pytest.fixture(scope="module", autouse=True, params=[(-1, 0), (0, 0), (1, 0), (2, 0), (-1, 1)],
+                ids=["geo_default", "geo4x256", "geo6x128", "geo7x64", "general_panel_path"])
 def _bind(cuda_lib, request):
-    """every test of this module runs once per Four-Russians table geometry"""
+    """every test of this module runs once per Four-Russians table geometry, and once with
+    the register-resident fast panel factorisation disabled"""
     device.bind(0)
-    cuda_lib.oblas_b200_set_tuning(request.param, request.param)
+    geo, general = request.param
+    cuda_lib.oblas_b200_set_tuning(geo, geo)
+    cuda_lib.oblas_b200_set_panel_path(general)
     yield
     cuda_lib.oblas_b200_set_tuning(-1, -1)
+    cuda_lib.oblas_b200_set_panel_path(0)
 
 
 def _batch(field, rows, cols, b_bytes, seed, nsys, deficient_every=0):
