@@ -1,0 +1,460 @@
+// peaks.cu -- measured per-SM peaks the elimination / apply kernels are judged against
+// ("Builder must measure LOP3, PRMT, IMMA/UTCIMMA int8 peaks on
+// the box and record them next to the HBM figure").  Stand-alone program, NOT part of the
+// product library:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/peaks tools/peaks.cu
+//
+// Prints one JSON object per line:
+//   alu      : LOP3 / PRMT / SHF / IMAD thread-ops per clock per SM (ILP 8, 1024 threads/SM)
+//   lds      : LDS.128 table look-ups, 8 lanes reading one contiguous 128-byte entry at a
+//              pseudo-random entry index (the Four-Russians access pattern of solve.cuh /
+//              apply.cuh) -> shared-memory bytes per clock per SM
+//   umma     : tcgen05.mma cta_group::1, M=128 N=256, operands in shared memory (SS), issued
+//              back to back by one thread per CTA: MACs per clock per SM for kind::i8
+//              (K=32), kind::f8f6f4 e4m3 (K=32), kind::f16 bf16 (K=16) and
+//              kind::mxf4 e2m1 block-scaled (K=64); optionally with the other warps of the
+//              CTA streaming STS.128 into shared memory at the same time (does operand
+//              fetch share the 128 B/clk crossbar with LSU traffic?).
+// Operand VALUES are irrelevant here (timing only); descriptors are valid no-swizzle K-major.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#define CK(x)                                                                              \
+  do {                                                                                     \
+    cudaError_t e_ = (x);                                                                  \
+    if (e_ != cudaSuccess) {                                                               \
+      printf("{\"error\": \"%s at %s:%d\"}\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      fflush(stdout);                                                                      \
+      exit(2);                                                                             \
+    }                                                                                      \
+  } while (0)
+
+// ---------------------------------------------------------------------------------- ALU
+template <int OP>
+__global__ void __launch_bounds__(1024, 1) alu_kernel(uint32_t *out, int iters, uint32_t seed,
+                                                      unsigned long long *cycles) {
+  uint32_t x[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) x[i] = seed * (threadIdx.x + 1) + i;
+  uint32_t a = seed ^ 0x9e3779b9u, b = (seed | 1u) * 0x85ebca6bu, sel = 0x3210u ^ (seed & 0x4444u);
+  __syncthreads();
+  long long t0 = clock64();
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        if (OP == 0) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(a), "r"(b));
+        if (OP == 1) asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(a), "r"(sel));
+        if (OP == 2) asm volatile("shf.l.wrap.b32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(a), "r"(sel));
+        if (OP == 3) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(a), "r"(b));
+      }
+    }
+  }
+  long long t1 = clock64();
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s ^= x[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) atomicMax(cycles, (unsigned long long)(t1 - t0));
+}
+
+// ---------------------------------------------------------------------------------- LDS
+// 512 threads, table of `entries` x 128 B; each 8-lane group reads one entry per step.
+__global__ void __launch_bounds__(512, 1) lds_kernel(uint32_t *out, int iters, uint32_t entries,
+                                                     unsigned long long *cycles) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint4 *tab = reinterpret_cast<uint4 *>(smem);
+  for (uint32_t i = threadIdx.x; i < entries * 8; i += blockDim.x)
+    tab[i] = make_uint4(i, i * 3u, i * 5u, i * 7u);
+  __syncthreads();
+  const uint32_t ch = threadIdx.x & 7;
+  uint32_t rowseed = (threadIdx.x >> 3) * 2654435761u + blockIdx.x;
+  uint4 acc[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) acc[k] = make_uint4(0, 0, 0, 0);
+  long long t0 = clock64();
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      uint32_t v = rowseed * (uint32_t)(4 * it + k + 1);
+#pragma unroll
+      for (int g = 0; g < 8; g++) {
+        uint32_t idx = (v >> (3 * g)) & (entries - 1);  // entries is a power of two
+        uint4 t = tab[idx * 8 + ch];
+        acc[k].x ^= t.x; acc[k].y ^= t.y; acc[k].z ^= t.z; acc[k].w ^= t.w;
+      }
+    }
+  }
+  long long t1 = clock64();
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) s ^= acc[k].x ^ acc[k].y ^ acc[k].z ^ acc[k].w;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) atomicMax(cycles, (unsigned long long)(t1 - t0));
+}
+
+// --------------------------------------------------------------------------------- UMMA
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  // K-major, SWIZZLE_NONE: core matrix = 8 rows x 16 B (128 B contiguous); LBO = byte step
+  // between core matrices along K, SBO = byte step between 8-row groups.  version = 1 (sm_100).
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+// KIND: 0 = i8 (u8 x u8 -> s32), 1 = f8f6f4 (e4m3 -> f32), 2 = f16 (bf16 -> f32), 3 = mxf4 block-scaled
+template <int KIND>
+__global__ void __launch_bounds__(128, 1) umma_kernel(int n_mma, int sts_warps, unsigned long long *cycles,
+                                                      unsigned long long *sts_bytes, int *status) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ uint32_t tmem_base;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // operand tiles: A 128 rows x 32 B, B 256 rows x 32 B, zero-filled (values do not matter)
+  for (uint32_t i = threadIdx.x; i < 65536 / 16; i += blockDim.x)
+    reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // make the generic-proxy zero fill visible to the async (tensor core) proxy
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tm = tmem_base;
+  const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem + 16384);
+  // per instruction the K extent is 32 bytes (i8/f8/bf16) = two 16-byte core-matrix columns
+  const uint64_t adesc = make_desc(a_addr, 128, 256), bdesc = make_desc(b_addr, 128, 256);
+  uint32_t idesc;
+  if (KIND == 0) idesc = (2u << 4) | (0u << 7) | (0u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+  if (KIND == 1) idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+  if (KIND == 2) idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+  if (KIND == 3) idesc = (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | (1u << 23) | ((128u >> 4) << 24);
+  long long t0 = 0, t1 = 0;
+  int ok = 1;
+  if (warp == 0) {
+    if (lane == 0) {
+      t0 = clock64();
+      for (int i = 0; i < n_mma; i++) {
+        // alternate between two accumulator tiles (columns 0..255 and 256..511; the mxf4
+        // variant keeps its scale factors in columns 256.. and uses one tile)
+        uint32_t d = tm + ((KIND != 3 && (i & 1)) ? 256u : 0u);
+        uint32_t acc = i >= 2 ? 1u : 0u;
+        if (KIND == 0)
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                       "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                       ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+        if (KIND == 1)
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                       "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                       ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+        if (KIND == 2)
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                       ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+        if (KIND == 3)
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                       "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+                       ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(tm + 256u), "r"(tm + 320u)
+                       : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                   ::"r"(smem_u32(&bar)) : "memory");
+      // bounded wait (never hang the box): ~4 s at 2 GHz
+      uint32_t done = 0;
+      long long tw = clock64();
+      while (!done) {
+        asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, q;\n\t}" : "=r"(done) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
+        if (!done && clock64() - tw > 8000000000ll) { ok = 0; break; }
+      }
+      t1 = clock64();
+      atomicMax(cycles, (unsigned long long)(t1 - t0));
+      if (!ok) atomicExch(status, 1);
+      *reinterpret_cast<volatile uint32_t *>(smem + 60000) = 1u;  // stop flag for the STS warps
+    }
+  } else if ((int)warp <= sts_warps) {
+    // concurrent LSU traffic: STS.128 stream into the upper 32 KB until the MMA thread is done
+    uint4 v = make_uint4(threadIdx.x, 1, 2, 3);
+    uint4 *dst = reinterpret_cast<uint4 *>(smem + 32768);
+    unsigned long long n = 0;
+    volatile uint32_t *flag = reinterpret_cast<volatile uint32_t *>(smem + 60000);
+    while (*flag == 0u) {
+#pragma unroll
+      for (int k = 0; k < 16; k++) dst[(k * 96 + threadIdx.x - 32) & 1535] = v;  // 24 KB window
+      n += 16;
+      v.x += 1;
+    }
+    if (lane == 0) atomicAdd(sts_bytes, n * 32ull * 16ull);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm));
+}
+
+
+// ------------------------------------------------------------------- fp4 exactness probe
+// A (128 x 64) and B (256 x 64) all e2m1 1.0 (nibble 0b0010), all scale factors ue8m0 1.0
+// (0x7F): after n MMAs every accumulator must read exactly 64*n if the fp32 accumulation
+// of 0/1 products is exact (what a bit-sliced GF(2) product needs).  KIND 3 = mxf4, 0 = i8
+// (all-ones bytes, s32 accumulators: exact by construction, validates the read-back path).
+template <int KIND>
+__global__ void __launch_bounds__(128, 1) umma_exact_kernel(int n_mma, float *out, int *status) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ uint32_t tmem_base;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t fillw = (KIND == 3) ? 0x22222222u : 0x01010101u;
+  for (uint32_t i = threadIdx.x; i < 32768 / 16; i += blockDim.x)
+    reinterpret_cast<uint4 *>(smem)[i] = make_uint4(fillw, fillw, fillw, fillw);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tm = tmem_base;
+  // scale factors: columns 256..511 of every lane = 0x7F7F7F7F
+  for (uint32_t c = 256; c < 512; c += 8) {
+    uint32_t ta = tm + ((warp * 32u) << 16) + c, v = 0x7f7f7f7fu;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(ta), "r"(v) : "memory");
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint64_t adesc = make_desc(smem_u32(smem), 128, 256), bdesc = make_desc(smem_u32(smem + 16384), 128, 256);
+  uint32_t idesc;
+  if (KIND == 0) idesc = (2u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+  if (KIND == 3) idesc = (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | (1u << 23) | ((128u >> 4) << 24);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < n_mma; i++) {
+      uint32_t acc = i > 0 ? 1u : 0u;
+      if (KIND == 0)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                     ::"r"(tm), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+      if (KIND == 3)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+                     ::"r"(tm), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(tm + 256u), "r"(tm + 320u) : "memory");
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+  }
+  // everybody waits (bounded)
+  {
+    uint32_t done = 0;
+    long long tw = clock64();
+    while (!done) {
+      asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
+                   "selp.u32 %0, 1, 0, q;\n\t}" : "=r"(done) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
+      if (!done && clock64() - tw > 8000000000ll) { atomicExch(status, 1); break; }
+    }
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // read accumulator columns {0..7} and {248..255} of this thread's lane
+  uint32_t r[16];
+  uint32_t ta = tm + ((warp * 32u) << 16);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(ta));
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(ta + 248u));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  for (int k = 0; k < 16; k++)
+    out[threadIdx.x * 16 + k] = (KIND == 3) ? __uint_as_float(r[k]) : (float)(int)r[k];
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm));
+}
+
+template <int KIND>
+static void run_exact(const char *name, int kdim, int n_mma) {
+  float *out;
+  int *status;
+  CK(cudaMalloc(&out, 128 * 16 * 4));
+  CK(cudaMalloc(&status, 4));
+  CK(cudaMemset(status, 0, 4));
+  auto k = umma_exact_kernel<KIND>;
+  CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  k<<<1, 128, 65536>>>(n_mma, out, status);
+  CK(cudaDeviceSynchronize());
+  float h[128 * 16];
+  int hs;
+  CK(cudaMemcpy(h, out, sizeof h, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&hs, status, 4, cudaMemcpyDeviceToHost));
+  float mn = h[0], mx = h[0];
+  for (int i = 0; i < 128 * 16; i++) { mn = h[i] < mn ? h[i] : mn; mx = h[i] > mx ? h[i] : mx; }
+  double want = (double)kdim * n_mma;
+  printf("{\"what\": \"umma_exact\", \"kind\": \"%s\", \"n_mma\": %d, \"expected\": %.0f, \"min\": %.1f, \"max\": %.1f, "
+         "\"exact\": %s, \"timed_out\": %d}\n", name, n_mma, want, mn, mx,
+         (mn == want && mx == want) ? "true" : "false", hs);
+  fflush(stdout);
+  cudaFree(out); cudaFree(status);
+}
+
+template <int KIND>
+static void run_umma(const char *name, int kdim, int sms, int n_mma, int sts_warps, int grid) {
+  unsigned long long *cyc, *stsb;
+  int *status;
+  CK(cudaMalloc(&cyc, 8));
+  CK(cudaMalloc(&stsb, 8));
+  CK(cudaMalloc(&status, 4));
+  auto k = umma_kernel<KIND>;
+  CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  float best_ms = 1e30f;
+  unsigned long long hc = 0, hb = 0;
+  int hs = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    CK(cudaMemset(cyc, 0, 8));
+    CK(cudaMemset(stsb, 0, 8));
+    CK(cudaMemset(status, 0, 4));
+    CK(cudaEventRecord(e0));
+    k<<<grid, 128, 65536>>>(n_mma, sts_warps, cyc, stsb, status);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best_ms) {
+      best_ms = ms;
+      CK(cudaMemcpy(&hc, cyc, 8, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(&hb, stsb, 8, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(&hs, status, 4, cudaMemcpyDeviceToHost));
+    }
+  }
+  double macs = 128.0 * 256.0 * kdim * n_mma;
+  printf("{\"what\": \"umma\", \"kind\": \"%s\", \"M\": 128, \"N\": 256, \"K\": %d, \"ctas\": %d, \"n_mma\": %d, "
+         "\"sts_warps\": %d, \"timed_out\": %d, \"cycles\": %llu, \"mac_per_clk_per_sm\": %.1f, "
+         "\"ms\": %.4f, \"chip_Tmac_per_s\": %.1f, \"mhz_effective\": %.0f, \"sts_bytes_per_clk_per_sm\": %.1f}\n",
+         name, kdim, grid, n_mma, sts_warps, hs, hc, macs / (double)hc, best_ms,
+         macs * grid / (best_ms * 1e-3) / 1e12, (double)hc / (best_ms * 1e-3) / 1e6,
+         (double)hb / grid / (double)hc);
+  fflush(stdout);
+  (void)sms;
+  cudaFree(cyc); cudaFree(stsb); cudaFree(status);
+}
+
+template <int OP>
+static void run_alu(const char *name, int sms) {
+  uint32_t *out;
+  unsigned long long *cyc;
+  CK(cudaMalloc(&out, (size_t)sms * 1024 * 4));
+  CK(cudaMalloc(&cyc, 8));
+  const int iters = 4096;
+  float best = 1e30f;
+  unsigned long long hc = 0;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  for (int rep = 0; rep < 4; rep++) {
+    CK(cudaMemset(cyc, 0, 8));
+    CK(cudaEventRecord(e0));
+    alu_kernel<OP><<<sms, 1024>>>(out, iters, 12345u + rep, cyc);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) { best = ms; CK(cudaMemcpy(&hc, cyc, 8, cudaMemcpyDeviceToHost)); }
+  }
+  double ops = 1024.0 * iters * 32.0;
+  printf("{\"what\": \"alu\", \"op\": \"%s\", \"thread_ops_per_clk_per_sm\": %.1f, \"ms\": %.4f, "
+         "\"chip_Tops_per_s\": %.2f, \"mhz_effective\": %.0f}\n",
+         name, ops / (double)hc, best, ops * sms / (best * 1e-3) / 1e12, (double)hc / (best * 1e-3) / 1e6);
+  fflush(stdout);
+  cudaFree(out); cudaFree(cyc);
+}
+
+static void run_lds(int sms, uint32_t entries) {
+  uint32_t *out;
+  unsigned long long *cyc;
+  CK(cudaMalloc(&out, (size_t)sms * 512 * 4));
+  CK(cudaMalloc(&cyc, 8));
+  size_t smem = (size_t)entries * 128;
+  CK(cudaFuncSetAttribute(lds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int iters = 2048;
+  float best = 1e30f;
+  unsigned long long hc = 0;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  for (int rep = 0; rep < 4; rep++) {
+    CK(cudaMemset(cyc, 0, 8));
+    CK(cudaEventRecord(e0));
+    lds_kernel<<<sms, 512, smem>>>(out, iters, entries, cyc);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) { best = ms; CK(cudaMemcpy(&hc, cyc, 8, cudaMemcpyDeviceToHost)); }
+  }
+  double bytes = 512.0 * iters * 32.0 * 16.0;
+  printf("{\"what\": \"lds\", \"pattern\": \"8 lanes x 16 B = one 128-byte table entry, pseudo-random entry, %u entries (%zu KB)\", "
+         "\"bytes_per_clk_per_sm\": %.1f, \"lookups128_per_clk_per_sm\": %.3f, \"ms\": %.4f, \"mhz_effective\": %.0f}\n",
+         entries, smem / 1024, bytes / (double)hc, bytes / 128.0 / (double)hc, best,
+         (double)hc / (best * 1e-3) / 1e6);
+  fflush(stdout);
+  cudaFree(out); cudaFree(cyc);
+}
+
+int main(int argc, char **argv) {
+  int dev = 0;
+  CK(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, dev));
+  int sms = prop.multiProcessorCount;
+  printf("{\"what\": \"device\", \"name\": \"%s\", \"sms\": %d, \"cc\": \"%d.%d\"}\n", prop.name, sms, prop.major, prop.minor);
+  fflush(stdout);
+  bool do_umma = true, do_mxf4 = false;
+  for (int i = 1; i < argc; i++) {
+    if (!strcmp(argv[i], "--no-umma")) do_umma = false;
+    if (!strcmp(argv[i], "--mxf4")) do_mxf4 = true;
+  }
+  run_alu<0>("LOP3", sms);
+  run_alu<1>("PRMT", sms);
+  run_alu<2>("SHF", sms);
+  run_alu<3>("IMAD", sms);
+  run_lds(sms, 1024);  // 128 KB of tables (solve.cuh default geometry: 1348 entries x 128 B)
+  run_lds(sms, 512);
+  if (do_umma) {
+    // single SM first (no power limit in play), then the whole chip
+    run_umma<2>("f16(bf16)", 16, sms, 2048, 0, 1);
+    run_umma<0>("i8", 32, sms, 2048, 0, 1);
+    run_umma<1>("f8f6f4(e4m3)", 32, sms, 2048, 0, 1);
+    run_umma<0>("i8", 32, sms, 2048, 3, 1);
+    run_umma<2>("f16(bf16)", 16, sms, 16384, 0, sms);
+    run_umma<0>("i8", 32, sms, 16384, 0, sms);
+    run_umma<1>("f8f6f4(e4m3)", 32, sms, 16384, 0, sms);
+    run_umma<0>("i8", 32, sms, 16384, 3, sms);
+    if (do_mxf4) {
+      for (int n = 1; n <= 65536; n *= 8) run_exact<0>("i8", 32, n);
+      for (int n = 1; n <= 65536; n *= 4) run_exact<3>("mxf4(e2m1,ue8m0)", 64, n);
+      run_umma<3>("mxf4(e2m1,ue8m0)", 64, sms, 2048, 0, 1);
+      run_umma<3>("mxf4(e2m1,ue8m0)", 64, sms, 16384, 0, sms);
+    }
+  }
+  return 0;
+}
