@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "apply.cuh"
+#include "apply_tc.cuh"
 #include "rowops.cuh"
 #include "solve.cuh"
 #include "tables_host.h"
@@ -37,6 +38,10 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   bool async = false;
   int solve_geo = -1, apply_geo = -1;  // table geometry overrides (-1 = default)
+  // tensor-core apply (apply_tc.cuh): expanded-D workspace and the device-written status word
+  void *tc_ws = nullptr;
+  size_t tc_ws_bytes = 0;
+  int *tc_status = nullptr;  // pinned + mapped: the kernel sets it if a barrier wait gave up
   int no_fast_panel = 0;               // diagnostics: general panel path only
   unsigned long long *d_phase = nullptr;  // solve-kernel phase counters (diagnostics)
   DevTableSet *d_sets = nullptr;  // [TS_COUNT] in device memory
@@ -203,6 +208,11 @@ void oblas_b200_shutdown(void) {
   if (g.scratch) cudaFree(g.scratch);
   g.scratch = nullptr;
   g.scratch_bytes = 0;
+  if (g.tc_ws) cudaFree(g.tc_ws);
+  g.tc_ws = nullptr;
+  g.tc_ws_bytes = 0;
+  if (g.tc_status) cudaFreeHost(g.tc_status);
+  g.tc_status = nullptr;
   lanes_release();
   cudaFree(g.d_sets);
   g.d_sets = nullptr;
@@ -223,10 +233,11 @@ void oblas_b200_use_own_stream(void) {
   g.stream = g.own_stream;
 }
 void *oblas_b200_get_stream(void) { return ensure_init() ? nullptr : (void *)g.stream; }
+int tc_check_status();
 int oblas_b200_sync(void) {
   if (ensure_init()) return -1;
   CK(cudaStreamSynchronize(g.stream));
-  return 0;
+  return tc_check_status();
 }
 void oblas_b200_set_async(int async) { g.async = async != 0; }
 void oblas_b200_set_panel_path(int general_only) { g.no_fast_panel = general_only != 0; }
@@ -630,6 +641,79 @@ int oblas_b200_solve_batch_host(int field, void *A_host, size_t a_row_stride, si
   return rc;
 }
 
+// ---- tensor-core apply: host side ---------------------------------------------------
+// Column window by column window: expand D into the fp4 operand blocks (workspace), then the
+// persistent tcgen05 kernel.  The workspace is bounded (tc_ws_budget) and cached.
+static size_t tc_ws_budget = (size_t)3 << 30;
+int tc_check_status() {
+  if (g.tc_status && *reinterpret_cast<volatile int *>(g.tc_status) != 0) {
+    *g.tc_status = 0;
+    return fail("apply (tensor-core path): a pipeline barrier wait hit its spin limit; result invalid");
+  }
+  return 0;
+}
+int apply_tc_run(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, const uint8_t *D, size_t d_stride,
+                 uint8_t *Y, size_t y_stride, size_t nbytes, int accumulate) {
+  using namespace ob2::tc;
+  if (!g.tc_status) {
+    CK(cudaHostAlloc((void **)&g.tc_status, sizeof(int), cudaHostAllocMapped));
+    *g.tc_status = 0;
+  }
+  const uint32_t ksteps = (Kc + kStepJ - 1) / kStepJ;
+  const size_t tile_bytes = (size_t)ksteps * kBTile;
+  const uint32_t ntiles_all = (uint32_t)((nbytes + kTileN - 1) / kTileN);
+  uint32_t tiles_per_pass = (uint32_t)(tc_ws_budget / tile_bytes);
+  if (tiles_per_pass == 0) tiles_per_pass = 1;
+  if (tiles_per_pass > ntiles_all) tiles_per_pass = ntiles_all;
+  size_t need = (size_t)tiles_per_pass * tile_bytes;
+  if (need > g.tc_ws_bytes) {
+    if (g.tc_ws) {
+      CK(cudaStreamSynchronize(g.stream));
+      CK(cudaFree(g.tc_ws));
+      g.tc_ws = nullptr;
+      g.tc_ws_bytes = 0;
+    }
+    while (cudaMalloc(&g.tc_ws, need) != cudaSuccess) {   // shrink the window until it fits
+      cudaGetLastError();
+      g.tc_ws = nullptr;
+      if (tiles_per_pass == 1) return fail("apply: cannot allocate %zu bytes of operand workspace", need);
+      tiles_per_pass = (tiles_per_pass + 1) / 2;
+      need = (size_t)tiles_per_pass * tile_bytes;
+    }
+    g.tc_ws_bytes = need;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(apply_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    attr_set = true;
+  }
+  int *dstatus = nullptr;
+  CK(cudaHostGetDevicePointer((void **)&dstatus, g.tc_status, 0));
+  const uint32_t itiles = (M + kRowsI - 1) / kRowsI;
+  for (uint32_t t0 = 0; t0 < ntiles_all; t0 += tiles_per_pass) {
+    const uint32_t nt = (ntiles_all - t0 < tiles_per_pass) ? (ntiles_all - t0) : tiles_per_pass;
+    const uint32_t n0 = t0 * kTileN;
+    const uint32_t ncols = (uint32_t)((nbytes - n0 < (size_t)nt * kTileN) ? (nbytes - n0) : (size_t)nt * kTileN);
+    ExpandArgs e;
+    e.D = D; e.d_stride = d_stride; e.Kc = Kc; e.n0 = n0; e.ncols = ncols;
+    e.Dx = (uint8_t *)g.tc_ws; e.ksteps = ksteps; e.ntiles = nt;
+    const size_t work = (size_t)nt * ksteps * (kTileN / 4);
+    uint32_t eg = (uint32_t)((work + 255) / 256);
+    if (eg > (uint32_t)g.sm_count * 16) eg = (uint32_t)g.sm_count * 16;
+    expand_d_kernel<<<eg, 256, 0, g.stream>>>(e);
+    if (after_launch("apply (operand expansion)")) return -1;
+    ApplyTcArgs a;
+    a.C = C; a.c_stride = c_stride; a.M = M; a.Kc = Kc; a.Dx = (const uint8_t *)g.tc_ws;
+    a.ksteps = ksteps; a.ntiles = nt; a.itiles = itiles; a.Y = Y; a.y_stride = y_stride;
+    a.n0 = n0; a.ncols = ncols; a.accumulate = accumulate; a.status = dstatus;
+    const uint32_t total = nt * itiles;
+    const uint32_t grid = total < (uint32_t)g.sm_count ? total : (uint32_t)g.sm_count;
+    apply_tc_kernel<<<grid, kThreads, kSmemBytes, g.stream>>>(a);
+    if (after_launch("apply (tcgen05)")) return -1;
+  }
+  return 0;
+}
+
 // ---- apply ---------------------------------------------------------------------
 int oblas_b200_gf256_apply(const void *C, size_t c_stride, uint32_t M, uint32_t Kc, const void *D,
                            size_t d_stride, void *Y, size_t y_stride, size_t nbytes, int accumulate) {
@@ -641,13 +725,24 @@ int oblas_b200_gf256_apply(const void *C, size_t c_stride, uint32_t M, uint32_t 
     return fail("apply: D, Y, their strides and nbytes must be multiples of 16");
   if (classify(C) != PK_DEVVIS || classify(D) != PK_DEVVIS || classify(Y) != PK_DEVVIS)
     return fail("apply: pointers must be device-visible");
+  std::lock_guard<std::mutex> lk(g.mu);
+  // path: apply_geo 0..2 force the shared-memory Four-Russians kernel with that geometry, 3 forces
+  // the tensor-core kernel, -1 picks by size (the fp4 expansion of D is amortised over M/16 row tiles)
+  const bool tc_ok = Kc > 0 && Kc < (1u << 20);
+  bool use_tc = g.apply_geo == 3 || (g.apply_geo < 0 && M >= 256 && Kc >= 64 && nbytes >= 480);
+  if (use_tc && !tc_ok) {
+    if (g.apply_geo == 3) return fail("apply: tensor-core path needs 0 < Kc < 2^20");
+    use_tc = false;
+  }
+  if (use_tc)
+    return apply_tc_run((const uint8_t *)C, c_stride, M, Kc, (const uint8_t *)D, d_stride, (uint8_t *)Y,
+                        y_stride, nbytes, accumulate);
   ApplyArgs p;
   memset(&p, 0, sizeof p);
   p.C = (const uint8_t *)C; p.c_stride = c_stride; p.M = M; p.Kc = Kc;
   p.D = (const uint8_t *)D; p.d_stride = d_stride;
   p.Y = (uint8_t *)Y; p.y_stride = y_stride; p.nbytes = (uint32_t)nbytes; p.accumulate = accumulate;
-  std::lock_guard<std::mutex> lk(g.mu);
-  int rc = launch_apply(p, g.apply_geo, 512, g.stream);
+  int rc = launch_apply(p, g.apply_geo == 3 ? -1 : g.apply_geo, 512, g.stream);
   if (rc) return fail("apply: launch configuration failed (%d)", rc);
   return after_launch("apply");
 }

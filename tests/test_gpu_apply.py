@@ -10,7 +10,7 @@ from oblas_b200 import capi, device
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", autouse=True, params=[-1, 0, 1, 2], ids=["geo_default", "geo4x256", "geo6x128", "geo7x64"])
+@pytest.fixture(scope="module", autouse=True, params=[-1, 0, 1, 2, 3], ids=["auto", "geo4x256", "geo6x128", "geo7x64", "tcgen05"])
 def _bind(cuda_lib, request):
     """every test of this module runs once per Four-Russians table geometry"""
     device.bind(0)
@@ -20,7 +20,8 @@ def _bind(cuda_lib, request):
 
 
 @pytest.mark.parametrize("M,Kc,nbytes,cs", [(10, 10, 32, 16), (40, 37, 272, 48), (300, 100, 512, 112),
-                                            (33, 16, 256, 16), (5, 3, 16, 7), (257, 260, 1296, 260)])
+                                            (33, 16, 256, 16), (5, 3, 16, 7), (257, 260, 1296, 260),
+                                            (1, 1, 16, 1), (17, 9, 480, 9), (16, 8, 496, 8), (130, 71, 976, 71)])
 def test_apply_vs_oracle(M, Kc, nbytes, cs):
     o = oracle()
     Cm = np.zeros((M, cs), dtype=np.uint8)
@@ -29,8 +30,10 @@ def test_apply_vs_oracle(M, Kc, nbytes, cs):
     Y0 = np.zeros((M, nbytes), dtype=np.uint8)
     o.orc_gf256_apply(ptr(Cm), cs, M, Kc, ptr(D), nbytes, ptr(Y0), nbytes, nbytes)
     Y = device.apply(dev(Cm)[:, :], dev(D))
+    capi.check(capi.lib().oblas_b200_sync(), "sync")  # also surfaces the tensor-core path's status word
     assert np.array_equal(host(Y), Y0)
     Y2 = device.apply(dev(Cm), dev(D), Y=Y.clone(), accumulate=True)
+    capi.check(capi.lib().oblas_b200_sync(), "sync")
     assert not host(Y2).any()  # Y ^ Y == 0
 
 
