@@ -78,8 +78,14 @@ int oblas_b200_sync(void);                /* wait for the current stream */
 void oblas_b200_set_async(int async);
 /* Four-Russians table geometry of the elimination / apply kernels (tuning knob for
  * measurements): 0 = 4-bit groups, 256-byte tiles; 1 = 6-bit groups, 128-byte tiles;
- * 2 = 7-bit groups, 64-byte tiles; -1 = library default.  Results are identical. */
+ * 2 = 7-bit groups, 64-byte tiles; -1 = library default.  Results are identical.
+ * apply_geo = 3 forces the tensor-core path of the dense apply (tcgen05 kind::mxf4
+ * bit-sliced GF(2) product, apply_tc.cuh); -1 picks it when M >= 256, Kc >= 64 and
+ * nbytes >= 480, the shared-memory table kernel otherwise. */
 void oblas_b200_set_tuning(int solve_geo, int apply_geo);
+/* CTAs per thread-block cluster of the tensor-core apply (each operand block is read from
+ * L2 once per cluster and multicast): 1, 2 or 4; 0 = library default */
+void oblas_b200_set_apply_cluster(int ctas);
 /* diagnostics/tests: general_only != 0 disables the register-resident fast panel
  * factorisation (identical results, slower) */
 void oblas_b200_set_panel_path(int general_only);

@@ -24,15 +24,15 @@
 //                     LBO = 128, SBO = 256); 4 bytes of fp4 per byte of D.  Written once,
 //                     read by every row tile.
 //   apply_tc_kernel   persistent, 1 CTA per SM, warp specialised:
-//                       warp 4      producer: one cp.async.bulk (TMA engine) per step, Dx -> smem
-//                       warps 6,7   A-operand builders: 16 rows x 8 coefficients of C per step,
+//                       warp 4      producer: one cp.async.bulk (TMA engine) per stage (2 steps), Dx -> smem
+//                       warps 6-9   A-operand builders: 16 rows x 8 coefficients of C per step,
 //                                   each coefficient expanded to its 8x8 bit matrix through a
-//                                   256 x 32-byte table in shared memory (alternate steps)
+//                                   256 x 32-byte table in shared memory (round robin over steps)
 //                       warp 5      one thread issues 2 x tcgen05.mma (M=128, N=240, K=64) per
 //                                   step into 480 TMEM columns, tcgen05.commit frees the stage
 //                       warps 0-3   epilogue: tcgen05.ld, parity, __ballot_sync packs the 8 bit
 //                                   lanes of 4 rows into 4 result bytes per column, stores
-//                     8-stage mbarrier ring between producers and the MMA thread.
+//                     5-stage mbarrier ring (2 steps = 4 MMAs per stage) between producers and the MMA thread.
 // TMEM lane (16 rows x 8 bit planes) = i*8 + a, TMEM column = symbol byte n.
 //
 // Only the product build sees this file (no host-thread emulation of tcgen05).
@@ -47,12 +47,20 @@ constexpr int kTileN = 2 * kHalfN;           // symbol bytes per CTA tile
 constexpr int kRowsI = 16;                   // C/Y rows per CTA tile (x 8 bit planes = 128 lanes)
 constexpr int kStepJ = 8;                    // coefficient columns per step (x 8 bits = K 64)
 constexpr int kBTile = kTileN * 32;          // bytes of one B-operand block (15360)
-constexpr int kATile = 128 * 32;             // bytes of one A-operand block (4096)
-constexpr int kStages = 8;
+// A-operand block: 16 row groups (one C row = 8 bit-plane rows) x 2 core matrices of 128 B.  The
+// groups are padded to 288 B and the second core matrix sits at +144 B, so that the 8 lanes of
+// a quarter-warp (row group = lane/2, core matrix = lane%2) hit 8 different 16-byte bank groups
+// when they all store the same bit-plane row: bank group = (2*group + core + row) mod 8.
+constexpr int kALbo = 144, kASbo = 288;
+constexpr int kATile = 16 * kASbo;           // bytes of one A-operand block (4608)
+constexpr int kBuilderWarps = 4;             // warps 6..9, one step each, round robin
+constexpr int kSPS = 2;                      // K-steps per pipeline stage (one barrier round trip per 4 MMAs)
+constexpr int kStages = 5;
+constexpr int kBStage = kSPS * kBTile, kAStage = kSPS * kATile;
 constexpr int kSfCol = 480;                  // TMEM columns 480..511: scale factors (all 1.0)
-constexpr int kThreads = 256;
+constexpr int kThreads = 32 * (6 + kBuilderWarps);
 constexpr int kLutBytes = 256 * 32;
-constexpr size_t kSmemBytes = (size_t)kStages * (kBTile + kATile) + kLutBytes + 256 + 1024;
+constexpr size_t kSmemBytes = (size_t)kStages * (kBStage + kAStage) + kLutBytes + 256 + 1024;
 constexpr uint32_t kSpinLimit = 1u << 24;    // bounded waits: never hang the device
 
 struct ExpandArgs {
@@ -61,7 +69,7 @@ struct ExpandArgs {
   uint32_t Kc;
   uint32_t n0, ncols;      // byte-column window [n0, n0+ncols) of D handled by this pass
   uint8_t *Dx;             // [ntiles][ksteps][kBTile]
-  uint32_t ksteps, ntiles;
+  uint32_t ksteps, ntiles; // ksteps is a multiple of kSPS (steps beyond Kc are zero blocks)
 };
 
 struct ApplyTcArgs {
@@ -75,6 +83,7 @@ struct ApplyTcArgs {
   uint32_t n0, ncols;
   int accumulate;
   int *status;             // set to 1 if a barrier wait ran into the spin limit
+  int dbg;                 // diagnostics (timing experiments only, results invalid): 1 = no bulk loads, 2 = no A build
 };
 
 // byte d -> 8 fp4 values, nibble b = e2m1 1.0 (0b0010) if bit b of d is set
@@ -135,22 +144,53 @@ OB2_D void mbar_arrive(uint32_t bar) {
 OB2_D void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// false = gave up (status flag set); every caller then leaves its loop
-OB2_D bool mbar_wait(uint32_t bar, uint32_t parity, int *status) {
+// false = gave up (status flag set); every caller then leaves its loop.  backoff_ns > 0 for
+// waits that are expected to be long (keeps the pollers off the LSU pipe).
+OB2_D bool mbar_wait(uint32_t bar, uint32_t parity, int *status, uint32_t backoff_ns = 0) {
   for (uint32_t spin = 0; spin < kSpinLimit; spin++) {
     uint32_t done;
     asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
                  "selp.u32 %0, 1, 0, q;\n\t}"
                  : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (done) return true;
+    if (backoff_ns) __nanosleep(backoff_ns);
     if ((spin & 1023u) == 1023u && *reinterpret_cast<volatile int *>(status) != 0) break;
   }
   atomicExch(status, 1);
   return false;
 }
+// whole-warp wait: lane 0 polls, the result is broadcast (one poller per warp instead of 32)
+OB2_D bool mbar_wait_warp(uint32_t bar, uint32_t parity, int *status, uint32_t backoff_ns = 0) {
+  uint32_t ok = 1;
+  if ((threadIdx.x & 31u) == 0) ok = mbar_wait(bar, parity, status, backoff_ns) ? 1u : 0u;
+  ok = __shfl_sync(0xffffffffu, ok, 0);
+  return ok != 0;
+}
 OB2_D void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// slice of a block to the same shared-memory offset (and full barrier) of every CTA in cta_mask
+OB2_D void bulk_g2s_multicast(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint16_t cta_mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask) : "memory");
+}
+OB2_D void tc_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask) : "memory");
+}
+OB2_D bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+OB2_D uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+OB2_D void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 OB2_D void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 OB2_D void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -160,8 +200,8 @@ OB2_D void tc_commit(uint32_t bar) {
 }
 // K-major, no swizzle: core matrix = 8 rows x 16 bytes; LBO = 128 (next core matrix along K),
 // SBO = 256 (next 8-row group); descriptor version 1 (sm_100)
-OB2_D uint64_t umma_desc(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(256u >> 4) << 32) |
+OB2_D uint64_t umma_desc(uint32_t saddr, uint32_t lbo = 128u, uint32_t sbo = 256u) {
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
          ((uint64_t)1 << 46);
 }
 OB2_D void umma_mxf4(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
@@ -174,12 +214,18 @@ OB2_D void umma_mxf4(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t i
 // ---------------------------------------------------------------------------------------
 // the GEMM kernel
 // ---------------------------------------------------------------------------------------
+// CS = CTAs per cluster.  The CS CTAs of a cluster work on the same column tile and CS
+// consecutive row tiles; every B block is fetched from L2 once per cluster: each CTA loads 1/CS
+// of it and multicasts the slice into the shared memory of all CS CTAs, and a stage is reused
+// only after the MMA threads of all CS CTAs have released it (multicast tcgen05.commit).
+template <int CS>
 __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs p) {
   extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
-  unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-  unsigned char *smB = sm;                                   // [kStages][kBTile]
-  unsigned char *smA = sm + (size_t)kStages * kBTile;        // [kStages][kATile]
-  uint32_t *lut = reinterpret_cast<uint32_t *>(smA + (size_t)kStages * kATile);  // [256][8]
+  // (offset arithmetic on the __shared__ array keeps the address space: LDS/STS, not generic LD/ST)
+  unsigned char *sm = tc_smem_raw + ((1024u - (smem_addr(tc_smem_raw) & 1023u)) & 1023u);
+  unsigned char *smB = sm;                                   // [kStages][kSPS][kBTile]
+  unsigned char *smA = sm + (size_t)kStages * kBStage;       // [kStages][kSPS][kATile]
+  uint32_t *lut = reinterpret_cast<uint32_t *>(smA + (size_t)kStages * kAStage);  // [256][8]
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(lut) + kLutBytes);
   // bars[0..S) full, [S..2S) empty, [2S] tmem_full, [2S+1] tmem_empty
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 2);
@@ -190,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
   const uint32_t tmem_full = bar0 + 8u * (2 * kStages), tmem_empty = bar0 + 8u * (2 * kStages + 1);
 
   // coefficient c -> its 8x8 bit matrix as 8 words (word a: nibble b = 2 * bit a of c*x^b)
-  {
+  if (tid < 256) {
     uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t pw = tid;
 #pragma unroll
@@ -205,8 +251,8 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
   }
   if (tid == 0) {
     for (uint32_t s = 0; s < kStages; s++) {
-      mbar_init(full_bar(s), 1 + 32);   // producer's expect_tx arrive + one builder warp
-      mbar_init(empty_bar(s), 1);       // tcgen05.commit
+      mbar_init(full_bar(s), 1 + 32);   // producer's expect_tx arrive + the 32 lanes of one builder warp
+      mbar_init(empty_bar(s), CS);      // tcgen05.commit of every CTA in the cluster
     }
     mbar_init(tmem_full, 1);
     mbar_init(tmem_empty, 128);
@@ -233,54 +279,85 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
   __syncthreads();
   tc_fence_after();
 
-  const uint32_t ntotal = p.ntiles * p.itiles;
+  // work units: (column tile, group of CS row tiles); cluster c takes units c, c + #clusters, ...
+  const uint32_t rank = CS > 1 ? cluster_ctarank() : 0u;
+  const uint32_t igroups = (p.itiles + CS - 1) / CS;
+  const uint32_t ntotal = p.ntiles * igroups;
+  const uint32_t unit0 = blockIdx.x / CS, ustep = gridDim.x / CS;
   const uint32_t ksteps = p.ksteps;
+  constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
+  constexpr uint32_t kSlice = kBStage / CS;
+  static_assert(kBStage % (CS * 16) == 0, "slice size");
+  const uint32_t nst = ksteps / kSPS;   // pipeline stages per tile
+  if (CS > 1) cluster_sync_all();   // every CTA's barriers are initialised before any peer touches them
 
   if (warp == 4) {
     // ------------------------------------------------------------ producer (TMA engine)
-    if (lane == 0) {
-      uint32_t g = 0;
-      bool ok = true;
-      for (uint32_t t = blockIdx.x; t < ntotal && ok; t += gridDim.x) {
-        const uint32_t nt = t / p.itiles;
-        const uint8_t *src = p.Dx + (size_t)nt * ksteps * kBTile;
-        for (uint32_t ks = 0; ks < ksteps; ks++, g++) {
-          const uint32_t s = g % kStages, ph = (g / kStages) & 1u;
-          if (!mbar_wait(empty_bar(s), ph ^ 1u, p.status)) { ok = false; break; }
-          mbar_arrive_expect_tx(full_bar(s), kBTile);
-          bulk_g2s(smem_addr(smB + (size_t)s * kBTile), src + (size_t)ks * kBTile, kBTile, full_bar(s));
+    // The whole warp runs the loop (warp-uniform control flow and addresses, so the compiler
+    // keeps them in uniform registers); one elected lane issues the copy.
+    const bool leader = elect_one();
+    const uint32_t b_dst0 = smem_addr(smB) + rank * kSlice;
+    uint32_t s = 0, ph = 0;
+    bool ok = true;
+    for (uint32_t t = unit0; t < ntotal && ok; t += ustep) {
+      const uint32_t nt = t / igroups;
+      const uint8_t *src = p.Dx + (size_t)nt * ksteps * kBTile + rank * kSlice;
+      for (uint32_t st = 0; st < nst; st++, src += kBStage) {
+        if (!mbar_wait(empty_bar(s), ph ^ 1u, p.status)) { ok = false; break; }
+        if (leader) {
+          if (p.dbg & 1) {
+            mbar_arrive(full_bar(s));
+          } else {
+            mbar_arrive_expect_tx(full_bar(s), kBStage);
+            if (CS == 1) bulk_g2s(b_dst0 + s * kBStage, src, kBStage, full_bar(s));
+            else bulk_g2s_multicast(b_dst0 + s * kBStage, src, kSlice, full_bar(s), kMask);
+          }
         }
+        if (++s == kStages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 5) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      // block-scaled descriptor: A,B = E2M1 (1), K-major, N = 240, scales UE8M0, M = 128, K = 64
-      const uint32_t idesc = (1u << 7) | (1u << 10) | ((uint32_t)(kHalfN >> 3) << 17) | (1u << 23) | ((128u >> 4) << 24);
-      uint32_t g = 0, iter = 0;
-      bool ok = true;
-      for (uint32_t t = blockIdx.x; t < ntotal && ok; t += gridDim.x, iter++) {
-        if (!mbar_wait(tmem_empty, (iter & 1u) ^ 1u, p.status)) break;  // epilogue drained the accumulators
+    // Warp-uniform loop, one elected lane issues.  A single thread issues ~1 instruction per
+    // 4-5 clocks, so the per-step instruction count is what bounds the MMA rate: descriptors
+    // are base + stage * constant, nothing else is computed in the loop.
+    const bool leader = elect_one();
+    // block-scaled descriptor: A,B = E2M1 (1), K-major, N = 240, scales UE8M0, M = 128, K = 64
+    const uint32_t idesc = (1u << 7) | (1u << 10) | ((uint32_t)(kHalfN >> 3) << 17) | (1u << 23) | ((128u >> 4) << 24);
+    const uint64_t a_desc0 = umma_desc(smem_addr(smA), kALbo, kASbo);
+    const uint64_t b_desc0 = umma_desc(smem_addr(smB));
+    const uint32_t sfa = tm + kSfCol, sfb = tm + kSfCol + 16;
+    uint32_t s = 0, ph = 0, iter = 0;
+    bool ok = true;
+    for (uint32_t t = unit0; t < ntotal && ok; t += ustep, iter++) {
+      if (!mbar_wait(tmem_empty, (iter & 1u) ^ 1u, p.status)) break;  // epilogue drained the accumulators
+      tc_fence_after();
+      for (uint32_t st = 0; st < nst; st++) {
+        if (!mbar_wait(full_bar(s), ph, p.status)) { ok = false; break; }
         tc_fence_after();
-        for (uint32_t ks = 0; ks < ksteps; ks++, g++) {
-          const uint32_t s = g % kStages, ph = (g / kStages) & 1u;
-          if (!mbar_wait(full_bar(s), ph, p.status)) { ok = false; break; }
-          tc_fence_after();
-          const uint64_t ad = umma_desc(smem_addr(smA + (size_t)s * kATile));
-          const uint32_t bbase = smem_addr(smB + (size_t)s * kBTile);
-          umma_mxf4(tm, ad, umma_desc(bbase), idesc, ks > 0, tm + kSfCol, tm + kSfCol + 16);
-          umma_mxf4(tm + kHalfN, ad, umma_desc(bbase + (kHalfN / 8) * 256), idesc, ks > 0, tm + kSfCol, tm + kSfCol + 16);
-          tc_commit(empty_bar(s));
+        if (leader) {
+          const uint64_t ad = a_desc0 + (uint64_t)(s * (kAStage >> 4));
+          const uint64_t bd = b_desc0 + (uint64_t)(s * (kBStage >> 4));
+#pragma unroll
+          for (int u = 0; u < kSPS; u++) {
+            const uint32_t acc = (u == 0) ? st : 1u;
+            const uint64_t au = ad + (uint64_t)(u * (kATile >> 4)), bu = bd + (uint64_t)(u * (kBTile >> 4));
+            umma_mxf4(tm, au, bu, idesc, acc, sfa, sfb);
+            umma_mxf4(tm + kHalfN, au, bu + (uint64_t)((kHalfN / 8) * 256 >> 4), idesc, acc, sfa, sfb);
+          }
+          if (CS == 1) tc_commit(empty_bar(s));
+          else tc_commit_multicast(empty_bar(s), kMask);
         }
-        if (ok) tc_commit(tmem_full);
+        if (++s == kStages) { s = 0; ph ^= 1u; }
       }
+      if (ok && leader) tc_commit(tmem_full);
     }
   } else if (warp >= 6) {
     // ------------------------------------------------------------ A-operand builders
-    const uint32_t b = warp - 6;          // this warp builds steps with g % 2 == b
+    const uint32_t b = warp - 6;          // this warp builds the stages with G % kBuilderWarps == b
     const uint32_t i = lane >> 1, q = lane & 1u;
     const bool c_vec = ((p.c_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 3) == 0);
-    uint32_t g = 0;
+    uint32_t G = 0;                       // stages of the tiles done so far
     bool ok = true;
     auto load_c = [&](uint32_t it, uint32_t ks) -> uint32_t {
       const uint32_t row = it * kRowsI + i, j = ks * kStepJ + 4 * q;
@@ -291,40 +368,53 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
       for (uint32_t k = 0; k < 4 && j + k < p.Kc; k++) w |= (uint32_t)__ldg(src + k) << (8 * k);
       return w;
     };
-    for (uint32_t t = blockIdx.x; t < ntotal && ok; t += gridDim.x) {
-      const uint32_t it = t % p.itiles;
-      uint32_t ks0 = (b + 2u - (g & 1u)) & 1u;   // first step of this tile that is ours
-      uint32_t cw = ks0 < ksteps ? load_c(it, ks0) : 0u;
-      for (uint32_t ks = ks0; ks < ksteps; ks += 2) {
-        const uint32_t gg = g + ks;
-        const uint32_t s = gg % kStages, ph = (gg / kStages) & 1u;
-        const uint32_t cur = cw;
-        if (ks + 2 < ksteps) cw = load_c(it, ks + 2);
-        if (!mbar_wait(empty_bar(s), ph ^ 1u, p.status)) { ok = false; break; }
-        const uint4 *e0 = reinterpret_cast<const uint4 *>(lut + ((cur >> 0) & 0xffu) * 8);
-        const uint4 *e1 = reinterpret_cast<const uint4 *>(lut + ((cur >> 8) & 0xffu) * 8);
-        const uint4 *e2 = reinterpret_cast<const uint4 *>(lut + ((cur >> 16) & 0xffu) * 8);
-        const uint4 *e3 = reinterpret_cast<const uint4 *>(lut + ((cur >> 24) & 0xffu) * 8);
-        uint4 *dst = reinterpret_cast<uint4 *>(smA + (size_t)s * kATile + i * 256 + q * 128);
+    for (uint32_t t = unit0; t < ntotal && ok; t += ustep) {
+      const uint32_t it = (t % igroups) * CS + rank;
+      const uint32_t st0 = (b + kBuilderWarps - (G % kBuilderWarps)) % kBuilderWarps;  // first stage of this tile that is ours
+      uint32_t cw[kSPS];
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const uint4 a0 = e0[h], a1 = e1[h], a2 = e2[h], a3 = e3[h];
-          dst[4 * h + 0] = make_uint4(a0.x, a1.x, a2.x, a3.x);
-          dst[4 * h + 1] = make_uint4(a0.y, a1.y, a2.y, a3.y);
-          dst[4 * h + 2] = make_uint4(a0.z, a1.z, a2.z, a3.z);
-          dst[4 * h + 3] = make_uint4(a0.w, a1.w, a2.w, a3.w);
+      for (int u = 0; u < kSPS; u++) cw[u] = st0 < nst ? load_c(it, st0 * kSPS + u) : 0u;
+      for (uint32_t st = st0; st < nst; st += kBuilderWarps) {
+        const uint32_t gs = G + st;
+        const uint32_t s = gs % kStages, ph = (gs / kStages) & 1u;
+        uint4 lo[kSPS][4], hi[kSPS][4];
+#pragma unroll
+        for (int u = 0; u < kSPS; u++) {
+          const uint32_t cur = cw[u];
+          if (st + kBuilderWarps < nst) cw[u] = load_c(it, (st + kBuilderWarps) * kSPS + u);
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const uint4 *e = reinterpret_cast<const uint4 *>(lut + ((cur >> (8 * k)) & 0xffu) * 8);
+            lo[u][k] = e[0];
+            hi[u][k] = e[1];
+          }
         }
-        fence_async_smem();
+        if (!mbar_wait_warp(empty_bar(s), ph ^ 1u, p.status)) { ok = false; break; }
+        if (!(p.dbg & 2)) {
+#pragma unroll
+          for (int u = 0; u < kSPS; u++) {
+            uint4 *dst = reinterpret_cast<uint4 *>(smA + (size_t)s * kAStage + u * kATile + i * kASbo + q * kALbo);
+            dst[0] = make_uint4(lo[u][0].x, lo[u][1].x, lo[u][2].x, lo[u][3].x);
+            dst[1] = make_uint4(lo[u][0].y, lo[u][1].y, lo[u][2].y, lo[u][3].y);
+            dst[2] = make_uint4(lo[u][0].z, lo[u][1].z, lo[u][2].z, lo[u][3].z);
+            dst[3] = make_uint4(lo[u][0].w, lo[u][1].w, lo[u][2].w, lo[u][3].w);
+            dst[4] = make_uint4(hi[u][0].x, hi[u][1].x, hi[u][2].x, hi[u][3].x);
+            dst[5] = make_uint4(hi[u][0].y, hi[u][1].y, hi[u][2].y, hi[u][3].y);
+            dst[6] = make_uint4(hi[u][0].z, hi[u][1].z, hi[u][2].z, hi[u][3].z);
+            dst[7] = make_uint4(hi[u][0].w, hi[u][1].w, hi[u][2].w, hi[u][3].w);
+          }
+          fence_async_smem();
+        }
         mbar_arrive(full_bar(s));
       }
-      g += ksteps;
+      G += nst;
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 0..3)
     uint32_t iter = 0;
-    for (uint32_t t = blockIdx.x; t < ntotal; t += gridDim.x, iter++) {
-      const uint32_t nt = t / p.itiles, it = t % p.itiles;
-      if (!mbar_wait(tmem_full, iter & 1u, p.status)) break;
+    for (uint32_t t = unit0; t < ntotal; t += ustep, iter++) {
+      const uint32_t nt = t / igroups, it = (t % igroups) * CS + rank;
+      if (!mbar_wait_warp(tmem_full, iter & 1u, p.status, 256)) break;
       tc_fence_after();
       const uint32_t row0 = it * kRowsI + warp * 4;
       const uint32_t ncol0 = nt * kTileN;
@@ -370,11 +460,15 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
   }
   tc_fence_before();
   __syncthreads();
+  // no CTA leaves while a peer may still multicast into its shared memory or signal its barriers
+  if (CS > 1) cluster_sync_all();
   if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm) : "memory");
 }
 
-inline size_t dx_bytes(uint32_t Kc, uint32_t ntiles) {
-  return (size_t)ntiles * ((Kc + kStepJ - 1) / kStepJ) * kBTile;
+// K-steps of one tile: ceil(Kc / 8) rounded up to whole pipeline stages
+inline uint32_t ksteps_for(uint32_t Kc) {
+  uint32_t k = (Kc + kStepJ - 1) / kStepJ;
+  return (k + kSPS - 1) / kSPS * kSPS;
 }
 
 }  // namespace tc

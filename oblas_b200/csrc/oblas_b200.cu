@@ -42,6 +42,7 @@ struct Ctx {
   void *tc_ws = nullptr;
   size_t tc_ws_bytes = 0;
   int *tc_status = nullptr;  // pinned + mapped: the kernel sets it if a barrier wait gave up
+  int tc_cluster = 0;        // CTAs per cluster of the tensor-core apply (1, 2, 4; 0 = default)
   int no_fast_panel = 0;               // diagnostics: general panel path only
   unsigned long long *d_phase = nullptr;  // solve-kernel phase counters (diagnostics)
   DevTableSet *d_sets = nullptr;  // [TS_COUNT] in device memory
@@ -240,6 +241,7 @@ int oblas_b200_sync(void) {
   return tc_check_status();
 }
 void oblas_b200_set_async(int async) { g.async = async != 0; }
+void oblas_b200_set_apply_cluster(int ctas) { g.tc_cluster = ctas; }
 void oblas_b200_set_panel_path(int general_only) { g.no_fast_panel = general_only != 0; }
 void oblas_b200_set_tuning(int solve_geo, int apply_geo) {
   g.solve_geo = solve_geo;
@@ -659,7 +661,7 @@ int apply_tc_run(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, con
     CK(cudaHostAlloc((void **)&g.tc_status, sizeof(int), cudaHostAllocMapped));
     *g.tc_status = 0;
   }
-  const uint32_t ksteps = (Kc + kStepJ - 1) / kStepJ;
+  const uint32_t ksteps = ksteps_for(Kc);
   const size_t tile_bytes = (size_t)ksteps * kBTile;
   const uint32_t ntiles_all = (uint32_t)((nbytes + kTileN - 1) / kTileN);
   uint32_t tiles_per_pass = (uint32_t)(tc_ws_budget / tile_bytes);
@@ -684,9 +686,14 @@ int apply_tc_run(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, con
   }
   static bool attr_set = false;
   if (!attr_set) {
-    CK(cudaFuncSetAttribute(apply_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    CK(cudaFuncSetAttribute(apply_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    CK(cudaFuncSetAttribute(apply_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    CK(cudaFuncSetAttribute(apply_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     attr_set = true;
   }
+  // cluster size: multicast pays once there are enough row tiles to fill every SM with clusters
+  int cs = g.tc_cluster;
+  if (cs != 1 && cs != 2 && cs != 4) cs = 4;
   int *dstatus = nullptr;
   CK(cudaHostGetDevicePointer((void **)&dstatus, g.tc_status, 0));
   const uint32_t itiles = (M + kRowsI - 1) / kRowsI;
@@ -706,9 +713,26 @@ int apply_tc_run(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, con
     a.C = C; a.c_stride = c_stride; a.M = M; a.Kc = Kc; a.Dx = (const uint8_t *)g.tc_ws;
     a.ksteps = ksteps; a.ntiles = nt; a.itiles = itiles; a.Y = Y; a.y_stride = y_stride;
     a.n0 = n0; a.ncols = ncols; a.accumulate = accumulate; a.status = dstatus;
-    const uint32_t total = nt * itiles;
-    const uint32_t grid = total < (uint32_t)g.sm_count ? total : (uint32_t)g.sm_count;
-    apply_tc_kernel<<<grid, kThreads, kSmemBytes, g.stream>>>(a);
+    { const char *dv = getenv("OBLAS_B200_TC_DEBUG"); a.dbg = dv ? atoi(dv) : 0; }
+    const uint32_t units = nt * ((itiles + cs - 1) / cs);
+    uint32_t nclusters = (uint32_t)g.sm_count / cs;
+    if (units < nclusters) nclusters = units;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nclusters * cs);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = g.stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t le = cs == 1   ? cudaLaunchKernelEx(&cfg, apply_tc_kernel<1>, a)
+                     : cs == 2 ? cudaLaunchKernelEx(&cfg, apply_tc_kernel<2>, a)
+                               : cudaLaunchKernelEx(&cfg, apply_tc_kernel<4>, a);
+    if (le != cudaSuccess) return fail("apply (tcgen05) launch failed: %s", cudaGetErrorString(le));
     if (after_launch("apply (tcgen05)")) return -1;
   }
   return 0;
