@@ -63,24 +63,38 @@ constexpr int kLutBytes = 256 * 32;
 constexpr size_t kSmemBytes = (size_t)kStages * (kBStage + kAStage) + kLutBytes + 256 + 1024;
 constexpr uint32_t kSpinLimit = 1u << 24;    // bounded waits: never hang the device
 
+// A byte-column range of a (batched) row-major byte matrix.  The tensor-core kernels see the
+// concatenation of up to two regions (the elimination updates A's remaining columns and B in
+// one launch); every region starts on a column-tile boundary.
+struct TcRegion {
+  uint8_t *base;
+  size_t rs, ss;       // row stride, system stride (bytes)
+  uint32_t col0;       // first byte column of the range inside a row
+  uint32_t ncols;      // bytes per row in the range (multiple of 16)
+  uint32_t tile0;      // index of the region's first column tile
+};
+
 struct ExpandArgs {
-  const uint8_t *D;
-  size_t d_stride;
-  uint32_t Kc;
-  uint32_t n0, ncols;      // byte-column window [n0, n0+ncols) of D handled by this pass
-  uint8_t *Dx;             // [ntiles][ksteps][kBTile]
-  uint32_t ksteps, ntiles; // ksteps is a multiple of kSPS (steps beyond Kc are zero blocks)
+  TcRegion reg[2];         // where the rows of D live (plain apply: one region, one system)
+  uint32_t nreg;
+  uint32_t Kc;             // rows of D
+  // batched elimination: row j of system s is physical row rowmap[s * rowmap_stride + j] of
+  // the region and exists only for j < nrows[s]; both null for the plain apply
+  const uint16_t *rowmap;
+  uint32_t rowmap_stride;
+  const uint32_t *nrows;
+  uint8_t *Dx;             // [nsys][ntiles][ksteps][kBTile]
+  uint32_t ksteps, ntiles, nsys; // ksteps is a multiple of kSPS (steps beyond Kc are zero blocks)
 };
 
 struct ApplyTcArgs {
-  const uint8_t *C;
-  size_t c_stride;
+  const uint8_t *C;        // coefficients: [nsys][M][c_stride]
+  size_t c_stride, c_ss;
   uint32_t M, Kc;
-  const uint8_t *Dx;
-  uint32_t ksteps, ntiles, itiles;
-  uint8_t *Y;
-  size_t y_stride;
-  uint32_t n0, ncols;
+  const uint8_t *Dx;       // [nsys][ntiles][ksteps][kBTile]
+  uint32_t ksteps, ntiles, itiles, nsys;
+  TcRegion reg[2];         // Y
+  uint32_t nreg;
   int accumulate;
   int *status;             // set to 1 if a barrier wait ran into the spin limit
   int dbg;                 // diagnostics (timing experiments only, results invalid): 1 = no bulk loads, 2 = no A build
@@ -100,23 +114,31 @@ OB2_D uint32_t spread_fp4(uint32_t d) {
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) expand_d_kernel(const ExpandArgs p) {
   constexpr uint32_t G = kTileN / 4;  // column groups per tile
-  const size_t total = (size_t)p.ntiles * p.ksteps * G;
+  const size_t per_sys = (size_t)p.ntiles * p.ksteps * G;
+  const size_t total = per_sys * p.nsys;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
-    const uint32_t g4 = (uint32_t)(idx % G);
-    const size_t rest = idx / G;
+    const uint32_t sys = (uint32_t)(idx / per_sys);
+    const size_t li = idx - (size_t)sys * per_sys;
+    const uint32_t g4 = (uint32_t)(li % G);
+    const size_t rest = li / G;
     const uint32_t ks = (uint32_t)(rest % p.ksteps), tile = (uint32_t)(rest / p.ksteps);
-    const uint32_t nl = g4 * 4;                       // local column
-    const uint32_t n = tile * kTileN + nl;            // column inside the window
+    const TcRegion &rg = p.reg[(p.nreg > 1 && tile >= p.reg[1].tile0) ? 1 : 0];
+    const uint32_t nl = g4 * 4;                              // local column
+    const uint32_t n = (tile - rg.tile0) * kTileN + nl;      // column inside the region
+    const uint32_t nrows = p.nrows ? p.nrows[sys] : p.Kc;
+    const uint8_t *src0 = rg.base + (size_t)sys * rg.ss + rg.col0 + n;
     uint32_t x[kStepJ];
 #pragma unroll
     for (int jj = 0; jj < kStepJ; jj++) {
       const uint32_t j = ks * kStepJ + jj;
       x[jj] = 0;
-      if (j < p.Kc && n < p.ncols)
-        x[jj] = __ldg(reinterpret_cast<const uint32_t *>(p.D + (size_t)j * p.d_stride + p.n0 + n));
+      if (j < nrows && n < rg.ncols) {
+        const uint32_t row = p.rowmap ? (uint32_t)p.rowmap[(size_t)sys * p.rowmap_stride + j] : j;
+        x[jj] = *reinterpret_cast<const uint32_t *>(src0 + (size_t)row * rg.rs);
+      }
     }
-    uint8_t *blk = p.Dx + ((size_t)tile * p.ksteps + ks) * kBTile + (nl >> 3) * 256 + (nl & 7) * 16;
+    uint8_t *blk = p.Dx + (((size_t)sys * p.ntiles + tile) * p.ksteps + ks) * kBTile + (nl >> 3) * 256 + (nl & 7) * 16;
 #pragma unroll
     for (int bl = 0; bl < 4; bl++) {
       uint4 lo, hi;
@@ -279,10 +301,11 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
   __syncthreads();
   tc_fence_after();
 
-  // work units: (column tile, group of CS row tiles); cluster c takes units c, c + #clusters, ...
+  // work units: (system, column tile, group of CS row tiles), row tiles fastest; cluster c takes
+  // units c, c + #clusters, ...
   const uint32_t rank = CS > 1 ? cluster_ctarank() : 0u;
   const uint32_t igroups = (p.itiles + CS - 1) / CS;
-  const uint32_t ntotal = p.ntiles * igroups;
+  const uint32_t ntotal = p.nsys * p.ntiles * igroups;   // host keeps this below 2^32
   const uint32_t unit0 = blockIdx.x / CS, ustep = gridDim.x / CS;
   const uint32_t ksteps = p.ksteps;
   constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
@@ -300,7 +323,7 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
     uint32_t s = 0, ph = 0;
     bool ok = true;
     for (uint32_t t = unit0; t < ntotal && ok; t += ustep) {
-      const uint32_t nt = t / igroups;
+      const uint32_t nt = t / igroups;   // = system * ntiles + column tile
       const uint8_t *src = p.Dx + (size_t)nt * ksteps * kBTile + rank * kSlice;
       for (uint32_t st = 0; st < nst; st++, src += kBStage) {
         if (!mbar_wait(empty_bar(s), ph ^ 1u, p.status)) { ok = false; break; }
@@ -356,13 +379,14 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
     // ------------------------------------------------------------ A-operand builders
     const uint32_t b = warp - 6;          // this warp builds the stages with G % kBuilderWarps == b
     const uint32_t i = lane >> 1, q = lane & 1u;
-    const bool c_vec = ((p.c_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 3) == 0);
+    const bool c_vec = ((p.c_stride & 3) == 0) && ((p.c_ss & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 3) == 0);
     uint32_t G = 0;                       // stages of the tiles done so far
     bool ok = true;
+    const uint8_t *Cs = p.C;              // coefficient matrix of the current system
     auto load_c = [&](uint32_t it, uint32_t ks) -> uint32_t {
       const uint32_t row = it * kRowsI + i, j = ks * kStepJ + 4 * q;
       if (row >= p.M || j >= p.Kc) return 0u;
-      const uint8_t *src = p.C + (size_t)row * p.c_stride + j;
+      const uint8_t *src = Cs + (size_t)row * p.c_stride + j;
       if (c_vec && j + 4 <= p.Kc) return __ldg(reinterpret_cast<const uint32_t *>(src));
       uint32_t w = 0;
       for (uint32_t k = 0; k < 4 && j + k < p.Kc; k++) w |= (uint32_t)__ldg(src + k) << (8 * k);
@@ -370,6 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
     };
     for (uint32_t t = unit0; t < ntotal && ok; t += ustep) {
       const uint32_t it = (t % igroups) * CS + rank;
+      Cs = p.C + (size_t)(t / igroups / p.ntiles) * p.c_ss;
       const uint32_t st0 = (b + kBuilderWarps - (G % kBuilderWarps)) % kBuilderWarps;  // first stage of this tile that is ours
       uint32_t cw[kSPS];
 #pragma unroll
@@ -413,11 +438,27 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
     // ------------------------------------------------------------ epilogue (warps 0..3)
     uint32_t iter = 0;
     for (uint32_t t = unit0; t < ntotal; t += ustep, iter++) {
-      const uint32_t nt = t / igroups, it = (t % igroups) * CS + rank;
+      const uint32_t snt = t / igroups, it = (t % igroups) * CS + rank;
+      const uint32_t sys = snt / p.ntiles, nt = snt - sys * p.ntiles;
+      const TcRegion &rg = p.reg[(p.nreg > 1 && nt >= p.reg[1].tile0) ? 1 : 0];
+      const uint32_t row0 = it * kRowsI + warp * 4;
+      const uint32_t ncol0 = (nt - rg.tile0) * kTileN;          // first column of the tile inside the region
+      uint8_t *ybase = rg.base + (size_t)sys * rg.ss + rg.col0;
+      // accumulate mode: the old bytes of the first chunk are fetched while the MMAs still run
+      uint32_t oldv = 0;
+      auto load_old = [&](uint32_t cc) -> uint32_t {
+        uint32_t o = 0;
+        const uint32_t n = ncol0 + cc * 32 + lane;
+        if (p.accumulate && n < rg.ncols) {
+#pragma unroll
+          for (int rr = 0; rr < 4; rr++)
+            if (row0 + rr < p.M) o |= (uint32_t)ybase[(size_t)(row0 + rr) * rg.rs + n] << (8 * rr);
+        }
+        return o;
+      };
+      oldv = load_old(0);
       if (!mbar_wait_warp(tmem_full, iter & 1u, p.status, 256)) break;
       tc_fence_after();
-      const uint32_t row0 = it * kRowsI + warp * 4;
-      const uint32_t ncol0 = nt * kTileN;
 #pragma unroll 1
       for (uint32_t cc = 0; cc < (uint32_t)kTileN / 32; cc++) {
         uint32_t r[32];
@@ -431,6 +472,8 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
               "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
               "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(ta) : "memory");
+        const uint32_t cur_old = oldv;
+        if (cc + 1 < (uint32_t)kTileN / 32) oldv = load_old(cc + 1);   // next chunk's old bytes in flight
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         uint32_t mine = 0;
 #pragma unroll
@@ -440,17 +483,13 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
           const uint32_t v = __ballot_sync(0xffffffffu, bit != 0u);
           if (lane == (uint32_t)c) mine = v;
         }
-        const uint32_t n = ncol0 + cc * 32 + lane;     // column inside the window
-        if (n < p.ncols) {
+        mine ^= cur_old;
+        const uint32_t n = ncol0 + cc * 32 + lane;     // column inside the region
+        if (n < rg.ncols) {
 #pragma unroll
           for (int rr = 0; rr < 4; rr++) {
             const uint32_t row = row0 + rr;
-            if (row < p.M) {
-              uint8_t *dst = p.Y + (size_t)row * p.y_stride + p.n0 + n;
-              uint8_t v = (uint8_t)(mine >> (8 * rr));
-              if (p.accumulate) v ^= *dst;
-              *dst = v;
-            }
+            if (row < p.M) ybase[(size_t)row * rg.rs + n] = (uint8_t)(mine >> (8 * rr));
           }
         }
       }

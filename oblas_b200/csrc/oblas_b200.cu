@@ -436,6 +436,15 @@ int oblas_b200_rowops(int field, int variant, int op, int mul_mode, void *a, siz
 }
 
 // ---- elimination -----------------------------------------------------------------
+int solve_tc_run(SolveArgs &p, size_t nsys);   // tensor-core path (GF(256)), defined with apply_tc_run
+static bool solve_tc_eligible(int field, const SolveArgs &p, size_t nsys) {
+  if (field != OB2_GF256 || p.a_ptrs || p.b_ptrs) return false;
+  if (panel_smem_bytes(p.rows) > g.smem_optin || p.rows > 65535u) return false;
+  if (g.solve_geo == 3) return true;
+  if (g.solve_geo >= 0) return false;
+  // auto: the rank-128 tensor-core update pays once the systems are big enough to fill its tiles
+  return p.rows >= 512 && p.cols >= 256 && nsys >= 1;
+}
 static int solve_common(int field, SolveArgs &p, size_t nsys) {
   if (field < OB2_GF2 || field > OB2_GF256) return fail("solve: bad field %d", field);
   if (p.rows == 0 || p.cols == 0 || nsys == 0) return 0;
@@ -448,8 +457,9 @@ static int solve_common(int field, SolveArgs &p, size_t nsys) {
   p.nsys = (uint32_t)nsys;
   p.phase = g.d_phase;
   p.no_fast_panel = g.no_fast_panel;
+  if (solve_tc_eligible(field, p, nsys)) return solve_tc_run(p, nsys);
   uint32_t grid = nsys < (size_t)g.sm_count ? (uint32_t)nsys : (uint32_t)g.sm_count;
-  int rc = launch_solve(field, g.solve_geo, p, grid, 512, g.smem_optin, g.stream);
+  int rc = launch_solve(field, g.solve_geo == 3 ? -1 : g.solve_geo, p, grid, 512, g.smem_optin, g.stream);
   if (rc == -1)
     return fail("solve: %u rows do not fit the shared-memory panel (limit %zu bytes); no fallback", p.rows, g.smem_optin);
   if (rc) return fail("solve: cudaFuncSetAttribute failed");
@@ -654,35 +664,11 @@ int tc_check_status() {
   }
   return 0;
 }
-int apply_tc_run(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, const uint8_t *D, size_t d_stride,
-                 uint8_t *Y, size_t y_stride, size_t nbytes, int accumulate) {
+int tc_prepare(int **dstatus) {
   using namespace ob2::tc;
   if (!g.tc_status) {
     CK(cudaHostAlloc((void **)&g.tc_status, sizeof(int), cudaHostAllocMapped));
     *g.tc_status = 0;
-  }
-  const uint32_t ksteps = ksteps_for(Kc);
-  const size_t tile_bytes = (size_t)ksteps * kBTile;
-  const uint32_t ntiles_all = (uint32_t)((nbytes + kTileN - 1) / kTileN);
-  uint32_t tiles_per_pass = (uint32_t)(tc_ws_budget / tile_bytes);
-  if (tiles_per_pass == 0) tiles_per_pass = 1;
-  if (tiles_per_pass > ntiles_all) tiles_per_pass = ntiles_all;
-  size_t need = (size_t)tiles_per_pass * tile_bytes;
-  if (need > g.tc_ws_bytes) {
-    if (g.tc_ws) {
-      CK(cudaStreamSynchronize(g.stream));
-      CK(cudaFree(g.tc_ws));
-      g.tc_ws = nullptr;
-      g.tc_ws_bytes = 0;
-    }
-    while (cudaMalloc(&g.tc_ws, need) != cudaSuccess) {   // shrink the window until it fits
-      cudaGetLastError();
-      g.tc_ws = nullptr;
-      if (tiles_per_pass == 1) return fail("apply: cannot allocate %zu bytes of operand workspace", need);
-      tiles_per_pass = (tiles_per_pass + 1) / 2;
-      need = (size_t)tiles_per_pass * tile_bytes;
-    }
-    g.tc_ws_bytes = need;
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -691,49 +677,217 @@ int apply_tc_run(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, con
     CK(cudaFuncSetAttribute(apply_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     attr_set = true;
   }
-  // cluster size: multicast pays once there are enough row tiles to fill every SM with clusters
-  int cs = g.tc_cluster;
-  if (cs != 1 && cs != 2 && cs != 4) cs = 4;
+  CK(cudaHostGetDevicePointer((void **)dstatus, g.tc_status, 0));
+  return 0;
+}
+int tc_ws_reserve(size_t need) {
+  if (need <= g.tc_ws_bytes) return 0;
+  if (g.tc_ws) {
+    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaFree(g.tc_ws));
+    g.tc_ws = nullptr;
+    g.tc_ws_bytes = 0;
+  }
+  if (cudaMalloc(&g.tc_ws, need) != cudaSuccess) {
+    cudaGetLastError();
+    g.tc_ws = nullptr;
+    return 1;   // caller shrinks its request
+  }
+  g.tc_ws_bytes = need;
+  return 0;
+}
+// persistent launch of the tcgen05 GEMM kernel: one CTA per SM (clusters of cs)
+int tc_launch(const ob2::tc::ApplyTcArgs &a, int cs) {
+  using namespace ob2::tc;
+  const uint64_t units64 = (uint64_t)a.nsys * a.ntiles * ((a.itiles + cs - 1) / cs);
+  if (units64 >= (1ull << 32)) return fail("apply (tcgen05): too many tiles in one launch");
+  const uint32_t units = (uint32_t)units64;
+  uint32_t nclusters = (uint32_t)g.sm_count / cs;
+  if (units < nclusters) nclusters = units;
+  if (nclusters == 0) return 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nclusters * cs);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = g.stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cs;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t le = cs == 1   ? cudaLaunchKernelEx(&cfg, apply_tc_kernel<1>, a)
+                   : cs == 2 ? cudaLaunchKernelEx(&cfg, apply_tc_kernel<2>, a)
+                             : cudaLaunchKernelEx(&cfg, apply_tc_kernel<4>, a);
+  if (le != cudaSuccess) return fail("apply (tcgen05) launch failed: %s", cudaGetErrorString(le));
+  return after_launch("apply (tcgen05)");
+}
+int apply_tc_run(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, const uint8_t *D, size_t d_stride,
+                 uint8_t *Y, size_t y_stride, size_t nbytes, int accumulate) {
+  using namespace ob2::tc;
   int *dstatus = nullptr;
-  CK(cudaHostGetDevicePointer((void **)&dstatus, g.tc_status, 0));
+  if (tc_prepare(&dstatus)) return -1;
+  const uint32_t ksteps = ksteps_for(Kc);
+  const size_t tile_bytes = (size_t)ksteps * kBTile;
+  const uint32_t ntiles_all = (uint32_t)((nbytes + kTileN - 1) / kTileN);
+  uint32_t tiles_per_pass = (uint32_t)(tc_ws_budget / tile_bytes);
+  if (tiles_per_pass == 0) tiles_per_pass = 1;
+  if (tiles_per_pass > ntiles_all) tiles_per_pass = ntiles_all;
+  for (;;) {   // shrink the column window until the workspace fits
+    int rc = tc_ws_reserve((size_t)tiles_per_pass * tile_bytes);
+    if (rc < 0) return -1;
+    if (rc == 0) break;
+    if (tiles_per_pass == 1) return fail("apply: cannot allocate %zu bytes of operand workspace", tile_bytes);
+    tiles_per_pass = (tiles_per_pass + 1) / 2;
+  }
+  // CTAs per cluster (multicast of the operand blocks); measured: 1 is fastest on B200
+  int cs = g.tc_cluster;
+  if (cs != 1 && cs != 2 && cs != 4) cs = 1;
   const uint32_t itiles = (M + kRowsI - 1) / kRowsI;
   for (uint32_t t0 = 0; t0 < ntiles_all; t0 += tiles_per_pass) {
     const uint32_t nt = (ntiles_all - t0 < tiles_per_pass) ? (ntiles_all - t0) : tiles_per_pass;
     const uint32_t n0 = t0 * kTileN;
     const uint32_t ncols = (uint32_t)((nbytes - n0 < (size_t)nt * kTileN) ? (nbytes - n0) : (size_t)nt * kTileN);
     ExpandArgs e;
-    e.D = D; e.d_stride = d_stride; e.Kc = Kc; e.n0 = n0; e.ncols = ncols;
-    e.Dx = (uint8_t *)g.tc_ws; e.ksteps = ksteps; e.ntiles = nt;
+    memset(&e, 0, sizeof e);
+    e.reg[0].base = const_cast<uint8_t *>(D); e.reg[0].rs = d_stride; e.reg[0].ss = 0;
+    e.reg[0].col0 = n0; e.reg[0].ncols = ncols; e.reg[0].tile0 = 0;
+    e.nreg = 1; e.Kc = Kc; e.rowmap = nullptr; e.rowmap_stride = 0; e.nrows = nullptr;
+    e.Dx = (uint8_t *)g.tc_ws; e.ksteps = ksteps; e.ntiles = nt; e.nsys = 1;
     const size_t work = (size_t)nt * ksteps * (kTileN / 4);
     uint32_t eg = (uint32_t)((work + 255) / 256);
     if (eg > (uint32_t)g.sm_count * 16) eg = (uint32_t)g.sm_count * 16;
     expand_d_kernel<<<eg, 256, 0, g.stream>>>(e);
     if (after_launch("apply (operand expansion)")) return -1;
     ApplyTcArgs a;
-    a.C = C; a.c_stride = c_stride; a.M = M; a.Kc = Kc; a.Dx = (const uint8_t *)g.tc_ws;
-    a.ksteps = ksteps; a.ntiles = nt; a.itiles = itiles; a.Y = Y; a.y_stride = y_stride;
-    a.n0 = n0; a.ncols = ncols; a.accumulate = accumulate; a.status = dstatus;
+    memset(&a, 0, sizeof a);
+    a.C = C; a.c_stride = c_stride; a.c_ss = 0; a.M = M; a.Kc = Kc; a.Dx = (const uint8_t *)g.tc_ws;
+    a.ksteps = ksteps; a.ntiles = nt; a.itiles = itiles; a.nsys = 1;
+    a.reg[0].base = Y; a.reg[0].rs = y_stride; a.reg[0].ss = 0; a.reg[0].col0 = n0; a.reg[0].ncols = ncols;
+    a.reg[0].tile0 = 0; a.nreg = 1;
+    a.accumulate = accumulate; a.status = dstatus;
     { const char *dv = getenv("OBLAS_B200_TC_DEBUG"); a.dbg = dv ? atoi(dv) : 0; }
-    const uint32_t units = nt * ((itiles + cs - 1) / cs);
-    uint32_t nclusters = (uint32_t)g.sm_count / cs;
-    if (units < nclusters) nclusters = units;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(nclusters * cs);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = kSmemBytes;
-    cfg.stream = g.stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = cs;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    cudaError_t le = cs == 1   ? cudaLaunchKernelEx(&cfg, apply_tc_kernel<1>, a)
-                     : cs == 2 ? cudaLaunchKernelEx(&cfg, apply_tc_kernel<2>, a)
-                               : cudaLaunchKernelEx(&cfg, apply_tc_kernel<4>, a);
-    if (le != cudaSuccess) return fail("apply (tcgen05) launch failed: %s", cudaGetErrorString(le));
-    if (after_launch("apply (tcgen05)")) return -1;
+    if (tc_launch(a, cs)) return -1;
+  }
+  return 0;
+}
+
+
+// ---- tensor-core elimination: host side ------------------------------------------------
+// Outer panels of 128 columns.  Per outer panel and chunk of systems:
+//   panel_kernel    (solve.cuh)    factorises the 128-column window in shared memory, leaves the
+//                                  coefficient matrix E (rows x 128) and the pivot rows
+//   expand_d_kernel (apply_tc.cuh) old contents of the pivot rows, A's remaining columns and B,
+//                                  -> fp4 operand blocks
+//   apply_tc_kernel                [A_rest | B] ^= E * P_old  on tcgen05
+// then permute_kernel puts the rows into position order and writes the ranks.
+int solve_tc_run(SolveArgs &p, size_t nsys) {
+  using namespace ob2::tc;
+  int *dstatus = nullptr;
+  if (tc_prepare(&dstatus)) return -1;
+  const uint32_t rows = p.rows;
+  const uint32_t nouter = (p.cols + kOuterBytes - 1) / kOuterBytes;
+  const uint32_t ksteps = ksteps_for(kOuterBytes);
+  const uint32_t itiles = (rows + kRowsI - 1) / kRowsI;
+  // column tiles of the widest trailing update (outer panel 0)
+  auto tiles_of = [](uint32_t bytes) { return (bytes + kTileN - 1) / kTileN; };
+  const uint32_t a_rest0 = p.a_bytes > (uint32_t)kOuterBytes ? p.a_bytes - kOuterBytes : 0;
+  const uint32_t ntiles_max = tiles_of(a_rest0) + tiles_of(p.B ? p.b_bytes : 0);
+  const size_t dx_per_sys = (size_t)ntiles_max * ksteps * kBTile;
+  const size_t e_per_sys = (size_t)rows * kOuterBytes;
+  const size_t map_per_sys = ((size_t)rows * 2 + 15) / 16 * 16;
+  const size_t small_per_sys = 2 * kOuterBytes + 16;   // piv_all (u16 x 128) + tcount + npiv + pad
+  const size_t per_sys = dx_per_sys + e_per_sys + map_per_sys + small_per_sys;
+  size_t chunk = tc_ws_budget / per_sys;
+  if (chunk < 1) chunk = 1;
+  if (chunk > nsys) chunk = nsys;
+  for (;;) {
+    int rc = tc_ws_reserve(chunk * per_sys + 256);
+    if (rc < 0) return -1;
+    if (rc == 0) break;
+    if (chunk == 1) return fail("solve: cannot allocate %zu bytes of workspace", per_sys);
+    chunk = (chunk + 1) / 2;
+  }
+  uint8_t *ws = (uint8_t *)g.tc_ws;
+  uint8_t *Dx = ws;                                        ws += chunk * dx_per_sys;
+  uint8_t *E = ws;                                         ws += chunk * e_per_sys;
+  uint16_t *maps = (uint16_t *)ws;                         ws += chunk * map_per_sys;
+  uint16_t *piv_all = (uint16_t *)ws;                      ws += chunk * 2 * kOuterBytes;
+  uint32_t *tcount = (uint32_t *)ws;                       ws += chunk * 4;
+  uint32_t *npiv = (uint32_t *)ws;
+  int cs = g.tc_cluster;
+  if (cs != 1 && cs != 2 && cs != 4) cs = 1;
+  // permutation kernel: row map + staging area in shared memory
+  const size_t pmap = ((size_t)rows * 2 + 15) / 16 * 16;
+  if (pmap + 64 + (size_t)rows * 16 > g.smem_optin) return fail("solve: %u rows do not fit the permutation stage", rows);
+  const uint32_t stage_bytes = (uint32_t)((g.smem_optin - pmap - 64) & ~(size_t)15);
+  static bool perm_attr = false;
+  if (!perm_attr) {
+    CK(cudaFuncSetAttribute(permute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_optin));
+    perm_attr = true;
+  }
+  for (size_t first = 0; first < nsys; first += chunk) {
+    const uint32_t cnt = (uint32_t)((nsys - first < chunk) ? (nsys - first) : chunk);
+    uint8_t *A = p.A + first * p.a_ss;
+    uint8_t *B = p.B ? p.B + first * p.b_ss : nullptr;
+    const uint32_t grid = cnt < (uint32_t)g.sm_count ? cnt : (uint32_t)g.sm_count;
+    for (uint32_t outer = 0; outer < nouter; outer++) {
+      PanelArgs pa;
+      memset(&pa, 0, sizeof pa);
+      pa.A = A; pa.a_rs = p.a_rs; pa.a_ss = p.a_ss; pa.rows = rows; pa.cols = p.cols; pa.a_bytes = p.a_bytes;
+      pa.E = E; pa.pos2phys = maps; pa.tcount = tcount; pa.piv_all = piv_all; pa.npiv = npiv;
+      pa.pivcols = p.pivcols ? p.pivcols + first * rows : nullptr;
+      pa.nsys = cnt; pa.outer = outer; pa.inv = p.inv; pa.no_fast_panel = p.no_fast_panel;
+      // the row map lives in global memory as [sys][rows] u16 with a 16-byte aligned pitch
+      int rc = launch_panel_t<6, 128>(pa, grid, g.smem_optin, g.stream);
+      if (rc) return fail("solve (tensor-core path): panel kernel launch configuration failed (%d)", rc);
+      if (after_launch("solve (outer panel)")) return -1;
+      const uint32_t a_col0 = (outer + 1) * kOuterBytes;
+      const uint32_t a_rest = p.a_bytes > a_col0 ? p.a_bytes - a_col0 : 0;
+      const uint32_t b_cols = B ? p.b_bytes : 0;
+      if (a_rest == 0 && b_cols == 0) continue;
+      TcRegion reg[2];
+      memset(reg, 0, sizeof reg);
+      uint32_t nreg = 0, ntiles = 0;
+      if (a_rest) {
+        reg[nreg].base = A; reg[nreg].rs = p.a_rs; reg[nreg].ss = p.a_ss; reg[nreg].col0 = a_col0;
+        reg[nreg].ncols = a_rest; reg[nreg].tile0 = ntiles;
+        ntiles += tiles_of(a_rest);
+        nreg++;
+      }
+      if (b_cols) {
+        reg[nreg].base = B; reg[nreg].rs = p.b_rs; reg[nreg].ss = p.b_ss; reg[nreg].col0 = 0;
+        reg[nreg].ncols = b_cols; reg[nreg].tile0 = ntiles;
+        ntiles += tiles_of(b_cols);
+        nreg++;
+      }
+      ExpandArgs e;
+      memset(&e, 0, sizeof e);
+      e.reg[0] = reg[0]; e.reg[1] = reg[1]; e.nreg = nreg; e.Kc = kOuterBytes;
+      e.rowmap = piv_all; e.rowmap_stride = kOuterBytes; e.nrows = npiv;
+      e.Dx = Dx; e.ksteps = ksteps; e.ntiles = ntiles; e.nsys = cnt;
+      const size_t work = (size_t)cnt * ntiles * ksteps * (kTileN / 4);
+      uint32_t eg = (uint32_t)((work + 255) / 256);
+      if (eg > (uint32_t)g.sm_count * 16) eg = (uint32_t)g.sm_count * 16;
+      expand_d_kernel<<<eg, 256, 0, g.stream>>>(e);
+      if (after_launch("solve (pivot-row expansion)")) return -1;
+      ApplyTcArgs a;
+      memset(&a, 0, sizeof a);
+      a.C = E; a.c_stride = kOuterBytes; a.c_ss = e_per_sys; a.M = rows; a.Kc = kOuterBytes; a.Dx = Dx;
+      a.ksteps = ksteps; a.ntiles = ntiles; a.itiles = itiles; a.nsys = cnt;
+      a.reg[0] = reg[0]; a.reg[1] = reg[1]; a.nreg = nreg;
+      a.accumulate = 1; a.status = dstatus; a.dbg = 0;
+      if (tc_launch(a, cs)) return -1;
+    }
+    PermuteArgs pm;
+    memset(&pm, 0, sizeof pm);
+    pm.A = A; pm.a_rs = p.a_rs; pm.a_ss = p.a_ss; pm.a_bytes = p.a_bytes;
+    pm.B = B; pm.b_rs = p.b_rs; pm.b_ss = p.b_ss; pm.b_bytes = B ? p.b_bytes : 0;
+    pm.rows = rows; pm.nsys = cnt; pm.pos2phys = maps; pm.tcount = tcount; pm.rank = p.rank + first;
+    pm.stage_bytes = stage_bytes;
+    permute_kernel<<<grid, 512, pmap + stage_bytes + 16, g.stream>>>(pm);
+    if (after_launch("solve (row permutation)")) return -1;
   }
   return 0;
 }

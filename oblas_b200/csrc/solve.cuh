@@ -683,6 +683,272 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
 #endif
 }
 
+// ===========================================================================
+// Outer-panel factorisation for the tensor-core elimination (solve_tc.cuh).
+//
+// The batch is eliminated in OUTER panels of 128 columns.  For outer panel `outer` this kernel
+// does, per system, what solve_kernel does for 8 consecutive 16-column panels -- but its
+// trailing update only touches (a) the 128-byte column window of the outer panel itself and
+// (b) E, a rows x 128-byte coefficient matrix: E[r][g] is the multiple of the ORIGINAL
+// (pre-outer-panel) content of the g-th outer pivot row that has been added to row r.  E is
+// maintained exactly like a right-hand side: every 16-column step applies  E ^= V * E_piv,
+// after the unit e_g has been injected into the E row of each new pivot (its own content
+// becomes basis vector g).  Afterwards, for every row and every column right of the window,
+//       new_row[r] = old_row[r] ^ E[r] * P_old        (P_old = old contents of the pivot rows)
+// holds, pivot rows included (E[piv_g][g] gets the usual own-term cancellation), and that
+// rank-128 update of A's remaining columns and of all of B is one GF(256) matrix product,
+// done by the tcgen05 kernel.  The row map, the pivot count and the pivot columns persist in
+// global memory between the launches.
+// ===========================================================================
+struct PanelArgs {
+  uint8_t *A;
+  size_t a_rs, a_ss;
+  uint32_t rows, cols, a_bytes;
+  uint8_t *E;               // [nsys][rows][128]
+  uint16_t *pos2phys;       // [nsys][rows]   row map (position -> physical row)
+  uint32_t *tcount;         // [nsys]         pivots found so far
+  uint16_t *piv_all;        // [nsys][128]    physical rows of this outer panel's pivots
+  uint32_t *npiv;           // [nsys]         their number
+  uint32_t *pivcols;        // [nsys][rows] or null
+  uint32_t nsys;
+  uint32_t outer;           // outer panel index
+  const uint8_t *inv;
+  int no_fast_panel;
+};
+
+constexpr int kOuterBytes = 128;   // outer panel width (GF(256): bytes == columns)
+
+template <int KB, int WT>
+__global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
+  constexpr int EXP = 8, NBW = 4;
+  using SM = SolveSmem<EXP, NBW, KB, WT>;
+  using G = Geo<NBW, KB, WT>;
+  constexpr int NPIV = SM::NPIV;                 // 16 columns per inner panel
+  constexpr uint32_t EMASK = 0xffu;
+  constexpr uint32_t INNER = kOuterBytes / (NBW * 4);   // inner panels per outer panel (8)
+  static_assert(WT == kOuterBytes, "the window and E are one tile each");
+  const uint32_t tid = threadIdx.x, T = blockDim.x;
+  const uint32_t rows = p.rows;
+
+  OB2_DYN_SMEM(smem_raw);
+  unsigned char *sp = smem_raw;
+  uint4 *tab = reinterpret_cast<uint4 *>(sp);              sp += G::TAB_BYTES;
+  uint32_t *pan = reinterpret_cast<uint32_t *>(sp);        sp += (size_t)rows * NBW * 4;
+  uint32_t *V = reinterpret_cast<uint32_t *>(sp);          sp += (size_t)rows * NBW * 4;
+  sp = smem_raw + (((size_t)(sp - smem_raw) + 15) & ~(size_t)15);
+  uint16_t *pos2phys = reinterpret_cast<uint16_t *>(sp);   sp += ((size_t)rows * 2 + 15) / 16 * 16;
+  uint16_t *piv_phys = reinterpret_cast<uint16_t *>(sp);   sp += ((size_t)NPIV * 2 + 15) / 16 * 16;
+  uint32_t *prow = reinterpret_cast<uint32_t *>(sp);       sp += (size_t)EXP * NBW * 4;
+  uint32_t *vrow = reinterpret_cast<uint32_t *>(sp);       sp += (size_t)EXP * NBW * 4;
+  uint32_t *scal = reinterpret_cast<uint32_t *>(sp);
+
+  const uint32_t npanels = (p.cols + NPIV - 1) / NPIV;
+  const uint32_t win_off = p.outer * kOuterBytes;
+  const uint32_t win_bytes = (p.a_bytes - win_off < (uint32_t)kOuterBytes) ? (p.a_bytes - win_off) : (uint32_t)kOuterBytes;
+
+  for (uint32_t sys = blockIdx.x; sys < p.nsys; sys += gridDim.x) {
+    uint8_t *A = p.A + (size_t)sys * p.a_ss;
+    uint8_t *E = p.E + (size_t)sys * rows * kOuterBytes;
+    uint16_t *gmap = p.pos2phys + (size_t)sys * rows;
+    uint16_t *gpiv = p.piv_all + (size_t)sys * kOuterBytes;
+    for (uint32_t r = tid; r < rows; r += T) pos2phys[r] = (p.outer == 0) ? (uint16_t)r : gmap[r];
+    for (uint32_t it = tid; it < rows * (kOuterBytes / 16); it += T)
+      reinterpret_cast<uint4 *>(E)[it] = make_uint4(0, 0, 0, 0);
+    uint32_t t = (p.outer == 0) ? 0u : p.tcount[sys];   // uniform
+    uint32_t gcount = 0;                                // pivots of this outer panel so far
+    bool pan_ready = false;
+    __syncthreads();
+
+    for (uint32_t q = 0; q < INNER; q++) {
+      const uint32_t pi = p.outer * INNER + q;
+      if (pi >= npanels || t >= rows) break;
+      const uint32_t c0 = pi * NPIV;
+      const uint32_t ncols_p = (p.cols - c0 < (uint32_t)NPIV) ? (p.cols - c0) : (uint32_t)NPIV;
+      for (uint32_t r = tid; r < rows; r += T) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(A + (size_t)r * p.a_rs + (size_t)pi * (NBW * 4));
+#pragma unroll
+        for (int w = 0; w < NBW; w++) {
+          if (!pan_ready) pan[r * NBW + w] = src[w];
+          V[r * NBW + w] = 0;
+        }
+      }
+      __syncthreads();
+      uint32_t n = 0;
+      constexpr uint32_t kFastThreads = (uint32_t)((NPIV + 32 + 31) / 32 * 32);
+      bool fast = false;
+      if (ncols_p == (uint32_t)NPIV && rows - t >= (uint32_t)NPIV && kFastThreads <= T && !p.no_fast_panel)
+        fast = panel_fast<EXP, NBW>(pan, V, pos2phys, piv_phys, prow, vrow, scal,
+                                    reinterpret_cast<uint32_t *>(tab), t, rows, c0,
+                                    p.pivcols ? p.pivcols + (size_t)sys * rows : nullptr, p.inv);
+      if (fast) {
+        n = NPIV;
+        t += NPIV;
+      }
+      // general column-by-column path: identical to solve_kernel
+      for (uint32_t j = 0; !fast && j < ncols_p && t < rows; j++) {
+        const uint32_t wj = (j * EXP) >> 5, sh = (j * EXP) & 31;
+        uint32_t pos = t;
+        uint32_t ph = pos2phys[t];
+        uint32_t e = (pan[ph * NBW + wj] >> sh) & EMASK;
+        if (e == 0) {
+          if (tid == 0) scal[0] = 0xffffffffu;
+          __syncthreads();
+          uint32_t best = 0xffffffffu;
+          for (uint32_t q2 = t + 1 + tid; q2 < rows; q2 += T) {
+            uint32_t r2 = pos2phys[q2];
+            if ((pan[r2 * NBW + wj] >> sh) & EMASK) {
+              best = q2;
+              break;
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            uint32_t other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other < best ? other : best;
+          }
+          if ((tid & 31) == 0 && best != 0xffffffffu) atomicMin(&scal[0], best);
+          __syncthreads();
+          pos = scal[0];
+          __syncthreads();
+          if (pos == 0xffffffffu) continue;  // free column
+          ph = pos2phys[pos];
+          e = (pan[ph * NBW + wj] >> sh) & EMASK;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          uint16_t tmp = pos2phys[t];
+          pos2phys[t] = pos2phys[pos];
+          pos2phys[pos] = tmp;
+          piv_phys[n] = (uint16_t)ph;
+          if (p.pivcols) p.pivcols[(size_t)sys * rows + t] = c0 + j;
+        }
+        const uint32_t inv = (uint32_t)__ldg(p.inv + e);
+        if (tid < (uint32_t)NBW) {
+          uint32_t w = mul_scalar_word<EXP>(pan[ph * NBW + tid], inv);
+          uint32_t v = mul_scalar_word<EXP>(V[ph * NBW + tid], inv);
+          if (((n * EXP) >> 5) == tid) v ^= inv << ((n * EXP) & 31);
+          pan[ph * NBW + tid] = w;
+          V[ph * NBW + tid] = v;
+#pragma unroll
+          for (int b = 0; b < EXP; b++) {
+            prow[b * NBW + tid] = w;
+            vrow[b * NBW + tid] = v;
+            w = xtime<EXP>(w);
+            v = xtime<EXP>(v);
+          }
+        }
+        __syncthreads();
+        for (uint32_t r = tid; r < rows; r += T) {
+          if (r == ph) continue;
+          uint32_t f = (pan[r * NBW + wj] >> sh) & EMASK;
+          if (!f) continue;
+          PanelVec<NBW> pr = ldv<NBW>(pan + r * NBW), vr = ldv<NBW>(V + r * NBW);
+#pragma unroll
+          for (int b = 0; b < EXP; b++) {
+            uint32_t m = 0u - ((f >> b) & 1u);
+            PanelVec<NBW> pb = ldv<NBW>(prow + b * NBW), vb = ldv<NBW>(vrow + b * NBW);
+#pragma unroll
+            for (int w = 0; w < NBW; w++) {
+              pr.w[w] ^= m & pb.w[w];
+              vr.w[w] ^= m & vb.w[w];
+            }
+          }
+          stv<NBW>(pan + r * NBW, pr);
+          stv<NBW>(V + r * NBW, vr);
+        }
+        __syncthreads();
+        n++;
+        t++;
+      }
+      pan_ready = false;
+      if (n == 0) continue;
+      if (!fast) {
+        for (uint32_t s = tid; s < n; s += T) {
+          uint32_t ph = piv_phys[s];
+          V[ph * NBW + ((s * EXP) >> 5)] ^= 1u << ((s * EXP) & 31);
+        }
+      }
+      // the new pivots become basis vectors gcount .. gcount+n-1 of the outer panel
+      for (uint32_t s = tid; s < n; s += T) {
+        const uint32_t ph = piv_phys[s];
+        gpiv[gcount + s] = (uint16_t)ph;
+        E[(size_t)ph * kOuterBytes + gcount + s] ^= 1;
+      }
+      __syncthreads();
+      const uint32_t next_off = (q + 1 < INNER && pi + 1 < npanels) ? (pi + 1) * (NBW * 4) : 0xffffffffu;
+      update_tile<EXP, NBW, KB, WT>(A, p.a_rs, rows, win_off, win_bytes, n, piv_phys, V, tab, pan, next_off);
+      pan_ready = next_off != 0xffffffffu && next_off < p.a_bytes;
+      update_tile<EXP, NBW, KB, WT>(E, kOuterBytes, rows, 0, kOuterBytes, n, piv_phys, V, tab, nullptr, 0xffffffffu);
+      gcount += n;
+    }
+    // own-term cancellation of the outer update: new pivot row = E * P_old, not old ^ E * P_old
+    for (uint32_t g2 = tid; g2 < gcount; g2 += T) E[(size_t)gpiv[g2] * kOuterBytes + g2] ^= 1;
+    for (uint32_t r = tid; r < rows; r += T) gmap[r] = pos2phys[r];
+    if (tid == 0) {
+      p.tcount[sys] = t;
+      p.npiv[sys] = gcount;
+    }
+    __syncthreads();
+  }
+}
+
+template <int KB, int WT>
+inline int launch_panel_t(const PanelArgs &p, uint32_t grid, size_t smem_limit, cudaStream_t s) {
+  using SM = SolveSmem<8, 4, KB, WT>;
+  size_t smem = SM::bytes(p.rows);
+  if (smem > smem_limit || p.rows > 65535u || p.rows == 0) return -1;
+  auto k = panel_kernel<KB, WT>;
+#ifndef OB2_EMU
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
+#endif
+  OB2_LAUNCH(k, grid, 512, smem, s, p);
+  return 0;
+}
+inline size_t panel_smem_bytes(uint32_t rows) { return SolveSmem<8, 4, 6, 128>::bytes(rows); }
+
+// rows of A and B into position order + rank, after the last outer panel
+struct PermuteArgs {
+  uint8_t *A;
+  size_t a_rs, a_ss;
+  uint32_t a_bytes;
+  uint8_t *B;
+  size_t b_rs, b_ss;
+  uint32_t b_bytes;
+  uint32_t rows, nsys;
+  const uint16_t *pos2phys;
+  const uint32_t *tcount;
+  int32_t *rank;
+  uint32_t stage_bytes;
+};
+__global__ void __launch_bounds__(512, 1) permute_kernel(const PermuteArgs p) {
+  OB2_DYN_SMEM(smem_raw);
+  const uint32_t tid = threadIdx.x, T = blockDim.x;
+  uint16_t *map = reinterpret_cast<uint16_t *>(smem_raw);
+  const size_t map_bytes = ((size_t)p.rows * 2 + 15) / 16 * 16;
+  uint4 *stage = reinterpret_cast<uint4 *>(smem_raw + map_bytes);
+  uint32_t *flag = reinterpret_cast<uint32_t *>(smem_raw + map_bytes + p.stage_bytes);
+  for (uint32_t sys = blockIdx.x; sys < p.nsys; sys += gridDim.x) {
+    if (tid == 0) {
+      p.rank[sys] = (int32_t)p.tcount[sys];
+      *flag = 0;
+    }
+    __syncthreads();
+    uint32_t moved = 0;
+    for (uint32_t r = tid; r < p.rows; r += T) {
+      uint16_t v = p.pos2phys[(size_t)sys * p.rows + r];
+      map[r] = v;
+      moved |= (v != r);
+    }
+    if (moved) atomicOr(flag, 1u);
+    __syncthreads();
+    if (*flag) {
+      permute_rows(p.A + (size_t)sys * p.a_ss, p.a_rs, p.rows, p.a_bytes, map, stage, p.stage_bytes);
+      if (p.B) permute_rows(p.B + (size_t)sys * p.b_ss, p.b_rs, p.rows, p.b_bytes, map, stage, p.stage_bytes);
+    }
+    __syncthreads();
+  }
+}
+
 // rows limit: shared memory (SolveSmem::bytes <= 227 KB) and the u16 row map.
 template <int EXP, int NBW, int KB, int WT>
 inline int launch_solve_t(const SolveArgs &p, uint32_t grid, uint32_t threads,

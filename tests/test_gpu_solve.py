@@ -17,11 +17,12 @@ from oblas_b200 import capi, device
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", autouse=True, params=[(-1, 0), (0, 0), (1, 0), (2, 0), (-1, 1)],
-                ids=["geo_default", "geo4x256", "geo6x128", "geo7x64", "general_panel_path"])
+@pytest.fixture(scope="module", autouse=True, params=[(-1, 0), (0, 0), (1, 0), (2, 0), (-1, 1), (3, 0), (3, 1)],
+                ids=["auto", "geo4x256", "geo6x128", "geo7x64", "general_panel_path", "tcgen05", "tcgen05_general_panel"])
 def _bind(cuda_lib, request):
-    """every test of this module runs once per Four-Russians table geometry, and once with
-    the register-resident fast panel factorisation disabled"""
+    """every test of this module runs once per Four-Russians table geometry, once with the
+    register-resident fast panel factorisation disabled, and (GF(256)) on the tensor-core path
+    (outer panels of 128 columns + tcgen05 rank-128 updates) with both panel factorisations"""
     device.bind(0)
     geo, general = request.param
     cuda_lib.oblas_b200_set_tuning(geo, geo)
