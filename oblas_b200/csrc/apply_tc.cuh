@@ -53,12 +53,14 @@ constexpr int kBTile = kTileN * 32;          // bytes of one B-operand block (15
 // when they all store the same bit-plane row: bank group = (2*group + core + row) mod 8.
 constexpr int kALbo = 144, kASbo = 288;
 constexpr int kATile = 16 * kASbo;           // bytes of one A-operand block (4608)
-constexpr int kBuilderWarps = 4;             // warps 6..9, one step each, round robin
+constexpr int kEpiWarps = 8;                 // warps 0..7: lane quarter = warp % 4, column half = warp / 4
+constexpr int kProdWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1, kBuild0 = kEpiWarps + 2;
+constexpr int kBuilderWarps = 4;             // warps 10..13, one stage each, round robin
 constexpr int kSPS = 2;                      // K-steps per pipeline stage (one barrier round trip per 4 MMAs)
 constexpr int kStages = 5;
 constexpr int kBStage = kSPS * kBTile, kAStage = kSPS * kATile;
 constexpr int kSfCol = 480;                  // TMEM columns 480..511: scale factors (all 1.0)
-constexpr int kThreads = 32 * (6 + kBuilderWarps);
+constexpr int kThreads = 32 * (kBuild0 + kBuilderWarps);
 constexpr int kLutBytes = 256 * 32;
 constexpr size_t kSmemBytes = (size_t)kStages * (kBStage + kAStage) + kLutBytes + 256 + 1024;
 constexpr uint32_t kSpinLimit = 1u << 24;    // bounded waits: never hang the device
@@ -277,11 +279,11 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
       mbar_init(empty_bar(s), CS);      // tcgen05.commit of every CTA in the cluster
     }
     mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 128);
+    mbar_init(tmem_empty, 32 * kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
   const uint32_t nst = ksteps / kSPS;   // pipeline stages per tile
   if (CS > 1) cluster_sync_all();   // every CTA's barriers are initialised before any peer touches them
 
-  if (warp == 4) {
+  if (warp == kProdWarp) {
     // ------------------------------------------------------------ producer (TMA engine)
     // The whole warp runs the loop (warp-uniform control flow and addresses, so the compiler
     // keeps them in uniform registers); one elected lane issues the copy.
@@ -339,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
         if (++s == kStages) { s = 0; ph ^= 1u; }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------ MMA issuer
     // Warp-uniform loop, one elected lane issues.  A single thread issues ~1 instruction per
     // 4-5 clocks, so the per-step instruction count is what bounds the MMA rate: descriptors
@@ -375,9 +377,9 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
       }
       if (ok && leader) tc_commit(tmem_full);
     }
-  } else if (warp >= 6) {
+  } else if (warp >= kBuild0) {
     // ------------------------------------------------------------ A-operand builders
-    const uint32_t b = warp - 6;          // this warp builds the stages with G % kBuilderWarps == b
+    const uint32_t b = warp - kBuild0;          // this warp builds the stages with G % kBuilderWarps == b
     const uint32_t i = lane >> 1, q = lane & 1u;
     const bool c_vec = ((p.c_stride & 3) == 0) && ((p.c_ss & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 3) == 0);
     uint32_t G = 0;                       // stages of the tiles done so far
@@ -435,63 +437,88 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
       G += nst;
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 0..3)
+    // ------------------------------------------------------------ epilogue (warps 0..7)
+    // warp w reads TMEM lanes 32*(w%4).. (= 4 rows x 8 bit planes) and the 32-column chunks
+    // [c_lo, c_hi) of the tile: warps 0-3 the first 8 chunks, warps 4-7 the other 7.
+    const uint32_t lq = warp & 3u;
+    constexpr int kChunks = kTileN / 32;
+    const int c_lo = (warp < 4) ? 0 : 8, c_hi = (warp < 4) ? 8 : kChunks;
+    auto ld_chunk = [&](uint32_t (&r)[32], uint32_t cc) {
+      const uint32_t ta = tm + ((lq * 32u) << 16) + cc * 32;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(ta) : "memory");
+    };
+    // tcgen05.wait::ld with the destination registers as in/out operands: nothing that reads them
+    // can be scheduled above the wait
+    auto wait_chunk = [&](uint32_t (&r)[32]) {
+      asm volatile("tcgen05.wait::ld.sync.aligned;"
+                   : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                     "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                     "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                     "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                   :: "memory");
+    };
     uint32_t iter = 0;
     for (uint32_t t = unit0; t < ntotal; t += ustep, iter++) {
       const uint32_t snt = t / igroups, it = (t % igroups) * CS + rank;
       const uint32_t sys = snt / p.ntiles, nt = snt - sys * p.ntiles;
       const TcRegion &rg = p.reg[(p.nreg > 1 && nt >= p.reg[1].tile0) ? 1 : 0];
-      const uint32_t row0 = it * kRowsI + warp * 4;
+      const uint32_t row0 = it * kRowsI + lq * 4;
       const uint32_t ncol0 = (nt - rg.tile0) * kTileN;          // first column of the tile inside the region
       uint8_t *ybase = rg.base + (size_t)sys * rg.ss + rg.col0;
-      // accumulate mode: the old bytes of the first chunk are fetched while the MMAs still run
-      uint32_t oldv = 0;
-      auto load_old = [&](uint32_t cc) -> uint32_t {
-        uint32_t o = 0;
-        const uint32_t n = ncol0 + cc * 32 + lane;
-        if (p.accumulate && n < rg.ncols) {
+      // Output mapping of a 32-column chunk: lane = (row rr = lane / 8, columns 4*gc .. 4*gc+3 with
+      // gc = lane % 8), i.e. one aligned 32-bit word of Y per lane and 32 contiguous bytes per row.
+      const uint32_t rr = lane >> 3, gc = lane & 7u;
+      const bool row_ok = row0 + rr < p.M;
+      uint8_t *yrow = ybase + (size_t)(row0 + rr) * rg.rs + ncol0 + 4 * gc;
+      // accumulate mode: the old words of this warp's chunks are fetched while the MMAs still run
+      uint32_t oldw[8];
 #pragma unroll
-          for (int rr = 0; rr < 4; rr++)
-            if (row0 + rr < p.M) o |= (uint32_t)ybase[(size_t)(row0 + rr) * rg.rs + n] << (8 * rr);
-        }
-        return o;
-      };
-      oldv = load_old(0);
-      if (!mbar_wait_warp(tmem_full, iter & 1u, p.status, 256)) break;
+      for (int k = 0; k < 8; k++) {
+        const int cc = c_lo + k;
+        oldw[k] = 0;
+        if (p.accumulate && cc < c_hi && row_ok && ncol0 + cc * 32 + 4 * gc < rg.ncols)
+          oldw[k] = *reinterpret_cast<const uint32_t *>(yrow + cc * 32);
+      }
+      if (!mbar_wait_warp(tmem_full, iter & 1u, p.status, 128)) break;
       tc_fence_after();
-#pragma unroll 1
-      for (uint32_t cc = 0; cc < (uint32_t)kTileN / 32; cc++) {
-        uint32_t r[32];
-        const uint32_t ta = tm + ((warp * 32u) << 16) + cc * 32;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(ta) : "memory");
-        const uint32_t cur_old = oldv;
-        if (cc + 1 < (uint32_t)kTileN / 32) oldv = load_old(cc + 1);   // next chunk's old bytes in flight
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        uint32_t mine = 0;
+      uint32_t ra[32], rb[32];
+      ld_chunk(ra, c_lo);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int cc = c_lo + k;
+        if (cc >= c_hi) break;
+        uint32_t (&cur)[32] = (k & 1) ? rb : ra;
+        uint32_t (&nxt)[32] = (k & 1) ? ra : rb;
+        wait_chunk(cur);
+        if (cc + 1 < c_hi) ld_chunk(nxt, cc + 1);    // next chunk's TMEM read overlaps this chunk's packing
+        // parity of every accumulator (integer-valued fp32 < 2^23: adding 2^23 leaves it in the
+        // mantissa LSB), column c = 4*j + k2 packed at bit k2*8 + j of this lane's word
+        uint32_t w = 0;
 #pragma unroll
         for (int c = 0; c < 32; c++) {
-          // integer-valued fp32 < 2^23: adding 2^23 leaves the parity in the mantissa LSB
-          const uint32_t bit = __float_as_uint(__uint_as_float(r[c]) + 8388608.0f) & 1u;
-          const uint32_t v = __ballot_sync(0xffffffffu, bit != 0u);
-          if (lane == (uint32_t)c) mine = v;
+          const uint32_t bits = __float_as_uint(__uint_as_float(cur[c]) + 8388608.0f);
+          const int pos = (c & 3) * 8 + (c >> 2);
+          w |= (bits << pos) & (1u << pos);
         }
-        mine ^= cur_old;
-        const uint32_t n = ncol0 + cc * 32 + lane;     // column inside the region
-        if (n < rg.ncols) {
+        // 8x8 bit transposes across the 8 lanes (bit planes) of a row: lane bit i <-> index bit i.
+        // Afterwards lane (row rr, gc) holds bytes Y[rr][4*gc .. 4*gc+3] (bit a = plane a).
 #pragma unroll
-          for (int rr = 0; rr < 4; rr++) {
-            const uint32_t row = row0 + rr;
-            if (row < p.M) ybase[(size_t)row * rg.rs + n] = (uint8_t)(mine >> (8 * rr));
-          }
+        for (int i2 = 0; i2 < 3; i2++) {
+          const uint32_t d = 1u << i2;
+          const uint32_t m0 = (i2 == 0) ? 0x55555555u : (i2 == 1) ? 0x33333333u : 0x0f0f0f0fu;
+          const uint32_t tw = __shfl_xor_sync(0xffffffffu, w, d);
+          w = (lane & d) ? ((w & ~m0) | ((tw & ~m0) >> d)) : ((w & m0) | ((tw & m0) << d));
         }
+        w ^= oldw[k];
+        if (row_ok && ncol0 + cc * 32 + 4 * gc < rg.ncols) *reinterpret_cast<uint32_t *>(yrow + cc * 32) = w;
       }
       tc_fence_before();
       mbar_arrive(tmem_empty);
@@ -501,7 +528,7 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
   __syncthreads();
   // no CTA leaves while a peer may still multicast into its shared memory or signal its barriers
   if (CS > 1) cluster_sync_all();
-  if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm) : "memory");
+  if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm) : "memory");
 }
 
 // K-steps of one tile: ceil(Kc / 8) rounded up to whole pipeline stages
