@@ -79,13 +79,12 @@ void oblas_b200_set_async(int async);
 /* Four-Russians table geometry of the elimination / apply kernels (tuning knob for
  * measurements): 0 = 4-bit groups, 256-byte tiles; 1 = 6-bit groups, 128-byte tiles;
  * 2 = 7-bit groups, 64-byte tiles; -1 = library default.  Results are identical.
- * apply_geo = 3 forces the tensor-core path of the dense apply (tcgen05 kind::mxf4
- * bit-sliced GF(2) product, apply_tc.cuh); -1 picks it when M >= 256, Kc >= 64 and
- * nbytes >= 480, the shared-memory table kernel otherwise. */
+ * Value 3 forces the tensor-core path (tcgen05 kind::mxf4 bit-sliced GF(2) products,
+ * apply_tc.cuh): for apply_geo the dense apply, for solve_geo the GF(256) elimination in outer
+ * panels of 128 columns with tcgen05 rank-128 updates.  -1 picks it by size (apply: M >= 256,
+ * Kc >= 64, nbytes >= 480; solve: GF(256), rows >= 512, cols >= 256, strided batches) and the
+ * shared-memory table kernels otherwise. */
 void oblas_b200_set_tuning(int solve_geo, int apply_geo);
-/* CTAs per thread-block cluster of the tensor-core apply (each operand block is read from
- * L2 once per cluster and multicast): 1, 2 or 4; 0 = library default */
-void oblas_b200_set_apply_cluster(int ctas);
 /* diagnostics/tests: general_only != 0 disables the register-resident fast panel
  * factorisation (identical results, slower) */
 void oblas_b200_set_panel_path(int general_only);

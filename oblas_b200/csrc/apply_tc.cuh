@@ -1,6 +1,8 @@
-// apply_tc.cuh -- dense GF(256) apply  Y = C * D  on the 5th-generation tensor cores
-// (north_star: "a bit-sliced GF(2) product ... reduced mod 2,
-// kept only if ncu shows it beating the LUT path").
+// apply_tc.cuh -- GF(256) matrix products on the 5th-generation tensor cores: the dense apply
+// Y = C * D and the rank-128 trailing update of the blocked
+// elimination (rows a-9; host side in oblas_b200.cu: apply_tc_run / solve_tc_run).
+// north_star: "a bit-sliced GF(2) product ... reduced mod 2, kept only if ncu shows it beating
+// the LUT path" -- it does: profiles/r01_ncu_apply_tc.json, DESIGN.md section 4.
 //
 // The caller-side loop this replaces is  for i, j: oaxpy(Y, D, i, j, C[i][j])
 // (octmat.c:32-46 -> oblas_ref.c:1-8).  GF(256) multiplication by a constant is GF(2)-linear,
@@ -15,24 +17,31 @@
 // Both operands only hold 0 and 1, so they are stored as e2m1 (fp4) values 0.0 / 1.0 and
 // multiplied by tcgen05.mma kind::mxf4 (block scales all 1.0 = ue8m0 0x7F) with fp32
 // accumulation in TMEM -- exact for sums below 2^24 (measured: tools/peaks.cu, umma_exact),
-// at 16384 bit-MACs = 256 GF(256) MACs per clock per SM (4.3x the shared-memory LUT ceiling).
+// at 16384 bit-MACs = 256 GF(256) MACs per clock per SM (2.75x the shared-memory LUT ceiling).
 //
 // Data flow
-//   expand_d_kernel   D (Kc x nbytes)  ->  Dx: per (column tile of 480 bytes, step of 8
-//                     coefficient columns) one 15 KB block that is already the shared-memory
-//                     image of the B operand (K-major, no swizzle: 8x16-byte core matrices,
-//                     LBO = 128, SBO = 256); 4 bytes of fp4 per byte of D.  Written once,
-//                     read by every row tile.
-//   apply_tc_kernel   persistent, 1 CTA per SM, warp specialised:
-//                       warp 4      producer: one cp.async.bulk (TMA engine) per stage (2 steps), Dx -> smem
-//                       warps 6-9   A-operand builders: 16 rows x 8 coefficients of C per step,
+//   expand_d_kernel   rows of D  ->  Dx: per (half tile of 240 byte columns, step of 8 rows)
+//                     one 7680-byte block that is already the shared-memory image of the B
+//                     operand (K-major, no swizzle: 8x16-byte core matrices, LBO = 128,
+//                     SBO = 256); 4 bytes of fp4 per byte of D.  Written once, read by every
+//                     row tile.  In the elimination the rows are the pivot rows of the outer
+//                     panel, gathered through the row map.
+//   apply_tc_kernel<NH>  persistent, 1 CTA per SM, warp specialised, 14 warps:
+//                       warp 8      producer: cp.async.bulk (TMA engine) per stage, Dx -> smem
+//                       warps 10-13 A-operand builders: 16 rows x 8 coefficients of C per step,
 //                                   each coefficient expanded to its 8x8 bit matrix through a
-//                                   256 x 32-byte table in shared memory (round robin over steps)
-//                       warp 5      one thread issues 2 x tcgen05.mma (M=128, N=240, K=64) per
-//                                   step into 480 TMEM columns, tcgen05.commit frees the stage
-//                       warps 0-3   epilogue: tcgen05.ld, parity, __ballot_sync packs the 8 bit
-//                                   lanes of 4 rows into 4 result bytes per column, stores
-//                     5-stage mbarrier ring (2 steps = 4 MMAs per stage) between producers and the MMA thread.
+//                                   256 x 32-byte table in shared memory (round robin over stages)
+//                       warp 9      one elected thread issues tcgen05.mma (M=128, N=240, K=64),
+//                                   tcgen05.commit frees the stage
+//                       warps 0-7   epilogue: tcgen05.ld, parity, 8x8 bit transposes across the 8
+//                                   bit-plane lanes of a row, 32-bit coalesced stores (XOR with the
+//                                   old contents in accumulate mode)
+//                     mbarrier ring between producers and the MMA thread, 2 K-steps per stage.
+//                     NH = 2: tile = 16 rows x 480 bytes, one accumulator set (480 TMEM columns),
+//                             5 stages; the apply with a long inner dimension.
+//                     NH = 1: tile = 16 rows x 240 bytes, two accumulator sets: the epilogue of a
+//                             tile runs under the MMAs of the next one; 8 stages.  The rank-128
+//                             update of the elimination (inner dimension 16 steps only).
 // TMEM lane (16 rows x 8 bit planes) = i*8 + a, TMEM column = symbol byte n.
 //
 // Only the product build sees this file (no host-thread emulation of tcgen05).
@@ -42,28 +51,37 @@
 namespace ob2 {
 namespace tc {
 
-constexpr int kHalfN = 240;                  // N of one MMA
-constexpr int kTileN = 2 * kHalfN;           // symbol bytes per CTA tile
+constexpr int kHalfN = 240;                  // N of one MMA = columns of a half tile
 constexpr int kRowsI = 16;                   // C/Y rows per CTA tile (x 8 bit planes = 128 lanes)
 constexpr int kStepJ = 8;                    // coefficient columns per step (x 8 bits = K 64)
-constexpr int kBTile = kTileN * 32;          // bytes of one B-operand block (15360)
+constexpr int kHBlock = kHalfN * 32;         // bytes of one B-operand block: half tile x one step (7680)
 // A-operand block: 16 row groups (one C row = 8 bit-plane rows) x 2 core matrices of 128 B.  The
 // groups are padded to 288 B and the second core matrix sits at +144 B, so that the 8 lanes of
 // a quarter-warp (row group = lane/2, core matrix = lane%2) hit 8 different 16-byte bank groups
 // when they all store the same bit-plane row: bank group = (2*group + core + row) mod 8.
 constexpr int kALbo = 144, kASbo = 288;
 constexpr int kATile = 16 * kASbo;           // bytes of one A-operand block (4608)
-constexpr int kEpiWarps = 8;                 // warps 0..7: lane quarter = warp % 4, column half = warp / 4
+constexpr int kEpiWarps = 8;                 // warps 0..7: lane quarter = warp % 4, chunk half = warp / 4
 constexpr int kProdWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1, kBuild0 = kEpiWarps + 2;
 constexpr int kBuilderWarps = 4;             // warps 10..13, one stage each, round robin
-constexpr int kSPS = 2;                      // K-steps per pipeline stage (one barrier round trip per 4 MMAs)
-constexpr int kStages = 5;
-constexpr int kBStage = kSPS * kBTile, kAStage = kSPS * kATile;
 constexpr int kSfCol = 480;                  // TMEM columns 480..511: scale factors (all 1.0)
 constexpr int kThreads = 32 * (kBuild0 + kBuilderWarps);
 constexpr int kLutBytes = 256 * 32;
-constexpr size_t kSmemBytes = (size_t)kStages * (kBStage + kAStage) + kLutBytes + 256 + 1024;
 constexpr uint32_t kSpinLimit = 1u << 24;    // bounded waits: never hang the device
+
+template <int NH>
+struct Cfg {
+  static_assert(NH == 1 || NH == 2, "half tiles per tile");
+  static constexpr int kTileN = NH * kHalfN;                 // symbol bytes per CTA tile
+  // K-steps per pipeline stage: one barrier round trip of the MMA thread per NH * kSPS = 4 MMAs
+  static constexpr int kSPS = NH == 2 ? 2 : 4;
+  static constexpr int kStages = NH == 2 ? 5 : 4;
+  static constexpr int kBStage = NH * kSPS * kHBlock;        // B bytes per stage
+  static constexpr int kAStage = kSPS * kATile;              // A bytes per stage
+  static constexpr int kAccSets = NH == 2 ? 1 : 2;           // accumulator sets in TMEM
+  static constexpr int kChunks = (kTileN + 31) / 32;         // 32-column epilogue chunks (last may be partial)
+  static constexpr size_t kSmemBytes = (size_t)kStages * (kBStage + kAStage) + kLutBytes + 256 + 1024;
+};
 
 // A byte-column range of a (batched) row-major byte matrix.  The tensor-core kernels see the
 // concatenation of up to two regions (the elimination updates A's remaining columns and B in
@@ -85,21 +103,22 @@ struct ExpandArgs {
   const uint16_t *rowmap;
   uint32_t rowmap_stride;
   const uint32_t *nrows;
-  uint8_t *Dx;             // [nsys][ntiles][ksteps][kBTile]
-  uint32_t ksteps, ntiles, nsys; // ksteps is a multiple of kSPS (steps beyond Kc are zero blocks)
+  uint8_t *Dx;             // [nsys][nhalf][ksteps][kHBlock]
+  uint32_t ksteps, nhalf, nsys;  // ksteps is a multiple of Cfg::kSPS (steps beyond Kc are zero blocks);
+                                 // region tile0 counts HALF tiles here
 };
 
 struct ApplyTcArgs {
   const uint8_t *C;        // coefficients: [nsys][M][c_stride]
   size_t c_stride, c_ss;
   uint32_t M, Kc;
-  const uint8_t *Dx;       // [nsys][ntiles][ksteps][kBTile]
-  uint32_t ksteps, ntiles, itiles, nsys;
+  const uint8_t *Dx;       // [nsys][ntiles * NH][ksteps][kHBlock]
+  uint32_t ksteps, ntiles, itiles, nsys;   // ntiles: column tiles of NH * 240 bytes per system
   TcRegion reg[2];         // Y
   uint32_t nreg;
   int accumulate;
   int *status;             // set to 1 if a barrier wait ran into the spin limit
-  int dbg;                 // diagnostics (timing experiments only, results invalid): 1 = no bulk loads, 2 = no A build
+  int dbg;                 // diagnostics (timing experiments only, results invalid): 1 = no bulk loads, 2 = no A build, 4 = no epilogue
 };
 
 // byte d -> 8 fp4 values, nibble b = e2m1 1.0 (0b0010) if bit b of d is set
@@ -115,8 +134,8 @@ OB2_D uint32_t spread_fp4(uint32_t d) {
 // D -> Dx.  One thread = 4 consecutive byte columns of one step (8 rows of D).
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) expand_d_kernel(const ExpandArgs p) {
-  constexpr uint32_t G = kTileN / 4;  // column groups per tile
-  const size_t per_sys = (size_t)p.ntiles * p.ksteps * G;
+  constexpr uint32_t G = kHalfN / 4;  // column groups per half tile
+  const size_t per_sys = (size_t)p.nhalf * p.ksteps * G;
   const size_t total = per_sys * p.nsys;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
@@ -124,10 +143,10 @@ __global__ void __launch_bounds__(256) expand_d_kernel(const ExpandArgs p) {
     const size_t li = idx - (size_t)sys * per_sys;
     const uint32_t g4 = (uint32_t)(li % G);
     const size_t rest = li / G;
-    const uint32_t ks = (uint32_t)(rest % p.ksteps), tile = (uint32_t)(rest / p.ksteps);
-    const TcRegion &rg = p.reg[(p.nreg > 1 && tile >= p.reg[1].tile0) ? 1 : 0];
+    const uint32_t ks = (uint32_t)(rest % p.ksteps), half = (uint32_t)(rest / p.ksteps);
+    const TcRegion &rg = p.reg[(p.nreg > 1 && half >= p.reg[1].tile0) ? 1 : 0];
     const uint32_t nl = g4 * 4;                              // local column
-    const uint32_t n = (tile - rg.tile0) * kTileN + nl;      // column inside the region
+    const uint32_t n = (half - rg.tile0) * kHalfN + nl;      // column inside the region
     const uint32_t nrows = p.nrows ? p.nrows[sys] : p.Kc;
     const uint8_t *src0 = rg.base + (size_t)sys * rg.ss + rg.col0 + n;
     uint32_t x[kStepJ];
@@ -140,7 +159,7 @@ __global__ void __launch_bounds__(256) expand_d_kernel(const ExpandArgs p) {
         x[jj] = *reinterpret_cast<const uint32_t *>(src0 + (size_t)row * rg.rs);
       }
     }
-    uint8_t *blk = p.Dx + (((size_t)sys * p.ntiles + tile) * p.ksteps + ks) * kBTile + (nl >> 3) * 256 + (nl & 7) * 16;
+    uint8_t *blk = p.Dx + (((size_t)sys * p.nhalf + half) * p.ksteps + ks) * kHBlock + (nl >> 3) * 256 + (nl & 7) * 16;
 #pragma unroll
     for (int bl = 0; bl < 4; bl++) {
       uint4 lo, hi;
@@ -194,27 +213,10 @@ OB2_D void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-// slice of a block to the same shared-memory offset (and full barrier) of every CTA in cta_mask
-OB2_D void bulk_g2s_multicast(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint16_t cta_mask) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask) : "memory");
-}
-OB2_D void tc_commit_multicast(uint32_t bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(cta_mask) : "memory");
-}
 OB2_D bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
   return pred != 0;
-}
-OB2_D uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-OB2_D void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 OB2_D void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 OB2_D void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -236,30 +238,111 @@ OB2_D void umma_mxf4(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t i
 }
 
 // ---------------------------------------------------------------------------------------
-// the GEMM kernel
+// Epilogue of one tile (all 8 epilogue warps): accumulators of TMEM columns [acc_col,
+// acc_col + TILE_N) -> parity -> bytes -> Y.  Warp w reads TMEM lanes 32*(w%4).. (= 4 rows x 8
+// bit planes) and half of the tile's 32-column chunks.  `wait_full` blocks until the MMAs of the
+// tile have completed; the old words of accumulate mode are fetched before it is called.
 // ---------------------------------------------------------------------------------------
-// CS = CTAs per cluster.  The CS CTAs of a cluster work on the same column tile and CS
-// consecutive row tiles; every B block is fetched from L2 once per cluster: each CTA loads 1/CS
-// of it and multicasts the slice into the shared memory of all CS CTAs, and a stage is reused
-// only after the MMA threads of all CS CTAs have released it (multicast tcgen05.commit).
-template <int CS>
-__global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs p) {
-  extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
-  // (offset arithmetic on the __shared__ array keeps the address space: LDS/STS, not generic LD/ST)
-  unsigned char *sm = tc_smem_raw + ((1024u - (smem_addr(tc_smem_raw) & 1023u)) & 1023u);
-  unsigned char *smB = sm;                                   // [kStages][kSPS][kBTile]
-  unsigned char *smA = sm + (size_t)kStages * kBStage;       // [kStages][kSPS][kATile]
-  uint32_t *lut = reinterpret_cast<uint32_t *>(smA + (size_t)kStages * kAStage);  // [256][8]
-  unsigned long long *bars = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(lut) + kLutBytes);
-  // bars[0..S) full, [S..2S) empty, [2S] tmem_full, [2S+1] tmem_empty
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 2);
-  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t bar0 = smem_addr(bars);
-  auto full_bar = [&](uint32_t s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](uint32_t s) { return bar0 + 8u * (kStages + s); };
-  const uint32_t tmem_full = bar0 + 8u * (2 * kStages), tmem_empty = bar0 + 8u * (2 * kStages + 1);
+OB2_D void tmem_ld32(uint32_t (&r)[32], uint32_t taddr) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+// tcgen05.wait::ld with the destination registers as in/out operands: nothing that reads them
+// can be scheduled above the wait
+OB2_D void tmem_wait_ld32(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :: "memory");
+}
 
-  // coefficient c -> its 8x8 bit matrix as 8 words (word a: nibble b = 2 * bit a of c*x^b)
+// Where this lane's output words of a tile live: one aligned 32-bit word per 32-column chunk.
+// Output mapping of a chunk: lane = (row rr = lane / 8, columns 4*gc .. 4*gc+3 with gc = lane % 8),
+// i.e. 32 contiguous bytes per row and warp store.
+template <int TILE_N>
+struct EpiTile {
+  static constexpr int kChunks = (TILE_N + 31) / 32, kC0 = (kChunks + 1) / 2;
+  uint8_t *yrow;
+  uint32_t ncol0, ncols, gc;
+  int c_lo, c_hi;
+  bool row_ok;
+  OB2_D void set(uint32_t warp, uint32_t lane, const TcRegion &rg, uint32_t sys, uint32_t tile_in_region,
+                 uint32_t it, uint32_t M) {
+    const uint32_t lq = warp & 3u, rr = lane >> 3;
+    gc = lane & 7u;
+    c_lo = (warp < 4) ? 0 : kC0;
+    c_hi = (warp < 4) ? kC0 : kChunks;
+    const uint32_t row = it * kRowsI + lq * 4 + rr;
+    row_ok = row < M;
+    ncol0 = tile_in_region * TILE_N;          // first column of the tile inside the region
+    ncols = rg.ncols;
+    yrow = rg.base + (size_t)sys * rg.ss + rg.col0 + (size_t)row * rg.rs + ncol0 + 4 * gc;
+  }
+  OB2_D bool col_ok(int cc) const {
+    const uint32_t ct = (uint32_t)cc * 32 + 4 * gc;        // column inside the tile
+    return row_ok && ct < (uint32_t)TILE_N && ncol0 + ct < ncols;
+  }
+  // accumulate mode: the old contents of this warp's chunks (issued one tile ahead of their use)
+  OB2_D void load_old(uint32_t (&oldw)[kC0], int accumulate) const {
+#pragma unroll
+    for (int k = 0; k < kC0; k++) {
+      const int cc = c_lo + k;
+      oldw[k] = 0;
+      if (accumulate && cc < c_hi && col_ok(cc)) oldw[k] = *reinterpret_cast<const uint32_t *>(yrow + cc * 32);
+    }
+  }
+};
+
+// accumulators of TMEM columns [acc_col, acc_col + TILE_N) -> parity -> bytes -> Y (XOR oldw)
+template <int TILE_N>
+OB2_D void epilogue_tile(uint32_t tm, uint32_t acc_col, uint32_t warp, uint32_t lane, const EpiTile<TILE_N> &e,
+                         const uint32_t (&oldw)[EpiTile<TILE_N>::kC0]) {
+  constexpr int kC0 = EpiTile<TILE_N>::kC0;
+  const uint32_t tbase = tm + (((warp & 3u) * 32u) << 16) + acc_col;
+  uint32_t ra[32], rb[32];
+  tmem_ld32(ra, tbase + e.c_lo * 32);
+#pragma unroll
+  for (int k = 0; k < kC0; k++) {
+    const int cc = e.c_lo + k;
+    if (cc >= e.c_hi) break;
+    uint32_t (&cur)[32] = (k & 1) ? rb : ra;
+    uint32_t (&nxt)[32] = (k & 1) ? ra : rb;
+    tmem_wait_ld32(cur);
+    if (cc + 1 < e.c_hi) tmem_ld32(nxt, tbase + (cc + 1) * 32);   // next chunk's TMEM read overlaps this chunk's packing
+    // parity of every accumulator (integer-valued fp32 < 2^23: adding 2^23 leaves it in the
+    // mantissa LSB), column c = 4*j + k2 packed at bit k2*8 + j of this lane's word
+    uint32_t w = 0;
+#pragma unroll
+    for (int c = 0; c < 32; c++) {
+      const uint32_t bits = __float_as_uint(__uint_as_float(cur[c]) + 8388608.0f);
+      const int pos = (c & 3) * 8 + (c >> 2);
+      w |= (bits << pos) & (1u << pos);
+    }
+    // 8x8 bit transposes across the 8 lanes (bit planes) of a row: lane bit i <-> index bit i.
+    // Afterwards lane (row rr, gc) holds bytes Y[rr][4*gc .. 4*gc+3] (bit a = plane a).
+#pragma unroll
+    for (int i2 = 0; i2 < 3; i2++) {
+      const uint32_t d = 1u << i2;
+      const uint32_t m0 = (i2 == 0) ? 0x55555555u : (i2 == 1) ? 0x33333333u : 0x0f0f0f0fu;
+      const uint32_t tw = __shfl_xor_sync(0xffffffffu, w, d);
+      w = (lane & d) ? ((w & ~m0) | ((tw & ~m0) >> d)) : ((w & m0) | ((tw & m0) << d));
+    }
+    w ^= oldw[k];
+    if (e.col_ok(cc)) *reinterpret_cast<uint32_t *>(e.yrow + cc * 32) = w;
+  }
+}
+
+// coefficient c -> its 8x8 bit matrix as 8 words (word a: nibble b = 2 * bit a of c*x^b); 256 threads
+OB2_D void build_bitmatrix_lut(uint32_t *lut, uint32_t tid) {
   if (tid < 256) {
     uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t pw = tid;
@@ -273,13 +356,61 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
     dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
     dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
   }
+}
+
+// one K-step of the A operand: 4 coefficients of C row `i` (this lane: row i = lane/2, core
+// matrix q = lane%2) -> 8 bit-plane rows x 16 bytes at dst (block base + i*kASbo + q*kALbo)
+OB2_D void build_a_step(const uint32_t *lut, uint32_t cw, uint4 *dst) {
+  uint4 lo[4], hi[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const uint4 *e = reinterpret_cast<const uint4 *>(lut + ((cw >> (8 * k)) & 0xffu) * 8);
+    lo[k] = e[0];
+    hi[k] = e[1];
+  }
+  dst[0] = make_uint4(lo[0].x, lo[1].x, lo[2].x, lo[3].x);
+  dst[1] = make_uint4(lo[0].y, lo[1].y, lo[2].y, lo[3].y);
+  dst[2] = make_uint4(lo[0].z, lo[1].z, lo[2].z, lo[3].z);
+  dst[3] = make_uint4(lo[0].w, lo[1].w, lo[2].w, lo[3].w);
+  dst[4] = make_uint4(hi[0].x, hi[1].x, hi[2].x, hi[3].x);
+  dst[5] = make_uint4(hi[0].y, hi[1].y, hi[2].y, hi[3].y);
+  dst[6] = make_uint4(hi[0].z, hi[1].z, hi[2].z, hi[3].z);
+  dst[7] = make_uint4(hi[0].w, hi[1].w, hi[2].w, hi[3].w);
+}
+
+// ---------------------------------------------------------------------------------------
+// the GEMM kernel
+// ---------------------------------------------------------------------------------------
+template <int NH>
+__global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs p) {
+  using K = Cfg<NH>;
+  constexpr int kStages = K::kStages, kBStage = K::kBStage, kTileN = K::kTileN, kSPS = K::kSPS, kAStage = K::kAStage;
+  extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+  // (offset arithmetic on the __shared__ array keeps the address space: LDS/STS, not generic LD/ST)
+  unsigned char *sm = tc_smem_raw + ((1024u - (smem_addr(tc_smem_raw) & 1023u)) & 1023u);
+  unsigned char *smB = sm;                                   // [kStages][NH][kSPS][kHBlock]
+  unsigned char *smA = sm + (size_t)kStages * kBStage;       // [kStages][kSPS][kATile]
+  uint32_t *lut = reinterpret_cast<uint32_t *>(smA + (size_t)kStages * kAStage);  // [256][8]
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(lut) + kLutBytes);
+  // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar0 = smem_addr(bars);
+  auto full_bar = [&](uint32_t s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](uint32_t s) { return bar0 + 8u * (kStages + s); };
+  auto tmem_full = [&](uint32_t b) { return bar0 + 8u * (2 * kStages + b); };
+  auto tmem_empty = [&](uint32_t b) { return bar0 + 8u * (2 * kStages + 2 + b); };
+
+  build_bitmatrix_lut(lut, tid);
   if (tid == 0) {
-    for (uint32_t s = 0; s < kStages; s++) {
+    for (uint32_t s = 0; s < (uint32_t)kStages; s++) {
       mbar_init(full_bar(s), 1 + 32);   // producer's expect_tx arrive + the 32 lanes of one builder warp
-      mbar_init(empty_bar(s), CS);      // tcgen05.commit of every CTA in the cluster
+      mbar_init(empty_bar(s), 1);       // tcgen05.commit
     }
-    mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 32 * kEpiWarps);
+    for (uint32_t b = 0; b < 2; b++) {
+      mbar_init(tmem_full(b), 1);
+      mbar_init(tmem_empty(b), 32 * kEpiWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -303,48 +434,44 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
   __syncthreads();
   tc_fence_after();
 
-  // work units: (system, column tile, group of CS row tiles), row tiles fastest; cluster c takes
-  // units c, c + #clusters, ...
-  const uint32_t rank = CS > 1 ? cluster_ctarank() : 0u;
-  const uint32_t igroups = (p.itiles + CS - 1) / CS;
-  const uint32_t ntotal = p.nsys * p.ntiles * igroups;   // host keeps this below 2^32
-  const uint32_t unit0 = blockIdx.x / CS, ustep = gridDim.x / CS;
+  // work units: (system, column tile, row tile), row tiles fastest; CTA b takes units b, b + grid, ...
+  const uint32_t itiles = p.itiles;
+  const uint32_t ntotal = p.nsys * p.ntiles * itiles;   // host keeps this below 2^32
+  const uint32_t unit0 = blockIdx.x, ustep = gridDim.x;
   const uint32_t ksteps = p.ksteps;
-  constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
-  constexpr uint32_t kSlice = kBStage / CS;
-  static_assert(kBStage % (CS * 16) == 0, "slice size");
   const uint32_t nst = ksteps / kSPS;   // pipeline stages per tile
-  if (CS > 1) cluster_sync_all();   // every CTA's barriers are initialised before any peer touches them
 
   if (warp == kProdWarp) {
     // ------------------------------------------------------------ producer (TMA engine)
     // The whole warp runs the loop (warp-uniform control flow and addresses, so the compiler
-    // keeps them in uniform registers); one elected lane issues the copy.
+    // keeps them in uniform registers); one elected lane issues the copies.
     const bool leader = elect_one();
-    const uint32_t b_dst0 = smem_addr(smB) + rank * kSlice;
+    const uint32_t b_dst0 = smem_addr(smB);
     uint32_t s = 0, ph = 0;
     bool ok = true;
     for (uint32_t t = unit0; t < ntotal && ok; t += ustep) {
-      const uint32_t nt = t / igroups;   // = system * ntiles + column tile
-      const uint8_t *src = p.Dx + (size_t)nt * ksteps * kBTile + rank * kSlice;
-      for (uint32_t st = 0; st < nst; st++, src += kBStage) {
+      const uint32_t snt = t / itiles;   // = system * ntiles + column tile
+      const uint8_t *src = p.Dx + (size_t)snt * NH * ksteps * kHBlock;
+      for (uint32_t st = 0; st < nst; st++, src += kSPS * kHBlock) {
         if (!mbar_wait(empty_bar(s), ph ^ 1u, p.status)) { ok = false; break; }
         if (leader) {
           if (p.dbg & 1) {
             mbar_arrive(full_bar(s));
           } else {
             mbar_arrive_expect_tx(full_bar(s), kBStage);
-            if (CS == 1) bulk_g2s(b_dst0 + s * kBStage, src, kBStage, full_bar(s));
-            else bulk_g2s_multicast(b_dst0 + s * kBStage, src, kSlice, full_bar(s), kMask);
+#pragma unroll
+            for (int h = 0; h < NH; h++)
+              bulk_g2s(b_dst0 + s * kBStage + h * (kSPS * kHBlock), src + (size_t)h * ksteps * kHBlock,
+                       kSPS * kHBlock, full_bar(s));
           }
         }
-        if (++s == kStages) { s = 0; ph ^= 1u; }
+        if (++s == (uint32_t)kStages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------ MMA issuer
     // Warp-uniform loop, one elected lane issues.  A single thread issues ~1 instruction per
-    // 4-5 clocks, so the per-step instruction count is what bounds the MMA rate: descriptors
+    // 4-5 clocks, so the per-stage instruction count is what bounds the MMA rate: descriptors
     // are base + stage * constant, nothing else is computed in the loop.
     const bool leader = elect_one();
     // block-scaled descriptor: A,B = E2M1 (1), K-major, N = 240, scales UE8M0, M = 128, K = 64
@@ -354,32 +481,60 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
     const uint32_t sfa = tm + kSfCol, sfb = tm + kSfCol + 16;
     uint32_t s = 0, ph = 0, iter = 0;
     bool ok = true;
+    const bool ring_aligned = (nst % kStages) == 0;   // every tile starts at stage 0
     for (uint32_t t = unit0; t < ntotal && ok; t += ustep, iter++) {
-      if (!mbar_wait(tmem_empty, (iter & 1u) ^ 1u, p.status)) break;  // epilogue drained the accumulators
+      // accumulator set of this tile and how often it has been used before
+      const uint32_t ab = (K::kAccSets == 2) ? (iter & 1u) : 0u;
+      const uint32_t use = (K::kAccSets == 2) ? (iter >> 1) : iter;
+      if (!mbar_wait(tmem_empty(ab), (use & 1u) ^ 1u, p.status)) break;  // epilogue drained this set
       tc_fence_after();
-      for (uint32_t st = 0; st < nst; st++) {
-        if (!mbar_wait(full_bar(s), ph, p.status)) { ok = false; break; }
-        tc_fence_after();
-        if (leader) {
-          const uint64_t ad = a_desc0 + (uint64_t)(s * (kAStage >> 4));
-          const uint64_t bd = b_desc0 + (uint64_t)(s * (kBStage >> 4));
+      const uint32_t acc0 = tm + ab * kHalfN;
+      if (ring_aligned) {
+        // stage index known at compile time: every descriptor is base + immediate
+        for (uint32_t pass = 0; pass < nst / kStages && ok; pass++) {
 #pragma unroll
-          for (int u = 0; u < kSPS; u++) {
-            const uint32_t acc = (u == 0) ? st : 1u;
-            const uint64_t au = ad + (uint64_t)(u * (kATile >> 4)), bu = bd + (uint64_t)(u * (kBTile >> 4));
-            umma_mxf4(tm, au, bu, idesc, acc, sfa, sfb);
-            umma_mxf4(tm + kHalfN, au, bu + (uint64_t)((kHalfN / 8) * 256 >> 4), idesc, acc, sfa, sfb);
+          for (int cs = 0; cs < kStages; cs++) {
+            if (!mbar_wait(full_bar(cs), ph, p.status)) { ok = false; break; }
+            tc_fence_after();
+            if (leader) {
+#pragma unroll
+              for (int u = 0; u < kSPS; u++) {
+                const uint32_t acc = (cs == 0 && u == 0) ? pass : 1u;
+#pragma unroll
+                for (int h = 0; h < NH; h++)
+                  umma_mxf4(acc0 + h * kHalfN, a_desc0 + (uint64_t)((cs * kAStage + u * kATile) >> 4),
+                            b_desc0 + (uint64_t)((cs * kBStage + (h * kSPS + u) * kHBlock) >> 4), idesc, acc, sfa, sfb);
+              }
+              tc_commit(empty_bar(cs));
+            }
           }
-          if (CS == 1) tc_commit(empty_bar(s));
-          else tc_commit_multicast(empty_bar(s), kMask);
+          ph ^= 1u;
         }
-        if (++s == kStages) { s = 0; ph ^= 1u; }
+      } else {
+        for (uint32_t st = 0; st < nst; st++) {
+          if (!mbar_wait(full_bar(s), ph, p.status)) { ok = false; break; }
+          tc_fence_after();
+          if (leader) {
+            const uint64_t ad = a_desc0 + (uint64_t)(s * (kAStage >> 4));
+            const uint64_t bd = b_desc0 + (uint64_t)(s * (kBStage >> 4));
+#pragma unroll
+            for (int u = 0; u < kSPS; u++) {
+              const uint32_t acc = (u == 0) ? st : 1u;
+              const uint64_t au = ad + (uint64_t)(u * (kATile >> 4));
+#pragma unroll
+              for (int h = 0; h < NH; h++)
+                umma_mxf4(acc0 + h * kHalfN, au, bd + (uint64_t)(((h * kSPS + u) * kHBlock) >> 4), idesc, acc, sfa, sfb);
+            }
+            tc_commit(empty_bar(s));
+          }
+          if (++s == (uint32_t)kStages) { s = 0; ph ^= 1u; }
+        }
       }
-      if (ok && leader) tc_commit(tmem_full);
+      if (ok && leader) tc_commit(tmem_full(ab));
     }
   } else if (warp >= kBuild0) {
     // ------------------------------------------------------------ A-operand builders
-    const uint32_t b = warp - kBuild0;          // this warp builds the stages with G % kBuilderWarps == b
+    const uint32_t b = warp - kBuild0;    // this warp builds the stages with G % kBuilderWarps == b
     const uint32_t i = lane >> 1, q = lane & 1u;
     const bool c_vec = ((p.c_stride & 3) == 0) && ((p.c_ss & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 3) == 0);
     uint32_t G = 0;                       // stages of the tiles done so far
@@ -395,8 +550,8 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
       return w;
     };
     for (uint32_t t = unit0; t < ntotal && ok; t += ustep) {
-      const uint32_t it = (t % igroups) * CS + rank;
-      Cs = p.C + (size_t)(t / igroups / p.ntiles) * p.c_ss;
+      const uint32_t it = t % itiles;
+      Cs = p.C + (size_t)(t / itiles / p.ntiles) * p.c_ss;
       const uint32_t st0 = (b + kBuilderWarps - (G % kBuilderWarps)) % kBuilderWarps;  // first stage of this tile that is ours
       uint32_t cw[kSPS];
 #pragma unroll
@@ -404,31 +559,42 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
       for (uint32_t st = st0; st < nst; st += kBuilderWarps) {
         const uint32_t gs = G + st;
         const uint32_t s = gs % kStages, ph = (gs / kStages) & 1u;
-        uint4 lo[kSPS][4], hi[kSPS][4];
+        uint32_t cur[kSPS];
 #pragma unroll
         for (int u = 0; u < kSPS; u++) {
-          const uint32_t cur = cw[u];
-          if (st + kBuilderWarps < nst) cw[u] = load_c(it, (st + kBuilderWarps) * kSPS + u);
+          cur[u] = cw[u];
+          if (st + kBuilderWarps < nst) cw[u] = load_c(it, (st + kBuilderWarps) * kSPS + u);   // next stage's coefficients
+        }
+        // the first step's table rows are fetched before the wait, the others behind the stores
+        uint4 lo[4], hi[4];
 #pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const uint4 *e = reinterpret_cast<const uint4 *>(lut + ((cur >> (8 * k)) & 0xffu) * 8);
-            lo[u][k] = e[0];
-            hi[u][k] = e[1];
-          }
+        for (int k = 0; k < 4; k++) {
+          const uint4 *e = reinterpret_cast<const uint4 *>(lut + ((cur[0] >> (8 * k)) & 0xffu) * 8);
+          lo[k] = e[0];
+          hi[k] = e[1];
         }
         if (!mbar_wait_warp(empty_bar(s), ph ^ 1u, p.status)) { ok = false; break; }
         if (!(p.dbg & 2)) {
 #pragma unroll
           for (int u = 0; u < kSPS; u++) {
             uint4 *dst = reinterpret_cast<uint4 *>(smA + (size_t)s * kAStage + u * kATile + i * kASbo + q * kALbo);
-            dst[0] = make_uint4(lo[u][0].x, lo[u][1].x, lo[u][2].x, lo[u][3].x);
-            dst[1] = make_uint4(lo[u][0].y, lo[u][1].y, lo[u][2].y, lo[u][3].y);
-            dst[2] = make_uint4(lo[u][0].z, lo[u][1].z, lo[u][2].z, lo[u][3].z);
-            dst[3] = make_uint4(lo[u][0].w, lo[u][1].w, lo[u][2].w, lo[u][3].w);
-            dst[4] = make_uint4(hi[u][0].x, hi[u][1].x, hi[u][2].x, hi[u][3].x);
-            dst[5] = make_uint4(hi[u][0].y, hi[u][1].y, hi[u][2].y, hi[u][3].y);
-            dst[6] = make_uint4(hi[u][0].z, hi[u][1].z, hi[u][2].z, hi[u][3].z);
-            dst[7] = make_uint4(hi[u][0].w, hi[u][1].w, hi[u][2].w, hi[u][3].w);
+            const uint4 l0 = lo[0], l1 = lo[1], l2 = lo[2], l3 = lo[3], h0 = hi[0], h1 = hi[1], h2 = hi[2], h3 = hi[3];
+            if (u + 1 < kSPS) {
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                const uint4 *e = reinterpret_cast<const uint4 *>(lut + ((cur[u + 1 < kSPS ? u + 1 : u] >> (8 * k)) & 0xffu) * 8);
+                lo[k] = e[0];
+                hi[k] = e[1];
+              }
+            }
+            dst[0] = make_uint4(l0.x, l1.x, l2.x, l3.x);
+            dst[1] = make_uint4(l0.y, l1.y, l2.y, l3.y);
+            dst[2] = make_uint4(l0.z, l1.z, l2.z, l3.z);
+            dst[3] = make_uint4(l0.w, l1.w, l2.w, l3.w);
+            dst[4] = make_uint4(h0.x, h1.x, h2.x, h3.x);
+            dst[5] = make_uint4(h0.y, h1.y, h2.y, h3.y);
+            dst[6] = make_uint4(h0.z, h1.z, h2.z, h3.z);
+            dst[7] = make_uint4(h0.w, h1.w, h2.w, h3.w);
           }
           fence_async_smem();
         }
@@ -438,103 +604,253 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 0..7)
-    // warp w reads TMEM lanes 32*(w%4).. (= 4 rows x 8 bit planes) and the 32-column chunks
-    // [c_lo, c_hi) of the tile: warps 0-3 the first 8 chunks, warps 4-7 the other 7.
-    const uint32_t lq = warp & 3u;
-    constexpr int kChunks = kTileN / 32;
-    const int c_lo = (warp < 4) ? 0 : 8, c_hi = (warp < 4) ? 8 : kChunks;
-    auto ld_chunk = [&](uint32_t (&r)[32], uint32_t cc) {
-      const uint32_t ta = tm + ((lq * 32u) << 16) + cc * 32;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(ta) : "memory");
-    };
-    // tcgen05.wait::ld with the destination registers as in/out operands: nothing that reads them
-    // can be scheduled above the wait
-    auto wait_chunk = [&](uint32_t (&r)[32]) {
-      asm volatile("tcgen05.wait::ld.sync.aligned;"
-                   : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                     "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
-                     "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
-                     "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-                   :: "memory");
-    };
-    uint32_t iter = 0;
-    for (uint32_t t = unit0; t < ntotal; t += ustep, iter++) {
-      const uint32_t snt = t / igroups, it = (t % igroups) * CS + rank;
+    using ET = EpiTile<kTileN>;
+    auto tile_of = [&](uint32_t t, ET &e) {
+      const uint32_t snt = t / itiles, it = t % itiles;
       const uint32_t sys = snt / p.ntiles, nt = snt - sys * p.ntiles;
       const TcRegion &rg = p.reg[(p.nreg > 1 && nt >= p.reg[1].tile0) ? 1 : 0];
-      const uint32_t row0 = it * kRowsI + lq * 4;
-      const uint32_t ncol0 = (nt - rg.tile0) * kTileN;          // first column of the tile inside the region
-      uint8_t *ybase = rg.base + (size_t)sys * rg.ss + rg.col0;
-      // Output mapping of a 32-column chunk: lane = (row rr = lane / 8, columns 4*gc .. 4*gc+3 with
-      // gc = lane % 8), i.e. one aligned 32-bit word of Y per lane and 32 contiguous bytes per row.
-      const uint32_t rr = lane >> 3, gc = lane & 7u;
-      const bool row_ok = row0 + rr < p.M;
-      uint8_t *yrow = ybase + (size_t)(row0 + rr) * rg.rs + ncol0 + 4 * gc;
-      // accumulate mode: the old words of this warp's chunks are fetched while the MMAs still run
-      uint32_t oldw[8];
+      e.set(warp, lane, rg, sys, nt - rg.tile0, it, p.M);
+    };
+    ET cur, nxt;
+    uint32_t old_cur[ET::kC0], old_nxt[ET::kC0];
+    if (unit0 < ntotal) {
+      tile_of(unit0, nxt);
+      nxt.load_old(old_nxt, p.accumulate);
+    }
+    uint32_t iter = 0;
+    for (uint32_t t = unit0; t < ntotal; t += ustep, iter++) {
+      cur = nxt;
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const int cc = c_lo + k;
-        oldw[k] = 0;
-        if (p.accumulate && cc < c_hi && row_ok && ncol0 + cc * 32 + 4 * gc < rg.ncols)
-          oldw[k] = *reinterpret_cast<const uint32_t *>(yrow + cc * 32);
+      for (int k = 0; k < ET::kC0; k++) old_cur[k] = old_nxt[k];
+      if (t + ustep < ntotal) {          // old contents of the next tile: in flight during this tile
+        tile_of(t + ustep, nxt);
+        nxt.load_old(old_nxt, p.accumulate);
       }
-      if (!mbar_wait_warp(tmem_full, iter & 1u, p.status, 128)) break;
+      const uint32_t ab = (K::kAccSets == 2) ? (iter & 1u) : 0u;
+      const uint32_t use = (K::kAccSets == 2) ? (iter >> 1) : iter;
+      if (!mbar_wait_warp(tmem_full(ab), use & 1u, p.status, 64)) break;
       tc_fence_after();
-      uint32_t ra[32], rb[32];
-      ld_chunk(ra, c_lo);
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const int cc = c_lo + k;
-        if (cc >= c_hi) break;
-        uint32_t (&cur)[32] = (k & 1) ? rb : ra;
-        uint32_t (&nxt)[32] = (k & 1) ? ra : rb;
-        wait_chunk(cur);
-        if (cc + 1 < c_hi) ld_chunk(nxt, cc + 1);    // next chunk's TMEM read overlaps this chunk's packing
-        // parity of every accumulator (integer-valued fp32 < 2^23: adding 2^23 leaves it in the
-        // mantissa LSB), column c = 4*j + k2 packed at bit k2*8 + j of this lane's word
-        uint32_t w = 0;
-#pragma unroll
-        for (int c = 0; c < 32; c++) {
-          const uint32_t bits = __float_as_uint(__uint_as_float(cur[c]) + 8388608.0f);
-          const int pos = (c & 3) * 8 + (c >> 2);
-          w |= (bits << pos) & (1u << pos);
-        }
-        // 8x8 bit transposes across the 8 lanes (bit planes) of a row: lane bit i <-> index bit i.
-        // Afterwards lane (row rr, gc) holds bytes Y[rr][4*gc .. 4*gc+3] (bit a = plane a).
-#pragma unroll
-        for (int i2 = 0; i2 < 3; i2++) {
-          const uint32_t d = 1u << i2;
-          const uint32_t m0 = (i2 == 0) ? 0x55555555u : (i2 == 1) ? 0x33333333u : 0x0f0f0f0fu;
-          const uint32_t tw = __shfl_xor_sync(0xffffffffu, w, d);
-          w = (lane & d) ? ((w & ~m0) | ((tw & ~m0) >> d)) : ((w & m0) | ((tw & m0) << d));
-        }
-        w ^= oldw[k];
-        if (row_ok && ncol0 + cc * 32 + 4 * gc < rg.ncols) *reinterpret_cast<uint32_t *>(yrow + cc * 32) = w;
-      }
+      if (!(p.dbg & 4)) epilogue_tile<kTileN>(tm, ab * kHalfN, warp, lane, cur, old_cur);
       tc_fence_before();
-      mbar_arrive(tmem_empty);
+      mbar_arrive(tmem_empty(ab));
     }
   }
   tc_fence_before();
   __syncthreads();
-  // no CTA leaves while a peer may still multicast into its shared memory or signal its barriers
-  if (CS > 1) cluster_sync_all();
   if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm) : "memory");
 }
 
-// K-steps of one tile: ceil(Kc / 8) rounded up to whole pipeline stages
-inline uint32_t ksteps_for(uint32_t Kc) {
+// ---------------------------------------------------------------------------------------
+// Rank-128 update kernel of the elimination:  [A_rest | B] ^= E * P_old  for a batch of systems.
+// Same MMA / epilogue scheme as apply_tc_kernel<1> (tiles of 16 rows x 240 bytes, two accumulator
+// sets), but the inner dimension is only 16 steps and the A operand (the bit matrices of the 16
+// x 128 coefficients of a row tile) is the same for every column tile of that row tile: it is
+// built ONCE per (system, row tile) into a resident, double-buffered shared-memory block while
+// only the B blocks stream through a 4-stage ring.  Work unit of a CTA = (system, row tile), its
+// column tiles are processed back to back.
+//   warps 0-7 epilogue | warp 8 producer (B ring) | warp 9 MMA issuer | warps 10-13 A builders
+// ---------------------------------------------------------------------------------------
+constexpr int kUSteps = 16;                       // K-steps = 128 coefficient columns
+constexpr int kUSPS = 2, kUStages = 4;            // B ring: 4 stages of 2 steps (15360 B)
+constexpr int kUBStage = kUSPS * kHBlock;
+constexpr int kUABuf = kUSteps * kATile;          // resident A operand of one row tile (73728 B)
+constexpr size_t kUSmemBytes = (size_t)2 * kUABuf + (size_t)kUStages * kUBStage + kLutBytes + 256 + 1024;
+
+__global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArgs p) {
+  extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+  unsigned char *sm = tc_smem_raw + ((1024u - (smem_addr(tc_smem_raw) & 1023u)) & 1023u);
+  unsigned char *smA = sm;                                   // [2][kUSteps][kATile]
+  unsigned char *smB = sm + (size_t)2 * kUABuf;              // [kUStages][kUSPS][kHBlock]
+  uint32_t *lut = reinterpret_cast<uint32_t *>(smB + (size_t)kUStages * kUBStage);
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(lut) + kLutBytes);
+  // bars: [0..4) b_full, [4..8) b_empty, [8..10) a_full, [10..12) a_empty, [12..14) tmem_full, [14..16) tmem_empty
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar0 = smem_addr(bars);
+  auto b_full = [&](uint32_t s) { return bar0 + 8u * s; };
+  auto b_empty = [&](uint32_t s) { return bar0 + 8u * (4 + s); };
+  auto a_full = [&](uint32_t b) { return bar0 + 8u * (8 + b); };
+  auto a_empty = [&](uint32_t b) { return bar0 + 8u * (10 + b); };
+  auto tmem_full = [&](uint32_t b) { return bar0 + 8u * (12 + b); };
+  auto tmem_empty = [&](uint32_t b) { return bar0 + 8u * (14 + b); };
+
+  build_bitmatrix_lut(lut, tid);
+  if (tid == 0) {
+    for (uint32_t s = 0; s < (uint32_t)kUStages; s++) {
+      mbar_init(b_full(s), 1);          // producer's expect_tx arrive
+      mbar_init(b_empty(s), 1);         // tcgen05.commit
+    }
+    for (uint32_t b = 0; b < 2; b++) {
+      mbar_init(a_full(b), 32 * kBuilderWarps);
+      mbar_init(a_empty(b), 1);
+      mbar_init(tmem_full(b), 1);
+      mbar_init(tmem_empty(b), 32 * kEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *tmem_slot;
+  if (warp < 4) {  // scale factors = 1.0 everywhere in columns 480..511 of this warp's lanes
+#pragma unroll
+    for (uint32_t c = kSfCol; c < 512; c += 8) {
+      uint32_t ta = tm + ((warp * 32u) << 16) + c, v = 0x7f7f7f7fu;
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(ta), "r"(v) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  const uint32_t itiles = p.itiles, ntiles = p.ntiles;
+  const uint32_t nunits = p.nsys * itiles;       // (system, row tile)
+  static_assert(kUSteps % (kUSPS * kUStages) == 0, "the B ring is aligned to tiles");
+
+  if (warp == kProdWarp) {
+    // ------------------------------------------------------------ producer: B blocks of every column tile
+    const bool leader = elect_one();
+    const uint32_t b_dst0 = smem_addr(smB);
+    uint32_t s = 0, ph = 0;
+    bool ok = true;
+    for (uint32_t su = blockIdx.x; su < nunits && ok; su += gridDim.x) {
+      const uint32_t sys = su / itiles;
+      const uint8_t *src = p.Dx + (size_t)sys * ntiles * kUSteps * kHBlock;
+      for (uint32_t q = 0; q < ntiles * (kUSteps / kUSPS) && ok; q++, src += kUBStage) {
+        if (!mbar_wait(b_empty(s), ph ^ 1u, p.status)) { ok = false; break; }
+        if (leader) {
+          if (p.dbg & 1) {
+            mbar_arrive(b_full(s));
+          } else {
+            mbar_arrive_expect_tx(b_full(s), kUBStage);
+            bulk_g2s(b_dst0 + s * kUBStage, src, kUBStage, b_full(s));
+          }
+        }
+        if (++s == (uint32_t)kUStages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ------------------------------------------------------------ MMA issuer
+    const bool leader = elect_one();
+    const uint32_t idesc = (1u << 7) | (1u << 10) | ((uint32_t)(kHalfN >> 3) << 17) | (1u << 23) | ((128u >> 4) << 24);
+    const uint64_t a_desc0 = umma_desc(smem_addr(smA), kALbo, kASbo);
+    const uint64_t b_desc0 = umma_desc(smem_addr(smB));
+    const uint32_t sfa = tm + kSfCol, sfb = tm + kSfCol + 16;
+    uint32_t ph = 0, tile_iter = 0, unit_iter = 0;
+    bool ok = true;
+    for (uint32_t su = blockIdx.x; su < nunits && ok; su += gridDim.x, unit_iter++) {
+      const uint32_t abuf = unit_iter & 1u;
+      if (!mbar_wait(a_full(abuf), (unit_iter >> 1) & 1u, p.status)) break;      // A operand of this row tile built
+      tc_fence_after();
+      const uint64_t a_desc = a_desc0 + (uint64_t)(abuf * (kUABuf >> 4));
+      for (uint32_t nt = 0; nt < ntiles && ok; nt++, tile_iter++) {
+        const uint32_t ab = tile_iter & 1u;
+        if (!mbar_wait(tmem_empty(ab), ((tile_iter >> 1) & 1u) ^ 1u, p.status)) { ok = false; break; }
+        tc_fence_after();
+        const uint32_t acc0 = tm + ab * kHalfN;
+#pragma unroll
+        for (int pass = 0; pass < kUSteps / (kUSPS * kUStages); pass++) {
+#pragma unroll
+          for (int cs = 0; cs < kUStages; cs++) {
+            if (!mbar_wait(b_full(cs), ph, p.status)) { ok = false; break; }
+            tc_fence_after();
+            if (leader) {
+#pragma unroll
+              for (int u = 0; u < kUSPS; u++) {
+                const int step = (pass * kUStages + cs) * kUSPS + u;
+                umma_mxf4(acc0, a_desc + (uint64_t)((step * kATile) >> 4),
+                          b_desc0 + (uint64_t)((cs * kUBStage + u * kHBlock) >> 4), idesc, step > 0 ? 1u : 0u, sfa, sfb);
+              }
+              tc_commit(b_empty(cs));
+            }
+          }
+          ph ^= 1u;
+          if (!ok) break;
+        }
+        if (ok && leader) tc_commit(tmem_full(ab));
+      }
+      if (ok && leader) tc_commit(a_empty(abuf));     // all MMAs that read this A block are done
+    }
+  } else if (warp >= kBuild0) {
+    // ------------------------------------------------------------ A builders: once per (system, row tile)
+    const uint32_t b = warp - kBuild0;
+    const uint32_t i = lane >> 1, q = lane & 1u;
+    uint32_t unit_iter = 0;
+    for (uint32_t su = blockIdx.x; su < nunits; su += gridDim.x, unit_iter++) {
+      const uint32_t sys = su / itiles, it = su - sys * itiles;
+      const uint32_t abuf = unit_iter & 1u;
+      const uint32_t row = it * kRowsI + i;
+      const uint8_t *crow = p.C + (size_t)sys * p.c_ss + (size_t)row * p.c_stride + 4 * q;
+      uint32_t cw[kUSteps / kBuilderWarps];
+#pragma unroll
+      for (int k = 0; k < kUSteps / kBuilderWarps; k++) {
+        const uint32_t step = b + k * kBuilderWarps;
+        cw[k] = (row < p.M && step * kStepJ + 4 * q < p.Kc) ? __ldg(reinterpret_cast<const uint32_t *>(crow + step * kStepJ)) : 0u;
+      }
+      if (!mbar_wait_warp(a_empty(abuf), ((unit_iter >> 1) & 1u) ^ 1u, p.status)) break;
+      if (!(p.dbg & 2)) {
+#pragma unroll
+        for (int k = 0; k < kUSteps / kBuilderWarps; k++) {
+          const uint32_t step = b + k * kBuilderWarps;
+          build_a_step(lut, cw[k], reinterpret_cast<uint4 *>(smA + (size_t)abuf * kUABuf + step * kATile + i * kASbo + q * kALbo));
+        }
+        fence_async_smem();
+      }
+      mbar_arrive(a_full(abuf));
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 0..7)
+    using ET = EpiTile<kHalfN>;
+    auto tile_of = [&](uint32_t su, uint32_t nt, ET &e) {
+      const uint32_t sys = su / itiles, it = su - sys * itiles;
+      const TcRegion &rg = p.reg[(p.nreg > 1 && nt >= p.reg[1].tile0) ? 1 : 0];
+      e.set(warp, lane, rg, sys, nt - rg.tile0, it, p.M);
+    };
+    ET cur, nxt;
+    uint32_t old_cur[ET::kC0], old_nxt[ET::kC0];
+    if (blockIdx.x < nunits && ntiles > 0) {
+      tile_of(blockIdx.x, 0, nxt);
+      nxt.load_old(old_nxt, p.accumulate);
+    }
+    uint32_t tile_iter = 0;
+    bool ok = true;
+    for (uint32_t su = blockIdx.x; su < nunits && ok; su += gridDim.x) {
+      for (uint32_t nt = 0; nt < ntiles; nt++, tile_iter++) {
+        cur = nxt;
+#pragma unroll
+        for (int k = 0; k < ET::kC0; k++) old_cur[k] = old_nxt[k];
+        // old contents of the next tile: in flight during this tile
+        if (nt + 1 < ntiles) {
+          tile_of(su, nt + 1, nxt);
+          nxt.load_old(old_nxt, p.accumulate);
+        } else if (su + gridDim.x < nunits) {
+          tile_of(su + gridDim.x, 0, nxt);
+          nxt.load_old(old_nxt, p.accumulate);
+        }
+        const uint32_t ab = tile_iter & 1u, use = tile_iter >> 1;
+        if (!mbar_wait_warp(tmem_full(ab), use & 1u, p.status, 32)) { ok = false; break; }
+        tc_fence_after();
+        if (!(p.dbg & 4)) epilogue_tile<kHalfN>(tm, ab * kHalfN, warp, lane, cur, old_cur);
+        tc_fence_before();
+        mbar_arrive(tmem_empty(ab));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm) : "memory");
+}
+
+// K-steps of one tile: ceil(Kc / 8) rounded up to whole pipeline stages of `sps` steps
+inline uint32_t ksteps_for(uint32_t Kc, uint32_t sps) {
   uint32_t k = (Kc + kStepJ - 1) / kStepJ;
-  return (k + kSPS - 1) / kSPS * kSPS;
+  return (k + sps - 1) / sps * sps;
 }
 
 }  // namespace tc

@@ -42,7 +42,6 @@ struct Ctx {
   void *tc_ws = nullptr;
   size_t tc_ws_bytes = 0;
   int *tc_status = nullptr;  // pinned + mapped: the kernel sets it if a barrier wait gave up
-  int tc_cluster = 0;        // CTAs per cluster of the tensor-core apply (1, 2, 4; 0 = default)
   int no_fast_panel = 0;               // diagnostics: general panel path only
   unsigned long long *d_phase = nullptr;  // solve-kernel phase counters (diagnostics)
   DevTableSet *d_sets = nullptr;  // [TS_COUNT] in device memory
@@ -241,7 +240,6 @@ int oblas_b200_sync(void) {
   return tc_check_status();
 }
 void oblas_b200_set_async(int async) { g.async = async != 0; }
-void oblas_b200_set_apply_cluster(int ctas) { g.tc_cluster = ctas; }
 void oblas_b200_set_panel_path(int general_only) { g.no_fast_panel = general_only != 0; }
 void oblas_b200_set_tuning(int solve_geo, int apply_geo) {
   g.solve_geo = solve_geo;
@@ -672,9 +670,9 @@ int tc_prepare(int **dstatus) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    CK(cudaFuncSetAttribute(apply_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    CK(cudaFuncSetAttribute(apply_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    CK(cudaFuncSetAttribute(apply_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    CK(cudaFuncSetAttribute(apply_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<1>::kSmemBytes));
+    CK(cudaFuncSetAttribute(apply_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<2>::kSmemBytes));
+    CK(cudaFuncSetAttribute(update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
     attr_set = true;
   }
   CK(cudaHostGetDevicePointer((void **)dstatus, g.tc_status, 0));
@@ -696,31 +694,25 @@ int tc_ws_reserve(size_t need) {
   g.tc_ws_bytes = need;
   return 0;
 }
-// persistent launch of the tcgen05 GEMM kernel: one CTA per SM (clusters of cs)
-int tc_launch(const ob2::tc::ApplyTcArgs &a, int cs) {
+// persistent launch of the tcgen05 GEMM kernel: one CTA per SM.  nh = half tiles (240 byte
+// columns) per tile: 2 = one accumulator set, long inner dimension; 1 = double-buffered accumulators
+int tc_launch(const ob2::tc::ApplyTcArgs &a, int nh) {
   using namespace ob2::tc;
-  const uint64_t units64 = (uint64_t)a.nsys * a.ntiles * ((a.itiles + cs - 1) / cs);
+  const uint64_t units64 = (uint64_t)a.nsys * a.ntiles * a.itiles;
   if (units64 >= (1ull << 32)) return fail("apply (tcgen05): too many tiles in one launch");
-  const uint32_t units = (uint32_t)units64;
-  uint32_t nclusters = (uint32_t)g.sm_count / cs;
-  if (units < nclusters) nclusters = units;
-  if (nclusters == 0) return 0;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(nclusters * cs);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = kSmemBytes;
-  cfg.stream = g.stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = cs;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  cudaError_t le = cs == 1   ? cudaLaunchKernelEx(&cfg, apply_tc_kernel<1>, a)
-                   : cs == 2 ? cudaLaunchKernelEx(&cfg, apply_tc_kernel<2>, a)
-                             : cudaLaunchKernelEx(&cfg, apply_tc_kernel<4>, a);
-  if (le != cudaSuccess) return fail("apply (tcgen05) launch failed: %s", cudaGetErrorString(le));
+  uint32_t grid = (uint32_t)g.sm_count;
+  if (units64 < grid) grid = (uint32_t)units64;
+  if (grid == 0) return 0;
+  if (nh == 2) {
+    apply_tc_kernel<2><<<grid, kThreads, Cfg<2>::kSmemBytes, g.stream>>>(a);
+  } else if (nh == 1) {
+    apply_tc_kernel<1><<<grid, kThreads, Cfg<1>::kSmemBytes, g.stream>>>(a);
+  } else {   // rank-128 update with the A operand resident per (system, row tile)
+    const uint64_t nunits = (uint64_t)a.nsys * a.itiles;
+    grid = (uint32_t)g.sm_count;
+    if (nunits < grid) grid = (uint32_t)nunits;
+    update_tc_kernel<<<grid, kThreads, kUSmemBytes, g.stream>>>(a);
+  }
   return after_launch("apply (tcgen05)");
 }
 int apply_tc_run(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, const uint8_t *D, size_t d_stride,
@@ -728,8 +720,9 @@ int apply_tc_run(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, con
   using namespace ob2::tc;
   int *dstatus = nullptr;
   if (tc_prepare(&dstatus)) return -1;
-  const uint32_t ksteps = ksteps_for(Kc);
-  const size_t tile_bytes = (size_t)ksteps * kBTile;
+  const uint32_t ksteps = ksteps_for(Kc, Cfg<2>::kSPS);
+  constexpr int kTileN = Cfg<2>::kTileN;
+  const size_t tile_bytes = (size_t)ksteps * 2 * kHBlock;
   const uint32_t ntiles_all = (uint32_t)((nbytes + kTileN - 1) / kTileN);
   uint32_t tiles_per_pass = (uint32_t)(tc_ws_budget / tile_bytes);
   if (tiles_per_pass == 0) tiles_per_pass = 1;
@@ -741,9 +734,6 @@ int apply_tc_run(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, con
     if (tiles_per_pass == 1) return fail("apply: cannot allocate %zu bytes of operand workspace", tile_bytes);
     tiles_per_pass = (tiles_per_pass + 1) / 2;
   }
-  // CTAs per cluster (multicast of the operand blocks); measured: 1 is fastest on B200
-  int cs = g.tc_cluster;
-  if (cs != 1 && cs != 2 && cs != 4) cs = 1;
   const uint32_t itiles = (M + kRowsI - 1) / kRowsI;
   for (uint32_t t0 = 0; t0 < ntiles_all; t0 += tiles_per_pass) {
     const uint32_t nt = (ntiles_all - t0 < tiles_per_pass) ? (ntiles_all - t0) : tiles_per_pass;
@@ -754,7 +744,7 @@ int apply_tc_run(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, con
     e.reg[0].base = const_cast<uint8_t *>(D); e.reg[0].rs = d_stride; e.reg[0].ss = 0;
     e.reg[0].col0 = n0; e.reg[0].ncols = ncols; e.reg[0].tile0 = 0;
     e.nreg = 1; e.Kc = Kc; e.rowmap = nullptr; e.rowmap_stride = 0; e.nrows = nullptr;
-    e.Dx = (uint8_t *)g.tc_ws; e.ksteps = ksteps; e.ntiles = nt; e.nsys = 1;
+    e.Dx = (uint8_t *)g.tc_ws; e.ksteps = ksteps; e.nhalf = 2 * nt; e.nsys = 1;
     const size_t work = (size_t)nt * ksteps * (kTileN / 4);
     uint32_t eg = (uint32_t)((work + 255) / 256);
     if (eg > (uint32_t)g.sm_count * 16) eg = (uint32_t)g.sm_count * 16;
@@ -768,7 +758,7 @@ int apply_tc_run(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, con
     a.reg[0].tile0 = 0; a.nreg = 1;
     a.accumulate = accumulate; a.status = dstatus;
     { const char *dv = getenv("OBLAS_B200_TC_DEBUG"); a.dbg = dv ? atoi(dv) : 0; }
-    if (tc_launch(a, cs)) return -1;
+    if (tc_launch(a, 2)) return -1;
   }
   return 0;
 }
@@ -788,13 +778,14 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
   if (tc_prepare(&dstatus)) return -1;
   const uint32_t rows = p.rows;
   const uint32_t nouter = (p.cols + kOuterBytes - 1) / kOuterBytes;
-  const uint32_t ksteps = ksteps_for(kOuterBytes);
+  const uint32_t ksteps = ksteps_for(kOuterBytes, Cfg<1>::kSPS);   // 16 = kUSteps
   const uint32_t itiles = (rows + kRowsI - 1) / kRowsI;
   // column tiles of the widest trailing update (outer panel 0)
+  constexpr int kTileN = Cfg<1>::kTileN;   // 240: double-buffered accumulators
   auto tiles_of = [](uint32_t bytes) { return (bytes + kTileN - 1) / kTileN; };
   const uint32_t a_rest0 = p.a_bytes > (uint32_t)kOuterBytes ? p.a_bytes - kOuterBytes : 0;
   const uint32_t ntiles_max = tiles_of(a_rest0) + tiles_of(p.B ? p.b_bytes : 0);
-  const size_t dx_per_sys = (size_t)ntiles_max * ksteps * kBTile;
+  const size_t dx_per_sys = (size_t)ntiles_max * ksteps * kHBlock;
   const size_t e_per_sys = (size_t)rows * kOuterBytes;
   const size_t map_per_sys = ((size_t)rows * 2 + 15) / 16 * 16;
   const size_t small_per_sys = 2 * kOuterBytes + 16;   // piv_all (u16 x 128) + tcount + npiv + pad
@@ -816,8 +807,6 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
   uint16_t *piv_all = (uint16_t *)ws;                      ws += chunk * 2 * kOuterBytes;
   uint32_t *tcount = (uint32_t *)ws;                       ws += chunk * 4;
   uint32_t *npiv = (uint32_t *)ws;
-  int cs = g.tc_cluster;
-  if (cs != 1 && cs != 2 && cs != 4) cs = 1;
   // permutation kernel: row map + staging area in shared memory
   const size_t pmap = ((size_t)rows * 2 + 15) / 16 * 16;
   if (pmap + 64 + (size_t)rows * 16 > g.smem_optin) return fail("solve: %u rows do not fit the permutation stage", rows);
@@ -866,7 +855,7 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
       memset(&e, 0, sizeof e);
       e.reg[0] = reg[0]; e.reg[1] = reg[1]; e.nreg = nreg; e.Kc = kOuterBytes;
       e.rowmap = piv_all; e.rowmap_stride = kOuterBytes; e.nrows = npiv;
-      e.Dx = Dx; e.ksteps = ksteps; e.ntiles = ntiles; e.nsys = cnt;
+      e.Dx = Dx; e.ksteps = ksteps; e.nhalf = ntiles; e.nsys = cnt;
       const size_t work = (size_t)cnt * ntiles * ksteps * (kTileN / 4);
       uint32_t eg = (uint32_t)((work + 255) / 256);
       if (eg > (uint32_t)g.sm_count * 16) eg = (uint32_t)g.sm_count * 16;
@@ -877,8 +866,9 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
       a.C = E; a.c_stride = kOuterBytes; a.c_ss = e_per_sys; a.M = rows; a.Kc = kOuterBytes; a.Dx = Dx;
       a.ksteps = ksteps; a.ntiles = ntiles; a.itiles = itiles; a.nsys = cnt;
       a.reg[0] = reg[0]; a.reg[1] = reg[1]; a.nreg = nreg;
-      a.accumulate = 1; a.status = dstatus; a.dbg = 0;
-      if (tc_launch(a, cs)) return -1;
+      a.accumulate = 1; a.status = dstatus;
+      { const char *dv = getenv("OBLAS_B200_TC_DEBUG"); a.dbg = dv ? atoi(dv) : 0; }
+      if (tc_launch(a, getenv("OBLAS_B200_TC_STREAM_A") ? 1 : 0)) return -1;
     }
     PermuteArgs pm;
     memset(&pm, 0, sizeof pm);

@@ -15,7 +15,6 @@ D = torch.empty((Kc, N), dtype=torch.uint8, device="cuda")
 device.fill_random(Cm, 1)
 device.fill_random(D, 2)
 lib.oblas_b200_set_tuning(-1, 3)
-lib.oblas_b200_set_apply_cluster(cs)
 Y = device.apply(Cm, D)
 capi.check(lib.oblas_b200_sync(), "sync")
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
