@@ -39,7 +39,15 @@ struct Ctx {
   bool async = false;
   int solve_geo = -1, apply_geo = -1;  // table geometry overrides (-1 = default)
   // tensor-core apply (apply_tc.cuh): expanded-D workspace and the device-written status word
-  void *tc_ws = nullptr;
+  // one workspace per stream that has used the tensor-core paths (the host-streaming lanes run
+  // concurrently on their own streams and must not share operand blocks / row maps)
+  struct TcWs {
+    cudaStream_t stream = nullptr;
+    void *p = nullptr;
+    size_t bytes = 0;
+    bool used = false;
+  } tc_slots[8];
+  void *tc_ws = nullptr;      // workspace of the current stream (set by tc_ws_reserve)
   size_t tc_ws_bytes = 0;
   int *tc_status = nullptr;  // pinned + mapped: the kernel sets it if a barrier wait gave up
   int no_fast_panel = 0;               // diagnostics: general panel path only
@@ -208,7 +216,10 @@ void oblas_b200_shutdown(void) {
   if (g.scratch) cudaFree(g.scratch);
   g.scratch = nullptr;
   g.scratch_bytes = 0;
-  if (g.tc_ws) cudaFree(g.tc_ws);
+  for (auto &w : g.tc_slots) {
+    if (w.p) cudaFree(w.p);
+    w = Ctx::TcWs();
+  }
   g.tc_ws = nullptr;
   g.tc_ws_bytes = 0;
   if (g.tc_status) cudaFreeHost(g.tc_status);
@@ -679,19 +690,36 @@ int tc_prepare(int **dstatus) {
   return 0;
 }
 int tc_ws_reserve(size_t need) {
-  if (need <= g.tc_ws_bytes) return 0;
-  if (g.tc_ws) {
-    CK(cudaStreamSynchronize(g.stream));
-    CK(cudaFree(g.tc_ws));
-    g.tc_ws = nullptr;
-    g.tc_ws_bytes = 0;
+  Ctx::TcWs *slot = nullptr;
+  for (auto &w : g.tc_slots)
+    if (w.used && w.stream == g.stream) slot = &w;
+  if (!slot)
+    for (auto &w : g.tc_slots)
+      if (!w.used) {
+        slot = &w;
+        w.used = true;
+        w.stream = g.stream;
+        break;
+      }
+  if (!slot) return fail("tensor-core workspace: more than 8 streams in use");
+  if (need > slot->bytes) {
+    if (slot->p) {
+      CK(cudaStreamSynchronize(g.stream));
+      CK(cudaFree(slot->p));
+      slot->p = nullptr;
+      slot->bytes = 0;
+    }
+    if (cudaMalloc(&slot->p, need) != cudaSuccess) {
+      cudaGetLastError();
+      slot->p = nullptr;
+      g.tc_ws = nullptr;
+      g.tc_ws_bytes = 0;
+      return 1;   // caller shrinks its request
+    }
+    slot->bytes = need;
   }
-  if (cudaMalloc(&g.tc_ws, need) != cudaSuccess) {
-    cudaGetLastError();
-    g.tc_ws = nullptr;
-    return 1;   // caller shrinks its request
-  }
-  g.tc_ws_bytes = need;
+  g.tc_ws = slot->p;
+  g.tc_ws_bytes = slot->bytes;
   return 0;
 }
 // persistent launch of the tcgen05 GEMM kernel: one CTA per SM.  nh = half tiles (240 byte
