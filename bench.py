@@ -11,11 +11,15 @@ shard with no data-path collective).  A "step" is one pass
 the hot path over one batch; metric = systems solved per second, whole job.
 
 Besides the contract keys the JSON line carries:
-  roofline      dominant kernel (solve_kernel) against the measured HBM peak, by the
-                rule "algorithmic bytes / kernel time" -- the kernel is NOT HBM bound,
-                the binding resource is reported in roofline_binding
-  roofline_binding  GF(256) multiply-adds per second against the shared-memory
-                look-up ceiling (64 byte-MACs/clk/SM)
+  roofline      dominant kernel = ob2::tc::update_tc_kernel (the tcgen05 rank-128 update of
+                A's remaining columns and B, ~65 % of a step): bound "tensor", achieved =
+                algorithmic fp4 flops of the launches / their CUDA-event time, peak = the
+                measured kind::mxf4 rate of this pool's B200 (tools/peaks.cu ->
+                profiles/r01_peaks_b200.jsonl; MEASURED_PEAKS.json carries only bf16)
+  roofline_panel  the outer-panel factorisation kernel (shared-memory look-up bound) and
+                the time shares of all four kernel classes of a step
+  roofline_hbm  the whole step against the measured HBM peak by the rule "algorithmic
+                bytes / kernel time" (the path is not HBM bound; kept for the contract)
   rowops        GF(256) oaxpy / oaddrow / oscal streaming GB/s on a working set >> L2
                 (BASELINE's first metric) with their HBM roofline fractions
   cpu_baseline  the unmodified reference (oracle/_ref, AVX-512 build when the host
@@ -40,6 +44,9 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 K_DEFAULT, L_DEFAULT, NSYS_DEFAULT = 1024, 1280, 4096
+# dram__bytes_read.sum + dram__bytes_write.sum of one update_tc_kernel launch (outer panel 0) on 296
+# systems, ncu --set full (profiles/r01_ncu_update_tc.json)
+NCU_UPDATE_DRAM_BYTES_296 = 1.062188e9 + 0.612285e9
 METRIC = "GF(256) K=1024 solves/sec (batched Gaussian elimination + 1280-byte RHS symbol update)"
 
 
@@ -50,6 +57,23 @@ def measured_peaks():
         return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", p
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)", {}
+
+
+def measured_fp4_peak():
+    """TFLOP/s of tcgen05 kind::mxf4 (M=128, N=256, K=64, all SMs) measured by tools/peaks.cu on a
+    B200 of this pool; MEASURED_PEAKS.json has no fp4 figure.  Fallback: nominal 9000."""
+    try:
+        best = 0.0
+        with open(os.path.join(ROOT, "profiles", "r01_peaks_b200.jsonl")) as f:
+            for ln in f:
+                d = json.loads(ln)
+                if d.get("what") == "umma" and str(d.get("kind", "")).startswith("mxf4") and d.get("ctas", 0) > 1:
+                    best = max(best, 2.0 * float(d["chip_Tmac_per_s"]))
+        if best > 0:
+            return best, "measured: tools/peaks.cu kind::mxf4 burst on all SMs (profiles/r01_peaks_b200.jsonl)"
+    except Exception:
+        pass
+    return 9000.0, "nominal dense fp4 (no measured figure found)"
 
 
 # ------------------------------------------------------------------ clocks sampling
@@ -230,6 +254,7 @@ def run_b200_arm(args):
     if rank == 0:
         sampler.start()
     launches0 = L_.oblas_b200_launch_count()
+    L_.oblas_b200_solve_tc_times(1, None, None)   # CUDA events around every kernel of the elimination
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern_events = []
     ev0.record()
@@ -239,6 +264,10 @@ def run_b200_arm(args):
     ev1.record()
     barrier()
     launches = L_.oblas_b200_launch_count() - launches0
+    cls_ms, cls_n = (C.c_double * 4)(), (C.c_uint64 * 4)()
+    L_.oblas_b200_solve_tc_times(0, cls_ms, cls_n)
+    cls_ms = [float(x) / args.steps for x in cls_ms]   # per step
+    cls_n = [int(x) // args.steps for x in cls_n]
     clocks = sampler.stop() if rank == 0 else None
     total_ms = ev0.elapsed_time(ev1)
     kern_ms = sum(a.elapsed_time(b) for a, b in kern_events) / len(kern_events)
@@ -251,30 +280,66 @@ def run_b200_arm(args):
     # ---- parity on this run's outputs (outside the timed region)
     parity = check_parity(A0, B0, A, B, ranks, K, L, rank)
 
-    # ---- roofline of the dominant kernel
+    # ---- rooflines
     algo_bytes = nsys * (K * K + 2 * K * L)          # min bytes per system
     macs = nsys * (K ** 3 / 2.0 + K * K * L)         # Gauss-Jordan as executed (K^3/2 + K^2 L)
     macs_min = nsys * (K ** 3 / 3.0 + K * K * L)     # SURVEY 8d algorithmic minimum
-    ach = algo_bytes / (kern_ms / 1e3) / 1e9
-    # DRAM bytes of this kernel from the committed ncu --set full capture (profiles/):
-    # dram__bytes_read.sum + dram__bytes_write.sum = 72.01 GB for a 296-system launch
-    traffic = 72.011960e9 / 296 * nsys if (K, L) == (K_DEFAULT, L_DEFAULT) else None
-    roofline = {"kernel": "ob2::solve_kernel<8,4,6,128>", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                "note": "by construction not HBM bound (arithmetic intensity ~460 MAC/B); see roofline_binding"}
     sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("clocks_under_load", {}).get("sm_mhz_median") or 1500.0
     sms = L_.oblas_b200_sm_count()
-    # shared-memory look-up ceiling of the kernel's table geometry: a row update of 16 bytes x
-    # 16 pivots (256 byte-MACs) costs 22 LDS.128 (6-bit groups of the 128 coefficient bits), the
-    # crossbar delivers 8 x 16 B per clk per SM  =>  256 * 8 / 22 = 93.1 byte-MACs/clk/SM
-    macs_per_clk_sm = 256.0 * 8.0 / 22.0
-    lut_peak = macs_per_clk_sm * sms * sm_mhz * 1e6
-    binding = {"kernel": "ob2::solve_kernel<8,4,6,128>",
-               "bound": "shared-memory LUT bandwidth (6-bit Four-Russians tables: %.1f GF(256) MAC/clk/SM)" % macs_per_clk_sm,
-               "achieved": macs / (kern_ms / 1e3) / 1e12, "peak": lut_peak / 1e12, "unit": "T GF-MAC/s",
-               "frac": macs / (kern_ms / 1e3) / lut_peak, "sm_mhz_used": sm_mhz,
-               "algorithmic_min_gmacs_per_system": macs_min / nsys / 1e9,
-               "executed_gmacs_per_system": macs / nsys / 1e9}
+    roofline_hbm = {"bound": "hbm", "achieved": algo_bytes / (kern_ms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": algo_bytes / (kern_ms / 1e3) / 1e9 / hbm_peak, "peak_source": peak_src,
+                    "note": "whole step; arithmetic intensity ~460 MAC/B, the path is compute bound"}
+    tc_path = sum(cls_n) > 0
+    if tc_path:
+        # dominant kernel: the tcgen05 rank-128 update.  Launch p (outer panel p of 128 columns)
+        # multiplies, per system, the K x 128 coefficient matrix with the 128 pivot rows over the
+        # trailing bytes (K - 128(p+1)) + L: that many GF(256) MACs, x 64 bit-MACs, x 2 flops.
+        nouter = (K + 127) // 128
+        trailing = sum(max(K - 128 * (p + 1), 0) + L for p in range(nouter))
+        upd_macs = nsys * K * 128 * trailing
+        upd_ms = cls_ms[2]
+        fp4_peak, fp4_src = measured_fp4_peak()
+        ach = upd_macs * 64 * 2 / (upd_ms / 1e3) / 1e12
+        # DRAM bytes of the update launches from the committed ncu --set full capture
+        # (profiles/r01_ncu_update_tc.json: dram read + write of one launch on 296 systems)
+        # (outer panel 0, the widest), scaled to the systems of one launch of this run
+        sys_per_launch = nsys * nouter / max(cls_n[2], 1)
+        traffic = NCU_UPDATE_DRAM_BYTES_296 / 296 * sys_per_launch if (K, L) == (K_DEFAULT, L_DEFAULT) else None
+        roofline = {"kernel": "ob2::tc::update_tc_kernel", "bound": "tensor", "achieved": ach, "peak": fp4_peak,
+                    "unit": "TFLOP/s", "frac": ach / fp4_peak, "traffic": traffic, "peak_source": fp4_src,
+                    "launches_per_step": cls_n[2], "ms_per_step": upd_ms, "share_of_step": upd_ms / kern_ms,
+                    "algorithmic_bytes_per_launch": sys_per_launch * 2 * K * (trailing / nouter),
+                    "gf256_macs_per_system": upd_macs / nsys,
+                    "note": "fp4 e2m1 0/1 operands, fp32 accumulation in TMEM, parity in the epilogue; inner dimension "
+                            "128 coefficients = 16 K-steps per tile, so TMEM read-out of the accumulators is as "
+                            "long as the MMAs of a tile"}
+        # outer-panel factorisation: shared-memory look-up bound.  Per 16-column step it streams
+        # two 128-byte tiles (the window and E) of every row: 22 LDS.128 per 16 bytes x 16 pivots
+        macs_per_clk_sm = 256.0 * 8.0 / 22.0
+        pan_macs = nsys * K * (K / 16.0) * 16 * (128 + 128)   # rows x 16-col steps x 16 pivots x 256 bytes
+        lut_peak = macs_per_clk_sm * sms * sm_mhz * 1e6
+        binding = {"kernel": "ob2::panel_kernel<6,128>",
+                   "bound": "shared-memory LUT bandwidth (6-bit Four-Russians tables: %.1f GF(256) MAC/clk/SM)" % macs_per_clk_sm,
+                   "achieved": pan_macs / (cls_ms[0] / 1e3) / 1e12, "peak": lut_peak / 1e12, "unit": "T GF-MAC/s",
+                   "frac": pan_macs / (cls_ms[0] / 1e3) / lut_peak, "sm_mhz_used": sm_mhz,
+                   "ms_per_step": {"panel_kernel": cls_ms[0], "expand_d_kernel": cls_ms[1],
+                                   "update_tc_kernel": cls_ms[2], "permute_kernel": cls_ms[3]},
+                   "launches_per_step": {"panel_kernel": cls_n[0], "expand_d_kernel": cls_n[1],
+                                         "update_tc_kernel": cls_n[2], "permute_kernel": cls_n[3]},
+                   "algorithmic_min_gmacs_per_system": macs_min / nsys / 1e9,
+                   "executed_gmacs_per_system": macs / nsys / 1e9}
+    else:
+        # shared-memory look-up ceiling of the table kernel: a row update of 16 bytes x 16 pivots
+        # (256 byte-MACs) costs 22 LDS.128, the crossbar delivers 8 x 16 B per clk per SM
+        macs_per_clk_sm = 256.0 * 8.0 / 22.0
+        lut_peak = macs_per_clk_sm * sms * sm_mhz * 1e6
+        roofline = dict(roofline_hbm, kernel="ob2::solve_kernel<8,4,6,128>")
+        binding = {"kernel": "ob2::solve_kernel<8,4,6,128>",
+                   "bound": "shared-memory LUT bandwidth (6-bit Four-Russians tables: %.1f GF(256) MAC/clk/SM)" % macs_per_clk_sm,
+                   "achieved": macs / (kern_ms / 1e3) / 1e12, "peak": lut_peak / 1e12, "unit": "T GF-MAC/s",
+                   "frac": macs / (kern_ms / 1e3) / lut_peak, "sm_mhz_used": sm_mhz,
+                   "algorithmic_min_gmacs_per_system": macs_min / nsys / 1e9,
+                   "executed_gmacs_per_system": macs / nsys / 1e9}
 
     # ---- streaming row ops (BASELINE metric 1), working set 1.34 GB >> L2
     rowops = None
@@ -290,7 +355,8 @@ def run_b200_arm(args):
                        "l2": "inputs %.2f GB per GPU >> 126 MB L2; pristine batch restored by a device copy inside the timed region" % ((A0.numel() + B0.numel()) / 1e9),
                        "generator": "splitmix64 counter stream (oblas_b200_fill_random)"},
             "kernel_ms_per_step": kern_ms, "gpu_launches": int(launches),
-            "roofline": roofline, "roofline_binding": binding, "rowops": rowops, "parity": parity}
+            "roofline": roofline, "roofline_panel": binding, "roofline_hbm": roofline_hbm, "rowops": rowops,
+            "parity": parity}
     if rank == 0:
         line["clocks"] = clocks
     # ---- e2e through the host-buffer C-ABI call (rank-local, max over ranks)

@@ -92,6 +92,11 @@ void oblas_b200_set_panel_path(int general_only);
  * (panel load, panel factorisation, trailing update, permutation; SM cycles summed
  * over CTAs); out (may be NULL) receives the 4 counters collected so far */
 int oblas_b200_solve_phases(int enable, uint64_t *out);
+/* diagnostics: CUDA-event device times of the kernel classes of the tensor-core elimination,
+ * recorded on the launching stream.  enable != 0 starts recording; ms_out / launches_out (4
+ * entries each, may be NULL) receive what was recorded so far (0 outer-panel factorisation,
+ * 1 pivot-row expansion, 2 tcgen05 rank-128 update, 3 row permutation) and reset it. */
+int oblas_b200_solve_tc_times(int enable, double *ms_out, uint64_t *launches_out);
 /* number of kernels this library has launched so far */
 uint64_t oblas_b200_launch_count(void);
 

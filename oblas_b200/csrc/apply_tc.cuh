@@ -320,13 +320,15 @@ OB2_D void epilogue_tile(uint32_t tm, uint32_t acc_col, uint32_t warp, uint32_t 
     if (cc + 1 < e.c_hi) tmem_ld32(nxt, tbase + (cc + 1) * 32);   // next chunk's TMEM read overlaps this chunk's packing
     // parity of every accumulator (integer-valued fp32 < 2^23: adding 2^23 leaves it in the
     // mantissa LSB), column c = 4*j + k2 packed at bit k2*8 + j of this lane's word
-    uint32_t w = 0;
+    // (four partial words: the OR chain is 8 deep instead of 32)
+    uint32_t wp[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int c = 0; c < 32; c++) {
       const uint32_t bits = __float_as_uint(__uint_as_float(cur[c]) + 8388608.0f);
       const int pos = (c & 3) * 8 + (c >> 2);
-      w |= (bits << pos) & (1u << pos);
+      wp[c & 3] |= (bits << pos) & (1u << pos);
     }
+    uint32_t w = (wp[0] | wp[1]) | (wp[2] | wp[3]);
     // 8x8 bit transposes across the 8 lanes (bit planes) of a row: lane bit i <-> index bit i.
     // Afterwards lane (row rr, gc) holds bytes Y[rr][4*gc .. 4*gc+3] (bit a = plane a).
 #pragma unroll

@@ -50,6 +50,9 @@ struct Ctx {
   void *tc_ws = nullptr;      // workspace of the current stream (set by tc_ws_reserve)
   size_t tc_ws_bytes = 0;
   int *tc_status = nullptr;  // pinned + mapped: the kernel sets it if a barrier wait gave up
+  // diagnostics: CUDA-event timing of the kernel classes of the tensor-core elimination
+  bool tc_timing = false;
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> tc_events;  // (class, (start, stop))
   int no_fast_panel = 0;               // diagnostics: general panel path only
   unsigned long long *d_phase = nullptr;  // solve-kernel phase counters (diagnostics)
   DevTableSet *d_sets = nullptr;  // [TS_COUNT] in device memory
@@ -792,6 +795,46 @@ int apply_tc_run(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, con
 }
 
 
+// ---- diagnostics: per-kernel-class device times of the tensor-core elimination ----------
+// classes: 0 outer-panel factorisation, 1 pivot-row expansion, 2 tcgen05 update, 3 permutation
+struct TcTimer {
+  int cls;
+  cudaEvent_t a = nullptr, b = nullptr;
+  explicit TcTimer(int c) : cls(c) {
+    if (!g.tc_timing) return;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { a = b = nullptr; return; }
+    cudaEventRecord(a, g.stream);
+  }
+  ~TcTimer() {
+    if (!a) return;
+    cudaEventRecord(b, g.stream);
+    g.tc_events.push_back({cls, {a, b}});
+  }
+};
+extern "C" int oblas_b200_solve_tc_times(int enable, double *ms_out, uint64_t *launches_out) {
+  if (ensure_init()) return -1;
+  std::lock_guard<std::mutex> lk(g.mu);
+  double ms[4] = {0, 0, 0, 0};
+  uint64_t n[4] = {0, 0, 0, 0};
+  if (!g.tc_events.empty()) CK(cudaDeviceSynchronize());
+  for (auto &e : g.tc_events) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, e.second.first, e.second.second) == cudaSuccess) {
+      ms[e.first] += t;
+      n[e.first]++;
+    }
+    cudaEventDestroy(e.second.first);
+    cudaEventDestroy(e.second.second);
+  }
+  g.tc_events.clear();
+  for (int k = 0; k < 4; k++) {
+    if (ms_out) ms_out[k] = ms[k];
+    if (launches_out) launches_out[k] = n[k];
+  }
+  g.tc_timing = enable != 0;
+  return 0;
+}
+
 // ---- tensor-core elimination: host side ------------------------------------------------
 // Outer panels of 128 columns.  Per outer panel and chunk of systems:
 //   panel_kernel    (solve.cuh)    factorises the 128-column window in shared memory, leaves the
@@ -857,8 +900,11 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
       pa.pivcols = p.pivcols ? p.pivcols + first * rows : nullptr;
       pa.nsys = cnt; pa.outer = outer; pa.inv = p.inv; pa.no_fast_panel = p.no_fast_panel;
       // the row map lives in global memory as [sys][rows] u16 with a 16-byte aligned pitch
-      int rc = launch_panel_t<6, 128>(pa, grid, g.smem_optin, g.stream);
-      if (rc) return fail("solve (tensor-core path): panel kernel launch configuration failed (%d)", rc);
+      {
+        TcTimer tt(0);
+        int rc = launch_panel_t<6, 128>(pa, grid, g.smem_optin, g.stream);
+        if (rc) return fail("solve (tensor-core path): panel kernel launch configuration failed (%d)", rc);
+      }
       if (after_launch("solve (outer panel)")) return -1;
       const uint32_t a_col0 = (outer + 1) * kOuterBytes;
       const uint32_t a_rest = p.a_bytes > a_col0 ? p.a_bytes - a_col0 : 0;
@@ -887,7 +933,10 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
       const size_t work = (size_t)cnt * ntiles * ksteps * (kTileN / 4);
       uint32_t eg = (uint32_t)((work + 255) / 256);
       if (eg > (uint32_t)g.sm_count * 16) eg = (uint32_t)g.sm_count * 16;
-      expand_d_kernel<<<eg, 256, 0, g.stream>>>(e);
+      {
+        TcTimer tt(1);
+        expand_d_kernel<<<eg, 256, 0, g.stream>>>(e);
+      }
       if (after_launch("solve (pivot-row expansion)")) return -1;
       ApplyTcArgs a;
       memset(&a, 0, sizeof a);
@@ -896,7 +945,10 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
       a.reg[0] = reg[0]; a.reg[1] = reg[1]; a.nreg = nreg;
       a.accumulate = 1; a.status = dstatus;
       { const char *dv = getenv("OBLAS_B200_TC_DEBUG"); a.dbg = dv ? atoi(dv) : 0; }
-      if (tc_launch(a, getenv("OBLAS_B200_TC_STREAM_A") ? 1 : 0)) return -1;
+      {
+        TcTimer tt(2);
+        if (tc_launch(a, getenv("OBLAS_B200_TC_STREAM_A") ? 1 : 0)) return -1;
+      }
     }
     PermuteArgs pm;
     memset(&pm, 0, sizeof pm);
@@ -904,7 +956,10 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
     pm.B = B; pm.b_rs = p.b_rs; pm.b_ss = p.b_ss; pm.b_bytes = B ? p.b_bytes : 0;
     pm.rows = rows; pm.nsys = cnt; pm.pos2phys = maps; pm.tcount = tcount; pm.rank = p.rank + first;
     pm.stage_bytes = stage_bytes;
-    permute_kernel<<<grid, 512, pmap + stage_bytes + 16, g.stream>>>(pm);
+    {
+      TcTimer tt(3);
+      permute_kernel<<<grid, 512, pmap + stage_bytes + 16, g.stream>>>(pm);
+    }
     if (after_launch("solve (row permutation)")) return -1;
   }
   return 0;
