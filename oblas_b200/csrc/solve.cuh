@@ -192,11 +192,25 @@ OB2_D void build_table_part(uint4 *tg /* entry 0 of table g, this chunk */, int 
 // ---------------------------------------------------------------------------
 // trailing update of one column tile (tile_bytes <= WT) of A or B
 // ---------------------------------------------------------------------------
+// Optional second source of a tile: chunks (16-byte columns) below `split` are taken from / written
+// to the matrix at base2 (row stride rs2, chunk c at byte 16*c of a row) instead of the tile's own
+// matrix.  The outer-panel factorisation (panel_kernel) uses it to update the live part of its
+// 128-byte column window and the live part of the coefficient matrix E in ONE pass.
+struct TileAlt {
+  uint8_t *base2 = nullptr;
+  size_t rs2 = 0;
+  uint32_t split = 0;
+};
+
 template <int EXP, int NBW, int KB, int WT>
 OB2_D void update_tile(uint8_t *base, size_t rs, uint32_t rows, uint32_t tile_off,
                        uint32_t tile_bytes, uint32_t npiv, const uint16_t *piv_phys,
-                       const uint32_t *V, uint4 *tab, uint32_t *pan_next, uint32_t pan_off) {
+                       const uint32_t *V, uint4 *tab, uint32_t *pan_next, uint32_t pan_off,
+                       const TileAlt alt = TileAlt()) {
   using G = Geo<NBW, KB, WT>;
+  auto chunk_ptr = [&](uint32_t r, uint32_t ch) -> uint8_t * {
+    return ch < alt.split ? alt.base2 + (size_t)r * alt.rs2 + ch * 16 : base + (size_t)r * rs + tile_off + ch * 16;
+  };
   constexpr int CW = G::CW, NG = G::NG, LASTBITS = G::LASTBITS;
   constexpr int PARTS = 1 << (KB - 4);                 // threads per (table, chunk)
   constexpr int LPARTS = LASTBITS > 4 ? (1 << (LASTBITS - 4)) : 1;
@@ -209,14 +223,14 @@ OB2_D void update_tile(uint8_t *base, size_t rs, uint32_t rows, uint32_t tile_of
     uint32_t ch = it % cwt, q = it / cwt;
     uint32_t part = q % PARTS, g = q / PARTS;
     build_table_part<EXP, KB>(tab + (size_t)(g << KB) * CW + ch, CW, g * KB, nbasis, part, [&](uint32_t s) {
-      return *reinterpret_cast<const uint4 *>(base + (size_t)piv_phys[s] * rs + tile_off + ch * 16);
+      return *reinterpret_cast<const uint4 *>(chunk_ptr(piv_phys[s], ch));
     });
   }
   for (uint32_t it = tid; it < (uint32_t)LPARTS * cwt; it += T) {
     uint32_t ch = it % cwt, part = it / cwt;
     build_table_part<EXP, LASTBITS>(tab + (size_t)((NG - 1) << KB) * CW + ch, CW, (NG - 1) * KB, nbasis, part,
                                     [&](uint32_t s) {
-      return *reinterpret_cast<const uint4 *>(base + (size_t)piv_phys[s] * rs + tile_off + ch * 16);
+      return *reinterpret_cast<const uint4 *>(chunk_ptr(piv_phys[s], ch));
     });
   }
   __syncthreads();
@@ -247,7 +261,7 @@ OB2_D void update_tile(uint8_t *base, size_t rs, uint32_t rows, uint32_t tile_of
 #pragma unroll
     for (int w = 0; w < NBW; w++) any |= m.v.w[w];
     m.upd = m.live && (any != 0);
-    m.p = base + (size_t)m.r * rs + tile_off + my_ch * 16;
+    m.p = chunk_ptr(m.r, my_ch);
     m.x = make_uint4(0, 0, 0, 0);
     if (m.upd || (m.live && pan_lane)) m.x = *reinterpret_cast<const uint4 *>(m.p);
     return m;
@@ -876,9 +890,28 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
       }
       __syncthreads();
       const uint32_t next_off = (q + 1 < INNER && pi + 1 < npanels) ? (pi + 1) * (NBW * 4) : 0xffffffffu;
-      update_tile<EXP, NBW, KB, WT>(A, p.a_rs, rows, win_off, win_bytes, n, piv_phys, V, tab, pan, next_off);
+      if (n == (uint32_t)NPIV && (gcount & 15u) == 0 && win_bytes == (uint32_t)kOuterBytes) {
+        // Full 16-pivot step on a 16-aligned basis range: the window only changes from byte
+        // gcount on (left of it the pivot rows are zero) and E only has contents below byte
+        // gcount, so ONE tile pass updates chunks [0, gcount/16) of E and chunks [gcount/16, 8)
+        // of the window.  E's new 16 columns are the step's coefficients themselves:
+        // E[r][gcount..gcount+16) = V[r] (own-term cancellation of the pivot rows undone).
+        const uint32_t split = gcount >> 4;
+        for (uint32_t r = tid; r < rows; r += T) {
+          PanelVec<NBW> v = ldv<NBW>(V + r * NBW);
+          *reinterpret_cast<uint4 *>(E + (size_t)r * kOuterBytes + gcount) = make_uint4(v.w[0], v.w[1], v.w[2], v.w[3]);
+        }
+        __syncthreads();
+        for (uint32_t s2 = tid; s2 < n; s2 += T)   // V holds V ^ e_s for pivot s; the unit injected above cancels it
+          E[(size_t)piv_phys[s2] * kOuterBytes + gcount + s2] ^= 1;
+        TileAlt alt;
+        alt.base2 = E; alt.rs2 = kOuterBytes; alt.split = split;
+        update_tile<EXP, NBW, KB, WT>(A, p.a_rs, rows, win_off, win_bytes, n, piv_phys, V, tab, pan, next_off, alt);
+      } else {
+        update_tile<EXP, NBW, KB, WT>(A, p.a_rs, rows, win_off, win_bytes, n, piv_phys, V, tab, pan, next_off);
+        update_tile<EXP, NBW, KB, WT>(E, kOuterBytes, rows, 0, kOuterBytes, n, piv_phys, V, tab, nullptr, 0xffffffffu);
+      }
       pan_ready = next_off != 0xffffffffu && next_off < p.a_bytes;
-      update_tile<EXP, NBW, KB, WT>(E, kOuterBytes, rows, 0, kOuterBytes, n, piv_phys, V, tab, nullptr, 0xffffffffu);
       gcount += n;
     }
     // own-term cancellation of the outer update: new pivot row = E * P_old, not old ^ E * P_old
