@@ -173,6 +173,19 @@ int oblas_b200_nnz_batch(int field, const void *bits, size_t row_stride, uint32_
                          const uint32_t *rows_idx, size_t nrows, uint32_t s, uint32_t e,
                          uint32_t *out);
 
+/* ---- column operations and accessors on device-resident matrices ("next" row f-3) ---------- */
+/* gfmat_swapcol (gfmat.c:215-231) for a batch: in system s (base + s * sys_stride, `rows` rows of
+ * row_stride bytes) columns col_i[s] and col_j[s] are exchanged.  Elements are packed as in gfmat
+ * (gfmat.c:88,97); an octmat is field GF256.  col_i/col_j: nsys entries, device-visible or host. */
+int oblas_b200_swapcols_batch(int field, void *bits, size_t row_stride, size_t sys_stride, uint32_t rows,
+                              const uint32_t *col_i, const uint32_t *col_j, size_t nsys);
+/* gfmat_get / gfmat_set (gfmat.c:83-98) for n (row, column) pairs of one matrix.  Index arrays and
+ * vals: device-visible or host; out_dev: device-visible.  Pairs of one set call must be distinct. */
+int oblas_b200_get_elements(int field, const void *bits, size_t row_stride, const uint32_t *rows_idx,
+                            const uint32_t *cols_idx, size_t n, uint8_t *out_dev);
+int oblas_b200_set_elements(int field, void *bits, size_t row_stride, const uint32_t *rows_idx,
+                            const uint32_t *cols_idx, const uint8_t *vals, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -176,6 +176,63 @@ __global__ void nnz_kernel(const uint8_t *bits, size_t row_stride, const uint32_
   if (lane == 0) out[warp] = cnt;
 }
 
+// ---- column operations / accessors on packed matrices -----------
+// element j of a row = bits [(j % vpw) * EXP, +EXP) of 32-bit word j / vpw (gfmat.c:88,97;
+// for octmat bytes the same with EXP = 8 on a little-endian machine)
+template <int EXP>
+__device__ __forceinline__ uint32_t elem_get(uint32_t w, uint32_t at) { return (w >> at) & ((1u << EXP) - 1u); }
+template <int EXP>
+__device__ __forceinline__ uint32_t elem_put(uint32_t w, uint32_t at, uint32_t v) {
+  const uint32_t m = ((1u << EXP) - 1u) << at;
+  return (w & ~m) | ((v << at) & m);
+}
+// gfmat_swapcol (gfmat.c:215-231) for a batch: system s swaps columns ci[s] and cj[s] in all rows
+template <int EXP>
+__global__ void swapcols_kernel(uint8_t *bits, size_t row_stride, size_t sys_stride, uint32_t rows,
+                                const uint32_t *ci, const uint32_t *cj, uint32_t nsys) {
+  constexpr uint32_t VPW = 32 / EXP;
+  const size_t total = (size_t)nsys * rows;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t sys = (uint32_t)(idx / rows), r = (uint32_t)(idx - (size_t)sys * rows);
+    const uint32_t i = ci[sys], j = cj[sys];
+    if (i == j) continue;
+    uint32_t *row = reinterpret_cast<uint32_t *>(bits + (size_t)sys * sys_stride + (size_t)r * row_stride);
+    const uint32_t p = i / VPW, q = j / VPW, pa = (i % VPW) * EXP, qa = (j % VPW) * EXP;
+    if (p == q) {
+      uint32_t w = row[p];
+      const uint32_t vi = elem_get<EXP>(w, pa), vj = elem_get<EXP>(w, qa);
+      row[p] = elem_put<EXP>(elem_put<EXP>(w, pa, vj), qa, vi);
+    } else {
+      const uint32_t wp = row[p], wq = row[q];
+      row[p] = elem_put<EXP>(wp, pa, elem_get<EXP>(wq, qa));
+      row[q] = elem_put<EXP>(wq, qa, elem_get<EXP>(wp, pa));
+    }
+  }
+}
+// gfmat_get / gfmat_set (gfmat.c:83-98) for n (row, column) pairs; set = clear + or with atomics so
+// that different elements of one word may be written by different threads of the same launch
+template <int EXP>
+__global__ void get_elements_kernel(const uint8_t *bits, size_t row_stride, const uint32_t *ri, const uint32_t *ci,
+                                    uint32_t n, uint8_t *out) {
+  constexpr uint32_t VPW = 32 / EXP;
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t *row = reinterpret_cast<const uint32_t *>(bits + (size_t)ri[k] * row_stride);
+  out[k] = (uint8_t)elem_get<EXP>(row[ci[k] / VPW], (ci[k] % VPW) * EXP);
+}
+template <int EXP>
+__global__ void set_elements_kernel(uint8_t *bits, size_t row_stride, const uint32_t *ri, const uint32_t *ci,
+                                    const uint8_t *vals, uint32_t n) {
+  constexpr uint32_t VPW = 32 / EXP;
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  uint32_t *w = reinterpret_cast<uint32_t *>(bits + (size_t)ri[k] * row_stride) + ci[k] / VPW;
+  const uint32_t at = (ci[k] % VPW) * EXP, m = ((1u << EXP) - 1u) << at;
+  atomicAnd(w, ~m);
+  atomicOr(w, ((uint32_t)vals[k] << at) & m);
+}
+
 }  // namespace
 
 // ============================================================================
@@ -1019,6 +1076,73 @@ int oblas_b200_nnz_batch(int field, const void *bits, size_t row_stride, uint32_
   }
   return after_launch("nnz");
 }
+
+// ---- column operations / accessors on device-resident matrices (row f-3) --------------------
+#define OB2_FIELD_SWITCH(KERNEL, GRID, BLOCK, ...)                                              \
+  switch (field) {                                                                             \
+  case OB2_GF2: KERNEL<1><<<GRID, BLOCK, 0, g.stream>>>(__VA_ARGS__); break;                    \
+  case OB2_GF4: KERNEL<2><<<GRID, BLOCK, 0, g.stream>>>(__VA_ARGS__); break;                    \
+  case OB2_GF16: KERNEL<4><<<GRID, BLOCK, 0, g.stream>>>(__VA_ARGS__); break;                   \
+  case OB2_GF256: KERNEL<8><<<GRID, BLOCK, 0, g.stream>>>(__VA_ARGS__); break;                  \
+  default: return fail("bad field %d", field);                                                 \
+  }
+int oblas_b200_swapcols_batch(int field, void *bits, size_t row_stride, size_t sys_stride, uint32_t rows,
+                              const uint32_t *col_i, const uint32_t *col_j, size_t nsys) {
+  if (ensure_init()) return -1;
+  if (nsys == 0 || rows == 0) return 0;
+  if (!bits || !col_i || !col_j) return fail("swapcols: null pointer");
+  if (classify(bits) != PK_DEVVIS) return fail("swapcols: matrix must be device-visible");
+  if ((row_stride & 3) || (sys_stride & 3) || (reinterpret_cast<uintptr_t>(bits) & 3))
+    return fail("swapcols: base / strides must be multiples of 4");
+  std::lock_guard<std::mutex> lk(g.mu);
+  const size_t ib = nsys * sizeof(uint32_t), slot = (ib + 255) & ~(size_t)255;
+  if (scratch_reserve(2 * slot + 256)) return -1;
+  const void *di, *dj;
+  if (stage_array(col_i, ib, 0, &di) || stage_array(col_j, ib, slot, &dj)) return -1;
+  const size_t total = nsys * (size_t)rows;
+  unsigned blocks = (unsigned)((total + 255) / 256);
+  if (blocks > (unsigned)g.sm_count * 32) blocks = (unsigned)g.sm_count * 32;
+  OB2_FIELD_SWITCH(swapcols_kernel, blocks, 256, (uint8_t *)bits, row_stride, sys_stride, rows,
+                   (const uint32_t *)di, (const uint32_t *)dj, (uint32_t)nsys)
+  return after_launch("swapcols");
+}
+int oblas_b200_get_elements(int field, const void *bits, size_t row_stride, const uint32_t *rows_idx,
+                            const uint32_t *cols_idx, size_t n, uint8_t *out_dev) {
+  if (ensure_init()) return -1;
+  if (n == 0) return 0;
+  if (!bits || !rows_idx || !cols_idx || !out_dev) return fail("get_elements: null pointer");
+  if (classify(bits) != PK_DEVVIS || classify(out_dev) != PK_DEVVIS)
+    return fail("get_elements: matrix and output must be device-visible");
+  if (n > 0x7fffffffu) return fail("get_elements: too many elements");
+  std::lock_guard<std::mutex> lk(g.mu);
+  const size_t ib = n * sizeof(uint32_t), slot = (ib + 255) & ~(size_t)255;
+  if (scratch_reserve(2 * slot + 256)) return -1;
+  const void *dr, *dc;
+  if (stage_array(rows_idx, ib, 0, &dr) || stage_array(cols_idx, ib, slot, &dc)) return -1;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  OB2_FIELD_SWITCH(get_elements_kernel, blocks, 256, (const uint8_t *)bits, row_stride, (const uint32_t *)dr,
+                   (const uint32_t *)dc, (uint32_t)n, out_dev)
+  return after_launch("get_elements");
+}
+int oblas_b200_set_elements(int field, void *bits, size_t row_stride, const uint32_t *rows_idx,
+                            const uint32_t *cols_idx, const uint8_t *vals, size_t n) {
+  if (ensure_init()) return -1;
+  if (n == 0) return 0;
+  if (!bits || !rows_idx || !cols_idx || !vals) return fail("set_elements: null pointer");
+  if (classify(bits) != PK_DEVVIS) return fail("set_elements: matrix must be device-visible");
+  if (n > 0x7fffffffu) return fail("set_elements: too many elements");
+  std::lock_guard<std::mutex> lk(g.mu);
+  const size_t ib = n * sizeof(uint32_t), slot = (ib + 255) & ~(size_t)255;
+  if (scratch_reserve(2 * slot + n + 512)) return -1;
+  const void *dr, *dc, *dv;
+  if (stage_array(rows_idx, ib, 0, &dr) || stage_array(cols_idx, ib, slot, &dc) || stage_array(vals, n, 2 * slot, &dv))
+    return -1;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  OB2_FIELD_SWITCH(set_elements_kernel, blocks, 256, (uint8_t *)bits, row_stride, (const uint32_t *)dr,
+                   (const uint32_t *)dc, (const uint8_t *)dv, (uint32_t)n)
+  return after_launch("set_elements");
+}
+#undef OB2_FIELD_SWITCH
 
 }  // extern "C"
 
