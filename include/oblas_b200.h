@@ -186,6 +186,17 @@ int oblas_b200_get_elements(int field, const void *bits, size_t row_stride, cons
 int oblas_b200_set_elements(int field, void *bits, size_t row_stride, const uint32_t *rows_idx,
                             const uint32_t *cols_idx, const uint8_t *vals, size_t n);
 
+/* ---- tables for other field polynomials ("next" row f-4) ---------------------------------- */
+/* Host helper: split-nibble tables in the reference generator's layout (tablegen.c:66-106) for an
+ * irreducible polynomial `poly` (leading term included, e.g. 0x11B) of degree exp_bits = 2, 4 or 8.
+ * lo, hi: 16 << exp_bits bytes, inv: 1 << exp_bits bytes.  The rows lo + 16*u / hi + 16*u are what
+ * oblas_axpy(a, b, k, lo_row, hi_row) / oblas_scal take (oblas.h:24-27). */
+int oblas_b200_make_tables(unsigned exp_bits, unsigned poly, uint8_t *lo, uint8_t *hi, uint8_t *inv);
+/* Registers a table set with the device; returns a handle (>= 16) to pass as `variant` to
+ * oblas_b200_rowops together with the field of the same element width.  (The elimination and
+ * apply kernels are built for the reference's polynomials only.) */
+int oblas_b200_register_tables(unsigned exp_bits, const uint8_t *lo, const uint8_t *hi, const uint8_t *inv);
+
 #ifdef __cplusplus
 }
 #endif

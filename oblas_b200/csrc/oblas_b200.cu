@@ -57,6 +57,9 @@ struct Ctx {
   unsigned long long *d_phase = nullptr;  // solve-kernel phase counters (diagnostics)
   DevTableSet *d_sets = nullptr;  // [TS_COUNT] in device memory
   DevTableSet h_sets[TS_COUNT];
+  // table sets registered at run time for other field polynomials (row f-4): handle = 16 + index
+  std::vector<DevTableSet *> d_custom;
+  std::vector<int> custom_linear, custom_bits;
   // device scratch for index arrays handed over from plain host memory
   void *scratch = nullptr;
   size_t scratch_bytes = 0;
@@ -285,6 +288,10 @@ void oblas_b200_shutdown(void) {
   if (g.tc_status) cudaFreeHost(g.tc_status);
   g.tc_status = nullptr;
   lanes_release();
+  for (auto *d : g.d_custom) cudaFree(d);
+  g.d_custom.clear();
+  g.custom_linear.clear();
+  g.custom_bits.clear();
   cudaFree(g.d_sets);
   g.d_sets = nullptr;
   cudaStreamDestroy(g.own_stream);
@@ -458,9 +465,18 @@ int oblas_b200_rowops(int field, int variant, int op, int mul_mode, void *a, siz
   const bool needs_tab = (op == OP_AXPY || op == OP_SCAL);
   int ts = -1, mode = MUL_LIN;
   if (needs_tab && field != OB2_GF2) {
-    ts = table_set_id(field, variant);
-    if (ts < 0) return fail("rowops: bad field %d", field);
-    bool linear = g.h_sets[ts].linear != 0;
+    bool linear;
+    if (variant >= 16) {   // table set registered with oblas_b200_register_tables
+      const size_t ci = (size_t)variant - 16;
+      if (ci >= g.d_custom.size()) return fail("rowops: unknown table handle %d", variant);
+      if (g.custom_bits[ci] != (int)kBits[field]) return fail("rowops: table handle %d is for %d-bit elements", variant, g.custom_bits[ci]);
+      ts = 1000 + (int)ci;
+      linear = g.custom_linear[ci] != 0;
+    } else {
+      ts = table_set_id(field, variant);
+      if (ts < 0) return fail("rowops: bad field %d", field);
+      linear = g.h_sets[ts].linear != 0;
+    }
     if (mul_mode == OBLAS_B200_MUL_AUTO) mode = linear ? MUL_LIN : MUL_LUT;
     else if (mul_mode == OBLAS_B200_MUL_LIN) {
       if (!linear) return fail("rowops: table set %d is not GF(2)-linear, MUL_LIN is invalid", ts);
@@ -497,7 +513,7 @@ int oblas_b200_rowops(int field, int variant, int op, int mul_mode, void *a, siz
     p.dst_rows = (const uint32_t *)d_dst + first;
     p.src_rows = d_src ? (const uint32_t *)d_src + first : nullptr;
     p.u = d_u ? (const uint8_t *)d_u + first : nullptr;
-    p.ts = ts >= 0 ? g.d_sets + ts : nullptr;
+    p.ts = ts >= 1000 ? g.d_custom[ts - 1000] : (ts >= 0 ? g.d_sets + ts : nullptr);
     launch_rowops(op, mode, p, g.stream);
     if (after_launch("rowops")) return -1;
   }
@@ -1075,6 +1091,58 @@ int oblas_b200_nnz_batch(int field, const void *bits, size_t row_stride, uint32_
   default: return fail("nnz_batch: bad field %d", field);
   }
   return after_launch("nnz");
+}
+
+// ---- tables for other field polynomials ("next" row f-4) -------------------------------------
+// Split-nibble tables in the layout of the reference's generator (tablegen.c:66-106):
+//   8-bit elements: LO[u][j] = u*j, HI[u][j] = u*(j<<4);  4-bit: LO[u][j] = u*j, HI = LO<<4;
+//   2-bit: LO[u][j] = (u*(j>>2))<<2 | u*(j&3), HI = LO<<4 (the corrected form).
+// poly includes the leading term (285 = x^8+x^4+x^3+x^2+1 is the reference's GF(256) polynomial).
+int oblas_b200_make_tables(unsigned exp_bits, unsigned poly, uint8_t *lo, uint8_t *hi, uint8_t *inv) {
+  if (exp_bits != 2 && exp_bits != 4 && exp_bits != 8) return fail("make_tables: element width must be 2, 4 or 8 bits");
+  if (!lo || !hi || !inv) return fail("make_tables: null pointer");
+  if ((poly >> exp_bits) != 1u) return fail("make_tables: polynomial 0x%x is not of degree %u", poly, exp_bits);
+  const unsigned len = 1u << exp_bits;
+  auto mul = [&](unsigned a, unsigned b) { return (unsigned)gf_mul_slow(exp_bits, poly, a, b); };
+  for (unsigned u = 0; u < len; u++) {
+    inv[u] = 0;
+    for (unsigned v = 1; v < len && u; v++)
+      if (mul(u, v) == 1) inv[u] = (uint8_t)v;
+    if (u && !inv[u]) return fail("make_tables: 0x%x is not irreducible (element %u has no inverse)", poly, u);
+    for (unsigned j = 0; j < 16; j++) {
+      uint8_t l, h;
+      if (exp_bits == 8) {
+        l = (uint8_t)mul(u, j);
+        h = (uint8_t)mul(u, j << 4);
+      } else if (exp_bits == 4) {
+        l = (uint8_t)mul(u, j);
+        h = (uint8_t)(l << 4);
+      } else {
+        l = (uint8_t)((mul(u, j >> 2) << 2) | mul(u, j & 3));
+        h = (uint8_t)(l << 4);
+      }
+      lo[u * 16 + j] = l;
+      hi[u * 16 + j] = h;
+    }
+  }
+  return 0;
+}
+// Makes a table set usable by oblas_b200_rowops: returns a handle to pass as `variant` (>= 16) with
+// the field of the same element width, or a negative code.  lo/hi: 16 * 2^exp_bits bytes, inv: 2^exp_bits.
+int oblas_b200_register_tables(unsigned exp_bits, const uint8_t *lo, const uint8_t *hi, const uint8_t *inv) {
+  if (ensure_init()) return -1;
+  if (exp_bits != 2 && exp_bits != 4 && exp_bits != 8) return fail("register_tables: element width must be 2, 4 or 8 bits");
+  if (!lo || !hi || !inv) return fail("register_tables: null pointer");
+  std::lock_guard<std::mutex> lk(g.mu);
+  DevTableSet h;
+  fill_table_set(h, lo, hi, inv, 1u << exp_bits);
+  DevTableSet *d = nullptr;
+  CK(cudaMalloc(&d, sizeof(DevTableSet)));
+  CK(cudaMemcpy(d, &h, sizeof h, cudaMemcpyHostToDevice));
+  g.d_custom.push_back(d);
+  g.custom_linear.push_back(h.linear);
+  g.custom_bits.push_back((int)exp_bits);
+  return 16 + (int)g.d_custom.size() - 1;
 }
 
 // ---- column operations / accessors on device-resident matrices (row f-3) --------------------

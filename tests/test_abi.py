@@ -46,6 +46,29 @@ def test_exported_tables_match_golden(golden):
         assert hashlib.sha256(b).hexdigest() == g["sha256"], name
 
 
+def test_make_tables_reproduces_the_reference_tables_and_rejects_bad_polynomials():
+    """oblas_b200_make_tables (row f-4, host-only) with the reference's polynomials (tablegen.c:7-12)
+    gives the shipped GF(256)/GF(16) tables byte for byte and, for GF(4), the LO table plus the
+    corrected HI (= LO << 4; the shipped HI carries the defect of SURVEY 9.2)."""
+    L = capi.lib()
+    for bits, poly, tag in ((8, 285, "GF2_8"), (4, 19, "GF2_4"), (2, 7, "GF2_2")):
+        n = 1 << bits
+        lo, hi, inv = (C.c_uint8 * (16 * n))(), (C.c_uint8 * (16 * n))(), (C.c_uint8 * n)()
+        assert L.oblas_b200_make_tables(bits, poly, lo, hi, inv) == 0
+        assert bytes(lo) == capi.table(tag + "_SHUF_LO")
+        assert bytes(inv) == capi.table(tag + "_INV")
+        if bits == 2:
+            assert bytes(hi) == bytes((b << 4) & 0xFF for b in bytes(lo))
+        else:
+            assert bytes(hi) == capi.table(tag + "_SHUF_HI")
+    lo, hi, inv = (C.c_uint8 * 4096)(), (C.c_uint8 * 4096)(), (C.c_uint8 * 256)()
+    assert L.oblas_b200_make_tables(8, 0x11B, lo, hi, inv) == 0          # AES polynomial
+    assert inv[0x53] == 0xCA                                             # FIPS-197 example: {53}^-1 = {CA}
+    assert L.oblas_b200_make_tables(8, 0x100, lo, hi, inv) != 0          # reducible
+    assert L.oblas_b200_make_tables(8, 0x1D, lo, hi, inv) != 0           # wrong degree
+    assert L.oblas_b200_make_tables(3, 0xB, lo, hi, inv) != 0            # unsupported width
+
+
 def test_struct_layouts(golden):
     assert [C.sizeof(capi.Octmat), C.sizeof(capi.Gfmat), C.sizeof(capi.Binmat)] == golden["layout"]["sizeof"]
     assert [capi.Octmat.bits.offset, capi.Gfmat.bits.offset, capi.Binmat.bits.offset] == golden["layout"]["bits_offset"]

@@ -156,3 +156,46 @@ def test_host_index_arrays_are_staged(cuda_lib):
                                           C.c_void_p(dA.data_ptr()), 64, 64, dst.ctypes.data, src.ctypes.data,
                                           u.ctypes.data, 2))
     assert np.array_equal(host(dA), A0)
+
+
+def test_rowops_with_tables_of_another_polynomial(cuda_lib):
+    """row f-4: GF(2^8) over the AES polynomial 0x11B -- tables from oblas_b200_make_tables,
+    registered on the device, used by the batched oaxpy/oscal kernels; expected values by
+    carry-less multiplication in numpy."""
+    import ctypes as C
+    lo, hi, inv = (C.c_uint8 * 4096)(), (C.c_uint8 * 4096)(), (C.c_uint8 * 256)()
+    capi.check(cuda_lib.oblas_b200_make_tables(8, 0x11B, lo, hi, inv))
+    handle = cuda_lib.oblas_b200_register_tables(8, lo, hi, inv)
+    assert handle >= 16
+
+    def mul(a, b):   # a: array, b: scalar
+        a = a.astype(np.uint16)
+        acc = np.zeros_like(a)
+        for i in range(8):
+            if (b >> i) & 1:
+                acc ^= a
+            a = a << 1
+            a = np.where(a & 0x100, a ^ 0x11B, a)
+        return acc.astype(np.uint8)
+
+    rows, st = 64, 272
+    a = splitmix_bytes(301, rows * st).reshape(rows, st).copy()
+    b = splitmix_bytes(302, rows * st).reshape(rows, st).copy()
+    dst = np.arange(rows, dtype=np.int32)
+    src = np.roll(dst, 5)
+    u = (np.arange(rows) * 7 % 256).astype(np.uint8)
+    for mulmode in (capi.MUL_AUTO, capi.MUL_LUT):
+        da = dev(a)
+        device.rowops(GF256, OP_AXPY, da, dev(b), dev(dst), dev(src), dev(u), variant=handle, mul=mulmode)
+        want = a.copy()
+        for k in range(rows):
+            if u[k]:
+                want[k] ^= mul(b[src[k]], int(u[k]))
+        assert np.array_equal(host(da), want)
+    da = dev(a)
+    device.rowops(GF256, OP_SCAL, da, None, dev(dst), None, dev(u), variant=handle)
+    want = a.copy()
+    for k in range(rows):
+        if u[k] >= 2:           # oscal: u < 2 is a no-op (octmat.c:54-63)
+            want[k] = mul(a[k], int(u[k]))
+    assert np.array_equal(host(da), want)
