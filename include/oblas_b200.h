@@ -88,9 +88,11 @@ void oblas_b200_set_tuning(int solve_geo, int apply_geo);
 /* diagnostics/tests: general_only != 0 disables the register-resident fast panel
  * factorisation (identical results, slower) */
 void oblas_b200_set_panel_path(int general_only);
-/* diagnostics: enable != 0 starts per-phase cycle counters of the elimination kernel
- * (panel load, panel factorisation, trailing update, permutation; SM cycles summed
- * over CTAs); out (may be NULL) receives the 4 counters collected so far */
+/* diagnostics: enable != 0 starts per-phase cycle counters of the elimination kernels (SM cycles
+ * of thread 0 summed over CTAs); out (may be NULL) receives the 5 counters collected so far.
+ * Table kernel: panel load, panel factorisation, trailing update, permutation, 0.  Outer-panel
+ * kernel of the tensor-core path: panel load + clear, factorisation, unit injection / direct E
+ * columns, tile passes, per-system prologue and epilogue. */
 int oblas_b200_solve_phases(int enable, uint64_t *out);
 /* diagnostics: CUDA-event device times of the kernel classes of the tensor-core elimination,
  * recorded on the launching stream.  enable != 0 starts recording; ms_out / launches_out (4

@@ -331,7 +331,7 @@ int oblas_b200_solve_phases(int enable, uint64_t *out) {
   if (ensure_init()) return -1;
   if (out && g.d_phase) {
     CK(cudaStreamSynchronize(g.stream));
-    CK(cudaMemcpy(out, g.d_phase, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out, g.d_phase, 5 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   }
   if (enable) {
     if (!g.d_phase) CK(cudaMalloc(&g.d_phase, 8 * sizeof(uint64_t)));
@@ -972,6 +972,7 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
       pa.E = E; pa.pos2phys = maps; pa.tcount = tcount; pa.piv_all = piv_all; pa.npiv = npiv;
       pa.pivcols = p.pivcols ? p.pivcols + first * rows : nullptr;
       pa.nsys = cnt; pa.outer = outer; pa.inv = p.inv; pa.no_fast_panel = p.no_fast_panel;
+      pa.phase = g.d_phase;
       // the row map lives in global memory as [sys][rows] u16 with a 16-byte aligned pitch
       {
         TcTimer tt(0);

@@ -728,6 +728,7 @@ struct PanelArgs {
   uint32_t outer;           // outer panel index
   const uint8_t *inv;
   int no_fast_panel;
+  unsigned long long *phase;   // optional diagnostics: cycles per phase summed over CTAs (5 counters)
 };
 
 constexpr int kOuterBytes = 128;   // outer panel width (GF(256): bytes == columns)
@@ -756,6 +757,22 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
   uint32_t *vrow = reinterpret_cast<uint32_t *>(sp);       sp += (size_t)EXP * NBW * 4;
   uint32_t *scal = reinterpret_cast<uint32_t *>(sp);
 
+  // phase clock (diagnostics only): 0 panel load + clear, 1 factorisation, 2 unit injection and
+  // direct E columns, 3 tile pass(es), 4 per-system prologue / epilogue
+  long long t_last = 0;
+  unsigned long long acc_phase[5] = {0, 0, 0, 0, 0};
+  auto tick = [&](int ph) {
+#ifndef OB2_EMU
+    if (p.phase && tid == 0) {
+      long long now = clock64();
+      acc_phase[ph] += (unsigned long long)(now - t_last);
+      t_last = now;
+    }
+#endif
+  };
+#ifndef OB2_EMU
+  if (p.phase && tid == 0) t_last = clock64();
+#endif
   const uint32_t npanels = (p.cols + NPIV - 1) / NPIV;
   const uint32_t win_off = p.outer * kOuterBytes;
   const uint32_t win_bytes = (p.a_bytes - win_off < (uint32_t)kOuterBytes) ? (p.a_bytes - win_off) : (uint32_t)kOuterBytes;
@@ -772,6 +789,7 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
     uint32_t gcount = 0;                                // pivots of this outer panel so far
     bool pan_ready = false;
     __syncthreads();
+    tick(4);
 
     for (uint32_t q = 0; q < INNER; q++) {
       const uint32_t pi = p.outer * INNER + q;
@@ -787,6 +805,7 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
         }
       }
       __syncthreads();
+      tick(0);
       uint32_t n = 0;
       constexpr uint32_t kFastThreads = (uint32_t)((NPIV + 32 + 31) / 32 * 32);
       bool fast = false;
@@ -874,6 +893,7 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
         n++;
         t++;
       }
+      tick(1);
       pan_ready = false;
       if (n == 0) continue;
       if (!fast) {
@@ -904,6 +924,7 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
         __syncthreads();
         for (uint32_t s2 = tid; s2 < n; s2 += T)   // V holds V ^ e_s for pivot s; the unit injected above cancels it
           E[(size_t)piv_phys[s2] * kOuterBytes + gcount + s2] ^= 1;
+        tick(2);
         TileAlt alt;
         alt.base2 = E; alt.rs2 = kOuterBytes; alt.split = split;
         update_tile<EXP, NBW, KB, WT>(A, p.a_rs, rows, win_off, win_bytes, n, piv_phys, V, tab, pan, next_off, alt);
@@ -912,6 +933,7 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
         update_tile<EXP, NBW, KB, WT>(E, kOuterBytes, rows, 0, kOuterBytes, n, piv_phys, V, tab, nullptr, 0xffffffffu);
       }
       pan_ready = next_off != 0xffffffffu && next_off < p.a_bytes;
+      tick(3);
       gcount += n;
     }
     // own-term cancellation of the outer update: new pivot row = E * P_old, not old ^ E * P_old
@@ -922,7 +944,12 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
       p.npiv[sys] = gcount;
     }
     __syncthreads();
+    tick(4);
   }
+#ifndef OB2_EMU
+  if (p.phase && tid == 0)
+    for (int k2 = 0; k2 < 5; k2++) atomicAdd(p.phase + k2, acc_phase[k2]);
+#endif
 }
 
 template <int KB, int WT>

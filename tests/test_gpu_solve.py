@@ -179,3 +179,47 @@ def test_rows_beyond_shared_memory_fail_loudly():
     rc = capi.lib().oblas_b200_solve_batch(GF256, C.c_void_p(dA.data_ptr()), 16, 16, K, 16, 16, None, 0, 0, 0,
                                            C.c_void_p(rank.data_ptr()), None, 1)
     assert rc != 0 and b"no fallback" in capi.lib().oblas_b200_last_error()
+
+
+@pytest.mark.parametrize("rows,cols,b_bytes,nsys,deficient", [
+    (640, 640, 272, 3, 0),        # auto-dispatch size (rows >= 512): tensor-core path by default
+    (700, 650, 400, 2, 2),        # tall, cols not a multiple of 128, rank deficient
+    (520, 900, 0, 2, 0),          # wide, no right-hand side
+    (1024, 1024, 1280, 2, 1),     # cfg2 shape, one deficient system
+])
+def test_tensor_core_path_equals_table_kernel_at_mid_sizes(rows, cols, b_bytes, nsys, deficient, cuda_lib):
+    """the two elimination paths must leave identical bytes, ranks and pivot columns (the table
+    kernel itself is pinned against the oracle / the compiled reference above)"""
+    a_bytes = (cols + 15) // 16 * 16
+    A = torch.empty((nsys, rows, a_bytes), dtype=torch.uint8, device="cuda")
+    device.fill_random(A, 900 + rows)
+    if a_bytes > cols:
+        A[:, :, cols:] = 0
+    if deficient:   # make some rows / columns dependent in system 0
+        A[0, 5] = A[0, 3] ^ A[0, 4]
+        A[0, :, 17] = A[0, :, 2]
+        if deficient > 1:
+            A[0, :, 300] = 0
+    B = None
+    if b_bytes:
+        B = torch.empty((nsys, rows, b_bytes), dtype=torch.uint8, device="cuda")
+        device.fill_random(B, 901 + rows)
+    out = {}
+    for name, geo in (("table", 1), ("tc", 3)):
+        cuda_lib.oblas_b200_set_tuning(geo, -1)
+        a, b = A.clone(), (B.clone() if B is not None else None)
+        rank, piv = device.solve_batch(GF256, a, cols, b, want_pivcols=True)
+        capi.check(cuda_lib.oblas_b200_sync(), "sync")
+        out[name] = (a, b, rank, piv)
+    cuda_lib.oblas_b200_set_tuning(-1, -1)
+    ta, tb, trank, tpiv = out["table"]
+    ca, cb, crank, cpiv = out["tc"]
+    assert torch.equal(trank, crank)
+    for s in range(nsys):
+        r = int(trank[s])
+        assert torch.equal(tpiv[s, :r], cpiv[s, :r])
+    assert torch.equal(ta, ca)
+    if B is not None:
+        assert torch.equal(tb, cb)
+    if deficient:
+        assert int(trank[0]) < min(rows, cols)

@@ -34,7 +34,8 @@ for _ in range(3):
     torch.cuda.synchronize()
     print("geo", geo, "ms", e0.elapsed_time(e1), "solves/s", nsys / e0.elapsed_time(e1) * 1e3, "full", int((rank == K).sum()))
 if os.environ.get("PHASES"):
-    ph = np.zeros(4, dtype=np.uint64)
+    ph = np.zeros(8, dtype=np.uint64)
     capi.lib().oblas_b200_solve_phases(0, ph.ctypes.data)
+    ph = ph[:4]
     tot = ph.sum()
     print("phases (share of CTA cycles): load %.3f  panel %.3f  update %.3f  permute %.3f" % tuple(ph / tot))

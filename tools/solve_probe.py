@@ -24,4 +24,14 @@ for it in range(2):
     torch.cuda.synchronize()
     capi.check(lib.oblas_b200_sync(), "sync")
     ms = e0.elapsed_time(e1)
+import numpy as np
+ph = np.zeros(8, dtype=np.uint64)
+lib.oblas_b200_solve_phases(1, None)
+A, B = A0.clone(), B0.clone()
+device.solve_batch(capi.GF256, A, K, B)
+torch.cuda.synchronize()
+lib.oblas_b200_solve_phases(0, ph.ctypes.data)
+tot = float(ph[:5].sum()) or 1.0
+print("phase cycles per system (M clk): " + ", ".join("%.3f" % (float(x) / nsys / 1e6) for x in ph[:5]) +
+      "  shares: " + ", ".join("%.1f%%" % (100 * float(x) / tot) for x in ph[:5]))
 print("solve geo=%d nsys=%d K=%d L=%d: %.2f ms, %.0f solves/s, full rank %d" % (geo, nsys, K, L, ms, nsys / ms * 1e3, int((r == K).sum())))
