@@ -445,9 +445,35 @@ def bench_rowops(device, capi, torch, hbm_peak):
     return res
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """N > 1: run this rank (and first-touch its pinned host buffers) on the CPUs of the NUMA node its
+    GPU hangs off, read from sysfs -- 8 ranks pinning 77 GB on one node share one memory controller."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        dev = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % dev) as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            return "cpus %s of %s" % (txt, dev)
+    except Exception as e:  # no sysfs / no permission: stay where we are
+        return "unchanged (%s)" % type(e).__name__
+    return "unchanged"
+
+
 def bench_e2e(L_, capi, torch, A0, B0, K, L, nsys, world, dist):
     """systems/s through oblas_b200_solve_batch_host: pinned host buffers in and out."""
     import numpy as np
+    numa = bind_to_gpu_numa_node(torch, torch.cuda.current_device()) if world > 1 else "n/a (single rank)"
     a_bytes, b_bytes = nsys * K * K, nsys * K * L
     n = nsys
     hA = L_.oblas_b200_host_alloc(a_bytes)
@@ -489,7 +515,7 @@ def bench_e2e(L_, capi, torch, A0, B0, K, L, nsys, world, dist):
     return {"value": world * n / dt, "unit": "solves/s", "h2d_bytes_per_step": a_bytes + b_bytes,
             "d2h_bytes_per_step": a_bytes + b_bytes + 4 * n, "systems_per_gpu": n, "s_per_call": dt,
             "api": "oblas_b200_solve_batch_host (pinned host A,B in; A,B,rank out; 3-lane chunked copy/compute overlap)",
-            "first_system_identity": ok}
+            "first_system_identity": ok, "host_numa_binding": numa}
 
 
 def main():
