@@ -953,15 +953,17 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
 }
 
 template <int KB, int WT>
-inline int launch_panel_t(const PanelArgs &p, uint32_t grid, size_t smem_limit, cudaStream_t s) {
+inline int launch_panel_t(const PanelArgs &p, uint32_t grid, size_t smem_limit, cudaStream_t s,
+                          uint32_t threads = 512) {
   using SM = SolveSmem<8, 4, KB, WT>;
   size_t smem = SM::bytes(p.rows);
   if (smem > smem_limit || p.rows > 65535u || p.rows == 0) return -1;
+  if (threads % SM::G::CW) return -3;
   auto k = panel_kernel<KB, WT>;
 #ifndef OB2_EMU
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
 #endif
-  OB2_LAUNCH(k, grid, 512, smem, s, p);
+  OB2_LAUNCH(k, grid, threads, smem, s, p);
   return 0;
 }
 inline size_t panel_smem_bytes(uint32_t rows) { return SolveSmem<8, 4, 6, 128>::bytes(rows); }

@@ -2,6 +2,7 @@
 // Compiles the product's kernel sources (rowops.cuh, solve.cuh, apply.cuh) for the
 // host-thread emulation of cuda_emu.h and exposes them through a small C ABI so
 // that tests/test_emu.py can compare kernel LOGIC with the oracle without a GPU.
+#include <vector>
 #include "cuda_emu.h"
 
 #include "apply.cuh"
@@ -135,6 +136,73 @@ int emu_apply(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, const 
   p.C = C; p.c_stride = c_stride; p.M = M; p.Kc = Kc; p.D = D; p.d_stride = d_stride;
   p.Y = Y; p.y_stride = y_stride; p.nbytes = nbytes; p.accumulate = accumulate;
   return launch_apply(p, geo, threads, nullptr);
+}
+
+// The tensor-core elimination (oblas_b200.cu: solve_tc_run) with its outer-panel kernel run on
+// host threads and the tcgen05 rank-128 update replaced by a plain CPU loop: checks the
+// algorithm the GPU path implements -- E as a tracked right-hand side, unit injection, the
+// combined window/E tile pass, the pivot-row snapshot, own-term cancellation, the row map that
+// persists between launches -- without a GPU.
+int emu_solve_outer(uint8_t *A, size_t a_rs, size_t a_ss, uint32_t rows, uint32_t cols, uint32_t a_bytes,
+                    uint8_t *B, size_t b_rs, size_t b_ss, uint32_t b_bytes, int32_t *rank,
+                    uint32_t *pivcols, uint32_t nsys, uint32_t grid, uint32_t threads, size_t smem_limit,
+                    int no_fast) {
+  ensure_sets();
+  const DevTableSet &T = g_sets[TS_GF256];
+  auto mul = [&](uint8_t c, uint8_t x) -> uint8_t { return T.lo[c * 16 + (x & 15)] ^ T.hi[c * 16 + (x >> 4)]; };
+  std::vector<uint8_t> E((size_t)nsys * rows * kOuterBytes);
+  std::vector<uint16_t> maps((size_t)nsys * rows), piv_all((size_t)nsys * kOuterBytes);
+  std::vector<uint32_t> tcount(nsys), npiv(nsys);
+  const uint32_t nouter = (cols + kOuterBytes - 1) / kOuterBytes;
+  if (!B) b_bytes = 0;
+  for (uint32_t outer = 0; outer < nouter; outer++) {
+    PanelArgs pa;
+    memset(&pa, 0, sizeof pa);
+    pa.A = A; pa.a_rs = a_rs; pa.a_ss = a_ss; pa.rows = rows; pa.cols = cols; pa.a_bytes = a_bytes;
+    pa.E = E.data(); pa.pos2phys = maps.data(); pa.tcount = tcount.data(); pa.piv_all = piv_all.data();
+    pa.npiv = npiv.data(); pa.pivcols = pivcols; pa.nsys = nsys; pa.outer = outer;
+    pa.inv = T.inv; pa.no_fast_panel = no_fast;
+    int rc = launch_panel_t<6, 128>(pa, grid, smem_limit, nullptr, threads);
+    if (rc) return rc;
+    const uint32_t a0 = (outer + 1) * kOuterBytes;
+    for (uint32_t s = 0; s < nsys; s++) {
+      uint8_t *As = A + (size_t)s * a_ss, *Bs = B ? B + (size_t)s * b_ss : nullptr;
+      const uint32_t np = npiv[s];
+      const uint32_t wa = a_bytes > a0 ? a_bytes - a0 : 0;
+      // snapshot of the old pivot rows (what expand_d_kernel turns into operand blocks)
+      std::vector<uint8_t> P((size_t)np * (wa + b_bytes));
+      for (uint32_t g2 = 0; g2 < np; g2++) {
+        const uint32_t pr = piv_all[(size_t)s * kOuterBytes + g2];
+        if (wa) memcpy(&P[(size_t)g2 * (wa + b_bytes)], As + (size_t)pr * a_rs + a0, wa);
+        if (b_bytes) memcpy(&P[(size_t)g2 * (wa + b_bytes) + wa], Bs + (size_t)pr * b_rs, b_bytes);
+      }
+      for (uint32_t r = 0; r < rows; r++) {
+        const uint8_t *e = &E[((size_t)s * rows + r) * kOuterBytes];
+        for (uint32_t g2 = 0; g2 < np; g2++) {
+          const uint8_t c = e[g2];
+          if (!c) continue;
+          const uint8_t *src = &P[(size_t)g2 * (wa + b_bytes)];
+          uint8_t *ya = As + (size_t)r * a_rs + a0;
+          for (uint32_t k = 0; k < wa; k++) ya[k] ^= mul(c, src[k]);
+          if (b_bytes) {
+            uint8_t *yb = Bs + (size_t)r * b_rs;
+            for (uint32_t k = 0; k < b_bytes; k++) yb[k] ^= mul(c, src[wa + k]);
+          }
+        }
+      }
+    }
+  }
+  for (uint32_t s = 0; s < nsys; s++) {   // rows into position order, ranks
+    rank[s] = (int32_t)tcount[s];
+    auto permute = [&](uint8_t *base, size_t rs, uint32_t nbytes) {
+      std::vector<uint8_t> tmp((size_t)rows * nbytes);
+      for (uint32_t i = 0; i < rows; i++) memcpy(&tmp[(size_t)i * nbytes], base + (size_t)maps[(size_t)s * rows + i] * rs, nbytes);
+      for (uint32_t i = 0; i < rows; i++) memcpy(base + (size_t)i * rs, &tmp[(size_t)i * nbytes], nbytes);
+    };
+    permute(A + (size_t)s * a_ss, a_rs, a_bytes);
+    if (B) permute(B + (size_t)s * b_ss, b_rs, b_bytes);
+  }
+  return 0;
 }
 
 }  // extern "C"

@@ -278,6 +278,9 @@ def emu():
                                   u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_size_t, C.c_int, C.c_int, C.c_int]
         lib.emu_apply.argtypes = [u8p, C.c_size_t, C.c_uint32, C.c_uint32, u8p, C.c_size_t,
                                   u8p, C.c_size_t, C.c_uint32, C.c_int, C.c_uint32, C.c_int]
+        lib.emu_solve_outer.argtypes = [u8p, C.c_size_t, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32,
+                                        u8p, C.c_size_t, C.c_size_t, C.c_uint32, i32p, u32p, C.c_uint32,
+                                        C.c_uint32, C.c_uint32, C.c_size_t, C.c_int]
         _emu = lib
     return _emu
 

@@ -196,3 +196,40 @@ def test_apply():
             Y2 = Y1.copy()
             assert e.emu_apply(ptr(Cm), cs, M, Kc, ptr(D), nbytes, ptr(Y2), nbytes, nbytes, acc, threads, geo) == 0
             assert np.array_equal(Y0, Y2), geo
+
+
+@pytest.mark.parametrize("args", [
+    dict(rows=150, cols=150, b_bytes=48, seed=400),                      # two outer panels
+    dict(rows=150, cols=150, b_bytes=48, seed=401, no_fast=1),           # general panel path
+    dict(rows=140, cols=270, b_bytes=32, seed=402),                      # wide: three outer panels, rank = rows
+    dict(rows=270, cols=140, b_bytes=0, seed=403),                       # tall, no right-hand side
+    dict(rows=160, cols=160, b_bytes=64, seed=404, deficient=2),         # free columns inside an outer panel
+    dict(rows=130, cols=130, b_bytes=16, seed=405, nsys=3, grid=2),      # persistent loop over systems
+])
+def test_outer_panel_elimination(args):
+    """the algorithm of the tensor-core elimination (outer panels of 128 columns, E tracked as a
+    right-hand side, rank-128 update) with panel_kernel on host threads and the tcgen05 product
+    replaced by a CPU loop, against the oracle: ranks, pivot columns and every byte of A and B"""
+    rows, cols, b_bytes, seed = args["rows"], args["cols"], args["b_bytes"], args["seed"]
+    nsys, deficient = args.get("nsys", 1), args.get("deficient", 0)
+    e = emu()
+    A = np.stack([random_matrix(GF256, rows, cols, seed + 2 * s, rank_deficient=deficient) for s in range(nsys)])
+    B = np.stack([splitmix_bytes(seed + 2 * s + 1, rows * b_bytes).reshape(rows, b_bytes)
+                  for s in range(nsys)]).copy() if b_bytes else None
+    A0, B0 = A.copy(), (B.copy() if B is not None else None)
+    want = [oracle_solve(GF256, A0[s], B0[s] if B0 is not None else None, cols) for s in range(nsys)]
+    rank = np.zeros(nsys, dtype=np.int32)
+    piv = np.full((nsys, rows), 0xFFFFFFFF, dtype=np.uint32)
+    rc = e.emu_solve_outer(ptr(A), A.strides[1], A.strides[0], rows, cols, A.shape[2],
+                           ptr(B) if B is not None else None, B.strides[1] if B is not None else 0,
+                           B.strides[0] if B is not None else 0, B.shape[2] if B is not None else 0,
+                           ptr(rank, i32p), ptr(piv, u32p), nsys, args.get("grid", 1), 64, SMEM, args.get("no_fast", 0))
+    assert rc == 0
+    assert [int(r) for r in rank] == [w[0] for w in want]
+    for s in range(nsys):
+        assert np.array_equal(piv[s][:want[s][0]], want[s][1][:want[s][0]])
+    assert np.array_equal(A, A0)
+    if B is not None:
+        assert np.array_equal(B, B0)
+    if deficient:
+        assert want[0][0] < min(rows, cols)
