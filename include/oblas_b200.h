@@ -94,6 +94,13 @@ void oblas_b200_set_panel_path(int general_only);
  * kernel of the tensor-core path: panel load + clear, factorisation, unit injection / direct E
  * columns, tile passes, per-system prologue and epilogue. */
 int oblas_b200_solve_phases(int enable, uint64_t *out);
+/* diagnostics: enable != 0 starts the role counters of the tcgen05 rank-128 update kernel (SM
+ * cycles of one thread per role, summed over CTAs); out (16 entries, may be NULL) receives what was
+ * collected so far.  MMA thread: 0 wait for the A operand, 1 wait for drained accumulators, 2 wait
+ * for a B stage, 3 whole loop; epilogue warp 0: 4 wait for complete accumulators, 5 read-out and
+ * stores, 6 whole loop; producer: 7 wait for a free stage, 8 whole loop; A builder warp 0: 9 wait
+ * for a free buffer, 10 build, 11 whole loop; 12 = column tiles processed. */
+int oblas_b200_update_phases(int enable, uint64_t *out);
 /* diagnostics: CUDA-event device times of the kernel classes of the tensor-core elimination,
  * recorded on the launching stream.  enable != 0 starts recording; ms_out / launches_out (4
  * entries each, may be NULL) receive what was recorded so far (0 outer-panel factorisation,

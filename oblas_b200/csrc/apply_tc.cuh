@@ -84,14 +84,15 @@ struct Cfg {
 };
 
 // A byte-column range of a (batched) row-major byte matrix.  The tensor-core kernels see the
-// concatenation of up to two regions (the elimination updates A's remaining columns and B in
-// one launch); every region starts on a column-tile boundary.
+// concatenation of up to two regions as ONE range of virtual columns (the elimination updates A's
+// remaining columns and B in one launch); column tiles are cut from the virtual range, so a tile
+// may straddle the boundary between the regions (which is a multiple of 16 columns).
 struct TcRegion {
   uint8_t *base;
   size_t rs, ss;       // row stride, system stride (bytes)
   uint32_t col0;       // first byte column of the range inside a row
   uint32_t ncols;      // bytes per row in the range (multiple of 16)
-  uint32_t tile0;      // index of the region's first column tile
+  uint32_t v0;         // first virtual column of the region (0 for region 0, region 0's ncols for region 1)
 };
 
 struct ExpandArgs {
@@ -104,8 +105,7 @@ struct ExpandArgs {
   uint32_t rowmap_stride;
   const uint32_t *nrows;
   uint8_t *Dx;             // [nsys][nhalf][ksteps][kHBlock]
-  uint32_t ksteps, nhalf, nsys;  // ksteps is a multiple of Cfg::kSPS (steps beyond Kc are zero blocks);
-                                 // region tile0 counts HALF tiles here
+  uint32_t ksteps, nhalf, nsys;  // ksteps is a multiple of Cfg::kSPS (steps beyond Kc are zero blocks)
 };
 
 struct ApplyTcArgs {
@@ -119,6 +119,11 @@ struct ApplyTcArgs {
   int accumulate;
   int *status;             // set to 1 if a barrier wait ran into the spin limit
   int dbg;                 // diagnostics (timing experiments only, results invalid): 1 = no bulk loads, 2 = no A build, 4 = no epilogue
+  // diagnostics (update_tc_kernel, may be null): SM cycles of one thread per role summed over CTAs --
+  // MMA thread: 0 wait A built, 1 wait accumulators drained, 2 wait B stage, 3 whole loop;
+  // epilogue warp 0: 4 wait accumulators complete, 5 read-out + stores, 6 whole loop; producer: 7 wait
+  // stage free, 8 whole loop; builder warp 0: 9 wait A buffer free, 10 build, 11 whole loop; 12 tiles
+  unsigned long long *prof;
 };
 
 // byte d -> 8 fp4 values, nibble b = e2m1 1.0 (0b0010) if bit b of d is set
@@ -144,9 +149,10 @@ __global__ void __launch_bounds__(256) expand_d_kernel(const ExpandArgs p) {
     const uint32_t g4 = (uint32_t)(li % G);
     const size_t rest = li / G;
     const uint32_t ks = (uint32_t)(rest % p.ksteps), half = (uint32_t)(rest / p.ksteps);
-    const TcRegion &rg = p.reg[(p.nreg > 1 && half >= p.reg[1].tile0) ? 1 : 0];
     const uint32_t nl = g4 * 4;                              // local column
-    const uint32_t n = (half - rg.tile0) * kHalfN + nl;      // column inside the region
+    const uint32_t v = half * kHalfN + nl;                   // virtual column (4 columns never straddle regions)
+    const TcRegion &rg = p.reg[(p.nreg > 1 && v >= p.reg[1].v0) ? 1 : 0];
+    const uint32_t n = v - rg.v0;                            // column inside the region
     const uint32_t nrows = p.nrows ? p.nrows[sys] : p.Kc;
     const uint8_t *src0 = rg.base + (size_t)sys * rg.ss + rg.col0 + n;
     uint32_t x[kStepJ];
@@ -189,9 +195,14 @@ OB2_D void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 // false = gave up (status flag set); every caller then leaves its loop.  backoff_ns > 0 for
 // waits that are expected to be long (keeps the pollers off the LSU pipe).
-OB2_D bool mbar_wait(uint32_t bar, uint32_t parity, int *status, uint32_t backoff_ns = 0) {
+OB2_D bool mbar_wait(uint32_t bar, uint32_t parity, int *status, uint32_t backoff_ns = 0, bool poll = false) {
   for (uint32_t spin = 0; spin < kSpinLimit; spin++) {
     uint32_t done;
+    if (poll)   // non-blocking test in a tight loop (experiment: is the wake-up of try_wait slow?)
+      asm volatile("{\n\t.reg .pred q;\n\tmbarrier.test_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
+                   "selp.u32 %0, 1, 0, q;\n\t}"
+                   : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    else
     asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
                  "selp.u32 %0, 1, 0, q;\n\t}"
                  : "=r"(done) : "r"(bar), "r"(parity) : "memory");
@@ -265,81 +276,134 @@ OB2_D void tmem_wait_ld32(uint32_t (&r)[32]) {
                :: "memory");
 }
 
+// predicated 32-bit global load (0 if !pred) / store: no branches, no divergence bookkeeping
+OB2_D uint32_t ldg_pred(const void *ptr, bool pred) {
+  uint32_t v;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.u32 %0, 0;\n\t@p ld.global.u32 %0, [%1];\n\t}"
+               : "=r"(v) : "l"(ptr), "r"((uint32_t)pred) : "memory");
+  return v;
+}
+OB2_D void stg_pred(void *ptr, uint32_t v, bool pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.u32 [%0], %1;\n\t}"
+               :: "l"(ptr), "r"(v), "r"((uint32_t)pred) : "memory");
+}
+
 // Where this lane's output words of a tile live: one aligned 32-bit word per 32-column chunk.
 // Output mapping of a chunk: lane = (row rr = lane / 8, columns 4*gc .. 4*gc+3 with gc = lane % 8),
-// i.e. 32 contiguous bytes per row and warp store.
+// i.e. 32 contiguous bytes per row and warp store.  A tile is a range of VIRTUAL columns; the
+// word of chunk cc lies in region 1 if its virtual column is >= split, else in region 0.
+// ncur = MMA width of the tile (240, or the 16-aligned rest of the virtual range for the last
+// tile): the chunks below ncur are shared out between the two warps of a lane quarter.
 template <int TILE_N>
 struct EpiTile {
   static constexpr int kChunks = (TILE_N + 31) / 32, kC0 = (kChunks + 1) / 2;
-  uint8_t *yrow;
-  uint32_t ncol0, ncols, gc;
+  uint8_t *y0, *y1;       // this lane's word of chunk 0, addressed in region 0 / in region 1
+  uint32_t vt;            // virtual column of that word
+  uint32_t split, vend;   // first virtual column of region 1, end of the virtual range
+  uint32_t ct0;           // column of that word inside the tile (4 * gc)
   int c_lo, c_hi;
   bool row_ok;
-  OB2_D void set(uint32_t warp, uint32_t lane, const TcRegion &rg, uint32_t sys, uint32_t tile_in_region,
+  OB2_D void set(uint32_t warp, uint32_t lane, const TcRegion *reg, uint32_t nreg, uint32_t sys, uint32_t tile,
                  uint32_t it, uint32_t M) {
     const uint32_t lq = warp & 3u, rr = lane >> 3;
-    gc = lane & 7u;
-    c_lo = (warp < 4) ? 0 : kC0;
-    c_hi = (warp < 4) ? kC0 : kChunks;
+    ct0 = 4 * (lane & 7u);
     const uint32_t row = it * kRowsI + lq * 4 + rr;
     row_ok = row < M;
-    ncol0 = tile_in_region * TILE_N;          // first column of the tile inside the region
-    ncols = rg.ncols;
-    yrow = rg.base + (size_t)sys * rg.ss + rg.col0 + (size_t)row * rg.rs + ncol0 + 4 * gc;
+    vt = tile * TILE_N + ct0;
+    const TcRegion &r0 = reg[0];
+    y0 = r0.base + (size_t)sys * r0.ss + r0.col0 + (size_t)row * r0.rs + vt;
+    vend = r0.ncols;
+    split = vend;
+    y1 = y0;
+    if (nreg > 1) {
+      const TcRegion &r1 = reg[1];
+      split = r1.v0;
+      vend = r1.v0 + r1.ncols;
+      y1 = r1.base + (size_t)sys * r1.ss + r1.col0 + (size_t)row * r1.rs + ((ptrdiff_t)vt - (ptrdiff_t)split);
+    }
+    const uint32_t v_tile = tile * TILE_N;
+    const uint32_t rest = vend > v_tile ? vend - v_tile : 0u;
+    const int nch = rest >= (uint32_t)TILE_N ? kChunks : (int)((rest + 31) / 32);
+    const int h = (nch + 1) / 2;
+    c_lo = (warp < 4) ? 0 : h;
+    c_hi = (warp < 4) ? h : nch;
   }
   OB2_D bool col_ok(int cc) const {
-    const uint32_t ct = (uint32_t)cc * 32 + 4 * gc;        // column inside the tile
-    return row_ok && ct < (uint32_t)TILE_N && ncol0 + ct < ncols;
+    return row_ok && (uint32_t)cc * 32 + ct0 < (uint32_t)TILE_N && vt + (uint32_t)cc * 32 < vend;
   }
+  OB2_D uint8_t *word(int cc) const { return ((vt + (uint32_t)cc * 32 >= split) ? y1 : y0) + cc * 32; }
   // accumulate mode: the old contents of this warp's chunks (issued one tile ahead of their use)
   OB2_D void load_old(uint32_t (&oldw)[kC0], int accumulate) const {
 #pragma unroll
     for (int k = 0; k < kC0; k++) {
       const int cc = c_lo + k;
-      oldw[k] = 0;
-      if (accumulate && cc < c_hi && col_ok(cc)) oldw[k] = *reinterpret_cast<const uint32_t *>(yrow + cc * 32);
+      oldw[k] = ldg_pred(word(cc), accumulate && cc < c_hi && col_ok(cc));
     }
   }
 };
 
-// accumulators of TMEM columns [acc_col, acc_col + TILE_N) -> parity -> bytes -> Y (XOR oldw)
+// accumulators of TMEM columns [acc_col, acc_col + TILE_N) -> parity -> bytes -> Y (XOR oldw).
+// One 32-register TMEM buffer per thread: tcgen05.ld of 32 columns completes in ~40 clk (measured,
+// tools/tmem_ld.cu: 720 B/clk/SM next to running MMAs), so a second buffer buys nothing -- but its 32
+// registers forced the packing into one serial FADD -> SHF chain (440 clk per chunk measured).
+// pc (diagnostics, may be null): cycles in 0 = TMEM read, 1 = packing + transposes, 2 = stores.
 template <int TILE_N>
 OB2_D void epilogue_tile(uint32_t tm, uint32_t acc_col, uint32_t warp, uint32_t lane, const EpiTile<TILE_N> &e,
-                         const uint32_t (&oldw)[EpiTile<TILE_N>::kC0]) {
+                         const uint32_t (&oldw)[EpiTile<TILE_N>::kC0], long long *pc = nullptr) {
   constexpr int kC0 = EpiTile<TILE_N>::kC0;
+  if (e.c_lo >= e.c_hi) return;
   const uint32_t tbase = tm + (((warp & 3u) * 32u) << 16) + acc_col;
-  uint32_t ra[32], rb[32];
-  tmem_ld32(ra, tbase + e.c_lo * 32);
+  uint32_t w[kC0];
+  long long q0 = pc ? clock64() : 0, t_ld = 0;
 #pragma unroll
   for (int k = 0; k < kC0; k++) {
     const int cc = e.c_lo + k;
-    if (cc >= e.c_hi) break;
-    uint32_t (&cur)[32] = (k & 1) ? rb : ra;
-    uint32_t (&nxt)[32] = (k & 1) ? ra : rb;
-    tmem_wait_ld32(cur);
-    if (cc + 1 < e.c_hi) tmem_ld32(nxt, tbase + (cc + 1) * 32);   // next chunk's TMEM read overlaps this chunk's packing
-    // parity of every accumulator (integer-valued fp32 < 2^23: adding 2^23 leaves it in the
-    // mantissa LSB), column c = 4*j + k2 packed at bit k2*8 + j of this lane's word
-    // (four partial words: the OR chain is 8 deep instead of 32)
-    uint32_t wp[4] = {0, 0, 0, 0};
+    w[k] = 0;
+    if (cc < e.c_hi) {   // warp-uniform
+      uint32_t r[32];
+      const long long l0 = pc ? clock64() : 0;
+      tmem_ld32(r, tbase + cc * 32);
+      tmem_wait_ld32(r);
+      if (pc) t_ld += clock64() - l0;
+      // parity of every accumulator (integer-valued fp32 < 2^23: adding 2^23 leaves it in the
+      // mantissa LSB).  Column c = 4*j + k2 goes to bit k2*8 + j of this lane's word: one funnel
+      // shift per accumulator pushes the LSB into the top of one of four 8-deep chains (chain k2
+      // collects byte k2 in its top byte), two instructions per accumulator in all.
+      uint32_t wq[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int c = 0; c < 32; c++) {
-      const uint32_t bits = __float_as_uint(__uint_as_float(cur[c]) + 8388608.0f);
-      const int pos = (c & 3) * 8 + (c >> 2);
-      wp[c & 3] |= (bits << pos) & (1u << pos);
+      for (int pp = 0; pp < 32; pp++) {
+        const int c = (pp & 7) * 4 + (pp >> 3);
+        const uint32_t bits = __float_as_uint(__uint_as_float(r[c]) + 8388608.0f);
+        wq[pp >> 3] = __funnelshift_r(wq[pp >> 3], bits, 1);
+      }
+      w[k] = __byte_perm(__byte_perm(wq[0], wq[1], 0x0073), __byte_perm(wq[2], wq[3], 0x0073), 0x5410);
     }
-    uint32_t w = (wp[0] | wp[1]) | (wp[2] | wp[3]);
-    // 8x8 bit transposes across the 8 lanes (bit planes) of a row: lane bit i <-> index bit i.
-    // Afterwards lane (row rr, gc) holds bytes Y[rr][4*gc .. 4*gc+3] (bit a = plane a).
+  }
+  // 8x8 bit transposes across the 8 lanes (bit planes) of a row: lane bit i <-> index bit i, all
+  // chunks of the tile together (independent shuffles).  Afterwards lane (row rr, gc) holds bytes
+  // Y[rr][4*gc .. 4*gc+3] (bit a = plane a).
 #pragma unroll
-    for (int i2 = 0; i2 < 3; i2++) {
-      const uint32_t d = 1u << i2;
-      const uint32_t m0 = (i2 == 0) ? 0x55555555u : (i2 == 1) ? 0x33333333u : 0x0f0f0f0fu;
-      const uint32_t tw = __shfl_xor_sync(0xffffffffu, w, d);
-      w = (lane & d) ? ((w & ~m0) | ((tw & ~m0) >> d)) : ((w & m0) | ((tw & m0) << d));
+  for (int i2 = 0; i2 < 3; i2++) {
+    const uint32_t d = 1u << i2;
+    const uint32_t m0 = (i2 == 0) ? 0x55555555u : (i2 == 1) ? 0x33333333u : 0x0f0f0f0fu;
+    const bool up = (lane & d) != 0;
+#pragma unroll
+    for (int k = 0; k < kC0; k++) {
+      const uint32_t tw = __shfl_xor_sync(0xffffffffu, w[k], d);
+      w[k] = up ? ((w[k] & ~m0) | ((tw & ~m0) >> d)) : ((w[k] & m0) | ((tw & m0) << d));
     }
-    w ^= oldw[k];
-    if (e.col_ok(cc)) *reinterpret_cast<uint32_t *>(e.yrow + cc * 32) = w;
+  }
+  const long long q1 = pc ? clock64() : 0;
+#pragma unroll
+  for (int k = 0; k < kC0; k++) {
+    const int cc = e.c_lo + k;
+    stg_pred(e.word(cc), w[k] ^ oldw[k], cc < e.c_hi && e.col_ok(cc));
+  }
+  if (pc) {
+    const long long q2 = clock64();
+    pc[0] += t_ld;
+    pc[1] += q1 - q0 - t_ld;
+    pc[2] += q2 - q1;
   }
 }
 
@@ -610,8 +674,7 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
     auto tile_of = [&](uint32_t t, ET &e) {
       const uint32_t snt = t / itiles, it = t % itiles;
       const uint32_t sys = snt / p.ntiles, nt = snt - sys * p.ntiles;
-      const TcRegion &rg = p.reg[(p.nreg > 1 && nt >= p.reg[1].tile0) ? 1 : 0];
-      e.set(warp, lane, rg, sys, nt - rg.tile0, it, p.M);
+      e.set(warp, lane, p.reg, p.nreg, sys, nt, it, p.M);
     };
     ET cur, nxt;
     uint32_t old_cur[ET::kC0], old_nxt[ET::kC0];
@@ -647,34 +710,47 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
 // Same MMA / epilogue scheme as apply_tc_kernel<1> (tiles of 16 rows x 240 bytes, two accumulator
 // sets), but the inner dimension is only 16 steps and the A operand (the bit matrices of the 16
 // x 128 coefficients of a row tile) is the same for every column tile of that row tile: it is
-// built ONCE per (system, row tile) into a resident, double-buffered shared-memory block while
-// only the B blocks stream through a 4-stage ring.  Work unit of a CTA = (system, row tile), its
-// column tiles are processed back to back.
+// built ONCE per (system, row tile) into a resident shared-memory block while only the B blocks
+// stream through a ring.  Work unit of a CTA = (system, row tile), its column tiles are
+// processed back to back.
 //   warps 0-7 epilogue | warp 8 producer (B ring) | warp 9 MMA issuer | warps 10-13 A builders
+// What bounds it (measured: role counters below, ncu warp-state samples of the MMA warp,
+// tools/tmem_ld.cu): the MMA warp is ONE warp running dependent code at ~0.3 IPC, so every barrier
+// round trip (try_wait, descriptors to uniform registers, commit) costs it 150-250 clk -- as much
+// as two MMAs take on the tensor pipe.  Hence 4 MMAs per round trip (stages of 4 steps) and a
+// ring of 4 such stages = one column tile = 120 KB, which only fits next to ONE A buffer.  The A
+// buffer is therefore handed over in two halves (steps 0-7 / 8-15, one barrier pair each): the
+// builders rebuild a half as soon as the last column tile of the previous unit is done with it,
+// while its other half is still being multiplied, so the hand-over costs no tensor time.
+// PROF = true compiles the role cycle counters in (diagnostics; clock reads slow the MMA warp).
 // ---------------------------------------------------------------------------------------
 constexpr int kUSteps = 16;                       // K-steps = 128 coefficient columns
-constexpr int kUSPS = 2, kUStages = 4;            // B ring: 4 stages of 2 steps (15360 B)
+constexpr int kUSPS = 4, kUStages = 4;            // B ring: 4 stages of 4 steps (30720 B) = one column tile
 constexpr int kUBStage = kUSPS * kHBlock;
 constexpr int kUABuf = kUSteps * kATile;          // resident A operand of one row tile (73728 B)
-constexpr size_t kUSmemBytes = (size_t)2 * kUABuf + (size_t)kUStages * kUBStage + kLutBytes + 256 + 1024;
+constexpr int kUHalfStages = kUStages / 2;        // stages per A half
+constexpr size_t kUSmemBytes = (size_t)kUABuf + (size_t)kUStages * kUBStage + kLutBytes + 256 + 1024;
+static_assert(kUSteps == kUSPS * kUStages, "one trip around the B ring per column tile");
+static_assert(kUSteps / 2 == 2 * kBuilderWarps, "each builder warp builds two steps per A half");
 
+template <bool PROF>
 __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArgs p) {
   extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
   unsigned char *sm = tc_smem_raw + ((1024u - (smem_addr(tc_smem_raw) & 1023u)) & 1023u);
-  unsigned char *smA = sm;                                   // [2][kUSteps][kATile]
-  unsigned char *smB = sm + (size_t)2 * kUABuf;              // [kUStages][kUSPS][kHBlock]
+  unsigned char *smA = sm;                                   // [kUSteps][kATile]
+  unsigned char *smB = sm + (size_t)kUABuf;                  // [kUStages][kUSPS][kHBlock]
   uint32_t *lut = reinterpret_cast<uint32_t *>(smB + (size_t)kUStages * kUBStage);
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(lut) + kLutBytes);
-  // bars: [0..4) b_full, [4..8) b_empty, [8..10) a_full, [10..12) a_empty, [12..14) tmem_full, [14..16) tmem_empty
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+  // bars: [0..8) b_full, [8..16) b_empty, [16..18) a_full, [18..20) a_empty, [20..22) tmem_full, [22..24) tmem_empty
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 24);
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar0 = smem_addr(bars);
   auto b_full = [&](uint32_t s) { return bar0 + 8u * s; };
-  auto b_empty = [&](uint32_t s) { return bar0 + 8u * (4 + s); };
-  auto a_full = [&](uint32_t b) { return bar0 + 8u * (8 + b); };
-  auto a_empty = [&](uint32_t b) { return bar0 + 8u * (10 + b); };
-  auto tmem_full = [&](uint32_t b) { return bar0 + 8u * (12 + b); };
-  auto tmem_empty = [&](uint32_t b) { return bar0 + 8u * (14 + b); };
+  auto b_empty = [&](uint32_t s) { return bar0 + 8u * (kUStages + s); };
+  auto a_full = [&](uint32_t h) { return bar0 + 8u * (2 * kUStages + h); };
+  auto a_empty = [&](uint32_t h) { return bar0 + 8u * (2 * kUStages + 2 + h); };
+  auto tmem_full = [&](uint32_t b) { return bar0 + 8u * (2 * kUStages + 4 + b); };
+  auto tmem_empty = [&](uint32_t b) { return bar0 + 8u * (2 * kUStages + 6 + b); };
 
   build_bitmatrix_lut(lut, tid);
   if (tid == 0) {
@@ -713,7 +789,6 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
 
   const uint32_t itiles = p.itiles, ntiles = p.ntiles;
   const uint32_t nunits = p.nsys * itiles;       // (system, row tile)
-  static_assert(kUSteps % (kUSPS * kUStages) == 0, "the B ring is aligned to tiles");
 
   if (warp == kProdWarp) {
     // ------------------------------------------------------------ producer: B blocks of every column tile
@@ -721,11 +796,15 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
     const uint32_t b_dst0 = smem_addr(smB);
     uint32_t s = 0, ph = 0;
     bool ok = true;
+    const bool prof = PROF && p.prof != nullptr;
+    long long pt0 = prof ? clock64() : 0, pw = 0;
     for (uint32_t su = blockIdx.x; su < nunits && ok; su += gridDim.x) {
       const uint32_t sys = su / itiles;
       const uint8_t *src = p.Dx + (size_t)sys * ntiles * kUSteps * kHBlock;
-      for (uint32_t q = 0; q < ntiles * (kUSteps / kUSPS) && ok; q++, src += kUBStage) {
+      for (uint32_t q = 0; q < ntiles * (uint32_t)kUStages && ok; q++, src += kUBStage) {
+        const long long w0 = prof ? clock64() : 0;
         if (!mbar_wait(b_empty(s), ph ^ 1u, p.status)) { ok = false; break; }
+        if (prof) pw += clock64() - w0;
         if (leader) {
           if (p.dbg & 1) {
             mbar_arrive(b_full(s));
@@ -737,82 +816,118 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
         if (++s == (uint32_t)kUStages) { s = 0; ph ^= 1u; }
       }
     }
+    if (prof && leader) {
+      atomicAdd(p.prof + 7, (unsigned long long)pw);
+      atomicAdd(p.prof + 8, (unsigned long long)(clock64() - pt0));
+    }
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------ MMA issuer
     const bool leader = elect_one();
-    const uint32_t idesc = (1u << 7) | (1u << 10) | ((uint32_t)(kHalfN >> 3) << 17) | (1u << 23) | ((128u >> 4) << 24);
+    // A,B = E2M1 (1), K-major, scales UE8M0, M = 128, K = 64; N is set per tile: 240, or the
+    // 16-aligned rest of the virtual column range for the last tile (MMA time is proportional to N)
+    const uint32_t idesc0 = (1u << 7) | (1u << 10) | (1u << 23) | ((128u >> 4) << 24);
+    const uint32_t vend = p.reg[p.nreg - 1].v0 + p.reg[p.nreg - 1].ncols;
     const uint64_t a_desc0 = umma_desc(smem_addr(smA), kALbo, kASbo);
     const uint64_t b_desc0 = umma_desc(smem_addr(smB));
     const uint32_t sfa = tm + kSfCol, sfb = tm + kSfCol + 16;
     uint32_t ph = 0, tile_iter = 0, unit_iter = 0;
     bool ok = true;
+    const bool prof = PROF && p.prof != nullptr;
+    long long pt0 = prof ? clock64() : 0, pwa = 0, pwt = 0, pwb = 0;
     for (uint32_t su = blockIdx.x; su < nunits && ok; su += gridDim.x, unit_iter++) {
-      const uint32_t abuf = unit_iter & 1u;
-      if (!mbar_wait(a_full(abuf), (unit_iter >> 1) & 1u, p.status)) break;      // A operand of this row tile built
-      tc_fence_after();
-      const uint64_t a_desc = a_desc0 + (uint64_t)(abuf * (kUABuf >> 4));
       for (uint32_t nt = 0; nt < ntiles && ok; nt++, tile_iter++) {
         const uint32_t ab = tile_iter & 1u;
+        const bool first = nt == 0, last = nt + 1 == ntiles;
+        long long w0 = prof ? clock64() : 0;
         if (!mbar_wait(tmem_empty(ab), ((tile_iter >> 1) & 1u) ^ 1u, p.status)) { ok = false; break; }
+        if (prof) pwt += clock64() - w0;
         tc_fence_after();
         const uint32_t acc0 = tm + ab * kHalfN;
+        const uint32_t rest = vend - nt * kHalfN;          // > 0: ntiles = ceil(vend / 240)
+        const uint32_t ncur = rest >= (uint32_t)kHalfN ? (uint32_t)kHalfN : ((rest + 15u) & ~15u);
+        const uint32_t idesc = idesc0 | ((ncur >> 3) << 17);
 #pragma unroll
-        for (int pass = 0; pass < kUSteps / (kUSPS * kUStages); pass++) {
-#pragma unroll
-          for (int cs = 0; cs < kUStages; cs++) {
-            if (!mbar_wait(b_full(cs), ph, p.status)) { ok = false; break; }
-            tc_fence_after();
-            if (leader) {
-#pragma unroll
-              for (int u = 0; u < kUSPS; u++) {
-                const int step = (pass * kUStages + cs) * kUSPS + u;
-                umma_mxf4(acc0, a_desc + (uint64_t)((step * kATile) >> 4),
-                          b_desc0 + (uint64_t)((cs * kUBStage + u * kHBlock) >> 4), idesc, step > 0 ? 1u : 0u, sfa, sfb);
-              }
-              tc_commit(b_empty(cs));
-            }
+        for (int cs = 0; cs < kUStages; cs++) {
+          if (first && (cs % kUHalfStages) == 0) {          // this half of the unit's A operand is built
+            w0 = prof ? clock64() : 0;
+            if (!mbar_wait(a_full(cs / kUHalfStages), unit_iter & 1u, p.status)) { ok = false; break; }
+            if (prof) pwa += clock64() - w0;
           }
-          ph ^= 1u;
-          if (!ok) break;
+          w0 = prof ? clock64() : 0;
+          if (!mbar_wait(b_full(cs), ph, p.status)) { ok = false; break; }
+          if (prof) pwb += clock64() - w0;
+          tc_fence_after();
+          if (leader) {
+#pragma unroll
+            for (int u = 0; u < kUSPS; u++) {
+              const int step = cs * kUSPS + u;
+              umma_mxf4(acc0, a_desc0 + (uint64_t)((step * kATile) >> 4),
+                        b_desc0 + (uint64_t)((cs * kUBStage + u * kHBlock) >> 4), idesc, step > 0 ? 1u : 0u, sfa, sfb);
+            }
+            tc_commit(b_empty(cs));
+            // last column tile of the unit: everything that reads this half of A has been issued
+            if (last && (cs % kUHalfStages) == kUHalfStages - 1) tc_commit(a_empty(cs / kUHalfStages));
+          }
         }
+        ph ^= 1u;
         if (ok && leader) tc_commit(tmem_full(ab));
       }
-      if (ok && leader) tc_commit(a_empty(abuf));     // all MMAs that read this A block are done
+    }
+    if (prof && leader) {
+      atomicAdd(p.prof + 0, (unsigned long long)pwa);
+      atomicAdd(p.prof + 1, (unsigned long long)pwt);
+      atomicAdd(p.prof + 2, (unsigned long long)pwb);
+      atomicAdd(p.prof + 3, (unsigned long long)(clock64() - pt0));
+      atomicAdd(p.prof + 12, (unsigned long long)tile_iter);
     }
   } else if (warp >= kBuild0) {
     // ------------------------------------------------------------ A builders: once per (system, row tile)
     const uint32_t b = warp - kBuild0;
     const uint32_t i = lane >> 1, q = lane & 1u;
     uint32_t unit_iter = 0;
-    for (uint32_t su = blockIdx.x; su < nunits; su += gridDim.x, unit_iter++) {
+    const bool prof = PROF && p.prof != nullptr && b == 0;
+    long long pt0 = prof ? clock64() : 0, pw = 0, pb = 0;
+    bool ok = true;
+    for (uint32_t su = blockIdx.x; su < nunits && ok; su += gridDim.x, unit_iter++) {
       const uint32_t sys = su / itiles, it = su - sys * itiles;
-      const uint32_t abuf = unit_iter & 1u;
       const uint32_t row = it * kRowsI + i;
       const uint8_t *crow = p.C + (size_t)sys * p.c_ss + (size_t)row * p.c_stride + 4 * q;
+      // steps of this warp: b, b + 4 (first half), b + 8, b + 12 (second half)
       uint32_t cw[kUSteps / kBuilderWarps];
 #pragma unroll
       for (int k = 0; k < kUSteps / kBuilderWarps; k++) {
         const uint32_t step = b + k * kBuilderWarps;
         cw[k] = (row < p.M && step * kStepJ + 4 * q < p.Kc) ? __ldg(reinterpret_cast<const uint32_t *>(crow + step * kStepJ)) : 0u;
       }
-      if (!mbar_wait_warp(a_empty(abuf), ((unit_iter >> 1) & 1u) ^ 1u, p.status)) break;
-      if (!(p.dbg & 2)) {
 #pragma unroll
-        for (int k = 0; k < kUSteps / kBuilderWarps; k++) {
-          const uint32_t step = b + k * kBuilderWarps;
-          build_a_step(lut, cw[k], reinterpret_cast<uint4 *>(smA + (size_t)abuf * kUABuf + step * kATile + i * kASbo + q * kALbo));
+      for (int h = 0; h < 2; h++) {
+        const long long w0 = prof ? clock64() : 0;
+        if (!mbar_wait_warp(a_empty(h), (unit_iter & 1u) ^ 1u, p.status)) { ok = false; break; }
+        const long long w1 = prof ? clock64() : 0;
+        if (!(p.dbg & 2)) {
+#pragma unroll
+          for (int k2 = 0; k2 < 2; k2++) {
+            const int k = h * 2 + k2;
+            const uint32_t step = b + k * kBuilderWarps;
+            build_a_step(lut, cw[k], reinterpret_cast<uint4 *>(smA + step * kATile + i * kASbo + q * kALbo));
+          }
+          fence_async_smem();
         }
-        fence_async_smem();
+        mbar_arrive(a_full(h));
+        if (prof) { pw += w1 - w0; pb += clock64() - w1; }
       }
-      mbar_arrive(a_full(abuf));
+    }
+    if (prof && lane == 0) {
+      atomicAdd(p.prof + 9, (unsigned long long)pw);
+      atomicAdd(p.prof + 10, (unsigned long long)pb);
+      atomicAdd(p.prof + 11, (unsigned long long)(clock64() - pt0));
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 0..7)
     using ET = EpiTile<kHalfN>;
     auto tile_of = [&](uint32_t su, uint32_t nt, ET &e) {
       const uint32_t sys = su / itiles, it = su - sys * itiles;
-      const TcRegion &rg = p.reg[(p.nreg > 1 && nt >= p.reg[1].tile0) ? 1 : 0];
-      e.set(warp, lane, rg, sys, nt - rg.tile0, it, p.M);
+      e.set(warp, lane, p.reg, p.nreg, sys, nt, it, p.M);
     };
     ET cur, nxt;
     uint32_t old_cur[ET::kC0], old_nxt[ET::kC0];
@@ -822,6 +937,9 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
     }
     uint32_t tile_iter = 0;
     bool ok = true;
+    const bool prof = PROF && p.prof != nullptr && warp == 0;
+    long long pt0 = prof ? clock64() : 0, pw = 0, pe = 0;
+    long long pc[3] = {0, 0, 0};
     for (uint32_t su = blockIdx.x; su < nunits && ok; su += gridDim.x) {
       for (uint32_t nt = 0; nt < ntiles; nt++, tile_iter++) {
         cur = nxt;
@@ -836,12 +954,23 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
           nxt.load_old(old_nxt, p.accumulate);
         }
         const uint32_t ab = tile_iter & 1u, use = tile_iter >> 1;
+        const long long w0 = prof ? clock64() : 0;
         if (!mbar_wait_warp(tmem_full(ab), use & 1u, p.status, 32)) { ok = false; break; }
+        const long long w1 = prof ? clock64() : 0;
         tc_fence_after();
-        if (!(p.dbg & 4)) epilogue_tile<kHalfN>(tm, ab * kHalfN, warp, lane, cur, old_cur);
+        if (!(p.dbg & 4)) epilogue_tile<kHalfN>(tm, ab * kHalfN, warp, lane, cur, old_cur, prof ? pc : nullptr);
         tc_fence_before();
         mbar_arrive(tmem_empty(ab));
+        if (prof) { pw += w1 - w0; pe += clock64() - w1; }
       }
+    }
+    if (prof && lane == 0) {
+      atomicAdd(p.prof + 4, (unsigned long long)pw);
+      atomicAdd(p.prof + 5, (unsigned long long)pe);
+      atomicAdd(p.prof + 6, (unsigned long long)(clock64() - pt0));
+      atomicAdd(p.prof + 13, (unsigned long long)pc[0]);
+      atomicAdd(p.prof + 14, (unsigned long long)pc[1]);
+      atomicAdd(p.prof + 15, (unsigned long long)pc[2]);
     }
   }
   tc_fence_before();

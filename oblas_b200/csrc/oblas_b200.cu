@@ -55,6 +55,7 @@ struct Ctx {
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> tc_events;  // (class, (start, stop))
   int no_fast_panel = 0;               // diagnostics: general panel path only
   unsigned long long *d_phase = nullptr;  // solve-kernel phase counters (diagnostics)
+  unsigned long long *d_uprof = nullptr;  // update_tc_kernel role counters (diagnostics)
   DevTableSet *d_sets = nullptr;  // [TS_COUNT] in device memory
   DevTableSet h_sets[TS_COUNT];
   // table sets registered at run time for other field polynomials (row f-4): handle = 16 + index
@@ -759,7 +760,8 @@ int tc_prepare(int **dstatus) {
   if (!attr_set) {
     CK(cudaFuncSetAttribute(apply_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<1>::kSmemBytes));
     CK(cudaFuncSetAttribute(apply_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<2>::kSmemBytes));
-    CK(cudaFuncSetAttribute(update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
+    CK(cudaFuncSetAttribute(update_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
+    CK(cudaFuncSetAttribute(update_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
     attr_set = true;
   }
   CK(cudaHostGetDevicePointer((void **)dstatus, g.tc_status, 0));
@@ -815,7 +817,8 @@ int tc_launch(const ob2::tc::ApplyTcArgs &a, int nh) {
     const uint64_t nunits = (uint64_t)a.nsys * a.itiles;
     grid = (uint32_t)g.sm_count;
     if (nunits < grid) grid = (uint32_t)nunits;
-    update_tc_kernel<<<grid, kThreads, kUSmemBytes, g.stream>>>(a);
+    if (a.prof) update_tc_kernel<true><<<grid, kThreads, kUSmemBytes, g.stream>>>(a);
+    else update_tc_kernel<false><<<grid, kThreads, kUSmemBytes, g.stream>>>(a);
   }
   return after_launch("apply (tcgen05)");
 }
@@ -846,7 +849,7 @@ int apply_tc_run(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, con
     ExpandArgs e;
     memset(&e, 0, sizeof e);
     e.reg[0].base = const_cast<uint8_t *>(D); e.reg[0].rs = d_stride; e.reg[0].ss = 0;
-    e.reg[0].col0 = n0; e.reg[0].ncols = ncols; e.reg[0].tile0 = 0;
+    e.reg[0].col0 = n0; e.reg[0].ncols = ncols; e.reg[0].v0 = 0;
     e.nreg = 1; e.Kc = Kc; e.rowmap = nullptr; e.rowmap_stride = 0; e.nrows = nullptr;
     e.Dx = (uint8_t *)g.tc_ws; e.ksteps = ksteps; e.nhalf = 2 * nt; e.nsys = 1;
     const size_t work = (size_t)nt * ksteps * (kTileN / 4);
@@ -859,7 +862,7 @@ int apply_tc_run(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, con
     a.C = C; a.c_stride = c_stride; a.c_ss = 0; a.M = M; a.Kc = Kc; a.Dx = (const uint8_t *)g.tc_ws;
     a.ksteps = ksteps; a.ntiles = nt; a.itiles = itiles; a.nsys = 1;
     a.reg[0].base = Y; a.reg[0].rs = y_stride; a.reg[0].ss = 0; a.reg[0].col0 = n0; a.reg[0].ncols = ncols;
-    a.reg[0].tile0 = 0; a.nreg = 1;
+    a.reg[0].v0 = 0; a.nreg = 1;
     a.accumulate = accumulate; a.status = dstatus;
     { const char *dv = getenv("OBLAS_B200_TC_DEBUG"); a.dbg = dv ? atoi(dv) : 0; }
     if (tc_launch(a, 2)) return -1;
@@ -867,6 +870,24 @@ int apply_tc_run(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, con
   return 0;
 }
 
+
+// ---- diagnostics: where the roles of update_tc_kernel spend their cycles ------------------
+extern "C" int oblas_b200_update_phases(int enable, uint64_t *out) {
+  if (ensure_init()) return -1;
+  std::lock_guard<std::mutex> lk(g.mu);
+  if (out && g.d_uprof) {
+    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaMemcpy(out, g.d_uprof, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  }
+  if (enable) {
+    if (!g.d_uprof) CK(cudaMalloc(&g.d_uprof, 16 * sizeof(uint64_t)));
+    CK(cudaMemset(g.d_uprof, 0, 16 * sizeof(uint64_t)));
+  } else if (g.d_uprof) {
+    CK(cudaFree(g.d_uprof));
+    g.d_uprof = nullptr;
+  }
+  return 0;
+}
 
 // ---- diagnostics: per-kernel-class device times of the tensor-core elimination ----------
 // classes: 0 outer-panel factorisation, 1 pivot-row expansion, 2 tcgen05 update, 3 permutation
@@ -928,7 +949,7 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
   constexpr int kTileN = Cfg<1>::kTileN;   // 240: double-buffered accumulators
   auto tiles_of = [](uint32_t bytes) { return (bytes + kTileN - 1) / kTileN; };
   const uint32_t a_rest0 = p.a_bytes > (uint32_t)kOuterBytes ? p.a_bytes - kOuterBytes : 0;
-  const uint32_t ntiles_max = tiles_of(a_rest0) + tiles_of(p.B ? p.b_bytes : 0);
+  const uint32_t ntiles_max = tiles_of(a_rest0 + (p.B ? p.b_bytes : 0));
   const size_t dx_per_sys = (size_t)ntiles_max * ksteps * kHBlock;
   const size_t e_per_sys = (size_t)rows * kOuterBytes;
   const size_t map_per_sys = ((size_t)rows * 2 + 15) / 16 * 16;
@@ -986,19 +1007,21 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
       if (a_rest == 0 && b_cols == 0) continue;
       TcRegion reg[2];
       memset(reg, 0, sizeof reg);
-      uint32_t nreg = 0, ntiles = 0;
+      // A's remaining columns and B form one range of virtual columns; tiles are cut from the range
+      uint32_t nreg = 0, vcols = 0;
       if (a_rest) {
         reg[nreg].base = A; reg[nreg].rs = p.a_rs; reg[nreg].ss = p.a_ss; reg[nreg].col0 = a_col0;
-        reg[nreg].ncols = a_rest; reg[nreg].tile0 = ntiles;
-        ntiles += tiles_of(a_rest);
+        reg[nreg].ncols = a_rest; reg[nreg].v0 = vcols;
+        vcols += a_rest;
         nreg++;
       }
       if (b_cols) {
         reg[nreg].base = B; reg[nreg].rs = p.b_rs; reg[nreg].ss = p.b_ss; reg[nreg].col0 = 0;
-        reg[nreg].ncols = b_cols; reg[nreg].tile0 = ntiles;
-        ntiles += tiles_of(b_cols);
+        reg[nreg].ncols = b_cols; reg[nreg].v0 = vcols;
+        vcols += b_cols;
         nreg++;
       }
+      const uint32_t ntiles = tiles_of(vcols);
       ExpandArgs e;
       memset(&e, 0, sizeof e);
       e.reg[0] = reg[0]; e.reg[1] = reg[1]; e.nreg = nreg; e.Kc = kOuterBytes;
@@ -1017,7 +1040,7 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
       a.C = E; a.c_stride = kOuterBytes; a.c_ss = e_per_sys; a.M = rows; a.Kc = kOuterBytes; a.Dx = Dx;
       a.ksteps = ksteps; a.ntiles = ntiles; a.itiles = itiles; a.nsys = cnt;
       a.reg[0] = reg[0]; a.reg[1] = reg[1]; a.nreg = nreg;
-      a.accumulate = 1; a.status = dstatus;
+      a.accumulate = 1; a.status = dstatus; a.prof = g.d_uprof;
       { const char *dv = getenv("OBLAS_B200_TC_DEBUG"); a.dbg = dv ? atoi(dv) : 0; }
       {
         TcTimer tt(2);

@@ -1,0 +1,49 @@
+"""Per-kernel-class device times of the tensor-core elimination on one shape:
+python tools/tc_classes.py [nsys K L]   (OBLAS_B200_TC_DEBUG=1|2|4 switches parts of the update
+kernel off for timing experiments -- results are then invalid, only the times mean something)"""
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from oblas_b200 import capi, device
+
+nsys, K, L = (int(x) for x in (sys.argv[1:4] if len(sys.argv) >= 4 else (592, 1024, 1280)))
+device.bind(0)
+lib = capi.lib()
+A0 = torch.empty((nsys, K, K), dtype=torch.uint8, device="cuda")
+B0 = torch.empty((nsys, K, L), dtype=torch.uint8, device="cuda")
+device.fill_random(A0, 1)
+device.fill_random(B0, 2)
+lib.oblas_b200_set_tuning(3, -1)
+names = ["panel", "expand", "update", "permute"]
+for it in range(3):
+    A, B = A0.clone(), B0.clone()
+    lib.oblas_b200_solve_tc_times(1, None, None)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r, _ = device.solve_batch(capi.GF256, A, K, B)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = (C.c_double * 4)()
+    n = (C.c_uint64 * 4)()
+    lib.oblas_b200_solve_tc_times(0, ms, n)
+    rc = lib.oblas_b200_sync()
+if os.environ.get("UPROF"):
+    import numpy as np
+    lib.oblas_b200_update_phases(1, None)
+    A, B = A0.clone(), B0.clone()
+    device.solve_batch(capi.GF256, A, K, B)
+    torch.cuda.synchronize()
+    up = np.zeros(16, dtype=np.uint64)
+    lib.oblas_b200_update_phases(0, up.ctypes.data)
+    tiles = float(up[12]) or 1.0
+    lab = ["mma:wait A", "mma:wait acc drained", "mma:wait B", "mma:loop", "epi:wait acc full", "epi:readout", "epi:loop",
+           "prod:wait free", "prod:loop", "build:wait free", "build:build", "build:loop", "tiles", "epi:wait ld", "epi:pack", "epi:store"]
+    print("update_tc_kernel cycles per column tile (%d tiles): " % int(tiles) + ", ".join("%s %.0f" % (lab[k], float(up[k]) / tiles) for k in range(16) if k != 12))
+tot = e0.elapsed_time(e1)
+print("dbg=%s nsys=%d K=%d L=%d: %.2f ms, %.0f solves/s, full rank %d, sync rc %d | " % (
+    os.environ.get("OBLAS_B200_TC_DEBUG", "0"), nsys, K, L, tot, nsys / tot * 1e3, int((r == K).sum()), rc) +
+    ", ".join("%s %.2f ms/%d" % (names[k], ms[k], n[k]) for k in range(4)))
