@@ -46,7 +46,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 K_DEFAULT, L_DEFAULT, NSYS_DEFAULT = 1024, 1280, 4096
 # dram__bytes_read.sum + dram__bytes_write.sum of one update_tc_kernel launch (outer panel 0) on 296
 # systems, ncu --set full (profiles/r01_ncu_update_tc.json)
-NCU_UPDATE_DRAM_BYTES_296 = 1.062188e9 + 0.612285e9
+NCU_UPDATE_DRAM_BYTES_296 = 1.062881e9 + 0.616082e9
 METRIC = "GF(256) K=1024 solves/sec (batched Gaussian elimination + 1280-byte RHS symbol update)"
 
 
@@ -311,12 +311,13 @@ def run_b200_arm(args):
                     "algorithmic_bytes_per_launch": sys_per_launch * 2 * K * (trailing / nouter),
                     "gf256_macs_per_system": upd_macs / nsys,
                     "note": "fp4 e2m1 0/1 operands, fp32 accumulation in TMEM, parity in the epilogue; inner dimension "
-                            "128 coefficients = 16 K-steps per tile, so TMEM read-out of the accumulators is as "
-                            "long as the MMAs of a tile"}
-        # outer-panel factorisation: shared-memory look-up bound.  Per 16-column step it streams
-        # two 128-byte tiles (the window and E) of every row: 22 LDS.128 per 16 bytes x 16 pivots
+                            "128 coefficients = 16 K-steps per tile: per 2000 clk of MMAs one epilogue (2 instructions "
+                            "per accumulator) and, per row tile, one rebuild of the coefficient operand"}
+        # outer-panel factorisation: shared-memory look-up bound.  Per 16-column step it streams ONE
+        # combined 128-byte tile of every row (the live right part of the 128-column window and the
+        # live left part of E are complementary): 22 LDS.128 per 16 bytes x 16 pivots
         macs_per_clk_sm = 256.0 * 8.0 / 22.0
-        pan_macs = nsys * K * (K / 16.0) * 16 * (128 + 128)   # rows x 16-col steps x 16 pivots x 256 bytes
+        pan_macs = nsys * K * (K / 16.0) * 16 * 128            # rows x 16-col steps x 16 pivots x 128 bytes
         lut_peak = macs_per_clk_sm * sms * sm_mhz * 1e6
         binding = {"kernel": "ob2::panel_kernel<6,128>",
                    "bound": "shared-memory LUT bandwidth (6-bit Four-Russians tables: %.1f GF(256) MAC/clk/SM)" % macs_per_clk_sm,

@@ -89,7 +89,9 @@ void oblas_b200_set_tuning(int solve_geo, int apply_geo);
  * factorisation (identical results, slower) */
 void oblas_b200_set_panel_path(int general_only);
 /* diagnostics: enable != 0 starts per-phase cycle counters of the elimination kernels (SM cycles
- * of thread 0 summed over CTAs); out (may be NULL) receives the 5 counters collected so far.
+ * of thread 0 summed over CTAs); out (8 entries, may be NULL) receives the counters collected so far
+ * (entries 5..7, outer-panel kernel only: inside the factorisation -- candidate elimination, tables
+ * of the panel's bit matrix, coefficient vectors of all rows).
  * Table kernel: panel load, panel factorisation, trailing update, permutation, 0.  Outer-panel
  * kernel of the tensor-core path: panel load + clear, factorisation, unit injection / direct E
  * columns, tile passes, per-system prologue and epilogue. */

@@ -27,21 +27,22 @@
 //                     row tile.  In the elimination the rows are the pivot rows of the outer
 //                     panel, gathered through the row map.
 //   apply_tc_kernel<NH>  persistent, 1 CTA per SM, warp specialised, 14 warps:
-//                       warp 8      producer: cp.async.bulk (TMA engine) per stage, Dx -> smem
-//                       warps 10-13 A-operand builders: 16 rows x 8 coefficients of C per step,
+//                       warp 0      one elected thread issues tcgen05.mma (M=128, N=240, K=64),
+//                                   tcgen05.commit frees the stage
+//                       warp 1      producer: cp.async.bulk (TMA engine) per stage, Dx -> smem
+//                       warps 2-5   A-operand builders: 16 rows x 8 coefficients of C per step,
 //                                   each coefficient expanded to its 8x8 bit matrix through a
 //                                   256 x 32-byte table in shared memory (round robin over stages)
-//                       warp 9      one elected thread issues tcgen05.mma (M=128, N=240, K=64),
-//                                   tcgen05.commit frees the stage
-//                       warps 0-7   epilogue: tcgen05.ld, parity, 8x8 bit transposes across the 8
+//                       warps 6-13  epilogue: tcgen05.ld, parity, 8x8 bit transposes across the 8
 //                                   bit-plane lanes of a row, 32-bit coalesced stores (XOR with the
 //                                   old contents in accumulate mode)
-//                     mbarrier ring between producers and the MMA thread, 2 K-steps per stage.
+//                     mbarrier ring between producers and the MMA thread, 4 MMAs per stage.
 //                     NH = 2: tile = 16 rows x 480 bytes, one accumulator set (480 TMEM columns),
-//                             5 stages; the apply with a long inner dimension.
+//                             5 stages of 2 K-steps; the apply with a long inner dimension.
 //                     NH = 1: tile = 16 rows x 240 bytes, two accumulator sets: the epilogue of a
-//                             tile runs under the MMAs of the next one; 8 stages.  The rank-128
-//                             update of the elimination (inner dimension 16 steps only).
+//                             tile runs under the MMAs of the next one; 4 stages of 4 K-steps.
+//   update_tc_kernel   the rank-128 update of the elimination (inner dimension 16 steps only):
+//                     same roles, A operand resident per (system, row tile) -- see its header.
 // TMEM lane (16 rows x 8 bit planes) = i*8 + a, TMEM column = symbol byte n.
 //
 // Only the product build sees this file (no host-thread emulation of tcgen05).
@@ -61,11 +62,14 @@ constexpr int kHBlock = kHalfN * 32;         // bytes of one B-operand block: ha
 // when they all store the same bit-plane row: bank group = (2*group + core + row) mod 8.
 constexpr int kALbo = 144, kASbo = 288;
 constexpr int kATile = 16 * kASbo;           // bytes of one A-operand block (4608)
-constexpr int kEpiWarps = 8;                 // warps 0..7: lane quarter = warp % 4, chunk half = warp / 4
-constexpr int kProdWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1, kBuild0 = kEpiWarps + 2;
-constexpr int kBuilderWarps = 4;             // warps 10..13, one stage each, round robin
+// Warp roles.  The latency-critical single-thread roles get the LOWEST warp ids: the MMA issuer and
+// the producer run short dependent instruction sequences between barrier waits, and every cycle they
+// lose to the epilogue warps of their scheduler is a cycle the tensor pipe may run dry.
+constexpr int kMmaWarp = 0, kProdWarp = 1, kBuild0 = 2;
+constexpr int kEpi0 = 6, kEpiWarps = 8;      // warps 6..13: TMEM lane quarter = warp % 4, chunk half = (warp - 6) / 4
+constexpr int kBuilderWarps = 4;             // warps 2..5, one stage each, round robin
 constexpr int kSfCol = 480;                  // TMEM columns 480..511: scale factors (all 1.0)
-constexpr int kThreads = 32 * (kBuild0 + kBuilderWarps);
+constexpr int kThreads = 32 * (kEpi0 + kEpiWarps);
 constexpr int kLutBytes = 256 * 32;
 constexpr uint32_t kSpinLimit = 1u << 24;    // bounded waits: never hang the device
 
@@ -195,14 +199,9 @@ OB2_D void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 // false = gave up (status flag set); every caller then leaves its loop.  backoff_ns > 0 for
 // waits that are expected to be long (keeps the pollers off the LSU pipe).
-OB2_D bool mbar_wait(uint32_t bar, uint32_t parity, int *status, uint32_t backoff_ns = 0, bool poll = false) {
+OB2_D bool mbar_wait(uint32_t bar, uint32_t parity, int *status, uint32_t backoff_ns = 0) {
   for (uint32_t spin = 0; spin < kSpinLimit; spin++) {
     uint32_t done;
-    if (poll)   // non-blocking test in a tight loop (experiment: is the wake-up of try_wait slow?)
-      asm volatile("{\n\t.reg .pred q;\n\tmbarrier.test_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
-                   "selp.u32 %0, 1, 0, q;\n\t}"
-                   : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    else
     asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
                  "selp.u32 %0, 1, 0, q;\n\t}"
                  : "=r"(done) : "r"(bar), "r"(parity) : "memory");
@@ -297,21 +296,24 @@ OB2_D void stg_pred(void *ptr, uint32_t v, bool pred) {
 template <int TILE_N>
 struct EpiTile {
   static constexpr int kChunks = (TILE_N + 31) / 32, kC0 = (kChunks + 1) / 2;
-  uint8_t *y0, *y1;       // this lane's word of chunk 0, addressed in region 0 / in region 1
-  uint32_t vt;            // virtual column of that word
-  uint32_t split, vend;   // first virtual column of region 1, end of the virtual range
-  uint32_t ct0;           // column of that word inside the tile (4 * gc)
+  // per (system, row): this lane's row in region 0 / region 1 (y1 has "- split" folded in, so both
+  // are indexed by the virtual column), the region boundary and the end of the virtual range
+  uint8_t *y0, *y1;
+  uint32_t split, vend;
+  uint32_t ct0;           // column of this lane's word inside a chunk (4 * gc)
+  bool row_ok, upper;     // upper: this warp takes the second half of the tile's chunks
+  // per tile
+  uint32_t vt;            // virtual column of this lane's word of chunk 0
   int c_lo, c_hi;
-  bool row_ok;
-  OB2_D void set(uint32_t warp, uint32_t lane, const TcRegion *reg, uint32_t nreg, uint32_t sys, uint32_t tile,
-                 uint32_t it, uint32_t M) {
+  OB2_D void set_unit(uint32_t warp, uint32_t lane, const TcRegion *reg, uint32_t nreg, uint32_t sys, uint32_t it,
+                      uint32_t M) {
     const uint32_t lq = warp & 3u, rr = lane >> 3;
     ct0 = 4 * (lane & 7u);
+    upper = warp >= (uint32_t)(kEpi0 + 4);
     const uint32_t row = it * kRowsI + lq * 4 + rr;
     row_ok = row < M;
-    vt = tile * TILE_N + ct0;
     const TcRegion &r0 = reg[0];
-    y0 = r0.base + (size_t)sys * r0.ss + r0.col0 + (size_t)row * r0.rs + vt;
+    y0 = r0.base + (size_t)sys * r0.ss + r0.col0 + (size_t)row * r0.rs;
     vend = r0.ncols;
     split = vend;
     y1 = y0;
@@ -319,19 +321,30 @@ struct EpiTile {
       const TcRegion &r1 = reg[1];
       split = r1.v0;
       vend = r1.v0 + r1.ncols;
-      y1 = r1.base + (size_t)sys * r1.ss + r1.col0 + (size_t)row * r1.rs + ((ptrdiff_t)vt - (ptrdiff_t)split);
+      y1 = r1.base + (size_t)sys * r1.ss + r1.col0 + (size_t)row * r1.rs - (ptrdiff_t)split;
     }
+  }
+  OB2_D void set_tile(uint32_t tile) {
     const uint32_t v_tile = tile * TILE_N;
+    vt = v_tile + ct0;
     const uint32_t rest = vend > v_tile ? vend - v_tile : 0u;
     const int nch = rest >= (uint32_t)TILE_N ? kChunks : (int)((rest + 31) / 32);
     const int h = (nch + 1) / 2;
-    c_lo = (warp < 4) ? 0 : h;
-    c_hi = (warp < 4) ? h : nch;
+    c_lo = upper ? h : 0;
+    c_hi = upper ? nch : h;
+  }
+  OB2_D void set(uint32_t warp, uint32_t lane, const TcRegion *reg, uint32_t nreg, uint32_t sys, uint32_t tile,
+                 uint32_t it, uint32_t M) {
+    set_unit(warp, lane, reg, nreg, sys, it, M);
+    set_tile(tile);
   }
   OB2_D bool col_ok(int cc) const {
     return row_ok && (uint32_t)cc * 32 + ct0 < (uint32_t)TILE_N && vt + (uint32_t)cc * 32 < vend;
   }
-  OB2_D uint8_t *word(int cc) const { return ((vt + (uint32_t)cc * 32 >= split) ? y1 : y0) + cc * 32; }
+  OB2_D uint8_t *word(int cc) const {
+    const uint32_t v = vt + (uint32_t)cc * 32;
+    return ((v >= split) ? y1 : y0) + v;
+  }
   // accumulate mode: the old contents of this warp's chunks (issued one tile ahead of their use)
   OB2_D void load_old(uint32_t (&oldw)[kC0], int accumulate) const {
 #pragma unroll
@@ -488,10 +501,10 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = *tmem_slot;
-  if (warp < 4) {  // scale factors = 1.0 everywhere in columns 480..511 of this warp's lanes
+  if (warp >= (uint32_t)kEpi0 && warp < (uint32_t)kEpi0 + 4) {  // scale factors = 1.0 in columns 480..511 of this warp's lane quarter
 #pragma unroll
     for (uint32_t c = kSfCol; c < 512; c += 8) {
-      uint32_t ta = tm + ((warp * 32u) << 16) + c, v = 0x7f7f7f7fu;
+      uint32_t ta = tm + (((warp & 3u) * 32u) << 16) + c, v = 0x7f7f7f7fu;
       asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(ta), "r"(v) : "memory");
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -598,7 +611,7 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
       }
       if (ok && leader) tc_commit(tmem_full(ab));
     }
-  } else if (warp >= kBuild0) {
+  } else if (warp >= (uint32_t)kBuild0 && warp < (uint32_t)(kBuild0 + kBuilderWarps)) {
     // ------------------------------------------------------------ A-operand builders
     const uint32_t b = warp - kBuild0;    // this warp builds the stages with G % kBuilderWarps == b
     const uint32_t i = lane >> 1, q = lane & 1u;
@@ -669,7 +682,7 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
       G += nst;
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 0..7)
+    // ------------------------------------------------------------ epilogue (warps 6..13)
     using ET = EpiTile<kTileN>;
     auto tile_of = [&](uint32_t t, ET &e) {
       const uint32_t snt = t / itiles, it = t % itiles;
@@ -713,25 +726,36 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
 // built ONCE per (system, row tile) into a resident shared-memory block while only the B blocks
 // stream through a ring.  Work unit of a CTA = (system, row tile), its column tiles are
 // processed back to back.
-//   warps 0-7 epilogue | warp 8 producer (B ring) | warp 9 MMA issuer | warps 10-13 A builders
+//   warp 0 MMA issuer | warp 1 producer (B ring) | warps 2-5 A builders | warps 6-13 epilogue
 // What bounds it (measured: role counters below, ncu warp-state samples of the MMA warp,
 // tools/tmem_ld.cu): the MMA warp is ONE warp running dependent code at ~0.3 IPC, so every barrier
 // round trip (try_wait, descriptors to uniform registers, commit) costs it 150-250 clk -- as much
 // as two MMAs take on the tensor pipe.  Hence 4 MMAs per round trip (stages of 4 steps) and a
 // ring of 4 such stages = one column tile = 120 KB, which only fits next to ONE A buffer.  The A
-// buffer is therefore handed over in two halves (steps 0-7 / 8-15, one barrier pair each): the
-// builders rebuild a half as soon as the last column tile of the previous unit is done with it,
-// while its other half is still being multiplied, so the hand-over costs no tensor time.
+// buffer is therefore handed over in four parts (the 4 steps of a ring stage each, one barrier
+// pair per part): the builders rebuild a part as soon as the last column tile of the previous unit
+// is done with it -- 1.5 column tiles before the next unit needs it -- while the other parts are
+// still being multiplied, so the hand-over costs no tensor time.
 // PROF = true compiles the role cycle counters in (diagnostics; clock reads slow the MMA warp).
 // ---------------------------------------------------------------------------------------
 constexpr int kUSteps = 16;                       // K-steps = 128 coefficient columns
 constexpr int kUSPS = 4, kUStages = 4;            // B ring: 4 stages of 4 steps (30720 B) = one column tile
 constexpr int kUBStage = kUSPS * kHBlock;
 constexpr int kUABuf = kUSteps * kATile;          // resident A operand of one row tile (73728 B)
-constexpr int kUHalfStages = kUStages / 2;        // stages per A half
 constexpr size_t kUSmemBytes = (size_t)kUABuf + (size_t)kUStages * kUBStage + kLutBytes + 256 + 1024;
 static_assert(kUSteps == kUSPS * kUStages, "one trip around the B ring per column tile");
-static_assert(kUSteps / 2 == 2 * kBuilderWarps, "each builder warp builds two steps per A half");
+static_assert(kUSPS == kBuilderWarps, "each builder warp builds one step of every stage's A part");
+
+// Order of the column tiles inside a unit: the narrow last tile of the virtual range (its MMAs take
+// N/240 of a full tile's time) is processed SECOND.  The unit then ends with a full tile, whose 2000
+// clk of MMAs cover the part-by-part rebuild of the A operand for the next unit, and starts with a
+// full tile, whose stages need the parts 500 clk apart -- as fast as the builders deliver them.
+// (Measured: what the rebuild costs -- 14 % of the kernel -- is NOT hand-over latency but shared-
+// memory contention: the same LDS/STS work done off the hand-over path into scratch costs the same,
+// the running MMAs fetch their operands through the same banks.)
+OB2_D uint32_t update_tile_at(uint32_t j, uint32_t ntiles) {
+  return ntiles < 3 ? j : (j == 0 ? 0u : (j == 1 ? ntiles - 1 : j - 1));
+}
 
 template <bool PROF>
 __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArgs p) {
@@ -741,16 +765,17 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
   unsigned char *smB = sm + (size_t)kUABuf;                  // [kUStages][kUSPS][kHBlock]
   uint32_t *lut = reinterpret_cast<uint32_t *>(smB + (size_t)kUStages * kUBStage);
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(lut) + kLutBytes);
-  // bars: [0..8) b_full, [8..16) b_empty, [16..18) a_full, [18..20) a_empty, [20..22) tmem_full, [22..24) tmem_empty
+  // bars: b_full[S], b_empty[S], a_full[S], a_empty[S] (one A part per ring stage), tmem_full[2], tmem_empty[2]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 24);
+  static_assert(4 * kUStages + 4 <= 24, "barrier block");
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar0 = smem_addr(bars);
   auto b_full = [&](uint32_t s) { return bar0 + 8u * s; };
   auto b_empty = [&](uint32_t s) { return bar0 + 8u * (kUStages + s); };
   auto a_full = [&](uint32_t h) { return bar0 + 8u * (2 * kUStages + h); };
-  auto a_empty = [&](uint32_t h) { return bar0 + 8u * (2 * kUStages + 2 + h); };
-  auto tmem_full = [&](uint32_t b) { return bar0 + 8u * (2 * kUStages + 4 + b); };
-  auto tmem_empty = [&](uint32_t b) { return bar0 + 8u * (2 * kUStages + 6 + b); };
+  auto a_empty = [&](uint32_t h) { return bar0 + 8u * (3 * kUStages + h); };
+  auto tmem_full = [&](uint32_t b) { return bar0 + 8u * (4 * kUStages + b); };
+  auto tmem_empty = [&](uint32_t b) { return bar0 + 8u * (4 * kUStages + 2 + b); };
 
   build_bitmatrix_lut(lut, tid);
   if (tid == 0) {
@@ -758,9 +783,11 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
       mbar_init(b_full(s), 1);          // producer's expect_tx arrive
       mbar_init(b_empty(s), 1);         // tcgen05.commit
     }
+    for (uint32_t s = 0; s < (uint32_t)kUStages; s++) {
+      mbar_init(a_full(s), 32 * kBuilderWarps);
+      mbar_init(a_empty(s), 1);
+    }
     for (uint32_t b = 0; b < 2; b++) {
-      mbar_init(a_full(b), 32 * kBuilderWarps);
-      mbar_init(a_empty(b), 1);
       mbar_init(tmem_full(b), 1);
       mbar_init(tmem_empty(b), 32 * kEpiWarps);
     }
@@ -775,10 +802,10 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = *tmem_slot;
-  if (warp < 4) {  // scale factors = 1.0 everywhere in columns 480..511 of this warp's lanes
+  if (warp >= (uint32_t)kEpi0 && warp < (uint32_t)kEpi0 + 4) {  // scale factors = 1.0 in columns 480..511 of this warp's lane quarter
 #pragma unroll
     for (uint32_t c = kSfCol; c < 512; c += 8) {
-      uint32_t ta = tm + ((warp * 32u) << 16) + c, v = 0x7f7f7f7fu;
+      uint32_t ta = tm + (((warp & 3u) * 32u) << 16) + c, v = 0x7f7f7f7fu;
       asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(ta), "r"(v) : "memory");
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -800,8 +827,9 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
     long long pt0 = prof ? clock64() : 0, pw = 0;
     for (uint32_t su = blockIdx.x; su < nunits && ok; su += gridDim.x) {
       const uint32_t sys = su / itiles;
-      const uint8_t *src = p.Dx + (size_t)sys * ntiles * kUSteps * kHBlock;
-      for (uint32_t q = 0; q < ntiles * (uint32_t)kUStages && ok; q++, src += kUBStage) {
+      const uint8_t *src0 = p.Dx + (size_t)sys * ntiles * kUSteps * kHBlock;
+      for (uint32_t q = 0; q < ntiles * (uint32_t)kUStages && ok; q++) {
+        const uint8_t *src = src0 + ((size_t)update_tile_at(q / kUStages, ntiles) * kUStages + q % kUStages) * kUBStage;
         const long long w0 = prof ? clock64() : 0;
         if (!mbar_wait(b_empty(s), ph ^ 1u, p.status)) { ok = false; break; }
         if (prof) pw += clock64() - w0;
@@ -835,9 +863,10 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
     const bool prof = PROF && p.prof != nullptr;
     long long pt0 = prof ? clock64() : 0, pwa = 0, pwt = 0, pwb = 0;
     for (uint32_t su = blockIdx.x; su < nunits && ok; su += gridDim.x, unit_iter++) {
-      for (uint32_t nt = 0; nt < ntiles && ok; nt++, tile_iter++) {
+      for (uint32_t j = 0; j < ntiles && ok; j++, tile_iter++) {
+        const uint32_t nt = update_tile_at(j, ntiles);
         const uint32_t ab = tile_iter & 1u;
-        const bool first = nt == 0, last = nt + 1 == ntiles;
+        const bool first = j == 0, last = j + 1 == ntiles;
         long long w0 = prof ? clock64() : 0;
         if (!mbar_wait(tmem_empty(ab), ((tile_iter >> 1) & 1u) ^ 1u, p.status)) { ok = false; break; }
         if (prof) pwt += clock64() - w0;
@@ -848,9 +877,9 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
         const uint32_t idesc = idesc0 | ((ncur >> 3) << 17);
 #pragma unroll
         for (int cs = 0; cs < kUStages; cs++) {
-          if (first && (cs % kUHalfStages) == 0) {          // this half of the unit's A operand is built
+          if (first) {                                      // this stage's part of the unit's A operand is built
             w0 = prof ? clock64() : 0;
-            if (!mbar_wait(a_full(cs / kUHalfStages), unit_iter & 1u, p.status)) { ok = false; break; }
+            if (!mbar_wait(a_full(cs), unit_iter & 1u, p.status)) { ok = false; break; }
             if (prof) pwa += clock64() - w0;
           }
           w0 = prof ? clock64() : 0;
@@ -866,7 +895,7 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
             }
             tc_commit(b_empty(cs));
             // last column tile of the unit: everything that reads this half of A has been issued
-            if (last && (cs % kUHalfStages) == kUHalfStages - 1) tc_commit(a_empty(cs / kUHalfStages));
+            if (last) tc_commit(a_empty(cs));
           }
         }
         ph ^= 1u;
@@ -880,7 +909,7 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
       atomicAdd(p.prof + 3, (unsigned long long)(clock64() - pt0));
       atomicAdd(p.prof + 12, (unsigned long long)tile_iter);
     }
-  } else if (warp >= kBuild0) {
+  } else if (warp >= (uint32_t)kBuild0 && warp < (uint32_t)(kBuild0 + kBuilderWarps)) {
     // ------------------------------------------------------------ A builders: once per (system, row tile)
     const uint32_t b = warp - kBuild0;
     const uint32_t i = lane >> 1, q = lane & 1u;
@@ -892,25 +921,21 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
       const uint32_t sys = su / itiles, it = su - sys * itiles;
       const uint32_t row = it * kRowsI + i;
       const uint8_t *crow = p.C + (size_t)sys * p.c_ss + (size_t)row * p.c_stride + 4 * q;
-      // steps of this warp: b, b + 4 (first half), b + 8, b + 12 (second half)
-      uint32_t cw[kUSteps / kBuilderWarps];
+      // this warp builds step b of every stage's part (steps 4*s .. 4*s+3)
+      uint32_t cw[kUStages];
 #pragma unroll
-      for (int k = 0; k < kUSteps / kBuilderWarps; k++) {
-        const uint32_t step = b + k * kBuilderWarps;
+      for (int k = 0; k < kUStages; k++) {
+        const uint32_t step = k * kUSPS + b;
         cw[k] = (row < p.M && step * kStepJ + 4 * q < p.Kc) ? __ldg(reinterpret_cast<const uint32_t *>(crow + step * kStepJ)) : 0u;
       }
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
+      for (int h = 0; h < kUStages; h++) {
         const long long w0 = prof ? clock64() : 0;
         if (!mbar_wait_warp(a_empty(h), (unit_iter & 1u) ^ 1u, p.status)) { ok = false; break; }
         const long long w1 = prof ? clock64() : 0;
         if (!(p.dbg & 2)) {
-#pragma unroll
-          for (int k2 = 0; k2 < 2; k2++) {
-            const int k = h * 2 + k2;
-            const uint32_t step = b + k * kBuilderWarps;
-            build_a_step(lut, cw[k], reinterpret_cast<uint4 *>(smA + step * kATile + i * kASbo + q * kALbo));
-          }
+          const uint32_t step = h * kUSPS + b;
+          build_a_step(lut, cw[h], reinterpret_cast<uint4 *>(smA + step * kATile + i * kASbo + q * kALbo));
           fence_async_smem();
         }
         mbar_arrive(a_full(h));
@@ -923,7 +948,7 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
       atomicAdd(p.prof + 11, (unsigned long long)(clock64() - pt0));
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 0..7)
+    // ------------------------------------------------------------ epilogue (warps 6..13)
     using ET = EpiTile<kHalfN>;
     auto tile_of = [&](uint32_t su, uint32_t nt, ET &e) {
       const uint32_t sys = su / itiles, it = su - sys * itiles;
@@ -937,17 +962,17 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
     }
     uint32_t tile_iter = 0;
     bool ok = true;
-    const bool prof = PROF && p.prof != nullptr && warp == 0;
+    const bool prof = PROF && p.prof != nullptr && warp == (uint32_t)kEpi0;
     long long pt0 = prof ? clock64() : 0, pw = 0, pe = 0;
     long long pc[3] = {0, 0, 0};
     for (uint32_t su = blockIdx.x; su < nunits && ok; su += gridDim.x) {
-      for (uint32_t nt = 0; nt < ntiles; nt++, tile_iter++) {
+      for (uint32_t j = 0; j < ntiles; j++, tile_iter++) {
         cur = nxt;
 #pragma unroll
         for (int k = 0; k < ET::kC0; k++) old_cur[k] = old_nxt[k];
         // old contents of the next tile: in flight during this tile
-        if (nt + 1 < ntiles) {
-          tile_of(su, nt + 1, nxt);
+        if (j + 1 < ntiles) {
+          nxt.set_tile(update_tile_at(j + 1, ntiles));   // same (system, row)
           nxt.load_old(old_nxt, p.accumulate);
         } else if (su + gridDim.x < nunits) {
           tile_of(su + gridDim.x, 0, nxt);

@@ -332,7 +332,7 @@ int oblas_b200_solve_phases(int enable, uint64_t *out) {
   if (ensure_init()) return -1;
   if (out && g.d_phase) {
     CK(cudaStreamSynchronize(g.stream));
-    CK(cudaMemcpy(out, g.d_phase, 5 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out, g.d_phase, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   }
   if (enable) {
     if (!g.d_phase) CK(cudaMalloc(&g.d_phase, 8 * sizeof(uint64_t)));

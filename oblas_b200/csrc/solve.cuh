@@ -85,6 +85,9 @@ struct SolveSmem {
   using G = Geo<NBW, KB, WT>;
   static constexpr int NB = 32 * NBW;          // panel width in bits
   static constexpr int NPIV = NB / EXP;        // max pivots per panel
+  // the fast panel factorisation borrows the table area: Mb + 8 copies of its 4-bit tables
+  static constexpr int T2C = (G::TAB_BYTES >= (size_t)NB * NBW * 4 + (size_t)(NB / 4) * 16 * 8 * NBW * 4) ? 8 : 4;
+  static_assert(G::TAB_BYTES >= (size_t)NB * NBW * 4 + (size_t)(NB / 4) * 16 * T2C * NBW * 4, "scratch of panel_fast");
   static size_t bytes(uint32_t rows) {
     size_t s = 0;
     s += G::TAB_BYTES;                         // tables
@@ -93,7 +96,7 @@ struct SolveSmem {
     s += ((size_t)rows * 2 + 15) / 16 * 16;    // pos2phys (u16)
     s += (size_t)NPIV * 2 + 16;                // piv_phys (u16)
     s += (size_t)2 * EXP * NBW * 4 + 16;       // prow / vrow basis
-    s += 64;                                   // scalars
+    s += 128 + 256;                            // scalars + inverse table of the field
     return (s + 15) / 16 * 16;
   }
 };
@@ -324,6 +327,18 @@ OB2_D void permute_rows(uint8_t *base, size_t rs, uint32_t rows, uint32_t nbytes
   }
 }
 
+OB2_D uint32_t warp_min(uint32_t v) {
+#ifdef OB2_EMU
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint32_t other = __shfl_xor_sync(0xffffffffu, v, o);
+    v = other < v ? other : v;
+  }
+  return v;
+#else
+  return __reduce_min_sync(0xffffffffu, v);
+#endif
+}
+
 // select word `wi` (run-time) of a register-resident panel vector without dynamic indexing
 template <int NBW>
 OB2_D uint32_t pick_word(const PanelVec<NBW> &v, uint32_t wi) {
@@ -345,11 +360,19 @@ OB2_D uint32_t pick_word(const PanelVec<NBW> &v, uint32_t wi) {
 // changes nothing but scratch) if some column has no pivot among the candidates;
 // the caller then runs the general column-by-column path.
 // ---------------------------------------------------------------------------
-template <int EXP, int NBW>
+template <int EXP, int NBW, int T2C = 8>
 OB2_D bool panel_fast(uint32_t *pan, uint32_t *V, uint16_t *pos2phys, uint16_t *piv_phys,
                       uint32_t *prow, uint32_t *vrow, uint32_t *scal, uint32_t *scratch,
                       uint32_t t, uint32_t rows, uint32_t c0, uint32_t *pivcols_sys,
-                      const uint8_t *inv_tab) {
+                      const uint8_t *inv_tab, unsigned long long *pf = nullptr) {
+  // pf (diagnostics, thread 0 only, may be null): cycles in 0 = candidate elimination, 1 = tables
+  // of M, 2 = V = pan * M
+#ifndef OB2_EMU
+  long long pf_t = pf ? clock64() : 0;
+#define OB2_PF_TICK(k) do { if (pf) { long long n_ = clock64(); pf[k] += (unsigned long long)(n_ - pf_t); pf_t = n_; } } while (0)
+#else
+#define OB2_PF_TICK(k) do { } while (0)
+#endif
   constexpr int NB = 32 * NBW, NPIV = NB / EXP;
   constexpr uint32_t EMASK = (1u << EXP) - 1u;
   constexpr uint32_t NBT = (uint32_t)((NPIV + 32 + 31) / 32 * 32);  // threads in the candidate group
@@ -357,12 +380,14 @@ OB2_D bool panel_fast(uint32_t *pan, uint32_t *V, uint16_t *pos2phys, uint16_t *
   const uint32_t tid = threadIdx.x, T = blockDim.x;
   const uint32_t ncand = (rows - t < NBT) ? (rows - t) : NBT;      // candidate rows
   uint32_t *Mb = scratch;                       // [NB][NBW]  x^b * (vector of the pivot of column m/EXP)
-  uint32_t *T2 = scratch + NB * NBW;            // [NB/4][16][NBW]
-  if (tid == 0) {
-    scal[0] = NONE;  // search slots, alternating per column
-    scal[1] = NONE;
-    scal[2] = 0;     // fail flag
-  }
+  // [NB/4][16][8 copies][NBW]: lane l reads copy l % 8, so the 8 lanes of a 128-bit shared-memory
+  // phase always hit 8 different 16-byte bank groups whatever their table indices are (random
+  // indices into ONE copy conflict ~2.5-way, and this product is 1/3 of the factorisation time)
+  // (T2C = 4 where the table area is too small for 8 copies: lanes l and l + 4 then share a copy)
+  uint32_t *T2 = scratch + NB * NBW;
+  static_assert(T2C == 8 || T2C == 4, "copies of the 4-bit tables");
+  static_assert(NBT / 32 <= 8, "per-warp search slots: scal[16..32), alternating per column");
+  if (tid == 0) scal[2] = 0;     // fail flag
   __syncthreads();
   const bool have = tid < ncand && tid < NBT;
   uint32_t phys = 0;
@@ -380,9 +405,15 @@ OB2_D bool panel_fast(uint32_t *pan, uint32_t *V, uint16_t *pos2phys, uint16_t *
     for (uint32_t j = 0; j < (uint32_t)NPIV; j++) {
       const uint32_t wj = (j * EXP) >> 5, sh = (j * EXP) & 31;
       const uint32_t e = (pick_word<NBW>(blk, wj) >> sh) & EMASK;
-      if (have && mypos >= j && e) atomicMin(&scal[j & 1], mypos);
+      // lowest candidate position with a non-zero entry: one warp reduction + one word per warp
+      // (48 threads doing atomicMin on one shared word serialise)
+      const uint32_t wmin = warp_min((have && mypos >= j && e) ? mypos : NONE);
+      uint32_t *slots = scal + 16 + (j & 1) * 8;
+      if ((tid & 31u) == 0) slots[tid >> 5] = wmin;
       OB2_NAMED_BAR(1, NBT);
-      const uint32_t pv = scal[j & 1];
+      uint32_t pv = NONE;
+#pragma unroll
+      for (uint32_t k = 0; k < NBT / 32; k++) pv = slots[k] < pv ? slots[k] : pv;
       if (pv == NONE) {  // no pivot among the candidates (uniform over the group)
         failed = true;
         break;
@@ -394,25 +425,31 @@ OB2_D bool panel_fast(uint32_t *pan, uint32_t *V, uint16_t *pos2phys, uint16_t *
       }
       if (is_piv) {
         my_col = (int)j;
-        const uint32_t inv = (EXP == 1) ? 1u : (uint32_t)__ldg(inv_tab + e);
-        // content = inv*(own old row) ^ inv*E*P_old : the own base moves into slot j
+        // content = inv*(own old row) ^ inv*E*P_old : the own base moves into slot j.  The pivot
+        // thread only publishes its raw row; the scaling by inv * x^q (EXP multiples of 2*NBW
+        // words) is spread over the threads of the group instead of one thread's serial chain.
 #pragma unroll
         for (int w = 0; w < NBW; w++) {
           uint32_t unit = (((j * EXP) >> 5) == (uint32_t)w) ? (1u << ((j * EXP) & 31)) : 0u;
-          blk.w[w] = mul_scalar_word<EXP>(blk.w[w], inv);
-          E.w[w] = mul_scalar_word<EXP>(E.w[w] ^ unit, inv);
-          uint32_t a = blk.w[w], b = E.w[w];
-#pragma unroll
-          for (int q = 0; q < EXP; q++) {
-            prow[q * NBW + w] = a;
-            vrow[q * NBW + w] = b;
-            a = xtime<EXP>(a);
-            b = xtime<EXP>(b);
-          }
+          scal[4 + w] = blk.w[w];
+          scal[4 + NBW + w] = E.w[w] ^ unit;
         }
-        scal[(j + 1) & 1] = NONE;  // re-arm the slot of the next column
+        scal[3] = (EXP == 1) ? 1u : (uint32_t)inv_tab[e];   // shared-memory copy of the table
       }
       OB2_NAMED_BAR(1, NBT);
+      if (tid < (uint32_t)(EXP * 2 * NBW)) {
+        const uint32_t q = tid / (2 * NBW), w2 = tid % (2 * NBW);
+        uint32_t sq = scal[3];                    // inv * x^q
+        for (uint32_t k = 0; k < q; k++) sq = xtime<EXP>(sq) & EMASK;
+        const uint32_t val = mul_scalar_word<EXP>(scal[4 + w2], sq);
+        if (w2 < (uint32_t)NBW) prow[q * NBW + w2] = val;
+        else vrow[q * NBW + (w2 - NBW)] = val;
+      }
+      OB2_NAMED_BAR(1, NBT);
+      if (is_piv) {
+        blk = ldv<NBW>(prow);
+        E = ldv<NBW>(vrow);
+      }
       if (have && !is_piv) {
         const uint32_t f = (pick_word<NBW>(blk, wj) >> sh) & EMASK;
         if (f) {
@@ -447,6 +484,7 @@ OB2_D bool panel_fast(uint32_t *pan, uint32_t *V, uint16_t *pos2phys, uint16_t *
     }
   }
   __syncthreads();                        // fail flag, Mb, row map visible
+  OB2_PF_TICK(0);
   if (scal[2]) return false;
   // 4-bit Four-Russians tables of the bit matrix M
   for (uint32_t it = tid; it < (uint32_t)(NB / 4) * 16; it += T) {
@@ -461,10 +499,14 @@ OB2_D bool panel_fast(uint32_t *pan, uint32_t *V, uint16_t *pos2phys, uint16_t *
 #pragma unroll
         for (int w = 0; w < NBW; w++) acc.w[w] ^= b.w[w];
       }
-    stv<NBW>(T2 + it * NBW, acc);
+#pragma unroll
+    for (int c = 0; c < T2C; c++)   // copy order rotated by lane: the 8 lanes of a phase store to 8 bank groups
+      stv<NBW>(T2 + (it * T2C + ((c + tid) & (T2C - 1))) * NBW, acc);
   }
   __syncthreads();
+  OB2_PF_TICK(1);
   // V[r] = pan[r] * M for every row
+  const uint32_t *T2l = T2 + (tid & (T2C - 1)) * NBW;
   for (uint32_t r = tid; r < rows; r += T) {
     PanelVec<NBW> pr = ldv<NBW>(pan + r * NBW), acc;
 #pragma unroll
@@ -472,7 +514,7 @@ OB2_D bool panel_fast(uint32_t *pan, uint32_t *V, uint16_t *pos2phys, uint16_t *
 #pragma unroll
     for (int g = 0; g < NB / 4; g++) {
       uint32_t nib = (pr.w[g >> 3] >> (4 * (g & 7))) & 15u;
-      PanelVec<NBW> tv = ldv<NBW>(T2 + (g * 16 + nib) * NBW);
+      PanelVec<NBW> tv = ldv<NBW>(T2l + (g * 16 + nib) * (T2C * NBW));
 #pragma unroll
       for (int w = 0; w < NBW; w++) acc.w[w] ^= tv.w[w];
     }
@@ -488,6 +530,8 @@ OB2_D bool panel_fast(uint32_t *pan, uint32_t *V, uint16_t *pos2phys, uint16_t *
     }
   }
   __syncthreads();
+  OB2_PF_TICK(2);
+#undef OB2_PF_TICK
   return true;
 }
 
@@ -511,6 +555,10 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
   uint32_t *prow = reinterpret_cast<uint32_t *>(sp);       sp += (size_t)EXP * NBW * 4;   // x^b * pivot row (panel part)
   uint32_t *vrow = reinterpret_cast<uint32_t *>(sp);       sp += (size_t)EXP * NBW * 4;   // x^b * its V
   uint32_t *scal = reinterpret_cast<uint32_t *>(sp);       // [0] search result, [1] flag
+  uint8_t *inv_s = reinterpret_cast<uint8_t *>(scal + 32);  // field inverses (a global load per pivot is 1/3 of a column step)
+  if (EXP > 1)
+    for (uint32_t k = threadIdx.x; k < (1u << EXP); k += blockDim.x) inv_s[k] = p.inv[k];
+  __syncthreads();
 
   // phase clock (diagnostics only): 0 panel load, 1 panel factorisation, 2 trailing update,
   // 3 final permutation / bookkeeping
@@ -560,9 +608,9 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
       constexpr uint32_t kFastThreads = (uint32_t)((NPIV + 32 + 31) / 32 * 32);
       bool fast = false;
       if (ncols_p == (uint32_t)NPIV && rows - t >= (uint32_t)NPIV && kFastThreads <= T && !p.no_fast_panel)
-        fast = panel_fast<EXP, NBW>(pan, V, pos2phys, piv_phys, prow, vrow, scal,
+        fast = panel_fast<EXP, NBW, SM::T2C>(pan, V, pos2phys, piv_phys, prow, vrow, scal,
                                     reinterpret_cast<uint32_t *>(tab), t, rows, c0,
-                                    p.pivcols ? p.pivcols + (size_t)sys * rows : nullptr, p.inv);
+                                    p.pivcols ? p.pivcols + (size_t)sys * rows : nullptr, inv_s);
       if (fast) {
         n = NPIV;
         t += NPIV;
@@ -606,7 +654,7 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
         }
         // normalise the pivot row (panel part and V part); V gets the unit term
         // of the row's own base: content = inv*old + inv*V*P  =>  V' = inv*V ^ inv*e_n
-        const uint32_t inv = (EXP == 1) ? 1u : (uint32_t)__ldg(p.inv + e);
+        const uint32_t inv = (EXP == 1) ? 1u : (uint32_t)inv_s[e];
         if (tid < (uint32_t)NBW) {
           uint32_t w = mul_scalar_word<EXP>(pan[ph * NBW + tid], inv);
           uint32_t v = mul_scalar_word<EXP>(V[ph * NBW + tid], inv);
@@ -756,11 +804,15 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
   uint32_t *prow = reinterpret_cast<uint32_t *>(sp);       sp += (size_t)EXP * NBW * 4;
   uint32_t *vrow = reinterpret_cast<uint32_t *>(sp);       sp += (size_t)EXP * NBW * 4;
   uint32_t *scal = reinterpret_cast<uint32_t *>(sp);
+  uint8_t *inv_s = reinterpret_cast<uint8_t *>(scal + 32);
+  for (uint32_t k = threadIdx.x; k < 256u; k += blockDim.x) inv_s[k] = p.inv[k];
+  __syncthreads();
 
   // phase clock (diagnostics only): 0 panel load + clear, 1 factorisation, 2 unit injection and
   // direct E columns, 3 tile pass(es), 4 per-system prologue / epilogue
   long long t_last = 0;
   unsigned long long acc_phase[5] = {0, 0, 0, 0, 0};
+  unsigned long long acc_pf[3] = {0, 0, 0};   // inside the fast factorisation: candidates, tables, V product
   auto tick = [&](int ph) {
 #ifndef OB2_EMU
     if (p.phase && tid == 0) {
@@ -810,9 +862,10 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
       constexpr uint32_t kFastThreads = (uint32_t)((NPIV + 32 + 31) / 32 * 32);
       bool fast = false;
       if (ncols_p == (uint32_t)NPIV && rows - t >= (uint32_t)NPIV && kFastThreads <= T && !p.no_fast_panel)
-        fast = panel_fast<EXP, NBW>(pan, V, pos2phys, piv_phys, prow, vrow, scal,
+        fast = panel_fast<EXP, NBW, SM::T2C>(pan, V, pos2phys, piv_phys, prow, vrow, scal,
                                     reinterpret_cast<uint32_t *>(tab), t, rows, c0,
-                                    p.pivcols ? p.pivcols + (size_t)sys * rows : nullptr, p.inv);
+                                    p.pivcols ? p.pivcols + (size_t)sys * rows : nullptr, inv_s,
+                                    (p.phase && tid == 0) ? acc_pf : nullptr);
       if (fast) {
         n = NPIV;
         t += NPIV;
@@ -855,7 +908,7 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
           piv_phys[n] = (uint16_t)ph;
           if (p.pivcols) p.pivcols[(size_t)sys * rows + t] = c0 + j;
         }
-        const uint32_t inv = (uint32_t)__ldg(p.inv + e);
+        const uint32_t inv = (uint32_t)inv_s[e];
         if (tid < (uint32_t)NBW) {
           uint32_t w = mul_scalar_word<EXP>(pan[ph * NBW + tid], inv);
           uint32_t v = mul_scalar_word<EXP>(V[ph * NBW + tid], inv);
@@ -947,8 +1000,10 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
     tick(4);
   }
 #ifndef OB2_EMU
-  if (p.phase && tid == 0)
+  if (p.phase && tid == 0) {
     for (int k2 = 0; k2 < 5; k2++) atomicAdd(p.phase + k2, acc_phase[k2]);
+    for (int k2 = 0; k2 < 3; k2++) atomicAdd(p.phase + 5 + k2, acc_pf[k2]);
+  }
 #endif
 }
 
@@ -962,6 +1017,8 @@ inline int launch_panel_t(const PanelArgs &p, uint32_t grid, size_t smem_limit, 
   auto k = panel_kernel<KB, WT>;
 #ifndef OB2_EMU
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
+  // two CTAs per SM where they fit (small table geometry): ask for the largest shared-memory carve-out
+  if (cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared) != cudaSuccess) return -2;
 #endif
   OB2_LAUNCH(k, grid, threads, smem, s, p);
   return 0;

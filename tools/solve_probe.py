@@ -32,6 +32,7 @@ device.solve_batch(capi.GF256, A, K, B)
 torch.cuda.synchronize()
 lib.oblas_b200_solve_phases(0, ph.ctypes.data)
 tot = float(ph[:5].sum()) or 1.0
+print("inside factorisation (M clk per system): candidates %.3f, tables %.3f, V product %.3f" % tuple(float(x) / nsys / 1e6 for x in ph[5:8]))
 print("phase cycles per system (M clk): " + ", ".join("%.3f" % (float(x) / nsys / 1e6) for x in ph[:5]) +
       "  shares: " + ", ".join("%.1f%%" % (100 * float(x) / tot) for x in ph[:5]))
 print("solve geo=%d nsys=%d K=%d L=%d: %.2f ms, %.0f solves/s, full rank %d" % (geo, nsys, K, L, ms, nsys / ms * 1e3, int((r == K).sum())))
