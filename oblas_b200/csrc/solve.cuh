@@ -360,132 +360,149 @@ OB2_D uint32_t pick_word(const PanelVec<NBW> &v, uint32_t wi) {
 // changes nothing but scratch) if some column has no pivot among the candidates;
 // the caller then runs the general column-by-column path.
 // ---------------------------------------------------------------------------
-template <int EXP, int NBW, int T2C = 8>
-OB2_D bool panel_fast(uint32_t *pan, uint32_t *V, uint16_t *pos2phys, uint16_t *piv_phys,
-                      uint32_t *prow, uint32_t *vrow, uint32_t *scal, uint32_t *scratch,
-                      uint32_t t, uint32_t rows, uint32_t c0, uint32_t *pivcols_sys,
-                      const uint8_t *inv_tab, unsigned long long *pf = nullptr) {
-  // pf (diagnostics, thread 0 only, may be null): cycles in 0 = candidate elimination, 1 = tables
-  // of M, 2 = V = pan * M
-#ifndef OB2_EMU
-  long long pf_t = pf ? clock64() : 0;
-#define OB2_PF_TICK(k) do { if (pf) { long long n_ = clock64(); pf[k] += (unsigned long long)(n_ - pf_t); pf_t = n_; } } while (0)
-#else
-#define OB2_PF_TICK(k) do { } while (0)
-#endif
-  constexpr int NB = 32 * NBW, NPIV = NB / EXP;
+// what a thread of the candidate group keeps from the candidate elimination for the finish
+template <int NBW>
+struct FastCand {
+  int my_col = -1;       // column this thread's row became the pivot of
+  uint32_t phys = 0;     // its physical row
+  PanelVec<NBW> E;       // its coefficient vector
+};
+
+// threads in the candidate group of the fast factorisation
+template <int EXP, int NBW>
+struct FastGeo {
+  static constexpr int NB = 32 * NBW, NPIV = NB / EXP;
+  static constexpr uint32_t NBT = (uint32_t)((NPIV + 32 + 31) / 32 * 32);
+};
+
+// Part 1, threads tid < NBT only (they synchronise among themselves on named barrier 1): eliminate
+// the candidate rows in registers.  On success the row map, piv_phys, the pivot columns and Mb
+// ([NB][NBW]: x^b * vector of the pivot of column m/EXP) are written; on failure only scal[2] = 1.
+// The caller clears scal[2] before and makes the results visible with a block barrier after.
+template <int EXP, int NBW>
+OB2_D void panel_fast_candidates(const uint32_t *pan, uint16_t *pos2phys, uint16_t *piv_phys, uint32_t *prow,
+                                 uint32_t *vrow, uint32_t *scal, uint32_t *Mb, uint32_t t, uint32_t rows,
+                                 uint32_t c0, uint32_t *pivcols_sys, const uint8_t *inv_tab, FastCand<NBW> &fc) {
+  constexpr int NPIV = FastGeo<EXP, NBW>::NPIV;
   constexpr uint32_t EMASK = (1u << EXP) - 1u;
-  constexpr uint32_t NBT = (uint32_t)((NPIV + 32 + 31) / 32 * 32);  // threads in the candidate group
+  constexpr uint32_t NBT = FastGeo<EXP, NBW>::NBT;
   constexpr uint32_t NONE = 0xffffffffu;
-  const uint32_t tid = threadIdx.x, T = blockDim.x;
-  const uint32_t ncand = (rows - t < NBT) ? (rows - t) : NBT;      // candidate rows
-  uint32_t *Mb = scratch;                       // [NB][NBW]  x^b * (vector of the pivot of column m/EXP)
-  // [NB/4][16][8 copies][NBW]: lane l reads copy l % 8, so the 8 lanes of a 128-bit shared-memory
-  // phase always hit 8 different 16-byte bank groups whatever their table indices are (random
-  // indices into ONE copy conflict ~2.5-way, and this product is 1/3 of the factorisation time)
-  // (T2C = 4 where the table area is too small for 8 copies: lanes l and l + 4 then share a copy)
-  uint32_t *T2 = scratch + NB * NBW;
-  static_assert(T2C == 8 || T2C == 4, "copies of the 4-bit tables");
   static_assert(NBT / 32 <= 8, "per-warp search slots: scal[16..32), alternating per column");
-  if (tid == 0) scal[2] = 0;     // fail flag
-  __syncthreads();
-  const bool have = tid < ncand && tid < NBT;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t ncand = (rows - t < NBT) ? (rows - t) : NBT;      // candidate rows
+  const bool have = tid < ncand;
   uint32_t phys = 0;
   int my_col = -1;  // column this row became the pivot of
   PanelVec<NBW> E;
 #pragma unroll
   for (int w = 0; w < NBW; w++) E.w[w] = 0;
-  if (tid < NBT) {
-    uint32_t mypos = tid;  // position offset inside the candidate set
-    phys = have ? pos2phys[t + tid] : 0;
-    PanelVec<NBW> blk;
+  uint32_t mypos = tid;  // position offset inside the candidate set
+  phys = have ? pos2phys[t + tid] : 0;
+  PanelVec<NBW> blk;
 #pragma unroll
-    for (int w = 0; w < NBW; w++) blk.w[w] = have ? pan[phys * NBW + w] : 0;
-    bool failed = false;
-    for (uint32_t j = 0; j < (uint32_t)NPIV; j++) {
-      const uint32_t wj = (j * EXP) >> 5, sh = (j * EXP) & 31;
-      const uint32_t e = (pick_word<NBW>(blk, wj) >> sh) & EMASK;
-      // lowest candidate position with a non-zero entry: one warp reduction + one word per warp
-      // (48 threads doing atomicMin on one shared word serialise)
-      const uint32_t wmin = warp_min((have && mypos >= j && e) ? mypos : NONE);
-      uint32_t *slots = scal + 16 + (j & 1) * 8;
-      if ((tid & 31u) == 0) slots[tid >> 5] = wmin;
-      OB2_NAMED_BAR(1, NBT);
-      uint32_t pv = NONE;
+  for (int w = 0; w < NBW; w++) blk.w[w] = have ? pan[phys * NBW + w] : 0;
+  bool failed = false;
+  for (uint32_t j = 0; j < (uint32_t)NPIV; j++) {
+    const uint32_t wj = (j * EXP) >> 5, sh = (j * EXP) & 31;
+    const uint32_t e = (pick_word<NBW>(blk, wj) >> sh) & EMASK;
+    // lowest candidate position with a non-zero entry: one warp reduction + one word per warp
+    // (48 threads doing atomicMin on one shared word serialise)
+    const uint32_t wmin = warp_min((have && mypos >= j && e) ? mypos : NONE);
+    uint32_t *slots = scal + 16 + (j & 1) * 8;
+    if ((tid & 31u) == 0) slots[tid >> 5] = wmin;
+    OB2_NAMED_BAR(1, NBT);
+    uint32_t pv = NONE;
 #pragma unroll
-      for (uint32_t k = 0; k < NBT / 32; k++) pv = slots[k] < pv ? slots[k] : pv;
-      if (pv == NONE) {  // no pivot among the candidates (uniform over the group)
-        failed = true;
-        break;
-      }
-      const bool is_piv = have && mypos == pv;
-      if (have) {
-        if (is_piv) mypos = j;
-        else if (mypos == j) mypos = pv;
-      }
-      if (is_piv) {
-        my_col = (int)j;
-        // content = inv*(own old row) ^ inv*E*P_old : the own base moves into slot j.  The pivot
-        // thread only publishes its raw row; the scaling by inv * x^q (EXP multiples of 2*NBW
-        // words) is spread over the threads of the group instead of one thread's serial chain.
+    for (uint32_t k = 0; k < NBT / 32; k++) pv = slots[k] < pv ? slots[k] : pv;
+    if (pv == NONE) {  // no pivot among the candidates (uniform over the group)
+      failed = true;
+      break;
+    }
+    const bool is_piv = have && mypos == pv;
+    if (have) {
+      if (is_piv) mypos = j;
+      else if (mypos == j) mypos = pv;
+    }
+    if (is_piv) {
+      my_col = (int)j;
+      // content = inv*(own old row) ^ inv*E*P_old : the own base moves into slot j.  The pivot
+      // thread only publishes its raw row; the scaling by inv * x^q (EXP multiples of 2*NBW
+      // words) is spread over the threads of the group instead of one thread's serial chain.
 #pragma unroll
-        for (int w = 0; w < NBW; w++) {
-          uint32_t unit = (((j * EXP) >> 5) == (uint32_t)w) ? (1u << ((j * EXP) & 31)) : 0u;
-          scal[4 + w] = blk.w[w];
-          scal[4 + NBW + w] = E.w[w] ^ unit;
-        }
-        scal[3] = (EXP == 1) ? 1u : (uint32_t)inv_tab[e];   // shared-memory copy of the table
+      for (int w = 0; w < NBW; w++) {
+        uint32_t unit = (((j * EXP) >> 5) == (uint32_t)w) ? (1u << ((j * EXP) & 31)) : 0u;
+        scal[4 + w] = blk.w[w];
+        scal[4 + NBW + w] = E.w[w] ^ unit;
       }
-      OB2_NAMED_BAR(1, NBT);
-      if (tid < (uint32_t)(EXP * 2 * NBW)) {
-        const uint32_t q = tid / (2 * NBW), w2 = tid % (2 * NBW);
-        uint32_t sq = scal[3];                    // inv * x^q
-        for (uint32_t k = 0; k < q; k++) sq = xtime<EXP>(sq) & EMASK;
-        const uint32_t val = mul_scalar_word<EXP>(scal[4 + w2], sq);
-        if (w2 < (uint32_t)NBW) prow[q * NBW + w2] = val;
-        else vrow[q * NBW + (w2 - NBW)] = val;
-      }
-      OB2_NAMED_BAR(1, NBT);
-      if (is_piv) {
-        blk = ldv<NBW>(prow);
-        E = ldv<NBW>(vrow);
-      }
-      if (have && !is_piv) {
-        const uint32_t f = (pick_word<NBW>(blk, wj) >> sh) & EMASK;
-        if (f) {
+      scal[3] = (EXP == 1) ? 1u : (uint32_t)inv_tab[e];   // shared-memory copy of the table
+    }
+    OB2_NAMED_BAR(1, NBT);
+    if (tid < (uint32_t)(EXP * 2 * NBW)) {
+      const uint32_t q = tid / (2 * NBW), w2 = tid % (2 * NBW);
+      uint32_t sq = scal[3];                    // inv * x^q
+      for (uint32_t k = 0; k < q; k++) sq = xtime<EXP>(sq) & EMASK;
+      const uint32_t val = mul_scalar_word<EXP>(scal[4 + w2], sq);
+      if (w2 < (uint32_t)NBW) prow[q * NBW + w2] = val;
+      else vrow[q * NBW + (w2 - NBW)] = val;
+    }
+    OB2_NAMED_BAR(1, NBT);
+    if (is_piv) {
+      blk = ldv<NBW>(prow);
+      E = ldv<NBW>(vrow);
+    }
+    if (have && !is_piv) {
+      const uint32_t f = (pick_word<NBW>(blk, wj) >> sh) & EMASK;
+      if (f) {
 #pragma unroll
-          for (int q = 0; q < EXP; q++) {
-            uint32_t m = 0u - ((f >> q) & 1u);
-            PanelVec<NBW> pb = ldv<NBW>(prow + q * NBW), vb = ldv<NBW>(vrow + q * NBW);
+        for (int q = 0; q < EXP; q++) {
+          uint32_t m = 0u - ((f >> q) & 1u);
+          PanelVec<NBW> pb = ldv<NBW>(prow + q * NBW), vb = ldv<NBW>(vrow + q * NBW);
 #pragma unroll
-            for (int w = 0; w < NBW; w++) {
-              blk.w[w] ^= m & pb.w[w];
-              E.w[w] ^= m & vb.w[w];
-            }
+          for (int w = 0; w < NBW; w++) {
+            blk.w[w] ^= m & pb.w[w];
+            E.w[w] ^= m & vb.w[w];
           }
         }
       }
     }
-    if (failed) {
-      if (tid == 0) scal[2] = 1;
-    } else if (have) {
-      pos2phys[t + mypos] = (uint16_t)phys;  // row map: the candidate window is permuted
-      if (my_col >= 0) {
-        piv_phys[my_col] = (uint16_t)phys;
-        if (pivcols_sys) pivcols_sys[t + my_col] = c0 + (uint32_t)my_col;
-        PanelVec<NBW> x = E;
+  }
+  if (failed) {
+    if (tid == 0) scal[2] = 1;
+  } else if (have) {
+    pos2phys[t + mypos] = (uint16_t)phys;  // row map: the candidate window is permuted
+    if (my_col >= 0) {
+      piv_phys[my_col] = (uint16_t)phys;
+      if (pivcols_sys) pivcols_sys[t + my_col] = c0 + (uint32_t)my_col;
+      PanelVec<NBW> x = E;
 #pragma unroll
-        for (int q = 0; q < EXP; q++) {
-          stv<NBW>(Mb + ((uint32_t)my_col * EXP + q) * NBW, x);
+      for (int q = 0; q < EXP; q++) {
+        stv<NBW>(Mb + ((uint32_t)my_col * EXP + q) * NBW, x);
 #pragma unroll
-          for (int w = 0; w < NBW; w++) x.w[w] = xtime<EXP>(x.w[w]);
-        }
+        for (int w = 0; w < NBW; w++) x.w[w] = xtime<EXP>(x.w[w]);
       }
     }
   }
-  __syncthreads();                        // fail flag, Mb, row map visible
-  OB2_PF_TICK(0);
-  if (scal[2]) return false;
+  fc.my_col = my_col;
+  fc.phys = phys;
+  fc.E = E;
+}
+
+// Part 2, all threads, after a block barrier: V of every row from the pivots' vectors (Mb).
+// T2: [NB/4][16][T2C copies][NBW] -- lane l reads copy l % T2C, so the 8 lanes of a 128-bit
+// shared-memory phase always hit 8 different 16-byte bank groups whatever their table indices are
+// (random indices into ONE copy conflict ~2.5-way).  T2C = 4 where the table area is too small for
+// 8 copies: lanes l and l + 4 then share a copy.  fc: valid on the threads of the candidate group.
+template <int EXP, int NBW, int T2C>
+OB2_D void panel_fast_finish(const uint32_t *pan, uint32_t *V, uint32_t *T2, const uint32_t *Mb,
+                             const FastCand<NBW> &fc, uint32_t rows, unsigned long long *pf, long long &pf_t) {
+  constexpr int NB = 32 * NBW;
+  static_assert(T2C == 8 || T2C == 4, "copies of the 4-bit tables");
+  const uint32_t tid = threadIdx.x, T = blockDim.x;
+#ifndef OB2_EMU
+#define OB2_PF_TICK(k) do { if (pf) { long long n_ = clock64(); pf[k] += (unsigned long long)(n_ - pf_t); pf_t = n_; } } while (0)
+#else
+#define OB2_PF_TICK(k) do { } while (0)
+#endif
   // 4-bit Four-Russians tables of the bit matrix M
   for (uint32_t it = tid; it < (uint32_t)(NB / 4) * 16; it += T) {
     uint32_t g = it >> 4, v = it & 15;
@@ -522,16 +539,45 @@ OB2_D bool panel_fast(uint32_t *pan, uint32_t *V, uint16_t *pos2phys, uint16_t *
   }
   __syncthreads();
   // pivot rows: new content = E * P_old, so cancel the own base term: V = E ^ e_col
-  if (my_col >= 0) {
+  if (tid < FastGeo<EXP, NBW>::NBT && fc.my_col >= 0) {
 #pragma unroll
     for (int w = 0; w < NBW; w++) {
-      uint32_t unit = ((((uint32_t)my_col * EXP) >> 5) == (uint32_t)w) ? (1u << (((uint32_t)my_col * EXP) & 31)) : 0u;
-      V[phys * NBW + w] = E.w[w] ^ unit;
+      uint32_t unit = ((((uint32_t)fc.my_col * EXP) >> 5) == (uint32_t)w) ? (1u << (((uint32_t)fc.my_col * EXP) & 31)) : 0u;
+      V[fc.phys * NBW + w] = fc.E.w[w] ^ unit;
     }
   }
   __syncthreads();
   OB2_PF_TICK(2);
 #undef OB2_PF_TICK
+}
+
+// Both parts back to back (the other warps wait while the candidate group works).  Returns false
+// (and changes nothing but scratch) if some column has no pivot among the candidates; the caller
+// then runs the general column-by-column path.  scratch: Mb, then T2.
+template <int EXP, int NBW, int T2C = 8>
+OB2_D bool panel_fast(uint32_t *pan, uint32_t *V, uint16_t *pos2phys, uint16_t *piv_phys,
+                      uint32_t *prow, uint32_t *vrow, uint32_t *scal, uint32_t *scratch,
+                      uint32_t t, uint32_t rows, uint32_t c0, uint32_t *pivcols_sys,
+                      const uint8_t *inv_tab, unsigned long long *pf = nullptr) {
+  // pf (diagnostics, thread 0 only, may be null): cycles in 0 = candidate elimination, 1 = tables
+  // of M, 2 = V = pan * M
+  constexpr int NB = 32 * NBW;
+  long long pf_t = 0;
+#ifndef OB2_EMU
+  if (pf) pf_t = clock64();
+#endif
+  uint32_t *Mb = scratch, *T2 = scratch + NB * NBW;
+  if (threadIdx.x == 0) scal[2] = 0;     // fail flag
+  __syncthreads();
+  FastCand<NBW> fc;
+  if (threadIdx.x < FastGeo<EXP, NBW>::NBT)
+    panel_fast_candidates<EXP, NBW>(pan, pos2phys, piv_phys, prow, vrow, scal, Mb, t, rows, c0, pivcols_sys, inv_tab, fc);
+  __syncthreads();                        // fail flag, Mb, row map visible
+#ifndef OB2_EMU
+  if (pf) { long long n_ = clock64(); pf[0] += (unsigned long long)(n_ - pf_t); pf_t = n_; }
+#endif
+  if (scal[2]) return false;
+  panel_fast_finish<EXP, NBW, T2C>(pan, V, T2, Mb, fc, rows, pf, pf_t);
   return true;
 }
 

@@ -186,6 +186,10 @@ def test_rows_beyond_shared_memory_fail_loudly():
     (700, 650, 400, 2, 2),        # tall, cols not a multiple of 128, rank deficient
     (520, 900, 0, 2, 0),          # wide, no right-hand side
     (1024, 1024, 1280, 2, 1),     # cfg2 shape, one deficient system
+    (640, 640, 16, 2, 0),         # column tiles straddle A|B, last tile 48 / 16 columns wide (narrow MMA)
+    (768, 768, 224, 2, 1),        # A|B boundary inside a tile in every outer panel; 3 tiles in the last panels
+    (512, 512, 2400, 2, 0),       # B much wider than A: 10+ tiles per unit, exact multiple of the tile width
+    (530, 530, 240, 1, 0),        # rows not a multiple of 16 (partial last row tile), single-tile last panel
 ])
 def test_tensor_core_path_equals_table_kernel_at_mid_sizes(rows, cols, b_bytes, nsys, deficient, cuda_lib):
     """the two elimination paths must leave identical bytes, ranks and pivot columns (the table
