@@ -85,8 +85,9 @@ void oblas_b200_set_async(int async);
  * Kc >= 64, nbytes >= 480; solve: GF(256), rows >= 512, cols >= 256, strided batches) and the
  * shared-memory table kernels otherwise. */
 void oblas_b200_set_tuning(int solve_geo, int apply_geo);
-/* diagnostics/tests: general_only != 0 disables the register-resident fast panel
- * factorisation (identical results, slower) */
+/* diagnostics/tests (identical results, slower): bit 0 disables the register-resident fast panel
+ * factorisation, bit 1 the look-ahead of the outer-panel kernel (candidate elimination of the next
+ * 16-column step overlapped with the current step's tile pass) */
 void oblas_b200_set_panel_path(int general_only);
 /* diagnostics: enable != 0 starts per-phase cycle counters of the elimination kernels (SM cycles
  * of thread 0 summed over CTAs); out (8 entries, may be NULL) receives the counters collected so far

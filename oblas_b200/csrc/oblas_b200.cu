@@ -319,7 +319,7 @@ int oblas_b200_sync(void) {
   return tc_check_status();
 }
 void oblas_b200_set_async(int async) { g.async = async != 0; }
-void oblas_b200_set_panel_path(int general_only) { g.no_fast_panel = general_only != 0; }
+void oblas_b200_set_panel_path(int general_only) { g.no_fast_panel = general_only & 3; }
 void oblas_b200_set_tuning(int solve_geo, int apply_geo) {
   g.solve_geo = solve_geo;
   g.apply_geo = apply_geo;
@@ -542,7 +542,8 @@ static int solve_common(int field, SolveArgs &p, size_t nsys) {
   p.inv = ts >= 0 ? g.d_sets[ts].inv : nullptr;
   p.nsys = (uint32_t)nsys;
   p.phase = g.d_phase;
-  p.no_fast_panel = g.no_fast_panel;
+  p.no_fast_panel = g.no_fast_panel & 1;
+  p.no_look_ahead = (g.no_fast_panel >> 1) & 1;
   if (solve_tc_eligible(field, p, nsys)) return solve_tc_run(p, nsys);
   uint32_t grid = nsys < (size_t)g.sm_count ? (uint32_t)nsys : (uint32_t)g.sm_count;
   int rc = launch_solve(field, g.solve_geo == 3 ? -1 : g.solve_geo, p, grid, 512, g.smem_optin, g.stream);
@@ -993,6 +994,7 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
       pa.E = E; pa.pos2phys = maps; pa.tcount = tcount; pa.piv_all = piv_all; pa.npiv = npiv;
       pa.pivcols = p.pivcols ? p.pivcols + first * rows : nullptr;
       pa.nsys = cnt; pa.outer = outer; pa.inv = p.inv; pa.no_fast_panel = p.no_fast_panel;
+      pa.no_look_ahead = p.no_look_ahead;
       pa.phase = g.d_phase;
       // the row map lives in global memory as [sys][rows] u16 with a 16-byte aligned pitch
       {

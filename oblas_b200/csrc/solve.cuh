@@ -57,6 +57,7 @@ struct SolveArgs {
   // optional diagnostics: cycles spent per phase, summed over CTAs (8 counters)
   unsigned long long *phase;
   int no_fast_panel;  // diagnostics/tests: always use the general column-by-column panel path
+  int no_look_ahead;   // outer-panel kernel only: see PanelArgs
 };
 
 // Tile / table geometry.  NB = 32*NBW panel bits are cut into groups of KB bits
@@ -205,11 +206,35 @@ struct TileAlt {
   uint32_t split = 0;
 };
 
+template <int NBW> struct FastCand;
+template <int EXP, int NBW> struct FastGeo;
+template <int EXP, int NBW>
+OB2_D void panel_fast_candidates(const uint32_t *pan, uint16_t *pos2phys, uint16_t *piv_phys, uint32_t *prow,
+                                 uint32_t *vrow, uint32_t *scal, uint32_t *Mb, uint32_t t, uint32_t rows,
+                                 uint32_t c0, uint32_t *pivcols_sys, const uint8_t *inv_tab, FastCand<NBW> &fc);
+
+// Look-ahead of the outer-panel factorisation (panel_kernel): while the other warps stream the tile
+// pass of inner step q, the candidate group (the first NBT threads) first brings the NEXT panel's
+// chunk of the next step's candidate rows up to date and then runs that step's candidate elimination
+// -- a chain of NPIV dependent column steps that keeps two warps busy and would otherwise leave
+// the other fourteen waiting (37 % of the kernel before).  The tile pass only reads V, the tables and
+// the rows themselves; the elimination only touches the row map, piv_phys (read by the pass before
+// its first barrier), prow/vrow/scal and Mb, so the two do not interfere.
+struct LookAhead {
+  uint32_t t_next, c0_next;      // first free row position / first column of the next inner step
+  uint32_t *pivcols_sys;
+  const uint8_t *inv_tab;
+  uint16_t *pos2phys, *piv_phys;
+  uint32_t *prow, *vrow, *scal, *Mb;
+  uint8_t *is_cand;              // [rows] shared-memory flags, all zero outside update_tile
+};
+
 template <int EXP, int NBW, int KB, int WT>
 OB2_D void update_tile(uint8_t *base, size_t rs, uint32_t rows, uint32_t tile_off,
                        uint32_t tile_bytes, uint32_t npiv, const uint16_t *piv_phys,
                        const uint32_t *V, uint4 *tab, uint32_t *pan_next, uint32_t pan_off,
-                       const TileAlt alt = TileAlt()) {
+                       const TileAlt alt = TileAlt(), const LookAhead *look = nullptr,
+                       FastCand<NBW> *fc = nullptr) {
   using G = Geo<NBW, KB, WT>;
   auto chunk_ptr = [&](uint32_t r, uint32_t ch) -> uint8_t * {
     return ch < alt.split ? alt.base2 + (size_t)r * alt.rs2 + ch * 16 : base + (size_t)r * rs + tile_off + ch * 16;
@@ -220,6 +245,19 @@ OB2_D void update_tile(uint8_t *base, size_t rs, uint32_t rows, uint32_t tile_of
   const uint32_t tid = threadIdx.x, T = blockDim.x;
   const uint32_t cwt = tile_bytes >> 4;                // 16-byte chunks in this tile
   const uint32_t nbasis = npiv * EXP;                  // basis rows in use
+  // look-ahead: the candidate group leaves the streaming loop to the other threads
+  constexpr uint32_t LNBT = FastGeo<EXP, NBW>::NBT;
+  const bool la_thread = look != nullptr && tid < LNBT;
+  uint32_t la_phys = 0;
+  bool la_have = false;
+  if (la_thread) {
+    la_have = look->t_next + tid < rows;
+    if (la_have) {
+      la_phys = look->pos2phys[look->t_next + tid];
+      look->is_cand[la_phys] = 1;
+    }
+    if (tid == 0) look->scal[2] = 0;                   // fail flag of the candidate elimination
+  }
 
   // (a) tables, straight from global memory, no shared-memory reads
   for (uint32_t it = tid; it < (uint32_t)(NG - 1) * PARTS * cwt; it += T) {
@@ -252,13 +290,52 @@ OB2_D void update_tile(uint8_t *base, size_t rs, uint32_t rows, uint32_t tile_of
   // T % CW == 0: every item of this thread has the same chunk ch = tid % CW.  The lane whose
   // chunk holds the NEXT panel's bytes also writes the updated chunk into the shared-memory
   // panel, so the next panel factorisation starts without a global gather.
-  const uint32_t my_ch = tid % CW;
+  // with look-ahead the streaming threads are tid >= LNBT, renumbered from 0 (T - LNBT is a multiple of CW)
+  const uint32_t stid = look ? tid - LNBT : tid, ST = look ? T - LNBT : T;
+  const uint32_t my_ch = stid % CW;
   const bool pan_lane = pan_next != nullptr && pan_off >= tile_off + my_ch * 16 &&
                         pan_off < tile_off + my_ch * 16 + 16 && pan_off < tile_off + tile_bytes;
+  if (la_thread) {
+    // the next panel's chunk of this thread's candidate row, then the next step's candidate elimination
+    const uint32_t ch = (pan_off - tile_off) >> 4;
+    if (la_have) {
+      const PanelVec<NBW> v = ldv<NBW>(V + la_phys * NBW);
+      uint32_t any = 0;
+#pragma unroll
+      for (int w = 0; w < NBW; w++) any |= v.w[w];
+      uint8_t *ptr = chunk_ptr(la_phys, ch);
+      uint4 x = *reinterpret_cast<const uint4 *>(ptr);
+      if (any) {
+        const uint4 *tcl = tab + ch;
+#pragma unroll
+        for (int g = 0; g < NG; g++) {
+          const int bits = (g == NG - 1) ? LASTBITS : KB;
+          uint32_t idx = get_bits<NBW>(v, g * KB, bits);
+          x = xor4(x, tcl[(size_t)((g << KB) + idx) * CW]);
+        }
+        *reinterpret_cast<uint4 *>(ptr) = x;
+      }
+      if (NBW == 4) {
+        *reinterpret_cast<uint4 *>(pan_next + la_phys * NBW) = x;
+      } else {
+        uint2 h = (pan_off & 8) ? make_uint2(x.z, x.w) : make_uint2(x.x, x.y);
+        *reinterpret_cast<uint2 *>(pan_next + la_phys * NBW) = h;
+      }
+    }
+    OB2_NAMED_BAR(1, LNBT);
+    panel_fast_candidates<EXP, NBW>(pan_next, look->pos2phys, look->piv_phys, look->prow, look->vrow, look->scal,
+                                    look->Mb, look->t_next, rows, look->c0_next, look->pivcols_sys, look->inv_tab, *fc);
+    __syncthreads();  // tables are rebuilt by the next tile; the streaming threads are done with the flags
+    if (la_have) look->is_cand[la_phys] = 0;   // (next reader: the next update_tile, block barriers away)
+    return;
+  }
+  const uint8_t *is_cand = look ? look->is_cand : nullptr;
   auto fetch = [&](uint32_t it) {
     Item m;
     m.r = it / CW;
     m.live = (it < items) && (my_ch < cwt);
+    // the candidate group has done (row, next panel's chunk) of its rows itself
+    if (is_cand && pan_lane && m.live && is_cand[m.r]) m.live = false;
     m.v = ldv<NBW>(V + (m.live ? m.r : 0) * NBW);
     uint32_t any = 0;
 #pragma unroll
@@ -289,9 +366,9 @@ OB2_D void update_tile(uint8_t *base, size_t rs, uint32_t rows, uint32_t tile_of
       }
     }
   };
-  Item c0 = fetch(tid), c1 = fetch(tid + T);
-  for (uint32_t it0 = tid; it0 < items; it0 += T * RU) {
-    Item n0 = fetch(it0 + T * RU), n1 = fetch(it0 + T * RU + T);
+  Item c0 = fetch(stid), c1 = fetch(stid + ST);
+  for (uint32_t it0 = stid; it0 < items; it0 += ST * RU) {
+    Item n0 = fetch(it0 + ST * RU), n1 = fetch(it0 + ST * RU + ST);
     apply(c0);
     apply(c1);
     c0 = n0;
@@ -822,6 +899,7 @@ struct PanelArgs {
   uint32_t outer;           // outer panel index
   const uint8_t *inv;
   int no_fast_panel;
+  int no_look_ahead;           // diagnostics/tests: candidate elimination never overlapped with the tile pass
   unsigned long long *phase;   // optional diagnostics: cycles per phase summed over CTAs (5 counters)
 };
 
@@ -851,7 +929,10 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
   uint32_t *vrow = reinterpret_cast<uint32_t *>(sp);       sp += (size_t)EXP * NBW * 4;
   uint32_t *scal = reinterpret_cast<uint32_t *>(sp);
   uint8_t *inv_s = reinterpret_cast<uint8_t *>(scal + 32);
+  uint32_t *Mb = reinterpret_cast<uint32_t *>(inv_s + 256);          // [128][NBW] pivots' vectors (look-ahead: not in the table area)
+  uint8_t *is_cand = reinterpret_cast<uint8_t *>(Mb + 32 * NBW * NBW);  // [rows] look-ahead flags
   for (uint32_t k = threadIdx.x; k < 256u; k += blockDim.x) inv_s[k] = p.inv[k];
+  for (uint32_t k = threadIdx.x; k < rows; k += blockDim.x) is_cand[k] = 0;
   __syncthreads();
 
   // phase clock (diagnostics only): 0 panel load + clear, 1 factorisation, 2 unit injection and
@@ -886,6 +967,8 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
     uint32_t t = (p.outer == 0) ? 0u : p.tcount[sys];   // uniform
     uint32_t gcount = 0;                                // pivots of this outer panel so far
     bool pan_ready = false;
+    bool la_done = false;          // look-ahead: this step's candidate elimination is already done
+    FastCand<NBW> fc;              // ... and what the candidate group's threads keep from it
     __syncthreads();
     tick(4);
 
@@ -907,11 +990,22 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
       uint32_t n = 0;
       constexpr uint32_t kFastThreads = (uint32_t)((NPIV + 32 + 31) / 32 * 32);
       bool fast = false;
-      if (ncols_p == (uint32_t)NPIV && rows - t >= (uint32_t)NPIV && kFastThreads <= T && !p.no_fast_panel)
+      if (la_done) {
+        // the candidate rows of this step were eliminated during the previous step's tile pass
+        long long pf_t = 0;
+#ifndef OB2_EMU
+        if (p.phase && tid == 0) pf_t = clock64();
+#endif
+        panel_fast_finish<EXP, NBW, SM::T2C>(pan, V, reinterpret_cast<uint32_t *>(tab) + 32 * NBW * NBW, Mb, fc, rows,
+                                             (p.phase && tid == 0) ? acc_pf : nullptr, pf_t);
+        fast = true;
+      } else if (ncols_p == (uint32_t)NPIV && rows - t >= (uint32_t)NPIV && kFastThreads <= T && !p.no_fast_panel) {
         fast = panel_fast<EXP, NBW, SM::T2C>(pan, V, pos2phys, piv_phys, prow, vrow, scal,
                                     reinterpret_cast<uint32_t *>(tab), t, rows, c0,
                                     p.pivcols ? p.pivcols + (size_t)sys * rows : nullptr, inv_s,
                                     (p.phase && tid == 0) ? acc_pf : nullptr);
+      }
+      la_done = false;
       if (fast) {
         n = NPIV;
         t += NPIV;
@@ -1026,7 +1120,21 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
         tick(2);
         TileAlt alt;
         alt.base2 = E; alt.rs2 = kOuterBytes; alt.split = split;
-        update_tile<EXP, NBW, KB, WT>(A, p.a_rs, rows, win_off, win_bytes, n, piv_phys, V, tab, pan, next_off, alt);
+        // look-ahead: the next inner step is a full 16-column step of this outer panel with enough rows left
+        const uint32_t c0n = c0 + NPIV;
+        const bool look_ok = fast && !p.no_look_ahead && next_off != 0xffffffffu && c0n + NPIV <= p.cols &&
+                             rows - t >= (uint32_t)NPIV && kFastThreads < T && (T - kFastThreads) % G::CW == 0;
+        if (look_ok) {
+          LookAhead lk;
+          lk.t_next = t; lk.c0_next = c0n;
+          lk.pivcols_sys = p.pivcols ? p.pivcols + (size_t)sys * rows : nullptr;
+          lk.inv_tab = inv_s; lk.pos2phys = pos2phys; lk.piv_phys = piv_phys;
+          lk.prow = prow; lk.vrow = vrow; lk.scal = scal; lk.Mb = Mb; lk.is_cand = is_cand;
+          update_tile<EXP, NBW, KB, WT>(A, p.a_rs, rows, win_off, win_bytes, n, piv_phys, V, tab, pan, next_off, alt, &lk, &fc);
+          la_done = scal[2] == 0;          // uniform: read after the closing barrier of the pass
+        } else {
+          update_tile<EXP, NBW, KB, WT>(A, p.a_rs, rows, win_off, win_bytes, n, piv_phys, V, tab, pan, next_off, alt);
+        }
       } else {
         update_tile<EXP, NBW, KB, WT>(A, p.a_rs, rows, win_off, win_bytes, n, piv_phys, V, tab, pan, next_off);
         update_tile<EXP, NBW, KB, WT>(E, kOuterBytes, rows, 0, kOuterBytes, n, piv_phys, V, tab, nullptr, 0xffffffffu);
@@ -1053,11 +1161,14 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
 #endif
 }
 
+// look-ahead state of panel_kernel behind the SolveSmem layout: Mb (2 KB) + one flag byte per row
+inline size_t panel_extra_bytes(uint32_t rows) { return (size_t)32 * 4 * 4 * 4 + (((size_t)rows + 15) & ~(size_t)15); }
+
 template <int KB, int WT>
 inline int launch_panel_t(const PanelArgs &p, uint32_t grid, size_t smem_limit, cudaStream_t s,
                           uint32_t threads = 512) {
   using SM = SolveSmem<8, 4, KB, WT>;
-  size_t smem = SM::bytes(p.rows);
+  size_t smem = SM::bytes(p.rows) + panel_extra_bytes(p.rows);
   if (smem > smem_limit || p.rows > 65535u || p.rows == 0) return -1;
   if (threads % SM::G::CW) return -3;
   auto k = panel_kernel<KB, WT>;
@@ -1069,7 +1180,7 @@ inline int launch_panel_t(const PanelArgs &p, uint32_t grid, size_t smem_limit, 
   OB2_LAUNCH(k, grid, threads, smem, s, p);
   return 0;
 }
-inline size_t panel_smem_bytes(uint32_t rows) { return SolveSmem<8, 4, 6, 128>::bytes(rows); }
+inline size_t panel_smem_bytes(uint32_t rows) { return SolveSmem<8, 4, 6, 128>::bytes(rows) + panel_extra_bytes(rows); }
 
 // rows of A and B into position order + rank, after the last outer panel
 struct PermuteArgs {

@@ -161,7 +161,7 @@ int emu_solve_outer(uint8_t *A, size_t a_rs, size_t a_ss, uint32_t rows, uint32_
     pa.A = A; pa.a_rs = a_rs; pa.a_ss = a_ss; pa.rows = rows; pa.cols = cols; pa.a_bytes = a_bytes;
     pa.E = E.data(); pa.pos2phys = maps.data(); pa.tcount = tcount.data(); pa.piv_all = piv_all.data();
     pa.npiv = npiv.data(); pa.pivcols = pivcols; pa.nsys = nsys; pa.outer = outer;
-    pa.inv = T.inv; pa.no_fast_panel = no_fast;
+    pa.inv = T.inv; pa.no_fast_panel = no_fast & 1; pa.no_look_ahead = (no_fast >> 1) & 1;
     int rc = launch_panel_t<6, 128>(pa, grid, smem_limit, nullptr, threads);
     if (rc) return rc;
     const uint32_t a0 = (outer + 1) * kOuterBytes;

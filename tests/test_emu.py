@@ -205,6 +205,14 @@ def test_apply():
     dict(rows=270, cols=140, b_bytes=0, seed=403),                       # tall, no right-hand side
     dict(rows=160, cols=160, b_bytes=64, seed=404, deficient=2),         # free columns inside an outer panel
     dict(rows=130, cols=130, b_bytes=16, seed=405, nsys=3, grid=2),      # persistent loop over systems
+    # 128 threads: the candidate group (64) runs the NEXT step's candidate elimination while the other
+    # 64 stream the tile pass (look-ahead); 64-thread runs above have no streaming threads left for it
+    dict(rows=150, cols=150, b_bytes=48, seed=406, threads=128),
+    dict(rows=150, cols=150, b_bytes=48, seed=406, threads=128, no_fast=2),   # same with the look-ahead off
+    dict(rows=270, cols=140, b_bytes=0, seed=407, threads=128),          # tall: candidate window never short
+    dict(rows=140, cols=270, b_bytes=32, seed=408, threads=128),         # wide: rows run out inside an outer panel
+    dict(rows=160, cols=160, b_bytes=64, seed=409, deficient=2, threads=128),  # look-ahead fails (free column) -> general path
+    dict(rows=200, cols=200, b_bytes=16, seed=410, nsys=3, grid=2, threads=128),
 ])
 def test_outer_panel_elimination(args):
     """the algorithm of the tensor-core elimination (outer panels of 128 columns, E tracked as a
@@ -223,7 +231,8 @@ def test_outer_panel_elimination(args):
     rc = e.emu_solve_outer(ptr(A), A.strides[1], A.strides[0], rows, cols, A.shape[2],
                            ptr(B) if B is not None else None, B.strides[1] if B is not None else 0,
                            B.strides[0] if B is not None else 0, B.shape[2] if B is not None else 0,
-                           ptr(rank, i32p), ptr(piv, u32p), nsys, args.get("grid", 1), 64, SMEM, args.get("no_fast", 0))
+                           ptr(rank, i32p), ptr(piv, u32p), nsys, args.get("grid", 1), args.get("threads", 64), SMEM,
+                           args.get("no_fast", 0))
     assert rc == 0
     assert [int(r) for r in rank] == [w[0] for w in want]
     for s in range(nsys):
