@@ -975,7 +975,8 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
   uint32_t *npiv = (uint32_t *)ws;
   // permutation kernel: row map + staging area in shared memory
   const size_t pmap = ((size_t)rows * 2 + 15) / 16 * 16;
-  if (pmap + 64 + (size_t)rows * 16 > g.smem_optin) return fail("solve: %u rows do not fit the permutation stage", rows);
+  // stage = count + list of moved rows (u16 x rows) + at least 16 bytes per row
+  if (pmap + 64 + 16 + pmap + (size_t)rows * 16 > g.smem_optin) return fail("solve: %u rows do not fit the permutation stage", rows);
   const uint32_t stage_bytes = (uint32_t)((g.smem_optin - pmap - 64) & ~(size_t)15);
   static bool perm_attr = false;
   if (!perm_attr) {

@@ -383,22 +383,36 @@ OB2_D void update_tile(uint8_t *base, size_t rs, uint32_t rows, uint32_t tile_of
 // ---------------------------------------------------------------------------
 OB2_D void permute_rows(uint8_t *base, size_t rs, uint32_t rows, uint32_t nbytes,
                         const uint16_t *pos2phys, uint4 *stage, uint32_t stage_bytes) {
+  // Only the rows that change position are touched.  With the canonical pivot rule a random system
+  // swaps a handful of rows (the pivot of a column is the row already in place with probability
+  // 255/256), so staging ALL rows -- what this did before -- read the whole system for nothing.
+  // stage: [count (16 B)] [destinations of the moved rows, u16 x rows] [row blocks]
   const uint32_t tid = threadIdx.x, T = blockDim.x;
-  uint32_t bw = (stage_bytes / rows) & ~15u;  // block width in bytes
-  if (bw > 256) bw = 256;
+  uint32_t *cnt = reinterpret_cast<uint32_t *>(stage);
+  uint16_t *list = reinterpret_cast<uint16_t *>(stage + 1);
+  const uint32_t list_bytes = (rows * 2 + 15) & ~15u;
+  uint4 *blocks = stage + 1 + list_bytes / 16;
+  if (tid == 0) *cnt = 0;
+  __syncthreads();
+  for (uint32_t i = tid; i < rows; i += T)
+    if (pos2phys[i] != i) list[atomicAdd(cnt, 1u)] = (uint16_t)i;
+  __syncthreads();
+  const uint32_t m = *cnt;                           // uniform
+  if (m == 0) return;
+  const uint32_t avail = stage_bytes - 16 - list_bytes;   // callers guarantee >= 16 bytes per row
+  uint32_t bw = (avail / m) & ~15u;                  // block width in bytes
+  if (bw > nbytes) bw = nbytes;
   for (uint32_t off = 0; off < nbytes; off += bw) {
     uint32_t w = (nbytes - off < bw) ? (nbytes - off) : bw;
     uint32_t cw = w >> 4;
-    for (uint32_t it = tid; it < rows * cw; it += T) {
-      uint32_t r = it / cw, ch = it - r * cw;
-      stage[it] = *reinterpret_cast<const uint4 *>(base + (size_t)r * rs + off + ch * 16);
+    for (uint32_t it = tid; it < m * cw; it += T) {
+      uint32_t k = it / cw, ch = it - k * cw;
+      blocks[it] = *reinterpret_cast<const uint4 *>(base + (size_t)pos2phys[list[k]] * rs + off + ch * 16);
     }
     __syncthreads();
-    for (uint32_t it = tid; it < rows * cw; it += T) {
-      uint32_t i = it / cw, ch = it - i * cw;
-      uint32_t src = pos2phys[i];
-      if (src != i)
-        *reinterpret_cast<uint4 *>(base + (size_t)i * rs + off + ch * 16) = stage[src * cw + ch];
+    for (uint32_t it = tid; it < m * cw; it += T) {
+      uint32_t k = it / cw, ch = it - k * cw;
+      *reinterpret_cast<uint4 *>(base + (size_t)list[k] * rs + off + ch * 16) = blocks[it];
     }
     __syncthreads();
   }

@@ -100,6 +100,28 @@ def test_zero_and_identity_systems():
     assert np.array_equal(host(dA), A0) and np.array_equal(host(dB), B0)
 
 
+def test_every_row_moves():
+    """row-reversed systems: the pivot of column c is the LAST row with a non-zero entry, so every row
+    changes position -- the row permutation at the end stages all rows (several column blocks), the
+    other extreme of the usual handful of swaps.  Both elimination paths; system 1 is rank deficient."""
+    K, L = 640, 272
+    A = np.stack([random_matrix(GF256, K, K, 7700 + s) for s in range(2)])
+    for s in range(2):   # zero above the anti-diagonal: column c has its first non-zero entry in row K-1-c
+        for i in range(K):
+            A[s, i, :K - 1 - i] = 0
+        A[s, np.arange(K), K - 1 - np.arange(K)] |= 1
+    A[1, :, 5] = 0   # a free column
+    B = splitmix_bytes(7702, 2 * K * L).reshape(2, K, L).copy()
+    dA, dB = dev(A), dev(B)
+    rank, piv = device.solve_batch(GF256, dA, K, dB, want_pivcols=True)
+    A0, B0 = A.copy(), B.copy()
+    for s in range(2):
+        rk, pv = oracle_solve(GF256, A0[s], B0[s], K)
+        assert int(host(rank)[s]) == rk
+        assert np.array_equal(host(piv)[s][:rk].astype(np.uint32), pv[:rk])
+    assert np.array_equal(host(dA), A0) and np.array_equal(host(dB), B0)
+
+
 def test_config2_shape_vs_reference():
     """K=1024, 1280-byte RHS symbols (BASELINE.json configs[1]) -- whole buffers against
     the unmodified reference's AVX build driven by oracle/ref_driver.c (falls back to a
