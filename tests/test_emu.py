@@ -213,6 +213,10 @@ def test_apply():
     dict(rows=140, cols=270, b_bytes=32, seed=408, threads=128),         # wide: rows run out inside an outer panel
     dict(rows=160, cols=160, b_bytes=64, seed=409, deficient=2, threads=128),  # look-ahead fails (free column) -> general path
     dict(rows=200, cols=200, b_bytes=16, seed=410, nsys=3, grid=2, threads=128),
+    # a whole 16-column step without pivots inside an outer panel: the next step's own columns are then
+    # window chunk 1 while E still has no columns (split 0) -- the directly written chunk is q, not split
+    dict(rows=150, cols=150, b_bytes=32, seed=411, threads=128, zero_cols=(0, 16)),
+    dict(rows=150, cols=150, b_bytes=32, seed=412, threads=128, zero_cols=(32, 48)),
 ])
 def test_outer_panel_elimination(args):
     """the algorithm of the tensor-core elimination (outer panels of 128 columns, E tracked as a
@@ -222,6 +226,8 @@ def test_outer_panel_elimination(args):
     nsys, deficient = args.get("nsys", 1), args.get("deficient", 0)
     e = emu()
     A = np.stack([random_matrix(GF256, rows, cols, seed + 2 * s, rank_deficient=deficient) for s in range(nsys)])
+    if "zero_cols" in args:
+        A[:, :, args["zero_cols"][0]:args["zero_cols"][1]] = 0
     B = np.stack([splitmix_bytes(seed + 2 * s + 1, rows * b_bytes).reshape(rows, b_bytes)
                   for s in range(nsys)]).copy() if b_bytes else None
     A0, B0 = A.copy(), (B.copy() if B is not None else None)

@@ -100,6 +100,25 @@ def test_zero_and_identity_systems():
     assert np.array_equal(host(dA), A0) and np.array_equal(host(dB), B0)
 
 
+def test_pivotless_steps_inside_an_outer_panel():
+    """whole 16-column steps without pivots (zero columns) at the start and in the middle of an outer
+    panel of the tensor-core path: window chunk of the next full step != number of E chunks"""
+    K, L = 640, 96
+    A = np.stack([random_matrix(GF256, K, K, 7800 + s) for s in range(2)])
+    A[:, :, 0:16] = 0
+    A[:, :, 160:192] = 0
+    A[1, :, 300] = 0
+    B = splitmix_bytes(7802, 2 * K * L).reshape(2, K, L).copy()
+    dA, dB = dev(A), dev(B)
+    rank, piv = device.solve_batch(GF256, dA, K, dB, want_pivcols=True)
+    A0, B0 = A.copy(), B.copy()
+    for s in range(2):
+        rk, pv = oracle_solve(GF256, A0[s], B0[s], K)
+        assert int(host(rank)[s]) == rk
+        assert np.array_equal(host(piv)[s][:rk].astype(np.uint32), pv[:rk])
+    assert np.array_equal(host(dA), A0) and np.array_equal(host(dB), B0)
+
+
 def test_every_row_moves():
     """row-reversed systems: the pivot of column c is the LAST row with a non-zero entry, so every row
     changes position -- the row permutation at the end stages all rows (several column blocks), the
