@@ -167,6 +167,36 @@ def test_solve_fast_and_general_panel_paths(args, no_fast):
     _solve(no_fast=no_fast, **args)
 
 
+def test_solve_every_row_moves():
+    """zero above the anti-diagonal: column c has its first non-zero entry in row n-1-c, so every row
+    changes position -- the final row permutation stages all rows (several column blocks) instead of
+    the usual handful; table kernel and outer-panel path"""
+    e = emu()
+    rows = cols = 96
+    b_bytes = 48
+    A = random_matrix(GF256, rows, cols, 301)[None].copy()
+    for i in range(rows):
+        A[0, i, :cols - 1 - i] = 0
+    A[0, np.arange(rows), cols - 1 - np.arange(rows)] |= 1
+    B = splitmix_bytes(302, rows * b_bytes).reshape(1, rows, b_bytes).copy()
+    A0, B0 = A.copy(), B.copy()
+    rk, pv = oracle_solve(GF256, A0[0], B0[0], cols)
+    assert rk == rows
+    for outer in (0, 1):
+        a, b = A.copy(), B.copy()
+        rank = np.zeros(1, dtype=np.int32)
+        piv = np.full((1, rows), 0xFFFFFFFF, dtype=np.uint32)
+        if outer:
+            rc = e.emu_solve_outer(ptr(a), a.strides[1], a.strides[0], rows, cols, a.shape[2], ptr(b), b.strides[1],
+                                   b.strides[0], b.shape[2], ptr(rank, i32p), ptr(piv, u32p), 1, 1, 128, SMEM, 0)
+        else:
+            rc = e.emu_solve(GF256, ptr(a), a.strides[1], a.strides[0], rows, cols, a.shape[2], ptr(b), b.strides[1],
+                             b.strides[0], b.shape[2], ptr(rank, i32p), ptr(piv, u32p), 1, 1, 64, SMEM, 4, -1, 0)
+        assert rc == 0 and rank[0] == rk
+        assert np.array_equal(piv[0][:rk], pv[:rk])
+        assert np.array_equal(a, A0) and np.array_equal(b, B0)
+
+
 def test_solve_zero_and_identity():
     e = emu()
     for field in (GF256, GF2):
