@@ -26,14 +26,14 @@
 //                     SBO = 256); 4 bytes of fp4 per byte of D.  Written once, read by every
 //                     row tile.  In the elimination the rows are the pivot rows of the outer
 //                     panel, gathered through the row map.
-//   apply_tc_kernel<NH>  persistent, 1 CTA per SM, warp specialised, 14 warps:
+//   apply_tc_kernel<NH>  persistent, 1 CTA per SM, warp specialised, 18 warps:
 //                       warp 0      one elected thread issues tcgen05.mma (M=128, N=240, K=64),
 //                                   tcgen05.commit frees the stage
 //                       warp 1      producer: cp.async.bulk (TMA engine) per stage, Dx -> smem
 //                       warps 2-5   A-operand builders: 16 rows x 8 coefficients of C per step,
 //                                   each coefficient expanded to its 8x8 bit matrix through a
 //                                   256 x 32-byte table in shared memory (round robin over stages)
-//                       warps 6-13  epilogue: tcgen05.ld, parity, 8x8 bit transposes across the 8
+//                       warps 6-17  epilogue: tcgen05.ld, parity, 8x8 bit transposes across the 8
 //                                   bit-plane lanes of a row, 32-bit coalesced stores (XOR with the
 //                                   old contents in accumulate mode)
 //                     mbarrier ring between producers and the MMA thread, 4 MMAs per stage.
@@ -66,7 +66,8 @@ constexpr int kATile = 16 * kASbo;           // bytes of one A-operand block (46
 // the producer run short dependent instruction sequences between barrier waits, and every cycle they
 // lose to the epilogue warps of their scheduler is a cycle the tensor pipe may run dry.
 constexpr int kMmaWarp = 0, kProdWarp = 1, kBuild0 = 2;
-constexpr int kEpi0 = 6, kEpiWarps = 8;      // warps 6..13: TMEM lane quarter = warp % 4, chunk half = (warp - 6) / 4
+constexpr int kEpi0 = 6, kEpiWarps = 12;     // warps 6..17: TMEM lane quarter = warp % 4, chunk part = (warp - 6) / 4
+constexpr int kEpiParts = kEpiWarps / 4;     // warps per lane quarter: they share out the chunks of a tile
 constexpr int kBuilderWarps = 4;             // warps 2..5, one stage each, round robin
 constexpr int kSfCol = 480;                  // TMEM columns 480..511: scale factors (all 1.0)
 constexpr int kThreads = 32 * (kEpi0 + kEpiWarps);
@@ -309,13 +310,14 @@ OB2_D void stg_pred(void *ptr, uint32_t v, bool pred) {
 // tile): the chunks below ncur are shared out between the two warps of a lane quarter.
 template <int TILE_N>
 struct EpiTile {
-  static constexpr int kChunks = (TILE_N + 31) / 32, kC0 = (kChunks + 1) / 2;
+  static constexpr int kChunks = (TILE_N + 31) / 32, kC0 = (kChunks + kEpiParts - 1) / kEpiParts;
   // per (system, row): this lane's row in region 0 / region 1 (y1 has "- split" folded in, so both
   // are indexed by the virtual column), the region boundary and the end of the virtual range
   uint8_t *y0, *y1;
   uint32_t split, vend;
   uint32_t ct0;           // column of this lane's word inside a chunk (4 * gc)
-  bool row_ok, upper;     // upper: this warp takes the second half of the tile's chunks
+  bool row_ok;
+  uint32_t part;          // which share of the tile's chunks this warp takes (0 .. kEpiParts-1)
   // per tile
   uint32_t vt;            // virtual column of this lane's word of chunk 0
   int c_lo, c_hi;
@@ -323,7 +325,7 @@ struct EpiTile {
                       uint32_t M) {
     const uint32_t lq = warp & 3u, rr = lane >> 3;
     ct0 = 4 * (lane & 7u);
-    upper = warp >= (uint32_t)(kEpi0 + 4);
+    part = (warp - (uint32_t)kEpi0) >> 2;
     const uint32_t row = it * kRowsI + lq * 4 + rr;
     row_ok = row < M;
     const TcRegion &r0 = reg[0];
@@ -343,9 +345,8 @@ struct EpiTile {
     vt = v_tile + ct0;
     const uint32_t rest = vend > v_tile ? vend - v_tile : 0u;
     const int nch = rest >= (uint32_t)TILE_N ? kChunks : (int)((rest + 31) / 32);
-    const int h = (nch + 1) / 2;
-    c_lo = upper ? h : 0;
-    c_hi = upper ? nch : h;
+    c_lo = (nch * (int)part) / kEpiParts;
+    c_hi = (nch * ((int)part + 1)) / kEpiParts;
   }
   OB2_D void set(uint32_t warp, uint32_t lane, const TcRegion *reg, uint32_t nreg, uint32_t sys, uint32_t tile,
                  uint32_t it, uint32_t M) {
@@ -704,7 +705,7 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
       G += nst;
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 6..13)
+    // ------------------------------------------------------------ epilogue (warps 6..17)
     using ET = EpiTile<kTileN>;
     auto tile_of = [&](uint32_t t, ET &e) {
       const uint32_t snt = t / itiles, it = t % itiles;
@@ -748,7 +749,7 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
 // built ONCE per (system, row tile) into a resident shared-memory block while only the B blocks
 // stream through a ring.  Work unit of a CTA = (system, row tile), its column tiles are
 // processed back to back.
-//   warp 0 MMA issuer | warp 1 producer (B ring) | warps 2-5 A builders | warps 6-13 epilogue
+//   warp 0 MMA issuer | warp 1 producer (B ring) | warps 2-5 A builders | warps 6-17 epilogue
 // What bounds it (measured: role counters below, ncu warp-state samples of the MMA warp,
 // tools/tmem_ld.cu): the MMA warp is ONE warp running dependent code at ~0.3 IPC, so every barrier
 // round trip (try_wait, descriptors to uniform registers, commit) costs it 150-250 clk -- as much
@@ -971,7 +972,7 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
       atomicAdd(p.prof + 11, (unsigned long long)(clock64() - pt0));
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 6..13)
+    // ------------------------------------------------------------ epilogue (warps 6..17)
     using ET = EpiTile<kHalfN>;
     auto tile_of = [&](uint32_t su, uint32_t nt, ET &e) {
       const uint32_t sys = su / itiles, it = su - sys * itiles;
