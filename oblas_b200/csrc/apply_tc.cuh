@@ -26,14 +26,14 @@
 //                     SBO = 256); 4 bytes of fp4 per byte of D.  Written once, read by every
 //                     row tile.  In the elimination the rows are the pivot rows of the outer
 //                     panel, gathered through the row map.
-//   apply_tc_kernel<NH>  persistent, 1 CTA per SM, warp specialised, 18 warps:
+//   apply_tc_kernel<NH>  persistent, 1 CTA per SM, warp specialised, 14 warps:
 //                       warp 0      one elected thread issues tcgen05.mma (M=128, N=240, K=64),
 //                                   tcgen05.commit frees the stage
 //                       warp 1      producer: cp.async.bulk (TMA engine) per stage, Dx -> smem
 //                       warps 2-5   A-operand builders: 16 rows x 8 coefficients of C per step,
 //                                   each coefficient expanded to its 8x8 bit matrix through a
 //                                   256 x 32-byte table in shared memory (round robin over stages)
-//                       warps 6-17  epilogue: tcgen05.ld, parity, 8x8 bit transposes across the 8
+//                       warps 6-13  epilogue: tcgen05.ld, parity, 8x8 bit transposes across the 8
 //                                   bit-plane lanes of a row, 32-bit coalesced stores (XOR with the
 //                                   old contents in accumulate mode)
 //                     mbarrier ring between producers and the MMA thread, 4 MMAs per stage.
@@ -66,8 +66,9 @@ constexpr int kATile = 16 * kASbo;           // bytes of one A-operand block (46
 // the producer run short dependent instruction sequences between barrier waits, and every cycle they
 // lose to the epilogue warps of their scheduler is a cycle the tensor pipe may run dry.
 constexpr int kMmaWarp = 0, kProdWarp = 1, kBuild0 = 2;
-constexpr int kEpi0 = 6, kEpiWarps = 12;     // warps 6..17: TMEM lane quarter = warp % 4, chunk part = (warp - 6) / 4
+constexpr int kEpi0 = 6, kEpiWarps = 8;      // warps 6..13: TMEM lane quarter = warp % 4, chunk part = (warp - 6) / 4
 constexpr int kEpiParts = kEpiWarps / 4;     // warps per lane quarter: they share out the chunks of a tile
+                                             // (12 warps = 3 per quarter measured no faster than 8)
 constexpr int kBuilderWarps = 4;             // warps 2..5, one stage each, round robin
 constexpr int kSfCol = 480;                  // TMEM columns 480..511: scale factors (all 1.0)
 constexpr int kThreads = 32 * (kEpi0 + kEpiWarps);
@@ -705,7 +706,7 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
       G += nst;
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 6..17)
+    // ------------------------------------------------------------ epilogue (warps 6..13)
     using ET = EpiTile<kTileN>;
     auto tile_of = [&](uint32_t t, ET &e) {
       const uint32_t snt = t / itiles, it = t % itiles;
@@ -749,7 +750,7 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
 // built ONCE per (system, row tile) into a resident shared-memory block while only the B blocks
 // stream through a ring.  Work unit of a CTA = (system, row tile), its column tiles are
 // processed back to back.
-//   warp 0 MMA issuer | warp 1 producer (B ring) | warps 2-5 A builders | warps 6-17 epilogue
+//   warp 0 MMA issuer | warp 1 producer (B ring) | warps 2-5 A builders | warps 6-13 epilogue
 // What bounds it (measured: role counters below, ncu warp-state samples of the MMA warp,
 // tools/tmem_ld.cu): the MMA warp is ONE warp running dependent code at ~0.3 IPC, so every barrier
 // round trip (try_wait, descriptors to uniform registers, commit) costs it 150-250 clk -- as much
@@ -972,7 +973,7 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
       atomicAdd(p.prof + 11, (unsigned long long)(clock64() - pt0));
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 6..17)
+    // ------------------------------------------------------------ epilogue (warps 6..13)
     using ET = EpiTile<kHalfN>;
     auto tile_of = [&](uint32_t su, uint32_t nt, ET &e) {
       const uint32_t sys = su / itiles, it = su - sys * itiles;
