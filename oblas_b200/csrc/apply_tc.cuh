@@ -1028,6 +1028,273 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
   if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------
+// The same rank-128 update on CTA PAIRS (tcgen05 cta_group::2, M = 256): the two CTAs of a cluster own
+// two neighbouring row tiles of one system and share every B block -- each loads HALF of its columns,
+// the tensor cores of both SMs read both halves.  Per SM that halves the bulk-copy traffic into shared
+// memory and the B-operand fetch, and the one issuing warp (CTA 0) drives twice the work per barrier
+// round trip.  Roles as in update_tc_kernel; what differs:
+//   * only CTA 0 issues MMAs (tcgen05.mma.cta_group::2) and commits, with multicast commits so that
+//     the b_empty / a_empty / tmem_full barriers of BOTH CTAs see the completion;
+//   * what the issuer waits for lives in CTA 0: b_full (its own bulk copy + a relay arrive from the
+//     idle MMA warp of CTA 1 once CTA 1's half has landed), a_full (builders of both CTAs, remote
+//     arrives through mapa) and tmem_empty (epilogue warps of both CTAs, one arrive per warp);
+//   * a column tile of width N is split N/2 | N/2 (the narrow last tile too), so CTA r copies bytes
+//     [r * N * 16, (r + 1) * N * 16) of every K-step block.
+// ---------------------------------------------------------------------------------------
+OB2_D uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+OB2_D void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+OB2_D uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {   // shared::cta address -> shared::cluster address in CTA `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+OB2_D void mbar_arrive_cluster(uint32_t caddr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
+}
+OB2_D void tc_commit2(uint32_t bar) {   // arrives on the barrier at this offset in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+OB2_D void umma_mxf4_2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                       uint32_t sfa, uint32_t sfb) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(sfa), "r"(sfb) : "memory");
+}
+
+constexpr int kU2Stages = 8;                          // ring of 8 half-width stages = two column tiles
+constexpr int kU2HBlock = kHBlock / 2;                // bytes of half a K-step block (3840)
+constexpr int kU2BStage = kUSPS * kU2HBlock;          // 15360
+constexpr size_t kU2SmemBytes = (size_t)kUABuf + (size_t)kU2Stages * kU2BStage + kLutBytes + 512 + 1024;
+static_assert(kU2Stages == 2 * kUStages, "two trips of the A parts around the ring");
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) update_tc2_kernel(const ApplyTcArgs p) {
+  extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+  unsigned char *sm = tc_smem_raw + ((1024u - (smem_addr(tc_smem_raw) & 1023u)) & 1023u);
+  unsigned char *smA = sm;                                   // [kUSteps][kATile]
+  unsigned char *smB = sm + (size_t)kUABuf;                  // [kU2Stages][kUSPS][kU2HBlock]
+  uint32_t *lut = reinterpret_cast<uint32_t *>(smB + (size_t)kU2Stages * kU2BStage);
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(lut) + kLutBytes);
+  // bars: b_full[8], b_empty[8], a_full[4], a_empty[4], tmem_full[2], tmem_empty[2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 32);
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t bar0 = smem_addr(bars);
+  auto b_full = [&](uint32_t s) { return bar0 + 8u * s; };
+  auto b_empty = [&](uint32_t s) { return bar0 + 8u * (8 + s); };
+  auto a_full = [&](uint32_t h) { return bar0 + 8u * (16 + h); };
+  auto a_empty = [&](uint32_t h) { return bar0 + 8u * (20 + h); };
+  auto tmem_full = [&](uint32_t b) { return bar0 + 8u * (24 + b); };
+  auto tmem_empty = [&](uint32_t b) { return bar0 + 8u * (26 + b); };
+
+  build_bitmatrix_lut(lut, tid);
+  if (tid == 0) {
+    for (uint32_t s = 0; s < (uint32_t)kU2Stages; s++) {
+      mbar_init(b_full(s), rank == 0 ? 2 : 1);   // own bulk copy (+ in CTA 0: the relay arrive of CTA 1)
+      mbar_init(b_empty(s), 1);                  // multicast commit
+    }
+    for (uint32_t s = 0; s < (uint32_t)kUStages; s++) {
+      mbar_init(a_full(s), 2 * 32 * kBuilderWarps);   // builders of both CTAs (used in CTA 0 only)
+      mbar_init(a_empty(s), 1);
+    }
+    for (uint32_t b = 0; b < 2; b++) {
+      mbar_init(tmem_full(b), 1);
+      mbar_init(tmem_empty(b), 2 * kEpiWarps);        // one arrive per epilogue warp of both CTAs (CTA 0 only)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_sync_all();      // both CTAs are resident before the pair allocates tensor memory
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *tmem_slot;
+  if (warp >= (uint32_t)kEpi0 && warp < (uint32_t)kEpi0 + 4) {  // scale factors = 1.0 in columns 480..511
+#pragma unroll
+    for (uint32_t c = kSfCol; c < 512; c += 8) {
+      uint32_t ta = tm + (((warp & 3u) * 32u) << 16) + c, v = 0x7f7f7f7fu;
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(ta), "r"(v) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();      // barriers initialised and scale factors written in both CTAs
+  tc_fence_after();
+
+  const uint32_t itiles = p.itiles, ntiles = p.ntiles;
+  const uint32_t ipairs = (itiles + 1) / 2;
+  const uint32_t nunits = p.nsys * ipairs;       // (system, pair of row tiles)
+  const uint32_t unit0 = blockIdx.x >> 1, ustep = gridDim.x >> 1;
+  const uint32_t vend = p.reg[p.nreg - 1].v0 + p.reg[p.nreg - 1].ncols;
+  auto tile_width = [&](uint32_t nt) {             // MMA N of column tile nt (multiple of 16)
+    const uint32_t rest = vend - nt * kHalfN;
+    return rest >= (uint32_t)kHalfN ? (uint32_t)kHalfN : ((rest + 15u) & ~15u);
+  };
+
+  if (warp == kProdWarp) {
+    // ------------------------------------------------------------ producer: this CTA's half of every B block
+    const bool leader = elect_one();
+    const uint32_t b_dst0 = smem_addr(smB);
+    uint32_t s = 0, ph = 0;
+    bool ok = true;
+    for (uint32_t su = unit0; su < nunits && ok; su += ustep) {
+      const uint32_t sys = su / ipairs;
+      const uint8_t *src0 = p.Dx + (size_t)sys * ntiles * kUSteps * kHBlock;
+      for (uint32_t q = 0; q < ntiles * (uint32_t)kUStages && ok; q++) {
+        const uint32_t nt = update_tile_at(q / kUStages, ntiles), cs = q % kUStages;
+        const uint32_t hbytes = tile_width(nt) * 16u;                 // N/2 columns x 32 bytes
+        const uint8_t *src = src0 + ((size_t)nt * kUSteps + cs * kUSPS) * kHBlock + (size_t)rank * hbytes;
+        if (!mbar_wait(b_empty(s), ph ^ 1u, p.status)) { ok = false; break; }
+        if (leader) {
+          if (p.dbg & 1) {
+            mbar_arrive(b_full(s));
+          } else {
+            mbar_arrive_expect_tx(b_full(s), kUSPS * hbytes);
+#pragma unroll
+            for (int u = 0; u < kUSPS; u++)
+              bulk_g2s(b_dst0 + s * kU2BStage + u * kU2HBlock, src + (size_t)u * kHBlock, hbytes, b_full(s));
+          }
+        }
+        if (++s == (uint32_t)kU2Stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == kMmaWarp && rank != 0) {
+    // ------------------------------------------------------------ CTA 1: relay "my half has landed" to CTA 0
+    const bool leader = elect_one();
+    uint32_t s = 0, ph = 0;
+    bool ok = true;
+    for (uint32_t su = unit0; su < nunits && ok; su += ustep) {
+      for (uint32_t q = 0; q < ntiles * (uint32_t)kUStages && ok; q++) {
+        if (!mbar_wait(b_full(s), ph, p.status)) { ok = false; break; }
+        if (leader) mbar_arrive_cluster(map_to_cta(b_full(s), 0));
+        if (++s == (uint32_t)kU2Stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ------------------------------------------------------------ CTA 0: MMA issuer for the pair
+    const bool leader = elect_one();
+    // A,B = E2M1 (1), K-major, scales UE8M0, M = 256 (pair), K = 64; N per tile
+    const uint32_t idesc0 = (1u << 7) | (1u << 10) | (1u << 23) | ((256u >> 4) << 24);
+    const uint64_t a_desc0 = umma_desc(smem_addr(smA), kALbo, kASbo);
+    const uint64_t b_desc0 = umma_desc(smem_addr(smB));
+    const uint32_t sfa = tm + kSfCol, sfb = tm + kSfCol + 16;
+    uint32_t s = 0, ph = 0, tile_iter = 0, unit_iter = 0;
+    bool ok = true;
+    for (uint32_t su = unit0; su < nunits && ok; su += ustep, unit_iter++) {
+      for (uint32_t j = 0; j < ntiles && ok; j++, tile_iter++) {
+        const uint32_t nt = update_tile_at(j, ntiles);
+        const uint32_t ab = tile_iter & 1u;
+        const bool first = j == 0, last = j + 1 == ntiles;
+        if (!mbar_wait(tmem_empty(ab), ((tile_iter >> 1) & 1u) ^ 1u, p.status)) { ok = false; break; }
+        tc_fence_after();
+        const uint32_t acc0 = tm + ab * kHalfN;
+        const uint32_t idesc = idesc0 | ((tile_width(nt) >> 3) << 17);
+#pragma unroll
+        for (int cs = 0; cs < kUStages; cs++) {
+          if (first) {                                      // this stage's part of the pair's A operands is built
+            if (!mbar_wait(a_full(cs), unit_iter & 1u, p.status)) { ok = false; break; }
+          }
+          if (!mbar_wait(b_full(s), ph, p.status)) { ok = false; break; }
+          tc_fence_after();
+          if (leader) {
+            const uint64_t bd = b_desc0 + (uint64_t)((s * kU2BStage) >> 4);
+#pragma unroll
+            for (int u = 0; u < kUSPS; u++) {
+              const int step = cs * kUSPS + u;
+              umma_mxf4_2(acc0, a_desc0 + (uint64_t)((step * kATile) >> 4), bd + (uint64_t)((u * kU2HBlock) >> 4), idesc,
+                          step > 0 ? 1u : 0u, sfa, sfb);
+            }
+            tc_commit2(b_empty(s));
+            if (last) tc_commit2(a_empty(cs));
+          }
+          if (++s == (uint32_t)kU2Stages) { s = 0; ph ^= 1u; }
+        }
+        if (ok && leader) tc_commit2(tmem_full(ab));
+      }
+    }
+  } else if (warp >= (uint32_t)kBuild0 && warp < (uint32_t)(kBuild0 + kBuilderWarps)) {
+    // ------------------------------------------------------------ A builders: this CTA's row tile of the pair
+    const uint32_t b = warp - kBuild0;
+    const uint32_t i = lane >> 1, q = lane & 1u;
+    const uint4 *lutc = lut_copy(lut, lane);
+    uint32_t unit_iter = 0;
+    bool ok = true;
+    for (uint32_t su = unit0; su < nunits && ok; su += ustep, unit_iter++) {
+      const uint32_t sys = su / ipairs, it = 2 * (su - sys * ipairs) + rank;
+      const uint32_t row = it * kRowsI + i;
+      const uint8_t *crow = p.C + (size_t)sys * p.c_ss + (size_t)row * p.c_stride + 4 * q;
+      uint32_t cw[kUStages];
+#pragma unroll
+      for (int k = 0; k < kUStages; k++) {
+        const uint32_t step = k * kUSPS + b;
+        cw[k] = (row < p.M && step * kStepJ + 4 * q < p.Kc) ? __ldg(reinterpret_cast<const uint32_t *>(crow + step * kStepJ)) : 0u;
+      }
+#pragma unroll
+      for (int h = 0; h < kUStages; h++) {
+        if (!mbar_wait_warp(a_empty(h), (unit_iter & 1u) ^ 1u, p.status)) { ok = false; break; }
+        if (!(p.dbg & 2)) {
+          const uint32_t step = h * kUSPS + b;
+          build_a_step(lutc, cw[h], reinterpret_cast<uint4 *>(smA + step * kATile + i * kASbo + q * kALbo));
+          fence_async_smem();
+        }
+        mbar_arrive_cluster(map_to_cta(a_full(h), 0));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 6..13): this CTA's rows
+    using ET = EpiTile<kHalfN>;
+    auto tile_of = [&](uint32_t su, uint32_t nt, ET &e) {
+      const uint32_t sys = su / ipairs, it = 2 * (su - sys * ipairs) + rank;
+      e.set(warp, lane, p.reg, p.nreg, sys, nt, it, p.M);
+    };
+    ET cur, nxt;
+    uint32_t old_cur[ET::kC0], old_nxt[ET::kC0];
+    if (unit0 < nunits && ntiles > 0) {
+      tile_of(unit0, 0, nxt);
+      nxt.load_old(old_nxt, p.accumulate);
+    }
+    uint32_t tile_iter = 0;
+    bool ok = true;
+    for (uint32_t su = unit0; su < nunits && ok; su += ustep) {
+      for (uint32_t j = 0; j < ntiles; j++, tile_iter++) {
+        cur = nxt;
+#pragma unroll
+        for (int k = 0; k < ET::kC0; k++) old_cur[k] = old_nxt[k];
+        if (j + 1 < ntiles) {
+          nxt.set_tile(update_tile_at(j + 1, ntiles));
+          nxt.load_old(old_nxt, p.accumulate);
+        } else if (su + ustep < nunits) {
+          tile_of(su + ustep, 0, nxt);
+          nxt.load_old(old_nxt, p.accumulate);
+        }
+        const uint32_t ab = tile_iter & 1u, use = tile_iter >> 1;
+        if (!mbar_wait_warp(tmem_full(ab), use & 1u, p.status, 32)) { ok = false; break; }
+        tc_fence_after();
+        if (!(p.dbg & 4)) epilogue_tile<kHalfN>(tm, ab * kHalfN, warp, lane, cur, old_cur, nullptr);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(map_to_cta(tmem_empty(ab), 0));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();      // no CTA leaves while its peer may still signal its barriers or read its shared memory
+  if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tm) : "memory");
+}
+
 // K-steps of one tile: ceil(Kc / 8) rounded up to whole pipeline stages of `sps` steps
 inline uint32_t ksteps_for(uint32_t Kc, uint32_t sps) {
   uint32_t k = (Kc + kStepJ - 1) / kStepJ;

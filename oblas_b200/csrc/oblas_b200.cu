@@ -763,6 +763,7 @@ int tc_prepare(int **dstatus) {
     CK(cudaFuncSetAttribute(apply_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<2>::kSmemBytes));
     CK(cudaFuncSetAttribute(update_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
     CK(cudaFuncSetAttribute(update_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
+    CK(cudaFuncSetAttribute(update_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kU2SmemBytes));
     attr_set = true;
   }
   CK(cudaHostGetDevicePointer((void **)dstatus, g.tc_status, 0));
@@ -818,7 +819,32 @@ int tc_launch(const ob2::tc::ApplyTcArgs &a, int nh) {
     const uint64_t nunits = (uint64_t)a.nsys * a.itiles;
     grid = (uint32_t)g.sm_count;
     if (nunits < grid) grid = (uint32_t)nunits;
-    if (a.prof) update_tc_kernel<true><<<grid, kThreads, kUSmemBytes, g.stream>>>(a);
+    // OBLAS_B200_TC_PAIR=1: the CTA-pair variant (tcgen05 cta_group::2).  Bit-exact (the whole GPU suite
+    // passes on it) but as built 1.75x slower than the single-CTA kernel -- see DESIGN.md 4.5 -- so off by default.
+    static const bool pair = getenv("OBLAS_B200_TC_PAIR") && atoi(getenv("OBLAS_B200_TC_PAIR")) != 0;
+    if (pair && !a.prof) {
+      // CTA pairs (cta_group::2): a cluster of 2 per pair of row tiles
+      const uint64_t npairs = (uint64_t)a.nsys * ((a.itiles + 1) / 2);
+      grid = (uint32_t)g.sm_count & ~1u;
+      // a persistent kernel must not launch more clusters than can be resident at once
+      static int max_clusters = -1;
+      if (max_clusters < 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kU2SmemBytes;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, update_tc2_kernel, &cfg) != cudaSuccess) {
+          cudaGetLastError();
+          max_clusters = (int)grid / 2;
+        }
+        if (getenv("OBLAS_B200_TRACE")) fprintf(stderr, "oblas_b200: update_tc2_kernel: %d clusters of 2 resident\n", max_clusters);
+      }
+      if (max_clusters > 0 && (uint32_t)(2 * max_clusters) < grid) grid = (uint32_t)(2 * max_clusters);
+      if (2 * npairs < grid) grid = (uint32_t)(2 * npairs);
+      update_tc2_kernel<<<grid, kThreads, kU2SmemBytes, g.stream>>>(a);
+    } else if (a.prof) update_tc_kernel<true><<<grid, kThreads, kUSmemBytes, g.stream>>>(a);
     else update_tc_kernel<false><<<grid, kThreads, kUSmemBytes, g.stream>>>(a);
   }
   return after_launch("apply (tcgen05)");

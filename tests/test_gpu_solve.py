@@ -3,6 +3,7 @@ streaming variant) against the oracle / the compiled reference, bit for bit, and
 BASELINE.json's full size through properties that do not need the CPU to redo the
 work (A -> I, A_orig * X == B_orig on sampled rows)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -13,6 +14,8 @@ from gpu_helpers import dev, gf256_vecmat, host
 from helpers import (GF2, GF4, GF16, GF256, FIELD_BITS, field_row_bytes, mat_view, oracle, oracle_solve, ptr,
                      random_matrix, reference, splitmix_bytes, u32p)
 from oblas_b200 import capi, device
+
+ROOT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
@@ -268,3 +271,44 @@ def test_tensor_core_path_equals_table_kernel_at_mid_sizes(rows, cols, b_bytes, 
         assert torch.equal(tb, cb)
     if deficient:
         assert int(trank[0]) < min(rows, cols)
+
+
+_pair_checked = False
+
+
+def test_cta_pair_update_kernel_in_a_subprocess():
+    """OBLAS_B200_TC_PAIR=1 switches the rank-128 update to CTA pairs (tcgen05 cta_group::2, multicast
+    commits, remote barrier arrives); the switch is read once per process, so a child process runs a
+    tensor-core elimination on it and compares every byte with the table kernel"""
+    import subprocess
+    import sys
+    global _pair_checked
+    if _pair_checked:
+        pytest.skip("once per module is enough (the child process sets its own tuning)")
+    _pair_checked = True
+    code = r"""
+import os, sys
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+import torch
+from oblas_b200 import capi, device
+device.bind(0)
+lib = capi.lib()
+for rows, cols, L, nsys in ((640, 640, 272, 3), (530, 700, 96, 2)):
+    ab = (cols + 15) // 16 * 16
+    A = torch.empty((nsys, rows, ab), dtype=torch.uint8, device="cuda"); device.fill_random(A, 11 + rows)
+    if ab > cols: A[:, :, cols:] = 0
+    A[0, 5] = A[0, 3] ^ A[0, 4]
+    B = torch.empty((nsys, rows, L), dtype=torch.uint8, device="cuda"); device.fill_random(B, 12 + rows)
+    out = []
+    for geo in (1, 3):
+        lib.oblas_b200_set_tuning(geo, -1)
+        a, b = A.clone(), B.clone()
+        r, pv = device.solve_batch(capi.GF256, a, cols, b, want_pivcols=True)
+        capi.check(lib.oblas_b200_sync(), "sync")
+        out.append((a, b, r))
+    assert torch.equal(out[0][2], out[1][2]) and torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+print("pair ok")
+""" % (ROOT_DIR, ROOT_DIR)
+    env = dict(os.environ, OBLAS_B200_TC_PAIR="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0 and "pair ok" in r.stdout, r.stdout[-2000:]
