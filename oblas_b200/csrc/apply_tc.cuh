@@ -1101,7 +1101,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) update_
       mbar_init(b_empty(s), 1);                  // multicast commit
     }
     for (uint32_t s = 0; s < (uint32_t)kUStages; s++) {
-      mbar_init(a_full(s), 2 * 32 * kBuilderWarps);   // builders of both CTAs (used in CTA 0 only)
+      mbar_init(a_full(s), 2 * kBuilderWarps);        // one arrive per builder warp of both CTAs (CTA 0 only)
       mbar_init(a_empty(s), 1);
     }
     for (uint32_t b = 0; b < 2; b++) {
@@ -1249,7 +1249,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) update_
           build_a_step(lutc, cw[h], reinterpret_cast<uint4 *>(smA + step * kATile + i * kASbo + q * kALbo));
           fence_async_smem();
         }
-        mbar_arrive_cluster(map_to_cta(a_full(h), 0));
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(map_to_cta(a_full(h), 0));
       }
     }
   } else {
