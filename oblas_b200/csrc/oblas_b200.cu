@@ -802,6 +802,16 @@ int tc_ws_reserve(size_t need) {
   g.tc_ws_bytes = slot->bytes;
   return 0;
 }
+// OBLAS_B200_TC_DEBUG switches parts of the tensor-core kernels off (timing experiments: results are
+// WRONG).  Only honoured by builds made for that purpose: make EXTRA=-DOB2_TC_TIMING_EXPERIMENTS
+static int tc_debug_switches() {
+#ifdef OB2_TC_TIMING_EXPERIMENTS
+  static const int v = getenv("OBLAS_B200_TC_DEBUG") ? atoi(getenv("OBLAS_B200_TC_DEBUG")) : 0;
+  return v;
+#else
+  return 0;
+#endif
+}
 // persistent launch of the tcgen05 GEMM kernel: one CTA per SM.  nh = half tiles (240 byte
 // columns) per tile: 2 = one accumulator set, long inner dimension; 1 = double-buffered accumulators
 int tc_launch(const ob2::tc::ApplyTcArgs &a, int nh) {
@@ -891,7 +901,7 @@ int apply_tc_run(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, con
     a.reg[0].base = Y; a.reg[0].rs = y_stride; a.reg[0].ss = 0; a.reg[0].col0 = n0; a.reg[0].ncols = ncols;
     a.reg[0].v0 = 0; a.nreg = 1;
     a.accumulate = accumulate; a.status = dstatus;
-    { const char *dv = getenv("OBLAS_B200_TC_DEBUG"); a.dbg = dv ? atoi(dv) : 0; }
+    a.dbg = tc_debug_switches();
     if (tc_launch(a, 2)) return -1;
   }
   return 0;
@@ -1070,7 +1080,7 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
       a.ksteps = ksteps; a.ntiles = ntiles; a.itiles = itiles; a.nsys = cnt;
       a.reg[0] = reg[0]; a.reg[1] = reg[1]; a.nreg = nreg;
       a.accumulate = 1; a.status = dstatus; a.prof = g.d_uprof;
-      { const char *dv = getenv("OBLAS_B200_TC_DEBUG"); a.dbg = dv ? atoi(dv) : 0; }
+      a.dbg = tc_debug_switches();
       {
         TcTimer tt(2);
         if (tc_launch(a, getenv("OBLAS_B200_TC_STREAM_A") ? 1 : 0)) return -1;

@@ -1,6 +1,8 @@
 """Per-kernel-class device times of the tensor-core elimination on one shape:
-python tools/tc_classes.py [nsys K L]   (OBLAS_B200_TC_DEBUG=1|2|4 switches parts of the update
-kernel off for timing experiments -- results are then invalid, only the times mean something)"""
+python tools/tc_classes.py [nsys K L]   (UPROF=1 adds the role cycle counters of the update kernel.
+OBLAS_B200_TC_DEBUG=1|2|4 switches the loads / the A build / the epilogue of the update kernel off for
+timing experiments -- results are then invalid, only the times mean something -- and needs a library
+built with  make -C oblas_b200/csrc EXTRA=-DOB2_TC_TIMING_EXPERIMENTS)"""
 import ctypes as C
 import os
 import sys
