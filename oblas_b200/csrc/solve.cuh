@@ -98,6 +98,8 @@ struct SolveSmem {
     s += (size_t)NPIV * 2 + 16;                // piv_phys (u16)
     s += (size_t)2 * EXP * NBW * 4 + 16;       // prow / vrow basis
     s += 128 + 256;                            // scalars + inverse table of the field
+    s += (size_t)NB * NBW * 4;                 // look-ahead: pivots' vectors
+    s += ((size_t)rows + 15) / 16 * 16;        // look-ahead: candidate flags
     return (s + 15) / 16 * 16;
   }
 };
@@ -213,6 +215,28 @@ OB2_D void panel_fast_candidates(const uint32_t *pan, uint16_t *pos2phys, uint16
                                  uint32_t *vrow, uint32_t *scal, uint32_t *Mb, uint32_t t, uint32_t rows,
                                  uint32_t c0, uint32_t *pivcols_sys, const uint8_t *inv_tab, FastCand<NBW> &fc);
 
+template <int NBW> struct FastChain;
+template <int EXP, int NBW>
+OB2_D void chain_init(FastChain<NBW> &c, const uint32_t *pan, const uint16_t *pos2phys, uint32_t t, uint32_t rows);
+template <int EXP, int NBW>
+OB2_D void chain_run(FastChain<NBW> &c, uint32_t *prow, uint32_t *vrow, uint32_t *scal, const uint8_t *inv_tab,
+                     const uint32_t *done, uint32_t done_target);
+
+// Look-ahead of the table kernel (solve_kernel), whose trailing update is a SEQUENCE of tile passes:
+// the candidate elimination of the next panel is a resumable chain (FastChain, state in the registers
+// of the candidate group).  It starts in the pass over the tile that holds the next panel's bytes and
+// runs beside every following pass for as long as the streaming warps are busy (they count themselves
+// done in *done; the chain pauses between two columns once all have); whatever is left is finished
+// after the last pass.  Nothing the passes read is written before chain_finish.
+struct LookChain {
+  uint32_t t_next;
+  const uint8_t *inv_tab;
+  const uint16_t *pos2phys;
+  uint32_t *prow, *vrow, *scal;
+  uint8_t *is_cand;              // [rows] shared-memory flags, all zero outside update_tile
+  uint32_t *done;                // streaming warps that have finished the current pass
+};
+
 // Look-ahead of the outer-panel factorisation (panel_kernel): while the other warps stream the tile
 // pass of inner step q, the candidate group (the first NBT threads) first brings the NEXT panel's
 // chunk of the next step's candidate rows up to date and then runs that step's candidate elimination
@@ -234,7 +258,8 @@ OB2_D void update_tile(uint8_t *base, size_t rs, uint32_t rows, uint32_t tile_of
                        uint32_t tile_bytes, uint32_t npiv, const uint16_t *piv_phys,
                        const uint32_t *V, uint4 *tab, uint32_t *pan_next, uint32_t pan_off,
                        const TileAlt alt = TileAlt(), const LookAhead *look = nullptr,
-                       FastCand<NBW> *fc = nullptr) {
+                       FastCand<NBW> *fc = nullptr, const LookChain *lc = nullptr,
+                       FastChain<NBW> *chain = nullptr) {
   using G = Geo<NBW, KB, WT>;
   auto chunk_ptr = [&](uint32_t r, uint32_t ch) -> uint8_t * {
     return ch < alt.split ? alt.base2 + (size_t)r * alt.rs2 + ch * 16 : base + (size_t)r * rs + tile_off + ch * 16;
@@ -247,16 +272,28 @@ OB2_D void update_tile(uint8_t *base, size_t rs, uint32_t rows, uint32_t tile_of
   const uint32_t nbasis = npiv * EXP;                  // basis rows in use
   // look-ahead: the candidate group leaves the streaming loop to the other threads
   constexpr uint32_t LNBT = FastGeo<EXP, NBW>::NBT;
-  const bool la_thread = look != nullptr && tid < LNBT;
+  const bool la_thread = (look != nullptr || lc != nullptr) && tid < LNBT;
+  // (table kernel) the chain starts in the pass over the tile that holds the next panel's bytes
+  const bool lc_first = lc != nullptr && pan_next != nullptr && pan_off >= tile_off && pan_off < tile_off + tile_bytes;
   uint32_t la_phys = 0;
   bool la_have = false;
-  if (la_thread) {
+  if (la_thread && look) {
     la_have = look->t_next + tid < rows;
     if (la_have) {
       la_phys = look->pos2phys[look->t_next + tid];
       look->is_cand[la_phys] = 1;
     }
     if (tid == 0) look->scal[2] = 0;                   // fail flag of the candidate elimination
+  }
+  if (la_thread && lc) {
+    if (lc_first) {
+      la_have = lc->t_next + tid < rows;
+      if (la_have) {
+        la_phys = lc->pos2phys[lc->t_next + tid];
+        lc->is_cand[la_phys] = 1;
+      }
+    }
+    if (tid == 0) *lc->done = 0;
   }
 
   // (a) tables, straight from global memory, no shared-memory reads
@@ -291,11 +328,11 @@ OB2_D void update_tile(uint8_t *base, size_t rs, uint32_t rows, uint32_t tile_of
   // chunk holds the NEXT panel's bytes also writes the updated chunk into the shared-memory
   // panel, so the next panel factorisation starts without a global gather.
   // with look-ahead the streaming threads are tid >= LNBT, renumbered from 0 (T - LNBT is a multiple of CW)
-  const uint32_t stid = look ? tid - LNBT : tid, ST = look ? T - LNBT : T;
+  const uint32_t stid = (look || lc) ? tid - LNBT : tid, ST = (look || lc) ? T - LNBT : T;
   const uint32_t my_ch = stid % CW;
   const bool pan_lane = pan_next != nullptr && pan_off >= tile_off + my_ch * 16 &&
                         pan_off < tile_off + my_ch * 16 + 16 && pan_off < tile_off + tile_bytes;
-  if (la_thread) {
+  if (la_thread && (look || lc_first)) {
     // the next panel's chunk of this thread's candidate row, then the next step's candidate elimination
     const uint32_t ch = (pan_off - tile_off) >> 4;
     if (la_have) {
@@ -323,13 +360,24 @@ OB2_D void update_tile(uint8_t *base, size_t rs, uint32_t rows, uint32_t tile_of
       }
     }
     OB2_NAMED_BAR(1, LNBT);
-    panel_fast_candidates<EXP, NBW>(pan_next, look->pos2phys, look->piv_phys, look->prow, look->vrow, look->scal,
-                                    look->Mb, look->t_next, rows, look->c0_next, look->pivcols_sys, look->inv_tab, *fc);
-    __syncthreads();  // tables are rebuilt by the next tile; the streaming threads are done with the flags
-    if (la_have) look->is_cand[la_phys] = 0;   // (next reader: the next update_tile, block barriers away)
+    if (look) {
+      panel_fast_candidates<EXP, NBW>(pan_next, look->pos2phys, look->piv_phys, look->prow, look->vrow, look->scal,
+                                      look->Mb, look->t_next, rows, look->c0_next, look->pivcols_sys, look->inv_tab, *fc);
+      __syncthreads();  // tables are rebuilt by the next tile; the streaming threads are done with the flags
+      if (la_have) look->is_cand[la_phys] = 0;   // (next reader: the next update_tile, block barriers away)
+      return;
+    }
+    chain_init<EXP, NBW>(*chain, pan_next, lc->pos2phys, lc->t_next, rows);
+  }
+  if (la_thread) {   // table kernel: run the chain beside this pass
+    chain_run<EXP, NBW>(*chain, lc->prow, lc->vrow, lc->scal, lc->inv_tab, lc->done, (T - LNBT) / 32);
+    // tell the block whether the chain still needs the candidate group in the next pass
+    if (tid == 0) lc->scal[14] = (chain->failed || chain->j >= (uint32_t)FastGeo<EXP, NBW>::NPIV) ? 1u : 0u;
+    __syncthreads();
+    if (lc_first && la_have) lc->is_cand[la_phys] = 0;
     return;
   }
-  const uint8_t *is_cand = look ? look->is_cand : nullptr;
+  const uint8_t *is_cand = look ? look->is_cand : (lc_first ? lc->is_cand : nullptr);
   auto fetch = [&](uint32_t it) {
     Item m;
     m.r = it / CW;
@@ -373,6 +421,12 @@ OB2_D void update_tile(uint8_t *base, size_t rs, uint32_t rows, uint32_t tile_of
     apply(c1);
     c0 = n0;
     c1 = n1;
+  }
+  if (lc) {   // this warp is done streaming: the look-ahead chain pauses once all are
+#ifndef OB2_EMU
+    __syncwarp();
+#endif
+    if ((stid & 31u) == 0) atomicAdd(lc->done, 1u);
   }
   __syncthreads();  // tables are rebuilt by the next tile
 }
@@ -578,6 +632,136 @@ OB2_D void panel_fast_candidates(const uint32_t *pan, uint16_t *pos2phys, uint16
   fc.E = E;
 }
 
+// The same candidate elimination as a resumable chain (table kernel look-ahead): chain_init loads the
+// candidate rows, chain_run eliminates columns until all NPIV are done, no pivot is found, or -- checked
+// between two columns, uniformly over the group -- *done has reached done_target; chain_finish
+// publishes what panel_fast_candidates publishes.  All three: threads tid < NBT only.
+template <int NBW>
+struct FastChain {
+  PanelVec<NBW> blk, E;
+  uint32_t mypos = 0, phys = 0, j = 0;
+  int my_col = -1;
+  bool have = false, failed = false, active = false;
+};
+template <int EXP, int NBW>
+OB2_D void chain_init(FastChain<NBW> &c, const uint32_t *pan, const uint16_t *pos2phys, uint32_t t, uint32_t rows) {
+  constexpr uint32_t NBT = FastGeo<EXP, NBW>::NBT;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t ncand = (rows - t < NBT) ? (rows - t) : NBT;
+  c.have = tid < ncand;
+  c.phys = c.have ? pos2phys[t + tid] : 0;
+#pragma unroll
+  for (int w = 0; w < NBW; w++) {
+    c.blk.w[w] = c.have ? pan[c.phys * NBW + w] : 0;
+    c.E.w[w] = 0;
+  }
+  c.mypos = tid;
+  c.j = 0;
+  c.my_col = -1;
+  c.failed = false;
+  c.active = true;
+}
+template <int EXP, int NBW>
+OB2_D void chain_run(FastChain<NBW> &c, uint32_t *prow, uint32_t *vrow, uint32_t *scal, const uint8_t *inv_tab,
+                     const uint32_t *done, uint32_t done_target) {
+  constexpr int NPIV = FastGeo<EXP, NBW>::NPIV;
+  constexpr uint32_t EMASK = (1u << EXP) - 1u;
+  constexpr uint32_t NBT = FastGeo<EXP, NBW>::NBT;
+  constexpr uint32_t NONE = 0xffffffffu;
+  const uint32_t tid = threadIdx.x;
+  if (!c.active || c.failed) return;
+  for (; c.j < (uint32_t)NPIV; c.j++) {
+    const uint32_t j = c.j;
+    const uint32_t wj = (j * EXP) >> 5, sh = (j * EXP) & 31;
+    const uint32_t e = (pick_word<NBW>(c.blk, wj) >> sh) & EMASK;
+    const uint32_t wmin = warp_min((c.have && c.mypos >= j && e) ? c.mypos : NONE);
+    uint32_t *slots = scal + 16 + (j & 1) * 8;
+    if ((tid & 31u) == 0) slots[tid >> 5] = wmin;
+    if (tid == 0) scal[12] = (done && atomicAdd(const_cast<uint32_t *>(done), 0u) >= done_target) ? 1u : 0u;
+    OB2_NAMED_BAR(1, NBT);
+    if (scal[12]) {            // the streaming warps are waiting: pause before this column (uniform)
+      OB2_NAMED_BAR(1, NBT);   // (everybody has read scal[12] before thread 0 may rewrite it)
+      return;
+    }
+    uint32_t pv = NONE;
+#pragma unroll
+    for (uint32_t k = 0; k < NBT / 32; k++) pv = slots[k] < pv ? slots[k] : pv;
+    if (pv == NONE) {
+      c.failed = true;
+      return;
+    }
+    const bool is_piv = c.have && c.mypos == pv;
+    if (c.have) {
+      if (is_piv) c.mypos = j;
+      else if (c.mypos == j) c.mypos = pv;
+    }
+    if (is_piv) {
+      c.my_col = (int)j;
+#pragma unroll
+      for (int w = 0; w < NBW; w++) {
+        uint32_t unit = (((j * EXP) >> 5) == (uint32_t)w) ? (1u << ((j * EXP) & 31)) : 0u;
+        scal[4 + w] = c.blk.w[w];
+        scal[4 + NBW + w] = c.E.w[w] ^ unit;
+      }
+      scal[3] = (EXP == 1) ? 1u : (uint32_t)inv_tab[e];
+    }
+    OB2_NAMED_BAR(1, NBT);
+    if (tid < (uint32_t)(EXP * 2 * NBW)) {
+      const uint32_t q = tid / (2 * NBW), w2 = tid % (2 * NBW);
+      uint32_t sq = scal[3];
+      for (uint32_t k = 0; k < q; k++) sq = xtime<EXP>(sq) & EMASK;
+      const uint32_t val = mul_scalar_word<EXP>(scal[4 + w2], sq);
+      if (w2 < (uint32_t)NBW) prow[q * NBW + w2] = val;
+      else vrow[q * NBW + (w2 - NBW)] = val;
+    }
+    OB2_NAMED_BAR(1, NBT);
+    if (is_piv) {
+      c.blk = ldv<NBW>(prow);
+      c.E = ldv<NBW>(vrow);
+    }
+    if (c.have && !is_piv) {
+      const uint32_t f = (pick_word<NBW>(c.blk, wj) >> sh) & EMASK;
+      if (f) {
+#pragma unroll
+        for (int q = 0; q < EXP; q++) {
+          uint32_t m = 0u - ((f >> q) & 1u);
+          PanelVec<NBW> pb = ldv<NBW>(prow + q * NBW), vb = ldv<NBW>(vrow + q * NBW);
+#pragma unroll
+          for (int w = 0; w < NBW; w++) {
+            c.blk.w[w] ^= m & pb.w[w];
+            c.E.w[w] ^= m & vb.w[w];
+          }
+        }
+      }
+    }
+  }
+}
+template <int EXP, int NBW>
+OB2_D void chain_finish(FastChain<NBW> &c, uint16_t *pos2phys, uint16_t *piv_phys, uint32_t *Mb, uint32_t *scal,
+                        uint32_t t, uint32_t c0, uint32_t *pivcols_sys, FastCand<NBW> &fc) {
+  const uint32_t tid = threadIdx.x;
+  if (c.failed) {
+    if (tid == 0) scal[2] = 1;
+  } else if (c.have) {
+    pos2phys[t + c.mypos] = (uint16_t)c.phys;
+    if (c.my_col >= 0) {
+      piv_phys[c.my_col] = (uint16_t)c.phys;
+      if (pivcols_sys) pivcols_sys[t + c.my_col] = c0 + (uint32_t)c.my_col;
+      PanelVec<NBW> x = c.E;
+#pragma unroll
+      for (int q = 0; q < EXP; q++) {
+        stv<NBW>(Mb + ((uint32_t)c.my_col * EXP + q) * NBW, x);
+#pragma unroll
+        for (int w = 0; w < NBW; w++) x.w[w] = xtime<EXP>(x.w[w]);
+      }
+    }
+  }
+  fc.my_col = c.my_col;
+  fc.phys = c.phys;
+  fc.E = c.E;
+  c.active = false;
+}
+
 // Part 2, all threads, after a block barrier: V of every row from the pivots' vectors (Mb).
 // T2: [NB/4][16][T2C copies][NBW] -- lane l reads copy l % T2C, so the 8 lanes of a 128-bit
 // shared-memory phase always hit 8 different 16-byte bank groups whatever their table indices are
@@ -693,8 +877,11 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
   uint32_t *vrow = reinterpret_cast<uint32_t *>(sp);       sp += (size_t)EXP * NBW * 4;   // x^b * its V
   uint32_t *scal = reinterpret_cast<uint32_t *>(sp);       // [0] search result, [1] flag
   uint8_t *inv_s = reinterpret_cast<uint8_t *>(scal + 32);  // field inverses (a global load per pivot is 1/3 of a column step)
+  uint32_t *Mb = reinterpret_cast<uint32_t *>(inv_s + 256);   // [NB][NBW] pivots' vectors of the look-ahead (not in the table area)
+  uint8_t *is_cand = reinterpret_cast<uint8_t *>(Mb + NB * NBW);   // [rows] look-ahead flags
   if (EXP > 1)
     for (uint32_t k = threadIdx.x; k < (1u << EXP); k += blockDim.x) inv_s[k] = p.inv[k];
+  for (uint32_t k = threadIdx.x; k < p.rows; k += blockDim.x) is_cand[k] = 0;
   __syncthreads();
 
   // phase clock (diagnostics only): 0 panel load, 1 panel factorisation, 2 trailing update,
@@ -724,6 +911,9 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
     for (uint32_t r = tid; r < rows; r += T) pos2phys[r] = (uint16_t)r;
     uint32_t t = 0;  // pivots found so far == next pivot position (uniform)
     bool pan_ready = false;  // panel already written into shared memory by the previous update
+    bool la_done = false;    // look-ahead: this panel's candidate elimination is already done
+    FastCand<NBW> fc;
+    FastChain<NBW> chain;
     __syncthreads();
 
     for (uint32_t pi = 0; pi < npanels && t < rows; pi++) {
@@ -744,10 +934,17 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
       uint32_t n = 0;
       constexpr uint32_t kFastThreads = (uint32_t)((NPIV + 32 + 31) / 32 * 32);
       bool fast = false;
-      if (ncols_p == (uint32_t)NPIV && rows - t >= (uint32_t)NPIV && kFastThreads <= T && !p.no_fast_panel)
+      if (la_done) {
+        // the candidate rows of this panel were eliminated beside the previous trailing update
+        long long pf_t = 0;
+        panel_fast_finish<EXP, NBW, SM::T2C>(pan, V, reinterpret_cast<uint32_t *>(tab) + NB * NBW, Mb, fc, rows, nullptr, pf_t);
+        fast = true;
+      } else if (ncols_p == (uint32_t)NPIV && rows - t >= (uint32_t)NPIV && kFastThreads <= T && !p.no_fast_panel) {
         fast = panel_fast<EXP, NBW, SM::T2C>(pan, V, pos2phys, piv_phys, prow, vrow, scal,
                                     reinterpret_cast<uint32_t *>(tab), t, rows, c0,
                                     p.pivcols ? p.pivcols + (size_t)sys * rows : nullptr, inv_s);
+      }
+      la_done = false;
       if (fast) {
         n = NPIV;
         t += NPIV;
@@ -847,16 +1044,40 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
       const uint32_t a_from = (pi * (NBW * 4)) & ~15u;
       // the tile holding the next panel's bytes also refreshes the shared-memory panel
       const uint32_t next_off = (pi + 1 < npanels) ? (pi + 1) * (NBW * 4) : 0xffffffffu;
+      // look-ahead: the next panel is a full one with enough rows left, and there are streaming threads
+      const uint32_t c0n = c0 + NPIV;
+      const bool look_ok = !p.no_fast_panel && !p.no_look_ahead && next_off != 0xffffffffu && next_off < p.a_bytes &&
+                           c0n + NPIV <= p.cols && rows - t >= (uint32_t)NPIV && kFastThreads < T &&
+                           (T - kFastThreads) % G::CW == 0 && (T - kFastThreads) % 32 == 0;
+      LookChain lkc;
+      lkc.t_next = t; lkc.inv_tab = inv_s; lkc.pos2phys = pos2phys; lkc.prow = prow; lkc.vrow = vrow;
+      lkc.scal = scal; lkc.is_cand = is_cand; lkc.done = scal + 13;
+      const LookChain *lcp = look_ok ? &lkc : nullptr;   // null again once the chain is complete: all threads stream
+      if (look_ok && tid == 0) scal[2] = 0;   // fail flag (visible after the first barrier of the first pass)
       for (uint32_t off = a_from; off < p.a_bytes; off += WT) {
         uint32_t w = (p.a_bytes - off < (uint32_t)WT) ? (p.a_bytes - off) : (uint32_t)WT;
-        update_tile<EXP, NBW, KB, WT>(A, p.a_rs, rows, off, w, n, piv_phys, V, tab, pan, next_off);
+        update_tile<EXP, NBW, KB, WT>(A, p.a_rs, rows, off, w, n, piv_phys, V, tab, pan, next_off, TileAlt(), nullptr,
+                                      nullptr, lcp, &chain);
+        if (lcp && scal[14]) lcp = nullptr;
       }
       pan_ready = next_off != 0xffffffffu && next_off < p.a_bytes;
       if (B)
         for (uint32_t off = 0; off < p.b_bytes; off += WT) {
           uint32_t w = (p.b_bytes - off < (uint32_t)WT) ? (p.b_bytes - off) : (uint32_t)WT;
-          update_tile<EXP, NBW, KB, WT>(B, p.b_rs, rows, off, w, n, piv_phys, V, tab, nullptr, 0xffffffffu);
+          update_tile<EXP, NBW, KB, WT>(B, p.b_rs, rows, off, w, n, piv_phys, V, tab, nullptr, 0xffffffffu, TileAlt(),
+                                        nullptr, nullptr, lcp, &chain);
+          if (lcp && scal[14]) lcp = nullptr;
         }
+      if (look_ok) {
+        // whatever the passes left of the chain, then its results (nothing reads piv_phys / the row map any more)
+        if (tid < kFastThreads) {
+          chain_run<EXP, NBW>(chain, prow, vrow, scal, inv_s, nullptr, 0);
+          chain_finish<EXP, NBW>(chain, pos2phys, piv_phys, Mb, scal, t, c0n,
+                                 p.pivcols ? p.pivcols + (size_t)sys * rows : nullptr, fc);
+        }
+        __syncthreads();
+        la_done = scal[2] == 0;
+      }
       tick(2);
     }
     // ---- results ------------------------------------------------------------
@@ -1176,7 +1397,7 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
 }
 
 // look-ahead state of panel_kernel behind the SolveSmem layout: Mb (2 KB) + one flag byte per row
-inline size_t panel_extra_bytes(uint32_t rows) { return (size_t)32 * 4 * 4 * 4 + (((size_t)rows + 15) & ~(size_t)15); }
+inline size_t panel_extra_bytes(uint32_t) { return 0; }   // (Mb and the flags are part of SolveSmem now)
 
 template <int KB, int WT>
 inline int launch_panel_t(const PanelArgs &p, uint32_t grid, size_t smem_limit, cudaStream_t s,

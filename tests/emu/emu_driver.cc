@@ -114,7 +114,8 @@ int emu_solve(int field, uint8_t *A, size_t a_rs, size_t a_ss, uint32_t rows, ui
   p.A = A; p.a_rs = a_rs; p.a_ss = a_ss; p.rows = rows; p.cols = cols; p.a_bytes = a_bytes;
   p.B = B; p.b_rs = b_rs; p.b_ss = b_ss; p.b_bytes = B ? b_bytes : 0;
   p.rank = rank; p.pivcols = pivcols; p.nsys = nsys;
-  p.no_fast_panel = no_fast;
+  p.no_fast_panel = no_fast & 1;
+  p.no_look_ahead = (no_fast >> 1) & 1;
   int ts = table_set_id(field, 1);
   p.inv = ts >= 0 ? g_sets[ts].inv : nullptr;
   if (force_nbw == 2) {

@@ -167,6 +167,28 @@ def test_solve_fast_and_general_panel_paths(args, no_fast):
     _solve(no_fast=no_fast, **args)
 
 
+@pytest.mark.parametrize("args", [
+    # blocks with streaming threads beside the candidate group (NBT = 64 / 64 / 96 / 160 threads for
+    # GF(256) / GF(16) / GF(4) / GF(2)): the next panel's candidate elimination runs as a resumable chain
+    # beside the tile passes of the trailing update (several A tiles and B tiles per panel)
+    dict(field=GF256, rows=150, cols=150, b_bytes=528, seed=501, threads=128),
+    dict(field=GF256, rows=150, cols=150, b_bytes=0, seed=502, threads=128),
+    dict(field=GF256, rows=120, cols=200, b_bytes=64, seed=503, threads=128, deficient=2),
+    dict(field=GF256, rows=200, cols=150, b_bytes=272, seed=504, threads=192, nsys=2),
+    dict(field=GF16, rows=200, cols=200, b_bytes=48, seed=505, threads=128),
+    dict(field=GF16, rows=200, cols=200, b_bytes=48, seed=506, threads=128, deficient=1),
+    dict(field=GF4, rows=260, cols=260, b_bytes=32, seed=507, threads=160),
+    dict(field=GF4, rows=260, cols=260, b_bytes=0, seed=508, threads=160, deficient=2),
+    dict(field=GF2, rows=400, cols=400, b_bytes=32, seed=509, threads=224),
+    dict(field=GF2, rows=300, cols=500, b_bytes=16, seed=510, threads=224),
+    dict(field=GF16, rows=200, cols=200, b_bytes=48, seed=511, threads=128, nbw=2),
+])
+@pytest.mark.parametrize("no_fast", [0, 2])
+def test_solve_look_ahead_chain(args, no_fast):
+    """table kernel with the look-ahead chain on (0) and off (2): same bytes as the oracle"""
+    _solve(no_fast=no_fast, **args)
+
+
 def test_solve_every_row_moves():
     """zero above the anti-diagonal: column c has its first non-zero entry in row n-1-c, so every row
     changes position -- the final row permutation stages all rows (several column blocks) instead of

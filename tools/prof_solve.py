@@ -15,6 +15,7 @@ K = int(sys.argv[4]) if len(sys.argv) > 4 else 1024
 L = int(sys.argv[5]) if len(sys.argv) > 5 else 1280
 device.bind(0)
 capi.lib().oblas_b200_set_tuning(geo, geo)
+capi.lib().oblas_b200_set_panel_path(int(os.environ.get("PANEL_PATH", "0")))   # bit 0: general panel path, bit 1: no look-ahead
 a_bytes = (K * capi.FIELD_BITS[field] // 8 + 15) // 16 * 16
 A0 = torch.empty((nsys, K, a_bytes), dtype=torch.uint8, device="cuda")
 device.fill_random(A0, 3)
