@@ -30,10 +30,15 @@
 //     LDS.128 + XOR per 16 bytes, no per-byte field multiplication at all.  The
 //     tile of every row is streamed HBM/L2 -> registers -> HBM/L2 once per panel
 //     with 128-bit coalesced accesses.
-//  3. after the last panel the rows are permuted into position order.
+//  3. after the last panel the rows that changed position are moved into place.
 //
-// The roofline that bounds step 2 is shared-memory bandwidth: 32 table bytes per
-// 16 GF(256) multiply-adds => 64 byte-MACs/clk/SM at 128 B/clk/SM.
+// Step 1 starts with a chain of dependent column eliminations on a few candidate rows that only
+// the first two or three warps can work on ("fast" factorisation); both kernels here run that chain
+// for the NEXT panel beside step 2 of the current one (look-ahead: LookAhead / LookChain below).
+//
+// The roofline that bounds step 2 is shared-memory bandwidth: one 128-bit look-up per table group
+// and 16-byte chunk; with the default 6-bit groups 22 look-ups per 16 bytes x 16 GF(256) pivots
+// => 93 byte-MACs/clk/SM at 128 B/clk/SM (64 with 4-bit groups).
 #pragma once
 #include "gf_device.cuh"
 
