@@ -228,13 +228,9 @@ OB2_D bool mbar_wait(uint32_t bar, uint32_t parity, int *status, uint32_t backof
   atomicExch(status, 1);
   return false;
 }
-// whole-warp wait: lane 0 polls, the result is broadcast (one poller per warp instead of 32)
-OB2_D bool mbar_wait_warp(uint32_t bar, uint32_t parity, int *status, uint32_t backoff_ns = 0) {
-  uint32_t ok = 1;
-  if ((threadIdx.x & 31u) == 0) ok = mbar_wait(bar, parity, status, backoff_ns) ? 1u : 0u;
-  ok = __shfl_sync(0xffffffffu, ok, 0);
-  return ok != 0;
-}
+// (Every wait is executed by ALL lanes of the waiting warp.  A "lane 0 polls, then broadcasts by shuffle"
+// variant looked cheaper and cost the update kernel 15 %: the divergent single-lane spin loop keeps issuing,
+// the hardware-suspended warp-uniform try_wait does not.)
 OB2_D void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -676,7 +672,7 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
           lo[k] = e[0];
           hi[k] = e[256];
         }
-        if (!mbar_wait_warp(empty_bar(s), ph ^ 1u, p.status)) { ok = false; break; }
+        if (!mbar_wait(empty_bar(s), ph ^ 1u, p.status)) { ok = false; break; }
         if (!(p.dbg & 2)) {
 #pragma unroll
           for (int u = 0; u < kSPS; u++) {
@@ -730,7 +726,9 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
       }
       const uint32_t ab = (K::kAccSets == 2) ? (iter & 1u) : 0u;
       const uint32_t use = (K::kAccSets == 2) ? (iter >> 1) : iter;
-      if (!mbar_wait_warp(tmem_full(ab), use & 1u, p.status, 64)) break;
+      // a long wait (the MMAs of a whole tile): all lanes poll, with a back-off -- measured 105 ms (cfg5) against
+      // 108 without the back-off and 111 with one polling lane + shuffle broadcast
+      if (!mbar_wait(tmem_full(ab), use & 1u, p.status, 64)) break;
       tc_fence_after();
       if (!(p.dbg & 4)) epilogue_tile<kTileN>(tm, ab * kHalfN, warp, lane, cur, old_cur);
       tc_fence_before();
@@ -813,7 +811,7 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
     }
     for (uint32_t b = 0; b < 2; b++) {
       mbar_init(tmem_full(b), 1);
-      mbar_init(tmem_empty(b), 32 * kEpiWarps);
+      mbar_init(tmem_empty(b), 32 * kEpiWarps);     // every thread arrives as it finishes (one arrive per warp behind a __syncwarp measured 5 % slower)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -956,7 +954,7 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
 #pragma unroll
       for (int h = 0; h < kUStages; h++) {
         const long long w0 = prof ? clock64() : 0;
-        if (!mbar_wait_warp(a_empty(h), (unit_iter & 1u) ^ 1u, p.status)) { ok = false; break; }
+        if (!mbar_wait(a_empty(h), (unit_iter & 1u) ^ 1u, p.status)) { ok = false; break; }
         const long long w1 = prof ? clock64() : 0;
         if (!(p.dbg & 2)) {
           const uint32_t step = h * kUSPS + b;
@@ -1005,7 +1003,9 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
         }
         const uint32_t ab = tile_iter & 1u, use = tile_iter >> 1;
         const long long w0 = prof ? clock64() : 0;
-        if (!mbar_wait_warp(tmem_full(ab), use & 1u, p.status, 32)) { ok = false; break; }
+        // no back-off: the wait is short (a tile is 2000 clk) and a sleeping poller started the read-out
+        // late -- 32 ns of back-off cost 4.5 % of the kernel
+        if (!mbar_wait(tmem_full(ab), use & 1u, p.status)) { ok = false; break; }
         const long long w1 = prof ? clock64() : 0;
         tc_fence_after();
         if (!(p.dbg & 4)) epilogue_tile<kHalfN>(tm, ab * kHalfN, warp, lane, cur, old_cur, prof ? pc : nullptr);
@@ -1243,7 +1243,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) update_
       }
 #pragma unroll
       for (int h = 0; h < kUStages; h++) {
-        if (!mbar_wait_warp(a_empty(h), (unit_iter & 1u) ^ 1u, p.status)) { ok = false; break; }
+        if (!mbar_wait(a_empty(h), (unit_iter & 1u) ^ 1u, p.status)) { ok = false; break; }
         if (!(p.dbg & 2)) {
           const uint32_t step = h * kUSPS + b;
           build_a_step(lutc, cw[h], reinterpret_cast<uint4 *>(smA + step * kATile + i * kASbo + q * kALbo));
@@ -1281,7 +1281,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) update_
           nxt.load_old(old_nxt, p.accumulate);
         }
         const uint32_t ab = tile_iter & 1u, use = tile_iter >> 1;
-        if (!mbar_wait_warp(tmem_full(ab), use & 1u, p.status, 32)) { ok = false; break; }
+        if (!mbar_wait(tmem_full(ab), use & 1u, p.status)) { ok = false; break; }
         tc_fence_after();
         if (!(p.dbg & 4)) epilogue_tile<kHalfN>(tm, ab * kHalfN, warp, lane, cur, old_cur, nullptr);
         tc_fence_before();
