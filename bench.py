@@ -46,7 +46,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 K_DEFAULT, L_DEFAULT, NSYS_DEFAULT = 1024, 1280, 4096
 # dram__bytes_read.sum + dram__bytes_write.sum of one update_tc_kernel launch (outer panel 0) on 296
 # systems, ncu --set full (profiles/r01_ncu_update_tc.json)
-NCU_UPDATE_DRAM_BYTES_296 = 1.062153e9 + 0.615189e9
+NCU_UPDATE_DRAM_BYTES_296 = 1.062999e9 + 0.615194e9
 METRIC = "GF(256) K=1024 solves/sec (batched Gaussian elimination + 1280-byte RHS symbol update)"
 
 
