@@ -25,8 +25,17 @@ Besides the contract keys the JSON line carries:
   cpu_baseline  the unmodified reference (oracle/_ref, AVX-512 build when the host
                 has it) driven by oracle/ref_driver.c on the host cores, bounded sample
   e2e           same metric through oblas_b200_solve_batch_host: pinned HOST buffers
-                in, HOST buffers out, copies inside the timed region
-  parity        what was checked on this run's outputs
+                in, HOST buffers out, copies inside the timed region; e2e.roofline = the bytes
+                of the binding direction / time / the raw pinned-copy rate measured in the same
+                run (this many ranks copying concurrently); e2e.skip_identity_A = the variant
+                that does not copy back the A of full-rank systems (= I)
+  other_configs BASELINE configs[2], [3], [4] (GF(2) K=8192 x 256, GF(16)/GF(4) K=2048 x 1024,
+                apply 10000^2 x 64 KB) each with its own roofline, bit-exact check against the
+                reference and CPU figure; sharded over the ranks when N > 1 (systems / symbol
+                columns, the apply with one NCCL broadcast of the coefficient matrix)
+  parity        what was checked on this run's outputs: every rank-deficient system and 8
+                systems of every workspace chunk bit for bit against the reference, the
+                rank histogram beside the reference's
 Only this file's cpu_baseline / --impl reference legs and the parity check touch
 oracle/; the measured path is liboblas_b200.so.
 """
@@ -44,9 +53,26 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 K_DEFAULT, L_DEFAULT, NSYS_DEFAULT = 1024, 1280, 4096
-# dram__bytes_read.sum + dram__bytes_write.sum of one update_tc_kernel launch (outer panel 0) on 296
-# systems, ncu --set full (profiles/r01_ncu_update_tc.json)
-NCU_UPDATE_DRAM_BYTES_296 = 1.062999e9 + 0.615194e9
+
+
+def ncu_update_traffic_per_system():
+    """dram__bytes_read.sum + dram__bytes_write.sum per system and update_tc_kernel launch, AVERAGED over
+    the 8 launches (outer panels) of one K=1024/L=1280 elimination, from the committed ncu --set full
+    capture of all 8 (profiles/r02_ncu_update_tc_all_panels.json, written by tools/summarize_profiles.py).
+    Falls back to the round-1 capture of outer panel 0 scaled by the modelled bytes (Y read + write,
+    E, fp4 operand blocks) of the average panel over panel 0."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_update_tc_all_panels.json")) as f:
+            d = json.load(f)
+        return float(d["dram_bytes_per_system_per_launch"]), d.get("source", "profiles/r02_ncu_update_tc_all_panels.json")
+    except Exception:
+        def model(p):
+            trailing = max(1024 - 128 * (p + 1), 0) + 1280
+            tiles = (trailing + 239) // 240
+            return 2 * 1024 * trailing + 1024 * 128 + tiles * 16 * 7680
+        avg = sum(model(p) for p in range(8)) / 8.0
+        return (1.062999e9 + 0.615194e9) / 296 * avg / model(0), \
+            "profiles/r01_ncu_update_tc.json (outer panel 0) x modelled bytes of the average panel / panel 0"
 METRIC = "GF(256) K=1024 solves/sec (batched Gaussian elimination + 1280-byte RHS symbol update)"
 
 
@@ -138,33 +164,67 @@ def pick_reference():
     return None, "port", "oracle/oblas_oracle.c (scalar C port)"
 
 
-def cpu_solve_rate(K, L, budget_s, threads):
-    """systems/s of the reference's CPU path on `threads` host threads, bounded sample."""
+SEED_A, SEED_B = 1000, 1001   # + 2 * rank: the batch of rank r is the splitmix64 streams SEED_A + 2r / SEED_B + 2r
+
+
+def batch_system(K, L, s, rank=0):
+    """system s of the synthetic batch of `rank` (what oblas_b200_fill_random leaves in HBM), generated on
+    the CPU by the oracle's C generator (no GIL held: the CPU arm's threads do not serialise on it)"""
     import numpy as np
-    from helpers import GF256, mat_view, oracle_solve, ptr, splitmix_bytes
+    from helpers import oracle, ptr
+    A, B = np.empty((K, K), dtype=np.uint8), np.empty((K, L), dtype=np.uint8)
+    oracle().orc_fill_random(ptr(A), K * K, SEED_A + 2 * rank, s * K * K)
+    oracle().orc_fill_random(ptr(B), K * L, SEED_B + 2 * rank, s * K * L)
+    return A, B
+
+
+def ref_solve_system(lib, K, L, A, B, keep=False):
+    """the caller-side elimination loop on one system by the compiled reference (oracle port if lib is
+    None); returns (rank, A', B', seconds inside the solve) -- the matrices only when keep"""
+    import numpy as np
+    from helpers import GF256, mat_view, oracle_solve
+    if lib is not None:
+        a, b = lib.octmat_new(K, K), lib.octmat_new(K, L)
+        mat_view(a)[:, :K] = A
+        mat_view(b)[:, :L] = B
+        t0 = time.perf_counter()
+        rk = lib.refdrv_octmat_solve(a, b, None)
+        dt = time.perf_counter() - t0
+        out = (rk, mat_view(a)[:, :K].copy(), mat_view(b)[:, :L].copy(), dt) if keep else (rk, None, None, dt)
+        lib.octmat_free(a)
+        lib.octmat_free(b)
+        return out
+    A, B = A.copy(), B.copy()
+    t0 = time.perf_counter()
+    rk, _ = oracle_solve(GF256, A, B, K)
+    dt = time.perf_counter() - t0
+    return (rk, A, B, dt) if keep else (rk, None, None, dt)
+
+
+def cpu_solve_rate(K, L, budget_s, threads, nsys=None):
+    """systems/s of the reference's CPU path on `threads` host threads: the systems of rank 0's own
+    batch, in order, for about budget_s seconds (a bounded sample of the same workload).  Only the time
+    inside the reference's solve loop counts (value = sum over threads of systems / solve seconds), not
+    the generation of the inputs.  The ranks the reference finds are returned for the parity block."""
     lib, kind, name = pick_reference()
-    done = [0] * threads
+    ranks = {}
+    nxt = [0]
+    lock = threading.Lock()
     t_end = time.perf_counter() + budget_s
+    per_thread = [[0, 0.0] for _ in range(threads)]
 
     def work(tid):
-        n = 0
-        while True:
-            seed = 10_000 + 64 * tid + n
-            if lib is not None:
-                a, b = lib.octmat_new(K, K), lib.octmat_new(K, L)
-                mat_view(a)[:, :K] = splitmix_bytes(seed, K * K).reshape(K, K)
-                mat_view(b)[:, :L] = splitmix_bytes(seed + 5000, K * L).reshape(K, L)
-                lib.refdrv_octmat_solve(a, b, None)
-                lib.octmat_free(a)
-                lib.octmat_free(b)
-            else:
-                A = splitmix_bytes(seed, K * K).reshape(K, K).copy()
-                B = splitmix_bytes(seed + 5000, K * L).reshape(K, L).copy()
-                oracle_solve(GF256, A, B, K)
-            n += 1
-            done[tid] = n
-            if time.perf_counter() >= t_end:
+        while time.perf_counter() < t_end:
+            with lock:
+                sidx = nxt[0]
+                nxt[0] += 1
+            if nsys is not None and sidx >= nsys:
                 break
+            A, B = batch_system(K, L, sidx)
+            rk, _, _, dt = ref_solve_system(lib, K, L, A, B)
+            ranks[sidx] = rk
+            per_thread[tid][0] += 1
+            per_thread[tid][1] += dt
 
     t0 = time.perf_counter()
     ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
@@ -172,10 +232,12 @@ def cpu_solve_rate(K, L, budget_s, threads):
         t.start()
     for t in ths:
         t.join()
-    dt = time.perf_counter() - t0
-    total = sum(done)
-    return {"value": total / dt, "unit": "solves/s", "cores": threads, "kind": kind,
-            "sample": "%d systems of K=%d, L=%d in %.1f s on %d threads; %s" % (total, K, L, dt, threads, name)}
+    wall = time.perf_counter() - t0
+    total = len(ranks)
+    value = sum(n / t for n, t in per_thread if n)
+    return {"value": value, "unit": "solves/s", "cores": threads, "kind": kind,
+            "sample": "systems 0..%d of this run's batch (K=%d, L=%d) on %d threads, %.1f s wall (%.0f solves/s incl. "
+                      "generating the inputs); %s" % (total - 1, K, L, threads, wall, total / wall, name)}, ranks
 
 
 def run_reference_arm(args):
@@ -190,7 +252,7 @@ def run_reference_arm(args):
     last = None
     t0 = time.perf_counter()
     for _ in range(steps):
-        last = cpu_solve_rate(args.K, args.L, per_step, threads)
+        last, _ = cpu_solve_rate(args.K, args.L, per_step, threads)
         rates.append(last["value"])
     dt = time.perf_counter() - t0
     v = sum(rates) / len(rates)
@@ -198,12 +260,22 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "solves/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "configs[1]: GF(256) octmat Gaussian elimination K=%d, %d-byte RHS symbols; "
-                                   "CPU arm: bounded sample per step on all host threads" % (args.K, args.L),
-                       "K": args.K, "rhs_bytes": args.L},
+            "config": config_block(args.K, args.L, args.nsys, int(os.environ.get("WORLD_SIZE", "1"))),
+            "sample_per_step": "a time-bounded run of systems 0.. of the batch on all host threads (%.0f s per step)" % per_step,
             "cpu_baseline": last,
             "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def config_block(K, L, nsys, world):
+    """identical in both arms: the driver compares the arms' `config`"""
+    return {"workload": "configs[1]: GF(256) octmat Gaussian elimination, K=%d square systems with "
+                        "%d-byte RHS symbols, batch of %d systems per GPU" % (K, L, nsys),
+            "K": K, "rhs_bytes": L, "systems_per_gpu": nsys,
+            "parallelism": "batch-sharded x%d, no collective" % world,
+            "l2": "inputs %.2f GB per GPU >> 126 MB L2; pristine batch restored by a device copy inside the timed "
+                  "region" % (nsys * (K * K + K * L) / 1e9),
+            "generator": "splitmix64 counter stream (oblas_b200_fill_random)"}
 
 
 # ------------------------------------------------------------------ GPU arm
@@ -234,8 +306,8 @@ def run_b200_arm(args):
     # ---- inputs: resident in HBM before the timed region (9.66 GB per GPU at defaults)
     A0 = torch.empty((nsys, K, K), dtype=torch.uint8, device="cuda")
     B0 = torch.empty((nsys, K, L), dtype=torch.uint8, device="cuda")
-    device.fill_random(A0, 1000 + 2 * rank)
-    device.fill_random(B0, 1001 + 2 * rank)
+    device.fill_random(A0, SEED_A + 2 * rank)
+    device.fill_random(B0, SEED_B + 2 * rank)
     A, B = torch.empty_like(A0), torch.empty_like(B0)
 
     def step():
@@ -278,7 +350,7 @@ def run_b200_arm(args):
     value = world * nsys * args.steps / (total_ms / 1e3)
 
     # ---- parity on this run's outputs (outside the timed region)
-    parity = check_parity(A0, B0, A, B, ranks, K, L, rank)
+    parity = check_parity(A0, B0, A, B, ranks, K, L, rank, L_)
 
     # ---- rooflines
     algo_bytes = nsys * (K * K + 2 * K * L)          # min bytes per system
@@ -304,9 +376,12 @@ def run_b200_arm(args):
         # (profiles/r01_ncu_update_tc.json: dram read + write of one launch on 296 systems)
         # (outer panel 0, the widest), scaled to the systems of one launch of this run
         sys_per_launch = nsys * nouter / max(cls_n[2], 1)
-        traffic = NCU_UPDATE_DRAM_BYTES_296 / 296 * sys_per_launch if (K, L) == (K_DEFAULT, L_DEFAULT) else None
+        traffic, traffic_src = None, None
+        if (K, L) == (K_DEFAULT, L_DEFAULT):
+            per_sys, traffic_src = ncu_update_traffic_per_system()   # same panel mix as algorithmic_bytes_per_launch
+            traffic = per_sys * sys_per_launch
         roofline = {"kernel": "ob2::tc::update_tc_kernel", "bound": "tensor", "achieved": ach, "peak": fp4_peak,
-                    "unit": "TFLOP/s", "frac": ach / fp4_peak, "traffic": traffic, "peak_source": fp4_src,
+                    "unit": "TFLOP/s", "frac": ach / fp4_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": fp4_src,
                     "launches_per_step": cls_n[2], "ms_per_step": upd_ms, "share_of_step": upd_ms / kern_ms,
                     "algorithmic_bytes_per_launch": sys_per_launch * 2 * K * (trailing / nouter),
                     "gf256_macs_per_system": upd_macs / nsys,
@@ -346,29 +421,43 @@ def run_b200_arm(args):
     rowops = None
     if rank == 0 and not args.skip_rowops:
         rowops = bench_rowops(device, capi, torch, hbm_peak)
+        if world == 1 and not args.skip_cpu:
+            rowops["cpu"] = cpu_rowops()
 
     line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "configs[1]: GF(256) octmat Gaussian elimination, K=%d square systems with "
-                                   "%d-byte RHS symbols, batch of %d systems per GPU" % (K, L, nsys),
-                       "K": K, "rhs_bytes": L, "systems_per_gpu": nsys, "parallelism": "batch-sharded x%d, no collective" % world,
-                       "l2": "inputs %.2f GB per GPU >> 126 MB L2; pristine batch restored by a device copy inside the timed region" % ((A0.numel() + B0.numel()) / 1e9),
-                       "generator": "splitmix64 counter stream (oblas_b200_fill_random)"},
+            "config": config_block(K, L, nsys, world),
             "kernel_ms_per_step": kern_ms, "gpu_launches": int(launches),
             "roofline": roofline, "roofline_panel": binding, "roofline_hbm": roofline_hbm, "rowops": rowops,
             "parity": parity}
     if rank == 0:
         line["clocks"] = clocks
+    ranks_gpu = ranks.cpu().numpy()
+    del A, B
     # ---- e2e through the host-buffer C-ABI call (rank-local, max over ranks)
     e2e = None
     if not args.skip_e2e:
-        e2e = bench_e2e(L_, capi, torch, A0, B0, K, L, nsys, world, dist)
+        e2e = bench_e2e(L_, capi, torch, A0, B0, K, L, nsys, world, dist, ranks_gpu)
     line["e2e"] = e2e
-    # ---- CPU baseline: rank 0, N=1 only
+    del A0, B0
+    torch.cuda.empty_cache()
+    # ---- the other BASELINE configs, each with its own roofline (sharded over the ranks when N > 1)
+    if not args.skip_other:
+        line["other_configs"] = other_configs(L_, capi, device, torch, dist, world, rank, hbm_peak, sms,
+                                              (clocks or {}).get("sm_mhz") or sm_mhz, with_cpu=(world == 1 and not args.skip_cpu))
+    # ---- CPU baseline: rank 0, N=1 only -- the batch's own systems, so its ranks pin the GPU's
     if rank == 0 and world == 1 and not args.skip_cpu:
-        del A, B
-        line["cpu_baseline"] = cpu_solve_rate(K, L, args.cpu_seconds, os.cpu_count() or 1)
+        cpu, ref_ranks = cpu_solve_rate(K, L, args.cpu_seconds, os.cpu_count() or 1, nsys)
+        line["cpu_baseline"] = cpu
+        import numpy as np
+        idx = np.array(sorted(ref_ranks), dtype=np.int64)
+        rr = np.array([ref_ranks[int(i)] for i in idx], dtype=np.int64)
+        gg = ranks_gpu[idx].astype(np.int64)
+        hist = lambda v: {str(int(k)): int(c) for k, c in zip(*np.unique(v, return_counts=True))}
+        parity["rank_histogram_all_systems_gpu"] = hist(ranks_gpu)
+        parity["ranks_vs_reference"] = {"systems_compared": int(len(idx)), "equal": bool(np.array_equal(rr, gg)),
+                                        "rank_histogram_reference": hist(rr), "rank_histogram_gpu_same_systems": hist(gg)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -376,20 +465,27 @@ def run_b200_arm(args):
         dist.destroy_process_group()
 
 
-def check_parity(A0, B0, A, B, ranks, K, L, rank):
-    """(1) every full-rank system ended as A == I; (2) A_orig * X == B_orig on sampled rows,
-    recomputed on the CPU with numpy; (3) whole-buffer equality with the compiled reference
-    (or the oracle port) for the first systems."""
+def check_parity(A0, B0, A, B, ranks, K, L, rank, L_=None):
+    """(1) EVERY full-rank system ended as A == I (one fused comparison on the device);
+    (2) A_orig * X == B_orig on sampled rows, recomputed on the CPU with numpy;
+    (3) whole-buffer equality (A and B, padding included) with the compiled reference (or the
+        oracle port) for EVERY rank-deficient system of the batch and 8 random systems of every
+        workspace chunk of the tensor-core path (oblas_b200_solve_plan gives the chunking)."""
+    import ctypes as C
     import numpy as np
     import torch
     from gpu_helpers import gf256_vecmat
-    from helpers import mat_view, ptr, u32p
     torch.cuda.synchronize()
     r = ranks.cpu().numpy()
     nsys = len(r)
     full = np.nonzero(r == K)[0]
+    deficient = np.nonzero(r != K)[0]
     eye = torch.eye(K, dtype=torch.uint8, device="cuda")
-    ident_ok = all(bool(torch.equal(A[int(s)], eye)) for s in full[:256])
+    full_t = torch.from_numpy(full).cuda()
+    ident_bad = 0
+    for i in range(0, len(full), 256):   # 256 systems (268 MB) per comparison
+        sel = full_t[i:i + 256]
+        ident_bad += int((A[sel] != eye).flatten(1).any(dim=1).sum())
     rng = np.random.default_rng(rank)
     rt_ok, n_rt = True, 0
     for s in rng.choice(full, min(4, len(full)), replace=False):
@@ -397,22 +493,100 @@ def check_parity(A0, B0, A, B, ranks, K, L, rank):
         for row in rng.choice(K, 3, replace=False):
             rt_ok &= bool(np.array_equal(gf256_vecmat(Ao[row], X), Bo[row]))
             n_rt += 1
+    # chunks of the tensor-core path
+    path, chunk = C.c_int(0), C.c_size_t(nsys)
+    if L_ is not None:
+        L_.oblas_b200_solve_plan(3, K, K, K, L, nsys, C.byref(path), C.byref(chunk), None)
+    chunk = max(1, int(chunk.value))
+    picks = set(int(x) for x in deficient)
+    per_chunk = []
+    for first in range(0, nsys, chunk):
+        cnt = min(chunk, nsys - first)
+        sel = first + rng.choice(cnt, min(8, cnt), replace=False)
+        picks.update(int(x) for x in sel)
+        per_chunk.append({"first": first, "systems": cnt, "sampled": sorted(int(x) for x in sel)})
+    picks = sorted(picks)
     lib, kind, name = pick_reference()
-    exact_ok, n_exact = True, 0
-    if lib is not None and lib.refdrv_octmat_align() in (16, 32, 64) and K % 64 == 0 and L % 64 == 0:
-        for s in ([0] + [int(x) for x in np.nonzero(r != K)[0][:1]]):
-            a, b = lib.octmat_new(K, K), lib.octmat_new(K, L)
-            mat_view(a)[:] = A0[s].cpu().numpy()
-            mat_view(b)[:] = B0[s].cpu().numpy()
-            rk = lib.refdrv_octmat_solve(a, b, None)
-            exact_ok &= rk == r[s] and np.array_equal(mat_view(a), A[s].cpu().numpy()) and \
-                np.array_equal(mat_view(b), B[s].cpu().numpy())
-            lib.octmat_free(a)
-            lib.octmat_free(b)
-            n_exact += 1
-    return {"systems": int(nsys), "full_rank": int(len(full)), "identity_after_solve": bool(ident_ok),
+    if lib is not None and (K % 64 or L % 64) and lib.refdrv_octmat_align() != 16:
+        lib = None   # the AVX builds pad rows to 32 / 64 bytes: compare with the port then
+        name = "oracle/oblas_oracle.c (scalar C port)"
+    got = {s_: (A[s_].cpu().numpy(), B[s_].cpu().numpy()) for s_ in picks}
+    inp = {s_: (A0[s_].cpu().numpy(), B0[s_].cpu().numpy()) for s_ in picks}
+    bad = []
+
+    def one(s_):
+        rk, wa, wb, _ = ref_solve_system(lib, K, L, inp[s_][0], inp[s_][1], keep=True)
+        if not (rk == r[s_] and np.array_equal(wa, got[s_][0]) and np.array_equal(wb, got[s_][1])):
+            bad.append(s_)
+
+    ths = [threading.Thread(target=lambda lo: [one(s_) for s_ in picks[lo::8]], args=(i,)) for i in range(8)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    return {"systems": int(nsys), "full_rank": int(len(full)), "rank_deficient": int(len(deficient)),
+            "identity_after_solve": ident_bad == 0, "identity_checked_systems": int(len(full)),
             "roundtrip_rows_checked": n_rt, "roundtrip_ok": bool(rt_ok), "bit_exact_vs": name,
-            "bit_exact_systems": n_exact, "bit_exact_ok": bool(exact_ok)}
+            "bit_exact_systems": len(picks), "bit_exact_ok": not bad, "bit_exact_mismatches": sorted(bad),
+            "bit_exact_rank_deficient_systems": int(len(deficient)),
+            "elimination_path": "tensor-core (outer panels + tcgen05 updates)" if path.value else "table kernel",
+            "chunks": per_chunk}
+
+
+def cpu_rowops():
+    """BASELINE configs[0] on the host: the reference's oaxpy / oaddrow / oscal on 1024 x 1280-byte
+    octmats (refdrv_*_many = loops of reference calls), one thread and all threads (one matrix pair per
+    thread, so the all-thread figure is cache resident per core like the single-thread one)."""
+    import numpy as np
+    from helpers import mat_view, ptr, splitmix_bytes, u32p, u8p
+    lib, kind, name = pick_reference()
+    if lib is None:
+        return {"unavailable": "no compiled reference on this host"}
+    rows, cols, reps = 1024, 1280, 200
+    threads = os.cpu_count() or 1
+
+    def make():
+        a, b = lib.octmat_new(rows, cols), lib.octmat_new(rows, cols)
+        mat_view(a)[:, :cols] = splitmix_bytes(1, rows * cols).reshape(rows, cols)
+        mat_view(b)[:, :cols] = splitmix_bytes(2, rows * cols).reshape(rows, cols)
+        return a, b
+
+    rng = np.random.default_rng(0)
+    n = rows * reps
+    di = np.tile(rng.permutation(rows).astype(np.uint32), reps)
+    sj = rng.integers(0, rows, n).astype(np.uint32)
+    uu = rng.integers(2, 256, n).astype(np.uint8)
+    stride = make()[0].contents.stride
+    out = {"shape": "%d x %d-byte rows (stride %d), %d row ops per timing, u in 2..255; %s" % (rows, cols, stride, n, name)}
+
+    def run(op, a, b):
+        if op == "oaxpy":
+            lib.refdrv_oaxpy_many(a, b, ptr(di, u32p), ptr(sj, u32p), ptr(uu, u8p), n)
+        elif op == "oaddrow":
+            lib.refdrv_oaddrow_many(a, b, ptr(di, u32p), ptr(sj, u32p), n)
+        else:
+            lib.refdrv_oscal_many(a, ptr(di, u32p), ptr(uu, u8p), n)
+
+    for op, mult in (("oaxpy", 3), ("oaddrow", 3), ("oscal", 2)):
+        a, b = make()
+        run(op, a, b)
+        t0 = time.perf_counter()
+        run(op, a, b)
+        t1 = time.perf_counter() - t0
+        pairs = [make() for _ in range(threads)]
+        ths = [threading.Thread(target=run, args=(op, pa, pb)) for pa, pb in pairs]
+        t0 = time.perf_counter()
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        tn = time.perf_counter() - t0
+        out[op] = {"GBs_1_thread": mult * n * stride / t1 / 1e9, "GBs_all_threads": threads * mult * n * stride / tn / 1e9,
+                   "threads": threads}
+        for pa, pb in pairs + [(a, b)]:
+            lib.octmat_free(pa)
+            lib.octmat_free(pb)
+    return out
 
 
 def bench_rowops(device, capi, torch, hbm_peak):
@@ -446,35 +620,50 @@ def bench_rowops(device, capi, torch, hbm_peak):
     return res
 
 
-def bind_to_gpu_numa_node(torch, local):
-    """N > 1: run this rank (and first-touch its pinned host buffers) on the CPUs of the NUMA node its
-    GPU hangs off, read from sysfs -- 8 ranks pinning 77 GB on one node share one memory controller."""
+def raw_pinned_copy_rates(L_, torch, dist, world, hA, hB, dA, dB, nbytes):
+    """GB/s of plain cudaMemcpyAsync between pinned host memory and HBM on this rank while all `world`
+    ranks do the same: H2D alone, D2H alone, both directions at once (two streams).  The ceiling the
+    e2e number is judged against.  max over ranks of the time."""
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    hp = lambda p: int(p)
+
+    def timed(do_h2d, do_d2h):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        if do_h2d:
+            with torch.cuda.stream(s1):
+                L_.oblas_b200_set_stream(s1.cuda_stream)
+                L_.oblas_b200_copy(dA, hp(hA), nbytes)
+        if do_d2h:
+            with torch.cuda.stream(s2):
+                L_.oblas_b200_set_stream(s2.cuda_stream)
+                L_.oblas_b200_copy(hp(hB), dB, nbytes)
+        s1.synchronize()
+        s2.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return nbytes / float(t[0]) / 1e9
+
+    cur = L_.oblas_b200_get_stream()
     try:
-        p = torch.cuda.get_device_properties(local)
-        dev = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
-        with open("/sys/bus/pci/devices/%s/local_cpulist" % dev) as f:
-            txt = f.read().strip()
-        cpus = set()
-        for part in txt.split(","):
-            if "-" in part:
-                a, b = part.split("-")
-                cpus.update(range(int(a), int(b) + 1))
-            elif part:
-                cpus.add(int(part))
-        allowed = os.sched_getaffinity(0)
-        cpus &= allowed
-        if cpus and cpus != allowed:
-            os.sched_setaffinity(0, cpus)
-            return "cpus %s of %s" % (txt, dev)
-    except Exception as e:  # no sysfs / no permission: stay where we are
-        return "unchanged (%s)" % type(e).__name__
-    return "unchanged"
+        timed(True, True)   # warm-up
+        res = {"h2d_GBs": timed(True, False), "d2h_GBs": timed(False, True), "bidirectional_each_GBs": timed(True, True)}
+    finally:
+        L_.oblas_b200_set_stream(cur)
+    res["bytes_per_copy"] = int(nbytes)
+    res["concurrent_ranks"] = world
+    return res
 
 
-def bench_e2e(L_, capi, torch, A0, B0, K, L, nsys, world, dist):
-    """systems/s through oblas_b200_solve_batch_host: pinned host buffers in and out."""
+def bench_e2e(L_, capi, torch, A0, B0, K, L, nsys, world, dist, ranks_gpu):
+    """systems/s through oblas_b200_solve_batch_host(_ex): pinned host buffers in and out, copies inside
+    the timed region.  Two variants: everything copied back (the headline `value`), and with
+    OBLAS_B200_SOLVE_SKIP_IDENTITY_A (the A of full-rank systems is the identity and stays on the device)."""
     import numpy as np
-    numa = bind_to_gpu_numa_node(torch, torch.cuda.current_device()) if world > 1 else "n/a (single rank)"
     a_bytes, b_bytes = nsys * K * K, nsys * K * L
     n = nsys
     hA = L_.oblas_b200_host_alloc(a_bytes)
@@ -489,34 +678,290 @@ def bench_e2e(L_, capi, torch, A0, B0, K, L, nsys, world, dist):
         if not hA or not hB:
             return {"value": None, "unit": "solves/s", "error": "pinned host allocation failed"}
     rank = np.zeros(n, dtype=np.int32)
-    times = []
-    for it in range(3):  # 1 warm-up + 2 timed calls
-        torch.cuda.synchronize()
-        capi.check(L_.oblas_b200_copy(hA, A0.data_ptr(), a_bytes))   # refill host inputs (untimed)
-        capi.check(L_.oblas_b200_copy(hB, B0.data_ptr(), b_bytes))
-        capi.check(L_.oblas_b200_sync())
-        torch.cuda.synchronize()
+
+    def run(flags):
+        times = []
+        for it in range(3):  # 1 warm-up + 2 timed calls
+            torch.cuda.synchronize()
+            capi.check(L_.oblas_b200_copy(hA, A0.data_ptr(), a_bytes))   # refill host inputs (untimed)
+            capi.check(L_.oblas_b200_copy(hB, B0.data_ptr(), b_bytes))
+            capi.check(L_.oblas_b200_sync())
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            capi.check(L_.oblas_b200_solve_batch_host_ex(capi.GF256, hA, K, K * K, K, K, K, hB, L, K * L, L,
+                                                         rank.ctypes.data, None, n, 0, flags))
+            dt = time.perf_counter() - t0
+            if it:
+                times.append(dt)
+        dt = sum(times) / len(times)
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
         if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        capi.check(L_.oblas_b200_solve_batch_host(capi.GF256, hA, K, K * K, K, K, K, hB, L, K * L, L,
-                                                  rank.ctypes.data, None, n, 0))
-        dt = time.perf_counter() - t0
-        if it:
-            times.append(dt)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    dt = run(0)
     hb = np.ctypeslib.as_array(C.cast(hA, C.POINTER(C.c_uint8)), shape=(n, K, K))
     ok = bool(np.array_equal(hb[0], np.eye(K, dtype=np.uint8))) if rank[0] == K else None
+    ranks_ok = bool(np.array_equal(rank, ranks_gpu[:n]))
+    dt_skip = run(1)
+    deficient = int((rank != K).sum())
+    ranks_ok &= bool(np.array_equal(rank, ranks_gpu[:n]))
+    # raw copy ceiling, same buffers, same number of concurrent ranks
+    nraw = min(a_bytes, 4 << 30)
+    raw = raw_pinned_copy_rates(L_, torch, dist, world, hA, hB, A0.data_ptr(), B0.data_ptr(), nraw)
     L_.oblas_b200_host_free(hA)
     L_.oblas_b200_host_free(hB)
-    dt = sum(times) / len(times)
-    t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+    h2d, d2h = a_bytes + b_bytes, a_bytes + b_bytes + 4 * n
+    d2h_skip = b_bytes + 4 * n + deficient * K * K
+    # both directions run at once: the call cannot finish before the larger direction has moved its bytes
+    # at the rate one direction gets while both are busy
+    floor_s = max(h2d, d2h) / (raw["bidirectional_each_GBs"] * 1e9)
+    floor_skip_s = max(h2d / (raw["bidirectional_each_GBs"] * 1e9), d2h_skip / (raw["bidirectional_each_GBs"] * 1e9))
+    return {"value": world * n / dt, "unit": "solves/s", "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "systems_per_gpu": n, "s_per_call": dt,
+            "api": "oblas_b200_solve_batch_host (pinned host A,B in; A,B,rank out; 3-lane chunked copy/compute overlap)",
+            "first_system_identity": ok, "ranks_equal_device_resident_run": ranks_ok,
+            "roofline": {"bound": "host<->device copies (PCIe / host memory), both directions busy", "unit": "GB/s",
+                         "achieved": max(h2d, d2h) / dt / 1e9, "peak": raw["bidirectional_each_GBs"],
+                         "frac": floor_s / dt, "raw_pinned_copy": raw,
+                         "note": "achieved = bytes of the larger direction / call time; peak = what one direction of a plain "
+                                 "pinned cudaMemcpyAsync gets on this rank while the other direction and the other ranks "
+                                 "copy too, measured in this run"},
+            "skip_identity_A": {"value": world * n / dt_skip, "unit": "solves/s", "s_per_call": dt_skip,
+                                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_skip, "frac_of_copy_floor": floor_skip_s / dt_skip,
+                                "api": "oblas_b200_solve_batch_host_ex(..., OBLAS_B200_SOLVE_SKIP_IDENTITY_A): A of the %d "
+                                       "full-rank systems (= I) is not copied back" % (n - deficient)}}
+
+
+# ------------------------------------------------------------------ the other BASELINE configs
+def _timed_steps(torch, dist, world, fn, steps=3, warm=3):
+    """CUDA-event time of fn's own (e0, e1) bracket, mean over steps, max over ranks"""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    evs = [fn() for _ in range(steps)]
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt = float(t[0])
-    return {"value": world * n / dt, "unit": "solves/s", "h2d_bytes_per_step": a_bytes + b_bytes,
-            "d2h_bytes_per_step": a_bytes + b_bytes + 4 * n, "systems_per_gpu": n, "s_per_call": dt,
-            "api": "oblas_b200_solve_batch_host (pinned host A,B in; A,B,rank out; 3-lane chunked copy/compute overlap)",
-            "first_system_identity": ok, "host_numa_binding": numa}
+    return float(t[0])
+
+
+def solve_config(name, field, K, nsys_total, L_, capi, device, torch, dist, world, rank, hbm_peak, sms, sm_mhz, with_cpu):
+    """A batch of K x K eliminations over a packed field without right-hand side (BASELINE configs[2] and
+    [3]), sharded by systems.  Roofline: the shared-memory table kernel is bound by LDS.128 look-ups
+    (one per group of KB coefficient bits and 16-byte chunk; the crossbar delivers 8 per clk per SM)."""
+    import ctypes as C
+    import numpy as np
+    from helpers import FIELD_BITS, mat_view, ptr, u32p
+    from oblas_b200 import shard
+    bits = FIELD_BITS[field]
+    a_bytes = (K * bits // 8 + 15) // 16 * 16
+    lo, hi = shard.batch_range(nsys_total, rank, world)
+    n = hi - lo
+    A0 = torch.empty((n, K, a_bytes), dtype=torch.uint8, device="cuda")
+    device.fill_random(A0, 100 + field, lo * K * a_bytes)
+    A = torch.empty_like(A0)
+    state = {}
+
+    def step():
+        A.copy_(A0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        state["rank"], state["piv"] = device.solve_batch(field, A, K, None, want_pivcols=True)
+        e1.record()
+        return e0, e1
+
+    ms = _timed_steps(torch, dist, world, step)
+    capi.check(L_.oblas_b200_sync(), "sync")
+    ranks = state["rank"].cpu().numpy()
+    geo = (C.c_int * 4)()
+    path = C.c_int(0)
+    capi.check(L_.oblas_b200_solve_plan(field, K, K, a_bytes, 0, n, C.byref(path), None, geo), "solve_plan")
+    nbw, kb, wt = int(geo[0]), int(geo[1]), int(geo[2])
+    # executed look-ups: per panel of 32*NBW coefficient bits every row streams the bytes right of the panel,
+    # NG = ceil(32*NBW / KB) look-ups per 16-byte chunk
+    pan_bytes = 4 * nbw
+    ng = (32 * nbw + kb - 1) // kb
+    npan = (a_bytes + pan_bytes - 1) // pan_bytes
+    lookups = sum(K * max(a_bytes - (p + 1) * pan_bytes, 0) / 16.0 * ng for p in range(npan))
+    peak_lookups = 8.0 * sms * sm_mhz * 1e6
+    ach = nsys_total * lookups / (ms / 1e3)
+    # the same in field terms: a look-up applies KB coefficient bits to 128 data bits
+    macs_exec = K * K * (K / 2.0)          # Gauss-Jordan, A only: K^3 / 2 field MACs
+    res = {"config": name, "metric": "solves/s", "value": nsys_total / (ms / 1e3), "unit": "solves/s", "n_gpus": world,
+           "scaling": "strong (fixed batch sharded by systems)", "ms_per_batch": ms, "systems": nsys_total, "K": K,
+           "field_bits": bits, "row_bytes": a_bytes,
+           "kernel": "ob2::solve_kernel<EXP=%d, NBW=%d, KB=%d, WT=%d>" % (bits, nbw, kb, wt),
+           "roofline": {"bound": "shared-memory look-up bandwidth (LDS.128, 8 per clk per SM measured: "
+                                 "profiles/r01_peaks_b200.jsonl)", "unit": "T look-ups/s",
+                        "achieved": ach / 1e12, "peak": peak_lookups / 1e12, "frac": ach / peak_lookups,
+                        "lookups_per_system": lookups, "groups_per_chunk": ng, "sm_mhz_used": sm_mhz,
+                        "field_gmacs_per_system_executed": macs_exec / 1e9,
+                        "T_field_MAC_per_s": nsys_total * macs_exec / (ms / 1e3) / 1e12},
+           "roofline_hbm": {"bound": "hbm", "unit": "GB/s", "achieved": 2.0 * nsys_total * K * a_bytes / (ms / 1e3) / 1e9,
+                            "peak": hbm_peak, "frac": 2.0 * nsys_total * K * a_bytes / (ms / 1e3) / 1e9 / hbm_peak,
+                            "note": "algorithmic bytes = every matrix read and written once; the kernel streams each "
+                                    "matrix once per panel (compute bound by construction)"},
+           "full_rank_fraction": float((ranks == K).mean()), "mean_rank": float(ranks.mean())}
+    if rank == 0:
+        lib, kind, rname = pick_reference()
+        picks = [0] + [int(x) for x in np.nonzero(ranks != ranks.max())[0][:1]]
+        picks = sorted(set(picks))
+        ok, cpu_s = True, []
+        for s_ in picks:
+            a_h = A0[s_].cpu().numpy()
+            pv = np.zeros(K, dtype=np.uint32)
+            if lib is not None:
+                m = lib.binmat_new(K, K) if field == 0 else lib.gfmat_new(field, K, K)
+                if mat_view(m).shape[1] != a_bytes:
+                    (lib.binmat_free if field == 0 else lib.gfmat_free)(m)
+                    lib = None
+            if lib is not None:
+                mat_view(m)[:] = a_h
+                t0 = time.perf_counter()
+                rk = lib.refdrv_binmat_rref(m, None, ptr(pv, u32p)) if field == 0 else \
+                    lib.refdrv_gfmat_solve(m, None, ptr(pv, u32p), 1)
+                cpu_s.append(time.perf_counter() - t0)
+                want = mat_view(m).copy()
+                (lib.binmat_free if field == 0 else lib.gfmat_free)(m)
+            else:
+                from helpers import oracle_solve
+                want = a_h.copy()
+                t0 = time.perf_counter()
+                rk, pv = oracle_solve(field, want, None, K)
+                cpu_s.append(time.perf_counter() - t0)
+                kind, rname = "port", "oracle/oblas_oracle.c (scalar C port)"
+            gp = state["piv"][s_].cpu().numpy().astype(np.uint32)
+            ok &= bool(rk == ranks[s_] and np.array_equal(A[s_].cpu().numpy(), want) and np.array_equal(gp[:rk], pv[:rk]))
+        res["parity"] = {"bit_exact_systems": picks, "bit_exact_ok": bool(ok), "checked_against": rname,
+                         "ranks_of_checked_systems": [int(ranks[s_]) for s_ in picks]}
+        if with_cpu:
+            res["cpu_baseline"] = {"value": len(cpu_s) / sum(cpu_s), "unit": "solves/s", "cores": 1, "kind": kind,
+                                   "sample": "%d system(s) of this batch on 1 thread, %.2f s; %s" % (len(cpu_s), sum(cpu_s), rname)}
+    del A, A0
+    torch.cuda.empty_cache()
+    return res
+
+
+def apply_config(L_, capi, device, torch, dist, world, rank, with_cpu, K=10000, N=65536):
+    """BASELINE configs[4]: Y = C * D over GF(256), C K x K, D K x N bytes; symbol-byte columns sharded
+    over the ranks (256-byte aligned slices), the coefficient matrix broadcast once with NCCL."""
+    import numpy as np
+    from gpu_helpers import gf256_vecmat
+    from helpers import mat_view
+    from oblas_b200 import shard
+    cs = (K + 63) // 64 * 64
+    lo, hi = shard.column_slice(N, rank, world)
+    w = hi - lo
+    Cm = torch.zeros((K, cs), dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        tmp = torch.empty((K, cs), dtype=torch.uint8, device="cuda")
+        device.fill_random(tmp, 7)
+        Cm[:, :K] = tmp[:, :K]
+        del tmp
+    bcast_ms = 0.0
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.broadcast(Cm, src=0)     # the one collective of this config: C over NVLink / NVSwitch (NCCL)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        bcast_ms = float(t[0])
+    # column slice [lo, hi) of the global D (row r = bytes [r*N, (r+1)*N) of the stream): identical data for every world size
+    D = torch.empty((K, w), dtype=torch.uint8, device="cuda")
+    if world == 1:
+        device.fill_random(D, 8)
+    else:
+        blk = 500
+        full = torch.empty((blk, N), dtype=torch.uint8, device="cuda")
+        for r0 in range(0, K, blk):
+            nb = min(blk, K - r0)
+            device.fill_random(full[:nb], 8, r0 * N)
+            D[r0:r0 + nb] = full[:nb, lo:hi]
+        del full
+    Y = torch.empty((K, w), dtype=torch.uint8, device="cuda")
+
+    def step():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        device.apply(Cm, D, Y)
+        e1.record()
+        return e0, e1
+
+    ms = _timed_steps(torch, dist, world, step)
+    capi.check(L_.oblas_b200_sync(), "sync")
+    # parity: rows recomputed on the CPU; every rank checks its own slice
+    Ch = Cm.cpu().numpy()
+    rng = np.random.default_rng(rank)
+    ncheck = min(w, 1024)
+    Dh = D[:, :ncheck].cpu().numpy()
+    ok = True
+    for r_ in rng.choice(K, 4, replace=False):
+        ok &= bool(np.array_equal(gf256_vecmat(Ch[r_][:K], Dh), Y[r_, :ncheck].cpu().numpy()))
+    cpu, ref_rows = None, 0
+    if rank == 0:
+        lib, kind, rname = pick_reference()
+        if lib is not None:
+            rows_s = 64
+            c_, d_, y_ = lib.octmat_new(rows_s, K), lib.octmat_new(K, ncheck), lib.octmat_new(rows_s, ncheck)
+            if mat_view(d_).shape[1] == ncheck:
+                pick = np.sort(rng.choice(K, rows_s, replace=False))
+                mat_view(c_)[:, :K] = Ch[pick, :K]
+                mat_view(d_)[:] = Dh
+                t0 = time.perf_counter()
+                lib.refdrv_octmat_apply(c_, d_, y_)
+                dt = time.perf_counter() - t0
+                ok &= bool(np.array_equal(mat_view(y_)[:, :ncheck], Y[:, :ncheck].cpu().numpy()[pick]))
+                ref_rows = rows_s
+                if with_cpu:
+                    cpu = {"value": rows_s * K * ncheck / dt / 1e9, "unit": "G GF-MAC/s", "cores": 1, "kind": kind,
+                           "sample": "%d rows x %d coefficient columns x %d symbol bytes by oaxpy calls: %.2f s; %s"
+                                     % (rows_s, K, ncheck, dt, rname)}
+            for m in (c_, d_, y_):
+                lib.octmat_free(m)
+    okt = torch.tensor([1 if ok else 0], device="cuda")
+    if world > 1:
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    macs = float(K) * K * N
+    fp4_peak, fp4_src = measured_fp4_peak()
+    ach = macs * 64 * 2 / (ms / 1e3) / 1e12
+    res = {"config": "configs[4]: GF(256) apply, C %dx%d, D %d x %d bytes, column-sharded over %d GPU(s)" % (K, K, K, N, world),
+           "metric": "T GF-MAC/s", "value": macs / (ms / 1e3) / 1e12, "unit": "T GF(256)-MAC/s", "n_gpus": world,
+           "scaling": "strong (fixed problem, symbol columns sharded)", "ms_per_apply": ms,
+           "coefficient_broadcast_ms": bcast_ms, "coefficient_bytes": int(Cm.numel()),
+           "coefficient_broadcast_GBs": (Cm.numel() / (bcast_ms / 1e3) / 1e9) if bcast_ms else None,
+           "kernel": "ob2::tc::apply_tc_kernel<2> (+ expand_d_kernel)",
+           "roofline": {"bound": "tensor", "unit": "TFLOP/s", "achieved": ach, "peak": fp4_peak * world,
+                        "frac": ach / (fp4_peak * world), "peak_source": fp4_src,
+                        "note": "64 fp4 bit-MACs (x 2 flops) per GF(256) MAC; the time includes the fp4 expansion of D"},
+           "parity": {"rows_recomputed_numpy_per_rank": 4, "rows_vs_reference_oaxpy_loop": ref_rows, "columns": ncheck,
+                      "ok": bool(int(okt[0]))}}
+    if cpu:
+        res["cpu_baseline"] = cpu
+    del Cm, D, Y
+    torch.cuda.empty_cache()
+    return res
+
+
+def other_configs(L_, capi, device, torch, dist, world, rank, hbm_peak, sms, sm_mhz, with_cpu):
+    from oblas_b200.capi import GF2, GF4, GF16
+    common = (L_, capi, device, torch, dist, world, rank, hbm_peak, sms, sm_mhz, with_cpu)
+    out = []
+    out.append(solve_config("configs[2]: GF(2) binmat elimination K=8192 bit-packed, batch of 256", GF2, 8192, 256, *common))
+    out.append(solve_config("configs[3]: GF(16) packed-nibble elimination K=2048, batch of 1024", GF16, 2048, 1024, *common))
+    out.append(solve_config("configs[3]: GF(4) packed 2-bit elimination K=2048, batch of 1024 (true field arithmetic)", GF4, 2048, 1024, *common))
+    out.append(apply_config(L_, capi, device, torch, dist, world, rank, with_cpu))
+    return out
 
 
 def main():
@@ -532,6 +977,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-rowops", action="store_true")
+    ap.add_argument("--skip-other", action="store_true", help="skip BASELINE configs[2..4] (other_configs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -60,8 +60,16 @@ extern "C" {
 #define OBLAS_B200_MUL_LUT 1
 
 /* ---- context ------------------------------------------------------------ */
-int oblas_b200_init(int device);          /* idempotent; device < 0: keep current */
-void oblas_b200_shutdown(void);
+/* One context per CUDA device.  oblas_b200_init(device) creates the context of `device` if needed
+ * and makes it the one the CALLING HOST THREAD works on (thread-local); the first device ever
+ * initialised is the process default for threads that never chose.  device < 0: the default (or,
+ * before any init, CUDA's current device).  Idempotent.  oblas_b200_set_device is the same call
+ * under the name the multi-GPU callers use: one host thread per GPU, each thread calls
+ * oblas_b200_set_device(d) once and then any other entry point.  Stream, tuning and workspace
+ * settings belong to the device context. */
+int oblas_b200_init(int device);
+int oblas_b200_set_device(int device);
+void oblas_b200_shutdown(void);           /* releases the contexts of all devices */
 int oblas_b200_device(void);
 int oblas_b200_sm_count(void);
 const char *oblas_b200_last_error(void);
@@ -71,7 +79,12 @@ const char *oblas_b200_last_error(void);
 void oblas_b200_set_stream(void *cuda_stream);
 void oblas_b200_use_own_stream(void);
 void *oblas_b200_get_stream(void);
-int oblas_b200_sync(void);                /* wait for the current stream */
+/* wait for the current stream; also collects the status words of the tensor-core kernels: returns
+ * an error if a barrier wait of a launch since the last collection ran into its time limit (the
+ * result of that launch is invalid).  oblas_b200_solve_batch / oblas_b200_gf256_apply only enqueue:
+ * callers must sync (here, or on the stream they passed) before using the results, and should do it
+ * through this call.  The host-buffer entry points and the struct API collect it themselves. */
+int oblas_b200_sync(void);
 /* drop-in (layer 1) calls synchronise before returning unless async != 0, in
  * which case they only enqueue and the caller must oblas_b200_sync() before
  * touching `bits` from the host */
@@ -85,6 +98,18 @@ void oblas_b200_set_async(int async);
  * Kc >= 64, nbytes >= 480; solve: GF(256), rows >= 512, cols >= 256, strided batches) and the
  * shared-memory table kernels otherwise. */
 void oblas_b200_set_tuning(int solve_geo, int apply_geo);
+/* Bytes of device workspace (fp4 operand blocks, coefficient matrices E, row maps) the tensor-core
+ * paths may hold per stream; default 3 GiB, 0 restores it.  A batch / column range that needs more
+ * runs as several chunks of systems (elimination) or several column passes (apply) -- identical
+ * results.  Returns the previous value. */
+size_t oblas_b200_set_workspace_budget(size_t bytes);
+/* Every pipeline barrier wait inside the tensor-core kernels is bounded by WALL time (%globaltimer):
+ * default 10 s, ms <= 0 restores it.  A wait that gives up sets the launch's status word (see
+ * oblas_b200_sync); the kernel then drains, releases its tensor memory and exits. */
+void oblas_b200_set_wait_limit_ms(int ms);
+/* TESTS ONLY: bits = 8 makes the operand producer of the tensor-core kernels stop delivering, which
+ * forces the give-up path above; 0 = normal operation. */
+void oblas_b200_set_fault_injection(int bits);
 /* diagnostics/tests (identical results, slower): bit 0 disables the register-resident fast panel
  * factorisation, bit 1 the look-ahead of the outer-panel kernel (candidate elimination of the next
  * 16-column step overlapped with the current step's tile pass) */
@@ -158,6 +183,15 @@ int oblas_b200_solve_batch(int field, void *A, size_t a_row_stride, size_t a_sys
                            size_t b_row_bytes, int32_t *rank_out,
                            uint32_t *pivcols_out, size_t nsys);
 
+/* How oblas_b200_solve_batch would run a batch of this shape with the current settings:
+ * *path = 1 tensor-core elimination (GF(256), outer panels of 128 columns + tcgen05 rank-128
+ * updates), 0 shared-memory table kernel; *chunk_systems = systems per chunk of the tensor-core path
+ * (workspace budget / per-system workspace), nsys on the table kernel; geometry[3] = {panel width in
+ * 32-bit words (NBW), coefficient bits per look-up table (KB), table entry / tile width in bytes (WT)}
+ * of the Four-Russians kernel that runs.  Any output may be NULL.  Fails if the rows do not fit. */
+int oblas_b200_solve_plan(int field, uint32_t rows, uint32_t cols, size_t a_row_bytes, size_t b_row_bytes,
+                          size_t nsys, int *path, size_t *chunk_systems, int *geometry);
+
 /* Same job with HOST buffers (pinned for full speed, pageable works): systems are
  * streamed host -> device -> host in chunks, copies overlapped with the
  * elimination of the neighbouring chunks.  rank_out/pivcols_out are host arrays.
@@ -167,6 +201,19 @@ int oblas_b200_solve_batch_host(int field, void *A_host, size_t a_row_stride, si
                                 void *B_host, size_t b_row_stride, size_t b_sys_stride,
                                 size_t b_row_bytes, int32_t *rank_out,
                                 uint32_t *pivcols_out, size_t nsys, size_t chunk_systems);
+
+/* The same with flags.  OBLAS_B200_SOLVE_SKIP_IDENTITY_A: for square systems the reduced A of a
+ * full-rank system is the identity matrix -- known in advance -- so it is NOT copied back: A_host
+ * keeps the input for systems with rank_out[s] == rows and receives the reduced form only for the
+ * rank-deficient ones.  Saves rows*cols of the (rows*cols + rows*b_row_bytes) bytes returned per
+ * system (44 % at K=1024 with 1280-byte symbols). */
+#define OBLAS_B200_SOLVE_SKIP_IDENTITY_A 1u
+int oblas_b200_solve_batch_host_ex(int field, void *A_host, size_t a_row_stride, size_t a_sys_stride,
+                                   uint32_t rows, uint32_t cols, size_t a_row_bytes,
+                                   void *B_host, size_t b_row_stride, size_t b_sys_stride,
+                                   size_t b_row_bytes, int32_t *rank_out,
+                                   uint32_t *pivcols_out, size_t nsys, size_t chunk_systems,
+                                   unsigned flags);
 
 /* ---- dense apply (row a-12) ---------------------------------------------- */
 /* Y (M x nbytes) = C (M x Kc GF(256) coefficients) * D (Kc x nbytes), i.e. the

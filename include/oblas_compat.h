@@ -14,7 +14,7 @@
  *     malloc'd blocks), never with free().
  *   - the tables are `extern const` arrays exported by the library instead of
  *     `static const` arrays in a header; values are byte-identical
- *     (tests/test_tables.py).
+ *     (tests/test_abi.py::test_exported_tables_match_golden).
  *   - *_batch forms of the row operations are added (one launch for n rows).
  *
  * Reference citations are relative to /root/reference.
@@ -174,12 +174,14 @@ void binmat_swaprow_batch(binmat *m, const unsigned *i, const unsigned *j, size_
 
 /* ---- additions: the caller-side loops as single calls ------------------------ */
 /* In-place column-skipping Gauss-Jordan of A with the same row operations applied
- * to B (may be NULL); returns the rank; pivcols (may be NULL) receives rank column
- * indices.  Exactly the bytes the oswaprow/oscal/oaxpy loop of DESIGN.md leaves. */
+ * to B (may be NULL); returns the rank; pivcols (may be NULL) receives the rank pivot
+ * column indices: only entries [0, rank) are written, so an array of min(rows, cols) entries is
+ * always large enough.  B needs at least A->rows rows.  Exactly the bytes the oswaprow/oscal/oaxpy loop of DESIGN.md leaves. */
 unsigned octmat_solve(octmat *A, octmat *B, unsigned *pivcols);
 unsigned gfmat_solve(gfmat *A, gfmat *B, unsigned *pivcols);
 unsigned binmat_rref(binmat *A, binmat *B, unsigned *pivcols);
-/* n independent systems of identical shape */
+/* n independent systems of identical shape (rows, cols, stride, field; checked -- a mixed batch
+ * terminates like every other misuse of the void API) */
 void octmat_solve_batch(octmat **A, octmat **B, unsigned *rank, size_t n);
 void gfmat_solve_batch(gfmat **A, gfmat **B, unsigned *rank, size_t n);
 void binmat_rref_batch(binmat **A, binmat **B, unsigned *rank, size_t n);

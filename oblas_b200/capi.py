@@ -55,6 +55,11 @@ def lib():
     L = C.CDLL(LIB_PATH)
     vp, sz, u32, u64, ci = C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_int
     L.oblas_b200_init.argtypes = [ci]
+    L.oblas_b200_set_device.argtypes = [ci]
+    L.oblas_b200_set_wait_limit_ms.argtypes = [ci]
+    L.oblas_b200_set_fault_injection.argtypes = [ci]
+    L.oblas_b200_set_workspace_budget.argtypes = [sz]
+    L.oblas_b200_set_workspace_budget.restype = sz
     L.oblas_b200_device.restype = ci
     L.oblas_b200_sm_count.restype = ci
     L.oblas_b200_last_error.restype = C.c_char_p
@@ -88,7 +93,9 @@ def lib():
     L.oblas_b200_fill_random.argtypes = [vp, sz, u64, u64]
     L.oblas_b200_rowops.argtypes = [ci, ci, ci, ci, vp, sz, vp, sz, sz, vp, vp, vp, sz]
     L.oblas_b200_solve_batch.argtypes = [ci, vp, sz, sz, u32, u32, sz, vp, sz, sz, sz, vp, vp, sz]
+    L.oblas_b200_solve_plan.argtypes = [ci, u32, u32, sz, sz, sz, C.POINTER(ci), C.POINTER(sz), C.POINTER(ci)]
     L.oblas_b200_solve_batch_host.argtypes = [ci, vp, sz, sz, u32, u32, sz, vp, sz, sz, sz, vp, vp, sz, sz]
+    L.oblas_b200_solve_batch_host_ex.argtypes = [ci, vp, sz, sz, u32, u32, sz, vp, sz, sz, sz, vp, vp, sz, sz, C.c_uint]
     L.oblas_b200_gf256_apply.argtypes = [vp, sz, u32, u32, vp, sz, vp, sz, sz, ci]
     L.oblas_b200_nnz_batch.argtypes = [ci, vp, sz, u32, vp, sz, u32, u32, vp]
     _bind_compat(L)
@@ -193,12 +200,12 @@ TABLE_SYMBOLS = {
     "GF2_2_LOG": 4, "GF2_2_EXP": 6, "GF2_2_INV": 4, "GF2_2_SHUF_LO": 64, "GF2_2_SHUF_HI": 64,
 }
 EXTENSION_SYMBOLS = [
-    "oblas_b200_init", "oblas_b200_shutdown", "oblas_b200_device", "oblas_b200_sm_count",
+    "oblas_b200_init", "oblas_b200_set_device", "oblas_b200_set_workspace_budget", "oblas_b200_set_wait_limit_ms", "oblas_b200_set_fault_injection", "oblas_b200_shutdown", "oblas_b200_device", "oblas_b200_sm_count",
     "oblas_b200_last_error", "oblas_b200_set_stream", "oblas_b200_use_own_stream", "oblas_b200_get_stream", "oblas_b200_sync",
     "oblas_b200_set_async", "oblas_b200_set_tuning", "oblas_b200_solve_tc_times", "oblas_b200_set_panel_path", "oblas_b200_solve_phases", "oblas_b200_update_phases", "oblas_b200_launch_count", "oblas_b200_dev_alloc", "oblas_b200_dev_free",
     "oblas_b200_host_alloc", "oblas_b200_host_free", "oblas_b200_managed_alloc", "oblas_b200_free",
     "oblas_b200_copy", "oblas_b200_memset", "oblas_b200_fill_random", "oblas_b200_rowops",
-    "oblas_b200_solve_batch", "oblas_b200_solve_batch_host", "oblas_b200_gf256_apply",
+    "oblas_b200_solve_batch", "oblas_b200_solve_plan", "oblas_b200_solve_batch_host", "oblas_b200_solve_batch_host_ex", "oblas_b200_gf256_apply",
     "oblas_b200_nnz_batch", "oblas_b200_swapcols_batch", "oblas_b200_make_tables", "oblas_b200_register_tables", "oblas_b200_get_elements", "oblas_b200_set_elements",
     "octmat_new_aligned", "gfmat_new_aligned",
     "oaxpy_batch", "oaddrow_batch", "oscal_batch", "oswaprow_batch", "gfmat_axpy_batch",

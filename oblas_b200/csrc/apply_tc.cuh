@@ -79,7 +79,12 @@ constexpr int kThreads = 32 * (kEpi0 + kEpiWarps);
 constexpr int kLutCopies = 3;
 constexpr int kLutCopyBytes = 256 * 32;
 constexpr int kLutBytes = kLutCopies * kLutCopyBytes;
-constexpr uint32_t kSpinLimit = 1u << 24;    // bounded waits: never hang the device
+// Bounded waits, never a hung device: a barrier wait gives up after a limit of WALL time
+// (%globaltimer, read every 256 polls), not after a number of polls -- under time-slicing, MPS, a
+// profiler's replay or a long tcgen05.alloc stall a legitimate wait may need many polls.  The status
+// block of a launch is {flag, limit in ms} in mapped host memory (default kWaitLimitMs;
+// oblas_b200_set_wait_limit_ms).
+constexpr int kWaitLimitMs = 10000;
 
 template <int NH>
 struct Cfg {
@@ -129,8 +134,9 @@ struct ApplyTcArgs {
   TcRegion reg[2];         // Y
   uint32_t nreg;
   int accumulate;
-  int *status;             // set to 1 if a barrier wait ran into the spin limit
-  int dbg;                 // diagnostics (timing experiments only, results invalid): 1 = no bulk loads, 2 = no A build, 4 = no epilogue
+  int *status;             // {flag, wait limit in ms}: flag is set to 1 if a barrier wait ran into the time limit
+  int dbg;                 // diagnostics (timing experiments only, results invalid): 1 = no bulk loads, 2 = no A build, 4 = no epilogue;
+                           // 8 = fault injection for the time-out test: the B-operand producer never delivers
   // diagnostics (update_tc_kernel, may be null): SM cycles of one thread per role summed over CTAs --
   // MMA thread: 0 wait A built, 1 wait accumulators drained, 2 wait B stage, 3 whole loop;
   // epilogue warp 0: 4 wait accumulators complete, 5 read-out + stores, 6 whole loop; producer: 7 wait
@@ -214,15 +220,31 @@ OB2_D void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 // false = gave up (status flag set); every caller then leaves its loop.  backoff_ns > 0 for
 // waits that are expected to be long (keeps the pollers off the LSU pipe).
+OB2_D unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+OB2_D bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
+               "selp.u32 %0, 1, 0, q;\n\t}"
+               : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done != 0;
+}
 OB2_D bool mbar_wait(uint32_t bar, uint32_t parity, int *status, uint32_t backoff_ns = 0) {
-  for (uint32_t spin = 0; spin < kSpinLimit; spin++) {
-    uint32_t done;
-    asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
-                 "selp.u32 %0, 1, 0, q;\n\t}"
-                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (done) return true;
+  if (mbar_try(bar, parity)) return true;
+  unsigned long long t0 = 0;
+  for (uint32_t spin = 1;; spin++) {
+    if (mbar_try(bar, parity)) return true;
     if (backoff_ns) __nanosleep(backoff_ns);
-    if ((spin & 1023u) == 1023u && *reinterpret_cast<volatile int *>(status) != 0) break;
+    if ((spin & 255u) == 0u) {
+      // another role of this launch (or an earlier launch on this stream) already gave up
+      if (*reinterpret_cast<volatile int *>(status) != 0) break;
+      const unsigned long long now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 1000000ull * (unsigned long long)reinterpret_cast<volatile int *>(status)[1]) break;
+    }
   }
   atomicExch(status, 1);
   return false;
@@ -551,7 +573,7 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
       const uint8_t *src = p.Dx + (size_t)snt * NH * ksteps * kHBlock;
       for (uint32_t st = 0; st < nst; st++, src += kSPS * kHBlock) {
         if (!mbar_wait(empty_bar(s), ph ^ 1u, p.status)) { ok = false; break; }
-        if (leader) {
+        if (leader && !(p.dbg & 8)) {
           if (p.dbg & 1) {
             mbar_arrive(full_bar(s));
           } else {
@@ -853,7 +875,7 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
         const long long w0 = prof ? clock64() : 0;
         if (!mbar_wait(b_empty(s), ph ^ 1u, p.status)) { ok = false; break; }
         if (prof) pw += clock64() - w0;
-        if (leader) {
+        if (leader && !(p.dbg & 8)) {
           if (p.dbg & 1) {
             mbar_arrive(b_full(s));
           } else {
@@ -1155,7 +1177,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) update_
         const uint32_t hbytes = tile_width(nt) * 16u;                 // N/2 columns x 32 bytes
         const uint8_t *src = src0 + ((size_t)nt * kUSteps + cs * kUSPS) * kHBlock + (size_t)rank * hbytes;
         if (!mbar_wait(b_empty(s), ph ^ 1u, p.status)) { ok = false; break; }
-        if (leader) {
+        if (leader && !(p.dbg & 8)) {
           if (p.dbg & 1) {
             mbar_arrive(b_full(s));
           } else {

@@ -3,7 +3,7 @@
 // Replaces the generated headers of the reference (gf2_2_tables.h, gf2_4_tables.h,
 // gf2_8_tables.h; generator tablegen.c:29-106).  Values are derived here from the
 // field polynomials (tablegen.c:7-12: 7, 19, 285) by carry-less multiplication;
-// tests/test_tables.py proves them byte-identical to the reference's arrays,
+// tests/test_abi.py::test_exported_tables_match_golden and tests/test_oracle.py prove them byte-identical to the reference's arrays,
 // INCLUDING the shipped GF(4) high-nibble defect (tablegen.c:84-88 assigns the
 // HI entry only when the low 2-bit element of the nibble is non-zero, so
 // gf2_2_tables.h:30-32 hold 0 at nibbles 4, 8, 12).  `hi_fix` is the table the

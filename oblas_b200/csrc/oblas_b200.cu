@@ -49,7 +49,16 @@ struct Ctx {
   } tc_slots[8];
   void *tc_ws = nullptr;      // workspace of the current stream (set by tc_ws_reserve)
   size_t tc_ws_bytes = 0;
-  int *tc_status = nullptr;  // pinned + mapped: the kernel sets it if a barrier wait gave up
+  // pinned + mapped, one word per workspace slot: a kernel sets its slot's word when a barrier wait
+  // gave up (time limit); a failure on one stream does not stop the kernels of the other lanes
+  int *tc_status = nullptr;   // [8 slots][2]: {flag, wait limit in ms}
+  int tc_wait_limit_ms = ob2::tc::kWaitLimitMs;
+  int tc_inject = 0;          // tests: fault-injection bits OR-ed into ApplyTcArgs::dbg
+  int tc_cur_slot = 0;
+  size_t tc_ws_budget = (size_t)3 << 30;   // bytes of operand workspace per stream (oblas_b200_set_workspace_budget)
+  bool tc_attr_set = false, perm_attr_set = false;   // cudaFuncSetAttribute is per device
+  int max_clusters = -1;
+  uint32_t *d_zero = nullptr;  // a device word holding row index 0 (single-row launches)
   // diagnostics: CUDA-event timing of the kernel classes of the tensor-core elimination
   bool tc_timing = false;
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> tc_events;  // (class, (start, stop))
@@ -66,10 +75,33 @@ struct Ctx {
   size_t scratch_bytes = 0;
   std::mutex mu;
   std::atomic<uint64_t> launches{0};
+  // lanes of the host-streaming pipeline (oblas_b200_solve_batch_host): chunk c runs on lane c % kLanes
+  // (own stream, own device buffers); kept between calls (cudaMalloc/cudaFree of GB-sized blocks
+  // costs more than the elimination of a chunk)
+  static constexpr int kLanes = 3;
+  struct HostLane {
+    cudaStream_t s = nullptr;
+    uint8_t *A = nullptr, *B = nullptr;
+    int32_t *rank = nullptr;
+    uint32_t *piv = nullptr;
+    size_t a_cap = 0, b_cap = 0, r_cap = 0, p_cap = 0;
+  } lane[kLanes];
+  void *pin = nullptr;  // pinned staging for rank / pivcols of a whole host-streaming call
+  size_t pin_cap = 0;
 };
-Ctx g;
+// One context per CUDA device.  A host thread works on the device it selected with
+// oblas_b200_set_device (thread-local), else on the process default = the device of the first
+// oblas_b200_init.  Settings made through oblas_b200_set_* apply to the calling thread's device.
+constexpr int kMaxDev = 16;
+Ctx g_ctx[kMaxDev];
+std::atomic<int> g_default_dev{-1};
+thread_local int tl_dev = -1;
+inline Ctx &cx() {
+  int d = tl_dev >= 0 ? tl_dev : g_default_dev.load(std::memory_order_relaxed);
+  return g_ctx[d < 0 ? 0 : d];
+}
 thread_local char tl_err[512] = "";
-void lanes_release();  // host-streaming lanes, defined with oblas_b200_solve_batch_host
+void lanes_release(Ctx &c);  // host-streaming lanes, defined with oblas_b200_solve_batch_host
 
 int fail(const char *fmt, ...) {
   va_list ap;
@@ -86,8 +118,12 @@ int fail(const char *fmt, ...) {
   } while (0)
 
 int ensure_init() {
-  if (g.ready) return 0;
-  return oblas_b200_init(-1);
+  Ctx &c = cx();
+  if (!c.ready) return oblas_b200_init(tl_dev);
+  // entry points may be called from any host thread: make the context's device current
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != c.device) CK(cudaSetDevice(c.device));
+  return 0;
 }
 
 // The void functions of the reference API cannot report errors; like the
@@ -116,29 +152,29 @@ PtrKind classify(const void *p) {
 }
 
 int scratch_reserve(size_t bytes) {
-  if (bytes <= g.scratch_bytes) return 0;
-  if (g.scratch) {
-    CK(cudaStreamSynchronize(g.stream));
-    CK(cudaFree(g.scratch));
-    g.scratch = nullptr;
-    g.scratch_bytes = 0;
+  if (bytes <= cx().scratch_bytes) return 0;
+  if (cx().scratch) {
+    CK(cudaStreamSynchronize(cx().stream));
+    CK(cudaFree(cx().scratch));
+    cx().scratch = nullptr;
+    cx().scratch_bytes = 0;
   }
   size_t want = bytes < (1u << 20) ? (1u << 20) : bytes * 2;
-  CK(cudaMalloc(&g.scratch, want));
-  g.scratch_bytes = want;
+  CK(cudaMalloc(&cx().scratch, want));
+  cx().scratch_bytes = want;
   return 0;
 }
 
 int after_launch(const char *what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail("%s launch failed: %s", what, cudaGetErrorString(e));
-  g.launches.fetch_add(1, std::memory_order_relaxed);
+  cx().launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
 
 int finish_dropin() {
-  if (g.async) return 0;
-  CK(cudaStreamSynchronize(g.stream));
+  if (cx().async) return 0;
+  CK(cudaStreamSynchronize(cx().stream));
   return 0;
 }
 
@@ -245,101 +281,143 @@ __global__ void set_elements_kernel(uint8_t *bits, size_t row_stride, const uint
 extern "C" {
 
 int oblas_b200_init(int device) {
-  std::lock_guard<std::mutex> lk(g.mu);
-  if (g.ready) {
-    if (device >= 0 && device != g.device) return fail("already initialised on device %d", g.device);
-    return 0;
-  }
   int n = 0;
   CK(cudaGetDeviceCount(&n));
   if (n <= 0) return fail("no CUDA device");
-  if (device < 0) {
-    CK(cudaGetDevice(&device));
-  }
+  if (device < 0) device = g_default_dev.load();
+  if (device < 0) CK(cudaGetDevice(&device));
+  if (device >= n || device >= kMaxDev) return fail("no CUDA device %d (%d visible, at most %d supported)", device, n, kMaxDev);
+  Ctx &c = g_ctx[device];
+  std::lock_guard<std::mutex> lk(c.mu);
   CK(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 10)
-    return fail("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
-  g.device = device;
-  g.sm_count = prop.multiProcessorCount;
-  g.smem_optin = prop.sharedMemPerBlockOptin;
-  CK(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
-  g.stream = g.own_stream;
-  fill_all_table_sets(g.h_sets);
-  CK(cudaMalloc(&g.d_sets, sizeof(DevTableSet) * TS_COUNT));
-  CK(cudaMemcpy(g.d_sets, g.h_sets, sizeof(DevTableSet) * TS_COUNT, cudaMemcpyHostToDevice));
-  g.ready = true;
+  if (!c.ready) {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+      return fail("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    c.device = device;
+    c.sm_count = prop.multiProcessorCount;
+    c.smem_optin = prop.sharedMemPerBlockOptin;
+    CK(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+    c.stream = c.own_stream;
+    fill_all_table_sets(c.h_sets);
+    CK(cudaMalloc(&c.d_sets, sizeof(DevTableSet) * TS_COUNT));
+    CK(cudaMemcpy(c.d_sets, c.h_sets, sizeof(DevTableSet) * TS_COUNT, cudaMemcpyHostToDevice));
+    c.ready = true;
+  }
+  int none = -1;
+  g_default_dev.compare_exchange_strong(none, device);
+  tl_dev = device;   // the calling thread works on this device from now on
   return 0;
 }
 
-void oblas_b200_shutdown(void) {
-  std::lock_guard<std::mutex> lk(g.mu);
-  if (!g.ready) return;
-  cudaStreamSynchronize(g.stream);
-  if (g.scratch) cudaFree(g.scratch);
-  g.scratch = nullptr;
-  g.scratch_bytes = 0;
-  for (auto &w : g.tc_slots) {
+// Selects the device the calling host thread works on (its context is created on first use).
+int oblas_b200_set_device(int device) { return oblas_b200_init(device); }
+
+static void shutdown_ctx(Ctx &c) {
+  std::lock_guard<std::mutex> lk(c.mu);
+  if (!c.ready) return;
+  cudaSetDevice(c.device);
+  cudaStreamSynchronize(c.stream);
+  if (c.scratch) cudaFree(c.scratch);
+  c.scratch = nullptr;
+  c.scratch_bytes = 0;
+  for (auto &w : c.tc_slots) {
     if (w.p) cudaFree(w.p);
     w = Ctx::TcWs();
   }
-  g.tc_ws = nullptr;
-  g.tc_ws_bytes = 0;
-  if (g.tc_status) cudaFreeHost(g.tc_status);
-  g.tc_status = nullptr;
-  lanes_release();
-  for (auto *d : g.d_custom) cudaFree(d);
-  g.d_custom.clear();
-  g.custom_linear.clear();
-  g.custom_bits.clear();
-  cudaFree(g.d_sets);
-  g.d_sets = nullptr;
-  cudaStreamDestroy(g.own_stream);
-  g.own_stream = g.stream = nullptr;
-  g.ready = false;
+  c.tc_ws = nullptr;
+  c.tc_ws_bytes = 0;
+  if (c.tc_status) cudaFreeHost(c.tc_status);
+  c.tc_status = nullptr;
+  c.tc_attr_set = c.perm_attr_set = false;
+  c.max_clusters = -1;
+  if (c.d_zero) cudaFree(c.d_zero);
+  c.d_zero = nullptr;
+  if (c.d_phase) cudaFree(c.d_phase);
+  if (c.d_uprof) cudaFree(c.d_uprof);
+  c.d_phase = c.d_uprof = nullptr;
+  lanes_release(c);
+  for (auto *d : c.d_custom) cudaFree(d);
+  c.d_custom.clear();
+  c.custom_linear.clear();
+  c.custom_bits.clear();
+  cudaFree(c.d_sets);
+  c.d_sets = nullptr;
+  cudaStreamDestroy(c.own_stream);
+  c.own_stream = c.stream = nullptr;
+  c.ready = false;
+}
+// releases the contexts of ALL devices (the thread-local device selection of other threads
+// becomes stale: their next call re-initialises that device)
+void oblas_b200_shutdown(void) {
+  for (auto &c : g_ctx) shutdown_ctx(c);
+  g_default_dev.store(-1);
+  tl_dev = -1;
 }
 
-int oblas_b200_device(void) { return g.ready ? g.device : -1; }
-int oblas_b200_sm_count(void) { return ensure_init() ? -1 : g.sm_count; }
+int oblas_b200_device(void) { return cx().ready ? cx().device : -1; }
+int oblas_b200_sm_count(void) { return ensure_init() ? -1 : cx().sm_count; }
 const char *oblas_b200_last_error(void) { return tl_err; }
 void oblas_b200_set_stream(void *s) {
   if (ensure_init()) return;
-  g.stream = (cudaStream_t)s;  // NULL is the legacy default stream
+  cx().stream = (cudaStream_t)s;  // NULL is the legacy default stream
 }
 void oblas_b200_use_own_stream(void) {
   if (ensure_init()) return;
-  g.stream = g.own_stream;
+  cx().stream = cx().own_stream;
 }
-void *oblas_b200_get_stream(void) { return ensure_init() ? nullptr : (void *)g.stream; }
+void *oblas_b200_get_stream(void) { return ensure_init() ? nullptr : (void *)cx().stream; }
 int tc_check_status();
 int oblas_b200_sync(void) {
   if (ensure_init()) return -1;
-  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaStreamSynchronize(cx().stream));
   return tc_check_status();
 }
-void oblas_b200_set_async(int async) { g.async = async != 0; }
-void oblas_b200_set_panel_path(int general_only) { g.no_fast_panel = general_only & 3; }
+void oblas_b200_set_async(int async) { cx().async = async != 0; }
+void oblas_b200_set_panel_path(int general_only) { cx().no_fast_panel = general_only & 3; }
 void oblas_b200_set_tuning(int solve_geo, int apply_geo) {
-  g.solve_geo = solve_geo;
-  g.apply_geo = apply_geo;
+  cx().solve_geo = solve_geo;
+  cx().apply_geo = apply_geo;
 }
-uint64_t oblas_b200_launch_count(void) { return g.launches.load(); }
+uint64_t oblas_b200_launch_count(void) { return cx().launches.load(); }
+// Bytes of operand / coefficient workspace the tensor-core paths may hold per stream (default 3 GiB).
+// Batches and column ranges that need more run as several chunks / passes; results are identical.
+// 0 restores the default.  Returns the previous value.
+// Time limit of a pipeline barrier wait inside the tensor-core kernels (default 10 s; <= 0 restores it).
+void oblas_b200_set_wait_limit_ms(int ms) {
+  if (ensure_init()) return;
+  std::lock_guard<std::mutex> lk(cx().mu);
+  cx().tc_wait_limit_ms = ms > 0 ? ms : ob2::tc::kWaitLimitMs;
+}
+// TESTS ONLY.  bits = 8: the B-operand producer of the tensor-core kernels never delivers, so every
+// consumer wait runs into the time limit -- the give-up path (status word, TMEM release) under test.
+void oblas_b200_set_fault_injection(int bits) {
+  if (ensure_init()) return;
+  cx().tc_inject = bits & 8;
+}
+size_t oblas_b200_set_workspace_budget(size_t bytes) {
+  if (ensure_init()) return 0;
+  std::lock_guard<std::mutex> lk(cx().mu);
+  const size_t old = cx().tc_ws_budget;
+  cx().tc_ws_budget = bytes ? bytes : (size_t)3 << 30;
+  return old;
+}
 // diagnostics: enable != 0 starts (and zeroes) per-phase cycle counters of the elimination
 // kernel; out (may be NULL) receives 4 counters: panel load, panel factorisation,
 // trailing update, permutation -- SM cycles of thread 0 summed over all CTAs
 int oblas_b200_solve_phases(int enable, uint64_t *out) {
   if (ensure_init()) return -1;
-  if (out && g.d_phase) {
-    CK(cudaStreamSynchronize(g.stream));
-    CK(cudaMemcpy(out, g.d_phase, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  if (out && cx().d_phase) {
+    CK(cudaStreamSynchronize(cx().stream));
+    CK(cudaMemcpy(out, cx().d_phase, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   }
   if (enable) {
-    if (!g.d_phase) CK(cudaMalloc(&g.d_phase, 8 * sizeof(uint64_t)));
-    CK(cudaMemset(g.d_phase, 0, 8 * sizeof(uint64_t)));
-  } else if (g.d_phase) {
-    CK(cudaFree(g.d_phase));
-    g.d_phase = nullptr;
+    if (!cx().d_phase) CK(cudaMalloc(&cx().d_phase, 8 * sizeof(uint64_t)));
+    CK(cudaMemset(cx().d_phase, 0, 8 * sizeof(uint64_t)));
+  } else if (cx().d_phase) {
+    CK(cudaFree(cx().d_phase));
+    cx().d_phase = nullptr;
   }
   return 0;
 }
@@ -393,7 +471,7 @@ void oblas_b200_free(void *p) {
   switch (at.type) {
   case cudaMemoryTypeDevice:
   case cudaMemoryTypeManaged:
-    if (g.ready) cudaStreamSynchronize(g.stream);
+    if (cx().ready) cudaStreamSynchronize(cx().stream);
     cudaFree(p);
     break;
   case cudaMemoryTypeHost:
@@ -405,12 +483,12 @@ void oblas_b200_free(void *p) {
 }
 int oblas_b200_copy(void *dst, const void *src, size_t bytes) {
   if (ensure_init()) return -1;
-  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, g.stream));
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, cx().stream));
   return 0;
 }
 int oblas_b200_memset(void *dst, int value, size_t bytes) {
   if (ensure_init()) return -1;
-  CK(cudaMemsetAsync(dst, value, bytes, g.stream));
+  CK(cudaMemsetAsync(dst, value, bytes, cx().stream));
   return 0;
 }
 int oblas_b200_fill_random(void *dst, size_t bytes, uint64_t seed, uint64_t byte_offset) {
@@ -420,8 +498,8 @@ int oblas_b200_fill_random(void *dst, size_t bytes, uint64_t seed, uint64_t byte
   size_t nwords = bytes / 8;
   if (!nwords) return 0;
   size_t blocks = (nwords + 255) / 256;
-  if (blocks > (size_t)g.sm_count * 16) blocks = (size_t)g.sm_count * 16;
-  fill_random_kernel<<<(unsigned)blocks, 256, 0, g.stream>>>((uint64_t *)dst, nwords, seed, byte_offset / 8);
+  if (blocks > (size_t)cx().sm_count * 16) blocks = (size_t)cx().sm_count * 16;
+  fill_random_kernel<<<(unsigned)blocks, 256, 0, cx().stream>>>((uint64_t *)dst, nwords, seed, byte_offset / 8);
   return after_launch("fill_random");
 }
 
@@ -437,8 +515,8 @@ static int stage_array(const void *src, size_t bytes, size_t slot, const void **
     *out = src;
     return 0;
   }
-  void *dst = (char *)g.scratch + slot;
-  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g.stream));
+  void *dst = (char *)cx().scratch + slot;
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, cx().stream));
   *out = dst;
   return 0;
 }
@@ -465,18 +543,19 @@ int oblas_b200_rowops(int field, int variant, int op, int mul_mode, void *a, siz
     return fail("rowops: matrix pointers must be device-visible (device, managed or pinned)");
   const bool needs_tab = (op == OP_AXPY || op == OP_SCAL);
   int ts = -1, mode = MUL_LIN;
+  std::lock_guard<std::mutex> lk(cx().mu);   // before the table-handle lookup: register_tables appends concurrently
   if (needs_tab && field != OB2_GF2) {
     bool linear;
     if (variant >= 16) {   // table set registered with oblas_b200_register_tables
       const size_t ci = (size_t)variant - 16;
-      if (ci >= g.d_custom.size()) return fail("rowops: unknown table handle %d", variant);
-      if (g.custom_bits[ci] != (int)kBits[field]) return fail("rowops: table handle %d is for %d-bit elements", variant, g.custom_bits[ci]);
+      if (ci >= cx().d_custom.size()) return fail("rowops: unknown table handle %d", variant);
+      if (cx().custom_bits[ci] != (int)kBits[field]) return fail("rowops: table handle %d is for %d-bit elements", variant, cx().custom_bits[ci]);
       ts = 1000 + (int)ci;
-      linear = g.custom_linear[ci] != 0;
+      linear = cx().custom_linear[ci] != 0;
     } else {
       ts = table_set_id(field, variant);
       if (ts < 0) return fail("rowops: bad field %d", field);
-      linear = g.h_sets[ts].linear != 0;
+      linear = cx().h_sets[ts].linear != 0;
     }
     if (mul_mode == OBLAS_B200_MUL_AUTO) mode = linear ? MUL_LIN : MUL_LUT;
     else if (mul_mode == OBLAS_B200_MUL_LIN) {
@@ -484,10 +563,10 @@ int oblas_b200_rowops(int field, int variant, int op, int mul_mode, void *a, siz
       mode = MUL_LIN;
     } else mode = MUL_LUT;
   }
-  // GF(2) has no tables (gfmat.c:14-19): only u in {0,1} is meaningful (u==1 is XOR,
-  // the reference dereferences NULL for u>1); give the kernel a valid set anyway
+  // GF(2) has no tables (gfmat.c:14-19): the only scalars are 0 and 1 (u == 1 is XOR; the reference
+  // dereferences NULL for u > 1).  u > 1 is a no-op here, in single calls and in batches alike
+  // (RowOpArgs::u_max); the kernel still gets a valid table set.
   if (needs_tab && field == OB2_GF2) ts = TS_GF4_FIXED;
-  std::lock_guard<std::mutex> lk(g.mu);
   const size_t idx_bytes = nops * sizeof(uint32_t);
   const size_t slot1 = (idx_bytes + 255) & ~(size_t)255, slot2 = 2 * slot1;
   if (scratch_reserve(slot2 + nops + 256)) return -1;
@@ -514,8 +593,9 @@ int oblas_b200_rowops(int field, int variant, int op, int mul_mode, void *a, siz
     p.dst_rows = (const uint32_t *)d_dst + first;
     p.src_rows = d_src ? (const uint32_t *)d_src + first : nullptr;
     p.u = d_u ? (const uint8_t *)d_u + first : nullptr;
-    p.ts = ts >= 1000 ? g.d_custom[ts - 1000] : (ts >= 0 ? g.d_sets + ts : nullptr);
-    launch_rowops(op, mode, p, g.stream);
+    p.ts = ts >= 1000 ? cx().d_custom[ts - 1000] : (ts >= 0 ? cx().d_sets + ts : nullptr);
+    p.u_max = field == OB2_GF2 ? 1u : 255u;
+    launch_rowops(op, mode, p, cx().stream);
     if (after_launch("rowops")) return -1;
   }
   return 0;
@@ -525,9 +605,9 @@ int oblas_b200_rowops(int field, int variant, int op, int mul_mode, void *a, siz
 int solve_tc_run(SolveArgs &p, size_t nsys);   // tensor-core path (GF(256)), defined with apply_tc_run
 static bool solve_tc_eligible(int field, const SolveArgs &p, size_t nsys) {
   if (field != OB2_GF256 || p.a_ptrs || p.b_ptrs) return false;
-  if (panel_smem_bytes(p.rows) > g.smem_optin || p.rows > 65535u) return false;
-  if (g.solve_geo == 3) return true;
-  if (g.solve_geo >= 0) return false;
+  if (panel_smem_bytes(p.rows) > cx().smem_optin || p.rows > 65535u) return false;
+  if (cx().solve_geo == 3) return true;
+  if (cx().solve_geo >= 0) return false;
   // auto: the rank-128 tensor-core update pays once the systems are big enough to fill its tiles
   return p.rows >= 512 && p.cols >= 256 && nsys >= 1;
 }
@@ -539,16 +619,16 @@ static int solve_common(int field, SolveArgs &p, size_t nsys) {
   uint32_t ebits = kBits[field];
   if ((size_t)p.cols * ebits > (size_t)p.a_bytes * 8) return fail("solve: cols exceed a_row_bytes");
   int ts = table_set_id(field, 1);
-  p.inv = ts >= 0 ? g.d_sets[ts].inv : nullptr;
+  p.inv = ts >= 0 ? cx().d_sets[ts].inv : nullptr;
   p.nsys = (uint32_t)nsys;
-  p.phase = g.d_phase;
-  p.no_fast_panel = g.no_fast_panel & 1;
-  p.no_look_ahead = (g.no_fast_panel >> 1) & 1;
+  p.phase = cx().d_phase;
+  p.no_fast_panel = cx().no_fast_panel & 1;
+  p.no_look_ahead = (cx().no_fast_panel >> 1) & 1;
   if (solve_tc_eligible(field, p, nsys)) return solve_tc_run(p, nsys);
-  uint32_t grid = nsys < (size_t)g.sm_count ? (uint32_t)nsys : (uint32_t)g.sm_count;
-  int rc = launch_solve(field, g.solve_geo == 3 ? -1 : g.solve_geo, p, grid, 512, g.smem_optin, g.stream);
+  uint32_t grid = nsys < (size_t)cx().sm_count ? (uint32_t)nsys : (uint32_t)cx().sm_count;
+  int rc = launch_solve(field, cx().solve_geo == 3 ? -1 : cx().solve_geo, p, grid, 512, cx().smem_optin, cx().stream);
   if (rc == -1)
-    return fail("solve: %u rows do not fit the shared-memory panel (limit %zu bytes); no fallback", p.rows, g.smem_optin);
+    return fail("solve: %u rows do not fit the shared-memory panel (limit %zu bytes); no fallback", p.rows, cx().smem_optin);
   if (rc) return fail("solve: cudaFuncSetAttribute failed");
   return after_launch("solve");
 }
@@ -572,27 +652,15 @@ int oblas_b200_solve_batch(int field, void *A, size_t a_row_stride, size_t a_sys
   p.B = (uint8_t *)B; p.b_rs = b_row_stride; p.b_ss = b_sys_stride;
   p.b_bytes = B ? (uint32_t)b_row_bytes : 0;
   p.rank = rank_out; p.pivcols = pivcols_out;
-  std::lock_guard<std::mutex> lk(g.mu);
+  std::lock_guard<std::mutex> lk(cx().mu);
   return solve_common(field, p, nsys);
 }
 
 }  // extern "C"
 
-// Lanes of the host-streaming pipeline: chunk c runs on lane c % NL (own stream, own
-// device buffers).  Kept in the context between calls (cudaMalloc/cudaFree of GB-sized
-// blocks costs more than the elimination of a chunk).
 namespace {
-constexpr int kLanes = 3;
-struct HostLane {
-  cudaStream_t s = nullptr;
-  uint8_t *A = nullptr, *B = nullptr;
-  int32_t *rank = nullptr;
-  uint32_t *piv = nullptr;
-  size_t a_cap = 0, b_cap = 0, r_cap = 0, p_cap = 0;
-};
-HostLane g_lane[kLanes];
-void *g_pin = nullptr;  // pinned staging for rank / pivcols of the whole call
-size_t g_pin_cap = 0;
+using HostLane = Ctx::HostLane;
+constexpr int kLanes = Ctx::kLanes;
 
 int lane_reserve(HostLane &L, size_t a, size_t b, size_t r, size_t pv) {
   if (!L.s) CK(cudaStreamCreateWithFlags(&L.s, cudaStreamNonBlocking));
@@ -611,45 +679,48 @@ int lane_reserve(HostLane &L, size_t a, size_t b, size_t r, size_t pv) {
   if (grow((void **)&L.piv, L.p_cap, pv)) return -1;
   return 0;
 }
-void lanes_release() {
-  for (auto &L : g_lane) {
+void lanes_release(Ctx &c) {
+  for (auto &L : c.lane) {
     if (L.s) cudaStreamSynchronize(L.s);
     cudaFree(L.A); cudaFree(L.B); cudaFree(L.rank); cudaFree(L.piv);
     if (L.s) cudaStreamDestroy(L.s);
     L = HostLane();
   }
-  if (g_pin) cudaFreeHost(g_pin);
-  g_pin = nullptr;
-  g_pin_cap = 0;
+  if (c.pin) cudaFreeHost(c.pin);
+  c.pin = nullptr;
+  c.pin_cap = 0;
 }
 }  // namespace
 
 extern "C" {
 
-int oblas_b200_solve_batch_host(int field, void *A_host, size_t a_row_stride, size_t a_sys_stride,
-                                uint32_t rows, uint32_t cols, size_t a_row_bytes, void *B_host,
-                                size_t b_row_stride, size_t b_sys_stride, size_t b_row_bytes,
-                                int32_t *rank_out, uint32_t *pivcols_out, size_t nsys,
-                                size_t chunk_systems) {
+int oblas_b200_solve_batch_host_ex(int field, void *A_host, size_t a_row_stride, size_t a_sys_stride,
+                                   uint32_t rows, uint32_t cols, size_t a_row_bytes, void *B_host,
+                                   size_t b_row_stride, size_t b_sys_stride, size_t b_row_bytes,
+                                   int32_t *rank_out, uint32_t *pivcols_out, size_t nsys,
+                                   size_t chunk_systems, unsigned flags) {
   if (ensure_init()) return -1;
+  // OBLAS_B200_SOLVE_SKIP_IDENTITY_A: the reduced A of a full-rank square system is the identity --
+  // known in advance, so it is not copied back (A_host keeps the input for those systems)
+  const bool skip_ident = (flags & OBLAS_B200_SOLVE_SKIP_IDENTITY_A) && rows == cols;
   if (!A_host || !rank_out) return fail("solve_host: A and rank_out are required");
   if (nsys == 0) return 0;
   if ((a_sys_stride & 15) || (B_host && (b_sys_stride & 15)))
     return fail("solve_host: system strides must be multiples of 16");
-  std::lock_guard<std::mutex> lk(g.mu);
+  std::lock_guard<std::mutex> lk(cx().mu);
   const size_t per_sys = a_sys_stride + (B_host ? b_sys_stride : 0) + 4 + (pivcols_out ? (size_t)rows * 4 : 0);
   if (chunk_systems == 0) {
     // one wave of the persistent grid per chunk: no tail inside a chunk, fine-grained
     // overlap of the copies with the neighbouring chunks' elimination (measured best)
-    chunk_systems = (size_t)g.sm_count;
+    chunk_systems = (size_t)cx().sm_count;
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     size_t have = 0;
-    for (auto &L : g_lane) have += L.a_cap + L.b_cap;
+    for (auto &L : cx().lane) have += L.a_cap + L.b_cap;
     while (chunk_systems > 1 && chunk_systems * per_sys * kLanes > (free_b + have) / 2) chunk_systems /= 2;
   }
   if (chunk_systems > nsys) chunk_systems = nsys;
-  for (auto &L : g_lane)
+  for (auto &L : cx().lane)
     if (lane_reserve(L, chunk_systems * a_sys_stride, B_host ? chunk_systems * b_sys_stride : 0,
                      chunk_systems * 4, pivcols_out ? chunk_systems * (size_t)rows * 4 : 0))
       return -1;
@@ -657,22 +728,22 @@ int oblas_b200_solve_batch_host(int field, void *A_host, size_t a_row_stride, si
   // (usually pageable) rank array would block the host and serialise the lanes
   const size_t pin_rank = (nsys * 4 + 255) & ~(size_t)255;
   const size_t pin_need = pin_rank + (pivcols_out ? nsys * (size_t)rows * 4 : 0);
-  if (pin_need > g_pin_cap) {
-    if (g_pin) CK(cudaFreeHost(g_pin));
-    g_pin = nullptr;
-    g_pin_cap = 0;
-    CK(cudaHostAlloc(&g_pin, pin_need, cudaHostAllocDefault));
-    g_pin_cap = pin_need;
+  if (pin_need > cx().pin_cap) {
+    if (cx().pin) CK(cudaFreeHost(cx().pin));
+    cx().pin = nullptr;
+    cx().pin_cap = 0;
+    CK(cudaHostAlloc(&cx().pin, pin_need, cudaHostAllocDefault));
+    cx().pin_cap = pin_need;
   }
-  int32_t *pin_r = (int32_t *)g_pin;
-  uint32_t *pin_p = (uint32_t *)((uint8_t *)g_pin + pin_rank);
+  int32_t *pin_r = (int32_t *)cx().pin;
+  uint32_t *pin_p = (uint32_t *)((uint8_t *)cx().pin + pin_rank);
 
   const bool trace = getenv("OBLAS_B200_TRACE") != nullptr;
   std::vector<cudaEvent_t> ev;
   cudaEvent_t ev_start = nullptr;
   if (trace) {
     cudaEventCreate(&ev_start);
-    cudaEventRecord(ev_start, g_lane[0].s);
+    cudaEventRecord(ev_start, cx().lane[0].s);
   }
   auto mark = [&](cudaStream_t st) {
     if (!trace) return;
@@ -681,12 +752,32 @@ int oblas_b200_solve_batch_host(int field, void *A_host, size_t a_row_stride, si
     cudaEventRecord(e, st);
     ev.push_back(e);
   };
-  cudaStream_t saved = g.stream;
+  cudaStream_t saved = cx().stream;
   int rc = 0;
   size_t c = 0;
+  // skip_ident: the copy-back of A waits until the chunk's ranks are on the host; it is issued when
+  // the lane is about to be reused (3 chunks later) or at the end, for the deficient systems only
+  struct Pending { size_t first = 0, cnt = 0; cudaEvent_t done = nullptr; } pend[kLanes];
+  auto flush_lane = [&](int li) -> int {
+    Pending &pd = pend[li];
+    if (!pd.cnt) return 0;
+    HostLane &L = cx().lane[li];
+    CK(cudaEventSynchronize(pd.done));
+    for (size_t k = 0; k < pd.cnt;) {
+      if ((uint32_t)pin_r[pd.first + k] == rows) { k++; continue; }
+      size_t k1 = k + 1;
+      while (k1 < pd.cnt && (uint32_t)pin_r[pd.first + k1] != rows) k1++;
+      CK(cudaMemcpyAsync((uint8_t *)A_host + (pd.first + k) * a_sys_stride, L.A + k * a_sys_stride,
+                         (k1 - k) * a_sys_stride, cudaMemcpyDeviceToHost, L.s));
+      k = k1;
+    }
+    pd.cnt = 0;
+    return 0;
+  };
   for (size_t first = 0; first < nsys && rc == 0; first += chunk_systems, c++) {
-    HostLane &L = g_lane[c % kLanes];
+    HostLane &L = cx().lane[c % kLanes];
     size_t cnt = nsys - first < chunk_systems ? nsys - first : chunk_systems;
+    if (skip_ident && flush_lane((int)(c % kLanes))) { rc = -1; break; }
     cudaError_t e = cudaMemcpyAsync(L.A, (uint8_t *)A_host + first * a_sys_stride, cnt * a_sys_stride,
                                     cudaMemcpyHostToDevice, L.s);
     if (e == cudaSuccess && B_host)
@@ -702,13 +793,15 @@ int oblas_b200_solve_batch_host(int field, void *A_host, size_t a_row_stride, si
     p.B = B_host ? L.B : nullptr; p.b_rs = b_row_stride; p.b_ss = b_sys_stride;
     p.b_bytes = B_host ? (uint32_t)b_row_bytes : 0;
     p.rank = L.rank; p.pivcols = pivcols_out ? L.piv : nullptr;
-    g.stream = L.s;
+    cx().stream = L.s;
     rc = solve_common(field, p, cnt);
-    g.stream = saved;
+    cx().stream = saved;
     if (rc) break;
     mark(L.s);
-    e = cudaMemcpyAsync((uint8_t *)A_host + first * a_sys_stride, L.A, cnt * a_sys_stride,
-                        cudaMemcpyDeviceToHost, L.s);
+    e = cudaSuccess;
+    if (!skip_ident)
+      e = cudaMemcpyAsync((uint8_t *)A_host + first * a_sys_stride, L.A, cnt * a_sys_stride,
+                          cudaMemcpyDeviceToHost, L.s);
     if (e == cudaSuccess && B_host)
       e = cudaMemcpyAsync((uint8_t *)B_host + first * b_sys_stride, L.B, cnt * b_sys_stride,
                           cudaMemcpyDeviceToHost, L.s);
@@ -716,12 +809,25 @@ int oblas_b200_solve_batch_host(int field, void *A_host, size_t a_row_stride, si
     if (e == cudaSuccess && pivcols_out)
       e = cudaMemcpyAsync(pin_p + first * rows, L.piv, cnt * (size_t)rows * 4, cudaMemcpyDeviceToHost, L.s);
     if (e != cudaSuccess) { rc = fail("solve_host: copy to host failed: %s", cudaGetErrorString(e)); break; }
+    if (skip_ident) {
+      Pending &pd = pend[c % kLanes];
+      if (!pd.done && cudaEventCreateWithFlags(&pd.done, cudaEventDisableTiming) != cudaSuccess) { rc = fail("solve_host: event"); break; }
+      cudaEventRecord(pd.done, L.s);
+      pd.first = first;
+      pd.cnt = cnt;
+    }
     mark(L.s);
   }
-  for (auto &L : g_lane) {
+  for (int li = 0; li < kLanes && skip_ident; li++) {
+    if (rc == 0 && flush_lane(li)) rc = -1;
+    if (pend[li].done) cudaEventDestroy(pend[li].done);
+  }
+  for (auto &L : cx().lane) {
     cudaError_t e = cudaStreamSynchronize(L.s);
     if (e != cudaSuccess && rc == 0) rc = fail("solve_host: %s", cudaGetErrorString(e));
   }
+  // a tensor-core kernel of one of the lanes may have given up on a barrier wait: its chunk is invalid
+  if (rc == 0) rc = tc_check_status();
   if (rc == 0) {
     memcpy(rank_out, pin_r, nsys * 4);
     if (pivcols_out) memcpy(pivcols_out, pin_p, nsys * (size_t)rows * 4);
@@ -740,51 +846,89 @@ int oblas_b200_solve_batch_host(int field, void *A_host, size_t a_row_stride, si
   return rc;
 }
 
+int oblas_b200_solve_batch_host(int field, void *A_host, size_t a_row_stride, size_t a_sys_stride,
+                                uint32_t rows, uint32_t cols, size_t a_row_bytes, void *B_host,
+                                size_t b_row_stride, size_t b_sys_stride, size_t b_row_bytes,
+                                int32_t *rank_out, uint32_t *pivcols_out, size_t nsys,
+                                size_t chunk_systems) {
+  return oblas_b200_solve_batch_host_ex(field, A_host, a_row_stride, a_sys_stride, rows, cols, a_row_bytes, B_host,
+                                        b_row_stride, b_sys_stride, b_row_bytes, rank_out, pivcols_out, nsys,
+                                        chunk_systems, 0);
+}
+
 // ---- tensor-core apply: host side ---------------------------------------------------
 // Column window by column window: expand D into the fp4 operand blocks (workspace), then the
 // persistent tcgen05 kernel.  The workspace is bounded (tc_ws_budget) and cached.
-static size_t tc_ws_budget = (size_t)3 << 30;
+// Status words of the tensor-core kernels: one per workspace slot (= per stream).  A kernel whose
+// barrier wait exceeded the time limit sets its slot's word; the result of that launch is invalid.
+// Collected by oblas_b200_sync, by the host-streaming solve before it returns, and by tc_prepare
+// (an uncollected failure of an earlier asynchronous call on the same stream fails the next call
+// once instead of being lost).
 int tc_check_status() {
-  if (g.tc_status && *reinterpret_cast<volatile int *>(g.tc_status) != 0) {
-    *g.tc_status = 0;
-    return fail("apply (tensor-core path): a pipeline barrier wait hit its spin limit; result invalid");
-  }
+  Ctx &c = cx();
+  if (!c.tc_status) return 0;
+  int bad = -1;
+  for (int k = 0; k < 8; k++)
+    if (reinterpret_cast<volatile int *>(c.tc_status)[2 * k] != 0) {
+      c.tc_status[2 * k] = 0;
+      bad = k;
+    }
+  if (bad >= 0)
+    return fail("tensor-core path: a pipeline barrier wait exceeded its time limit (workspace slot %d); result invalid", bad);
   return 0;
+}
+int tc_ws_slot() {   // slot of the current stream (claims a free one)
+  Ctx &c = cx();
+  for (int k = 0; k < 8; k++)
+    if (c.tc_slots[k].used && c.tc_slots[k].stream == c.stream) return k;
+  for (int k = 0; k < 8; k++)
+    if (!c.tc_slots[k].used) {
+      c.tc_slots[k].used = true;
+      c.tc_slots[k].stream = c.stream;
+      return k;
+    }
+  return -1;
 }
 int tc_prepare(int **dstatus) {
   using namespace ob2::tc;
-  if (!g.tc_status) {
-    CK(cudaHostAlloc((void **)&g.tc_status, sizeof(int), cudaHostAllocMapped));
-    *g.tc_status = 0;
+  Ctx &c = cx();
+  if (!c.tc_status) {
+    CK(cudaHostAlloc((void **)&c.tc_status, 16 * sizeof(int), cudaHostAllocMapped));
+    memset(c.tc_status, 0, 16 * sizeof(int));
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  for (int k = 0; k < 8; k++) c.tc_status[2 * k + 1] = c.tc_wait_limit_ms;
+  if (!c.tc_attr_set) {
     CK(cudaFuncSetAttribute(apply_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<1>::kSmemBytes));
     CK(cudaFuncSetAttribute(apply_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<2>::kSmemBytes));
     CK(cudaFuncSetAttribute(update_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
     CK(cudaFuncSetAttribute(update_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
     CK(cudaFuncSetAttribute(update_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kU2SmemBytes));
-    attr_set = true;
+    c.tc_attr_set = true;
   }
-  CK(cudaHostGetDevicePointer((void **)dstatus, g.tc_status, 0));
+  const int slot = tc_ws_slot();
+  if (slot < 0) return fail("tensor-core workspace: more than 8 streams in use");
+  c.tc_cur_slot = slot;
+  if (reinterpret_cast<volatile int *>(c.tc_status)[2 * slot] != 0) {
+    // a kernel of an earlier call on this stream gave up and nobody collected it: the kernels of this
+    // call would bail out of their waits at once -- report it now, with a clean slate afterwards
+    CK(cudaStreamSynchronize(c.stream));
+    c.tc_status[2 * slot] = 0;
+    return fail("tensor-core path: an earlier launch on this stream exceeded its barrier time limit and was never "
+                "collected with oblas_b200_sync; its result was invalid (status cleared, call again)");
+  }
+  int *d = nullptr;
+  CK(cudaHostGetDevicePointer((void **)&d, c.tc_status, 0));
+  *dstatus = d + 2 * slot;
   return 0;
 }
 int tc_ws_reserve(size_t need) {
-  Ctx::TcWs *slot = nullptr;
-  for (auto &w : g.tc_slots)
-    if (w.used && w.stream == g.stream) slot = &w;
-  if (!slot)
-    for (auto &w : g.tc_slots)
-      if (!w.used) {
-        slot = &w;
-        w.used = true;
-        w.stream = g.stream;
-        break;
-      }
-  if (!slot) return fail("tensor-core workspace: more than 8 streams in use");
+  Ctx &c = cx();
+  const int k = tc_ws_slot();
+  if (k < 0) return fail("tensor-core workspace: more than 8 streams in use");
+  Ctx::TcWs *slot = &c.tc_slots[k];
   if (need > slot->bytes) {
     if (slot->p) {
-      CK(cudaStreamSynchronize(g.stream));
+      CK(cudaStreamSynchronize(c.stream));
       CK(cudaFree(slot->p));
       slot->p = nullptr;
       slot->bytes = 0;
@@ -792,14 +936,14 @@ int tc_ws_reserve(size_t need) {
     if (cudaMalloc(&slot->p, need) != cudaSuccess) {
       cudaGetLastError();
       slot->p = nullptr;
-      g.tc_ws = nullptr;
-      g.tc_ws_bytes = 0;
+      c.tc_ws = nullptr;
+      c.tc_ws_bytes = 0;
       return 1;   // caller shrinks its request
     }
     slot->bytes = need;
   }
-  g.tc_ws = slot->p;
-  g.tc_ws_bytes = slot->bytes;
+  c.tc_ws = slot->p;
+  c.tc_ws_bytes = slot->bytes;
   return 0;
 }
 // OBLAS_B200_TC_DEBUG switches parts of the tensor-core kernels off (timing experiments: results are
@@ -807,9 +951,9 @@ int tc_ws_reserve(size_t need) {
 static int tc_debug_switches() {
 #ifdef OB2_TC_TIMING_EXPERIMENTS
   static const int v = getenv("OBLAS_B200_TC_DEBUG") ? atoi(getenv("OBLAS_B200_TC_DEBUG")) : 0;
-  return v;
+  return v | cx().tc_inject;
 #else
-  return 0;
+  return cx().tc_inject;
 #endif
 }
 // persistent launch of the tcgen05 GEMM kernel: one CTA per SM.  nh = half tiles (240 byte
@@ -818,16 +962,16 @@ int tc_launch(const ob2::tc::ApplyTcArgs &a, int nh) {
   using namespace ob2::tc;
   const uint64_t units64 = (uint64_t)a.nsys * a.ntiles * a.itiles;
   if (units64 >= (1ull << 32)) return fail("apply (tcgen05): too many tiles in one launch");
-  uint32_t grid = (uint32_t)g.sm_count;
+  uint32_t grid = (uint32_t)cx().sm_count;
   if (units64 < grid) grid = (uint32_t)units64;
   if (grid == 0) return 0;
   if (nh == 2) {
-    apply_tc_kernel<2><<<grid, kThreads, Cfg<2>::kSmemBytes, g.stream>>>(a);
+    apply_tc_kernel<2><<<grid, kThreads, Cfg<2>::kSmemBytes, cx().stream>>>(a);
   } else if (nh == 1) {
-    apply_tc_kernel<1><<<grid, kThreads, Cfg<1>::kSmemBytes, g.stream>>>(a);
+    apply_tc_kernel<1><<<grid, kThreads, Cfg<1>::kSmemBytes, cx().stream>>>(a);
   } else {   // rank-128 update with the A operand resident per (system, row tile)
     const uint64_t nunits = (uint64_t)a.nsys * a.itiles;
-    grid = (uint32_t)g.sm_count;
+    grid = (uint32_t)cx().sm_count;
     if (nunits < grid) grid = (uint32_t)nunits;
     // OBLAS_B200_TC_PAIR=1: the CTA-pair variant (tcgen05 cta_group::2).  Bit-exact (the whole GPU suite
     // passes on it) but as built 1.75x slower than the single-CTA kernel -- see DESIGN.md 4.5 -- so off by default.
@@ -835,9 +979,9 @@ int tc_launch(const ob2::tc::ApplyTcArgs &a, int nh) {
     if (pair && !a.prof) {
       // CTA pairs (cta_group::2): a cluster of 2 per pair of row tiles
       const uint64_t npairs = (uint64_t)a.nsys * ((a.itiles + 1) / 2);
-      grid = (uint32_t)g.sm_count & ~1u;
+      grid = (uint32_t)cx().sm_count & ~1u;
       // a persistent kernel must not launch more clusters than can be resident at once
-      static int max_clusters = -1;
+      int &max_clusters = cx().max_clusters;
       if (max_clusters < 0) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kU2SmemBytes;
@@ -853,9 +997,9 @@ int tc_launch(const ob2::tc::ApplyTcArgs &a, int nh) {
       }
       if (max_clusters > 0 && (uint32_t)(2 * max_clusters) < grid) grid = (uint32_t)(2 * max_clusters);
       if (2 * npairs < grid) grid = (uint32_t)(2 * npairs);
-      update_tc2_kernel<<<grid, kThreads, kU2SmemBytes, g.stream>>>(a);
-    } else if (a.prof) update_tc_kernel<true><<<grid, kThreads, kUSmemBytes, g.stream>>>(a);
-    else update_tc_kernel<false><<<grid, kThreads, kUSmemBytes, g.stream>>>(a);
+      update_tc2_kernel<<<grid, kThreads, kU2SmemBytes, cx().stream>>>(a);
+    } else if (a.prof) update_tc_kernel<true><<<grid, kThreads, kUSmemBytes, cx().stream>>>(a);
+    else update_tc_kernel<false><<<grid, kThreads, kUSmemBytes, cx().stream>>>(a);
   }
   return after_launch("apply (tcgen05)");
 }
@@ -868,7 +1012,7 @@ int apply_tc_run(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, con
   constexpr int kTileN = Cfg<2>::kTileN;
   const size_t tile_bytes = (size_t)ksteps * 2 * kHBlock;
   const uint32_t ntiles_all = (uint32_t)((nbytes + kTileN - 1) / kTileN);
-  uint32_t tiles_per_pass = (uint32_t)(tc_ws_budget / tile_bytes);
+  uint32_t tiles_per_pass = (uint32_t)(cx().tc_ws_budget / tile_bytes);
   if (tiles_per_pass == 0) tiles_per_pass = 1;
   if (tiles_per_pass > ntiles_all) tiles_per_pass = ntiles_all;
   for (;;) {   // shrink the column window until the workspace fits
@@ -888,15 +1032,15 @@ int apply_tc_run(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, con
     e.reg[0].base = const_cast<uint8_t *>(D); e.reg[0].rs = d_stride; e.reg[0].ss = 0;
     e.reg[0].col0 = n0; e.reg[0].ncols = ncols; e.reg[0].v0 = 0;
     e.nreg = 1; e.Kc = Kc; e.rowmap = nullptr; e.rowmap_stride = 0; e.nrows = nullptr;
-    e.Dx = (uint8_t *)g.tc_ws; e.ksteps = ksteps; e.nhalf = 2 * nt; e.nsys = 1;
+    e.Dx = (uint8_t *)cx().tc_ws; e.ksteps = ksteps; e.nhalf = 2 * nt; e.nsys = 1;
     const size_t work = (size_t)nt * ksteps * (kTileN / 4);
     uint32_t eg = (uint32_t)((work + 255) / 256);
-    if (eg > (uint32_t)g.sm_count * 16) eg = (uint32_t)g.sm_count * 16;
-    expand_d_kernel<<<eg, 256, 0, g.stream>>>(e);
+    if (eg > (uint32_t)cx().sm_count * 16) eg = (uint32_t)cx().sm_count * 16;
+    expand_d_kernel<<<eg, 256, 0, cx().stream>>>(e);
     if (after_launch("apply (operand expansion)")) return -1;
     ApplyTcArgs a;
     memset(&a, 0, sizeof a);
-    a.C = C; a.c_stride = c_stride; a.c_ss = 0; a.M = M; a.Kc = Kc; a.Dx = (const uint8_t *)g.tc_ws;
+    a.C = C; a.c_stride = c_stride; a.c_ss = 0; a.M = M; a.Kc = Kc; a.Dx = (const uint8_t *)cx().tc_ws;
     a.ksteps = ksteps; a.ntiles = nt; a.itiles = itiles; a.nsys = 1;
     a.reg[0].base = Y; a.reg[0].rs = y_stride; a.reg[0].ss = 0; a.reg[0].col0 = n0; a.reg[0].ncols = ncols;
     a.reg[0].v0 = 0; a.nreg = 1;
@@ -911,17 +1055,17 @@ int apply_tc_run(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, con
 // ---- diagnostics: where the roles of update_tc_kernel spend their cycles ------------------
 extern "C" int oblas_b200_update_phases(int enable, uint64_t *out) {
   if (ensure_init()) return -1;
-  std::lock_guard<std::mutex> lk(g.mu);
-  if (out && g.d_uprof) {
-    CK(cudaStreamSynchronize(g.stream));
-    CK(cudaMemcpy(out, g.d_uprof, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  std::lock_guard<std::mutex> lk(cx().mu);
+  if (out && cx().d_uprof) {
+    CK(cudaStreamSynchronize(cx().stream));
+    CK(cudaMemcpy(out, cx().d_uprof, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   }
   if (enable) {
-    if (!g.d_uprof) CK(cudaMalloc(&g.d_uprof, 16 * sizeof(uint64_t)));
-    CK(cudaMemset(g.d_uprof, 0, 16 * sizeof(uint64_t)));
-  } else if (g.d_uprof) {
-    CK(cudaFree(g.d_uprof));
-    g.d_uprof = nullptr;
+    if (!cx().d_uprof) CK(cudaMalloc(&cx().d_uprof, 16 * sizeof(uint64_t)));
+    CK(cudaMemset(cx().d_uprof, 0, 16 * sizeof(uint64_t)));
+  } else if (cx().d_uprof) {
+    CK(cudaFree(cx().d_uprof));
+    cx().d_uprof = nullptr;
   }
   return 0;
 }
@@ -932,23 +1076,23 @@ struct TcTimer {
   int cls;
   cudaEvent_t a = nullptr, b = nullptr;
   explicit TcTimer(int c) : cls(c) {
-    if (!g.tc_timing) return;
+    if (!cx().tc_timing) return;
     if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { a = b = nullptr; return; }
-    cudaEventRecord(a, g.stream);
+    cudaEventRecord(a, cx().stream);
   }
   ~TcTimer() {
     if (!a) return;
-    cudaEventRecord(b, g.stream);
-    g.tc_events.push_back({cls, {a, b}});
+    cudaEventRecord(b, cx().stream);
+    cx().tc_events.push_back({cls, {a, b}});
   }
 };
 extern "C" int oblas_b200_solve_tc_times(int enable, double *ms_out, uint64_t *launches_out) {
   if (ensure_init()) return -1;
-  std::lock_guard<std::mutex> lk(g.mu);
+  std::lock_guard<std::mutex> lk(cx().mu);
   double ms[4] = {0, 0, 0, 0};
   uint64_t n[4] = {0, 0, 0, 0};
-  if (!g.tc_events.empty()) CK(cudaDeviceSynchronize());
-  for (auto &e : g.tc_events) {
+  if (!cx().tc_events.empty()) CK(cudaDeviceSynchronize());
+  for (auto &e : cx().tc_events) {
     float t = 0;
     if (cudaEventElapsedTime(&t, e.second.first, e.second.second) == cudaSuccess) {
       ms[e.first] += t;
@@ -957,12 +1101,12 @@ extern "C" int oblas_b200_solve_tc_times(int enable, double *ms_out, uint64_t *l
     cudaEventDestroy(e.second.first);
     cudaEventDestroy(e.second.second);
   }
-  g.tc_events.clear();
+  cx().tc_events.clear();
   for (int k = 0; k < 4; k++) {
     if (ms_out) ms_out[k] = ms[k];
     if (launches_out) launches_out[k] = n[k];
   }
-  g.tc_timing = enable != 0;
+  cx().tc_timing = enable != 0;
   return 0;
 }
 
@@ -974,6 +1118,43 @@ extern "C" int oblas_b200_solve_tc_times(int enable, double *ms_out, uint64_t *l
 //                                  -> fp4 operand blocks
 //   apply_tc_kernel                [A_rest | B] ^= E * P_old  on tcgen05
 // then permute_kernel puts the rows into position order and writes the ranks.
+// workspace bytes of one system on the tensor-core elimination path
+static size_t solve_tc_ws_per_system(uint32_t rows, uint32_t a_bytes, uint32_t b_bytes) {
+  using namespace ob2::tc;
+  const uint32_t a_rest0 = a_bytes > (uint32_t)kOuterBytes ? a_bytes - kOuterBytes : 0;
+  const uint32_t ntiles_max = (a_rest0 + b_bytes + kHalfN - 1) / kHalfN;
+  return (size_t)ntiles_max * kUSteps * kHBlock + (size_t)rows * kOuterBytes + ((size_t)rows * 2 + 15) / 16 * 16 +
+         2 * kOuterBytes + 16;
+}
+// How a batch would run: *path = 1 tensor-core elimination (outer panels + tcgen05 updates), 0 = shared-memory
+// table kernel; *chunk_systems = systems per chunk of the tensor-core path (the whole batch on the table kernel).
+extern "C" int oblas_b200_solve_plan(int field, uint32_t rows, uint32_t cols, size_t a_row_bytes, size_t b_row_bytes,
+                                     size_t nsys, int *path, size_t *chunk_systems, int *geometry) {
+  if (ensure_init()) return -1;
+  if (field < OB2_GF2 || field > OB2_GF256) return fail("solve_plan: bad field %d", field);
+  SolveArgs p;
+  memset(&p, 0, sizeof p);
+  p.rows = rows; p.cols = cols; p.a_bytes = (uint32_t)a_row_bytes; p.b_bytes = (uint32_t)b_row_bytes;
+  std::lock_guard<std::mutex> lk(cx().mu);
+  const bool tc = solve_tc_eligible(field, p, nsys);
+  if (path) *path = tc ? 1 : 0;
+  size_t chunk = nsys;
+  if (tc) {
+    chunk = cx().tc_ws_budget / solve_tc_ws_per_system(rows, p.a_bytes, p.b_bytes);
+    if (chunk < 1) chunk = 1;
+    if (chunk > nsys) chunk = nsys;
+  }
+  if (chunk_systems) *chunk_systems = chunk;
+  if (geometry) {
+    geometry[0] = geometry[1] = geometry[2] = 0;
+    if (tc) {   // the outer-panel kernel: 128-bit inner panels, 6-bit groups, one 128-byte tile
+      geometry[0] = 4; geometry[1] = 6; geometry[2] = 128;
+    } else if (!plan_solve(field, cx().solve_geo == 3 ? -1 : cx().solve_geo, rows, cx().smem_optin, geometry)) {
+      return fail("solve_plan: %u rows do not fit the shared-memory panel (limit %zu bytes); no fallback", rows, cx().smem_optin);
+    }
+  }
+  return 0;
+}
 int solve_tc_run(SolveArgs &p, size_t nsys) {
   using namespace ob2::tc;
   int *dstatus = nullptr;
@@ -992,7 +1173,7 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
   const size_t map_per_sys = ((size_t)rows * 2 + 15) / 16 * 16;
   const size_t small_per_sys = 2 * kOuterBytes + 16;   // piv_all (u16 x 128) + tcount + npiv + pad
   const size_t per_sys = dx_per_sys + e_per_sys + map_per_sys + small_per_sys;
-  size_t chunk = tc_ws_budget / per_sys;
+  size_t chunk = cx().tc_ws_budget / per_sys;
   if (chunk < 1) chunk = 1;
   if (chunk > nsys) chunk = nsys;
   for (;;) {
@@ -1002,7 +1183,7 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
     if (chunk == 1) return fail("solve: cannot allocate %zu bytes of workspace", per_sys);
     chunk = (chunk + 1) / 2;
   }
-  uint8_t *ws = (uint8_t *)g.tc_ws;
+  uint8_t *ws = (uint8_t *)cx().tc_ws;
   uint8_t *Dx = ws;                                        ws += chunk * dx_per_sys;
   uint8_t *E = ws;                                         ws += chunk * e_per_sys;
   uint16_t *maps = (uint16_t *)ws;                         ws += chunk * map_per_sys;
@@ -1012,18 +1193,17 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
   // permutation kernel: row map + staging area in shared memory
   const size_t pmap = ((size_t)rows * 2 + 15) / 16 * 16;
   // stage = count + list of moved rows (u16 x rows) + at least 16 bytes per row
-  if (pmap + 64 + 16 + pmap + (size_t)rows * 16 > g.smem_optin) return fail("solve: %u rows do not fit the permutation stage", rows);
-  const uint32_t stage_bytes = (uint32_t)((g.smem_optin - pmap - 64) & ~(size_t)15);
-  static bool perm_attr = false;
-  if (!perm_attr) {
-    CK(cudaFuncSetAttribute(permute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_optin));
-    perm_attr = true;
+  if (pmap + 64 + 16 + pmap + (size_t)rows * 16 > cx().smem_optin) return fail("solve: %u rows do not fit the permutation stage", rows);
+  const uint32_t stage_bytes = (uint32_t)((cx().smem_optin - pmap - 64) & ~(size_t)15);
+  if (!cx().perm_attr_set) {
+    CK(cudaFuncSetAttribute(permute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cx().smem_optin));
+    cx().perm_attr_set = true;
   }
   for (size_t first = 0; first < nsys; first += chunk) {
     const uint32_t cnt = (uint32_t)((nsys - first < chunk) ? (nsys - first) : chunk);
     uint8_t *A = p.A + first * p.a_ss;
     uint8_t *B = p.B ? p.B + first * p.b_ss : nullptr;
-    const uint32_t grid = cnt < (uint32_t)g.sm_count ? cnt : (uint32_t)g.sm_count;
+    const uint32_t grid = cnt < (uint32_t)cx().sm_count ? cnt : (uint32_t)cx().sm_count;
     for (uint32_t outer = 0; outer < nouter; outer++) {
       PanelArgs pa;
       memset(&pa, 0, sizeof pa);
@@ -1032,11 +1212,11 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
       pa.pivcols = p.pivcols ? p.pivcols + first * rows : nullptr;
       pa.nsys = cnt; pa.outer = outer; pa.inv = p.inv; pa.no_fast_panel = p.no_fast_panel;
       pa.no_look_ahead = p.no_look_ahead;
-      pa.phase = g.d_phase;
+      pa.phase = cx().d_phase;
       // the row map lives in global memory as [sys][rows] u16 with a 16-byte aligned pitch
       {
         TcTimer tt(0);
-        int rc = launch_panel_t<6, 128>(pa, grid, g.smem_optin, g.stream);
+        int rc = launch_panel_t<6, 128>(pa, grid, cx().smem_optin, cx().stream);
         if (rc) return fail("solve (tensor-core path): panel kernel launch configuration failed (%d)", rc);
       }
       if (after_launch("solve (outer panel)")) return -1;
@@ -1068,10 +1248,10 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
       e.Dx = Dx; e.ksteps = ksteps; e.nhalf = ntiles; e.nsys = cnt;
       const size_t work = (size_t)cnt * ntiles * ksteps * (kTileN / 4);
       uint32_t eg = (uint32_t)((work + 255) / 256);
-      if (eg > (uint32_t)g.sm_count * 16) eg = (uint32_t)g.sm_count * 16;
+      if (eg > (uint32_t)cx().sm_count * 16) eg = (uint32_t)cx().sm_count * 16;
       {
         TcTimer tt(1);
-        expand_d_kernel<<<eg, 256, 0, g.stream>>>(e);
+        expand_d_kernel<<<eg, 256, 0, cx().stream>>>(e);
       }
       if (after_launch("solve (pivot-row expansion)")) return -1;
       ApplyTcArgs a;
@@ -1079,7 +1259,7 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
       a.C = E; a.c_stride = kOuterBytes; a.c_ss = e_per_sys; a.M = rows; a.Kc = kOuterBytes; a.Dx = Dx;
       a.ksteps = ksteps; a.ntiles = ntiles; a.itiles = itiles; a.nsys = cnt;
       a.reg[0] = reg[0]; a.reg[1] = reg[1]; a.nreg = nreg;
-      a.accumulate = 1; a.status = dstatus; a.prof = g.d_uprof;
+      a.accumulate = 1; a.status = dstatus; a.prof = cx().d_uprof;
       a.dbg = tc_debug_switches();
       {
         TcTimer tt(2);
@@ -1094,7 +1274,7 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
     pm.stage_bytes = stage_bytes;
     {
       TcTimer tt(3);
-      permute_kernel<<<grid, 512, pmap + stage_bytes + 16, g.stream>>>(pm);
+      permute_kernel<<<grid, 512, pmap + stage_bytes + 16, cx().stream>>>(pm);
     }
     if (after_launch("solve (row permutation)")) return -1;
   }
@@ -1112,13 +1292,13 @@ int oblas_b200_gf256_apply(const void *C, size_t c_stride, uint32_t M, uint32_t 
     return fail("apply: D, Y, their strides and nbytes must be multiples of 16");
   if (classify(C) != PK_DEVVIS || classify(D) != PK_DEVVIS || classify(Y) != PK_DEVVIS)
     return fail("apply: pointers must be device-visible");
-  std::lock_guard<std::mutex> lk(g.mu);
+  std::lock_guard<std::mutex> lk(cx().mu);
   // path: apply_geo 0..2 force the shared-memory Four-Russians kernel with that geometry, 3 forces
   // the tensor-core kernel, -1 picks by size (the fp4 expansion of D is amortised over M/16 row tiles)
   const bool tc_ok = Kc > 0 && Kc < (1u << 20);
-  bool use_tc = g.apply_geo == 3 || (g.apply_geo < 0 && M >= 256 && Kc >= 64 && nbytes >= 480);
+  bool use_tc = cx().apply_geo == 3 || (cx().apply_geo < 0 && M >= 256 && Kc >= 64 && nbytes >= 480);
   if (use_tc && !tc_ok) {
-    if (g.apply_geo == 3) return fail("apply: tensor-core path needs 0 < Kc < 2^20");
+    if (cx().apply_geo == 3) return fail("apply: tensor-core path needs 0 < Kc < 2^20");
     use_tc = false;
   }
   if (use_tc)
@@ -1129,7 +1309,7 @@ int oblas_b200_gf256_apply(const void *C, size_t c_stride, uint32_t M, uint32_t 
   p.C = (const uint8_t *)C; p.c_stride = c_stride; p.M = M; p.Kc = Kc;
   p.D = (const uint8_t *)D; p.d_stride = d_stride;
   p.Y = (uint8_t *)Y; p.y_stride = y_stride; p.nbytes = (uint32_t)nbytes; p.accumulate = accumulate;
-  int rc = launch_apply(p, g.apply_geo == 3 ? -1 : g.apply_geo, 512, g.stream);
+  int rc = launch_apply(p, cx().apply_geo == 3 ? -1 : cx().apply_geo, 512, cx().stream);
   if (rc) return fail("apply: launch configuration failed (%d)", rc);
   return after_launch("apply");
 }
@@ -1143,14 +1323,14 @@ int oblas_b200_nnz_batch(int field, const void *bits, size_t row_stride, uint32_
   if (s > e) s = e;
   if (classify(bits) != PK_DEVVIS || classify(rows_idx) != PK_DEVVIS || classify(out) != PK_DEVVIS)
     return fail("nnz_batch: pointers must be device-visible");
-  std::lock_guard<std::mutex> lk(g.mu);
+  std::lock_guard<std::mutex> lk(cx().mu);
   unsigned blocks = (unsigned)((nrows * 32 + 255) / 256);
   const uint8_t *p = (const uint8_t *)bits;
   switch (field) {
-  case OB2_GF2: nnz_kernel<1><<<blocks, 256, 0, g.stream>>>(p, row_stride, rows_idx, (uint32_t)nrows, s, e, out); break;
-  case OB2_GF4: nnz_kernel<2><<<blocks, 256, 0, g.stream>>>(p, row_stride, rows_idx, (uint32_t)nrows, s, e, out); break;
-  case OB2_GF16: nnz_kernel<4><<<blocks, 256, 0, g.stream>>>(p, row_stride, rows_idx, (uint32_t)nrows, s, e, out); break;
-  case OB2_GF256: nnz_kernel<8><<<blocks, 256, 0, g.stream>>>(p, row_stride, rows_idx, (uint32_t)nrows, s, e, out); break;
+  case OB2_GF2: nnz_kernel<1><<<blocks, 256, 0, cx().stream>>>(p, row_stride, rows_idx, (uint32_t)nrows, s, e, out); break;
+  case OB2_GF4: nnz_kernel<2><<<blocks, 256, 0, cx().stream>>>(p, row_stride, rows_idx, (uint32_t)nrows, s, e, out); break;
+  case OB2_GF16: nnz_kernel<4><<<blocks, 256, 0, cx().stream>>>(p, row_stride, rows_idx, (uint32_t)nrows, s, e, out); break;
+  case OB2_GF256: nnz_kernel<8><<<blocks, 256, 0, cx().stream>>>(p, row_stride, rows_idx, (uint32_t)nrows, s, e, out); break;
   default: return fail("nnz_batch: bad field %d", field);
   }
   return after_launch("nnz");
@@ -1196,25 +1376,25 @@ int oblas_b200_register_tables(unsigned exp_bits, const uint8_t *lo, const uint8
   if (ensure_init()) return -1;
   if (exp_bits != 2 && exp_bits != 4 && exp_bits != 8) return fail("register_tables: element width must be 2, 4 or 8 bits");
   if (!lo || !hi || !inv) return fail("register_tables: null pointer");
-  std::lock_guard<std::mutex> lk(g.mu);
+  std::lock_guard<std::mutex> lk(cx().mu);
   DevTableSet h;
   fill_table_set(h, lo, hi, inv, 1u << exp_bits);
   DevTableSet *d = nullptr;
   CK(cudaMalloc(&d, sizeof(DevTableSet)));
   CK(cudaMemcpy(d, &h, sizeof h, cudaMemcpyHostToDevice));
-  g.d_custom.push_back(d);
-  g.custom_linear.push_back(h.linear);
-  g.custom_bits.push_back((int)exp_bits);
-  return 16 + (int)g.d_custom.size() - 1;
+  cx().d_custom.push_back(d);
+  cx().custom_linear.push_back(h.linear);
+  cx().custom_bits.push_back((int)exp_bits);
+  return 16 + (int)cx().d_custom.size() - 1;
 }
 
 // ---- column operations / accessors on device-resident matrices (row f-3) --------------------
 #define OB2_FIELD_SWITCH(KERNEL, GRID, BLOCK, ...)                                              \
   switch (field) {                                                                             \
-  case OB2_GF2: KERNEL<1><<<GRID, BLOCK, 0, g.stream>>>(__VA_ARGS__); break;                    \
-  case OB2_GF4: KERNEL<2><<<GRID, BLOCK, 0, g.stream>>>(__VA_ARGS__); break;                    \
-  case OB2_GF16: KERNEL<4><<<GRID, BLOCK, 0, g.stream>>>(__VA_ARGS__); break;                   \
-  case OB2_GF256: KERNEL<8><<<GRID, BLOCK, 0, g.stream>>>(__VA_ARGS__); break;                  \
+  case OB2_GF2: KERNEL<1><<<GRID, BLOCK, 0, cx().stream>>>(__VA_ARGS__); break;                    \
+  case OB2_GF4: KERNEL<2><<<GRID, BLOCK, 0, cx().stream>>>(__VA_ARGS__); break;                    \
+  case OB2_GF16: KERNEL<4><<<GRID, BLOCK, 0, cx().stream>>>(__VA_ARGS__); break;                   \
+  case OB2_GF256: KERNEL<8><<<GRID, BLOCK, 0, cx().stream>>>(__VA_ARGS__); break;                  \
   default: return fail("bad field %d", field);                                                 \
   }
 int oblas_b200_swapcols_batch(int field, void *bits, size_t row_stride, size_t sys_stride, uint32_t rows,
@@ -1225,14 +1405,14 @@ int oblas_b200_swapcols_batch(int field, void *bits, size_t row_stride, size_t s
   if (classify(bits) != PK_DEVVIS) return fail("swapcols: matrix must be device-visible");
   if ((row_stride & 3) || (sys_stride & 3) || (reinterpret_cast<uintptr_t>(bits) & 3))
     return fail("swapcols: base / strides must be multiples of 4");
-  std::lock_guard<std::mutex> lk(g.mu);
+  std::lock_guard<std::mutex> lk(cx().mu);
   const size_t ib = nsys * sizeof(uint32_t), slot = (ib + 255) & ~(size_t)255;
   if (scratch_reserve(2 * slot + 256)) return -1;
   const void *di, *dj;
   if (stage_array(col_i, ib, 0, &di) || stage_array(col_j, ib, slot, &dj)) return -1;
   const size_t total = nsys * (size_t)rows;
   unsigned blocks = (unsigned)((total + 255) / 256);
-  if (blocks > (unsigned)g.sm_count * 32) blocks = (unsigned)g.sm_count * 32;
+  if (blocks > (unsigned)cx().sm_count * 32) blocks = (unsigned)cx().sm_count * 32;
   OB2_FIELD_SWITCH(swapcols_kernel, blocks, 256, (uint8_t *)bits, row_stride, sys_stride, rows,
                    (const uint32_t *)di, (const uint32_t *)dj, (uint32_t)nsys)
   return after_launch("swapcols");
@@ -1245,7 +1425,7 @@ int oblas_b200_get_elements(int field, const void *bits, size_t row_stride, cons
   if (classify(bits) != PK_DEVVIS || classify(out_dev) != PK_DEVVIS)
     return fail("get_elements: matrix and output must be device-visible");
   if (n > 0x7fffffffu) return fail("get_elements: too many elements");
-  std::lock_guard<std::mutex> lk(g.mu);
+  std::lock_guard<std::mutex> lk(cx().mu);
   const size_t ib = n * sizeof(uint32_t), slot = (ib + 255) & ~(size_t)255;
   if (scratch_reserve(2 * slot + 256)) return -1;
   const void *dr, *dc;
@@ -1262,7 +1442,7 @@ int oblas_b200_set_elements(int field, void *bits, size_t row_stride, const uint
   if (!bits || !rows_idx || !cols_idx || !vals) return fail("set_elements: null pointer");
   if (classify(bits) != PK_DEVVIS) return fail("set_elements: matrix must be device-visible");
   if (n > 0x7fffffffu) return fail("set_elements: too many elements");
-  std::lock_guard<std::mutex> lk(g.mu);
+  std::lock_guard<std::mutex> lk(cx().mu);
   const size_t ib = n * sizeof(uint32_t), slot = (ib + 255) & ~(size_t)255;
   if (scratch_reserve(2 * slot + n + 512)) return -1;
   const void *dr, *dc, *dv;
@@ -1290,7 +1470,7 @@ unsigned round_up_u(unsigned k, unsigned a) { return (k + a - 1) / a * a; }
 // are already device-visible and 16-byte friendly.
 int single_vec(int op, int mode, uint8_t *a, const uint8_t *b, size_t k, const uint8_t *lo,
                const uint8_t *hi, uint32_t u) {
-  static uint32_t *d_zero = nullptr;  // a device word holding row index 0
+  uint32_t *&d_zero = cx().d_zero;  // a device word holding row index 0
   if (!d_zero) {
     CK(cudaMalloc(&d_zero, 4));
     CK(cudaMemset(d_zero, 0, 4));
@@ -1307,12 +1487,13 @@ int single_vec(int op, int mode, uint8_t *a, const uint8_t *b, size_t k, const u
   p.dst_rows = d_zero;
   p.src_rows = d_zero;
   p.u0 = u;
+  p.u_max = 255u;
   if (lo) {
     p.use_explicit = 1;
     make_lut(p.lut, lo, hi);
     make_basis(p.basis, lo, hi);
   }
-  launch_rowops(op, mode, p, g.stream);
+  launch_rowops(op, mode, p, cx().stream);
   return after_launch("row op");
 }
 
@@ -1320,7 +1501,7 @@ int single_vec(int op, int mode, uint8_t *a, const uint8_t *b, size_t k, const u
 int l1_op(int op, uint8_t *a, const uint8_t *b, size_t k, const uint8_t *lo, const uint8_t *hi, uint32_t u) {
   if (ensure_init()) return -1;
   if (k == 0) return 0;
-  std::lock_guard<std::mutex> lk(g.mu);
+  std::lock_guard<std::mutex> lk(cx().mu);
   const bool has_b = (op == OP_AXPY || op == OP_ADD || op == OP_SWAP || op == OP_AXPY_B32);
   const size_t b_bytes = (op == OP_AXPY_B32) ? ((k + 31) / 32) * 4 : k;
   int mode = MUL_LUT;
@@ -1332,14 +1513,14 @@ int l1_op(int op, uint8_t *a, const uint8_t *b, size_t k, const uint8_t *lo, con
   if (!a_dev || !b_dev) {  // stage plain host operands through device scratch
     if (scratch_reserve(ka + kb + 64)) return -1;
     if (!a_dev) {
-      da = (uint8_t *)g.scratch;
-      CK(cudaMemsetAsync(da + (ka - 16), 0, 16, g.stream));
-      CK(cudaMemcpyAsync(da, a, k, cudaMemcpyHostToDevice, g.stream));
+      da = (uint8_t *)cx().scratch;
+      CK(cudaMemsetAsync(da + (ka - 16), 0, 16, cx().stream));
+      CK(cudaMemcpyAsync(da, a, k, cudaMemcpyHostToDevice, cx().stream));
     }
     if (has_b && !b_dev) {
-      uint8_t *t = (uint8_t *)g.scratch + ka;
-      CK(cudaMemsetAsync(t + (kb - 16), 0, 16, g.stream));
-      CK(cudaMemcpyAsync(t, b, b_bytes, cudaMemcpyHostToDevice, g.stream));
+      uint8_t *t = (uint8_t *)cx().scratch + ka;
+      CK(cudaMemsetAsync(t + (kb - 16), 0, 16, cx().stream));
+      CK(cudaMemcpyAsync(t, b, b_bytes, cudaMemcpyHostToDevice, cx().stream));
       db = t;
     }
   }
@@ -1354,7 +1535,7 @@ int l1_op(int op, uint8_t *a, const uint8_t *b, size_t k, const uint8_t *lo, con
       // mask words beyond ceil(k/32) must not be read: fall through to bytes
       Lut16x2 lt;
       memset(&lt, 0, sizeof lt);
-      launch_rowop_bytes(op, da, db, k, lt, u, g.stream);
+      launch_rowop_bytes(op, da, db, k, lt, u, cx().stream);
       if (after_launch("row op (bytes)")) return -1;
     } else if (single_vec(op, mode, da, db, kk, lo, hi, u)) {
       return -1;
@@ -1363,12 +1544,12 @@ int l1_op(int op, uint8_t *a, const uint8_t *b, size_t k, const uint8_t *lo, con
     Lut16x2 lt;
     memset(&lt, 0, sizeof lt);
     if (lo) make_lut(lt, lo, hi);
-    launch_rowop_bytes(op, da, db, k, lt, u, g.stream);
+    launch_rowop_bytes(op, da, db, k, lt, u, cx().stream);
     if (after_launch("row op (bytes)")) return -1;
   }
-  if (a_staged) CK(cudaMemcpyAsync(a, da, k, cudaMemcpyDeviceToHost, g.stream));
-  if (op == OP_SWAP && b_staged) CK(cudaMemcpyAsync(const_cast<uint8_t *>(b), db, k, cudaMemcpyDeviceToHost, g.stream));
-  if (a_staged || b_staged) CK(cudaStreamSynchronize(g.stream));
+  if (a_staged) CK(cudaMemcpyAsync(a, da, k, cudaMemcpyDeviceToHost, cx().stream));
+  if (op == OP_SWAP && b_staged) CK(cudaMemcpyAsync(const_cast<uint8_t *>(b), db, k, cudaMemcpyDeviceToHost, cx().stream));
+  if (a_staged || b_staged) CK(cudaStreamSynchronize(cx().stream));
   return 0;
 }
 
@@ -1394,18 +1575,18 @@ int solve_ptrs(int field, uint8_t **abits, uint8_t **bbits, size_t a_rs, unsigne
                size_t a_bytes, size_t b_rs, size_t b_bytes, unsigned *rank, unsigned *pivcols, size_t n) {
   if (ensure_init()) return -1;
   if (n == 0) return 0;
-  std::lock_guard<std::mutex> lk(g.mu);
+  std::lock_guard<std::mutex> lk(cx().mu);
   const size_t ptr_bytes = ((n * 8) + 255) & ~(size_t)255;
   const size_t rank_bytes = ((n * 4) + 255) & ~(size_t)255;
   const size_t piv_bytes = pivcols ? n * (size_t)rows * 4 : 0;
   if (scratch_reserve(2 * ptr_bytes + rank_bytes + piv_bytes + 256)) return -1;
-  uint8_t *s = (uint8_t *)g.scratch;
+  uint8_t *s = (uint8_t *)cx().scratch;
   unsigned long long *d_a = (unsigned long long *)s, *d_b = (unsigned long long *)(s + ptr_bytes);
   int32_t *d_rank = (int32_t *)(s + 2 * ptr_bytes);
   uint32_t *d_piv = pivcols ? (uint32_t *)(s + 2 * ptr_bytes + rank_bytes) : nullptr;
-  CK(cudaMemcpyAsync(d_a, abits, n * 8, cudaMemcpyHostToDevice, g.stream));
-  if (bbits) CK(cudaMemcpyAsync(d_b, bbits, n * 8, cudaMemcpyHostToDevice, g.stream));
-  if (d_piv) CK(cudaMemsetAsync(d_piv, 0xff, piv_bytes, g.stream));
+  CK(cudaMemcpyAsync(d_a, abits, n * 8, cudaMemcpyHostToDevice, cx().stream));
+  if (bbits) CK(cudaMemcpyAsync(d_b, bbits, n * 8, cudaMemcpyHostToDevice, cx().stream));
+  if (d_piv) CK(cudaMemsetAsync(d_piv, 0xff, piv_bytes, cx().stream));
   SolveArgs p;
   memset(&p, 0, sizeof p);
   p.A = abits[0]; p.a_rs = a_rs; p.rows = rows; p.cols = cols; p.a_bytes = (uint32_t)a_bytes;
@@ -1414,9 +1595,39 @@ int solve_ptrs(int field, uint8_t **abits, uint8_t **bbits, size_t a_rs, unsigne
   p.a_ptrs = d_a;
   p.b_ptrs = bbits ? d_b : nullptr;
   if (solve_common(field, p, n)) return -1;
-  CK(cudaMemcpyAsync(rank, d_rank, n * 4, cudaMemcpyDeviceToHost, g.stream));
-  if (pivcols) CK(cudaMemcpyAsync(pivcols, d_piv, piv_bytes, cudaMemcpyDeviceToHost, g.stream));
-  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaMemcpyAsync(rank, d_rank, n * 4, cudaMemcpyDeviceToHost, cx().stream));
+  CK(cudaStreamSynchronize(cx().stream));
+  if (tc_check_status()) return -1;
+  if (pivcols) {
+    // like the caller-side loop (oracle/ref_driver.c) only the first rank[k] entries of a system's
+    // pivcols are written: a caller may size the array by min(rows, cols)
+    for (size_t k = 0; k < n; k++)
+      if (rank[k]) CK(cudaMemcpyAsync(pivcols + k * rows, d_piv + k * rows, (size_t)rank[k] * 4, cudaMemcpyDeviceToHost, cx().stream));
+    CK(cudaStreamSynchronize(cx().stream));
+  }
+  return 0;
+}
+
+// the *_solve_batch wrappers take the geometry from system 0: every system must have the same
+template <typename M>
+int same_shape(M **A, M **B, size_t n, const char *what) {
+  for (size_t k = 0; k < n; k++) {
+    if (!A[k] || !A[k]->bits) return fail("%s: A[%zu] is null", what, k);
+    if (A[k]->rows != A[0]->rows || A[k]->cols != A[0]->cols || A[k]->stride != A[0]->stride)
+      return fail("%s: A[%zu] is %ux%u (stride %u), A[0] is %ux%u (stride %u): one batch = one shape", what, k,
+                  A[k]->rows, A[k]->cols, A[k]->stride, A[0]->rows, A[0]->cols, A[0]->stride);
+    if (!B) continue;
+    if (!B[k] || !B[k]->bits) return fail("%s: B[%zu] is null", what, k);
+    if (B[k]->stride != B[0]->stride || B[k]->rows < A[k]->rows)
+      return fail("%s: B[%zu] has %u rows, stride %u; needs >= %u rows and stride %u", what, k, B[k]->rows,
+                  B[k]->stride, A[k]->rows, B[0]->stride);
+  }
+  return 0;
+}
+int same_field(gfmat **A, gfmat **B, size_t n, const char *what) {
+  for (size_t k = 0; k < n; k++)
+    if (A[k]->field != A[0]->field || (B && B[k]->field != A[0]->field))
+      return fail("%s: system %zu is over another field than system 0", what, k);
   return 0;
 }
 
@@ -1738,6 +1949,7 @@ void binmat_swaprow_batch(binmat *m, const unsigned *i, const unsigned *j, size_
 // ---- caller-side loops as single calls ------------------------------------------------
 void octmat_solve_batch(octmat **A, octmat **B, unsigned *rank, size_t n) {
   if (n == 0) return;
+  MUST(same_shape(A, B, n, "octmat_solve_batch"), "octmat_solve_batch");
   std::vector<uint8_t *> ab(n), bb(n);
   for (size_t k = 0; k < n; k++) {
     ab[k] = A[k]->bits;
@@ -1755,6 +1967,8 @@ unsigned octmat_solve(octmat *A, octmat *B, unsigned *pivcols) {
 }
 void gfmat_solve_batch(gfmat **A, gfmat **B, unsigned *rank, size_t n) {
   if (n == 0) return;
+  MUST(same_shape(A, B, n, "gfmat_solve_batch"), "gfmat_solve_batch");
+  MUST(same_field(A, B, n, "gfmat_solve_batch"), "gfmat_solve_batch");
   std::vector<uint8_t *> ab(n), bb(n);
   for (size_t k = 0; k < n; k++) {
     ab[k] = (uint8_t *)A[k]->bits;
@@ -1772,6 +1986,7 @@ unsigned gfmat_solve(gfmat *A, gfmat *B, unsigned *pivcols) {
 }
 void binmat_rref_batch(binmat **A, binmat **B, unsigned *rank, size_t n) {
   if (n == 0) return;
+  MUST(same_shape(A, B, n, "binmat_rref_batch"), "binmat_rref_batch");
   std::vector<uint8_t *> ab(n), bb(n);
   for (size_t k = 0; k < n; k++) {
     ab[k] = (uint8_t *)A[k]->bits;

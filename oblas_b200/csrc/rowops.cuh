@@ -52,6 +52,8 @@ struct RowOpArgs {
   const uint8_t *u;                    // [nops] or null (then u0)
   const DevTableSet *ts;               // null when explicit tables are given
   uint32_t u0;
+  uint32_t u_max;                      // AXPY / SCAL with u > u_max are no-ops (GF(2): 1 -- the field has no
+                                       // other scalars, gfmat.c:14-19; else 255)
   int use_explicit;                    // tables below instead of ts (L1 entry points)
   Lut16x2 lut;
   Basis8 basis;
@@ -147,6 +149,7 @@ __global__ void __launch_bounds__(256) rowop_kernel(const RowOpArgs p) {
       else
         pb[k] = p.b + (size_t)j * p.b_stride + (size_t)c * 16;
       // the reference's short-circuits
+      if ((OP == OP_AXPY || OP == OP_SCAL) && u > p.u_max) live[k] = false;
       if (OP == OP_AXPY && u == 0) live[k] = false;          // octmat.c:36-37
       if (OP == OP_SCAL && u < 2) live[k] = false;           // octmat.c:57-58
       if (OP == OP_SWAP && pa[k] == pb[k]) live[k] = false;  // octmat.c:25-26 (same row of the same matrix)

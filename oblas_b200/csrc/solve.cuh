@@ -1494,6 +1494,41 @@ inline int launch_solve_geo(int geo, const SolveArgs &p, uint32_t grid, uint32_t
   }
 }
 
+// Which table-kernel variant launch_solve would pick (same order of attempts, nothing launched):
+// out = {NBW, KB, WT}; false if no variant fits.
+template <int EXP, int NBW, int KB, int WT>
+inline bool solve_fits_t(uint32_t rows, size_t smem_limit) {
+  using SM = SolveSmem<EXP, NBW, KB, WT>;
+  const size_t stage = SM::G::TAB_BYTES + (size_t)rows * NBW * 8;
+  return rows != 0 && rows <= 65535u && SM::bytes(rows) <= smem_limit && stage / rows >= 16;
+}
+template <int EXP, int NBW>
+inline bool solve_fits_geo(int geo, uint32_t rows, size_t smem_limit, int out[3]) {
+  bool ok;
+  int kb, wt;
+  switch (geo) {
+  case 1: ok = solve_fits_t<EXP, NBW, 6, 128>(rows, smem_limit); kb = 6; wt = 128; break;
+  case 2: ok = solve_fits_t<EXP, NBW, 7, 64>(rows, smem_limit); kb = 7; wt = 64; break;
+  default: ok = solve_fits_t<EXP, NBW, 4, 256>(rows, smem_limit); kb = 4; wt = 256; break;
+  }
+  if (ok) { out[0] = NBW; out[1] = kb; out[2] = wt; }
+  return ok;
+}
+inline bool plan_solve(int field, int geo, uint32_t rows, size_t smem_limit, int out[3]) {
+  if (geo < 0) geo = 1;
+#define OB2_PLAN(E)                                                                                  \
+  return solve_fits_geo<E, 4>(geo, rows, smem_limit, out) || solve_fits_geo<E, 2>(geo, rows, smem_limit, out) || \
+         (geo != 0 && (solve_fits_geo<E, 4>(0, rows, smem_limit, out) || solve_fits_geo<E, 2>(0, rows, smem_limit, out)));
+  switch (field) {
+  case OB2_GF256: OB2_PLAN(8)
+  case OB2_GF16: OB2_PLAN(4)
+  case OB2_GF4: OB2_PLAN(2)
+  case OB2_GF2: OB2_PLAN(1)
+  }
+#undef OB2_PLAN
+  return false;
+}
+
 // field = OB2_GF2 .. OB2_GF256.  geo < 0: default geometry for the field.  Picks the
 // widest panel that fits shared memory (128-bit panels, then 64-bit, then 4-bit groups).
 inline int launch_solve(int field, int geo, const SolveArgs &p, uint32_t grid, uint32_t threads,

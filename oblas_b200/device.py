@@ -24,6 +24,13 @@ def bind(device=None):
     capi.lib().oblas_b200_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream))
 
 
+def sync():
+    """Wait for the library's stream and collect the tensor-core kernels' status words (raises if a
+    launch since the last call gave up on a barrier wait -- its result would be invalid).  The checked
+    way to finish after solve_batch / apply, which only enqueue."""
+    capi.check(capi.lib().oblas_b200_sync(), "sync")
+
+
 def fill_random(t, seed, byte_offset=0):
     assert t.is_cuda and t.is_contiguous()
     capi.check(capi.lib().oblas_b200_fill_random(_p(t), t.numel() * t.element_size(), seed, byte_offset),

@@ -58,6 +58,7 @@ int emu_rowops(int op, int mode, int ts, uint8_t *a, size_t a_stride, const uint
   p.src_rows = src_rows;
   p.u = u;
   p.u0 = u0;
+  p.u_max = 255u;
   p.ts = ts >= 0 ? &g_sets[ts] : nullptr;
   launch_rowops(op, mode, p, nullptr);
   return 0;
@@ -78,6 +79,7 @@ int emu_rowop_explicit(int op, int mode, uint8_t *a, const uint8_t *b, uint32_t 
   p.dst_rows = &zero;
   p.src_rows = &zero;
   p.u0 = 2;
+  p.u_max = 255u;
   p.use_explicit = 1;
   make_lut(p.lut, lo16, hi16);
   make_basis(p.basis, lo16, hi16);

@@ -1,0 +1,330 @@
+"""GPU parity at BASELINE.json's OWN sizes for configs[2], [3] and [4], whole buffers against the
+unmodified reference (oracle/_ref: AVX-512 / AVX2 / scalar build + oracle/ref_driver.c, falling
+back to the C restatement), plus the paths only large problems reach:
+
+  * GF(2) K=8192 runs solve_kernel<1, NBW=2, 4, 256> (the 64-bit-panel variant picked when the
+    128-bit panel does not fit shared memory) -- binmat.c:26-33,44-57 semantics;
+  * GF(16)/GF(4) K=2048 -- gfmat.c:83-89,124-156 (GF(4): corrected table);
+  * apply with Kc=10000 coefficient columns (octmat.c:32-46, one oaxpy per coefficient);
+  * several chunks of systems in solve_tc_run and several column passes in apply_tc_run, forced
+    with oblas_b200_set_workspace_budget;
+  * the give-up path of the tensor-core kernels (bounded barrier waits) through fault injection.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from gpu_helpers import dev, gf256_vecmat, host
+from helpers import (GF2, GF4, GF16, GF256, FIELD_BITS, field_row_bytes, mat_view, oracle, oracle_solve, ptr,
+                     random_matrix, reference, splitmix_bytes, u32p)
+from oblas_b200 import capi, device
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _bind(cuda_lib):
+    device.bind(0)
+    cuda_lib.oblas_b200_set_tuning(-1, -1)
+    cuda_lib.oblas_b200_set_panel_path(0)
+    yield
+    cuda_lib.oblas_b200_set_workspace_budget(0)
+    cuda_lib.oblas_b200_set_fault_injection(0)
+    cuda_lib.oblas_b200_set_wait_limit_ms(0)
+
+
+def best_reference():
+    for v in ("avx512", "avx2", "ref"):
+        lib = reference(v)
+        if lib is not None:
+            return lib
+    return None
+
+
+def ref_solve(field, A, B, cols):
+    """rank, pivcols, A', B' of the caller-side loop run by the compiled reference (oracle port if absent)"""
+    lib = best_reference()
+    rows = A.shape[0]
+    pv = np.full(rows, 0xFFFFFFFF, dtype=np.uint32)
+    if lib is None or (field == GF256 and lib.refdrv_octmat_align() != 16 and (A.shape[1] % 64 or (B is not None and B.shape[1] % 64))):
+        a, b = A.copy(), (B.copy() if B is not None else None)
+        rk, pv = oracle_solve(field, a, b, cols)
+        return rk, pv, a, b
+    if field == GF2:
+        new, free = lib.binmat_new, lib.binmat_free
+        ma = new(rows, cols)
+        mb = new(rows, B.shape[1] * 8) if B is not None else None
+    elif field == GF256:
+        new, free = lib.octmat_new, lib.octmat_free
+        ma = new(rows, cols)
+        mb = new(rows, B.shape[1]) if B is not None else None
+    else:
+        free = lib.gfmat_free
+        ma = lib.gfmat_new(field, rows, cols)
+        mb = lib.gfmat_new(field, rows, B.shape[1] * 8 // FIELD_BITS[field]) if B is not None else None
+    assert mat_view(ma).shape == A.shape, (mat_view(ma).shape, A.shape)
+    mat_view(ma)[:] = A
+    if mb is not None:
+        assert mat_view(mb).shape == B.shape, (mat_view(mb).shape, B.shape)
+        mat_view(mb)[:] = B
+    if field == GF2:
+        rk = lib.refdrv_binmat_rref(ma, mb, ptr(pv, u32p))
+    elif field == GF256:
+        rk = lib.refdrv_octmat_solve(ma, mb, ptr(pv, u32p))
+    else:
+        rk = lib.refdrv_gfmat_solve(ma, mb, ptr(pv, u32p), 1)
+    a, b = mat_view(ma).copy(), (mat_view(mb).copy() if mb is not None else None)
+    free(ma)
+    if mb is not None:
+        free(mb)
+    return rk, pv, a, b
+
+
+def check_batch(field, A, B, cols):
+    dA, dB = dev(A), (dev(B) if B is not None else None)
+    rank, piv = device.solve_batch(field, dA, cols, dB, want_pivcols=True)
+    device.sync()
+    rank, piv, gA = host(rank), host(piv), host(dA)
+    gB = host(dB) if B is not None else None
+    ranks = []
+    for s in range(A.shape[0]):
+        rk, pv, wa, wb = ref_solve(field, A[s], B[s] if B is not None else None, cols)
+        assert rank[s] == rk, (s, rank[s], rk)
+        assert np.array_equal(piv[s][:rk].astype(np.uint32), pv[:rk]), s
+        assert np.array_equal(gA[s], wa), s
+        if B is not None:
+            assert np.array_equal(gB[s], wb), s
+        ranks.append(rk)
+    return ranks
+
+
+def test_config3_gf2_k8192_whole_buffers_vs_reference():
+    """BASELINE configs[2]: GF(2) binmat elimination K=8192, bit-packed (1024-byte rows).  Three systems:
+    a random one (rank K-d, d = 0..2 with probability 0.29/0.58/0.13), one with a forced row
+    dependency (rank <= K-1) and one with a zero column and a duplicated row.  Ranks, pivot columns
+    and every byte of A against refdrv_binmat_rref (binmat_get / binmat_add / binmat_swaprow)."""
+    K = 8192
+    A = np.stack([random_matrix(GF2, K, K, 8100 + s) for s in range(3)])
+    assert A.shape[2] == 1024
+    A[1, 4000] = A[1, 17] ^ A[1, 4999]
+    A[2, :, 3] &= 0xFE          # zero column 24
+    A[2, 6000] = A[2, 1]
+    ranks = check_batch(GF2, A, None, K)
+    assert ranks[1] < K and ranks[2] < K - 1 and min(ranks) >= K - 8
+
+
+def test_config3_gf2_k8192_with_rhs():
+    """same size with a 32-byte right-hand side (binmat_add on B beside A)"""
+    K = 8192
+    A = random_matrix(GF2, K, K, 8200)[None]
+    B = splitmix_bytes(8201, K * 32).reshape(1, K, 32).copy()
+    check_batch(GF2, A, B, K)
+
+
+@pytest.mark.parametrize("field", [GF16, GF4], ids=["gf16", "gf4"])
+def test_config4_packed_fields_k2048_whole_buffers_vs_reference(field):
+    """BASELINE configs[3]: GF(16) / GF(4) elimination K=2048 (1024- / 512-byte rows), three systems, one
+    of them rank deficient, one with a right-hand side check in the second call; against
+    refdrv_gfmat_solve (gfmat_get/swaprow/scal/axpy; GF(4) with the corrected table)."""
+    K = 2048
+    A = np.stack([random_matrix(field, K, K, 8300 + 10 * field + s) for s in range(3)])
+    assert A.shape[2] == K * FIELD_BITS[field] // 8
+    A[1, 1500] = A[1, 2]                 # duplicate row
+    A[1, :, 0] &= 0xF0 if field == GF16 else 0xFC   # zero column 0
+    ranks = check_batch(field, A, None, K)
+    assert ranks[1] < K
+    B = splitmix_bytes(8400 + field, K * 256).reshape(1, K, 256).copy()   # 256 bytes: a legal stride for OCTMAT_ALIGN 16/32/64
+    check_batch(field, A[:1].copy(), B, K)
+
+
+def ref_apply(Cm, Kc, D, rows):
+    """rows `rows` of Y = C*D by the reference's oaxpy loop (refdrv_octmat_apply), oracle port if absent"""
+    lib = best_reference()
+    n = D.shape[1]
+    Cs = np.ascontiguousarray(Cm[rows, :Kc])
+    if lib is None or (lib.refdrv_octmat_align() != 16 and n % 64):
+        Y = np.zeros((len(rows), n), dtype=np.uint8)
+        oracle().orc_gf256_apply(ptr(Cs), Cs.strides[0], len(rows), Kc, ptr(D), D.strides[0], ptr(Y), n, n)
+        return Y
+    c_, d_, y_ = lib.octmat_new(len(rows), Kc), lib.octmat_new(Kc, n), lib.octmat_new(len(rows), n)
+    mat_view(c_)[:, :Kc] = Cs
+    mat_view(d_)[:, :n] = D
+    lib.refdrv_octmat_apply(c_, d_, y_)
+    Y = mat_view(y_)[:, :n].copy()
+    for m in (c_, d_, y_):
+        lib.octmat_free(m)
+    return Y
+
+
+def test_config5_apply_k10000_column_window_vs_reference(cuda_lib):
+    """BASELINE configs[4] at its own inner dimension: C 10000 x 10000, a 960-byte symbol-column window
+    of D (two full 480-byte tiles of the tcgen05 kernel; 1250 K-steps per tile).  Every 16th row plus
+    the last 16 rows of Y against the reference's K^2 oaxpy loop, all rows by linearity (D1 ^ D2), and
+    the same result again in three column passes (workspace budget below one tile's operand blocks)."""
+    K, N = 10000, 960 + 64
+    cs = 10048   # multiple of 64: the same C serves the AVX-512 build of the reference
+    Cm = torch.zeros((K, cs), dtype=torch.uint8, device="cuda")
+    tmp = torch.empty((K, cs), dtype=torch.uint8, device="cuda")
+    device.fill_random(tmp, 9100)
+    Cm[:, :K] = tmp[:, :K]
+    del tmp
+    D1 = torch.empty((K, N), dtype=torch.uint8, device="cuda")
+    D2 = torch.empty((K, N), dtype=torch.uint8, device="cuda")
+    device.fill_random(D1, 9101)
+    device.fill_random(D2, 9102)
+    Y1 = device.apply(Cm, D1)
+    Y2 = device.apply(Cm, D2)
+    Y12 = device.apply(Cm, D1 ^ D2)
+    device.sync()
+    assert torch.equal(Y1 ^ Y2, Y12)
+    rows = np.concatenate([np.arange(0, K, 16), np.arange(K - 16, K)])
+    want = ref_apply(host(Cm), K, host(D1), rows)
+    assert np.array_equal(host(Y1)[rows], want)
+    # several passes over the column range: one 480-byte tile of 1250 K-steps needs 19.2 MB of fp4 blocks
+    old = cuda_lib.oblas_b200_set_workspace_budget(20 << 20)
+    try:
+        launches0 = cuda_lib.oblas_b200_launch_count()
+        Y1p = device.apply(Cm, D1)
+        device.sync()
+        assert cuda_lib.oblas_b200_launch_count() - launches0 == 6   # 3 passes x (expansion + GEMM)
+        assert torch.equal(Y1p, Y1)
+        Y1p ^= Y1
+        Yacc = device.apply(Cm, D1, Y=Y1p, accumulate=True)       # 0 ^= C*D in three passes
+        device.sync()
+        assert torch.equal(Yacc, Y1)
+    finally:
+        cuda_lib.oblas_b200_set_workspace_budget(old)
+
+
+def test_elimination_in_several_chunks_of_systems(cuda_lib):
+    """solve_tc_run with a workspace budget that holds two systems: 7 systems = 4 chunks (the bench's
+    4096 systems run as 2 chunks with the default 3 GiB).  Whole buffers against the table kernel and,
+    for two systems of each chunk, against the reference."""
+    K, L, nsys = 640, 320, 7   # strides that are multiples of 64: the AVX-512 build of the reference (OCTMAT_ALIGN=64) takes them
+    A = np.stack([random_matrix(GF256, K, K, 9200 + s) for s in range(nsys)])
+    A[3, 77] = A[3, 5]
+    A[6, :, 130] = 0
+    B = np.stack([splitmix_bytes(9300 + s, K * L).reshape(K, L) for s in range(nsys)]).copy()
+    per_sys = 4 * 16 * 7680 + K * 128 + K * 2 + 272
+    old = cuda_lib.oblas_b200_set_workspace_budget(2 * per_sys + 4096)
+    try:
+        cuda_lib.oblas_b200_set_tuning(3, -1)
+        cuda_lib.oblas_b200_solve_tc_times(1, None, None)
+        dA, dB = dev(A), dev(B)
+        rank, piv = device.solve_batch(GF256, dA, K, dB, want_pivcols=True)
+        device.sync()
+        ms, n = (C.c_double * 4)(), (C.c_uint64 * 4)()
+        cuda_lib.oblas_b200_solve_tc_times(0, ms, n)
+        assert n[3] == 4 and n[0] == 4 * 5, list(n)      # 4 chunks x (5 outer panels + 1 permutation)
+    finally:
+        cuda_lib.oblas_b200_set_workspace_budget(old)
+        cuda_lib.oblas_b200_set_tuning(-1, -1)
+    cuda_lib.oblas_b200_set_tuning(1, -1)
+    tA, tB = dev(A), dev(B)
+    trank, tpiv = device.solve_batch(GF256, tA, K, tB, want_pivcols=True)
+    device.sync()
+    cuda_lib.oblas_b200_set_tuning(-1, -1)
+    assert torch.equal(rank, trank) and torch.equal(dA, tA) and torch.equal(dB, tB)
+    gA, gB, rank = host(dA), host(dB), host(rank)
+    for s in (0, 3, 4, 6):
+        rk, pv, wa, wb = ref_solve(GF256, A[s], B[s], K)
+        assert rank[s] == rk and np.array_equal(gA[s], wa) and np.array_equal(gB[s], wb), s
+    assert rank[3] == K - 1 and rank[6] == K - 1
+
+
+def test_host_streaming_on_the_tensor_core_path(cuda_lib):
+    """oblas_b200_solve_batch_host with systems big enough for the tcgen05 path: 3 lanes, each with its
+    own stream, workspace slot and status word; 7 systems in chunks of 2"""
+    K, L, nsys = 640, 320, 7   # strides that are multiples of 64: the AVX-512 build of the reference (OCTMAT_ALIGN=64) takes them
+    A = np.stack([random_matrix(GF256, K, K, 9400 + s) for s in range(nsys)])
+    A[2, 100] = A[2, 101]
+    B = np.stack([splitmix_bytes(9500 + s, K * L).reshape(K, L) for s in range(nsys)]).copy()
+    A0, B0 = A.copy(), B.copy()
+    rank = np.zeros(nsys, dtype=np.int32)
+    piv = np.zeros((nsys, K), dtype=np.uint32)
+    capi.check(cuda_lib.oblas_b200_solve_batch_host(
+        GF256, A.ctypes.data, A.strides[1], A.strides[0], K, K, K, B.ctypes.data, B.strides[1], B.strides[0], L,
+        rank.ctypes.data, piv.ctypes.data, nsys, 2))
+    want = [ref_solve(GF256, A0[s], B0[s], K) for s in range(nsys)]
+    for s in range(nsys):
+        rk, pv, wa, wb = want[s]
+        assert rank[s] == rk and np.array_equal(piv[s][:rk], pv[:rk]), s
+        assert np.array_equal(A[s], wa) and np.array_equal(B[s], wb), s
+    assert rank[2] == K - 1
+    # OBLAS_B200_SOLVE_SKIP_IDENTITY_A: A of the full-rank systems (= I, known in advance) is not copied back
+    A2, B2 = A0.copy(), B0.copy()
+    rank2 = np.zeros(nsys, dtype=np.int32)
+    capi.check(cuda_lib.oblas_b200_solve_batch_host_ex(
+        GF256, A2.ctypes.data, A2.strides[1], A2.strides[0], K, K, K, B2.ctypes.data, B2.strides[1], B2.strides[0], L,
+        rank2.ctypes.data, None, nsys, 2, 1))
+    assert np.array_equal(rank2, rank) and np.array_equal(B2, B)
+    for s in range(nsys):
+        assert np.array_equal(A2[s], A0[s] if rank[s] == K else want[s][2]), s
+
+
+def test_barrier_time_limit_is_reported_and_the_device_recovers(cuda_lib):
+    """fault injection: the operand producer of the tcgen05 kernels never delivers, so the MMA warp's
+    wait runs into the (shortened) WALL-time limit, every role drains, tensor memory is released and
+    the status word turns oblas_b200_sync into an error -- for the apply, the elimination's update
+    kernel and the host-streaming call.  Afterwards the same calls give the right answer again (a
+    kernel that had kept its 512 TMEM columns would block the next allocation on that SM)."""
+    M, Kc, N = 320, 96, 960
+    Cm = dev(splitmix_bytes(9600, M * Kc).reshape(M, Kc))
+    D = dev(splitmix_bytes(9601, Kc * N).reshape(Kc, N))
+    cuda_lib.oblas_b200_set_tuning(3, 3)
+    good = device.apply(Cm, D)
+    device.sync()
+    K, L = 256, 320
+    A = np.stack([random_matrix(GF256, K, K, 9610 + s) for s in range(2)])
+    B = splitmix_bytes(9612, 2 * K * L).reshape(2, K, L).copy()
+    cuda_lib.oblas_b200_set_wait_limit_ms(50)
+    cuda_lib.oblas_b200_set_fault_injection(8)
+    try:
+        device.apply(Cm, D)
+        assert cuda_lib.oblas_b200_sync() != 0
+        assert b"time limit" in cuda_lib.oblas_b200_last_error()
+        assert cuda_lib.oblas_b200_sync() == 0          # collected: the flag is not sticky
+        dA, dB = dev(A), dev(B)
+        device.solve_batch(GF256, dA, K, dB)
+        assert cuda_lib.oblas_b200_sync() != 0
+        # uncollected failure of an asynchronous call: the next call on the stream reports it once
+        device.apply(Cm, D)
+        torch.cuda.synchronize()
+        rc = cuda_lib.oblas_b200_gf256_apply(C.c_void_p(Cm.data_ptr()), Kc, M, Kc, C.c_void_p(D.data_ptr()), N,
+                                             C.c_void_p(good.data_ptr()), N, N, 1)
+        assert rc != 0 and b"never" in cuda_lib.oblas_b200_last_error()
+        hA, hB = A.copy(), B.copy()
+        rank = np.zeros(2, dtype=np.int32)
+        rc = cuda_lib.oblas_b200_solve_batch_host(GF256, hA.ctypes.data, K, K * K, K, K, K, hB.ctypes.data, L, K * L, L,
+                                                  rank.ctypes.data, None, 2, 1)
+        assert rc != 0 and b"time limit" in cuda_lib.oblas_b200_last_error()
+    finally:
+        cuda_lib.oblas_b200_set_fault_injection(0)
+        cuda_lib.oblas_b200_set_wait_limit_ms(0)
+    again = device.apply(Cm, D)
+    device.sync()
+    assert torch.equal(again, good)
+    dA, dB = dev(A), dev(B)
+    rank, _ = device.solve_batch(GF256, dA, K, dB)
+    device.sync()
+    cuda_lib.oblas_b200_set_tuning(-1, -1)
+    for s in range(2):
+        rk, pv, wa, wb = ref_solve(GF256, A[s], B[s], K)
+        assert int(rank[s]) == rk and np.array_equal(host(dA)[s], wa) and np.array_equal(host(dB)[s], wb)
+
+
+def test_gf2_scalars_above_one_are_no_ops_in_batches_too(cuda_lib):
+    """gfmat_axpy(GF2_1, u > 1) is a no-op in the single call; a batch must behave like n single calls"""
+    rows, st = 8, 64
+    a = splitmix_bytes(9700, rows * st).reshape(rows, st).copy()
+    b = splitmix_bytes(9701, rows * st).reshape(rows, st).copy()
+    da, db = dev(a), dev(b)
+    idx = torch.arange(rows, dtype=torch.int32, device="cuda")
+    u = dev(np.array([0, 1, 2, 3, 1, 255, 0, 1], dtype=np.uint8))
+    device.rowops(GF2, capi.OP_AXPY, da, db, idx, idx, u)
+    want = a.copy()
+    for k in (1, 4, 7):
+        want[k] ^= b[k]
+    assert np.array_equal(host(da), want)
