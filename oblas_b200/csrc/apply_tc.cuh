@@ -232,6 +232,12 @@ OB2_D bool mbar_try(uint32_t bar, uint32_t parity) {
                : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   return done != 0;
 }
+// (mbarrier.try_wait with a suspend-time hint would park the waiting warp in hardware -- measured on this
+// B200 / driver: the kernel then takes SECONDS, the parked warps are not woken when the phase completes.)
+// Waiting roles that are not latency critical (producers, A builders: they wait 70-80 % of the time) pass a
+// back-off: their polling loops otherwise issue as many instructions as the epilogue warps that do the
+// work -- ncu source view of update_tc_kernel: 4.9 k warp instructions per column tile in wait loops against
+// 4.8 k in the epilogue, together 2.4 k issue slots per scheduler and tile = the tile time.
 OB2_D bool mbar_wait(uint32_t bar, uint32_t parity, int *status, uint32_t backoff_ns = 0) {
   if (mbar_try(bar, parity)) return true;
   unsigned long long t0 = 0;
@@ -326,9 +332,9 @@ OB2_D void stg_pred(void *ptr, uint32_t v, bool pred) {
 // word of chunk cc lies in region 1 if its virtual column is >= split, else in region 0.
 // ncur = MMA width of the tile (240, or the 16-aligned rest of the virtual range for the last
 // tile): the chunks below ncur are shared out between the two warps of a lane quarter.
-template <int TILE_N>
+template <int TILE_N, int PARTS = kEpiParts>
 struct EpiTile {
-  static constexpr int kChunks = (TILE_N + 31) / 32, kC0 = (kChunks + kEpiParts - 1) / kEpiParts;
+  static constexpr int kChunks = (TILE_N + 31) / 32, kC0 = (kChunks + PARTS - 1) / PARTS;
   // per (system, row): this lane's row in region 0 / region 1 (y1 has "- split" folded in, so both
   // are indexed by the virtual column), the region boundary and the end of the virtual range
   uint8_t *y0, *y1;
@@ -363,8 +369,8 @@ struct EpiTile {
     vt = v_tile + ct0;
     const uint32_t rest = vend > v_tile ? vend - v_tile : 0u;
     const int nch = rest >= (uint32_t)TILE_N ? kChunks : (int)((rest + 31) / 32);
-    c_lo = (nch * (int)part) / kEpiParts;
-    c_hi = (nch * ((int)part + 1)) / kEpiParts;
+    c_lo = (nch * (int)part) / PARTS;
+    c_hi = (nch * ((int)part + 1)) / PARTS;
   }
   OB2_D void set(uint32_t warp, uint32_t lane, const TcRegion *reg, uint32_t nreg, uint32_t sys, uint32_t tile,
                  uint32_t it, uint32_t M) {
@@ -393,10 +399,10 @@ struct EpiTile {
 // tools/tmem_ld.cu: 720 B/clk/SM next to running MMAs), so a second buffer buys nothing -- but its 32
 // registers forced the packing into one serial FADD -> SHF chain (440 clk per chunk measured).
 // pc (diagnostics, may be null): cycles in 0 = TMEM read, 1 = packing + transposes, 2 = stores.
-template <int TILE_N>
-OB2_D void epilogue_tile(uint32_t tm, uint32_t acc_col, uint32_t warp, uint32_t lane, const EpiTile<TILE_N> &e,
-                         const uint32_t (&oldw)[EpiTile<TILE_N>::kC0], long long *pc = nullptr) {
-  constexpr int kC0 = EpiTile<TILE_N>::kC0;
+template <int TILE_N, int PARTS = kEpiParts>
+OB2_D void epilogue_tile(uint32_t tm, uint32_t acc_col, uint32_t warp, uint32_t lane, const EpiTile<TILE_N, PARTS> &e,
+                         const uint32_t (&oldw)[EpiTile<TILE_N, PARTS>::kC0], long long *pc = nullptr) {
+  constexpr int kC0 = EpiTile<TILE_N, PARTS>::kC0;
   if (e.c_lo >= e.c_hi) return;
   const uint32_t tbase = tm + (((warp & 3u) * 32u) << 16) + acc_col;
   uint32_t w[kC0];
@@ -415,6 +421,9 @@ OB2_D void epilogue_tile(uint32_t tm, uint32_t acc_col, uint32_t warp, uint32_t 
       // mantissa LSB).  Column c = 4*j + k2 goes to bit k2*8 + j of this lane's word: one funnel
       // shift per accumulator pushes the LSB into the top of one of four 8-deep chains (chain k2
       // collects byte k2 in its top byte), two instructions per accumulator in all.
+      // (Starting the accumulators at 2^23 instead -- every MMA accumulating, the epilogue storing the
+      // bias back with tcgen05.st after each read -- removes the add but was NOT exact on B200 and no
+      // faster either: measured and dropped)
       uint32_t wq[4] = {0, 0, 0, 0};
 #pragma unroll
       for (int pp = 0; pp < 32; pp++) {
@@ -785,8 +794,69 @@ constexpr int kUSteps = 16;                       // K-steps = 128 coefficient c
 constexpr int kUSPS = 4, kUStages = 4;            // B ring: 4 stages of 4 steps (30720 B) = one column tile
 constexpr int kUBStage = kUSPS * kHBlock;
 constexpr int kUABuf = kUSteps * kATile;          // resident A operand of one row tile (73728 B)
-constexpr size_t kUSmemBytes = (size_t)kUABuf + (size_t)kUStages * kUBStage + kLutBytes + 256 + 1024;
+// ---- what bounds this kernel, measured in round 2 (tools/mma_commit.cu -> profiles/r02_mma_issue_b200.jsonl,
+// role counters oblas_b200_update_phases, ncu source view profiles/r02_ncu_update_tc_roles.json) ----
+// * tcgen05.mma issue costs the issuing thread >= 46 clk, the tensor pipe queues 4-6 MMAs behind the running
+//   one; a try_wait on a barrier that completed long ago still takes ~115 clk, a tcgen05.commit ~77 clk.  With
+//   ONE issuing warp the thread's own instruction stream per column tile (16 MMAs, 6.5 waits, 5.5 commits) was
+//   ~2800 clk against 1870 clk of tensor-pipe time: the kernel ran at the speed of that thread.
+// * TWO issuing warps (kUIssuers): column tiles alternate between warp kMmaWarp (even tiles, accumulator set 0)
+//   and warp kMma2Warp (odd tiles, set 1; another scheduler).  All MMAs of a tile come from one thread, the two
+//   threads use different accumulators, every commit tracks its own thread's MMAs: b_empty / tmem_full as
+//   before, a_empty needs the commit of BOTH threads after their last tile of the unit.  A waiter must see every
+//   phase of a barrier (a parity wait is also satisfied by the phase before last), hence one set of b_full
+//   barriers per issuing warp and the pass through a_full for a unit the warp has no tile in.
+// * One producer iteration (wait for the slot, arrive.expect_tx, bulk copy) takes ~440 clk of its thread whatever
+//   the copy size (15 KB / 7.5 KB stages: the kernel slows down in proportion to the number of copies, so
+//   kRSPS stays 4); one producer serving the four slots in turn put up to four of those in front of a refill
+//   (MMA warp waiting 680 clk per tile for B).  kUProducers warps share the slots (s % kUProducers): 240 clk.
+// * What remains is the read-out: the 8 epilogue warps are busy ~2470 clk per tile (1660 TMEM read + parity
+//   packing + transposes + stores, ~800 addressing / prefetch of the old words) and hold an accumulator set
+//   meanwhile -- 2640 clk per tile now against 1870 clk of MMAs (0.78 of the fp4 peak on this kernel).  Measured
+//   and NOT faster: 12 epilogue warps (the per-warp time does not shrink), one tmem_empty arrive per warp,
+//   token passing between the issuers (tiles issued strictly in turn), testing the next barrier before
+//   issuing (the extra try_wait costs the issuing thread more than it hides), back-off in the producers' and
+//   builders' waits, accumulators biased by 2^23 so that the parity needs no add (not exact: dropped), and
+//   mbarrier.try_wait with a suspend-time hint (parked warps are not woken: the kernel takes seconds).
+#ifndef OB2_U_SPS
+#define OB2_U_SPS 4
+#endif
+constexpr int kRSPS = OB2_U_SPS, kRStages = kUSteps / kRSPS;   // B ring: kRStages stages of kRSPS steps = one column tile
+constexpr int kRBStage = kRSPS * kHBlock;
+static_assert(kRSPS * kRStages == kUSteps && (kUSPS % kRSPS) == 0, "ring stages do not straddle the A parts");
+constexpr size_t kUSmemBytes = (size_t)kUABuf + (size_t)kUStages * kUBStage + kLutBytes + 512 + 1024;
 static_assert(kUSteps == kUSPS * kUStages, "one trip around the B ring per column tile");
+#ifndef OB2_U_EPIPARTS
+#define OB2_U_EPIPARTS 2
+#endif
+#ifndef OB2_U_ISSUERS
+#define OB2_U_ISSUERS 2
+#endif
+#ifndef OB2_U_TURN
+#define OB2_U_TURN 0
+#endif
+#ifndef OB2_U_PRODUCERS
+#define OB2_U_PRODUCERS 2
+#endif
+#ifndef OB2_U_WARPARRIVE
+#define OB2_U_WARPARRIVE 0
+#endif
+#ifndef OB2_U_PROD_BACKOFF
+#define OB2_U_PROD_BACKOFF 0
+#endif
+#ifndef OB2_U_BUILD_BACKOFF
+#define OB2_U_BUILD_BACKOFF 0
+#endif
+constexpr int kUEpiParts = OB2_U_EPIPARTS, kUEpiWarps = 4 * kUEpiParts;   // epilogue warps per TMEM lane quarter
+constexpr int kUIssuers = OB2_U_ISSUERS;          // MMA-issuing warps
+constexpr bool kUTurn = OB2_U_TURN != 0;          // tiles issued strictly one after the other (token passing)
+constexpr int kMma2Warp = kEpi0 + kUEpiWarps;     // first warp after the epilogue warps (14 -> scheduler 2; warp 0 is on scheduler 0)
+constexpr int kUProducers = OB2_U_PRODUCERS;
+constexpr bool kUWarpArrive = OB2_U_WARPARRIVE != 0;   // one tmem_empty arrive per epilogue warp instead of one per thread
+constexpr uint32_t kUProdBackoff = OB2_U_PROD_BACKOFF, kUBuildBackoff = OB2_U_BUILD_BACKOFF;   // ns
+constexpr int kProd2Warp = kMma2Warp + (kUIssuers > 1 ? 1 : 0);   // producers 1 .. kUProducers-1
+constexpr int kUThreads = 32 * (kProd2Warp + kUProducers - 1);
+static_assert(kRStages % kUProducers == 0, "ring slots are dealt out evenly");
 static_assert(kUSPS == kBuilderWarps, "each builder warp builds one step of every stage's A part");
 
 // Order of the column tiles inside a unit: the narrow last tile of the virtual range (its MMAs take
@@ -800,38 +870,45 @@ OB2_D uint32_t update_tile_at(uint32_t j, uint32_t ntiles) {
 }
 
 template <bool PROF>
-__global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArgs p) {
+__global__ void __launch_bounds__(kUThreads, 1) update_tc_kernel(const ApplyTcArgs p) {
   extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
   unsigned char *sm = tc_smem_raw + ((1024u - (smem_addr(tc_smem_raw) & 1023u)) & 1023u);
   unsigned char *smA = sm;                                   // [kUSteps][kATile]
   unsigned char *smB = sm + (size_t)kUABuf;                  // [kUStages][kUSPS][kHBlock]
   uint32_t *lut = reinterpret_cast<uint32_t *>(smB + (size_t)kUStages * kUBStage);
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(lut) + kLutBytes);
-  // bars: b_full[S], b_empty[S], a_full[S], a_empty[S] (one A part per ring stage), tmem_full[2], tmem_empty[2]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 24);
-  static_assert(4 * kUStages + 4 <= 24, "barrier block");
+  // bars (R = kRStages ring stages, 4 A parts): b_full[R] (even tiles), b_empty[R], a_full[4], a_empty[4],
+  // tmem_full[2], tmem_empty[2], b_full[R] (odd tiles), turn[2].  A waiter must see EVERY phase of a barrier
+  // it waits on (a parity wait is satisfied by the phase before last as well), and each MMA-issuing warp only
+  // takes every other tile: hence one set of b_full barriers per warp.
+  constexpr int R = kRStages;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * R + 14);
+  static_assert((3 * R + 14) * 8 + 4 <= 512, "barrier block");
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar0 = smem_addr(bars);
-  auto b_full = [&](uint32_t s) { return bar0 + 8u * s; };
-  auto b_empty = [&](uint32_t s) { return bar0 + 8u * (kUStages + s); };
-  auto a_full = [&](uint32_t h) { return bar0 + 8u * (2 * kUStages + h); };
-  auto a_empty = [&](uint32_t h) { return bar0 + 8u * (3 * kUStages + h); };
-  auto tmem_full = [&](uint32_t b) { return bar0 + 8u * (4 * kUStages + b); };
-  auto tmem_empty = [&](uint32_t b) { return bar0 + 8u * (4 * kUStages + 2 + b); };
+  auto b_full = [&](uint32_t odd, uint32_t s) { return bar0 + 8u * (odd ? 2 * R + 12 + s : s); };
+  auto b_empty = [&](uint32_t s) { return bar0 + 8u * (R + s); };
+  auto a_full = [&](uint32_t h) { return bar0 + 8u * (2 * R + h); };
+  auto a_empty = [&](uint32_t h) { return bar0 + 8u * (2 * R + 4 + h); };
+  auto tmem_full = [&](uint32_t b) { return bar0 + 8u * (2 * R + 8 + b); };
+  auto tmem_empty = [&](uint32_t b) { return bar0 + 8u * (2 * R + 10 + b); };
+  auto turn = [&](uint32_t w) { return bar0 + 8u * (3 * R + 12 + w); };
 
   build_bitmatrix_lut(lut, tid);
   if (tid == 0) {
-    for (uint32_t s = 0; s < (uint32_t)kUStages; s++) {
-      mbar_init(b_full(s), 1);          // producer's expect_tx arrive
+    for (uint32_t s = 0; s < (uint32_t)kRStages; s++) {
+      mbar_init(b_full(0, s), 1);       // producer's expect_tx arrive
+      mbar_init(b_full(1, s), 1);
       mbar_init(b_empty(s), 1);         // tcgen05.commit
     }
     for (uint32_t s = 0; s < (uint32_t)kUStages; s++) {
       mbar_init(a_full(s), 32 * kBuilderWarps);
-      mbar_init(a_empty(s), 1);
+      mbar_init(a_empty(s), 2);         // tcgen05.commit of both MMA-issuing threads
     }
     for (uint32_t b = 0; b < 2; b++) {
+      mbar_init(turn(b), 1);
       mbar_init(tmem_full(b), 1);
-      mbar_init(tmem_empty(b), 32 * kEpiWarps);     // every thread arrives as it finishes (one arrive per warp behind a __syncwarp measured 5 % slower)
+      mbar_init(tmem_empty(b), kUWarpArrive ? kUEpiWarps : 32 * kUEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -859,39 +936,45 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
   const uint32_t itiles = p.itiles, ntiles = p.ntiles;
   const uint32_t nunits = p.nsys * itiles;       // (system, row tile)
 
-  if (warp == kProdWarp) {
-    // ------------------------------------------------------------ producer: B blocks of every column tile
+  if (warp == kProdWarp || (kUProducers > 1 && warp >= (uint32_t)kProd2Warp)) {
+    // ------------------------------------------------------------ producers: B blocks of every column tile
+    const uint32_t pwi = (warp == kProdWarp) ? 0u : warp - (uint32_t)kProd2Warp + 1u;   // producer index
     const bool leader = elect_one();
     const uint32_t b_dst0 = smem_addr(smB);
-    uint32_t s = 0, ph = 0;
+    uint32_t ph = 0, tile_iter = 0;
     bool ok = true;
-    const bool prof = PROF && p.prof != nullptr;
+    const bool prof = PROF && p.prof != nullptr && pwi == 0;
     long long pt0 = prof ? clock64() : 0, pw = 0;
     for (uint32_t su = blockIdx.x; su < nunits && ok; su += gridDim.x) {
       const uint32_t sys = su / itiles;
       const uint8_t *src0 = p.Dx + (size_t)sys * ntiles * kUSteps * kHBlock;
-      for (uint32_t q = 0; q < ntiles * (uint32_t)kUStages && ok; q++) {
-        const uint8_t *src = src0 + ((size_t)update_tile_at(q / kUStages, ntiles) * kUStages + q % kUStages) * kUBStage;
-        const long long w0 = prof ? clock64() : 0;
-        if (!mbar_wait(b_empty(s), ph ^ 1u, p.status)) { ok = false; break; }
-        if (prof) pw += clock64() - w0;
-        if (leader && !(p.dbg & 8)) {
-          if (p.dbg & 1) {
-            mbar_arrive(b_full(s));
-          } else {
-            mbar_arrive_expect_tx(b_full(s), kUBStage);
-            bulk_g2s(b_dst0 + s * kUBStage, src, kUBStage, b_full(s));
+      for (uint32_t j = 0; j < ntiles && ok; j++, ph ^= 1u) {
+        const uint32_t odd = (tile_iter + j) & 1u;            // which set of b_full barriers this tile uses
+        const uint8_t *srct = src0 + (size_t)update_tile_at(j, ntiles) * kUSteps * kHBlock;
+#pragma unroll
+        for (uint32_t s = pwi; s < (uint32_t)kRStages; s += (uint32_t)kUProducers) {
+          const long long w0 = prof ? clock64() : 0;
+          if (!mbar_wait(b_empty(s), ph ^ 1u, p.status, kUProdBackoff)) { ok = false; break; }
+          if (prof) pw += clock64() - w0;
+          if (leader && !(p.dbg & 8)) {
+            if (p.dbg & 1) {
+              mbar_arrive(b_full(odd, s));
+            } else {
+              mbar_arrive_expect_tx(b_full(odd, s), kRBStage);
+              bulk_g2s(b_dst0 + s * kRBStage, srct + (size_t)s * kRBStage, kRBStage, b_full(odd, s));
+            }
           }
         }
-        if (++s == (uint32_t)kUStages) { s = 0; ph ^= 1u; }
       }
+      tile_iter += ntiles;
     }
     if (prof && leader) {
       atomicAdd(p.prof + 7, (unsigned long long)pw);
       atomicAdd(p.prof + 8, (unsigned long long)(clock64() - pt0));
     }
-  } else if (warp == kMmaWarp) {
-    // ------------------------------------------------------------ MMA issuer
+  } else if (warp == kMmaWarp || (kUIssuers > 1 && warp == (uint32_t)kMma2Warp)) {
+    // ------------------------------------------------------------ MMA issuers (see kMma2Warp)
+    const uint32_t me = (warp == kMmaWarp) ? 0u : 1u;   // two issuers: = accumulator set = parity of the tiles this warp issues
     const bool leader = elect_one();
     // A,B = E2M1 (1), K-major, scales UE8M0, M = 128, K = 64; N is set per tile: 240, or the
     // 16-aligned rest of the virtual column range for the last tile (MMA time is proportional to N)
@@ -900,48 +983,73 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
     const uint64_t a_desc0 = umma_desc(smem_addr(smA), kALbo, kASbo);
     const uint64_t b_desc0 = umma_desc(smem_addr(smB));
     const uint32_t sfa = tm + kSfCol, sfb = tm + kSfCol + 16;
-    uint32_t ph = 0, tile_iter = 0, unit_iter = 0;
+    uint32_t tile_iter = 0, unit_iter = 0;
     bool ok = true;
-    const bool prof = PROF && p.prof != nullptr;
+    const bool prof = PROF && p.prof != nullptr && me == 0;
     long long pt0 = prof ? clock64() : 0, pwa = 0, pwt = 0, pwb = 0;
     for (uint32_t su = blockIdx.x; su < nunits && ok; su += gridDim.x, unit_iter++) {
+      bool a_seen = false;                                  // this warp has waited for the unit's A operand
       for (uint32_t j = 0; j < ntiles && ok; j++, tile_iter++) {
+        if (kUIssuers > 1 && (tile_iter & 1u) != me) continue;
         const uint32_t nt = update_tile_at(j, ntiles);
-        const uint32_t ab = tile_iter & 1u;
-        const bool first = j == 0, last = j + 1 == ntiles;
+        const uint32_t ab = tile_iter & 1u;                 // accumulator set (two issuers: == me)
+        const uint32_t acc0 = tm + ab * kHalfN;
+        // first / last tile of the unit issued by THIS warp
+        const bool first = !a_seen, last = (kUIssuers > 1) ? (j + 2 >= ntiles) : (j + 1 == ntiles);
+        a_seen = true;
+        const uint32_t ph = (tile_iter >> 1) & 1u;          // this warp's b_full barriers: one phase per tile it issues
         long long w0 = prof ? clock64() : 0;
         if (!mbar_wait(tmem_empty(ab), ((tile_iter >> 1) & 1u) ^ 1u, p.status)) { ok = false; break; }
         if (prof) pwt += clock64() - w0;
         tc_fence_after();
-        const uint32_t acc0 = tm + ab * kHalfN;
         const uint32_t rest = vend - nt * kHalfN;          // > 0: ntiles = ceil(vend / 240)
         const uint32_t ncur = rest >= (uint32_t)kHalfN ? (uint32_t)kHalfN : ((rest + 15u) & ~15u);
         const uint32_t idesc = idesc0 | ((ncur >> 3) << 17);
 #pragma unroll
-        for (int cs = 0; cs < kUStages; cs++) {
-          if (first) {                                      // this stage's part of the unit's A operand is built
+        for (int cs = 0; cs < kRStages; cs++) {
+          constexpr int kPerPart = kUSPS / kRSPS;           // ring stages per A part
+          const int h = cs / kPerPart;                      // the A part this stage reads
+          if (first && cs % kPerPart == 0) {                // this part of the unit's A operand is built
             w0 = prof ? clock64() : 0;
-            if (!mbar_wait(a_full(cs), unit_iter & 1u, p.status)) { ok = false; break; }
+            if (!mbar_wait(a_full(h), unit_iter & 1u, p.status)) { ok = false; break; }
             if (prof) pwa += clock64() - w0;
           }
           w0 = prof ? clock64() : 0;
-          if (!mbar_wait(b_full(cs), ph, p.status)) { ok = false; break; }
+          if (!mbar_wait(b_full(ab, cs), ph, p.status)) { ok = false; break; }
           if (prof) pwb += clock64() - w0;
+          // (kUTurn) the tiles are ISSUED one after the other: before its first MMA this warp waits until the
+          // other warp has issued all of the tile before -- measured no faster than free interleaving
+          if (kUIssuers > 1 && kUTurn && cs == 0 && tile_iter > 0) {
+            if (!mbar_wait(turn(me), ((tile_iter - 1) >> 1) & 1u, p.status)) { ok = false; break; }
+          }
           tc_fence_after();
           if (leader) {
 #pragma unroll
-            for (int u = 0; u < kUSPS; u++) {
-              const int step = cs * kUSPS + u;
+            for (int u = 0; u < kRSPS; u++) {
+              const int step = cs * kRSPS + u;
               umma_mxf4(acc0, a_desc0 + (uint64_t)((step * kATile) >> 4),
-                        b_desc0 + (uint64_t)((cs * kUBStage + u * kHBlock) >> 4), idesc, step > 0 ? 1u : 0u, sfa, sfb);
+                        b_desc0 + (uint64_t)((cs * kRBStage + u * kHBlock) >> 4), idesc, step > 0 ? 1u : 0u, sfa, sfb);
             }
             tc_commit(b_empty(cs));
-            // last column tile of the unit: everything that reads this half of A has been issued
-            if (last) tc_commit(a_empty(cs));
+            // this warp's last column tile of the unit: everything IT issued that reads this part of A is
+            // covered; the other warp commits after its own last tile (one issuer, or a unit of one tile:
+            // both arrivals here)
+            if (last && cs % kPerPart == kPerPart - 1) {
+              tc_commit(a_empty(h));
+              if (kUIssuers == 1 || ntiles == 1) tc_commit(a_empty(h));
+            }
           }
         }
-        ph ^= 1u;
-        if (ok && leader) tc_commit(tmem_full(ab));
+        if (ok && leader) {
+          if (kUIssuers > 1 && kUTurn) mbar_arrive(turn(me ^ 1u));   // the other warp may issue the next tile
+          tc_commit(tmem_full(ab));
+        }
+      }
+      // a unit of one tile issued by the other warp: still pass through the unit's a_full phases
+      if (!a_seen && ok) {
+#pragma unroll
+        for (int cs = 0; cs < kUStages; cs++)
+          if (!mbar_wait(a_full(cs), unit_iter & 1u, p.status)) { ok = false; break; }
       }
     }
     if (prof && leader) {
@@ -949,7 +1057,7 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
       atomicAdd(p.prof + 1, (unsigned long long)pwt);
       atomicAdd(p.prof + 2, (unsigned long long)pwb);
       atomicAdd(p.prof + 3, (unsigned long long)(clock64() - pt0));
-      atomicAdd(p.prof + 12, (unsigned long long)tile_iter);
+      atomicAdd(p.prof + 12, (unsigned long long)tile_iter);   // all column tiles (this warp issued every other one)
     }
   } else if (warp >= (uint32_t)kBuild0 && warp < (uint32_t)(kBuild0 + kBuilderWarps)) {
     // ------------------------------------------------------------ A builders: once per (system, row tile)
@@ -974,7 +1082,7 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
 #pragma unroll
       for (int h = 0; h < kUStages; h++) {
         const long long w0 = prof ? clock64() : 0;
-        if (!mbar_wait(a_empty(h), (unit_iter & 1u) ^ 1u, p.status)) { ok = false; break; }
+        if (!mbar_wait(a_empty(h), (unit_iter & 1u) ^ 1u, p.status, kUBuildBackoff)) { ok = false; break; }
         const long long w1 = prof ? clock64() : 0;
         if (!(p.dbg & 2)) {
           const uint32_t step = h * kUSPS + b;
@@ -991,8 +1099,8 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
       atomicAdd(p.prof + 11, (unsigned long long)(clock64() - pt0));
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 6..13)
-    using ET = EpiTile<kHalfN>;
+    // ------------------------------------------------------------ epilogue (warps 6 .. 6 + kUEpiWarps - 1)
+    using ET = EpiTile<kHalfN, kUEpiParts>;
     auto tile_of = [&](uint32_t su, uint32_t nt, ET &e) {
       const uint32_t sys = su / itiles, it = su - sys * itiles;
       e.set(warp, lane, p.reg, p.nreg, sys, nt, it, p.M);
@@ -1028,9 +1136,14 @@ __global__ void __launch_bounds__(kThreads, 1) update_tc_kernel(const ApplyTcArg
         if (!mbar_wait(tmem_full(ab), use & 1u, p.status)) { ok = false; break; }
         const long long w1 = prof ? clock64() : 0;
         tc_fence_after();
-        if (!(p.dbg & 4)) epilogue_tile<kHalfN>(tm, ab * kHalfN, warp, lane, cur, old_cur, prof ? pc : nullptr);
+        if (!(p.dbg & 4)) epilogue_tile<kHalfN, kUEpiParts>(tm, ab * kHalfN, warp, lane, cur, old_cur, prof ? pc : nullptr);
         tc_fence_before();
-        mbar_arrive(tmem_empty(ab));
+        if (kUWarpArrive) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty(ab));
+        } else {
+          mbar_arrive(tmem_empty(ab));
+        }
         if (prof) { pw += w1 - w0; pe += clock64() - w1; }
       }
     }

@@ -998,8 +998,8 @@ int tc_launch(const ob2::tc::ApplyTcArgs &a, int nh) {
       if (max_clusters > 0 && (uint32_t)(2 * max_clusters) < grid) grid = (uint32_t)(2 * max_clusters);
       if (2 * npairs < grid) grid = (uint32_t)(2 * npairs);
       update_tc2_kernel<<<grid, kThreads, kU2SmemBytes, cx().stream>>>(a);
-    } else if (a.prof) update_tc_kernel<true><<<grid, kThreads, kUSmemBytes, cx().stream>>>(a);
-    else update_tc_kernel<false><<<grid, kThreads, kUSmemBytes, cx().stream>>>(a);
+    } else if (a.prof) update_tc_kernel<true><<<grid, kUThreads, kUSmemBytes, cx().stream>>>(a);
+    else update_tc_kernel<false><<<grid, kUThreads, kUSmemBytes, cx().stream>>>(a);
   }
   return after_launch("apply (tcgen05)");
 }

@@ -11,6 +11,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 from oblas_b200 import capi, device
+if os.environ.get("OB2_LIB"):   # a build made for timing experiments (make EXTRA=-DOB2_TC_TIMING_EXPERIMENTS -> other file name)
+    capi.LIB_PATH = os.environ["OB2_LIB"]
 
 nsys, K, L = (int(x) for x in (sys.argv[1:4] if len(sys.argv) >= 4 else (592, 1024, 1280)))
 device.bind(0)
