@@ -223,6 +223,26 @@ int oblas_b200_gf256_apply(const void *C, size_t c_stride, uint32_t M, uint32_t 
                            const void *D, size_t d_stride, void *Y, size_t y_stride,
                            size_t nbytes, int accumulate);
 
+/* ---- several GPUs from ONE process ------------------------------------ */
+/* One context per device (oblas_b200_set_device); the two calls below run one host thread per
+ * device.  devices: ndev device ordinals, NULL = 0 .. ndev-1; ndev <= 0 = all visible devices. */
+int oblas_b200_device_count(void);
+/* oblas_b200_solve_batch_host_ex with the batch cut into one contiguous block of systems per
+ * device (independent systems: no collective). */
+int oblas_b200_solve_batch_host_multi(int field, void *A_host, size_t a_row_stride, size_t a_sys_stride,
+                                      uint32_t rows, uint32_t cols, size_t a_row_bytes,
+                                      void *B_host, size_t b_row_stride, size_t b_sys_stride,
+                                      size_t b_row_bytes, int32_t *rank_out, uint32_t *pivcols_out,
+                                      size_t nsys, const int *devices, int ndev, unsigned flags);
+/* Y = C * D over GF(256) with HOST matrices (octmat.c:32-46 semantics, Y overwritten), the symbol-byte
+ * columns of D and Y sharded over the devices in 256-byte aligned slices; C goes to the first device
+ * once and from there to the others over NVLink (peer copies along a binary tree).  seconds_out (3
+ * entries, may be NULL): coefficient upload + broadcast, slowest device's copy-in + apply + copy-out,
+ * whole call. */
+int oblas_b200_gf256_apply_sharded(const void *C_host, size_t c_stride, uint32_t M, uint32_t Kc,
+                                   const void *D_host, size_t d_stride, void *Y_host, size_t y_stride,
+                                   size_t nbytes, const int *devices, int ndev, double *seconds_out);
+
 /* ---- row-degree kernels ("next" row f-1) ---------------------------------- */
 /* out[k] = number of non-zero elements of row rows_idx[k] in columns [s, e) with
  * CORRECT counting (the reference's gfmat_nnz/binmat_nnz are only right for s==0,

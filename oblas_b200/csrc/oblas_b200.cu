@@ -10,8 +10,12 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <string>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "apply.cuh"
@@ -1312,6 +1316,169 @@ int oblas_b200_gf256_apply(const void *C, size_t c_stride, uint32_t M, uint32_t 
   int rc = launch_apply(p, cx().apply_geo == 3 ? -1 : cx().apply_geo, 512, cx().stream);
   if (rc) return fail("apply: launch configuration failed (%d)", rc);
   return after_launch("apply");
+}
+
+// ---- several GPUs from one process ---------------------------------
+// One host thread and one context per device; no data-path collective for batches of independent
+// systems, one coefficient broadcast over NVLink (peer copies, a binary tree) for the column-sharded
+// apply.  torch.distributed / NCCL drive the one-process-per-GPU form of the same split (bench.py).
+int oblas_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n < kMaxDev ? n : kMaxDev;
+}
+
+}  // extern "C"
+namespace {
+// runs fn(k) for k < ndev on its own host thread bound to device devs[k]; first error wins
+template <typename F>
+int on_devices(const int *devs, int ndev, F fn) {
+  std::vector<std::thread> th;
+  std::vector<int> rc((size_t)ndev, 0);
+  std::vector<std::string> err((size_t)ndev);
+  for (int k = 0; k < ndev; k++)
+    th.emplace_back([&, k]() {
+      rc[(size_t)k] = oblas_b200_set_device(devs[k]);
+      if (rc[(size_t)k] == 0) rc[(size_t)k] = fn(k);
+      if (rc[(size_t)k]) err[(size_t)k] = tl_err;
+    });
+  for (auto &t : th) t.join();
+  for (int k = 0; k < ndev; k++)
+    if (rc[(size_t)k]) return fail("device %d: %s", devs[k], err[(size_t)k].c_str());
+  return 0;
+}
+int pick_devices(const int *devices, int ndev, std::vector<int> &out) {
+  const int have = oblas_b200_device_count();
+  if (have <= 0) return fail("no CUDA device");
+  if (ndev <= 0) ndev = have;
+  out.clear();
+  for (int k = 0; k < ndev; k++) {
+    const int d = devices ? devices[k] : k;
+    if (d < 0 || d >= have) return fail("no CUDA device %d (%d visible)", d, have);
+    for (int q : out)
+      if (q == d) return fail("device %d listed twice", d);
+    out.push_back(d);
+  }
+  return 0;
+}
+}  // namespace
+extern "C" {
+
+// oblas_b200_solve_batch_host over several GPUs: device k gets the contiguous block of systems
+// [k * nsys / ndev, (k + 1) * nsys / ndev) -- independent systems, nothing is exchanged.
+int oblas_b200_solve_batch_host_multi(int field, void *A_host, size_t a_row_stride, size_t a_sys_stride,
+                                      uint32_t rows, uint32_t cols, size_t a_row_bytes, void *B_host,
+                                      size_t b_row_stride, size_t b_sys_stride, size_t b_row_bytes,
+                                      int32_t *rank_out, uint32_t *pivcols_out, size_t nsys,
+                                      const int *devices, int ndev, unsigned flags) {
+  std::vector<int> devs;
+  if (pick_devices(devices, ndev, devs)) return -1;
+  if (!A_host || !rank_out) return fail("solve_host_multi: A and rank_out are required");
+  const int nd = (int)devs.size();
+  return on_devices(devs.data(), nd, [&](int k) -> int {
+    const size_t lo = nsys * (size_t)k / (size_t)nd, hi = nsys * (size_t)(k + 1) / (size_t)nd;
+    if (hi == lo) return 0;
+    return oblas_b200_solve_batch_host_ex(field, (uint8_t *)A_host + lo * a_sys_stride, a_row_stride, a_sys_stride, rows, cols,
+                                          a_row_bytes, B_host ? (uint8_t *)B_host + lo * b_sys_stride : nullptr, b_row_stride,
+                                          b_sys_stride, b_row_bytes, rank_out + lo, pivcols_out ? pivcols_out + lo * rows : nullptr,
+                                          hi - lo, 0, flags);
+  });
+}
+
+// Y = C * D with HOST matrices over several GPUs (BASELINE configs[4]): the symbol-byte columns of D and Y
+// are cut into one slice per device (boundaries multiples of 256 bytes); the coefficient matrix goes to the
+// first device over PCIe once and from there to the others over NVLink (peer copies along a binary tree:
+// ceil(log2 ndev) rounds); every device then runs the tcgen05 apply on its slice.  seconds_out (may be
+// NULL, 3 entries): coefficient upload + broadcast, slowest device's H2D + apply + D2H, whole call.
+int oblas_b200_gf256_apply_sharded(const void *C_host, size_t c_stride, uint32_t M, uint32_t Kc, const void *D_host,
+                                   size_t d_stride, void *Y_host, size_t y_stride, size_t nbytes, const int *devices,
+                                   int ndev, double *seconds_out) {
+  std::vector<int> devs;
+  if (pick_devices(devices, ndev, devs)) return -1;
+  if (!C_host || !D_host || !Y_host) return fail("apply_sharded: null pointer");
+  if (M == 0 || Kc == 0 || nbytes == 0) return 0;
+  if ((nbytes & 15) || c_stride < Kc) return fail("apply_sharded: nbytes must be a multiple of 16 and c_stride >= Kc");
+  const int nd = (int)devs.size();
+  const size_t cpitch = ((size_t)Kc + 15) & ~(size_t)15;
+  std::vector<void *> dC((size_t)nd, nullptr), dD((size_t)nd, nullptr), dY((size_t)nd, nullptr);
+  std::vector<double> t_dev((size_t)nd, 0.0);
+  auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
+  // slices: 256-byte aligned boundaries
+  const size_t tiles = (nbytes + 255) / 256;
+  auto slice = [&](int k, size_t &lo, size_t &hi) {
+    lo = std::min(nbytes, (tiles * (size_t)k / (size_t)nd) * 256);
+    hi = std::min(nbytes, (tiles * (size_t)(k + 1) / (size_t)nd) * 256);
+  };
+  int rc = on_devices(devs.data(), nd, [&](int k) -> int {
+    size_t lo, hi;
+    slice(k, lo, hi);
+    CK(cudaMalloc(&dC[(size_t)k], (size_t)M * cpitch));
+    if (hi > lo) {
+      CK(cudaMalloc(&dD[(size_t)k], (size_t)Kc * (hi - lo)));
+      CK(cudaMalloc(&dY[(size_t)k], (size_t)M * (hi - lo)));
+    }
+    return 0;
+  });
+  double t_bcast = 0;
+  if (rc == 0) {
+    // coefficients: host -> first device, then a binary tree of peer copies
+    rc = on_devices(devs.data(), 1, [&](int) -> int {
+      CK(cudaMemcpy2DAsync(dC[0], cpitch, C_host, c_stride, Kc, M, cudaMemcpyHostToDevice, cx().stream));
+      if (cpitch > Kc) CK(cudaMemset2DAsync((uint8_t *)dC[0] + Kc, cpitch, 0, cpitch - Kc, M, cx().stream));
+      CK(cudaStreamSynchronize(cx().stream));
+      return 0;
+    });
+    for (int have = 1; have < nd && rc == 0; have *= 2) {
+      std::vector<int> src_dev;
+      const int cnt = std::min(have, nd - have);
+      for (int q = 0; q < cnt; q++) src_dev.push_back(devs[(size_t)q]);
+      rc = on_devices(src_dev.data(), cnt, [&](int q) -> int {
+        const int dst = have + q;
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, devs[(size_t)q], devs[(size_t)dst]));
+        if (can) {
+          cudaError_t e = cudaDeviceEnablePeerAccess(devs[(size_t)dst], 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+          cudaGetLastError();
+        }
+        CK(cudaMemcpyPeerAsync(dC[(size_t)dst], devs[(size_t)dst], dC[(size_t)q], devs[(size_t)q], (size_t)M * cpitch, cx().stream));
+        CK(cudaStreamSynchronize(cx().stream));
+        return 0;
+      });
+    }
+    t_bcast = now() - t0;
+  }
+  if (rc == 0)
+    rc = on_devices(devs.data(), nd, [&](int k) -> int {
+      size_t lo, hi;
+      slice(k, lo, hi);
+      if (hi == lo) return 0;
+      const double s0 = now();
+      const size_t w = hi - lo;
+      CK(cudaMemcpy2DAsync(dD[(size_t)k], w, (const uint8_t *)D_host + lo, d_stride, w, Kc, cudaMemcpyHostToDevice, cx().stream));
+      if (oblas_b200_gf256_apply(dC[(size_t)k], cpitch, M, Kc, dD[(size_t)k], w, dY[(size_t)k], w, w, 0)) return -1;
+      CK(cudaMemcpy2DAsync((uint8_t *)Y_host + lo, y_stride, dY[(size_t)k], w, w, M, cudaMemcpyDeviceToHost, cx().stream));
+      if (oblas_b200_sync()) return -1;
+      t_dev[(size_t)k] = now() - s0;
+      return 0;
+    });
+  on_devices(devs.data(), nd, [&](int k) -> int {
+    cudaFree(dC[(size_t)k]);
+    cudaFree(dD[(size_t)k]);
+    cudaFree(dY[(size_t)k]);
+    return 0;
+  });
+  if (seconds_out) {
+    seconds_out[0] = t_bcast;
+    seconds_out[1] = 0;
+    for (double t : t_dev) seconds_out[1] = std::max(seconds_out[1], t);
+    seconds_out[2] = now() - t0;
+  }
+  return rc;
 }
 
 // ---- row degree -------------------------------------------------------------------

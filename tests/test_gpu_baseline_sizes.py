@@ -328,3 +328,48 @@ def test_gf2_scalars_above_one_are_no_ops_in_batches_too(cuda_lib):
     for k in (1, 4, 7):
         want[k] ^= b[k]
     assert np.array_equal(host(da), want)
+
+
+def test_multi_device_entry_points(cuda_lib):
+    """one process, one host thread + context per visible GPU (oblas_b200_set_device underneath):
+    oblas_b200_solve_batch_host_multi shards a batch by systems, oblas_b200_gf256_apply_sharded shards
+    D / Y by 256-byte aligned symbol-column slices and sends C to the other devices by peer copies.
+    On a one-GPU box both run with a single shard (same code path, no peer copy)."""
+    ndev = cuda_lib.oblas_b200_device_count()
+    assert ndev >= 1
+    K, L, nsys = 96, 272, 11
+    A = np.stack([random_matrix(GF256, K, K, 9800 + s) for s in range(nsys)])
+    A[4, 50] = A[4, 7]
+    B = np.stack([splitmix_bytes(9900 + s, K * L).reshape(K, L) for s in range(nsys)]).copy()
+    A0, B0 = A.copy(), B.copy()
+    want = [oracle_solve(GF256, A0[s], B0[s], K) for s in range(nsys)]
+    rank = np.zeros(nsys, dtype=np.int32)
+    piv = np.zeros((nsys, K), dtype=np.uint32)
+    capi.check(cuda_lib.oblas_b200_solve_batch_host_multi(
+        GF256, A.ctypes.data, A.strides[1], A.strides[0], K, K, K, B.ctypes.data, B.strides[1], B.strides[0], L,
+        rank.ctypes.data, piv.ctypes.data, nsys, None, 0, 0))
+    assert rank.tolist() == [w[0] for w in want]
+    assert np.array_equal(A, A0) and np.array_equal(B, B0)
+    # sharded apply against the single-device kernel (itself pinned to the oracle in test_gpu_apply.py)
+    M, Kc, N = 300, 200, 256 * 5 + 48
+    Cm = np.zeros((M, 208), dtype=np.uint8)
+    Cm[:, :Kc] = splitmix_bytes(9950, M * Kc).reshape(M, Kc)
+    D = splitmix_bytes(9951, Kc * N).reshape(Kc, N).copy()
+    Y = np.full((M, N), 0xEE, dtype=np.uint8)
+    secs = (C.c_double * 3)()
+    capi.check(cuda_lib.oblas_b200_gf256_apply_sharded(Cm.ctypes.data, Cm.strides[0], M, Kc, D.ctypes.data, D.strides[0],
+                                                       Y.ctypes.data, Y.strides[0], N, None, 0, secs))
+    device.bind(0)
+    ref = device.apply(dev(Cm), dev(D))
+    device.sync()
+    assert np.array_equal(Y, host(ref))
+    Y0 = np.zeros((M, N), dtype=np.uint8)
+    oracle().orc_gf256_apply(ptr(Cm), Cm.strides[0], M, Kc, ptr(D), N, ptr(Y0), N, N)
+    assert np.array_equal(Y, Y0)
+    if ndev >= 2:   # an explicit device list in another order
+        devs = (C.c_int * 2)(1, 0)
+        Y2 = np.zeros_like(Y)
+        capi.check(cuda_lib.oblas_b200_gf256_apply_sharded(Cm.ctypes.data, Cm.strides[0], M, Kc, D.ctypes.data, D.strides[0],
+                                                           Y2.ctypes.data, Y2.strides[0], N, devs, 2, None))
+        assert np.array_equal(Y2, Y0)
+    assert cuda_lib.oblas_b200_set_device(0) == 0
