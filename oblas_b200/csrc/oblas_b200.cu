@@ -609,7 +609,10 @@ int oblas_b200_rowops(int field, int variant, int op, int mul_mode, void *a, siz
 int solve_tc_run(SolveArgs &p, size_t nsys);   // tensor-core path (GF(256)), defined with apply_tc_run
 static bool solve_tc_eligible(int field, const SolveArgs &p, size_t nsys) {
   if (field != OB2_GF256 || p.a_ptrs || p.b_ptrs) return false;
-  if (panel_smem_bytes(p.rows) > cx().smem_optin || p.rows > 65535u) return false;
+  // rows: u16 row map; the final row permutation stages at least 16 bytes of every row in shared memory.
+  // Systems too tall for the shared-memory row state of the outer-panel kernel (> ~2700 rows) keep it in a
+  // global workspace (panel_kernel<.., GROWS>): that is what makes e.g. a K = 10000 GF(256) solve possible.
+  if (p.rows > 65535u || 2 * (((size_t)p.rows * 2 + 15) / 16 * 16) + 80 + (size_t)p.rows * 16 > cx().smem_optin) return false;
   if (cx().solve_geo == 3) return true;
   if (cx().solve_geo >= 0) return false;
   // auto: the rank-128 tensor-core update pays once the systems are big enough to fill its tiles
@@ -1177,11 +1180,15 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
   const size_t map_per_sys = ((size_t)rows * 2 + 15) / 16 * 16;
   const size_t small_per_sys = 2 * kOuterBytes + 16;   // piv_all (u16 x 128) + tcount + npiv + pad
   const size_t per_sys = dx_per_sys + e_per_sys + map_per_sys + small_per_sys;
+  // tall systems: the per-row state of the outer-panel kernel lives in global memory, one block per CTA
+  const bool grows = panel_smem_bytes(rows) > cx().smem_optin;
+  const size_t row_ws_cta = grows ? panel_row_ws_bytes(rows) : 0;
+  const size_t row_ws_all = row_ws_cta * (size_t)cx().sm_count;
   size_t chunk = cx().tc_ws_budget / per_sys;
   if (chunk < 1) chunk = 1;
   if (chunk > nsys) chunk = nsys;
   for (;;) {
-    int rc = tc_ws_reserve(chunk * per_sys + 256);
+    int rc = tc_ws_reserve(chunk * per_sys + 256 + row_ws_all + 256);
     if (rc < 0) return -1;
     if (rc == 0) break;
     if (chunk == 1) return fail("solve: cannot allocate %zu bytes of workspace", per_sys);
@@ -1193,7 +1200,8 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
   uint16_t *maps = (uint16_t *)ws;                         ws += chunk * map_per_sys;
   uint16_t *piv_all = (uint16_t *)ws;                      ws += chunk * 2 * kOuterBytes;
   uint32_t *tcount = (uint32_t *)ws;                       ws += chunk * 4;
-  uint32_t *npiv = (uint32_t *)ws;
+  uint32_t *npiv = (uint32_t *)ws;                         ws += chunk * 4;
+  uint8_t *row_ws = grows ? (uint8_t *)(((uintptr_t)ws + 255) & ~(uintptr_t)255) : nullptr;
   // permutation kernel: row map + staging area in shared memory
   const size_t pmap = ((size_t)rows * 2 + 15) / 16 * 16;
   // stage = count + list of moved rows (u16 x rows) + at least 16 bytes per row
@@ -1217,6 +1225,7 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
       pa.nsys = cnt; pa.outer = outer; pa.inv = p.inv; pa.no_fast_panel = p.no_fast_panel;
       pa.no_look_ahead = p.no_look_ahead;
       pa.phase = cx().d_phase;
+      pa.row_ws = row_ws; pa.row_ws_cta = row_ws_cta;
       // the row map lives in global memory as [sys][rows] u16 with a 16-byte aligned pitch
       {
         TcTimer tt(0);

@@ -1141,11 +1141,21 @@ struct PanelArgs {
   int no_fast_panel;
   int no_look_ahead;           // diagnostics/tests: candidate elimination never overlapped with the tile pass
   unsigned long long *phase;   // optional diagnostics: cycles per phase summed over CTAs (5 counters)
+  // systems too tall for the shared-memory row state (panel_kernel<.., GROWS = true>): per-CTA block of
+  // panel_row_ws_bytes(rows) bytes in global memory (L2 resident) for the window chunk, the coefficient
+  // vectors, the row map and the candidate flags of the rows
+  uint8_t *row_ws;
+  size_t row_ws_cta;
 };
 
 constexpr int kOuterBytes = 128;   // outer panel width (GF(256): bytes == columns)
 
-template <int KB, int WT>
+// per-row state of panel_kernel when it lives in global memory (GROWS): pan + V + row map + flags
+inline size_t panel_row_ws_bytes(uint32_t rows) {
+  return ((size_t)rows * 4 * 4 * 2 + ((size_t)rows * 2 + 15) / 16 * 16 + ((size_t)rows + 15) / 16 * 16 + 255) & ~(size_t)255;
+}
+
+template <int KB, int WT, bool GROWS = false>
 __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
   constexpr int EXP = 8, NBW = 4;
   using SM = SolveSmem<EXP, NBW, KB, WT>;
@@ -1160,17 +1170,21 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
   OB2_DYN_SMEM(smem_raw);
   unsigned char *sp = smem_raw;
   uint4 *tab = reinterpret_cast<uint4 *>(sp);              sp += G::TAB_BYTES;
-  uint32_t *pan = reinterpret_cast<uint32_t *>(sp);        sp += (size_t)rows * NBW * 4;
-  uint32_t *V = reinterpret_cast<uint32_t *>(sp);          sp += (size_t)rows * NBW * 4;
+  // per-row state: shared memory, or (GROWS: systems of more than ~2700 rows) this CTA's block of the
+  // global workspace -- same code, generic pointers; __syncthreads orders the accesses either way
+  unsigned char *rp = GROWS ? p.row_ws + (size_t)blockIdx.x * p.row_ws_cta : sp;
+  uint32_t *pan = reinterpret_cast<uint32_t *>(rp);        rp += (size_t)rows * NBW * 4;
+  uint32_t *V = reinterpret_cast<uint32_t *>(rp);          rp += (size_t)rows * NBW * 4;
+  uint16_t *pos2phys = reinterpret_cast<uint16_t *>(rp);   rp += ((size_t)rows * 2 + 15) / 16 * 16;
+  uint8_t *is_cand = reinterpret_cast<uint8_t *>(rp);      rp += ((size_t)rows + 15) / 16 * 16;   // [rows] look-ahead flags
+  if (!GROWS) sp = rp;
   sp = smem_raw + (((size_t)(sp - smem_raw) + 15) & ~(size_t)15);
-  uint16_t *pos2phys = reinterpret_cast<uint16_t *>(sp);   sp += ((size_t)rows * 2 + 15) / 16 * 16;
   uint16_t *piv_phys = reinterpret_cast<uint16_t *>(sp);   sp += ((size_t)NPIV * 2 + 15) / 16 * 16;
   uint32_t *prow = reinterpret_cast<uint32_t *>(sp);       sp += (size_t)EXP * NBW * 4;
   uint32_t *vrow = reinterpret_cast<uint32_t *>(sp);       sp += (size_t)EXP * NBW * 4;
   uint32_t *scal = reinterpret_cast<uint32_t *>(sp);
   uint8_t *inv_s = reinterpret_cast<uint8_t *>(scal + 32);
   uint32_t *Mb = reinterpret_cast<uint32_t *>(inv_s + 256);          // [128][NBW] pivots' vectors (look-ahead: not in the table area)
-  uint8_t *is_cand = reinterpret_cast<uint8_t *>(Mb + 32 * NBW * NBW);  // [rows] look-ahead flags
   for (uint32_t k = threadIdx.x; k < 256u; k += blockDim.x) inv_s[k] = p.inv[k];
   for (uint32_t k = threadIdx.x; k < rows; k += blockDim.x) is_cand[k] = 0;
   __syncthreads();
@@ -1404,14 +1418,28 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
 // look-ahead state of panel_kernel behind the SolveSmem layout: Mb (2 KB) + one flag byte per row
 inline size_t panel_extra_bytes(uint32_t) { return 0; }   // (Mb and the flags are part of SolveSmem now)
 
+// shared memory of panel_kernel: everything (rows <= ~2700), or without the per-row state (GROWS)
+inline size_t panel_smem_bytes(uint32_t rows) { return SolveSmem<8, 4, 6, 128>::bytes(rows) + panel_extra_bytes(rows); }
+inline size_t panel_smem_bytes_grows() { return SolveSmem<8, 4, 6, 128>::bytes(0) + 64; }
+
 template <int KB, int WT>
 inline int launch_panel_t(const PanelArgs &p, uint32_t grid, size_t smem_limit, cudaStream_t s,
                           uint32_t threads = 512) {
   using SM = SolveSmem<8, 4, KB, WT>;
-  size_t smem = SM::bytes(p.rows) + panel_extra_bytes(p.rows);
-  if (smem > smem_limit || p.rows > 65535u || p.rows == 0) return -1;
+  if (p.rows > 65535u || p.rows == 0) return -1;
   if (threads % SM::G::CW) return -3;
-  auto k = panel_kernel<KB, WT>;
+  const bool grows = p.row_ws != nullptr;
+  size_t smem = grows ? SM::bytes(0) + 64 : SM::bytes(p.rows) + panel_extra_bytes(p.rows);
+  if (smem > smem_limit) return -1;
+  if (grows) {
+    auto k = panel_kernel<KB, WT, true>;
+#ifndef OB2_EMU
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
+#endif
+    OB2_LAUNCH(k, grid, threads, smem, s, p);
+    return 0;
+  }
+  auto k = panel_kernel<KB, WT, false>;
 #ifndef OB2_EMU
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
   // two CTAs per SM where they fit (small table geometry): ask for the largest shared-memory carve-out
@@ -1420,7 +1448,6 @@ inline int launch_panel_t(const PanelArgs &p, uint32_t grid, size_t smem_limit, 
   OB2_LAUNCH(k, grid, threads, smem, s, p);
   return 0;
 }
-inline size_t panel_smem_bytes(uint32_t rows) { return SolveSmem<8, 4, 6, 128>::bytes(rows) + panel_extra_bytes(rows); }
 
 // rows of A and B into position order + rank, after the last outer panel
 struct PermuteArgs {

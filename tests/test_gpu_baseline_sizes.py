@@ -373,3 +373,40 @@ def test_multi_device_entry_points(cuda_lib):
                                                            Y2.ctypes.data, Y2.strides[0], N, devs, 2, None))
         assert np.array_equal(Y2, Y0)
     assert cuda_lib.oblas_b200_set_device(0) == 0
+
+
+def test_tall_systems_on_the_tensor_core_path_vs_reference(cuda_lib):
+    """systems with more rows than the shared-memory row state of the outer-panel kernel holds (~2700):
+    panel_kernel<.., GROWS> keeps the window chunk, the coefficient vectors, the row map and the candidate
+    flags in a global workspace.  K = 3008, two systems (one rank deficient), every byte against the
+    reference's loop (octmat.c:24-63)."""
+    K, L = 3008, 320
+    A = np.stack([random_matrix(GF256, K, K, 9960 + s) for s in range(2)])
+    A[1, 2000] = A[1, 3]
+    A[1, :, 1500] = 0
+    B = np.stack([splitmix_bytes(9970 + s, K * L).reshape(K, L) for s in range(2)]).copy()
+    path = C.c_int(0)
+    capi.check(cuda_lib.oblas_b200_solve_plan(GF256, K, K, K, L, 2, C.byref(path), None, None))
+    assert path.value == 1
+    ranks = check_batch(GF256, A, B, K)
+    assert ranks[0] == K and ranks[1] == K - 1   # a duplicated row and a zero column: one dependency each, rank K - 1
+
+
+def test_raptorq_scale_solve_k10000_roundtrip():
+    """one K = 10000 GF(256) system with 1280-byte symbols (the apply of BASELINE configs[4] run
+    backwards): rank K, A -> I, and A_orig * X == B_orig on sampled rows recomputed on the CPU."""
+    K, L = 10000, 1280
+    a_bytes = 10000
+    dA = torch.empty((1, K, a_bytes), dtype=torch.uint8, device="cuda")
+    dB = torch.empty((1, K, L), dtype=torch.uint8, device="cuda")
+    device.fill_random(dA, 9980)
+    device.fill_random(dB, 9981)
+    A0, B0 = dA.clone(), dB.clone()
+    rank, _ = device.solve_batch(GF256, dA, K, dB)
+    device.sync()
+    assert int(rank[0]) == K      # P(singular) = 0.4 %; this seed is regular
+    assert torch.equal(dA[0], torch.eye(K, dtype=torch.uint8, device="cuda"))
+    X, Ao, Bo = host(dB[0]), host(A0[0]), host(B0[0])
+    rng = np.random.default_rng(1)
+    for r in rng.choice(K, 5, replace=False):
+        assert np.array_equal(gf256_vecmat(Ao[r], X), Bo[r]), r
