@@ -89,6 +89,19 @@ int oblas_b200_sync(void);
  * which case they only enqueue and the caller must oblas_b200_sync() before
  * touching `bits` from the host */
 void oblas_b200_set_async(int async);
+/* async == 2: OP QUEUE.  The drop-in row operations on matrices made by *_new (oaxpy, oaddrow, oscal,
+ * oswaprow, gfmat_add/axpy/scal/swaprow/zero, binmat_add/swaprow/zero) are collected instead of launched:
+ * consecutive calls of one kind on one matrix pair become ONE kernel launch.  A batch ends -- and is
+ * launched, in order, on the stream -- when the next call is of another kind or on another matrix, when it
+ * touches a row a queued operation writes (or writes a row a queued operation reads: the operations of a
+ * launch are unordered), at 65536 operations, and before every other entry point of this library does its
+ * work.  oblas_b200_sync, the accessors (gfmat_get/set/print/fill/nnz/swapcol, binmat_*) and *_free launch
+ * the queue AND wait.  As with async == 1 the caller must oblas_b200_sync() before dereferencing `bits`
+ * directly (om_A, om_P): a macro cannot be intercepted.  An elimination loop written against the
+ * reference (one oaxpy per row and column) then costs one or two launches per column instead of one per
+ * row; INTEGRATION.md has the measured difference. */
+/* launches made for / operations that went through the op queue so far (either may be NULL) */
+void oblas_b200_queue_stats(uint64_t *batches, uint64_t *ops);
 /* Four-Russians table geometry of the elimination / apply kernels (tuning knob for
  * measurements): 0 = 4-bit groups, 256-byte tiles; 1 = 6-bit groups, 128-byte tiles;
  * 2 = 7-bit groups, 64-byte tiles; -1 = library default.  Results are identical.

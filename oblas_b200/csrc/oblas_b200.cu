@@ -16,6 +16,7 @@
 #include <string>
 #include <mutex>
 #include <thread>
+#include <unordered_set>
 #include <vector>
 
 #include "apply.cuh"
@@ -40,7 +41,27 @@ struct Ctx {
   size_t smem_optin = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
-  bool async = false;
+  int async = 0;   // 0: drop-in calls synchronise; 1: enqueue only; 2: op queue (see OpQueue)
+  // Op queue behind the drop-in row operations (oblas_b200_set_async(2)): consecutive calls of one kind
+  // on one matrix pair are collected and become ONE rowop_kernel launch when the batch has to end -- a
+  // different kind / matrix, a row that a queued operation writes or reads (the operations of a launch
+  // are unordered), the capacity, or anything that lets the host observe results (oblas_b200_sync, the
+  // accessors, *_free, every other entry point).
+  struct OpQueue {
+    std::mutex mu;
+    bool flushing = false;
+    int field = 0, op = 0;
+    uint8_t *a = nullptr;
+    const uint8_t *b = nullptr;
+    size_t a_stride = 0, b_stride = 0, row_bytes = 0;
+    std::vector<uint32_t> dst, src;
+    std::vector<uint8_t> u;
+    // rows of matrix `a` written / rows of matrix `b` read by the queued operations: stamp == batch id
+    std::vector<uint32_t> written, read;
+    uint32_t stamp = 1;
+    const void *ok_a = nullptr, *ok_b = nullptr;   // matrices already checked to be device-visible
+    uint64_t batches = 0, ops = 0;
+  } q;
   int solve_geo = -1, apply_geo = -1;  // table geometry overrides (-1 = default)
   // tensor-core apply (apply_tc.cuh): expanded-D workspace and the device-written status word
   // one workspace per stream that has used the tensor-core paths (the host-streaming lanes run
@@ -121,12 +142,15 @@ int fail(const char *fmt, ...) {
       return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
-int ensure_init() {
+int queue_flush();
+int ensure_init(bool flush_queue = true) {
   Ctx &c = cx();
   if (!c.ready) return oblas_b200_init(tl_dev);
   // entry points may be called from any host thread: make the context's device current
   int cur = -1;
   if (cudaGetDevice(&cur) != cudaSuccess || cur != c.device) CK(cudaSetDevice(c.device));
+  // queue mode: whatever the drop-in calls have collected goes first (stream order does the rest)
+  if (flush_queue && c.async == 2 && !c.q.flushing && !c.q.dst.empty()) return queue_flush();
   return 0;
 }
 
@@ -179,6 +203,73 @@ int after_launch(const char *what) {
 int finish_dropin() {
   if (cx().async) return 0;
   CK(cudaStreamSynchronize(cx().stream));
+  return 0;
+}
+
+constexpr size_t kQueueCapacity = 1u << 16;
+// launches what is queued (asynchronously, on the context's stream)
+int queue_flush() {
+  Ctx &c = cx();
+  Ctx::OpQueue &q = c.q;
+  std::lock_guard<std::mutex> lk(q.mu);
+  if (q.flushing || q.dst.empty()) return 0;
+  q.flushing = true;
+  const bool needs_src = q.op == OP_AXPY || q.op == OP_ADD || q.op == OP_SWAP;
+  const int rc = oblas_b200_rowops(q.field, 0, q.op, OBLAS_B200_MUL_AUTO, q.a, q.a_stride, needs_src ? q.b : q.a,
+                                   needs_src ? q.b_stride : q.a_stride, q.row_bytes, q.dst.data(),
+                                   q.src.data(), q.u.data(), q.dst.size());
+  q.batches++;
+  q.ops += q.dst.size();
+  q.dst.clear(); q.src.clear(); q.u.clear();
+  if (++q.stamp == 0) {   // stamp wrapped: forget everything
+    std::fill(q.written.begin(), q.written.end(), 0u);
+    std::fill(q.read.begin(), q.read.end(), 0u);
+    q.stamp = 1;
+  }
+  q.flushing = false;
+  return rc;
+}
+// the host is about to look at results (or hands memory back): launch the queue and wait
+int queue_observe() {
+  Ctx &c = cx();
+  if (!c.ready || c.async != 2) return 0;
+  if (queue_flush()) return -1;
+  CK(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+int queue_push(int field, int op, uint8_t *a, size_t a_stride, const uint8_t *b, size_t b_stride, size_t row_bytes,
+               uint32_t i, uint32_t j, uint8_t u) {
+  Ctx::OpQueue &q = cx().q;
+  const bool has_src = op == OP_AXPY || op == OP_ADD || op == OP_SWAP;
+  if (!has_src) { b = a; b_stride = a_stride; j = i; }
+  const bool same = (a == b);   // one matrix: a row may be written by one operation and read by another
+  bool flush;
+  {
+    std::lock_guard<std::mutex> lk(q.mu);
+    auto hit = [&](const std::vector<uint32_t> &v, uint32_t r) { return r < v.size() && v[r] == q.stamp; };
+    flush = !q.dst.empty() &&
+            (q.field != field || q.op != op || q.a != a || q.b != b || q.a_stride != a_stride || q.b_stride != b_stride ||
+             q.row_bytes != row_bytes || q.dst.size() >= kQueueCapacity ||
+             hit(q.written, i) ||                                   // written twice
+             (same && (hit(q.read, i) ||                            // a queued operation still reads row i
+                       (j != i && hit(q.written, j)) ||             // row j is the result of a queued operation
+                       (op == OP_SWAP && hit(q.read, j)))));
+  }
+  if (flush && queue_flush()) return -1;
+  std::lock_guard<std::mutex> lk(q.mu);
+  if (q.dst.empty()) {
+    q.field = field; q.op = op; q.a = a; q.b = b; q.a_stride = a_stride; q.b_stride = b_stride; q.row_bytes = row_bytes;
+  }
+  auto mark = [&](std::vector<uint32_t> &v, uint32_t r) {
+    if (r >= v.size()) v.resize((size_t)r + 1024, 0u);
+    v[r] = q.stamp;
+  };
+  q.dst.push_back(i);
+  q.src.push_back(j);
+  q.u.push_back(u);
+  mark(q.written, i);
+  if (op == OP_SWAP) mark(q.written, j);
+  else if (same && j != i) mark(q.read, j);
   return 0;
 }
 
@@ -378,7 +469,15 @@ int oblas_b200_sync(void) {
   CK(cudaStreamSynchronize(cx().stream));
   return tc_check_status();
 }
-void oblas_b200_set_async(int async) { cx().async = async != 0; }
+void oblas_b200_set_async(int async) {
+  if (ensure_init()) return;   // (flushes a queue that is being switched off)
+  cx().async = async < 0 ? 0 : (async > 2 ? 2 : async);
+}
+// diagnostics: launches made for / operations that went through the op queue (set_async(2)) so far
+void oblas_b200_queue_stats(uint64_t *batches, uint64_t *ops) {
+  if (batches) *batches = cx().q.batches;
+  if (ops) *ops = cx().q.ops;
+}
 void oblas_b200_set_panel_path(int general_only) { cx().no_fast_panel = general_only & 3; }
 void oblas_b200_set_tuning(int solve_geo, int apply_geo) {
   cx().solve_geo = solve_geo;
@@ -466,6 +565,7 @@ void *oblas_b200_managed_alloc(size_t bytes, size_t align) {
 }
 void oblas_b200_free(void *p) {
   if (!p) return;
+  cx().q.ok_a = cx().q.ok_b = nullptr;   // the op queue's "known device-visible" pointers may go stale
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
     cudaGetLastError();
@@ -1733,6 +1833,18 @@ int l1_op(int op, uint8_t *a, const uint8_t *b, size_t k, const uint8_t *lo, con
 int mat_rowop(int field, int variant, int op, uint8_t *abits, size_t astride, const uint8_t *bbits,
               size_t bstride, size_t row_bytes, unsigned i, unsigned j, uint8_t u) {
   uint32_t di = i, dj = j;
+  if (cx().async == 2 && variant == 0 && op != OP_AXPY_B32 && !(row_bytes & 15) && !(astride & 15) &&
+      !(reinterpret_cast<uintptr_t>(abits) & 15)) {
+    Ctx::OpQueue &q = cx().q;
+    // cudaPointerGetAttributes costs more than everything else here: only for a matrix not seen last time
+    const bool vis = (abits == q.ok_a || classify(abits) == PK_DEVVIS) && (!bbits || bbits == q.ok_b || bbits == q.ok_a || classify(bbits) == PK_DEVVIS);
+    if (vis) {
+      q.ok_a = abits;
+      if (bbits) q.ok_b = bbits;
+      if (ensure_init(false)) return -1;
+      return queue_push(field, op, abits, astride, bbits, bstride, row_bytes, di, dj, u);
+    }
+  }
   return oblas_b200_rowops(field, variant, op, OBLAS_B200_MUL_AUTO, abits, astride, bbits, bstride,
                            row_bytes, &di, &dj, &u, 1);
 }
@@ -1867,6 +1979,7 @@ octmat *octmat_new_aligned(unsigned rows, unsigned cols, unsigned align) {
 octmat *octmat_new(unsigned rows, unsigned cols) { return octmat_new_aligned(rows, cols, 16); }
 // octmat.c:17-22
 void octmat_free(octmat *m) {
+  MUST(queue_observe(), "octmat_free");
   if (m && m->bits) oblas_b200_free(m->bits);
   if (m) free(m);
 }
@@ -1942,17 +2055,20 @@ gfmat *gfmat_copy(gfmat *src) {
   return m;
 }
 void gfmat_free(gfmat *m) {
+  MUST(queue_observe(), "gfmat_free");
   if (m && m->bits) oblas_b200_free(m->bits);
   if (m) free(m);
 }
 // host-side element access on managed memory (gfmat.c:83-98)
 uint8_t gfmat_get(gfmat *m, unsigned i, unsigned j) {
+  MUST(queue_observe(), "gfmat_get");
   if (i >= m->rows || j >= m->cols) return 0;
   unsigned e = kFieldBits[m->field], vpw = 32 / e;
   oblas_word *a = m->bits + (size_t)i * m->stride;
   return (uint8_t)bfx_32(a[j / vpw], (uint8_t)((j % vpw) * e), (uint8_t)e);
 }
 void gfmat_set(gfmat *m, unsigned i, unsigned j, uint8_t b) {
+  MUST(queue_observe(), "gfmat_set");
   if (i >= m->rows || j >= m->cols) return;
   unsigned e = kFieldBits[m->field], vpw = 32 / e;
   oblas_word *a = m->bits + (size_t)i * m->stride;
@@ -1960,6 +2076,7 @@ void gfmat_set(gfmat *m, unsigned i, unsigned j, uint8_t b) {
 }
 // gfmat.c:100-116
 void gfmat_print(gfmat *m, FILE *stream) {
+  MUST(queue_observe(), "gfmat_print");
   static const char *fn[] = {"gf2", "gf4", "gf16", "gf256"};
   fprintf(stream, "%s [%ux%u]\n", fn[m->field], m->rows, m->cols);
   fprintf(stream, "|     ");
@@ -1998,6 +2115,7 @@ void gfmat_zero(gfmat *a, unsigned i) {
 }
 // gfmat.c:163-175, truncation into uint8_t kept
 void gfmat_fill(gfmat *m, unsigned i, uint8_t *dst) {
+  MUST(queue_observe(), "gfmat_fill");
   unsigned e = kFieldBits[m->field], vpw = 32 / e;
   oblas_word *a = m->bits + (size_t)i * m->stride;
   for (unsigned idx = 0; idx < m->stride; idx++)
@@ -2025,11 +2143,13 @@ static unsigned nnz_compat(const oblas_word *a, unsigned e, unsigned s, unsigned
   return n;
 }
 unsigned gfmat_nnz(gfmat *m, unsigned i, unsigned s, unsigned e) {
+  MUST(queue_observe(), "gfmat_nnz");
   if (i >= m->rows || s > e || e > (m->cols + 1)) return 0;
   return nnz_compat(m->bits + (size_t)i * m->stride, kFieldBits[m->field], s, e);
 }
 // gfmat.c:215-231
 void gfmat_swapcol(gfmat *m, unsigned i, unsigned j) {
+  MUST(queue_observe(), "gfmat_swapcol");
   if (i == j) return;
   unsigned e = kFieldBits[m->field], vpw = 32 / e;
   for (unsigned r = 0; r < m->rows; r++) {
@@ -2071,15 +2191,18 @@ binmat *binmat_new(unsigned rows, unsigned cols) {
   return m;
 }
 void binmat_free(binmat *m) {
+  MUST(queue_observe(), "binmat_free");
   if (m && m->bits) oblas_b200_free(m->bits);
   if (m) free(m);
 }
 uint8_t binmat_get(binmat *m, unsigned i, unsigned j) {
+  MUST(queue_observe(), "binmat_get");
   if (i >= m->rows || j >= m->cols) return 0;
   return (uint8_t)((m->bits[(size_t)i * m->stride + j / 32] >> (j % 32)) & 1u);
 }
 // binmat.c:35-42: the bit is always set, `b` is ignored (line 41) -- kept
 void binmat_set(binmat *m, unsigned i, unsigned j, uint8_t b) {
+  MUST(queue_observe(), "binmat_set");
   (void)b;
   if (i >= m->rows || j >= m->cols) return;
   m->bits[(size_t)i * m->stride + j / 32] |= 1u << (j % 32);
@@ -2099,6 +2222,7 @@ void binmat_zero(binmat *a, unsigned i) {
 }
 // binmat.c:64-75
 void binmat_fill(binmat *m, unsigned i, uint8_t *dst) {
+  MUST(queue_observe(), "binmat_fill");
   oblas_word *a = m->bits + (size_t)i * m->stride;
   for (unsigned idx = 0; idx < m->stride; idx++)
     for (unsigned tz = 0; tz < 32; tz++)
@@ -2110,6 +2234,7 @@ void binmat_expand(binmat *m, uint32_t *src, unsigned i, uint8_t u) {
   MUST(finish_dropin(), "binmat_expand");
 }
 unsigned binmat_nnz(binmat *m, unsigned i, unsigned s, unsigned e) {
+  MUST(queue_observe(), "binmat_nnz");
   if (i >= m->rows || s > e || e > (m->cols + 1)) return 0;
   return nnz_compat(m->bits + (size_t)i * m->stride, 1, s, e);
 }
