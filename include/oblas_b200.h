@@ -104,7 +104,8 @@ void oblas_b200_set_async(int async);
 void oblas_b200_queue_stats(uint64_t *batches, uint64_t *ops);
 /* Four-Russians table geometry of the elimination / apply kernels (tuning knob for
  * measurements): 0 = 4-bit groups, 256-byte tiles; 1 = 6-bit groups, 128-byte tiles;
- * 2 = 7-bit groups, 64-byte tiles; -1 = library default.  Results are identical.
+ * 2 = 7-bit groups, 64-byte tiles; 4 = 5-bit groups, 128-byte tiles; -1 = library default (picked by
+ * what fits shared memory, oblas_b200_solve_plan reports it).  Results are identical.
  * Value 3 forces the tensor-core path (tcgen05 kind::mxf4 bit-sliced GF(2) products,
  * apply_tc.cuh): for apply_geo the dense apply, for solve_geo the GF(256) elimination in outer
  * panels of 128 columns with tcgen05 rank-128 updates.  -1 picks it by size (apply: M >= 256,

@@ -1510,13 +1510,14 @@ inline int launch_solve_t(const SolveArgs &p, uint32_t grid, uint32_t threads,
   return 0;
 }
 
-// table geometry: 0 = 4-bit groups / 256-byte tiles, 1 = 6-bit / 128, 2 = 7-bit / 64
+// table geometry: 0 = 4-bit groups / 256-byte tiles, 1 = 6-bit / 128, 2 = 7-bit / 64, 4 = 5-bit / 128
 template <int EXP, int NBW>
 inline int launch_solve_geo(int geo, const SolveArgs &p, uint32_t grid, uint32_t threads,
                             size_t smem_limit, cudaStream_t s) {
   switch (geo) {
   case 1: return launch_solve_t<EXP, NBW, 6, 128>(p, grid, threads, smem_limit, s);
   case 2: return launch_solve_t<EXP, NBW, 7, 64>(p, grid, threads, smem_limit, s);
+  case 4: return launch_solve_t<EXP, NBW, 5, 128>(p, grid, threads, smem_limit, s);
   default: return launch_solve_t<EXP, NBW, 4, 256>(p, grid, threads, smem_limit, s);
   }
 }
@@ -1536,15 +1537,18 @@ inline bool solve_fits_geo(int geo, uint32_t rows, size_t smem_limit, int out[3]
   switch (geo) {
   case 1: ok = solve_fits_t<EXP, NBW, 6, 128>(rows, smem_limit); kb = 6; wt = 128; break;
   case 2: ok = solve_fits_t<EXP, NBW, 7, 64>(rows, smem_limit); kb = 7; wt = 64; break;
+  case 4: ok = solve_fits_t<EXP, NBW, 5, 128>(rows, smem_limit); kb = 5; wt = 128; break;
   default: ok = solve_fits_t<EXP, NBW, 4, 256>(rows, smem_limit); kb = 4; wt = 256; break;
   }
   if (ok) { out[0] = NBW; out[1] = kb; out[2] = wt; }
   return ok;
 }
 inline bool plan_solve(int field, int geo, uint32_t rows, size_t smem_limit, int out[3]) {
+  const bool autosel = geo < 0;
   if (geo < 0) geo = 1;
 #define OB2_PLAN(E)                                                                                  \
-  return solve_fits_geo<E, 4>(geo, rows, smem_limit, out) || solve_fits_geo<E, 2>(geo, rows, smem_limit, out) || \
+  return solve_fits_geo<E, 4>(geo, rows, smem_limit, out) || (autosel && solve_fits_geo<E, 4>(4, rows, smem_limit, out)) || \
+         solve_fits_geo<E, 2>(geo, rows, smem_limit, out) ||                                         \
          (geo != 0 && (solve_fits_geo<E, 4>(0, rows, smem_limit, out) || solve_fits_geo<E, 2>(0, rows, smem_limit, out)));
   switch (field) {
   case OB2_GF256: OB2_PLAN(8)
@@ -1556,14 +1560,18 @@ inline bool plan_solve(int field, int geo, uint32_t rows, size_t smem_limit, int
   return false;
 }
 
-// field = OB2_GF2 .. OB2_GF256.  geo < 0: default geometry for the field.  Picks the
-// widest panel that fits shared memory (128-bit panels, then 64-bit, then 4-bit groups).
+// field = OB2_GF2 .. OB2_GF256.  geo < 0: automatic -- 128-bit panels with 6-bit groups, then 128-bit
+// panels with 5-bit groups (what K = 2048 systems of GF(16) / GF(4) get: 13.9k against 9.8k solves/s with
+// the 64-bit panels they fell to before, 42.6k against 39.9k for GF(4); tools/geo_probe.py), then 64-bit
+// panels, then 4-bit groups (GF(2), K = 8192: NBW = 2, 4-bit groups, 256-byte tiles).
 inline int launch_solve(int field, int geo, const SolveArgs &p, uint32_t grid, uint32_t threads,
                         size_t smem_limit, cudaStream_t s) {
+  const bool autosel = geo < 0;
   if (geo < 0) geo = 1;
   int rc = -1;
 #define OB2_TRY(E)                                                                     \
   rc = launch_solve_geo<E, 4>(geo, p, grid, threads, smem_limit, s);                   \
+  if (rc == -1 && autosel) rc = launch_solve_geo<E, 4>(4, p, grid, threads, smem_limit, s); \
   if (rc == -1) rc = launch_solve_geo<E, 2>(geo, p, grid, threads, smem_limit, s);     \
   if (rc == -1 && geo != 0) rc = launch_solve_geo<E, 4>(0, p, grid, threads, smem_limit, s); \
   if (rc == -1 && geo != 0) rc = launch_solve_geo<E, 2>(0, p, grid, threads, smem_limit, s);

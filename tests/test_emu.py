@@ -142,7 +142,7 @@ def _solve(field, rows, cols, b_bytes, seed, nsys=1, deficient=0, threads=64, gr
     dict(field=GF256, rows=1, cols=1, b_bytes=16, seed=122),
     dict(field=GF256, rows=5, cols=700, b_bytes=16, seed=123),
 ])
-@pytest.mark.parametrize("geo", [0, 1, 2])
+@pytest.mark.parametrize("geo", [0, 1, 2, 4])
 def test_solve(args, geo):
     _solve(geo=geo, **args)
 

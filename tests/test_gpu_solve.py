@@ -20,8 +20,8 @@ ROOT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", autouse=True, params=[(-1, 0), (0, 0), (1, 0), (2, 0), (-1, 1), (3, 0), (3, 1)],
-                ids=["auto", "geo4x256", "geo6x128", "geo7x64", "general_panel_path", "tcgen05", "tcgen05_general_panel"])
+@pytest.fixture(scope="module", autouse=True, params=[(-1, 0), (0, 0), (1, 0), (2, 0), (4, 0), (-1, 1), (3, 0), (3, 1)],
+                ids=["auto", "geo4x256", "geo6x128", "geo7x64", "geo5x128", "general_panel_path", "tcgen05", "tcgen05_general_panel"])
 def _bind(cuda_lib, request):
     """every test of this module runs once per Four-Russians table geometry, once with the
     register-resident fast panel factorisation disabled, and (GF(256)) on the tensor-core path
