@@ -509,8 +509,20 @@ OB2_D void build_a_step(const uint4 *lutc, uint32_t cw, uint4 *dst) {
 // ---------------------------------------------------------------------------------------
 // the GEMM kernel
 // ---------------------------------------------------------------------------------------
+// Optional second producer warp (one per half tile; -DOB2_A_PRODUCERS=2): an iteration of a producer costs
+// its thread ~440 clk (measured on the update kernel) and a stage of the NH = 2 kernel is worth 484 clk of
+// MMAs, so a second producer looked worthwhile -- measured: cfg5 111.0 ms against 107.5 ms with one.  Off.
+#ifndef OB2_A_PRODUCERS
+#define OB2_A_PRODUCERS 1
+#endif
+constexpr int kAProd2Warp = kEpi0 + kEpiWarps;
 template <int NH>
-__global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs p) {
+constexpr int apply_producers() { return (NH == 2 && OB2_A_PRODUCERS == 2) ? 2 : 1; }
+template <int NH>
+constexpr int apply_threads() { return kThreads + 32 * (apply_producers<NH>() - 1); }
+
+template <int NH>
+__global__ void __launch_bounds__(apply_threads<NH>(), 1) apply_tc_kernel(const ApplyTcArgs p) {
   using K = Cfg<NH>;
   constexpr int kStages = K::kStages, kBStage = K::kBStage, kTileN = K::kTileN, kSPS = K::kSPS, kAStage = K::kAStage;
   extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
@@ -532,7 +544,7 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
   build_bitmatrix_lut(lut, tid);
   if (tid == 0) {
     for (uint32_t s = 0; s < (uint32_t)kStages; s++) {
-      mbar_init(full_bar(s), 1 + 32);   // producer's expect_tx arrive + the 32 lanes of one builder warp
+      mbar_init(full_bar(s), apply_producers<NH>() + 32);   // the producers' expect_tx arrives + the 32 lanes of one builder warp
       mbar_init(empty_bar(s), 1);       // tcgen05.commit
     }
     for (uint32_t b = 0; b < 2; b++) {
@@ -569,10 +581,12 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
   const uint32_t ksteps = p.ksteps;
   const uint32_t nst = ksteps / kSPS;   // pipeline stages per tile
 
-  if (warp == kProdWarp) {
-    // ------------------------------------------------------------ producer (TMA engine)
+  constexpr int NPROD = apply_producers<NH>();
+  if (warp == kProdWarp || (NPROD > 1 && warp == (uint32_t)kAProd2Warp)) {
+    // ------------------------------------------------------------ producers (TMA engine)
     // The whole warp runs the loop (warp-uniform control flow and addresses, so the compiler
     // keeps them in uniform registers); one elected lane issues the copies.
+    const uint32_t pwi = (warp == kProdWarp) ? 0u : 1u;   // with two producers: this one's half tile
     const bool leader = elect_one();
     const uint32_t b_dst0 = smem_addr(smB);
     uint32_t s = 0, ph = 0;
@@ -585,6 +599,10 @@ __global__ void __launch_bounds__(kThreads, 1) apply_tc_kernel(const ApplyTcArgs
         if (leader && !(p.dbg & 8)) {
           if (p.dbg & 1) {
             mbar_arrive(full_bar(s));
+          } else if (NPROD > 1) {
+            mbar_arrive_expect_tx(full_bar(s), kSPS * kHBlock);
+            bulk_g2s(b_dst0 + s * kBStage + pwi * (kSPS * kHBlock), src + (size_t)pwi * ksteps * kHBlock,
+                     kSPS * kHBlock, full_bar(s));
           } else {
             mbar_arrive_expect_tx(full_bar(s), kBStage);
 #pragma unroll

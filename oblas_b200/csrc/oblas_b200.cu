@@ -1073,9 +1073,9 @@ int tc_launch(const ob2::tc::ApplyTcArgs &a, int nh) {
   if (units64 < grid) grid = (uint32_t)units64;
   if (grid == 0) return 0;
   if (nh == 2) {
-    apply_tc_kernel<2><<<grid, kThreads, Cfg<2>::kSmemBytes, cx().stream>>>(a);
+    apply_tc_kernel<2><<<grid, apply_threads<2>(), Cfg<2>::kSmemBytes, cx().stream>>>(a);
   } else if (nh == 1) {
-    apply_tc_kernel<1><<<grid, kThreads, Cfg<1>::kSmemBytes, cx().stream>>>(a);
+    apply_tc_kernel<1><<<grid, apply_threads<1>(), Cfg<1>::kSmemBytes, cx().stream>>>(a);
   } else {   // rank-128 update with the A operand resident per (system, row tile)
     const uint64_t nunits = (uint64_t)a.nsys * a.itiles;
     grid = (uint32_t)cx().sm_count;

@@ -118,8 +118,17 @@ OB2_D uint32_t spread4(uint32_t bits4) {
   return ((bits4 * 0x00204081u) & 0x01010101u) * 0xffu;
 }
 
+// Chunks per thread and resident CTAs per SM were measured per operation (tools/rowop_probe.py, 524288 row
+// ops of 1280 B): oaxpy 2 chunks with the registers capped for 8 CTAs per SM (6183 GB/s; 4 chunks / 6 CTAs:
+// 5795), oaddrow / oscal / the others 4 chunks (oscal is bound by the ALU pipe -- 74 % active at 5.2 TB/s,
+// profiles/r02_ncu_rowop_scal.json -- and does not care).
+template <int OP>
+struct RowOpTune {
+  static constexpr int kUnroll = (OP == OP_AXPY) ? 2 : 4;
+  static constexpr int kMinBlocks = (OP == OP_AXPY) ? 8 : 6;   // 6 = the 40 registers ptxas picks unprompted; (256, 1) let it take 64 and oscal fell to 3.9 TB/s
+};
 template <int OP, int MODE, int UNROLL>
-__global__ void __launch_bounds__(256) rowop_kernel(const RowOpArgs p) {
+__global__ void __launch_bounds__(256, (UNROLL == 1) ? 1 : RowOpTune<OP>::kMinBlocks) rowop_kernel(const RowOpArgs p) {
   const uint32_t base = blockIdx.x * (blockDim.x * UNROLL) + threadIdx.x;
   uint8_t *pa[UNROLL];
   const uint8_t *pb[UNROLL];
@@ -238,9 +247,10 @@ inline void launch_rowops_t(const RowOpArgs &p, cudaStream_t s) {
   const uint32_t threads = 256;
   // big batches: 4 chunks per thread (64 B in flight per operand per thread);
   // small ones: 1 chunk per thread so that the grid still covers the SMs
+  constexpr int U = RowOpTune<OP>::kUnroll;
   if (p.total_chunks >= 148u * 256u * 4u * 2u) {
-    uint32_t blocks = (p.total_chunks + threads * 4 - 1) / (threads * 4);
-    auto k = rowop_kernel<OP, MODE, 4>;
+    uint32_t blocks = (p.total_chunks + threads * U - 1) / (threads * U);
+    auto k = rowop_kernel<OP, MODE, U>;
     OB2_LAUNCH(k, blocks, threads, 0, s, p);
   } else {
     uint32_t blocks = (p.total_chunks + threads - 1) / threads;
