@@ -286,9 +286,17 @@ int oblas_b200_set_elements(int field, void *bits, size_t row_stride, const uint
  * oblas_axpy(a, b, k, lo_row, hi_row) / oblas_scal take (oblas.h:24-27). */
 int oblas_b200_make_tables(unsigned exp_bits, unsigned poly, uint8_t *lo, uint8_t *hi, uint8_t *inv);
 /* Registers a table set with the device; returns a handle (>= 16) to pass as `variant` to
- * oblas_b200_rowops together with the field of the same element width.  (The elimination and
- * apply kernels are built for the reference's polynomials only.) */
+ * oblas_b200_rowops together with the field of the same element width, and to
+ * oblas_b200_set_field_tables for the elimination / apply kernels. */
 int oblas_b200_register_tables(unsigned exp_bits, const uint8_t *lo, const uint8_t *hi, const uint8_t *inv);
+/* Which table set the ELIMINATION (oblas_b200_solve_batch*, octmat_solve / gfmat_solve) and the GF(256) APPLY
+ * use for `field` (GF4 / GF16 / GF256) from now on, in the calling thread's device context: variant 0 = the
+ * reference's polynomial (7 / 19 / 285, tablegen.c:7-12; GF(4) with true field arithmetic), a handle of
+ * oblas_b200_register_tables = the field polynomial those tables belong to.  Registration regenerates the
+ * tables from the polynomial they imply; a handle whose tables are not those of a field (e.g. the shipped
+ * GF(4) pair) is refused here.  All kernels -- the Four-Russians table kernels, the outer-panel
+ * factorisation and the tcgen05 bit-matrix products -- take the polynomial as a run-time parameter. */
+int oblas_b200_set_field_tables(int field, int variant);
 
 #ifdef __cplusplus
 }

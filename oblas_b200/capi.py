@@ -70,6 +70,7 @@ def lib():
     L.oblas_b200_set_tuning.argtypes = [ci, ci]
     L.oblas_b200_make_tables.argtypes = [C.c_uint, C.c_uint, vp, vp, vp]
     L.oblas_b200_register_tables.argtypes = [C.c_uint, vp, vp, vp]
+    L.oblas_b200_set_field_tables.argtypes = [ci, ci]
     L.oblas_b200_swapcols_batch.argtypes = [ci, vp, sz, sz, C.c_uint32, vp, vp, sz]
     L.oblas_b200_get_elements.argtypes = [ci, vp, sz, vp, vp, sz, vp]
     L.oblas_b200_set_elements.argtypes = [ci, vp, sz, vp, vp, vp, sz]
@@ -210,7 +211,7 @@ EXTENSION_SYMBOLS = [
     "oblas_b200_host_alloc", "oblas_b200_host_free", "oblas_b200_managed_alloc", "oblas_b200_free",
     "oblas_b200_copy", "oblas_b200_memset", "oblas_b200_fill_random", "oblas_b200_rowops",
     "oblas_b200_solve_batch", "oblas_b200_solve_plan", "oblas_b200_solve_batch_host", "oblas_b200_solve_batch_host_ex", "oblas_b200_solve_batch_host_multi", "oblas_b200_gf256_apply_sharded", "oblas_b200_device_count", "oblas_b200_gf256_apply",
-    "oblas_b200_nnz_batch", "oblas_b200_swapcols_batch", "oblas_b200_make_tables", "oblas_b200_register_tables", "oblas_b200_get_elements", "oblas_b200_set_elements",
+    "oblas_b200_nnz_batch", "oblas_b200_swapcols_batch", "oblas_b200_make_tables", "oblas_b200_register_tables", "oblas_b200_set_field_tables", "oblas_b200_get_elements", "oblas_b200_set_elements",
     "octmat_new_aligned", "gfmat_new_aligned",
     "oaxpy_batch", "oaddrow_batch", "oscal_batch", "oswaprow_batch", "gfmat_axpy_batch",
     "gfmat_add_batch", "gfmat_scal_batch", "gfmat_swaprow_batch", "binmat_add_batch",

@@ -27,6 +27,7 @@ struct ApplyArgs {
   uint32_t nbytes;        // symbol bytes per row (%16 == 0)
   uint32_t col_tiles;     // ceil(nbytes / 256)
   int accumulate;         // 0: Y = C*D, 1: Y ^= C*D
+  uint32_t red;           // field polynomial (field_red(8, poly))
 };
 
 constexpr int kApplyRU = 8;     // Y chunks (16 B) per thread
@@ -91,13 +92,13 @@ __global__ void __launch_bounds__(512, 1) apply_kernel(const ApplyArgs p) {
     for (uint32_t it = tid; it < (uint32_t)(NG - 1) * PARTS * cwt; it += T) {
       uint32_t c2 = it % cwt, q = it / cwt;
       uint32_t part = q % PARTS, g = q / PARTS;
-      build_table_part<8, KB>(tab + (size_t)(g << KB) * CW + c2, CW, g * KB, nbasis, part, [&](uint32_t s) {
+      build_table_part<8, KB>(tab + (size_t)(g << KB) * CW + c2, CW, g * KB, nbasis, part, p.red, [&](uint32_t s) {
         return __ldg(reinterpret_cast<const uint4 *>(p.D + (size_t)(j0 + s) * p.d_stride + off + c2 * 16));
       });
     }
     for (uint32_t it = tid; it < (uint32_t)LPARTS * cwt; it += T) {
       uint32_t c2 = it % cwt, part = it / cwt;
-      build_table_part<8, LASTBITS>(tab + (size_t)((NG - 1) << KB) * CW + c2, CW, (NG - 1) * KB, nbasis, part,
+      build_table_part<8, LASTBITS>(tab + (size_t)((NG - 1) << KB) * CW + c2, CW, (NG - 1) * KB, nbasis, part, p.red,
                                     [&](uint32_t s) {
         return __ldg(reinterpret_cast<const uint4 *>(p.D + (size_t)(j0 + s) * p.d_stride + off + c2 * 16));
       });

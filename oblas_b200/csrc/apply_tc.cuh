@@ -134,6 +134,7 @@ struct ApplyTcArgs {
   TcRegion reg[2];         // Y
   uint32_t nreg;
   int accumulate;
+  uint32_t poly;           // GF(256) field polynomial with its leading term (285 = the reference's)
   int *status;             // {flag, wait limit in ms}: flag is set to 1 if a barrier wait ran into the time limit
   int dbg;                 // diagnostics (timing experiments only, results invalid): 1 = no bulk loads, 2 = no A build, 4 = no epilogue;
                            // 8 = fault injection for the time-out test: the B-operand producer never delivers
@@ -463,7 +464,7 @@ OB2_D void epilogue_tile(uint32_t tm, uint32_t acc_col, uint32_t warp, uint32_t 
 }
 
 // coefficient c -> its 8x8 bit matrix as 8 words (word a: nibble b = 2 * bit a of c*x^b); 256 threads
-OB2_D void build_bitmatrix_lut(uint32_t *lut, uint32_t tid) {
+OB2_D void build_bitmatrix_lut(uint32_t *lut, uint32_t tid, uint32_t poly) {
   if (tid < 256) {
     uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t pw = tid;
@@ -471,7 +472,7 @@ OB2_D void build_bitmatrix_lut(uint32_t *lut, uint32_t tid) {
     for (int b = 0; b < 8; b++) {
 #pragma unroll
       for (int a = 0; a < 8; a++) w[a] |= ((pw >> a) & 1u) << (4 * b + 1);
-      pw = ((pw << 1) ^ ((pw & 0x80u) ? 0x11du : 0u)) & 0xffu;
+      pw = ((pw << 1) ^ ((pw & 0x80u) ? poly : 0u)) & 0xffu;
     }
 #pragma unroll
     for (int c = 0; c < kLutCopies; c++) {
@@ -541,7 +542,7 @@ __global__ void __launch_bounds__(apply_threads<NH>(), 1) apply_tc_kernel(const 
   auto tmem_full = [&](uint32_t b) { return bar0 + 8u * (2 * kStages + b); };
   auto tmem_empty = [&](uint32_t b) { return bar0 + 8u * (2 * kStages + 2 + b); };
 
-  build_bitmatrix_lut(lut, tid);
+  build_bitmatrix_lut(lut, tid, p.poly);
   if (tid == 0) {
     for (uint32_t s = 0; s < (uint32_t)kStages; s++) {
       mbar_init(full_bar(s), apply_producers<NH>() + 32);   // the producers' expect_tx arrives + the 32 lanes of one builder warp
@@ -912,7 +913,7 @@ __global__ void __launch_bounds__(kUThreads, 1) update_tc_kernel(const ApplyTcAr
   auto tmem_empty = [&](uint32_t b) { return bar0 + 8u * (2 * R + 10 + b); };
   auto turn = [&](uint32_t w) { return bar0 + 8u * (3 * R + 12 + w); };
 
-  build_bitmatrix_lut(lut, tid);
+  build_bitmatrix_lut(lut, tid, p.poly);
   if (tid == 0) {
     for (uint32_t s = 0; s < (uint32_t)kRStages; s++) {
       mbar_init(b_full(0, s), 1);       // producer's expect_tx arrive
@@ -1245,7 +1246,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) update_
   auto tmem_full = [&](uint32_t b) { return bar0 + 8u * (24 + b); };
   auto tmem_empty = [&](uint32_t b) { return bar0 + 8u * (26 + b); };
 
-  build_bitmatrix_lut(lut, tid);
+  build_bitmatrix_lut(lut, tid, p.poly);
   if (tid == 0) {
     for (uint32_t s = 0; s < (uint32_t)kU2Stages; s++) {
       mbar_init(b_full(s), rank == 0 ? 2 : 1);   // own bulk copy (+ in CTA 0: the relay arrive of CTA 1)

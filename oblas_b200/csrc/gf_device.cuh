@@ -66,36 +66,28 @@ OB2_D uint32_t mul_lut(uint32_t w, const Lut16x2 &t) {
 }
 
 // ---- multiply every packed element of a word by x (the field generator) ------
-// EXP = bits per element; elements are packed little-endian (gfmat.c:88).
+// EXP = bits per element; elements are packed little-endian (gfmat.c:88).  `red` describes the
+// field polynomial x^EXP = r(x): EXP = 8: r replicated into the four bytes (0x1d1d1d1d for the
+// reference's 285), EXP = 4 / 2: r itself (3 for 19 and for 7).  field_red() makes it.
 template <int EXP>
-OB2_D uint32_t xtime(uint32_t w) {
-  if (EXP == 8) {  // poly 285: x^8 = x^4+x^3+x^2+1 = 0x1d
+OB2_D uint32_t xtime(uint32_t w, uint32_t red) {
+  if (EXP == 8) {
     uint32_t m = spread_msb(w);
-    return ((w & 0x7f7f7f7fu) << 1) ^ (m & 0x1d1d1d1du);
-  } else if (EXP == 4) {  // poly 19: x^4 = x+1 = 3
+    return ((w & 0x7f7f7f7fu) << 1) ^ (m & red);
+  } else if (EXP == 4) {
     uint32_t top = (w >> 3) & 0x11111111u;
-    return ((w & 0x77777777u) << 1) ^ (top * 3u);
-  } else if (EXP == 2) {  // poly 7: x^2 = x+1 = 3
+    return ((w & 0x77777777u) << 1) ^ (top * red);
+  } else if (EXP == 2) {
     uint32_t top = (w >> 1) & 0x55555555u;
-    return ((w & 0x55555555u) << 1) ^ (top * 3u);
+    return ((w & 0x55555555u) << 1) ^ (top * red);
   } else {
     return w;
   }
 }
-
-// scalar field helpers on single elements (used by the panel factorisation)
-template <int EXP>
-OB2_D uint32_t gf_mul_scalar(uint32_t a, uint32_t b) {
-  if (EXP == 1) return a & b;
-  constexpr uint32_t poly = (EXP == 2) ? 7u : (EXP == 4) ? 19u : 285u;
-  uint32_t acc = 0;
-#pragma unroll
-  for (int i = 0; i < EXP; i++) {
-    acc ^= (0u - ((b >> i) & 1u)) & a;
-    a <<= 1;
-    a ^= (0u - ((a >> EXP) & 1u)) & poly;
-  }
-  return acc;
+// poly includes the leading term (285, 19, 7 are the reference's, tablegen.c:7-12)
+inline uint32_t field_red(unsigned exp_bits, unsigned poly) {
+  const uint32_t r = poly & ((1u << exp_bits) - 1u);
+  return exp_bits == 8 ? r * 0x01010101u : r;
 }
 
 }  // namespace ob2

@@ -95,6 +95,8 @@ struct Ctx {
   // table sets registered at run time for other field polynomials (row f-4): handle = 16 + index
   std::vector<DevTableSet *> d_custom;
   std::vector<int> custom_linear, custom_bits;
+  std::vector<unsigned> custom_poly;   // field polynomial if the registered tables are those of a field, else 0
+  int field_variant[4] = {0, 0, 0, 0};  // table set of the elimination / apply kernels per field (oblas_b200_set_field_tables)
   // device scratch for index arrays handed over from plain host memory
   void *scratch = nullptr;
   size_t scratch_bytes = 0;
@@ -437,6 +439,8 @@ static void shutdown_ctx(Ctx &c) {
   c.d_custom.clear();
   c.custom_linear.clear();
   c.custom_bits.clear();
+  c.custom_poly.clear();
+  for (int &v : c.field_variant) v = 0;
   cudaFree(c.d_sets);
   c.d_sets = nullptr;
   cudaStreamDestroy(c.own_stream);
@@ -718,6 +722,25 @@ static bool solve_tc_eligible(int field, const SolveArgs &p, size_t nsys) {
   // auto: the rank-128 tensor-core update pays once the systems are big enough to fill its tiles
   return p.rows >= 512 && p.cols >= 256 && nsys >= 1;
 }
+// inverse table (device) and polynomial the elimination / apply kernels use for `field`: the reference's
+// (GF(4): true field arithmetic) unless oblas_b200_set_field_tables selected a registered set
+static int field_arith(int field, const uint8_t **inv, unsigned *poly) {
+  static const unsigned kRefPoly[4] = {3, 7, 19, 285};   // tablegen.c:7-12 (GF(2): x + 1, unused)
+  Ctx &c = cx();
+  const int v = c.field_variant[field];
+  if (v >= 16) {
+    const size_t ci = (size_t)v - 16;
+    if (ci >= c.d_custom.size() || c.custom_bits[ci] != (int)kBits[field] || !c.custom_poly[ci])
+      return fail("field tables: handle %d cannot be used for eliminations / applies over this field", v);
+    *inv = c.d_custom[ci]->inv;
+    *poly = c.custom_poly[ci];
+    return 0;
+  }
+  const int ts = table_set_id(field, 1);
+  *inv = ts >= 0 ? c.d_sets[ts].inv : nullptr;
+  *poly = kRefPoly[field];
+  return 0;
+}
 static int solve_common(int field, SolveArgs &p, size_t nsys) {
   if (field < OB2_GF2 || field > OB2_GF256) return fail("solve: bad field %d", field);
   if (p.rows == 0 || p.cols == 0 || nsys == 0) return 0;
@@ -725,8 +748,13 @@ static int solve_common(int field, SolveArgs &p, size_t nsys) {
   if (p.B && ((p.b_bytes & 15) || (p.b_rs & 15))) return fail("solve: B row bytes / stride must be multiples of 16");
   uint32_t ebits = kBits[field];
   if ((size_t)p.cols * ebits > (size_t)p.a_bytes * 8) return fail("solve: cols exceed a_row_bytes");
-  int ts = table_set_id(field, 1);
-  p.inv = ts >= 0 ? cx().d_sets[ts].inv : nullptr;
+  {
+    const uint8_t *inv = nullptr;
+    unsigned poly = 0;
+    if (field_arith(field, &inv, &poly)) return -1;
+    p.inv = inv;
+    p.red = field_red(ebits, poly);
+  }
   p.nsys = (uint32_t)nsys;
   p.phase = cx().d_phase;
   p.no_fast_panel = cx().no_fast_panel & 1;
@@ -1111,7 +1139,7 @@ int tc_launch(const ob2::tc::ApplyTcArgs &a, int nh) {
   return after_launch("apply (tcgen05)");
 }
 int apply_tc_run(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, const uint8_t *D, size_t d_stride,
-                 uint8_t *Y, size_t y_stride, size_t nbytes, int accumulate) {
+                 uint8_t *Y, size_t y_stride, size_t nbytes, int accumulate, unsigned poly) {
   using namespace ob2::tc;
   int *dstatus = nullptr;
   if (tc_prepare(&dstatus)) return -1;
@@ -1151,7 +1179,7 @@ int apply_tc_run(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, con
     a.ksteps = ksteps; a.ntiles = nt; a.itiles = itiles; a.nsys = 1;
     a.reg[0].base = Y; a.reg[0].rs = y_stride; a.reg[0].ss = 0; a.reg[0].col0 = n0; a.reg[0].ncols = ncols;
     a.reg[0].v0 = 0; a.nreg = 1;
-    a.accumulate = accumulate; a.status = dstatus;
+    a.accumulate = accumulate; a.status = dstatus; a.poly = poly;
     a.dbg = tc_debug_switches();
     if (tc_launch(a, 2)) return -1;
   }
@@ -1322,7 +1350,7 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
       pa.A = A; pa.a_rs = p.a_rs; pa.a_ss = p.a_ss; pa.rows = rows; pa.cols = p.cols; pa.a_bytes = p.a_bytes;
       pa.E = E; pa.pos2phys = maps; pa.tcount = tcount; pa.piv_all = piv_all; pa.npiv = npiv;
       pa.pivcols = p.pivcols ? p.pivcols + first * rows : nullptr;
-      pa.nsys = cnt; pa.outer = outer; pa.inv = p.inv; pa.no_fast_panel = p.no_fast_panel;
+      pa.nsys = cnt; pa.outer = outer; pa.inv = p.inv; pa.red = p.red; pa.no_fast_panel = p.no_fast_panel;
       pa.no_look_ahead = p.no_look_ahead;
       pa.phase = cx().d_phase;
       pa.row_ws = row_ws; pa.row_ws_cta = row_ws_cta;
@@ -1373,6 +1401,7 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
       a.ksteps = ksteps; a.ntiles = ntiles; a.itiles = itiles; a.nsys = cnt;
       a.reg[0] = reg[0]; a.reg[1] = reg[1]; a.nreg = nreg;
       a.accumulate = 1; a.status = dstatus; a.prof = cx().d_uprof;
+      a.poly = 0x100u | (p.red & 0xffu);
       a.dbg = tc_debug_switches();
       {
         TcTimer tt(2);
@@ -1414,14 +1443,18 @@ int oblas_b200_gf256_apply(const void *C, size_t c_stride, uint32_t M, uint32_t 
     if (cx().apply_geo == 3) return fail("apply: tensor-core path needs 0 < Kc < 2^20");
     use_tc = false;
   }
+  const uint8_t *inv_unused = nullptr;
+  unsigned poly = 0;
+  if (field_arith(OB2_GF256, &inv_unused, &poly)) return -1;
   if (use_tc)
     return apply_tc_run((const uint8_t *)C, c_stride, M, Kc, (const uint8_t *)D, d_stride, (uint8_t *)Y,
-                        y_stride, nbytes, accumulate);
+                        y_stride, nbytes, accumulate, poly);
   ApplyArgs p;
   memset(&p, 0, sizeof p);
   p.C = (const uint8_t *)C; p.c_stride = c_stride; p.M = M; p.Kc = Kc;
   p.D = (const uint8_t *)D; p.d_stride = d_stride;
   p.Y = (uint8_t *)Y; p.y_stride = y_stride; p.nbytes = (uint32_t)nbytes; p.accumulate = accumulate;
+  p.red = field_red(8, poly);
   int rc = launch_apply(p, cx().apply_geo == 3 ? -1 : cx().apply_geo, 512, cx().stream);
   if (rc) return fail("apply: launch configuration failed (%d)", rc);
   return after_launch("apply");
@@ -1646,6 +1679,27 @@ int oblas_b200_make_tables(unsigned exp_bits, unsigned poly, uint8_t *lo, uint8_
   }
   return 0;
 }
+// Which table set the elimination and apply kernels use for `field` from now on (this context): 0 / 1 = the
+// reference's polynomial (GF(4): always the corrected, true-field table), a handle of
+// oblas_b200_register_tables = that field polynomial.  The handle must be for the field's element width and
+// its tables must be those of a field (checked at registration: regenerated from the polynomial they imply).
+int oblas_b200_set_field_tables(int field, int variant) {
+  if (ensure_init()) return -1;
+  if (field < OB2_GF4 || field > OB2_GF256) return fail("set_field_tables: field must be GF(4), GF(16) or GF(256)");
+  std::lock_guard<std::mutex> lk(cx().mu);
+  if (variant >= 16) {
+    const size_t ci = (size_t)variant - 16;
+    if (ci >= cx().d_custom.size()) return fail("set_field_tables: unknown table handle %d", variant);
+    if (cx().custom_bits[ci] != (int)kBits[field]) return fail("set_field_tables: handle %d is for %d-bit elements", variant, cx().custom_bits[ci]);
+    if (!cx().custom_poly[ci]) return fail("set_field_tables: the tables of handle %d are not those of a field polynomial", variant);
+  } else if (variant < 0) {
+    return fail("set_field_tables: bad variant %d", variant);
+  } else {
+    variant = 0;
+  }
+  cx().field_variant[field] = variant;
+  return 0;
+}
 // Makes a table set usable by oblas_b200_rowops: returns a handle to pass as `variant` (>= 16) with
 // the field of the same element width, or a negative code.  lo/hi: 16 * 2^exp_bits bytes, inv: 2^exp_bits.
 int oblas_b200_register_tables(unsigned exp_bits, const uint8_t *lo, const uint8_t *hi, const uint8_t *inv) {
@@ -1661,6 +1715,18 @@ int oblas_b200_register_tables(unsigned exp_bits, const uint8_t *lo, const uint8
   cx().d_custom.push_back(d);
   cx().custom_linear.push_back(h.linear);
   cx().custom_bits.push_back((int)exp_bits);
+  {
+    // are these the tables of a field?  x * x^(e-1) gives the polynomial; the generator must reproduce all of them
+    const unsigned e = exp_bits, n = 1u << e;
+    unsigned low = (e == 8) ? hi[2 * 16 + 8] : (e == 4) ? (unsigned)lo[2 * 16 + 8] : ((unsigned)lo[2 * 16 + 2] & 3u);
+    const unsigned poly = n | low;
+    std::vector<uint8_t> l2(16 * n), h2(16 * n), i2(n);
+    unsigned ok_poly = 0;
+    if (oblas_b200_make_tables(e, poly, l2.data(), h2.data(), i2.data()) == 0 && !memcmp(l2.data(), lo, 16 * n) &&
+        !memcmp(h2.data(), hi, 16 * n) && !memcmp(i2.data(), inv, n))
+      ok_poly = poly;
+    cx().custom_poly.push_back(ok_poly);
+  }
   return 16 + (int)cx().d_custom.size() - 1;
 }
 

@@ -56,6 +56,7 @@ struct SolveArgs {
   uint32_t *pivcols;   // [nsys][rows] or null
   uint32_t nsys;
   const uint8_t *inv;  // field inverse table (device), unused for GF(2)
+  uint32_t red;        // field polynomial in the form xtime<EXP> takes (gf_device.cuh: field_red)
   // optional per-system base pointers (device arrays of nsys addresses) for
   // batches whose systems are separate allocations; override A/a_ss, B/b_ss
   const unsigned long long *a_ptrs, *b_ptrs;
@@ -102,7 +103,7 @@ struct SolveSmem {
     s += ((size_t)rows * 2 + 15) / 16 * 16;    // pos2phys (u16)
     s += (size_t)NPIV * 2 + 16;                // piv_phys (u16)
     s += (size_t)2 * EXP * NBW * 4 + 16;       // prow / vrow basis
-    s += 128 + 256;                            // scalars + inverse table of the field
+    s += 144 + 256;                            // scalars (scal[32] = the field polynomial) + inverse table of the field
     s += (size_t)NB * NBW * 4;                 // look-ahead: pivots' vectors
     s += ((size_t)rows + 15) / 16 * 16;        // look-ahead: candidate flags
     return (s + 15) / 16 * 16;
@@ -110,13 +111,13 @@ struct SolveSmem {
 };
 
 template <int EXP>
-OB2_D uint32_t mul_scalar_word(uint32_t w, uint32_t s) {
+OB2_D uint32_t mul_scalar_word(uint32_t w, uint32_t s, uint32_t red) {
   // every packed element of w times the field element s
   uint32_t acc = 0;
 #pragma unroll
   for (int b = 0; b < EXP; b++) {
     acc ^= (0u - ((s >> b) & 1u)) & w;
-    w = xtime<EXP>(w);
+    w = xtime<EXP>(w, red);
   }
   return acc;
 }
@@ -146,8 +147,8 @@ OB2_D uint4 xor4(uint4 a, uint4 b) {
   return make_uint4(a.x ^ b.x, a.y ^ b.y, a.z ^ b.z, a.w ^ b.w);
 }
 template <int EXP>
-OB2_D uint4 xtime4(uint4 v) {
-  return make_uint4(xtime<EXP>(v.x), xtime<EXP>(v.y), xtime<EXP>(v.z), xtime<EXP>(v.w));
+OB2_D uint4 xtime4(uint4 v, uint32_t red) {
+  return make_uint4(xtime<EXP>(v.x, red), xtime<EXP>(v.y, red), xtime<EXP>(v.z, red), xtime<EXP>(v.w, red));
 }
 
 // bits [pos, pos+len) of the NBW-word little-endian bit string w (compile-time pos/len
@@ -162,12 +163,12 @@ OB2_D uint32_t get_bits(const PanelVec<NBW> &w, int pos, int len) {
 
 // basis vector m of the panel: x^(m % EXP) * row(m / EXP), zero beyond nbasis
 template <int EXP, typename LoadRow>
-OB2_D uint4 basis_vector(uint32_t m, uint32_t nbasis, uint4 prev, bool have_prev, LoadRow load_row) {
+OB2_D uint4 basis_vector(uint32_t m, uint32_t nbasis, uint4 prev, bool have_prev, uint32_t red, LoadRow load_row) {
   if (m >= nbasis) return make_uint4(0, 0, 0, 0);
   uint32_t b = m % EXP;
-  if (have_prev && b != 0) return xtime4<EXP>(prev);
+  if (have_prev && b != 0) return xtime4<EXP>(prev, red);
   uint4 cur = load_row(m / EXP);
-  for (uint32_t j = 0; j < b; j++) cur = xtime4<EXP>(cur);
+  for (uint32_t j = 0; j < b; j++) cur = xtime4<EXP>(cur, red);
   return cur;
 }
 
@@ -176,13 +177,13 @@ OB2_D uint4 basis_vector(uint32_t m, uint32_t nbasis, uint4 prev, bool have_prev
 // walked in Gray-code order: one XOR + one STS.128 per entry, nothing read back.
 template <int EXP, int BITS, typename LoadRow>
 OB2_D void build_table_part(uint4 *tg /* entry 0 of table g, this chunk */, int cw_stride,
-                            uint32_t m0, uint32_t nbasis, uint32_t part, LoadRow load_row) {
+                            uint32_t m0, uint32_t nbasis, uint32_t part, uint32_t red, LoadRow load_row) {
   constexpr int LOW = BITS < 4 ? BITS : 4;
   uint4 bv[BITS];
   uint4 prev = make_uint4(0, 0, 0, 0);
 #pragma unroll
   for (int i = 0; i < BITS; i++) {
-    bv[i] = basis_vector<EXP>(m0 + i, nbasis, prev, i > 0 && (m0 + i - 1) < nbasis, load_row);
+    bv[i] = basis_vector<EXP>(m0 + i, nbasis, prev, i > 0 && (m0 + i - 1) < nbasis, red, load_row);
     prev = bv[i];
   }
   uint4 cur = make_uint4(0, 0, 0, 0);
@@ -261,7 +262,7 @@ struct LookAhead {
 template <int EXP, int NBW, int KB, int WT>
 OB2_D void update_tile(uint8_t *base, size_t rs, uint32_t rows, uint32_t tile_off,
                        uint32_t tile_bytes, uint32_t npiv, const uint16_t *piv_phys,
-                       const uint32_t *V, uint4 *tab, uint32_t *pan_next, uint32_t pan_off,
+                       const uint32_t *V, uint4 *tab, uint32_t red, uint32_t *pan_next, uint32_t pan_off,
                        const TileAlt alt = TileAlt(), const LookAhead *look = nullptr,
                        FastCand<NBW> *fc = nullptr, const LookChain *lc = nullptr,
                        FastChain<NBW> *chain = nullptr) {
@@ -305,13 +306,13 @@ OB2_D void update_tile(uint8_t *base, size_t rs, uint32_t rows, uint32_t tile_of
   for (uint32_t it = tid; it < (uint32_t)(NG - 1) * PARTS * cwt; it += T) {
     uint32_t ch = it % cwt, q = it / cwt;
     uint32_t part = q % PARTS, g = q / PARTS;
-    build_table_part<EXP, KB>(tab + (size_t)(g << KB) * CW + ch, CW, g * KB, nbasis, part, [&](uint32_t s) {
+    build_table_part<EXP, KB>(tab + (size_t)(g << KB) * CW + ch, CW, g * KB, nbasis, part, red, [&](uint32_t s) {
       return *reinterpret_cast<const uint4 *>(chunk_ptr(piv_phys[s], ch));
     });
   }
   for (uint32_t it = tid; it < (uint32_t)LPARTS * cwt; it += T) {
     uint32_t ch = it % cwt, part = it / cwt;
-    build_table_part<EXP, LASTBITS>(tab + (size_t)((NG - 1) << KB) * CW + ch, CW, (NG - 1) * KB, nbasis, part,
+    build_table_part<EXP, LASTBITS>(tab + (size_t)((NG - 1) << KB) * CW + ch, CW, (NG - 1) * KB, nbasis, part, red,
                                     [&](uint32_t s) {
       return *reinterpret_cast<const uint4 *>(chunk_ptr(piv_phys[s], ch));
     });
@@ -590,8 +591,9 @@ OB2_D void panel_fast_candidates(const uint32_t *pan, uint16_t *pos2phys, uint16
     if (tid < (uint32_t)(EXP * 2 * NBW)) {
       const uint32_t q = tid / (2 * NBW), w2 = tid % (2 * NBW);
       uint32_t sq = scal[3];                    // inv * x^q
-      for (uint32_t k = 0; k < q; k++) sq = xtime<EXP>(sq) & EMASK;
-      const uint32_t val = mul_scalar_word<EXP>(scal[4 + w2], sq);
+      const uint32_t red = scal[32];
+      for (uint32_t k = 0; k < q; k++) sq = xtime<EXP>(sq, red) & EMASK;
+      const uint32_t val = mul_scalar_word<EXP>(scal[4 + w2], sq, red);
       if (w2 < (uint32_t)NBW) prow[q * NBW + w2] = val;
       else vrow[q * NBW + (w2 - NBW)] = val;
     }
@@ -628,7 +630,7 @@ OB2_D void panel_fast_candidates(const uint32_t *pan, uint16_t *pos2phys, uint16
       for (int q = 0; q < EXP; q++) {
         stv<NBW>(Mb + ((uint32_t)my_col * EXP + q) * NBW, x);
 #pragma unroll
-        for (int w = 0; w < NBW; w++) x.w[w] = xtime<EXP>(x.w[w]);
+        for (int w = 0; w < NBW; w++) x.w[w] = xtime<EXP>(x.w[w], scal[32]);
       }
     }
   }
@@ -714,8 +716,9 @@ OB2_D void chain_run(FastChain<NBW> &c, uint32_t *prow, uint32_t *vrow, uint32_t
     if (tid < (uint32_t)(EXP * 2 * NBW)) {
       const uint32_t q = tid / (2 * NBW), w2 = tid % (2 * NBW);
       uint32_t sq = scal[3];
-      for (uint32_t k = 0; k < q; k++) sq = xtime<EXP>(sq) & EMASK;
-      const uint32_t val = mul_scalar_word<EXP>(scal[4 + w2], sq);
+      const uint32_t red = scal[32];
+      for (uint32_t k = 0; k < q; k++) sq = xtime<EXP>(sq, red) & EMASK;
+      const uint32_t val = mul_scalar_word<EXP>(scal[4 + w2], sq, red);
       if (w2 < (uint32_t)NBW) prow[q * NBW + w2] = val;
       else vrow[q * NBW + (w2 - NBW)] = val;
     }
@@ -757,7 +760,7 @@ OB2_D void chain_finish(FastChain<NBW> &c, uint16_t *pos2phys, uint16_t *piv_phy
       for (int q = 0; q < EXP; q++) {
         stv<NBW>(Mb + ((uint32_t)c.my_col * EXP + q) * NBW, x);
 #pragma unroll
-        for (int w = 0; w < NBW; w++) x.w[w] = xtime<EXP>(x.w[w]);
+        for (int w = 0; w < NBW; w++) x.w[w] = xtime<EXP>(x.w[w], scal[32]);
       }
     }
   }
@@ -881,9 +884,10 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
   uint32_t *prow = reinterpret_cast<uint32_t *>(sp);       sp += (size_t)EXP * NBW * 4;   // x^b * pivot row (panel part)
   uint32_t *vrow = reinterpret_cast<uint32_t *>(sp);       sp += (size_t)EXP * NBW * 4;   // x^b * its V
   uint32_t *scal = reinterpret_cast<uint32_t *>(sp);       // [0] search result, [1] flag
-  uint8_t *inv_s = reinterpret_cast<uint8_t *>(scal + 32);  // field inverses (a global load per pivot is 1/3 of a column step)
+  uint8_t *inv_s = reinterpret_cast<uint8_t *>(scal + 36);  // field inverses (a global load per pivot is 1/3 of a column step)
   uint32_t *Mb = reinterpret_cast<uint32_t *>(inv_s + 256);   // [NB][NBW] pivots' vectors of the look-ahead (not in the table area)
   uint8_t *is_cand = reinterpret_cast<uint8_t *>(Mb + NB * NBW);   // [rows] look-ahead flags
+  if (threadIdx.x == 0) scal[32] = p.red;
   if (EXP > 1)
     for (uint32_t k = threadIdx.x; k < (1u << EXP); k += blockDim.x) inv_s[k] = p.inv[k];
   for (uint32_t k = threadIdx.x; k < p.rows; k += blockDim.x) is_cand[k] = 0;
@@ -995,8 +999,8 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
         // of the row's own base: content = inv*old + inv*V*P  =>  V' = inv*V ^ inv*e_n
         const uint32_t inv = (EXP == 1) ? 1u : (uint32_t)inv_s[e];
         if (tid < (uint32_t)NBW) {
-          uint32_t w = mul_scalar_word<EXP>(pan[ph * NBW + tid], inv);
-          uint32_t v = mul_scalar_word<EXP>(V[ph * NBW + tid], inv);
+          uint32_t w = mul_scalar_word<EXP>(pan[ph * NBW + tid], inv, p.red);
+          uint32_t v = mul_scalar_word<EXP>(V[ph * NBW + tid], inv, p.red);
           if (((n * EXP) >> 5) == tid) v ^= inv << ((n * EXP) & 31);
           pan[ph * NBW + tid] = w;
           V[ph * NBW + tid] = v;
@@ -1004,8 +1008,8 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
           for (int b = 0; b < EXP; b++) {
             prow[b * NBW + tid] = w;
             vrow[b * NBW + tid] = v;
-            w = xtime<EXP>(w);
-            v = xtime<EXP>(v);
+            w = xtime<EXP>(w, p.red);
+            v = xtime<EXP>(v, p.red);
           }
         }
         __syncthreads();
@@ -1061,7 +1065,7 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
       if (look_ok && tid == 0) scal[2] = 0;   // fail flag (visible after the first barrier of the first pass)
       for (uint32_t off = a_from; off < p.a_bytes; off += WT) {
         uint32_t w = (p.a_bytes - off < (uint32_t)WT) ? (p.a_bytes - off) : (uint32_t)WT;
-        update_tile<EXP, NBW, KB, WT>(A, p.a_rs, rows, off, w, n, piv_phys, V, tab, pan, next_off, TileAlt(), nullptr,
+        update_tile<EXP, NBW, KB, WT>(A, p.a_rs, rows, off, w, n, piv_phys, V, tab, p.red, pan, next_off, TileAlt(), nullptr,
                                       nullptr, lcp, &chain);
         if (lcp && scal[14]) lcp = nullptr;
       }
@@ -1069,7 +1073,7 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
       if (B)
         for (uint32_t off = 0; off < p.b_bytes; off += WT) {
           uint32_t w = (p.b_bytes - off < (uint32_t)WT) ? (p.b_bytes - off) : (uint32_t)WT;
-          update_tile<EXP, NBW, KB, WT>(B, p.b_rs, rows, off, w, n, piv_phys, V, tab, nullptr, 0xffffffffu, TileAlt(),
+          update_tile<EXP, NBW, KB, WT>(B, p.b_rs, rows, off, w, n, piv_phys, V, tab, p.red, nullptr, 0xffffffffu, TileAlt(),
                                         nullptr, nullptr, lcp, &chain);
           if (lcp && scal[14]) lcp = nullptr;
         }
@@ -1138,6 +1142,7 @@ struct PanelArgs {
   uint32_t nsys;
   uint32_t outer;           // outer panel index
   const uint8_t *inv;
+  uint32_t red;             // field polynomial (field_red(8, poly))
   int no_fast_panel;
   int no_look_ahead;           // diagnostics/tests: candidate elimination never overlapped with the tile pass
   unsigned long long *phase;   // optional diagnostics: cycles per phase summed over CTAs (5 counters)
@@ -1183,8 +1188,9 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
   uint32_t *prow = reinterpret_cast<uint32_t *>(sp);       sp += (size_t)EXP * NBW * 4;
   uint32_t *vrow = reinterpret_cast<uint32_t *>(sp);       sp += (size_t)EXP * NBW * 4;
   uint32_t *scal = reinterpret_cast<uint32_t *>(sp);
-  uint8_t *inv_s = reinterpret_cast<uint8_t *>(scal + 32);
+  uint8_t *inv_s = reinterpret_cast<uint8_t *>(scal + 36);
   uint32_t *Mb = reinterpret_cast<uint32_t *>(inv_s + 256);          // [128][NBW] pivots' vectors (look-ahead: not in the table area)
+  if (threadIdx.x == 0) scal[32] = p.red;
   for (uint32_t k = threadIdx.x; k < 256u; k += blockDim.x) inv_s[k] = p.inv[k];
   for (uint32_t k = threadIdx.x; k < rows; k += blockDim.x) is_cand[k] = 0;
   __syncthreads();
@@ -1304,8 +1310,8 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
         }
         const uint32_t inv = (uint32_t)inv_s[e];
         if (tid < (uint32_t)NBW) {
-          uint32_t w = mul_scalar_word<EXP>(pan[ph * NBW + tid], inv);
-          uint32_t v = mul_scalar_word<EXP>(V[ph * NBW + tid], inv);
+          uint32_t w = mul_scalar_word<EXP>(pan[ph * NBW + tid], inv, p.red);
+          uint32_t v = mul_scalar_word<EXP>(V[ph * NBW + tid], inv, p.red);
           if (((n * EXP) >> 5) == tid) v ^= inv << ((n * EXP) & 31);
           pan[ph * NBW + tid] = w;
           V[ph * NBW + tid] = v;
@@ -1313,8 +1319,8 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
           for (int b = 0; b < EXP; b++) {
             prow[b * NBW + tid] = w;
             vrow[b * NBW + tid] = v;
-            w = xtime<EXP>(w);
-            v = xtime<EXP>(v);
+            w = xtime<EXP>(w, p.red);
+            v = xtime<EXP>(v, p.red);
           }
         }
         __syncthreads();
@@ -1384,14 +1390,14 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
           lk.pivcols_sys = p.pivcols ? p.pivcols + (size_t)sys * rows : nullptr;
           lk.inv_tab = inv_s; lk.pos2phys = pos2phys; lk.piv_phys = piv_phys;
           lk.prow = prow; lk.vrow = vrow; lk.scal = scal; lk.Mb = Mb; lk.is_cand = is_cand;
-          update_tile<EXP, NBW, KB, WT>(A, p.a_rs, rows, win_off, win_bytes, n, piv_phys, V, tab, pan, next_off, alt, &lk, &fc);
+          update_tile<EXP, NBW, KB, WT>(A, p.a_rs, rows, win_off, win_bytes, n, piv_phys, V, tab, p.red, pan, next_off, alt, &lk, &fc);
           la_done = scal[2] == 0;          // uniform: read after the closing barrier of the pass
         } else {
-          update_tile<EXP, NBW, KB, WT>(A, p.a_rs, rows, win_off, win_bytes, n, piv_phys, V, tab, pan, next_off, alt);
+          update_tile<EXP, NBW, KB, WT>(A, p.a_rs, rows, win_off, win_bytes, n, piv_phys, V, tab, p.red, pan, next_off, alt);
         }
       } else {
-        update_tile<EXP, NBW, KB, WT>(A, p.a_rs, rows, win_off, win_bytes, n, piv_phys, V, tab, pan, next_off);
-        update_tile<EXP, NBW, KB, WT>(E, kOuterBytes, rows, 0, kOuterBytes, n, piv_phys, V, tab, nullptr, 0xffffffffu);
+        update_tile<EXP, NBW, KB, WT>(A, p.a_rs, rows, win_off, win_bytes, n, piv_phys, V, tab, p.red, pan, next_off);
+        update_tile<EXP, NBW, KB, WT>(E, kOuterBytes, rows, 0, kOuterBytes, n, piv_phys, V, tab, p.red, nullptr, 0xffffffffu);
       }
       pan_ready = next_off != 0xffffffffu && next_off < p.a_bytes;
       tick(3);

@@ -120,6 +120,10 @@ int emu_solve(int field, uint8_t *A, size_t a_rs, size_t a_ss, uint32_t rows, ui
   p.no_look_ahead = (no_fast >> 1) & 1;
   int ts = table_set_id(field, 1);
   p.inv = ts >= 0 ? g_sets[ts].inv : nullptr;
+  {
+    static const unsigned kPoly[4] = {3, 7, 19, 285}, kB[4] = {1, 2, 4, 8};
+    p.red = field_red(kB[field], kPoly[field]);
+  }
   if (force_nbw == 2) {
     switch (field) {
     case OB2_GF256: return launch_solve_geo<8, 2>(geo, p, grid, threads, smem_limit, nullptr);
@@ -136,6 +140,7 @@ int emu_apply(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, const 
               uint32_t threads, int geo) {
   ApplyArgs p;
   memset(&p, 0, sizeof p);
+  p.red = field_red(8, 285);
   p.C = C; p.c_stride = c_stride; p.M = M; p.Kc = Kc; p.D = D; p.d_stride = d_stride;
   p.Y = Y; p.y_stride = y_stride; p.nbytes = nbytes; p.accumulate = accumulate;
   return launch_apply(p, geo, threads, nullptr);
@@ -164,7 +169,7 @@ int emu_solve_outer(uint8_t *A, size_t a_rs, size_t a_ss, uint32_t rows, uint32_
     pa.A = A; pa.a_rs = a_rs; pa.a_ss = a_ss; pa.rows = rows; pa.cols = cols; pa.a_bytes = a_bytes;
     pa.E = E.data(); pa.pos2phys = maps.data(); pa.tcount = tcount.data(); pa.piv_all = piv_all.data();
     pa.npiv = npiv.data(); pa.pivcols = pivcols; pa.nsys = nsys; pa.outer = outer;
-    pa.inv = T.inv; pa.no_fast_panel = no_fast & 1; pa.no_look_ahead = (no_fast >> 1) & 1;
+    pa.inv = T.inv; pa.red = field_red(8, 285); pa.no_fast_panel = no_fast & 1; pa.no_look_ahead = (no_fast >> 1) & 1;
     int rc = launch_panel_t<6, 128>(pa, grid, smem_limit, nullptr, threads);
     if (rc) return rc;
     const uint32_t a0 = (outer + 1) * kOuterBytes;
