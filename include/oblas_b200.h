@@ -237,6 +237,18 @@ int oblas_b200_gf256_apply(const void *C, size_t c_stride, uint32_t M, uint32_t 
                            const void *D, size_t d_stride, void *Y, size_t y_stride,
                            size_t nbytes, int accumulate);
 
+/* ---- mixed-field apply ("next" row f-2) --------------------------------------------------- */
+/* Y (M x ncols bytes) = C (M x Kc GF(256) coefficients) * expand(Dbits): the Kc rows of D are GF(2) rows in
+ * binmat layout (one bit per column, 32 columns per uint32 word, row stride d_stride_words) and every bit
+ * counts as the field element 0 / 1 -- exactly what the loop
+ *     for i, j:  oaxpy_b32(Y, Dbits + j * d_stride_words, i, C[i][j])        (octmat.c:65-68, oblas_ref.c:19-28)
+ * leaves in a zeroed Y (accumulate != 0: Y ^= ...).  The bit -> element expansion happens inside the
+ * operand expansion of the tcgen05 apply: M * Kc row operations become one tensor-core product.
+ * ncols % 16 == 0; device-visible pointers. */
+int oblas_b200_gf256_apply_b32(const void *C, size_t c_stride, uint32_t M, uint32_t Kc,
+                               const uint32_t *Dbits, size_t d_stride_words, void *Y, size_t y_stride,
+                               size_t ncols, int accumulate);
+
 /* ---- several GPUs from ONE process ------------------------------------ */
 /* One context per device (oblas_b200_set_device); the two calls below run one host thread per
  * device.  devices: ndev device ordinals, NULL = 0 .. ndev-1; ndev <= 0 = all visible devices. */

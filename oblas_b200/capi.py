@@ -101,6 +101,7 @@ def lib():
     L.oblas_b200_device_count.restype = ci
     L.oblas_b200_solve_batch_host_multi.argtypes = [ci, vp, sz, sz, u32, u32, sz, vp, sz, sz, sz, vp, vp, sz, vp, ci, C.c_uint]
     L.oblas_b200_gf256_apply_sharded.argtypes = [vp, sz, u32, u32, vp, sz, vp, sz, sz, vp, ci, C.POINTER(C.c_double)]
+    L.oblas_b200_gf256_apply_b32.argtypes = [vp, sz, u32, u32, vp, sz, vp, sz, sz, ci]
     L.oblas_b200_gf256_apply.argtypes = [vp, sz, u32, u32, vp, sz, vp, sz, sz, ci]
     L.oblas_b200_nnz_batch.argtypes = [ci, vp, sz, u32, vp, sz, u32, u32, vp]
     _bind_compat(L)
@@ -210,7 +211,7 @@ EXTENSION_SYMBOLS = [
     "oblas_b200_set_async", "oblas_b200_queue_stats", "oblas_b200_set_tuning", "oblas_b200_solve_tc_times", "oblas_b200_set_panel_path", "oblas_b200_solve_phases", "oblas_b200_update_phases", "oblas_b200_launch_count", "oblas_b200_dev_alloc", "oblas_b200_dev_free",
     "oblas_b200_host_alloc", "oblas_b200_host_free", "oblas_b200_managed_alloc", "oblas_b200_free",
     "oblas_b200_copy", "oblas_b200_memset", "oblas_b200_fill_random", "oblas_b200_rowops",
-    "oblas_b200_solve_batch", "oblas_b200_solve_plan", "oblas_b200_solve_batch_host", "oblas_b200_solve_batch_host_ex", "oblas_b200_solve_batch_host_multi", "oblas_b200_gf256_apply_sharded", "oblas_b200_device_count", "oblas_b200_gf256_apply",
+    "oblas_b200_solve_batch", "oblas_b200_solve_plan", "oblas_b200_solve_batch_host", "oblas_b200_solve_batch_host_ex", "oblas_b200_solve_batch_host_multi", "oblas_b200_gf256_apply_sharded", "oblas_b200_device_count", "oblas_b200_gf256_apply", "oblas_b200_gf256_apply_b32",
     "oblas_b200_nnz_batch", "oblas_b200_swapcols_batch", "oblas_b200_make_tables", "oblas_b200_register_tables", "oblas_b200_set_field_tables", "oblas_b200_get_elements", "oblas_b200_set_elements",
     "octmat_new_aligned", "gfmat_new_aligned",
     "oaxpy_batch", "oaddrow_batch", "oscal_batch", "oswaprow_batch", "gfmat_axpy_batch",

@@ -123,6 +123,10 @@ struct ExpandArgs {
   const uint32_t *nrows;
   uint8_t *Dx;             // [nsys][nhalf][ksteps][kHBlock]
   uint32_t ksteps, nhalf, nsys;  // ksteps is a multiple of Cfg::kSPS (steps beyond Kc are zero blocks)
+  // the rows of D are GF(2) rows, one BIT per column, 32 columns per little-endian word (binmat layout,
+  // binmat.c:26-33; the mask operand of oaxpy_b32 / binmat_expand, oblas_ref.c:19-28): column n of a row is
+  // the field element 0 or 1.  Expanding them here fuses n x Kc oaxpy_b32 calls into one tensor-core apply.
+  int bit_rows;
 };
 
 struct ApplyTcArgs {
@@ -185,9 +189,15 @@ __global__ void __launch_bounds__(256) expand_d_kernel(const ExpandArgs p) {
       x[jj] = 0;
       if (j < nrows && n < rg.ncols) {
         const uint32_t row = p.rowmap ? (uint32_t)p.rowmap[(size_t)sys * p.rowmap_stride + j] : j;
-        const uint2 q = *reinterpret_cast<const uint2 *>(src0 + (size_t)row * rg.rs);
-        // bytes par, par+2 of q.x and of q.y -> one word
-        x[jj] = __byte_perm(q.x, q.y, par ? 0x7531u : 0x6420u);
+        if (p.bit_rows) {
+          // the 8 columns of the group are one byte of the bit row; columns par, par+2, par+4, par+6 -> bytes 0 / 1
+          const uint32_t m = *(rg.base + (size_t)sys * rg.ss + (size_t)row * rg.rs + ((rg.col0 + n) >> 3)) >> par;
+          x[jj] = (m & 1u) | ((m & 4u) << 6) | ((m & 16u) << 12) | ((m & 64u) << 18);
+        } else {
+          const uint2 q = *reinterpret_cast<const uint2 *>(src0 + (size_t)row * rg.rs);
+          // bytes par, par+2 of q.x and of q.y -> one word
+          x[jj] = __byte_perm(q.x, q.y, par ? 0x7531u : 0x6420u);
+        }
       }
     }
     uint8_t *blk = p.Dx + (((size_t)sys * p.nhalf + half) * p.ksteps + ks) * kHBlock + grp * 256;

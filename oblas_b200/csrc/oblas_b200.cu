@@ -1139,7 +1139,7 @@ int tc_launch(const ob2::tc::ApplyTcArgs &a, int nh) {
   return after_launch("apply (tcgen05)");
 }
 int apply_tc_run(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, const uint8_t *D, size_t d_stride,
-                 uint8_t *Y, size_t y_stride, size_t nbytes, int accumulate, unsigned poly) {
+                 uint8_t *Y, size_t y_stride, size_t nbytes, int accumulate, unsigned poly, int d_bit_rows = 0) {
   using namespace ob2::tc;
   int *dstatus = nullptr;
   if (tc_prepare(&dstatus)) return -1;
@@ -1166,7 +1166,7 @@ int apply_tc_run(const uint8_t *C, size_t c_stride, uint32_t M, uint32_t Kc, con
     memset(&e, 0, sizeof e);
     e.reg[0].base = const_cast<uint8_t *>(D); e.reg[0].rs = d_stride; e.reg[0].ss = 0;
     e.reg[0].col0 = n0; e.reg[0].ncols = ncols; e.reg[0].v0 = 0;
-    e.nreg = 1; e.Kc = Kc; e.rowmap = nullptr; e.rowmap_stride = 0; e.nrows = nullptr;
+    e.nreg = 1; e.Kc = Kc; e.rowmap = nullptr; e.rowmap_stride = 0; e.nrows = nullptr; e.bit_rows = d_bit_rows;
     e.Dx = (uint8_t *)cx().tc_ws; e.ksteps = ksteps; e.nhalf = 2 * nt; e.nsys = 1;
     const size_t work = (size_t)nt * ksteps * (kTileN / 4);
     uint32_t eg = (uint32_t)((work + 255) / 256);
@@ -1458,6 +1458,29 @@ int oblas_b200_gf256_apply(const void *C, size_t c_stride, uint32_t M, uint32_t 
   int rc = launch_apply(p, cx().apply_geo == 3 ? -1 : cx().apply_geo, 512, cx().stream);
   if (rc) return fail("apply: launch configuration failed (%d)", rc);
   return after_launch("apply");
+}
+
+// ---- mixed-field apply ("next" row f-2): the rows of D are GF(2) rows in binmat layout -------
+// Y (M x ncols bytes) = C (M x Kc over GF(256)) * expand(Dbits), expand = every bit as the field element 0 / 1:
+// what  for i, j: oaxpy_b32(Y, Dbits row j, i, C[i][j])  leaves (octmat.c:65-68 -> oblas_ref.c:19-28), the
+// expansion fused into the operand expansion of the tensor-core apply.
+int oblas_b200_gf256_apply_b32(const void *C, size_t c_stride, uint32_t M, uint32_t Kc, const uint32_t *Dbits,
+                               size_t d_stride_words, void *Y, size_t y_stride, size_t ncols, int accumulate) {
+  if (ensure_init()) return -1;
+  if (M == 0 || ncols == 0) return 0;
+  if (!C || !Dbits || !Y) return fail("apply_b32: null pointer");
+  if ((ncols & 15) || (y_stride & 15) || (reinterpret_cast<uintptr_t>(Y) & 15))
+    return fail("apply_b32: Y, its stride and ncols must be multiples of 16");
+  if (d_stride_words * 32 < ncols) return fail("apply_b32: d_stride_words * 32 < ncols");
+  if (Kc == 0 || Kc >= (1u << 20)) return fail("apply_b32: needs 0 < Kc < 2^20");
+  if (classify(C) != PK_DEVVIS || classify(Dbits) != PK_DEVVIS || classify(Y) != PK_DEVVIS)
+    return fail("apply_b32: pointers must be device-visible");
+  std::lock_guard<std::mutex> lk(cx().mu);
+  const uint8_t *inv_unused = nullptr;
+  unsigned poly = 0;
+  if (field_arith(OB2_GF256, &inv_unused, &poly)) return -1;
+  return apply_tc_run((const uint8_t *)C, c_stride, M, Kc, (const uint8_t *)Dbits, d_stride_words * 4, (uint8_t *)Y, y_stride,
+                      ncols, accumulate, poly, 1);
 }
 
 // ---- several GPUs from one process ---------------------------------

@@ -88,3 +88,41 @@ def test_nnz_batch(field, cuda_lib):
             Mw = np.ascontiguousarray(M).view(np.uint32)
             ref = [oracle().orc_nnz(field, ptr(Mw, u32p), Mw.shape[1], rows, cols, r, s, e) for r in range(rows)]
             assert ref == want.tolist(), (field, s, e)
+
+
+@pytest.mark.parametrize("M,Kc,ncols", [(40, 24, 512), (300, 130, 992), (17, 9, 32), (33, 20, 496)])
+def test_mixed_field_apply_equals_the_oaxpy_b32_composition(M, Kc, ncols, cuda_lib):
+    """row f-2: Y = C * expand(Dbits) on the tensor-core apply (the bit rows are expanded inside the operand
+    expansion) against (a) the oracle's oaxpy_b32 (oblas_ref.c:19-28) called M * Kc times and (b) the same
+    composition made of the library's own OP_AXPY_B32 row kernel, one batched launch per source row."""
+    import ctypes as C
+    from helpers import OP_AXPY_B32, u32p
+    o = oracle()
+    Cm = splitmix_bytes(41, M * Kc).reshape(M, Kc).copy()
+    words = (ncols + 31) // 32
+    Db = splitmix_bytes(42, Kc * words * 4).view(np.uint32).reshape(Kc, words).copy()
+    Y0 = np.zeros((M, words * 32), dtype=np.uint8)    # the reference's loop always works on whole mask words
+    for i in range(M):
+        for j in range(Kc):
+            o.orc_axpy_b32(ptr(Y0[i]), ptr(Db[j], u32p), words * 32, int(Cm[i, j]))
+    Y0 = np.ascontiguousarray(Y0[:, :ncols])          # the library touches the ncols columns it was given
+    dC, dD = dev(Cm), torch.from_numpy(Db.view(np.int32)).cuda()
+    Y = torch.full((M, ncols), 0x5A, dtype=torch.uint8, device="cuda")
+    capi.check(cuda_lib.oblas_b200_gf256_apply_b32(C.c_void_p(dC.data_ptr()), Kc, M, Kc, C.c_void_p(dD.data_ptr()), words,
+                                                  C.c_void_p(Y.data_ptr()), ncols, ncols, 0), "apply_b32")
+    device.sync()
+    assert np.array_equal(host(Y), Y0)
+    # accumulate mode: Y ^= the same product -> zero
+    capi.check(cuda_lib.oblas_b200_gf256_apply_b32(C.c_void_p(dC.data_ptr()), Kc, M, Kc, C.c_void_p(dD.data_ptr()), words,
+                                                  C.c_void_p(Y.data_ptr()), ncols, ncols, 1), "apply_b32")
+    device.sync()
+    assert not host(Y).any()
+    if ncols % 32 == 0:   # the row kernel reads whole mask words
+        Yr = torch.zeros((M, ncols), dtype=torch.uint8, device="cuda")
+        rows_i = torch.arange(M, dtype=torch.int32, device="cuda")
+        dDb = torch.from_numpy(Db.view(np.uint8).reshape(Kc, words * 4)).cuda()
+        for j in range(Kc):
+            device.rowops(GF256, OP_AXPY_B32, Yr, dDb, rows_i, torch.full((M,), j, dtype=torch.int32, device="cuda"),
+                          dev(Cm[:, j].copy()))
+        device.sync()
+        assert np.array_equal(host(Yr), Y0)
