@@ -790,7 +790,7 @@ def solve_config(name, field, K, nsys_total, L_, capi, device, torch, dist, worl
     ng = (32 * nbw + kb - 1) // kb
     npan = (a_bytes + pan_bytes - 1) // pan_bytes
     lookups = sum(K * max(a_bytes - (p + 1) * pan_bytes, 0) / 16.0 * ng for p in range(npan))
-    peak_lookups = 8.0 * sms * sm_mhz * 1e6
+    peak_lookups = 8.0 * sms * sm_mhz * 1e6 * world
     ach = nsys_total * lookups / (ms / 1e3)
     # the same in field terms: a look-up applies KB coefficient bits to 128 data bits
     macs_exec = K * K * (K / 2.0)          # Gauss-Jordan, A only: K^3 / 2 field MACs
@@ -805,7 +805,7 @@ def solve_config(name, field, K, nsys_total, L_, capi, device, torch, dist, worl
                         "field_gmacs_per_system_executed": macs_exec / 1e9,
                         "T_field_MAC_per_s": nsys_total * macs_exec / (ms / 1e3) / 1e12},
            "roofline_hbm": {"bound": "hbm", "unit": "GB/s", "achieved": 2.0 * nsys_total * K * a_bytes / (ms / 1e3) / 1e9,
-                            "peak": hbm_peak, "frac": 2.0 * nsys_total * K * a_bytes / (ms / 1e3) / 1e9 / hbm_peak,
+                            "peak": hbm_peak * world, "frac": 2.0 * nsys_total * K * a_bytes / (ms / 1e3) / 1e9 / (hbm_peak * world),
                             "note": "algorithmic bytes = every matrix read and written once; the kernel streams each "
                                     "matrix once per panel (compute bound by construction)"},
            "full_rank_fraction": float((ranks == K).mean()), "mean_rank": float(ranks.mean())}
