@@ -148,6 +148,20 @@ int oblas_b200_update_phases(int enable, uint64_t *out);
  * entries each, may be NULL) receive what was recorded so far (0 outer-panel factorisation,
  * 1 pivot-row expansion, 2 tcgen05 rank-128 update, 3 row permutation) and reset it. */
 int oblas_b200_solve_tc_times(int enable, double *ms_out, uint64_t *launches_out);
+/* the same with nclasses (1..5) entries: class 4 = lazy outer panels, the full kernel's pass over the systems
+ * the compact pass gave up (the 4-entry form counts it under class 0) */
+int oblas_b200_solve_tc_times_ex(int enable, double *ms_out, uint64_t *launches_out, int nclasses);
+/* Lazy outer panels of the tensor-core elimination.  Per outer panel of 128 columns only the windows of the
+ * first `compact_rows` not yet pivoted rows (in position order) are factorised in shared memory; those rows are
+ * updated against the OLD pivot rows (their own coefficient rows), every other row against the NEW pivot rows with
+ * its own 128-byte window as the coefficient row -- the rows x 128 x 128 products of the coefficient matrix
+ * disappear.  A system whose panel has a column without a pivot among the compact rows (rank deficiency, pivots
+ * far down) is redone by the kernel that looks at all rows; results are identical either way.
+ * compact_rows: rounded up to a multiple of 16, at least 128; 0 = off; < 0 = default (192). */
+void oblas_b200_set_lazy_panels(int compact_rows);
+/* out[0] = (system, outer panel) pairs factorised by the compact pass so far, out[1] = pairs it gave up;
+ * reset != 0 clears the counters */
+int oblas_b200_lazy_stats(uint64_t *out, int reset);
 /* number of kernels this library has launched so far */
 uint64_t oblas_b200_launch_count(void);
 

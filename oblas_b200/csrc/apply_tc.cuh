@@ -147,6 +147,14 @@ struct ApplyTcArgs {
   // epilogue warp 0: 4 wait accumulators complete, 5 read-out + stores, 6 whole loop; producer: 7 wait
   // stage free, 8 whole loop; builder warp 0: 9 wait A buffer free, 10 build, 11 whole loop; 12 tiles
   unsigned long long *prof;
+  // update_tc_kernel only (the lazy elimination, oblas_b200.cu: solve_tc_run): optional UNIT LIST -- unit u is
+  // units[u] = (system << 16 | row tile), *nunits_dev of them, both written by the outer-panel kernel; null = every
+  // (system, row tile) pair -- and optional ROW GATHER: row r of system s is physical row
+  // y_rowmap[s * y_rowmap_stride + r] of Y (0xffff: no such row); the coefficient rows C stay indexed by r
+  const uint32_t *units;
+  const uint32_t *nunits_dev;
+  const uint16_t *y_rowmap;
+  uint32_t y_rowmap_stride;
 };
 
 // byte d -> 8 fp4 values, nibble b = e2m1 1.0 (0b0010) if bit b of d is set
@@ -357,12 +365,17 @@ struct EpiTile {
   uint32_t vt;            // virtual column of this lane's word of chunk 0
   int c_lo, c_hi;
   OB2_D void set_unit(uint32_t warp, uint32_t lane, const TcRegion *reg, uint32_t nreg, uint32_t sys, uint32_t it,
-                      uint32_t M) {
+                      uint32_t M, const uint16_t *rowmap = nullptr, uint32_t rowmap_stride = 0) {
     const uint32_t lq = warp & 3u, rr = lane >> 3;
     ct0 = 4 * (lane & 7u);
     part = (warp - (uint32_t)kEpi0) >> 2;
-    const uint32_t row = it * kRowsI + lq * 4 + rr;
+    uint32_t row = it * kRowsI + lq * 4 + rr;
     row_ok = row < M;
+    if (rowmap) {   // row gather (lazy elimination, update launch A)
+      const uint32_t ph = row_ok ? (uint32_t)rowmap[(size_t)sys * rowmap_stride + row] : 0xffffu;
+      row_ok = ph != 0xffffu;
+      row = row_ok ? ph : 0u;
+    }
     const TcRegion &r0 = reg[0];
     y0 = r0.base + (size_t)sys * r0.ss + r0.col0 + (size_t)row * r0.rs;
     vend = r0.ncols;
@@ -384,8 +397,8 @@ struct EpiTile {
     c_hi = (nch * ((int)part + 1)) / PARTS;
   }
   OB2_D void set(uint32_t warp, uint32_t lane, const TcRegion *reg, uint32_t nreg, uint32_t sys, uint32_t tile,
-                 uint32_t it, uint32_t M) {
-    set_unit(warp, lane, reg, nreg, sys, it, M);
+                 uint32_t it, uint32_t M, const uint16_t *rowmap = nullptr, uint32_t rowmap_stride = 0) {
+    set_unit(warp, lane, reg, nreg, sys, it, M, rowmap, rowmap_stride);
     set_tile(tile);
   }
   OB2_D bool col_ok(int cc) const {
@@ -963,7 +976,18 @@ __global__ void __launch_bounds__(kUThreads, 1) update_tc_kernel(const ApplyTcAr
   tc_fence_after();
 
   const uint32_t itiles = p.itiles, ntiles = p.ntiles;
-  const uint32_t nunits = p.nsys * itiles;       // (system, row tile)
+  // units = (system, row tile): all pairs, or the list the outer-panel kernel left (lazy elimination)
+  const uint32_t nunits = p.units ? *p.nunits_dev : p.nsys * itiles;
+  auto unit_of = [&](uint32_t su, uint32_t &sys, uint32_t &it) {
+    if (p.units) {
+      const uint32_t u = p.units[su];
+      sys = u >> 16;
+      it = u & 0xffffu;
+    } else {
+      sys = su / itiles;
+      it = su - sys * itiles;
+    }
+  };
 
   if (warp == kProdWarp || (kUProducers > 1 && warp >= (uint32_t)kProd2Warp)) {
     // ------------------------------------------------------------ producers: B blocks of every column tile
@@ -975,7 +999,8 @@ __global__ void __launch_bounds__(kUThreads, 1) update_tc_kernel(const ApplyTcAr
     const bool prof = PROF && p.prof != nullptr && pwi == 0;
     long long pt0 = prof ? clock64() : 0, pw = 0;
     for (uint32_t su = blockIdx.x; su < nunits && ok; su += gridDim.x) {
-      const uint32_t sys = su / itiles;
+      uint32_t sys, it_unused;
+      unit_of(su, sys, it_unused);
       const uint8_t *src0 = p.Dx + (size_t)sys * ntiles * kUSteps * kHBlock;
       for (uint32_t j = 0; j < ntiles && ok; j++, ph ^= 1u) {
         const uint32_t odd = (tile_iter + j) & 1u;            // which set of b_full barriers this tile uses
@@ -1098,7 +1123,8 @@ __global__ void __launch_bounds__(kUThreads, 1) update_tc_kernel(const ApplyTcAr
     long long pt0 = prof ? clock64() : 0, pw = 0, pb = 0;
     bool ok = true;
     for (uint32_t su = blockIdx.x; su < nunits && ok; su += gridDim.x, unit_iter++) {
-      const uint32_t sys = su / itiles, it = su - sys * itiles;
+      uint32_t sys, it;
+      unit_of(su, sys, it);
       const uint32_t row = it * kRowsI + i;
       const uint8_t *crow = p.C + (size_t)sys * p.c_ss + (size_t)row * p.c_stride + 4 * q;
       // this warp builds step b of every stage's part (steps 4*s .. 4*s+3)
@@ -1131,8 +1157,9 @@ __global__ void __launch_bounds__(kUThreads, 1) update_tc_kernel(const ApplyTcAr
     // ------------------------------------------------------------ epilogue (warps 6 .. 6 + kUEpiWarps - 1)
     using ET = EpiTile<kHalfN, kUEpiParts>;
     auto tile_of = [&](uint32_t su, uint32_t nt, ET &e) {
-      const uint32_t sys = su / itiles, it = su - sys * itiles;
-      e.set(warp, lane, p.reg, p.nreg, sys, nt, it, p.M);
+      uint32_t sys, it;
+      unit_of(su, sys, it);
+      e.set(warp, lane, p.reg, p.nreg, sys, nt, it, p.M, p.y_rowmap, p.y_rowmap_stride);
     };
     ET cur, nxt;
     uint32_t old_cur[ET::kC0], old_nxt[ET::kC0];

@@ -88,6 +88,8 @@ struct Ctx {
   bool tc_timing = false;
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> tc_events;  // (class, (start, stop))
   int no_fast_panel = 0;               // diagnostics: general panel path only
+  unsigned long long *d_lazy_stats = nullptr;   // {compact, given up} (system, outer panel) pairs
+  int tc_lazy_rows = 192;              // tensor-core elimination: rows of the compact set of the lazy outer panels, 0 = off
   unsigned long long *d_phase = nullptr;  // solve-kernel phase counters (diagnostics)
   unsigned long long *d_uprof = nullptr;  // update_tc_kernel role counters (diagnostics)
   DevTableSet *d_sets = nullptr;  // [TS_COUNT] in device memory
@@ -433,7 +435,8 @@ static void shutdown_ctx(Ctx &c) {
   c.d_zero = nullptr;
   if (c.d_phase) cudaFree(c.d_phase);
   if (c.d_uprof) cudaFree(c.d_uprof);
-  c.d_phase = c.d_uprof = nullptr;
+  if (c.d_lazy_stats) cudaFree(c.d_lazy_stats);
+  c.d_phase = c.d_uprof = c.d_lazy_stats = nullptr;
   lanes_release(c);
   for (auto *d : c.d_custom) cudaFree(d);
   c.d_custom.clear();
@@ -483,6 +486,17 @@ void oblas_b200_queue_stats(uint64_t *batches, uint64_t *ops) {
   if (ops) *ops = cx().q.ops;
 }
 void oblas_b200_set_panel_path(int general_only) { cx().no_fast_panel = general_only & 3; }
+// Lazy outer panels of the tensor-core elimination (solve_tc_run): compact_rows = rows of the compact set
+// (rounded up to a multiple of 16, at least 128), 0 = off (every outer panel factorised over all rows), < 0 = default
+void oblas_b200_set_lazy_panels(int compact_rows) {
+  if (compact_rows < 0) compact_rows = 192;
+  if (compact_rows > 0) {
+    if (compact_rows < 128) compact_rows = 128;
+    if (compact_rows > 1024) compact_rows = 1024;
+    compact_rows = (compact_rows + 15) / 16 * 16;
+  }
+  cx().tc_lazy_rows = compact_rows;
+}
 void oblas_b200_set_tuning(int solve_geo, int apply_geo) {
   cx().solve_geo = solve_geo;
   cx().apply_geo = apply_geo;
@@ -1111,7 +1125,7 @@ int tc_launch(const ob2::tc::ApplyTcArgs &a, int nh) {
     // OBLAS_B200_TC_PAIR=1: the CTA-pair variant (tcgen05 cta_group::2).  Bit-exact (the whole GPU suite
     // passes on it) but as built 1.75x slower than the single-CTA kernel -- see DESIGN.md 4.5 -- so off by default.
     static const bool pair = getenv("OBLAS_B200_TC_PAIR") && atoi(getenv("OBLAS_B200_TC_PAIR")) != 0;
-    if (pair && !a.prof) {
+    if (pair && !a.prof && !a.units) {
       // CTA pairs (cta_group::2): a cluster of 2 per pair of row tiles
       const uint64_t npairs = (uint64_t)a.nsys * ((a.itiles + 1) / 2);
       grid = (uint32_t)cx().sm_count & ~1u;
@@ -1221,11 +1235,36 @@ struct TcTimer {
     cx().tc_events.push_back({cls, {a, b}});
   }
 };
+// classes of the _ex form: 0 outer-panel factorisation (lazy: the compact pass), 1 pivot-row expansion, 2 tcgen05
+// update, 3 permutation, 4 lazy: the full kernel's pass over the systems the compact pass gave up.  The 4-entry
+// form adds class 4 to class 0.
+static int solve_tc_times_impl(int enable, double *ms_out, uint64_t *launches_out, int nclasses);
 extern "C" int oblas_b200_solve_tc_times(int enable, double *ms_out, uint64_t *launches_out) {
+  return solve_tc_times_impl(enable, ms_out, launches_out, 4);
+}
+extern "C" int oblas_b200_solve_tc_times_ex(int enable, double *ms_out, uint64_t *launches_out, int nclasses) {
+  if (nclasses < 1 || nclasses > 5) return fail("solve_tc_times_ex: 1..5 classes");
+  return solve_tc_times_impl(enable, ms_out, launches_out, nclasses);
+}
+// lazy outer panels so far on this context: out[0] = (system, outer panel) pairs factorised by the compact pass,
+// out[1] = pairs it gave up (redone over all rows); reset != 0 clears the counters afterwards
+extern "C" int oblas_b200_lazy_stats(uint64_t *out, int reset) {
   if (ensure_init()) return -1;
   std::lock_guard<std::mutex> lk(cx().mu);
-  double ms[4] = {0, 0, 0, 0};
-  uint64_t n[4] = {0, 0, 0, 0};
+  uint64_t v[2] = {0, 0};
+  if (cx().d_lazy_stats) {
+    CK(cudaStreamSynchronize(cx().stream));
+    CK(cudaMemcpy(v, cx().d_lazy_stats, sizeof v, cudaMemcpyDeviceToHost));
+    if (reset) CK(cudaMemset(cx().d_lazy_stats, 0, sizeof v));
+  }
+  if (out) { out[0] = v[0]; out[1] = v[1]; }
+  return 0;
+}
+static int solve_tc_times_impl(int enable, double *ms_out, uint64_t *launches_out, int nclasses) {
+  if (ensure_init()) return -1;
+  std::lock_guard<std::mutex> lk(cx().mu);
+  double ms[5] = {0, 0, 0, 0, 0};
+  uint64_t n[5] = {0, 0, 0, 0, 0};
   if (!cx().tc_events.empty()) CK(cudaDeviceSynchronize());
   for (auto &e : cx().tc_events) {
     float t = 0;
@@ -1237,7 +1276,11 @@ extern "C" int oblas_b200_solve_tc_times(int enable, double *ms_out, uint64_t *l
     cudaEventDestroy(e.second.second);
   }
   cx().tc_events.clear();
-  for (int k = 0; k < 4; k++) {
+  if (nclasses < 5) {
+    ms[0] += ms[4];
+    n[0] += n[4];
+  }
+  for (int k = 0; k < nclasses; k++) {
     if (ms_out) ms_out[k] = ms[k];
     if (launches_out) launches_out[k] = n[k];
   }
@@ -1254,12 +1297,19 @@ extern "C" int oblas_b200_solve_tc_times(int enable, double *ms_out, uint64_t *l
 //   apply_tc_kernel                [A_rest | B] ^= E * P_old  on tcgen05
 // then permute_kernel puts the rows into position order and writes the ranks.
 // workspace bytes of one system on the tensor-core elimination path
+// ... of which the lazy outer panels: gathered windows + coefficient rows of the compact set, its row list, the flag,
+// the two unit lists
+static size_t solve_tc_lazy_ws_per_system(uint32_t rows) {
+  const size_t cmax = (size_t)cx().tc_lazy_rows;
+  if (cmax == 0) return 0;
+  return 2 * cmax * ob2::kOuterBytes + cmax * 2 + 16 + (cmax / 16 + (rows + 15) / 16) * 4;
+}
 static size_t solve_tc_ws_per_system(uint32_t rows, uint32_t a_bytes, uint32_t b_bytes) {
   using namespace ob2::tc;
   const uint32_t a_rest0 = a_bytes > (uint32_t)kOuterBytes ? a_bytes - kOuterBytes : 0;
   const uint32_t ntiles_max = (a_rest0 + b_bytes + kHalfN - 1) / kHalfN;
   return (size_t)ntiles_max * kUSteps * kHBlock + (size_t)rows * kOuterBytes + ((size_t)rows * 2 + 15) / 16 * 16 +
-         2 * kOuterBytes + 16;
+         2 * kOuterBytes + 16 + solve_tc_lazy_ws_per_system(rows);
 }
 // How a batch would run: *path = 1 tensor-core elimination (outer panels + tcgen05 updates), 0 = shared-memory
 // table kernel; *chunk_systems = systems per chunk of the tensor-core path (the whole batch on the table kernel).
@@ -1307,7 +1357,12 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
   const size_t e_per_sys = (size_t)rows * kOuterBytes;
   const size_t map_per_sys = ((size_t)rows * 2 + 15) / 16 * 16;
   const size_t small_per_sys = 2 * kOuterBytes + 16;   // piv_all (u16 x 128) + tcount + npiv + pad
-  const size_t per_sys = dx_per_sys + e_per_sys + map_per_sys + small_per_sys;
+  // lazy outer panels (header of panel_kernel, solve.cuh): compact set of cmax rows per system
+  const uint32_t cmax = (rows >= (uint32_t)kOuterBytes) ? (uint32_t)cx().tc_lazy_rows : 0u;
+  const bool lazy = cmax != 0;
+  const size_t wc_per_sys = (size_t)cmax * kOuterBytes;
+  const size_t lazy_per_sys = solve_tc_lazy_ws_per_system(rows);
+  const size_t per_sys = dx_per_sys + e_per_sys + map_per_sys + small_per_sys + lazy_per_sys;
   // tall systems: the per-row state of the outer-panel kernel lives in global memory, one block per CTA
   const bool grows = panel_smem_bytes(rows) > cx().smem_optin;
   const size_t row_ws_cta = grows ? panel_row_ws_bytes(rows) : 0;
@@ -1315,8 +1370,9 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
   size_t chunk = cx().tc_ws_budget / per_sys;
   if (chunk < 1) chunk = 1;
   if (chunk > nsys) chunk = nsys;
+  if (lazy && chunk > 65535) chunk = 65535;   // unit lists: (system << 16 | row tile)
   for (;;) {
-    int rc = tc_ws_reserve(chunk * per_sys + 256 + row_ws_all + 256);
+    int rc = tc_ws_reserve(chunk * per_sys + 256 + row_ws_all + 256 + 256);
     if (rc < 0) return -1;
     if (rc == 0) break;
     if (chunk == 1) return fail("solve: cannot allocate %zu bytes of workspace", per_sys);
@@ -1329,6 +1385,19 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
   uint16_t *piv_all = (uint16_t *)ws;                      ws += chunk * 2 * kOuterBytes;
   uint32_t *tcount = (uint32_t *)ws;                       ws += chunk * 4;
   uint32_t *npiv = (uint32_t *)ws;                         ws += chunk * 4;
+  uint8_t *Wc = nullptr, *Ec = nullptr, *flags = nullptr;
+  uint16_t *crow = nullptr;
+  uint32_t *unitsA = nullptr, *unitsB = nullptr, *ncount = nullptr;
+  if (lazy) {
+    ws = (uint8_t *)(((uintptr_t)ws + 15) & ~(uintptr_t)15);
+    Wc = ws;                                               ws += chunk * wc_per_sys;
+    Ec = ws;                                               ws += chunk * wc_per_sys;
+    unitsA = (uint32_t *)ws;                               ws += chunk * (cmax / 16) * 4;
+    unitsB = (uint32_t *)ws;                               ws += chunk * (size_t)itiles * 4;
+    ncount = (uint32_t *)ws;                               ws += 16;
+    crow = (uint16_t *)ws;                                 ws += chunk * (size_t)cmax * 2;
+    flags = ws;                                            ws += (chunk + 15) / 16 * 16;
+  }
   uint8_t *row_ws = grows ? (uint8_t *)(((uintptr_t)ws + 255) & ~(uintptr_t)255) : nullptr;
   // permutation kernel: row map + staging area in shared memory
   const size_t pmap = ((size_t)rows * 2 + 15) / 16 * 16;
@@ -1354,9 +1423,34 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
       pa.no_look_ahead = p.no_look_ahead;
       pa.phase = cx().d_phase;
       pa.row_ws = row_ws; pa.row_ws_cta = row_ws_cta;
+      // Lazy outer panel (a whole 128-column window): the compact kernel factorises the windows of the first cmax
+      // unpivoted rows only and leaves two unit lists; the systems it gives up (a column without a pivot among
+      // those rows: rank deficiency, or pivots far down) are redone by the full kernel, which puts all their row
+      // tiles on list B.  Otherwise (narrow last panel, lazy off): the full kernel for every system.
+      const uint32_t win_end = (outer + 1) * kOuterBytes;
+      const bool lazy_panel = lazy && win_end <= p.cols && win_end <= p.a_bytes;
+      if (lazy_panel) {
+        CK(cudaMemsetAsync(ncount, 0, 16, cx().stream));
+        PanelArgs pc = pa;
+        pc.cmax = cmax; pc.Wc = Wc; pc.Ec = Ec; pc.crow = crow; pc.flags = flags;
+        pc.unitsA = unitsA; pc.nunitsA = ncount; pc.unitsB = unitsB; pc.nunitsB = ncount + 1;
+        pc.row_ws = nullptr; pc.row_ws_cta = 0;
+        if (!cx().d_lazy_stats) {
+          CK(cudaMalloc(&cx().d_lazy_stats, 16));
+          CK(cudaMemset(cx().d_lazy_stats, 0, 16));
+        }
+        pc.stats = cx().d_lazy_stats;
+        {
+          TcTimer tt(0);
+          int rc = launch_panel_t<6, 128>(pc, grid, cx().smem_optin, cx().stream);
+          if (rc) return fail("solve (tensor-core path): compact panel kernel launch configuration failed (%d)", rc);
+        }
+        if (after_launch("solve (compact outer panel)")) return -1;
+        pa.flags = flags; pa.only_flagged = 1; pa.unitsB = unitsB; pa.nunitsB = ncount + 1;
+      }
       // the row map lives in global memory as [sys][rows] u16 with a 16-byte aligned pitch
       {
-        TcTimer tt(0);
+        TcTimer tt(lazy_panel ? 4 : 0);
         int rc = launch_panel_t<6, 128>(pa, grid, cx().smem_optin, cx().stream);
         if (rc) return fail("solve (tensor-core path): panel kernel launch configuration failed (%d)", rc);
       }
@@ -1390,11 +1484,6 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
       const size_t work = (size_t)cnt * ntiles * ksteps * (kTileN / 4);
       uint32_t eg = (uint32_t)((work + 255) / 256);
       if (eg > (uint32_t)cx().sm_count * 16) eg = (uint32_t)cx().sm_count * 16;
-      {
-        TcTimer tt(1);
-        expand_d_kernel<<<eg, 256, 0, cx().stream>>>(e);
-      }
-      if (after_launch("solve (pivot-row expansion)")) return -1;
       ApplyTcArgs a;
       memset(&a, 0, sizeof a);
       a.C = E; a.c_stride = kOuterBytes; a.c_ss = e_per_sys; a.M = rows; a.Kc = kOuterBytes; a.Dx = Dx;
@@ -1403,9 +1492,26 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
       a.accumulate = 1; a.status = dstatus; a.prof = cx().d_uprof;
       a.poly = 0x100u | (p.red & 0xffu);
       a.dbg = tc_debug_switches();
-      {
-        TcTimer tt(2);
-        if (tc_launch(a, getenv("OBLAS_B200_TC_STREAM_A") ? 1 : 0)) return -1;
+      // lazy: launch A -- the compact rows (gathered through crow) ^= their coefficient rows * OLD pivot rows --
+      // then the pivot rows are expanded again and launch B -- all other rows ^= their old windows * NEW pivot rows
+      for (int pass = lazy_panel ? 0 : 1; pass < 2; pass++) {
+        {
+          TcTimer tt(1);
+          expand_d_kernel<<<eg, 256, 0, cx().stream>>>(e);
+        }
+        if (after_launch("solve (pivot-row expansion)")) return -1;
+        ApplyTcArgs u = a;
+        if (lazy_panel && pass == 0) {
+          u.C = Ec; u.c_ss = wc_per_sys; u.M = cmax; u.itiles = cmax / kRowsI;
+          u.units = unitsA; u.nunits_dev = ncount;
+          u.y_rowmap = crow; u.y_rowmap_stride = cmax;
+        } else if (lazy_panel) {
+          u.units = unitsB; u.nunits_dev = ncount + 1;
+        }
+        {
+          TcTimer tt(2);
+          if (tc_launch(u, (!lazy_panel && getenv("OBLAS_B200_TC_STREAM_A")) ? 1 : 0)) return -1;
+        }
       }
     }
     PermuteArgs pm;

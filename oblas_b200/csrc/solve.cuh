@@ -1151,16 +1151,28 @@ struct PanelArgs {
   // vectors, the row map and the candidate flags of the rows
   uint8_t *row_ws;
   size_t row_ws_cta;
+  // ---- lazy outer panels (see the header of panel_kernel): cmax != 0 selects the COMPACT mode ----
+  uint32_t cmax;            // rows of the compact set (multiple of 16, >= 128)
+  uint8_t *Wc;              // [nsys][cmax][128]  scratch: the gathered windows of the compact rows
+  uint8_t *Ec;              // [nsys][cmax][128]  coefficient rows of the compact rows (operand of update launch A)
+  uint16_t *crow;           // [nsys][cmax]       physical rows of the compact set (0xffff beyond its end)
+  uint8_t *flags;           // [nsys]  compact mode: out, 1 = the full kernel has to redo this system's outer panel;
+                            //         full mode with only_flagged: in
+  int only_flagged;         // full mode: systems with flags[sys] == 0 are left alone
+  // unit lists of the two update launches: (sys << 16 | row tile), appended per system; counts zeroed by the host
+  uint32_t *unitsA, *nunitsA, *unitsB, *nunitsB;
+  unsigned long long *stats;   // optional, compact mode: {systems factorised, systems given up} so far
 };
 
 constexpr int kOuterBytes = 128;   // outer panel width (GF(256): bytes == columns)
+constexpr uint32_t kUnitTileRows = 16;   // rows of a row tile of the update kernel (tc::kRowsI)
 
 // per-row state of panel_kernel when it lives in global memory (GROWS): pan + V + row map + flags
 inline size_t panel_row_ws_bytes(uint32_t rows) {
   return ((size_t)rows * 4 * 4 * 2 + ((size_t)rows * 2 + 15) / 16 * 16 + ((size_t)rows + 15) / 16 * 16 + 255) & ~(size_t)255;
 }
 
-template <int KB, int WT, bool GROWS = false>
+template <int KB, int WT, bool GROWS = false, bool COMPACT = false>
 __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
   constexpr int EXP = 8, NBW = 4;
   using SM = SolveSmem<EXP, NBW, KB, WT>;
@@ -1170,7 +1182,8 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
   constexpr uint32_t INNER = kOuterBytes / (NBW * 4);   // inner panels per outer panel (8)
   static_assert(WT == kOuterBytes, "the window and E are one tile each");
   const uint32_t tid = threadIdx.x, T = blockDim.x;
-  const uint32_t rows = p.rows;
+  constexpr bool compact = COMPACT;                   // (p.cmax != 0: launch_panel_t picks the instantiation)
+  const uint32_t srows = compact ? p.cmax : p.rows;   // rows the per-row state is laid out for
 
   OB2_DYN_SMEM(smem_raw);
   unsigned char *sp = smem_raw;
@@ -1178,10 +1191,10 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
   // per-row state: shared memory, or (GROWS: systems of more than ~2700 rows) this CTA's block of the
   // global workspace -- same code, generic pointers; __syncthreads orders the accesses either way
   unsigned char *rp = GROWS ? p.row_ws + (size_t)blockIdx.x * p.row_ws_cta : sp;
-  uint32_t *pan = reinterpret_cast<uint32_t *>(rp);        rp += (size_t)rows * NBW * 4;
-  uint32_t *V = reinterpret_cast<uint32_t *>(rp);          rp += (size_t)rows * NBW * 4;
-  uint16_t *pos2phys = reinterpret_cast<uint16_t *>(rp);   rp += ((size_t)rows * 2 + 15) / 16 * 16;
-  uint8_t *is_cand = reinterpret_cast<uint8_t *>(rp);      rp += ((size_t)rows + 15) / 16 * 16;   // [rows] look-ahead flags
+  uint32_t *pan = reinterpret_cast<uint32_t *>(rp);        rp += (size_t)srows * NBW * 4;
+  uint32_t *V = reinterpret_cast<uint32_t *>(rp);          rp += (size_t)srows * NBW * 4;
+  uint16_t *pos2phys = reinterpret_cast<uint16_t *>(rp);   rp += ((size_t)srows * 2 + 15) / 16 * 16;
+  uint8_t *is_cand = reinterpret_cast<uint8_t *>(rp);      rp += ((size_t)srows + 15) / 16 * 16;   // [rows] look-ahead flags
   if (!GROWS) sp = rp;
   sp = smem_raw + (((size_t)(sp - smem_raw) + 15) & ~(size_t)15);
   uint16_t *piv_phys = reinterpret_cast<uint16_t *>(sp);   sp += ((size_t)NPIV * 2 + 15) / 16 * 16;
@@ -1190,9 +1203,17 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
   uint32_t *scal = reinterpret_cast<uint32_t *>(sp);
   uint8_t *inv_s = reinterpret_cast<uint8_t *>(scal + 36);
   uint32_t *Mb = reinterpret_cast<uint32_t *>(inv_s + 256);          // [128][NBW] pivots' vectors (look-ahead: not in the table area)
+  // compact mode: physical rows of the compact set, its pivots (local rows) and pivot columns (local), and one
+  // membership byte per physical row of the system (panel_compact_extra_bytes)
+  sp = reinterpret_cast<unsigned char *>(Mb) + (size_t)SM::NB * NBW * 4;
+  uint16_t *crow = reinterpret_cast<uint16_t *>(sp);       sp += ((size_t)srows * 2 + 15) / 16 * 16;
+  uint16_t *lpiv = reinterpret_cast<uint16_t *>(sp);       sp += (size_t)kOuterBytes * 2;
+  uint32_t *lpivcols = reinterpret_cast<uint32_t *>(sp);   sp += (size_t)srows * 4;
+  uint32_t *cscal = reinterpret_cast<uint32_t *>(sp);      sp += 16;
+  uint8_t *inset = reinterpret_cast<uint8_t *>(sp);
   if (threadIdx.x == 0) scal[32] = p.red;
   for (uint32_t k = threadIdx.x; k < 256u; k += blockDim.x) inv_s[k] = p.inv[k];
-  for (uint32_t k = threadIdx.x; k < rows; k += blockDim.x) is_cand[k] = 0;
+  for (uint32_t k = threadIdx.x; k < srows; k += blockDim.x) is_cand[k] = 0;
   __syncthreads();
 
   // phase clock (diagnostics only): 0 panel load + clear, 1 factorisation, 2 unit injection and
@@ -1212,19 +1233,53 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
 #ifndef OB2_EMU
   if (p.phase && tid == 0) t_last = clock64();
 #endif
-  const uint32_t npanels = (p.cols + NPIV - 1) / NPIV;
-  const uint32_t win_off = p.outer * kOuterBytes;
-  const uint32_t win_bytes = (p.a_bytes - win_off < (uint32_t)kOuterBytes) ? (p.a_bytes - win_off) : (uint32_t)kOuterBytes;
-
   for (uint32_t sys = blockIdx.x; sys < p.nsys; sys += gridDim.x) {
-    uint8_t *A = p.A + (size_t)sys * p.a_ss;
-    uint8_t *E = p.E + (size_t)sys * rows * kOuterBytes;
-    uint16_t *gmap = p.pos2phys + (size_t)sys * rows;
+    if (!compact && p.only_flagged && p.flags[sys] == 0) continue;   // (uniform) lazy flow: only the systems the compact pass gave up
+    // ---- the view the factorisation below works on: the system itself, or (compact mode) the little system made
+    // of the 128-byte windows of the first `cmax` not yet pivoted rows in position order
+    uint8_t *const Ag = p.A + (size_t)sys * p.a_ss;
+    uint16_t *const gmap = p.pos2phys + (size_t)sys * p.rows;
+    uint8_t *A = Ag;
+    size_t a_rs = p.a_rs;
+    uint32_t rows = p.rows, cols = p.cols, a_bytes = p.a_bytes, outer = p.outer;
+    uint8_t *E = p.E + (size_t)sys * p.rows * kOuterBytes;
     uint16_t *gpiv = p.piv_all + (size_t)sys * kOuterBytes;
-    for (uint32_t r = tid; r < rows; r += T) pos2phys[r] = (p.outer == 0) ? (uint16_t)r : gmap[r];
+    uint32_t *pivcols_sys = p.pivcols ? p.pivcols + (size_t)sys * p.rows : nullptr;
+    uint32_t t = (p.outer == 0) ? 0u : p.tcount[sys];   // uniform
+    const uint32_t t0 = t;
+    const uint32_t gwin_off = p.outer * kOuterBytes;     // the outer panel's window in the rows of the system
+    if (compact) {
+      const uint32_t left = p.rows - t0;
+      rows = left < p.cmax ? left : p.cmax;
+      const bool whole = gwin_off + kOuterBytes <= p.a_bytes && gwin_off + kOuterBytes <= p.cols;
+      if (!whole || rows < (uint32_t)kOuterBytes) {     // (uniform) not a full 128-column panel with 128 rows to take pivots from
+        if (tid == 0) {
+          p.flags[sys] = 1;
+          if (p.stats) atomicAdd(p.stats + 1, 1ull);
+        }
+        continue;
+      }
+      A = p.Wc + (size_t)sys * p.cmax * kOuterBytes;
+      a_rs = kOuterBytes; cols = kOuterBytes; a_bytes = kOuterBytes; outer = 0;
+      E = p.Ec + (size_t)sys * p.cmax * kOuterBytes;
+      gpiv = lpiv;
+      pivcols_sys = lpivcols;
+      t = 0;
+      for (uint32_t l = tid; l < rows; l += T) crow[l] = (p.outer == 0) ? (uint16_t)(t0 + l) : gmap[t0 + l];
+      __syncthreads();
+      for (uint32_t it = tid; it < rows * (kOuterBytes / 16); it += T) {
+        const uint32_t l = it / (kOuterBytes / 16), ch = it % (kOuterBytes / 16);
+        reinterpret_cast<uint4 *>(A)[it] = *reinterpret_cast<const uint4 *>(Ag + (size_t)crow[l] * p.a_rs + gwin_off + ch * 16);
+      }
+      for (uint32_t r = tid; r < rows; r += T) pos2phys[r] = (uint16_t)r;
+    } else {
+      for (uint32_t r = tid; r < rows; r += T) pos2phys[r] = (p.outer == 0) ? (uint16_t)r : gmap[r];
+    }
+    const uint32_t npanels = (cols + NPIV - 1) / NPIV;
+    const uint32_t win_off = outer * kOuterBytes;
+    const uint32_t win_bytes = (a_bytes - win_off < (uint32_t)kOuterBytes) ? (a_bytes - win_off) : (uint32_t)kOuterBytes;
     for (uint32_t it = tid; it < rows * (kOuterBytes / 16); it += T)
       reinterpret_cast<uint4 *>(E)[it] = make_uint4(0, 0, 0, 0);
-    uint32_t t = (p.outer == 0) ? 0u : p.tcount[sys];   // uniform
     uint32_t gcount = 0;                                // pivots of this outer panel so far
     bool pan_ready = false;
     bool la_done = false;          // look-ahead: this step's candidate elimination is already done
@@ -1233,12 +1288,12 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
     tick(4);
 
     for (uint32_t q = 0; q < INNER; q++) {
-      const uint32_t pi = p.outer * INNER + q;
+      const uint32_t pi = outer * INNER + q;
       if (pi >= npanels || t >= rows) break;
       const uint32_t c0 = pi * NPIV;
-      const uint32_t ncols_p = (p.cols - c0 < (uint32_t)NPIV) ? (p.cols - c0) : (uint32_t)NPIV;
+      const uint32_t ncols_p = (cols - c0 < (uint32_t)NPIV) ? (cols - c0) : (uint32_t)NPIV;
       for (uint32_t r = tid; r < rows; r += T) {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(A + (size_t)r * p.a_rs + (size_t)pi * (NBW * 4));
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(A + (size_t)r * a_rs + (size_t)pi * (NBW * 4));
 #pragma unroll
         for (int w = 0; w < NBW; w++) {
           if (!pan_ready) pan[r * NBW + w] = src[w];
@@ -1262,7 +1317,7 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
       } else if (ncols_p == (uint32_t)NPIV && rows - t >= (uint32_t)NPIV && kFastThreads <= T && !p.no_fast_panel) {
         fast = panel_fast<EXP, NBW, SM::T2C>(pan, V, pos2phys, piv_phys, prow, vrow, scal,
                                     reinterpret_cast<uint32_t *>(tab), t, rows, c0,
-                                    p.pivcols ? p.pivcols + (size_t)sys * rows : nullptr, inv_s,
+                                    pivcols_sys, inv_s,
                                     (p.phase && tid == 0) ? acc_pf : nullptr);
       }
       la_done = false;
@@ -1306,7 +1361,7 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
           pos2phys[t] = pos2phys[pos];
           pos2phys[pos] = tmp;
           piv_phys[n] = (uint16_t)ph;
-          if (p.pivcols) p.pivcols[(size_t)sys * rows + t] = c0 + j;
+          if (pivcols_sys) pivcols_sys[t] = c0 + j;
         }
         const uint32_t inv = (uint32_t)inv_s[e];
         if (tid < (uint32_t)NBW) {
@@ -1382,33 +1437,124 @@ __global__ void __launch_bounds__(512, 1) panel_kernel(const PanelArgs p) {
         alt.base2 = E; alt.rs2 = kOuterBytes; alt.split = split;
         // look-ahead: the next inner step is a full 16-column step of this outer panel with enough rows left
         const uint32_t c0n = c0 + NPIV;
-        const bool look_ok = fast && !p.no_look_ahead && next_off != 0xffffffffu && c0n + NPIV <= p.cols &&
+        const bool look_ok = fast && !p.no_look_ahead && next_off != 0xffffffffu && c0n + NPIV <= cols &&
                              rows - t >= (uint32_t)NPIV && kFastThreads < T && (T - kFastThreads) % G::CW == 0;
         if (look_ok) {
           LookAhead lk;
           lk.t_next = t; lk.c0_next = c0n;
-          lk.pivcols_sys = p.pivcols ? p.pivcols + (size_t)sys * rows : nullptr;
+          lk.pivcols_sys = pivcols_sys;
           lk.inv_tab = inv_s; lk.pos2phys = pos2phys; lk.piv_phys = piv_phys;
           lk.prow = prow; lk.vrow = vrow; lk.scal = scal; lk.Mb = Mb; lk.is_cand = is_cand;
-          update_tile<EXP, NBW, KB, WT>(A, p.a_rs, rows, win_off, win_bytes, n, piv_phys, V, tab, p.red, pan, next_off, alt, &lk, &fc);
+          update_tile<EXP, NBW, KB, WT>(A, a_rs, rows, win_off, win_bytes, n, piv_phys, V, tab, p.red, pan, next_off, alt, &lk, &fc);
           la_done = scal[2] == 0;          // uniform: read after the closing barrier of the pass
         } else {
-          update_tile<EXP, NBW, KB, WT>(A, p.a_rs, rows, win_off, win_bytes, n, piv_phys, V, tab, p.red, pan, next_off, alt);
+          update_tile<EXP, NBW, KB, WT>(A, a_rs, rows, win_off, win_bytes, n, piv_phys, V, tab, p.red, pan, next_off, alt);
         }
       } else {
-        update_tile<EXP, NBW, KB, WT>(A, p.a_rs, rows, win_off, win_bytes, n, piv_phys, V, tab, p.red, pan, next_off);
+        update_tile<EXP, NBW, KB, WT>(A, a_rs, rows, win_off, win_bytes, n, piv_phys, V, tab, p.red, pan, next_off);
         update_tile<EXP, NBW, KB, WT>(E, kOuterBytes, rows, 0, kOuterBytes, n, piv_phys, V, tab, p.red, nullptr, 0xffffffffu);
       }
-      pan_ready = next_off != 0xffffffffu && next_off < p.a_bytes;
+      pan_ready = next_off != 0xffffffffu && next_off < a_bytes;
       tick(3);
       gcount += n;
     }
     // own-term cancellation of the outer update: new pivot row = E * P_old, not old ^ E * P_old
     for (uint32_t g2 = tid; g2 < gcount; g2 += T) E[(size_t)gpiv[g2] * kOuterBytes + g2] ^= 1;
-    for (uint32_t r = tid; r < rows; r += T) gmap[r] = pos2phys[r];
-    if (tid == 0) {
-      p.tcount[sys] = t;
-      p.npiv[sys] = gcount;
+    if (!compact) {
+      for (uint32_t r = tid; r < rows; r += T) gmap[r] = pos2phys[r];
+      if (tid == 0) {
+        p.tcount[sys] = t;
+        p.npiv[sys] = gcount;
+      }
+      if (p.unitsB) {   // lazy flow, a system redone by this kernel: update launch B takes all of its row tiles, A none
+        const uint32_t nt = (rows + kUnitTileRows - 1) / kUnitTileRows;
+        if (tid == 0) scal[33] = atomicAdd(p.nunitsB, nt);   // (scal[33..35] are free; the compact scratch does not exist in this mode)
+        __syncthreads();
+        for (uint32_t i = tid; i < nt; i += T) p.unitsB[scal[33] + i] = (sys << 16) | i;
+      }
+      __syncthreads();
+      tick(4);
+      continue;
+    }
+    // ---- compact mode: hand the little system's result back, or give the outer panel up
+    if (gcount != (uint32_t)kOuterBytes) {   // (uniform) a column without a pivot among the compact rows: nothing global was touched
+      if (tid == 0) {
+        p.flags[sys] = 1;
+        if (p.stats) atomicAdd(p.stats + 1, 1ull);
+      }
+      __syncthreads();
+      tick(4);
+      continue;
+    }
+    {
+      const uint32_t R = rows, K = p.rows;
+      uint8_t *const Eg = p.E + (size_t)sys * K * kOuterBytes;
+      uint16_t *const crow_g = p.crow + (size_t)sys * p.cmax;
+      for (uint32_t r = tid; r < K; r += T) inset[r] = 0;
+      if (tid < 3) cscal[tid] = 0;
+      __syncthreads();
+      for (uint32_t l = tid; l < p.cmax; l += T) {
+        if (l < R) {
+          inset[crow[l]] = 1;
+          crow_g[l] = crow[l];
+          gmap[t0 + l] = crow[pos2phys[l]];
+        } else {
+          crow_g[l] = 0xffffu;
+        }
+      }
+      if (p.outer == 0)   // the row map outside the compact positions: still the identity
+        for (uint32_t r = tid; r < K; r += T)
+          if (r < t0 || r >= t0 + R) gmap[r] = (uint16_t)r;
+      for (uint32_t g2 = tid; g2 < (uint32_t)kOuterBytes; g2 += T) {
+        p.piv_all[(size_t)sys * kOuterBytes + g2] = crow[lpiv[g2]];
+        if (p.pivcols) p.pivcols[(size_t)sys * K + t0 + g2] = gwin_off + lpivcols[g2];
+      }
+      if (tid == 0) {
+        p.tcount[sys] = t0 + kOuterBytes;
+        p.npiv[sys] = kOuterBytes;
+        p.flags[sys] = 0;
+        if (p.stats) atomicAdd(p.stats, 1ull);
+      }
+      // coefficient rows beyond the compact set's end are zero (update launch A masks those rows anyway)
+      for (uint32_t it = R * (kOuterBytes / 16) + tid; it < p.cmax * (kOuterBytes / 16); it += T)
+        reinterpret_cast<uint4 *>(E)[it] = make_uint4(0, 0, 0, 0);
+      __syncthreads();
+      // windows: the compact rows get theirs back (unit vectors / zeros) and take no part in update launch B; every
+      // other row's window is its coefficient row with respect to the NEW pivot rows, and becomes zero
+      for (uint32_t it = tid; it < R * (kOuterBytes / 16); it += T) {
+        const uint32_t l = it / (kOuterBytes / 16), ch = it % (kOuterBytes / 16);
+        const size_t ph = crow[l];
+        *reinterpret_cast<uint4 *>(Ag + ph * p.a_rs + gwin_off + ch * 16) = reinterpret_cast<const uint4 *>(A)[it];
+        *reinterpret_cast<uint4 *>(Eg + ph * kOuterBytes + ch * 16) = make_uint4(0, 0, 0, 0);
+      }
+      for (uint32_t it = tid; it < K * (kOuterBytes / 16); it += T) {
+        const uint32_t r = it / (kOuterBytes / 16), ch = it % (kOuterBytes / 16);
+        if (inset[r]) continue;
+        uint4 *w = reinterpret_cast<uint4 *>(Ag + (size_t)r * p.a_rs + gwin_off + ch * 16);
+        *reinterpret_cast<uint4 *>(Eg + (size_t)r * kOuterBytes + ch * 16) = *w;
+        *w = make_uint4(0, 0, 0, 0);
+      }
+      // unit lists: launch A = the row tiles of the compact set (rows through crow), launch B = the physical row
+      // tiles that are not made of compact rows only
+      const uint32_t ntA = (R + kUnitTileRows - 1) / kUnitTileRows, ntB = (K + kUnitTileRows - 1) / kUnitTileRows;
+      for (uint32_t i = tid; i < ntB; i += T) {
+        uint32_t all_in = 1;
+        for (uint32_t k = 0; k < kUnitTileRows && i * kUnitTileRows + k < K; k++) all_in &= inset[i * kUnitTileRows + k];
+        if (!all_in) atomicAdd(&cscal[1], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        cscal[0] = atomicAdd(p.nunitsA, ntA);
+        cscal[2] = atomicAdd(p.nunitsB, cscal[1]);
+        cscal[1] = 0;
+      }
+      __syncthreads();
+      for (uint32_t i = tid; i < ntA; i += T) p.unitsA[cscal[0] + i] = (sys << 16) | i;
+      for (uint32_t i = tid; i < ntB; i += T) {
+        uint32_t all_in = 1;
+        for (uint32_t k = 0; k < kUnitTileRows && i * kUnitTileRows + k < K; k++) all_in &= inset[i * kUnitTileRows + k];
+        if (!all_in) p.unitsB[cscal[2] + atomicAdd(&cscal[1], 1u)] = (sys << 16) | i;
+      }
     }
     __syncthreads();
     tick(4);
@@ -1426,6 +1572,10 @@ inline size_t panel_extra_bytes(uint32_t) { return 0; }   // (Mb and the flags a
 
 // shared memory of panel_kernel: everything (rows <= ~2700), or without the per-row state (GROWS)
 inline size_t panel_smem_bytes(uint32_t rows) { return SolveSmem<8, 4, 6, 128>::bytes(rows) + panel_extra_bytes(rows); }
+// compact mode: crow + lpiv + lpivcols + scalars + one membership byte per row of the system
+inline size_t panel_compact_extra_bytes(uint32_t cmax, uint32_t rows) {
+  return ((size_t)cmax * 2 + 15) / 16 * 16 + (size_t)kOuterBytes * 2 + (size_t)cmax * 4 + 16 + ((size_t)rows + 15) / 16 * 16 + 32;
+}
 inline size_t panel_smem_bytes_grows() { return SolveSmem<8, 4, 6, 128>::bytes(0) + 64; }
 
 template <int KB, int WT>
@@ -1434,9 +1584,23 @@ inline int launch_panel_t(const PanelArgs &p, uint32_t grid, size_t smem_limit, 
   using SM = SolveSmem<8, 4, KB, WT>;
   if (p.rows > 65535u || p.rows == 0) return -1;
   if (threads % SM::G::CW) return -3;
-  const bool grows = p.row_ws != nullptr;
+  const bool grows = p.row_ws != nullptr && p.cmax == 0;
   size_t smem = grows ? SM::bytes(0) + 64 : SM::bytes(p.rows) + panel_extra_bytes(p.rows);
+  if (p.cmax) {   // compact mode: per-row state of cmax rows + the compact set's bookkeeping
+    if (p.cmax % kUnitTileRows || p.cmax < (uint32_t)kOuterBytes || p.nsys > 65535u) return -4;
+    smem = SM::bytes(p.cmax) + panel_compact_extra_bytes(p.cmax, p.rows);
+  } else if (p.unitsB && p.nsys > 65535u) {
+    return -4;
+  }
   if (smem > smem_limit) return -1;
+  if (p.cmax) {
+    auto k = panel_kernel<KB, WT, false, true>;
+#ifndef OB2_EMU
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
+#endif
+    OB2_LAUNCH(k, grid, threads, smem, s, p);
+    return 0;
+  }
   if (grows) {
     auto k = panel_kernel<KB, WT, true>;
 #ifndef OB2_EMU

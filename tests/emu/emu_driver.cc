@@ -213,4 +213,111 @@ int emu_solve_outer(uint8_t *A, size_t a_rs, size_t a_ss, uint32_t rows, uint32_
   return 0;
 }
 
+// The LAZY outer-panel flow (oblas_b200.cu: solve_tc_run, lazy): per outer panel the compact panel_kernel
+// factorises only the windows of the first `cmax` unpivoted rows, systems it gives up are redone by the full
+// kernel, then two updates -- launch A: the compact rows with their coefficient rows against the OLD pivot
+// rows (row tiles through crow), launch B: every other row with its own window as the coefficient row against
+// the NEW pivot rows.  Both updates are CPU loops here that walk the unit lists exactly as update_tc_kernel does.
+int emu_solve_outer_lazy(uint8_t *A, size_t a_rs, size_t a_ss, uint32_t rows, uint32_t cols, uint32_t a_bytes,
+                         uint8_t *B, size_t b_rs, size_t b_ss, uint32_t b_bytes, int32_t *rank,
+                         uint32_t *pivcols, uint32_t nsys, uint32_t grid, uint32_t threads, size_t smem_limit,
+                         int no_fast, uint32_t cmax, uint32_t *stats) {
+  ensure_sets();
+  const DevTableSet &T = g_sets[TS_GF256];
+  auto mul = [&](uint8_t c, uint8_t x) -> uint8_t { return T.lo[c * 16 + (x & 15)] ^ T.hi[c * 16 + (x >> 4)]; };
+  std::vector<uint8_t> E((size_t)nsys * rows * kOuterBytes), Wc((size_t)nsys * cmax * kOuterBytes),
+      Ec((size_t)nsys * cmax * kOuterBytes), flags(nsys);
+  std::vector<uint16_t> maps((size_t)nsys * rows), piv_all((size_t)nsys * kOuterBytes), crow((size_t)nsys * cmax);
+  std::vector<uint32_t> tcount(nsys), npiv(nsys);
+  const uint32_t itiles = (rows + 15) / 16, ctiles = cmax / 16;
+  std::vector<uint32_t> unitsA((size_t)nsys * ctiles), unitsB((size_t)nsys * itiles);
+  uint32_t ncount[2];
+  const uint32_t nouter = (cols + kOuterBytes - 1) / kOuterBytes;
+  if (!B) b_bytes = 0;
+  if (stats) stats[0] = stats[1] = stats[2] = 0;
+  for (uint32_t outer = 0; outer < nouter; outer++) {
+    PanelArgs pa;
+    memset(&pa, 0, sizeof pa);
+    pa.A = A; pa.a_rs = a_rs; pa.a_ss = a_ss; pa.rows = rows; pa.cols = cols; pa.a_bytes = a_bytes;
+    pa.E = E.data(); pa.pos2phys = maps.data(); pa.tcount = tcount.data(); pa.piv_all = piv_all.data();
+    pa.npiv = npiv.data(); pa.pivcols = pivcols; pa.nsys = nsys; pa.outer = outer;
+    pa.inv = T.inv; pa.red = field_red(8, 285); pa.no_fast_panel = no_fast & 1; pa.no_look_ahead = (no_fast >> 1) & 1;
+    pa.Wc = Wc.data(); pa.Ec = Ec.data(); pa.crow = crow.data(); pa.flags = flags.data();
+    pa.unitsA = unitsA.data(); pa.unitsB = unitsB.data(); pa.nunitsA = &ncount[0]; pa.nunitsB = &ncount[1];
+    ncount[0] = ncount[1] = 0;
+    pa.cmax = cmax;
+    int rc = launch_panel_t<6, 128>(pa, grid, smem_limit, nullptr, threads);
+    if (rc) return rc;
+    pa.cmax = 0; pa.only_flagged = 1;
+    rc = launch_panel_t<6, 128>(pa, grid, smem_limit, nullptr, threads);
+    if (rc) return rc;
+    if (stats) {
+      for (uint32_t s = 0; s < nsys; s++) stats[0] += flags[s];
+      stats[1] += ncount[0];
+      stats[2] += ncount[1];
+    }
+    const uint32_t a0 = (outer + 1) * kOuterBytes;
+    const uint32_t wa = a_bytes > a0 ? a_bytes - a0 : 0;
+    const uint32_t wtot = wa + b_bytes;
+    if (wtot == 0) continue;
+    std::vector<std::vector<uint8_t>> P(nsys);
+    auto snapshot = [&]() {   // what expand_d_kernel turns into operand blocks
+      for (uint32_t s = 0; s < nsys; s++) {
+        uint8_t *As = A + (size_t)s * a_ss, *Bs = B ? B + (size_t)s * b_ss : nullptr;
+        P[s].assign((size_t)kOuterBytes * wtot, 0);
+        for (uint32_t g2 = 0; g2 < npiv[s]; g2++) {
+          const uint32_t pr = piv_all[(size_t)s * kOuterBytes + g2];
+          if (wa) memcpy(&P[s][(size_t)g2 * wtot], As + (size_t)pr * a_rs + a0, wa);
+          if (b_bytes) memcpy(&P[s][(size_t)g2 * wtot + wa], Bs + (size_t)pr * b_rs, b_bytes);
+        }
+      }
+    };
+    auto update_row = [&](uint32_t s, uint32_t phys, const uint8_t *e) {
+      uint8_t *As = A + (size_t)s * a_ss, *Bs = B ? B + (size_t)s * b_ss : nullptr;
+      for (uint32_t g2 = 0; g2 < (uint32_t)kOuterBytes; g2++) {
+        const uint8_t c = e[g2];
+        if (!c) continue;
+        const uint8_t *src = &P[s][(size_t)g2 * wtot];
+        uint8_t *ya = As + (size_t)phys * a_rs + a0;
+        for (uint32_t k = 0; k < wa; k++) ya[k] ^= mul(c, src[k]);
+        if (b_bytes) {
+          uint8_t *yb = Bs + (size_t)phys * b_rs;
+          for (uint32_t k = 0; k < b_bytes; k++) yb[k] ^= mul(c, src[wa + k]);
+        }
+      }
+    };
+    snapshot();
+    for (uint32_t u = 0; u < ncount[0]; u++) {   // launch A
+      const uint32_t s = unitsA[u] >> 16, it = unitsA[u] & 0xffffu;
+      for (uint32_t k = 0; k < 16; k++) {
+        const uint32_t l = it * 16 + k;
+        if (l >= cmax) continue;
+        const uint16_t ph = crow[(size_t)s * cmax + l];
+        if (ph == 0xffffu) continue;
+        update_row(s, ph, &Ec[((size_t)s * cmax + l) * kOuterBytes]);
+      }
+    }
+    snapshot();
+    for (uint32_t u = 0; u < ncount[1]; u++) {   // launch B
+      const uint32_t s = unitsB[u] >> 16, it = unitsB[u] & 0xffffu;
+      for (uint32_t k = 0; k < 16; k++) {
+        const uint32_t r = it * 16 + k;
+        if (r >= rows) continue;
+        update_row(s, r, &E[((size_t)s * rows + r) * kOuterBytes]);
+      }
+    }
+  }
+  for (uint32_t s = 0; s < nsys; s++) {   // rows into position order, ranks
+    rank[s] = (int32_t)tcount[s];
+    auto permute = [&](uint8_t *base, size_t rs, uint32_t nbytes) {
+      std::vector<uint8_t> tmp((size_t)rows * nbytes);
+      for (uint32_t i = 0; i < rows; i++) memcpy(&tmp[(size_t)i * nbytes], base + (size_t)maps[(size_t)s * rows + i] * rs, nbytes);
+      for (uint32_t i = 0; i < rows; i++) memcpy(base + (size_t)i * rs, &tmp[(size_t)i * nbytes], nbytes);
+    };
+    permute(A + (size_t)s * a_ss, a_rs, a_bytes);
+    if (B) permute(B + (size_t)s * b_ss, b_rs, b_bytes);
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -281,6 +281,7 @@ def emu():
         lib.emu_solve_outer.argtypes = [u8p, C.c_size_t, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32,
                                         u8p, C.c_size_t, C.c_size_t, C.c_uint32, i32p, u32p, C.c_uint32,
                                         C.c_uint32, C.c_uint32, C.c_size_t, C.c_int]
+        lib.emu_solve_outer_lazy.argtypes = lib.emu_solve_outer.argtypes + [C.c_uint32, u32p]
         _emu = lib
     return _emu
 

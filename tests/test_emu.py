@@ -300,3 +300,60 @@ def test_outer_panel_elimination(args):
         assert np.array_equal(B, B0)
     if deficient:
         assert want[0][0] < min(rows, cols)
+
+
+@pytest.mark.parametrize("args", [
+    # (flagged = outer panels the compact pass gave up and the full kernel redid)
+    dict(rows=300, cols=256, b_bytes=32, seed=500, cmax=144, flagged=0),                 # two full panels, rows beyond the compact set
+    dict(rows=300, cols=256, b_bytes=32, seed=500, cmax=128, flagged=0),                 # smallest compact set
+    dict(rows=300, cols=300, b_bytes=32, seed=501, cmax=160, flagged=1),                 # narrow last panel -> full kernel
+    dict(rows=256, cols=256, b_bytes=48, seed=502, cmax=192, flagged=0),                 # compact set reaches the end of the system
+    dict(rows=320, cols=256, b_bytes=0, seed=503, cmax=144, flagged=0),                  # no right-hand side
+    dict(rows=300, cols=256, b_bytes=32, seed=504, cmax=144, deficient=2, flagged=1),    # free column in panel 0 (redone by the full kernel), a zero row in panel 1
+    dict(rows=300, cols=384, b_bytes=16, seed=505, cmax=144, flagged=1),                 # wide: the third panel has 44 rows left
+    dict(rows=300, cols=256, b_bytes=32, seed=506, cmax=144, sparse=0.25, flagged=None), # many zero entries: pivots swap rows inside the compact set
+    dict(rows=300, cols=256, b_bytes=32, seed=507, cmax=144, nsys=3, grid=2, flagged=0), # persistent loop, unit lists of several systems
+    dict(rows=300, cols=256, b_bytes=32, seed=508, cmax=144, antidiag=True, flagged=1),  # panel 0: pivots far below the compact set (redone); panel 1: right at its top
+    dict(rows=300, cols=256, b_bytes=32, seed=509, cmax=144, swap_far=True, flagged=None),
+])
+def test_lazy_outer_panel_elimination(args):
+    """the LAZY tensor-core elimination: compact outer-panel factorisation (windows of the first cmax unpivoted
+    rows only), full kernel for the panels it gives up, update launch A (compact rows, old pivot rows) and
+    launch B (all other rows with their own window as coefficients, NEW pivot rows) walked through the unit
+    lists on the CPU -- ranks, pivot columns and every byte of A and B against the oracle"""
+    rows, cols, b_bytes, seed, cmax = args["rows"], args["cols"], args["b_bytes"], args["seed"], args["cmax"]
+    nsys, deficient = args.get("nsys", 1), args.get("deficient", 0)
+    e = emu()
+    A = np.stack([random_matrix(GF256, rows, cols, seed + 2 * s, rank_deficient=deficient) for s in range(nsys)])
+    if "sparse" in args:
+        keep = np.random.default_rng(seed).random(A.shape) < args["sparse"]
+        A *= keep.astype(np.uint8)
+    if args.get("antidiag"):
+        for i in range(rows):
+            A[0, i, :max(cols - 1 - i, 0)] = 0
+    if args.get("swap_far"):
+        # the first 130 rows are zero in column 5: its pivot is row 130 (inside a compact set of 144), which puts an
+        # already used row in the middle of the positions the next outer panel takes its compact set from
+        A[0, :130, 5] = 0
+        A[0, 130, 5] = 7
+    B = np.stack([splitmix_bytes(seed + 2 * s + 1, rows * b_bytes).reshape(rows, b_bytes)
+                  for s in range(nsys)]).copy() if b_bytes else None
+    A0, B0 = A.copy(), (B.copy() if B is not None else None)
+    want = [oracle_solve(GF256, A0[s], B0[s] if B0 is not None else None, cols) for s in range(nsys)]
+    rank = np.zeros(nsys, dtype=np.int32)
+    piv = np.full((nsys, rows), 0xFFFFFFFF, dtype=np.uint32)
+    stats = np.zeros(3, dtype=np.uint32)
+    rc = e.emu_solve_outer_lazy(ptr(A), A.strides[1], A.strides[0], rows, cols, A.shape[2],
+                                ptr(B) if B is not None else None, B.strides[1] if B is not None else 0,
+                                B.strides[0] if B is not None else 0, B.shape[2] if B is not None else 0,
+                                ptr(rank, i32p), ptr(piv, u32p), nsys, args.get("grid", 1), args.get("threads", 128), SMEM,
+                                args.get("no_fast", 0), cmax, ptr(stats, u32p))
+    assert rc == 0
+    assert [int(r) for r in rank] == [w[0] for w in want]
+    for s in range(nsys):
+        assert np.array_equal(piv[s][:want[s][0]], want[s][1][:want[s][0]])
+    assert np.array_equal(A, A0)
+    if B is not None:
+        assert np.array_equal(B, B0)
+    if args["flagged"] is not None:
+        assert int(stats[0]) == args["flagged"], stats

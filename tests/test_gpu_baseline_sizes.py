@@ -208,6 +208,7 @@ def test_elimination_in_several_chunks_of_systems(cuda_lib):
     A[6, :, 130] = 0
     B = np.stack([splitmix_bytes(9300 + s, K * L).reshape(K, L) for s in range(nsys)]).copy()
     per_sys = 4 * 16 * 7680 + K * 128 + K * 2 + 272
+    per_sys += 2 * 192 * 128 + 192 * 2 + 16 + (192 // 16 + K // 16) * 4    # lazy outer panels, compact sets of 192 rows
     old = cuda_lib.oblas_b200_set_workspace_budget(2 * per_sys + 4096)
     try:
         cuda_lib.oblas_b200_set_tuning(3, -1)
@@ -215,9 +216,10 @@ def test_elimination_in_several_chunks_of_systems(cuda_lib):
         dA, dB = dev(A), dev(B)
         rank, piv = device.solve_batch(GF256, dA, K, dB, want_pivcols=True)
         device.sync()
-        ms, n = (C.c_double * 4)(), (C.c_uint64 * 4)()
-        cuda_lib.oblas_b200_solve_tc_times(0, ms, n)
-        assert n[3] == 4 and n[0] == 4 * 5, list(n)      # 4 chunks x (5 outer panels + 1 permutation)
+        ms, n = (C.c_double * 5)(), (C.c_uint64 * 5)()
+        cuda_lib.oblas_b200_solve_tc_times_ex(0, ms, n, 5)
+        # 4 chunks x (5 outer panels: compact pass + the full kernel's pass over what it gave up, + 1 permutation)
+        assert n[3] == 4 and n[0] == 4 * 5 and n[4] == 4 * 5, list(n)
     finally:
         cuda_lib.oblas_b200_set_workspace_budget(old)
         cuda_lib.oblas_b200_set_tuning(-1, -1)
@@ -410,3 +412,46 @@ def test_raptorq_scale_solve_k10000_roundtrip():
     rng = np.random.default_rng(1)
     for r in rng.choice(K, 5, replace=False):
         assert np.array_equal(gf256_vecmat(Ao[r], X), Bo[r]), r
+
+
+def test_lazy_outer_panels_counters_and_equality(cuda_lib):
+    """lazy outer panels (compact sets of 192 / 128 rows) against the full outer-panel kernel on the same batch:
+    identical bytes, ranks and pivot columns; the counters say which (system, outer panel) pairs the compact
+    pass factorised and which it gave up -- the rank-deficient panels and the one whose pivots lie far down."""
+    K, L, nsys = 512, 272, 40
+    A = np.stack([random_matrix(GF256, K, K, 9600 + s) for s in range(nsys)])
+    A[5, :, 200] = 0              # free column in outer panel 1
+    A[9, 300] = A[9, 2]           # duplicate row: a zero row from outer panel 0 on (no give-up: it is never needed)
+    A[11, :400, 130] = 0          # column 130: first non-zero entry in row >= 400, far below the compact set of panel 1
+    A[11, 400, 130] = 9
+    B = np.stack([splitmix_bytes(9700 + s, K * L).reshape(K, L) for s in range(nsys)]).copy()
+    out = {}
+    try:
+        cuda_lib.oblas_b200_set_tuning(3, -1)
+        for lazy in (0, 192, 128):
+            cuda_lib.oblas_b200_set_lazy_panels(lazy)
+            st = (C.c_uint64 * 2)()
+            cuda_lib.oblas_b200_lazy_stats(st, 1)
+            dA, dB = dev(A), dev(B)
+            rank, piv = device.solve_batch(GF256, dA, K, dB, want_pivcols=True)
+            device.sync()
+            cuda_lib.oblas_b200_lazy_stats(st, 1)
+            out[lazy] = (host(dA), host(dB), host(rank), host(piv), (int(st[0]), int(st[1])))
+    finally:
+        cuda_lib.oblas_b200_set_tuning(-1, -1)
+        cuda_lib.oblas_b200_set_lazy_panels(-1)
+    assert out[0][4] == (0, 0)
+    for lazy in (192, 128):
+        for k in range(4):
+            assert np.array_equal(out[0][k], out[lazy][k]), (lazy, k)
+        compact, given_up = out[lazy][4]
+        assert compact + given_up == nsys * 4
+        # system 5: panel 1 (free column) and every later panel (127 + 128 k pivots: a panel of 128 columns with only ...
+        # rows left is still fine) -- at least the one panel; system 11: panel 1
+        assert 2 <= given_up <= 8, out[lazy][4]
+    A0, B0 = A.copy(), B.copy()
+    for s in (0, 5, 9, 11):
+        rk, pv = oracle_solve(GF256, A0[s], B0[s], K)
+        assert int(out[192][2][s]) == rk
+        assert np.array_equal(out[192][0][s], A0[s]) and np.array_equal(out[192][1][s], B0[s])
+        assert np.array_equal(out[192][3][s][:rk].astype(np.uint32), pv[:rk])

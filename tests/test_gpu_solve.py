@@ -20,19 +20,25 @@ ROOT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", autouse=True, params=[(-1, 0), (0, 0), (1, 0), (2, 0), (4, 0), (-1, 1), (3, 0), (3, 1)],
-                ids=["auto", "geo4x256", "geo6x128", "geo7x64", "geo5x128", "general_panel_path", "tcgen05", "tcgen05_general_panel"])
+@pytest.fixture(scope="module", autouse=True,
+                params=[(-1, 0, -1), (0, 0, -1), (1, 0, -1), (2, 0, -1), (4, 0, -1), (-1, 1, -1), (3, 0, -1), (3, 1, -1),
+                        (3, 0, 0), (3, 0, 128), (3, 1, 144)],
+                ids=["auto", "geo4x256", "geo6x128", "geo7x64", "geo5x128", "general_panel_path", "tcgen05", "tcgen05_general_panel",
+                     "tcgen05_full_panels", "tcgen05_lazy128", "tcgen05_lazy144_general_panel"])
 def _bind(cuda_lib, request):
     """every test of this module runs once per Four-Russians table geometry, once with the
     register-resident fast panel factorisation disabled, and (GF(256)) on the tensor-core path
-    (outer panels of 128 columns + tcgen05 rank-128 updates) with both panel factorisations"""
+    (outer panels of 128 columns + tcgen05 rank-128 updates) with both panel factorisations, with the lazy
+    outer panels (default: compact sets of 192 rows; 128 and 144 rows) and with them off"""
     device.bind(0)
-    geo, general = request.param
+    geo, general, lazy = request.param
     cuda_lib.oblas_b200_set_tuning(geo, geo)
     cuda_lib.oblas_b200_set_panel_path(general)
+    cuda_lib.oblas_b200_set_lazy_panels(lazy)
     yield
     cuda_lib.oblas_b200_set_tuning(-1, -1)
     cuda_lib.oblas_b200_set_panel_path(0)
+    cuda_lib.oblas_b200_set_lazy_panels(-1)
 
 
 def _batch(field, rows, cols, b_bytes, seed, nsys, deficient_every=0):

@@ -22,7 +22,11 @@ B0 = torch.empty((nsys, K, L), dtype=torch.uint8, device="cuda")
 device.fill_random(A0, 1)
 device.fill_random(B0, 2)
 lib.oblas_b200_set_tuning(3, -1)
-names = ["panel", "expand", "update", "permute"]
+if os.environ.get("LAZY") is not None:   # LAZY=0: full outer-panel kernel; LAZY=n: compact sets of n rows
+    lib.oblas_b200_set_lazy_panels(int(os.environ["LAZY"]))
+if os.environ.get("PHASES"):
+    lib.oblas_b200_solve_phases(1, None)
+names = ["panel", "expand", "update", "permute", "panel-redo"]
 for it in range(3):
     A, B = A0.clone(), B0.clone()
     lib.oblas_b200_solve_tc_times(1, None, None)
@@ -31,9 +35,9 @@ for it in range(3):
     r, _ = device.solve_batch(capi.GF256, A, K, B)
     e1.record()
     torch.cuda.synchronize()
-    ms = (C.c_double * 4)()
-    n = (C.c_uint64 * 4)()
-    lib.oblas_b200_solve_tc_times(0, ms, n)
+    ms = (C.c_double * 5)()
+    n = (C.c_uint64 * 5)()
+    lib.oblas_b200_solve_tc_times_ex(0, ms, n, 5)
     rc = lib.oblas_b200_sync()
 if os.environ.get("UPROF"):
     import numpy as np
@@ -50,4 +54,13 @@ if os.environ.get("UPROF"):
 tot = e0.elapsed_time(e1)
 print("dbg=%s nsys=%d K=%d L=%d: %.2f ms, %.0f solves/s, full rank %d, sync rc %d | " % (
     os.environ.get("OBLAS_B200_TC_DEBUG", "0"), nsys, K, L, tot, nsys / tot * 1e3, int((r == K).sum()), rc) +
-    ", ".join("%s %.2f ms/%d" % (names[k], ms[k], n[k]) for k in range(4)))
+    ", ".join("%s %.2f ms/%d" % (names[k], ms[k], n[k]) for k in range(5)))
+st = (C.c_uint64 * 2)()
+lib.oblas_b200_lazy_stats(st, 0)
+print("lazy outer panels: %d (system, panel) pairs compact, %d given up" % (st[0], st[1]))
+if os.environ.get("PHASES"):
+    import numpy as np
+    ph = np.zeros(8, dtype=np.uint64)
+    lib.oblas_b200_solve_phases(0, ph.ctypes.data)
+    print("panel kernel phase cycles (sum over CTAs, 3 runs + clones): load %d fact %d inject %d pass %d pro/epilogue %d | cand %d tables %d vprod %d" % tuple(int(x) for x in ph))
+
