@@ -89,7 +89,7 @@ struct Ctx {
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> tc_events;  // (class, (start, stop))
   int no_fast_panel = 0;               // diagnostics: general panel path only
   unsigned long long *d_lazy_stats = nullptr;   // {compact, given up} (system, outer panel) pairs
-  int tc_lazy_rows = 192;              // tensor-core elimination: rows of the compact set of the lazy outer panels, 0 = off
+  int tc_lazy_rows = 0;                // tensor-core elimination: rows of the compact set of the lazy outer panels, 0 = off (the default: measured 2 % slower than the full outer-panel kernel)
   unsigned long long *d_phase = nullptr;  // solve-kernel phase counters (diagnostics)
   unsigned long long *d_uprof = nullptr;  // update_tc_kernel role counters (diagnostics)
   DevTableSet *d_sets = nullptr;  // [TS_COUNT] in device memory
@@ -489,7 +489,7 @@ void oblas_b200_set_panel_path(int general_only) { cx().no_fast_panel = general_
 // Lazy outer panels of the tensor-core elimination (solve_tc_run): compact_rows = rows of the compact set
 // (rounded up to a multiple of 16, at least 128), 0 = off (every outer panel factorised over all rows), < 0 = default
 void oblas_b200_set_lazy_panels(int compact_rows) {
-  if (compact_rows < 0) compact_rows = 192;
+  if (compact_rows < 0) compact_rows = 0;
   if (compact_rows > 0) {
     if (compact_rows < 128) compact_rows = 128;
     if (compact_rows > 1024) compact_rows = 1024;

@@ -209,6 +209,7 @@ def test_elimination_in_several_chunks_of_systems(cuda_lib):
     B = np.stack([splitmix_bytes(9300 + s, K * L).reshape(K, L) for s in range(nsys)]).copy()
     per_sys = 4 * 16 * 7680 + K * 128 + K * 2 + 272
     per_sys += 2 * 192 * 128 + 192 * 2 + 16 + (192 // 16 + K // 16) * 4    # lazy outer panels, compact sets of 192 rows
+    cuda_lib.oblas_b200_set_lazy_panels(192)   # (off by default: the lazy flow has the bigger workspace and more launch classes)
     old = cuda_lib.oblas_b200_set_workspace_budget(2 * per_sys + 4096)
     try:
         cuda_lib.oblas_b200_set_tuning(3, -1)
@@ -220,6 +221,23 @@ def test_elimination_in_several_chunks_of_systems(cuda_lib):
         cuda_lib.oblas_b200_solve_tc_times_ex(0, ms, n, 5)
         # 4 chunks x (5 outer panels: compact pass + the full kernel's pass over what it gave up, + 1 permutation)
         assert n[3] == 4 and n[0] == 4 * 5 and n[4] == 4 * 5, list(n)
+    finally:
+        cuda_lib.oblas_b200_set_workspace_budget(old)
+        cuda_lib.oblas_b200_set_tuning(-1, -1)
+        cuda_lib.oblas_b200_set_lazy_panels(-1)
+    # the same batch with the default flow (full outer panels), also in chunks of two systems
+    per_sys0 = 4 * 16 * 7680 + K * 128 + K * 2 + 272
+    old = cuda_lib.oblas_b200_set_workspace_budget(2 * per_sys0 + 4096)
+    try:
+        cuda_lib.oblas_b200_set_tuning(3, -1)
+        cuda_lib.oblas_b200_solve_tc_times(1, None, None)
+        fA, fB = dev(A), dev(B)
+        frank, fpiv = device.solve_batch(GF256, fA, K, fB, want_pivcols=True)
+        device.sync()
+        ms, n = (C.c_double * 5)(), (C.c_uint64 * 5)()
+        cuda_lib.oblas_b200_solve_tc_times_ex(0, ms, n, 5)
+        assert n[3] == 4 and n[0] == 4 * 5 and n[4] == 0, list(n)
+        assert torch.equal(rank, frank) and torch.equal(piv, fpiv) and torch.equal(dA, fA) and torch.equal(dB, fB)
     finally:
         cuda_lib.oblas_b200_set_workspace_budget(old)
         cuda_lib.oblas_b200_set_tuning(-1, -1)
@@ -455,3 +473,4 @@ def test_lazy_outer_panels_counters_and_equality(cuda_lib):
         assert int(out[192][2][s]) == rk
         assert np.array_equal(out[192][0][s], A0[s]) and np.array_equal(out[192][1][s], B0[s])
         assert np.array_equal(out[192][3][s][:rk].astype(np.uint32), pv[:rk])
+
