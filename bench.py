@@ -784,6 +784,13 @@ def solve_config(name, field, K, nsys_total, L_, capi, device, torch, dist, worl
     path = C.c_int(0)
     capi.check(L_.oblas_b200_solve_plan(field, K, K, a_bytes, 0, n, C.byref(path), None, geo), "solve_plan")
     nbw, kb, wt = int(geo[0]), int(geo[1]), int(geo[2])
+    # tall systems keep the 128-bit panels with the per-row state in a global workspace (solve_kernel<.., GROWS>):
+    # that is the case if the plan changes when the mode is switched off
+    geo0 = (C.c_int * 4)()
+    L_.oblas_b200_set_tall_mode(0)
+    rc0 = L_.oblas_b200_solve_plan(field, K, K, a_bytes, 0, n, C.byref(path), None, geo0)
+    L_.oblas_b200_set_tall_mode(1)
+    grows = rc0 != 0 or [int(x) for x in geo0[:3]] != [nbw, kb, wt]
     # executed look-ups: per panel of 32*NBW coefficient bits every row streams the bytes right of the panel,
     # NG = ceil(32*NBW / KB) look-ups per 16-byte chunk
     pan_bytes = 4 * nbw
@@ -797,7 +804,8 @@ def solve_config(name, field, K, nsys_total, L_, capi, device, torch, dist, worl
     res = {"config": name, "metric": "solves/s", "value": nsys_total / (ms / 1e3), "unit": "solves/s", "n_gpus": world,
            "scaling": "strong (fixed batch sharded by systems)", "ms_per_batch": ms, "systems": nsys_total, "K": K,
            "field_bits": bits, "row_bytes": a_bytes,
-           "kernel": "ob2::solve_kernel<EXP=%d, NBW=%d, KB=%d, WT=%d>" % (bits, nbw, kb, wt),
+           "kernel": "ob2::solve_kernel<EXP=%d, NBW=%d, KB=%d, WT=%d%s>" % (bits, nbw, kb, wt, ", GROWS" if grows else ""),
+           "per_row_state": "per-CTA block of global memory (L2)" if grows else "shared memory",
            "roofline": {"bound": "shared-memory look-up bandwidth (LDS.128, 8 per clk per SM measured: "
                                  "profiles/r01_peaks_b200.jsonl)", "unit": "T look-ups/s",
                         "achieved": ach / 1e12, "peak": peak_lookups / 1e12, "frac": ach / peak_lookups,

@@ -165,6 +165,10 @@ void oblas_b200_set_lazy_panels(int compact_rows);
 /* out[0] = (system, outer panel) pairs factorised by the compact pass so far, out[1] = pairs it gave up;
  * reset != 0 clears the counters */
 int oblas_b200_lazy_stats(uint64_t *out, int reset);
+/* Shared-memory table kernel, systems too tall for 128-bit panels in shared memory (GF(2) K = 8192 ...): mode 1
+ * (default) keeps the 128-bit panels and the big tables and holds the per-row state (35 bytes per row) in a per-CTA
+ * block of global memory; mode 0 falls back to 64-bit panels in shared memory.  Results are identical. */
+void oblas_b200_set_tall_mode(int mode);
 /* number of kernels this library has launched so far */
 uint64_t oblas_b200_launch_count(void);
 

@@ -80,6 +80,8 @@ def lib():
     L.oblas_b200_solve_tc_times_ex.argtypes = [ci, C.POINTER(C.c_double), C.POINTER(C.c_uint64), ci]
     L.oblas_b200_solve_tc_times_ex.restype = ci
     L.oblas_b200_set_lazy_panels.argtypes = [ci]
+    L.oblas_b200_set_tall_mode.argtypes = [ci]
+    L.oblas_b200_set_tall_mode.restype = None
     L.oblas_b200_lazy_stats.argtypes = [C.POINTER(u64), ci]
     L.oblas_b200_lazy_stats.restype = ci
     L.oblas_b200_solve_phases.argtypes = [ci, vp]
@@ -213,7 +215,7 @@ TABLE_SYMBOLS = {
 EXTENSION_SYMBOLS = [
     "oblas_b200_init", "oblas_b200_set_device", "oblas_b200_set_workspace_budget", "oblas_b200_set_wait_limit_ms", "oblas_b200_set_fault_injection", "oblas_b200_shutdown", "oblas_b200_device", "oblas_b200_sm_count",
     "oblas_b200_last_error", "oblas_b200_set_stream", "oblas_b200_use_own_stream", "oblas_b200_get_stream", "oblas_b200_sync",
-    "oblas_b200_set_async", "oblas_b200_queue_stats", "oblas_b200_set_tuning", "oblas_b200_solve_tc_times", "oblas_b200_solve_tc_times_ex", "oblas_b200_set_lazy_panels", "oblas_b200_lazy_stats", "oblas_b200_set_panel_path", "oblas_b200_solve_phases", "oblas_b200_update_phases", "oblas_b200_launch_count", "oblas_b200_dev_alloc", "oblas_b200_dev_free",
+    "oblas_b200_set_async", "oblas_b200_queue_stats", "oblas_b200_set_tuning", "oblas_b200_solve_tc_times", "oblas_b200_solve_tc_times_ex", "oblas_b200_set_lazy_panels", "oblas_b200_set_tall_mode", "oblas_b200_lazy_stats", "oblas_b200_set_panel_path", "oblas_b200_solve_phases", "oblas_b200_update_phases", "oblas_b200_launch_count", "oblas_b200_dev_alloc", "oblas_b200_dev_free",
     "oblas_b200_host_alloc", "oblas_b200_host_free", "oblas_b200_managed_alloc", "oblas_b200_free",
     "oblas_b200_copy", "oblas_b200_memset", "oblas_b200_fill_random", "oblas_b200_rowops",
     "oblas_b200_solve_batch", "oblas_b200_solve_plan", "oblas_b200_solve_batch_host", "oblas_b200_solve_batch_host_ex", "oblas_b200_solve_batch_host_multi", "oblas_b200_gf256_apply_sharded", "oblas_b200_device_count", "oblas_b200_gf256_apply", "oblas_b200_gf256_apply_b32",

@@ -88,6 +88,7 @@ struct Ctx {
   bool tc_timing = false;
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> tc_events;  // (class, (start, stop))
   int no_fast_panel = 0;               // diagnostics: general panel path only
+  int solve_tall = 1;                  // table kernel: per-row state in a global workspace when 128-bit panels do not fit shared memory (oblas_b200_set_tall_mode)
   unsigned long long *d_lazy_stats = nullptr;   // {compact, given up} (system, outer panel) pairs
   int tc_lazy_rows = 0;                // tensor-core elimination: rows of the compact set of the lazy outer panels, 0 = off (the default: measured 2 % slower than the full outer-panel kernel)
   unsigned long long *d_phase = nullptr;  // solve-kernel phase counters (diagnostics)
@@ -497,6 +498,10 @@ void oblas_b200_set_lazy_panels(int compact_rows) {
   }
   cx().tc_lazy_rows = compact_rows;
 }
+// Table kernel, systems whose per-row state does not fit shared memory beside the tables of the 128-bit panels:
+// 1 (default) = keep the 128-bit panels and hold the per-row state in a global workspace, 0 = 64-bit panels in
+// shared memory (the behaviour before; rows <= ~9800)
+void oblas_b200_set_tall_mode(int mode) { cx().solve_tall = mode ? 1 : 0; }
 void oblas_b200_set_tuning(int solve_geo, int apply_geo) {
   cx().solve_geo = solve_geo;
   cx().apply_geo = apply_geo;
@@ -725,6 +730,7 @@ int oblas_b200_rowops(int field, int variant, int op, int mul_mode, void *a, siz
 
 // ---- elimination -----------------------------------------------------------------
 int solve_tc_run(SolveArgs &p, size_t nsys);   // tensor-core path (GF(256)), defined with apply_tc_run
+int tc_ws_reserve(size_t need);                // per-stream workspace slot, defined with the tensor-core host code
 static bool solve_tc_eligible(int field, const SolveArgs &p, size_t nsys) {
   if (field != OB2_GF256 || p.a_ptrs || p.b_ptrs) return false;
   // rows: u16 row map; the final row permutation stages at least 16 bytes of every row in shared memory.
@@ -775,7 +781,29 @@ static int solve_common(int field, SolveArgs &p, size_t nsys) {
   p.no_look_ahead = (cx().no_fast_panel >> 1) & 1;
   if (solve_tc_eligible(field, p, nsys)) return solve_tc_run(p, nsys);
   uint32_t grid = nsys < (size_t)cx().sm_count ? (uint32_t)nsys : (uint32_t)cx().sm_count;
-  int rc = launch_solve(field, cx().solve_geo == 3 ? -1 : cx().solve_geo, p, grid, 512, cx().smem_optin, cx().stream);
+  const int geo = cx().solve_geo == 3 ? -1 : cx().solve_geo;
+  // Tall systems (rows x 35 bytes of per-row state do not fit beside the tables of the 128-bit panels): rather than
+  // 64-bit panels in shared memory, 128-bit panels with the per-row state in a per-CTA block of global memory
+  if (cx().solve_tall && (geo < 0 || geo == 1 || geo == 4) && !p.a_ptrs && !p.b_ptrs) {
+    int plan[3] = {0, 0, 0};
+    const bool fits = plan_solve(field, geo, p.rows, cx().smem_optin, plan);
+    const int ggeo = geo == 4 ? 4 : 1;
+    if ((!fits || plan[0] != 4) && solve_grows_fits(p.rows, ggeo)) {
+      const size_t per_cta = solve_row_ws_bytes<4>(p.rows);
+      const int wrc = tc_ws_reserve(per_cta * grid + 256);
+      if (wrc < 0) return -1;
+      if (wrc == 0) {
+        p.row_ws = (uint8_t *)(((uintptr_t)cx().tc_ws + 255) & ~(uintptr_t)255);
+        p.row_ws_cta = per_cta;
+        int rc = launch_solve_grows(field, ggeo, p, grid, 512, cx().smem_optin, cx().stream);
+        if (rc == 0) return after_launch("solve (tall)");
+        if (rc != -1) return fail("solve: cudaFuncSetAttribute failed");
+        p.row_ws = nullptr;
+        p.row_ws_cta = 0;
+      }
+    }
+  }
+  int rc = launch_solve(field, geo, p, grid, 512, cx().smem_optin, cx().stream);
   if (rc == -1)
     return fail("solve: %u rows do not fit the shared-memory panel (limit %zu bytes); no fallback", p.rows, cx().smem_optin);
   if (rc) return fail("solve: cudaFuncSetAttribute failed");
@@ -1334,8 +1362,15 @@ extern "C" int oblas_b200_solve_plan(int field, uint32_t rows, uint32_t cols, si
     geometry[0] = geometry[1] = geometry[2] = 0;
     if (tc) {   // the outer-panel kernel: 128-bit inner panels, 6-bit groups, one 128-byte tile
       geometry[0] = 4; geometry[1] = 6; geometry[2] = 128;
-    } else if (!plan_solve(field, cx().solve_geo == 3 ? -1 : cx().solve_geo, rows, cx().smem_optin, geometry)) {
-      return fail("solve_plan: %u rows do not fit the shared-memory panel (limit %zu bytes); no fallback", rows, cx().smem_optin);
+    } else {
+      const int geo = cx().solve_geo == 3 ? -1 : cx().solve_geo;
+      const bool fits = plan_solve(field, geo, rows, cx().smem_optin, geometry);
+      const int ggeo = geo == 4 ? 4 : 1;
+      if (cx().solve_tall && (geo < 0 || geo == 1 || geo == 4) && (!fits || geometry[0] != 4) && solve_grows_fits(rows, ggeo)) {
+        geometry[0] = 4; geometry[1] = ggeo == 4 ? 5 : 6; geometry[2] = 128;   // per-row state in global memory
+      } else if (!fits) {
+        return fail("solve_plan: %u rows do not fit the shared-memory panel (limit %zu bytes); no fallback", rows, cx().smem_optin);
+      }
     }
   }
   return 0;

@@ -64,6 +64,11 @@ struct SolveArgs {
   unsigned long long *phase;
   int no_fast_panel;  // diagnostics/tests: always use the general column-by-column panel path
   int no_look_ahead;   // outer-panel kernel only: see PanelArgs
+  // systems whose per-row state (panel chunk, coefficient vector, row map, candidate flag: 2 * 4 * NBW + 3 bytes
+  // per row) does not fit shared memory beside the tables of the 128-bit panels (solve_kernel<.., GROWS = true>):
+  // a block of solve_row_ws_bytes(rows) bytes per CTA in global memory (L2 resident) holds it
+  uint8_t *row_ws;
+  size_t row_ws_cta;
 };
 
 // Tile / table geometry.  NB = 32*NBW panel bits are cut into groups of KB bits
@@ -864,7 +869,16 @@ OB2_D bool panel_fast(uint32_t *pan, uint32_t *V, uint16_t *pos2phys, uint16_t *
   return true;
 }
 
-template <int EXP, int NBW, int KB, int WT>
+// per-row state of solve_kernel when it lives in global memory (GROWS): pan + V + row map + flags
+template <int NBW>
+inline size_t solve_row_ws_bytes(uint32_t rows) {
+  return ((size_t)rows * NBW * 4 * 2 + ((size_t)rows * 2 + 15) / 16 * 16 + ((size_t)rows + 15) / 16 * 16 + 255) & ~(size_t)255;
+}
+
+// GROWS: the per-row state lives in this CTA's block of a global workspace (same code, generic pointers), so that
+// tall systems keep the 128-bit panels and the big tables instead of falling to 64-bit panels: half the streaming
+// passes over the matrix and 22 instead of 32 look-ups per 128 coefficient bits (GF(2), K = 8192).
+template <int EXP, int NBW, int KB, int WT, bool GROWS = false>
 __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
   using SM = SolveSmem<EXP, NBW, KB, WT>;
   using G = Geo<NBW, KB, WT>;
@@ -876,17 +890,20 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
   OB2_DYN_SMEM(smem_raw);
   unsigned char *sp = smem_raw;
   uint4 *tab = reinterpret_cast<uint4 *>(sp);              sp += G::TAB_BYTES;
-  uint32_t *pan = reinterpret_cast<uint32_t *>(sp);        sp += (size_t)rows * NBW * 4;
-  uint32_t *V = reinterpret_cast<uint32_t *>(sp);          sp += (size_t)rows * NBW * 4;
-  sp = smem_raw + (((size_t)(sp - smem_raw) + 15) & ~(size_t)15);
-  uint16_t *pos2phys = reinterpret_cast<uint16_t *>(sp);   sp += ((size_t)rows * 2 + 15) / 16 * 16;
+  unsigned char *rp = GROWS ? p.row_ws + (size_t)blockIdx.x * p.row_ws_cta : sp;
+  uint32_t *pan = reinterpret_cast<uint32_t *>(rp);        rp += (size_t)rows * NBW * 4;
+  uint32_t *V = reinterpret_cast<uint32_t *>(rp);          rp += (size_t)rows * NBW * 4;
+  if (!GROWS) rp = smem_raw + (((size_t)(rp - smem_raw) + 15) & ~(size_t)15);
+  uint16_t *pos2phys = reinterpret_cast<uint16_t *>(rp);   rp += ((size_t)rows * 2 + 15) / 16 * 16;
+  uint8_t *is_cand_g = reinterpret_cast<uint8_t *>(rp);    // GROWS: [rows] look-ahead flags
+  if (!GROWS) sp = rp;
   uint16_t *piv_phys = reinterpret_cast<uint16_t *>(sp);   sp += ((size_t)NPIV * 2 + 15) / 16 * 16;
   uint32_t *prow = reinterpret_cast<uint32_t *>(sp);       sp += (size_t)EXP * NBW * 4;   // x^b * pivot row (panel part)
   uint32_t *vrow = reinterpret_cast<uint32_t *>(sp);       sp += (size_t)EXP * NBW * 4;   // x^b * its V
   uint32_t *scal = reinterpret_cast<uint32_t *>(sp);       // [0] search result, [1] flag
   uint8_t *inv_s = reinterpret_cast<uint8_t *>(scal + 36);  // field inverses (a global load per pivot is 1/3 of a column step)
   uint32_t *Mb = reinterpret_cast<uint32_t *>(inv_s + 256);   // [NB][NBW] pivots' vectors of the look-ahead (not in the table area)
-  uint8_t *is_cand = reinterpret_cast<uint8_t *>(Mb + NB * NBW);   // [rows] look-ahead flags
+  uint8_t *is_cand = GROWS ? is_cand_g : reinterpret_cast<uint8_t *>(Mb + NB * NBW);   // [rows] look-ahead flags
   if (threadIdx.x == 0) scal[32] = p.red;
   if (EXP > 1)
     for (uint32_t k = threadIdx.x; k < (1u << EXP); k += blockDim.x) inv_s[k] = p.inv[k];
@@ -911,7 +928,7 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(const SolveArgs p) {
 #endif
   const uint32_t npanels = (p.cols * EXP + NB - 1) / NB;
   // staging area of the final row permutation: tables + panel + V (all dead then)
-  const uint32_t stage_bytes = (uint32_t)G::TAB_BYTES + rows * NBW * 8;
+  const uint32_t stage_bytes = GROWS ? (uint32_t)G::TAB_BYTES : (uint32_t)G::TAB_BYTES + rows * NBW * 8;
 
   for (uint32_t sys = blockIdx.x; sys < p.nsys; sys += gridDim.x) {
     uint8_t *A = p.a_ptrs ? reinterpret_cast<uint8_t *>(p.a_ptrs[sys]) : p.A + (size_t)sys * p.a_ss;
@@ -1663,15 +1680,16 @@ __global__ void __launch_bounds__(512, 1) permute_kernel(const PermuteArgs p) {
 }
 
 // rows limit: shared memory (SolveSmem::bytes <= 227 KB) and the u16 row map.
-template <int EXP, int NBW, int KB, int WT>
+template <int EXP, int NBW, int KB, int WT, bool GROWS = false>
 inline int launch_solve_t(const SolveArgs &p, uint32_t grid, uint32_t threads,
                           size_t smem_limit, cudaStream_t s) {
   using SM = SolveSmem<EXP, NBW, KB, WT>;
-  size_t smem = SM::bytes(p.rows);
-  size_t stage = SM::G::TAB_BYTES + (size_t)p.rows * NBW * 8;
+  size_t smem = GROWS ? SM::bytes(0) + 64 : SM::bytes(p.rows);
+  size_t stage = GROWS ? SM::G::TAB_BYTES : SM::G::TAB_BYTES + (size_t)p.rows * NBW * 8;
   if (smem > smem_limit || p.rows > 65535u || p.rows == 0 || stage / p.rows < 16) return -1;
+  if (GROWS && (!p.row_ws || p.row_ws_cta < solve_row_ws_bytes<NBW>(p.rows))) return -1;
   if (threads % SM::G::CW) return -3;
-  auto k = solve_kernel<EXP, NBW, KB, WT>;
+  auto k = solve_kernel<EXP, NBW, KB, WT, GROWS>;
 #ifndef OB2_EMU
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return -2;
@@ -1690,6 +1708,28 @@ inline int launch_solve_geo(int geo, const SolveArgs &p, uint32_t grid, uint32_t
   case 4: return launch_solve_t<EXP, NBW, 5, 128>(p, grid, threads, smem_limit, s);
   default: return launch_solve_t<EXP, NBW, 4, 256>(p, grid, threads, smem_limit, s);
   }
+}
+
+// Tall systems: 128-bit panels with the per-row state in the global workspace p.row_ws (6-bit groups, or 5-bit
+// groups with geo == 4).  -1 if the system does not fit (more than 65535 rows, or less than 16 bytes per row in the
+// table area for the final row permutation: ~11 000 rows with the 6-bit tables).
+inline bool solve_grows_fits(uint32_t rows, int geo) {
+  const size_t tab = geo == 4 ? Geo<4, 5, 128>::TAB_BYTES : Geo<4, 6, 128>::TAB_BYTES;
+  return rows != 0 && rows <= 65535u && tab / rows >= 16;
+}
+inline int launch_solve_grows(int field, int geo, const SolveArgs &p, uint32_t grid, uint32_t threads,
+                              size_t smem_limit, cudaStream_t s) {
+#define OB2_TRYG(E)                                                                                  \
+  return geo == 4 ? launch_solve_t<E, 4, 5, 128, true>(p, grid, threads, smem_limit, s)              \
+                  : launch_solve_t<E, 4, 6, 128, true>(p, grid, threads, smem_limit, s);
+  switch (field) {
+  case OB2_GF256: OB2_TRYG(8)
+  case OB2_GF16: OB2_TRYG(4)
+  case OB2_GF4: OB2_TRYG(2)
+  case OB2_GF2: OB2_TRYG(1)
+  }
+#undef OB2_TRYG
+  return -1;
 }
 
 // Which table-kernel variant launch_solve would pick (same order of attempts, nothing launched):

@@ -2,8 +2,9 @@
 unmodified reference (oracle/_ref: AVX-512 / AVX2 / scalar build + oracle/ref_driver.c, falling
 back to the C restatement), plus the paths only large problems reach:
 
-  * GF(2) K=8192 runs solve_kernel<1, NBW=2, 4, 256> (the 64-bit-panel variant picked when the
-    128-bit panel does not fit shared memory) -- binmat.c:26-33,44-57 semantics;
+  * GF(2) K=8192 runs solve_kernel<1, 4, 6, 128, GROWS> (128-bit panels, per-row state in a global workspace:
+    the default for systems too tall for shared memory) and solve_kernel<1, NBW=2, 4, 256> (64-bit panels in
+    shared memory, oblas_b200_set_tall_mode(0)) -- binmat.c:26-33,44-57 semantics;
   * GF(16)/GF(4) K=2048 -- gfmat.c:83-89,124-156 (GF(4): corrected table, SURVEY 9.2);
   * apply with Kc=10000 coefficient columns (octmat.c:32-46, one oaxpy per coefficient);
   * several chunks of systems in solve_tc_run and several column passes in apply_tc_run, forced
@@ -100,7 +101,17 @@ def check_batch(field, A, B, cols):
     return ranks
 
 
-def test_config3_gf2_k8192_whole_buffers_vs_reference():
+@pytest.fixture(params=[1, 0], ids=["rows_in_global_128bit_panels", "64bit_panels_in_shared_memory"])
+def tall_mode(request):
+    """the two table-kernel variants a system too tall for 128-bit panels in shared memory can take:
+    solve_kernel<.., NBW=4, 6, 128, GROWS> (per-row state in a global workspace, the default) and
+    solve_kernel<.., NBW=2, ..> (64-bit panels, everything in shared memory)"""
+    capi.lib().oblas_b200_set_tall_mode(request.param)
+    yield request.param
+    capi.lib().oblas_b200_set_tall_mode(1)
+
+
+def test_config3_gf2_k8192_whole_buffers_vs_reference(tall_mode):
     """BASELINE configs[2]: GF(2) binmat elimination K=8192, bit-packed (1024-byte rows).  Three systems:
     a random one (rank K-d, d = 0..2 with probability 0.29/0.58/0.13), one with a forced row
     dependency (rank <= K-1) and one with a zero column and a duplicated row.  Ranks, pivot columns
@@ -113,9 +124,12 @@ def test_config3_gf2_k8192_whole_buffers_vs_reference():
     A[2, 6000] = A[2, 1]
     ranks = check_batch(GF2, A, None, K)
     assert ranks[1] < K and ranks[2] < K - 1 and min(ranks) >= K - 8
+    plan, chunk, geo = C.c_int(), C.c_size_t(), (C.c_int * 3)()
+    capi.check(capi.lib().oblas_b200_solve_plan(GF2, K, K, 1024, 0, 3, C.byref(plan), C.byref(chunk), geo))
+    assert plan.value == 0 and list(geo) == ([4, 6, 128] if tall_mode else [2, 4, 256])
 
 
-def test_config3_gf2_k8192_with_rhs():
+def test_config3_gf2_k8192_with_rhs(tall_mode):
     """same size with a 32-byte right-hand side (binmat_add on B beside A)"""
     K = 8192
     A = random_matrix(GF2, K, K, 8200)[None]
@@ -474,3 +488,42 @@ def test_lazy_outer_panels_counters_and_equality(cuda_lib):
         assert np.array_equal(out[192][0][s], A0[s]) and np.array_equal(out[192][1][s], B0[s])
         assert np.array_equal(out[192][3][s][:rk].astype(np.uint32), pv[:rk])
 
+
+
+@pytest.mark.parametrize("field,rows,cols,bbytes", [(GF16, 4000, 512, 256), (GF4, 6000, 1024, 0), (GF2, 10000, 2048, 32),
+                                                    (GF256, 3000, 320, 64)],
+                         ids=["gf16_4000x512", "gf4_6000x1024", "gf2_10000x2048", "gf256_3000x320_table_kernel"])
+def test_tall_systems_on_the_table_kernel(cuda_lib, field, rows, cols, bbytes):
+    """rows whose state does not fit shared memory beside the 128-bit-panel tables: the GROWS variant (per-row
+    state in global memory; GF(2) beyond the ~9800 rows the 64-bit panels could take) against the reference loop,
+    and against the 64-bit-panel variant where that one fits; two systems, one rank deficient"""
+    A = np.stack([random_matrix(field, rows, cols, 9900 + 7 * field + s) for s in range(2)])
+    A[1, rows - 3] = A[1, 5]
+    A[1, :, 1] = 0
+    B = np.stack([splitmix_bytes(9950 + s, rows * bbytes).reshape(rows, bbytes) for s in range(2)]).copy() if bbytes else None
+    try:
+        if field == GF256:
+            cuda_lib.oblas_b200_set_tuning(1, -1)   # the table kernel (the tensor-core path takes GF(256) by default)
+        cuda_lib.oblas_b200_set_tall_mode(1)
+        plan, chunk, geo = C.c_int(), C.c_size_t(), (C.c_int * 3)()
+        capi.check(cuda_lib.oblas_b200_solve_plan(field, rows, cols, A.shape[2], bbytes, 2, C.byref(plan), C.byref(chunk), geo))
+        assert plan.value == 0 and list(geo) == [4, 6, 128]
+        dA, dB = dev(A), (dev(B) if B is not None else None)
+        rank, piv = device.solve_batch(field, dA, cols, dB, want_pivcols=True)
+        device.sync()
+        for s in range(2):
+            rk, pv, wa, wb = ref_solve(field, A[s], B[s] if B is not None else None, cols)
+            assert int(rank[s]) == rk, s
+            assert np.array_equal(host(piv)[s][:rk].astype(np.uint32), pv[:rk]), s
+            assert np.array_equal(host(dA)[s], wa) and (B is None or np.array_equal(host(dB)[s], wb)), s
+        assert int(rank[1]) < min(rows, cols)
+        if rows <= 9000:
+            cuda_lib.oblas_b200_set_tall_mode(0)
+            tA, tB = dev(A), (dev(B) if B is not None else None)
+            trank, tpiv = device.solve_batch(field, tA, cols, tB, want_pivcols=True)
+            device.sync()
+            assert torch.equal(rank, trank) and torch.equal(piv, tpiv) and torch.equal(dA, tA)
+            assert B is None or torch.equal(dB, tB)
+    finally:
+        cuda_lib.oblas_b200_set_tall_mode(1)
+        cuda_lib.oblas_b200_set_tuning(-1, -1)
