@@ -112,6 +112,35 @@ struct TcRegion {
   uint32_t v0;         // first virtual column of the region (0 for region 0, region 0's ncols for region 1)
 };
 
+// Column tiles of a virtual column range [0, vend) (vend a multiple of 16), ntiles = ceil(vend / 240) of them.
+// FIXED geometry: tile t = columns [240 t, 240 t + 240), the last one takes the rest.  EVEN geometry (the rank-128
+// update of the elimination): the range is dealt out in groups of 16 columns as evenly as possible, every tile is
+// 16 * (q / ntiles) or 16 more columns wide.  The rest tile of the fixed geometry can be tiny (K = 1024, L = 1280,
+// outer panel 0: 2176 = 9 x 240 + 16) and costs its issuing thread the same ~1800 clk of waits, issues and commits as
+// a full tile for 1/15 of the tensor work -- ncu, tensor pipe active per outer panel: 85.8 % where 240 divides
+// the range (panel 2), 74-79 % with a narrow rest tile (panels 7, 0).
+struct TileGeo {
+  uint32_t b, x, vend;   // even: groups of 16 columns per tile, tiles with one group more; the end of the range
+  int even;
+  OB2_D void init(uint32_t vend_, uint32_t ntiles, int even_) {
+    vend = vend_;
+    even = even_ && ntiles > 0;
+    const uint32_t q = vend_ >> 4;
+    b = even ? q / ntiles : 0u;
+    x = even ? q - b * ntiles : 0u;
+  }
+  OB2_D void span(uint32_t t, uint32_t &v0, uint32_t &w) const {
+    if (even) {
+      v0 = 16u * (t * b + (t < x ? t : x));
+      w = 16u * (b + (t < x ? 1u : 0u));
+    } else {
+      v0 = t * (uint32_t)kHalfN;
+      const uint32_t rest = vend > v0 ? vend - v0 : 0u;
+      w = rest >= (uint32_t)kHalfN ? (uint32_t)kHalfN : ((rest + 15u) & ~15u);
+    }
+  }
+};
+
 struct ExpandArgs {
   TcRegion reg[2];         // where the rows of D live (plain apply: one region, one system)
   uint32_t nreg;
@@ -127,6 +156,7 @@ struct ExpandArgs {
   // binmat.c:26-33; the mask operand of oaxpy_b32 / binmat_expand, oblas_ref.c:19-28): column n of a row is
   // the field element 0 or 1.  Expanding them here fuses n x Kc oaxpy_b32 calls into one tensor-core apply.
   int bit_rows;
+  int even;               // column tiles in the EVEN geometry (TileGeo; nhalf = ceil(range / 240) tiles)
 };
 
 struct ApplyTcArgs {
@@ -155,6 +185,7 @@ struct ApplyTcArgs {
   const uint32_t *nunits_dev;
   const uint16_t *y_rowmap;
   uint32_t y_rowmap_stride;
+  int even_tiles;          // update_tc_kernel: column tiles in the EVEN geometry (TileGeo), as the expansion laid them out
 };
 
 // byte d -> 8 fp4 values, nibble b = e2m1 1.0 (0b0010) if bit b of d is set
@@ -176,6 +207,8 @@ __global__ void __launch_bounds__(256) expand_d_kernel(const ExpandArgs p) {
   constexpr uint32_t G = kHalfN / 4;  // threads per (half tile, step): 30 groups of 8 columns x 2 parities
   const size_t per_sys = (size_t)p.nhalf * p.ksteps * G;
   const size_t total = per_sys * p.nsys;
+  TileGeo geo;
+  geo.init(p.reg[p.nreg - 1].v0 + p.reg[p.nreg - 1].ncols, p.nhalf, p.even);
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
     const uint32_t sys = (uint32_t)(idx / per_sys);
@@ -184,7 +217,10 @@ __global__ void __launch_bounds__(256) expand_d_kernel(const ExpandArgs p) {
     const size_t rest = li / G;
     const uint32_t ks = (uint32_t)(rest % p.ksteps), half = (uint32_t)(rest / p.ksteps);
     const uint32_t grp = g4 >> 1, par = g4 & 1u;             // 8-column group, column parity
-    const uint32_t v = half * kHalfN + grp * 8;              // virtual column of the group (groups never straddle regions)
+    uint32_t v0t, wt;
+    geo.span(half, v0t, wt);
+    const bool in_tile = grp * 8 < wt;                       // (even geometry: tiles narrower than 240 columns)
+    const uint32_t v = v0t + grp * 8;                        // virtual column of the group (groups never straddle regions)
     const TcRegion &rg = p.reg[(p.nreg > 1 && v >= p.reg[1].v0) ? 1 : 0];
     const uint32_t n = v - rg.v0;                            // column inside the region
     const uint32_t nrows = p.nrows ? p.nrows[sys] : p.Kc;
@@ -195,7 +231,7 @@ __global__ void __launch_bounds__(256) expand_d_kernel(const ExpandArgs p) {
     for (int jj = 0; jj < kStepJ; jj++) {
       const uint32_t j = ks * kStepJ + jj;
       x[jj] = 0;
-      if (j < nrows && n < rg.ncols) {
+      if (j < nrows && n < rg.ncols && in_tile) {
         const uint32_t row = p.rowmap ? (uint32_t)p.rowmap[(size_t)sys * p.rowmap_stride + j] : j;
         if (p.bit_rows) {
           // the 8 columns of the group are one byte of the bit row; columns par, par+2, par+4, par+6 -> bytes 0 / 1
@@ -399,15 +435,13 @@ struct EpiTile {
   // per tile
   uint32_t vt;            // virtual column of this lane's word of chunk 0
   int c_lo, c_hi;
-  // FAST tiles (a full tile inside one region: all but the last tile of the range and the one that straddles the
-  // region boundary): the words of this lane's chunks are pw + 32 * k and which of them exist only depends on the
-  // lane (full_mask, per unit).  The general addressing (a region select and three range checks per word, for the
-  // prefetch of the old words and again for the stores) was ~110 dependent instructions per tile and warp on the
-  // serial path of the epilogue warps, which bound the update kernel.
+  // FAST tiles (inside one region: all but the tile that straddles the region boundary): the words of this lane's
+  // chunks are pw + 32 * k; okmask says which of them exist.  (The general addressing is a region select per word,
+  // for the prefetch of the old words and again for the stores.)
   bool fast;
   uint8_t *pw;
   uint32_t okmask;        // bit k: the word of chunk c_lo + k exists (is inside the tile, the range and the matrix)
-  uint32_t full_mask;     // okmask of a fast tile
+  uint32_t wcur;          // width of the tile
   OB2_D void set_unit(uint32_t warp, uint32_t lane, const TcRegion *reg, uint32_t nreg, uint32_t sys, uint32_t it,
                       uint32_t M, const uint16_t *rowmap = nullptr, uint32_t rowmap_stride = 0) {
     const uint32_t lq = warp & 3u, rr = lane >> 3;
@@ -431,30 +465,26 @@ struct EpiTile {
       vend = r1.v0 + r1.ncols;
       y1 = r1.base + (size_t)sys * r1.ss + r1.col0 + (size_t)row * r1.rs - (ptrdiff_t)split;
     }
-    full_mask = 0;
-    const int fl = (kChunks * (int)part) / PARTS, fh = (kChunks * ((int)part + 1)) / PARTS;
-#pragma unroll
-    for (int k = 0; k < kC0; k++)
-      if (row_ok && fl + k < fh && (uint32_t)(fl + k) * 32 + ct0 < (uint32_t)TILE_N) full_mask |= 1u << k;
   }
-  OB2_D void set_tile(uint32_t tile) {
-    const uint32_t v_tile = tile * TILE_N;
+  // a tile = virtual columns [v_tile, v_tile + w), w <= TILE_N a multiple of 16 inside the range
+  OB2_D void set_span(uint32_t v_tile, uint32_t w) {
     vt = v_tile + ct0;
-    const uint32_t rest = vend > v_tile ? vend - v_tile : 0u;
-    fast = OB2_EPI_FAST && rest >= (uint32_t)TILE_N && (v_tile >= split || v_tile + (uint32_t)TILE_N <= split);   // warp-uniform
-    const int nch = rest >= (uint32_t)TILE_N ? kChunks : (int)((rest + 31) / 32);
+    wcur = w;
+    fast = OB2_EPI_FAST && (v_tile >= split || v_tile + w <= split);   // warp-uniform: the tile lies inside one region
+    const int nch = (int)((w + 31) / 32);
     c_lo = (nch * (int)part) / PARTS;
     c_hi = (nch * ((int)part + 1)) / PARTS;
-    if (fast) {
-      pw = ((v_tile >= split) ? y1 : y0) + vt + (uint32_t)c_lo * 32;
-      okmask = full_mask;
-    } else {
-      pw = nullptr;
-      okmask = 0;
+    pw = ((v_tile >= split) ? y1 : y0) + vt + (uint32_t)c_lo * 32;
+    okmask = 0;
 #pragma unroll
-      for (int k = 0; k < kC0; k++)
-        if (c_lo + k < c_hi && col_ok(c_lo + k)) okmask |= 1u << k;
-    }
+    for (int k = 0; k < kC0; k++)
+      if (c_lo + k < c_hi && col_ok(c_lo + k)) okmask |= 1u << k;
+  }
+  // fixed geometry: tile `tile` of TILE_N columns, the last one of the range takes the rest
+  OB2_D void set_tile(uint32_t tile) {
+    const uint32_t v_tile = tile * TILE_N;
+    const uint32_t rest = vend > v_tile ? vend - v_tile : 0u;
+    set_span(v_tile, rest >= (uint32_t)TILE_N ? (uint32_t)TILE_N : rest);
   }
   OB2_D void set(uint32_t warp, uint32_t lane, const TcRegion *reg, uint32_t nreg, uint32_t sys, uint32_t tile,
                  uint32_t it, uint32_t M, const uint16_t *rowmap = nullptr, uint32_t rowmap_stride = 0) {
@@ -462,7 +492,7 @@ struct EpiTile {
     set_tile(tile);
   }
   OB2_D bool col_ok(int cc) const {
-    return row_ok && (uint32_t)cc * 32 + ct0 < (uint32_t)TILE_N && vt + (uint32_t)cc * 32 < vend;
+    return row_ok && (uint32_t)cc * 32 + ct0 < wcur && vt + (uint32_t)cc * 32 < vend;
   }
   OB2_D uint8_t *word(int cc) const {
     const uint32_t v = vt + (uint32_t)cc * 32;
@@ -1002,6 +1032,8 @@ static_assert(kUSPS == kBuilderWarps, "each builder warp builds one step of ever
 OB2_D uint32_t update_tile_at(uint32_t j, uint32_t ntiles) {
   return ntiles < 3 ? j : (j == 0 ? 0u : (j == 1 ? ntiles - 1 : j - 1));
 }
+// (even geometry: all tiles of a range are about as wide, they are processed in order)
+OB2_D uint32_t tile_order(uint32_t j, uint32_t ntiles, int even) { return even ? j : update_tile_at(j, ntiles); }
 
 template <bool PROF>
 __global__ void __launch_bounds__(kUThreads, 1) update_tc_kernel(const ApplyTcArgs p) {
@@ -1096,7 +1128,7 @@ __global__ void __launch_bounds__(kUThreads, 1) update_tc_kernel(const ApplyTcAr
       const uint8_t *src0 = p.Dx + (size_t)sys * ntiles * kUSteps * kHBlock;
       for (uint32_t j = 0; j < ntiles && ok; j++, ph ^= 1u) {
         const uint32_t odd = (tile_iter + j) & 1u;            // which set of b_full barriers this tile uses
-        const uint8_t *srct = src0 + (size_t)update_tile_at(j, ntiles) * kUSteps * kHBlock;
+        const uint8_t *srct = src0 + (size_t)tile_order(j, ntiles, p.even_tiles) * kUSteps * kHBlock;
 #pragma unroll
         for (uint32_t s = pwi; s < (uint32_t)kRStages; s += (uint32_t)kUProducers) {
           const long long w0 = prof ? clock64() : 0;
@@ -1125,7 +1157,8 @@ __global__ void __launch_bounds__(kUThreads, 1) update_tc_kernel(const ApplyTcAr
     // A,B = E2M1 (1), K-major, scales UE8M0, M = 128, K = 64; N is set per tile: 240, or the
     // 16-aligned rest of the virtual column range for the last tile (MMA time is proportional to N)
     const uint32_t idesc0 = (1u << 7) | (1u << 10) | (1u << 23) | ((128u >> 4) << 24);
-    const uint32_t vend = p.reg[p.nreg - 1].v0 + p.reg[p.nreg - 1].ncols;
+    TileGeo geo;
+    geo.init(p.reg[p.nreg - 1].v0 + p.reg[p.nreg - 1].ncols, ntiles, p.even_tiles);
     const uint64_t a_desc0 = umma_desc(smem_addr(smA), kALbo, kASbo);
     const uint64_t b_desc0 = umma_desc(smem_addr(smB));
     const uint32_t sfa = tm + kSfCol, sfb = tm + kSfCol + 16;
@@ -1137,7 +1170,7 @@ __global__ void __launch_bounds__(kUThreads, 1) update_tc_kernel(const ApplyTcAr
       bool a_seen = false;                                  // this warp has waited for the unit's A operand
       for (uint32_t j = 0; j < ntiles && ok; j++, tile_iter++) {
         if (kUIssuers > 1 && (tile_iter & 1u) != me) continue;
-        const uint32_t nt = update_tile_at(j, ntiles);
+        const uint32_t nt = tile_order(j, ntiles, p.even_tiles);
         const uint32_t ab = tile_iter & 1u;                 // accumulator set (two issuers: == me)
         const uint32_t acc0 = tm + ab * kHalfN;
         // first / last tile of the unit issued by THIS warp
@@ -1148,8 +1181,8 @@ __global__ void __launch_bounds__(kUThreads, 1) update_tc_kernel(const ApplyTcAr
         if (!mbar_wait(tmem_empty(ab), ((tile_iter >> 1) & 1u) ^ 1u, p.status)) { ok = false; break; }
         if (prof) pwt += clock64() - w0;
         tc_fence_after();
-        const uint32_t rest = vend - nt * kHalfN;          // > 0: ntiles = ceil(vend / 240)
-        const uint32_t ncur = rest >= (uint32_t)kHalfN ? (uint32_t)kHalfN : ((rest + 15u) & ~15u);
+        uint32_t v0cur, ncur;                               // the tile's MMA width: a multiple of 16, >= 16
+        geo.span(nt, v0cur, ncur);
         const uint32_t idesc = idesc0 | ((ncur >> 3) << 17);
 #pragma unroll
         for (int cs = 0; cs < kRStages; cs++) {
@@ -1259,17 +1292,25 @@ __global__ void __launch_bounds__(kUThreads, 1) update_tc_kernel(const ApplyTcAr
       }
       return su < nunits;
     };
-    auto tile_of = [&](uint32_t su, uint32_t nt, ET &e) {
+    TileGeo geo;
+    geo.init(p.reg[p.nreg - 1].v0 + p.reg[p.nreg - 1].ncols, ntiles, p.even_tiles);
+    auto span_of = [&](uint32_t j, ET &e) {   // the j-th tile of a unit in processing order
+      uint32_t v0, w;
+      geo.span(tile_order(j, ntiles, p.even_tiles), v0, w);
+      e.set_span(v0, w);
+    };
+    auto tile_of = [&](uint32_t su, uint32_t j, ET &e) {
       uint32_t sys, it;
       unit_of(su, sys, it);
-      e.set(warp, lane, p.reg, p.nreg, sys, nt, it, p.M, p.y_rowmap, p.y_rowmap_stride);
+      e.set_unit(warp, lane, p.reg, p.nreg, sys, it, p.M, p.y_rowmap, p.y_rowmap_stride);
+      span_of(j, e);
     };
     ET cur, nxt;
     uint32_t old_cur[ET::kC0], old_nxt[ET::kC0];
     uint32_t ti = (kUEpiGroups > 1) ? grp : 0u, su = blockIdx.x, j = 0;
     bool have = ntiles > 0 && next_tile(su, j, ti);
     if (have) {
-      tile_of(su, update_tile_at(j, ntiles), nxt);
+      tile_of(su, j, nxt);
       nxt.load_old(old_nxt, p.accumulate);
     }
     const bool prof = PROF && p.prof != nullptr && warp == (uint32_t)kEpi0;
@@ -1283,8 +1324,8 @@ __global__ void __launch_bounds__(kUThreads, 1) update_tc_kernel(const ApplyTcAr
       uint32_t su2 = su, j2 = j;
       const bool have2 = next_tile(su2, j2, (uint32_t)kUEpiGroups);
       if (have2) {
-        if (su2 == su) nxt.set_tile(update_tile_at(j2, ntiles));   // same (system, row)
-        else tile_of(su2, update_tile_at(j2, ntiles), nxt);
+        if (su2 == su) span_of(j2, nxt);   // same (system, row)
+        else tile_of(su2, j2, nxt);
         nxt.load_old(old_nxt, p.accumulate);
       }
       const uint32_t ab = ti & 1u, use = ti >> 1;

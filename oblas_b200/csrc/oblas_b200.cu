@@ -501,7 +501,7 @@ void oblas_b200_set_lazy_panels(int compact_rows) {
 // Table kernel, systems whose per-row state does not fit shared memory beside the tables of the 128-bit panels:
 // 1 (default) = keep the 128-bit panels and hold the per-row state in a global workspace, 0 = 64-bit panels in
 // shared memory (the behaviour before; rows <= ~9800)
-void oblas_b200_set_tall_mode(int mode) { cx().solve_tall = mode ? 1 : 0; }
+void oblas_b200_set_tall_mode(int mode) { cx().solve_tall = mode < 0 ? 1 : (mode > 2 ? 2 : mode); }
 void oblas_b200_set_tuning(int solve_geo, int apply_geo) {
   cx().solve_geo = solve_geo;
   cx().apply_geo = apply_geo;
@@ -788,7 +788,7 @@ static int solve_common(int field, SolveArgs &p, size_t nsys) {
     int plan[3] = {0, 0, 0};
     const bool fits = plan_solve(field, geo, p.rows, cx().smem_optin, plan);
     const int ggeo = geo == 4 ? 4 : 1;
-    if ((!fits || plan[0] != 4) && solve_grows_fits(p.rows, ggeo)) {
+    if ((!fits || plan[0] != 4 || (cx().solve_tall == 2 && geo < 0 && plan[1] != 6)) && solve_grows_fits(p.rows, ggeo)) {
       const size_t per_cta = solve_row_ws_bytes<4>(p.rows);
       const int wrc = tc_ws_reserve(per_cta * grid + 256);
       if (wrc < 0) return -1;
@@ -1133,6 +1133,17 @@ static int tc_debug_switches() {
   return cx().tc_inject;
 #endif
 }
+// OBLAS_B200_TC_PAIR=1: the CTA-pair variant of the update kernel (fixed tile geometry only)
+static bool tc_pair_enabled() {
+  static const bool pair = getenv("OBLAS_B200_TC_PAIR") && atoi(getenv("OBLAS_B200_TC_PAIR")) != 0;
+  return pair;
+}
+// Column tiles of the update launches in the EVEN geometry (apply_tc.cuh: TileGeo) unless OBLAS_B200_TC_EVEN=0
+// (same-box A/B runs) or the CTA-pair kernel is selected
+static int tc_even_tiles() {
+  static const bool off = getenv("OBLAS_B200_TC_EVEN") && atoi(getenv("OBLAS_B200_TC_EVEN")) == 0;
+  return (off || tc_pair_enabled()) ? 0 : 1;
+}
 // persistent launch of the tcgen05 GEMM kernel: one CTA per SM.  nh = half tiles (240 byte
 // columns) per tile: 2 = one accumulator set, long inner dimension; 1 = double-buffered accumulators
 int tc_launch(const ob2::tc::ApplyTcArgs &a, int nh) {
@@ -1152,7 +1163,7 @@ int tc_launch(const ob2::tc::ApplyTcArgs &a, int nh) {
     if (nunits < grid) grid = (uint32_t)nunits;
     // OBLAS_B200_TC_PAIR=1: the CTA-pair variant (tcgen05 cta_group::2).  Bit-exact (the whole GPU suite
     // passes on it) but as built 1.75x slower than the single-CTA kernel -- see DESIGN.md 4.5 -- so off by default.
-    static const bool pair = getenv("OBLAS_B200_TC_PAIR") && atoi(getenv("OBLAS_B200_TC_PAIR")) != 0;
+    const bool pair = tc_pair_enabled();
     if (pair && !a.prof && !a.units) {
       // CTA pairs (cta_group::2): a cluster of 2 per pair of row tiles
       const uint64_t npairs = (uint64_t)a.nsys * ((a.itiles + 1) / 2);
@@ -1366,7 +1377,8 @@ extern "C" int oblas_b200_solve_plan(int field, uint32_t rows, uint32_t cols, si
       const int geo = cx().solve_geo == 3 ? -1 : cx().solve_geo;
       const bool fits = plan_solve(field, geo, rows, cx().smem_optin, geometry);
       const int ggeo = geo == 4 ? 4 : 1;
-      if (cx().solve_tall && (geo < 0 || geo == 1 || geo == 4) && (!fits || geometry[0] != 4) && solve_grows_fits(rows, ggeo)) {
+      if (cx().solve_tall && (geo < 0 || geo == 1 || geo == 4) &&
+          (!fits || geometry[0] != 4 || (cx().solve_tall == 2 && geo < 0 && geometry[1] != 6)) && solve_grows_fits(rows, ggeo)) {
         geometry[0] = 4; geometry[1] = ggeo == 4 ? 5 : 6; geometry[2] = 128;   // per-row state in global memory
       } else if (!fits) {
         return fail("solve_plan: %u rows do not fit the shared-memory panel (limit %zu bytes); no fallback", rows, cx().smem_optin);
@@ -1516,6 +1528,7 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
       e.reg[0] = reg[0]; e.reg[1] = reg[1]; e.nreg = nreg; e.Kc = kOuterBytes;
       e.rowmap = piv_all; e.rowmap_stride = kOuterBytes; e.nrows = npiv;
       e.Dx = Dx; e.ksteps = ksteps; e.nhalf = ntiles; e.nsys = cnt;
+      e.even = tc_even_tiles();
       const size_t work = (size_t)cnt * ntiles * ksteps * (kTileN / 4);
       uint32_t eg = (uint32_t)((work + 255) / 256);
       if (eg > (uint32_t)cx().sm_count * 16) eg = (uint32_t)cx().sm_count * 16;
@@ -1525,6 +1538,7 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
       a.ksteps = ksteps; a.ntiles = ntiles; a.itiles = itiles; a.nsys = cnt;
       a.reg[0] = reg[0]; a.reg[1] = reg[1]; a.nreg = nreg;
       a.accumulate = 1; a.status = dstatus; a.prof = cx().d_uprof;
+      a.even_tiles = e.even;
       a.poly = 0x100u | (p.red & 0xffu);
       a.dbg = tc_debug_switches();
       // lazy: launch A -- the compact rows (gathered through crow) ^= their coefficient rows * OLD pivot rows --

@@ -12,13 +12,14 @@ from oblas_b200 import capi, device
 device.bind(0)
 lib = capi.lib()
 for name, field, K, nsys, geos in (("GF2 K=8192", capi.GF2, 8192, 256, (-1, 4)), ("GF16 K=4096", capi.GF16, 4096, 148, (-1, 4)),
-                                   ("GF4 K=8192", capi.GF4, 8192, 148, (-1, 4))):
+                                   ("GF4 K=8192", capi.GF4, 8192, 148, (-1, 4)), ("GF16 K=2048", capi.GF16, 2048, 592, (-1,)),
+                                   ("GF4 K=2048", capi.GF4, 2048, 592, (-1,)), ("GF256 K=448", capi.GF256, 448, 592, (-1,))):
     bits = capi.FIELD_BITS[field]
     a_bytes = K * bits // 8
     A0 = torch.empty((nsys, K, a_bytes), dtype=torch.uint8, device="cuda")
     device.fill_random(A0, 100 + field)
     ref = None
-    for mode, geo in [(0, -1)] + [(1, g) for g in geos]:
+    for mode, geo in [(0, -1)] + [(1, g) for g in geos] + [(2, -1)]:   # mode 2: 6-bit tables + global row state also where 5-bit tables fit
         lib.oblas_b200_set_tall_mode(mode)
         lib.oblas_b200_set_tuning(geo, -1)
         g = (C.c_int * 4)()
