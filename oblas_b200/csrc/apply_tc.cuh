@@ -524,11 +524,22 @@ struct EpiTile {
 // tools/tmem_ld.cu: 720 B/clk/SM next to running MMAs), so a second buffer buys nothing -- but its 32
 // registers forced the packing into one serial FADD -> SHF chain (440 clk per chunk measured).
 // pc (diagnostics, may be null): cycles in 0 = TMEM read, 1 = packing + transposes, 2 = stores.
+// (OB2_U_EARLY_RELEASE, measured on B200 and NOT kept: update kernel 18.89 against 18.84 ms per 592 systems)
+// release_bar != 0: the accumulator set is handed back (arrive on that barrier) as soon as this thread's LAST
+// tcgen05.ld of the tile has completed -- before the packing of that chunk, the transposes and the stores -- so the
+// MMAs of the tile after next start ~600 clk earlier; the caller then does not arrive itself.
 template <int TILE_N, int PARTS = kEpiParts>
 OB2_D void epilogue_tile(uint32_t tm, uint32_t acc_col, uint32_t warp, uint32_t lane, const EpiTile<TILE_N, PARTS> &e,
-                         const uint32_t (&oldw)[EpiTile<TILE_N, PARTS>::kC0], long long *pc = nullptr) {
+                         const uint32_t (&oldw)[EpiTile<TILE_N, PARTS>::kC0], long long *pc = nullptr,
+                         uint32_t release_bar = 0) {
   constexpr int kC0 = EpiTile<TILE_N, PARTS>::kC0;
-  if (e.c_lo >= e.c_hi) return;
+  if (e.c_lo >= e.c_hi) {
+    if (release_bar) {
+      tc_fence_before();
+      mbar_arrive(release_bar);
+    }
+    return;
+  }
   const uint32_t tbase = tm + (((warp & 3u) * 32u) << 16) + acc_col;
   uint32_t w[kC0];
   long long q0 = pc ? clock64() : 0, t_ld = 0;
@@ -542,6 +553,10 @@ OB2_D void epilogue_tile(uint32_t tm, uint32_t acc_col, uint32_t warp, uint32_t 
       tmem_ld32(r, tbase + cc * 32);
       tmem_wait_ld32(r);
       if (pc) t_ld += clock64() - l0;
+      if (release_bar && cc + 1 == e.c_hi) {   // (warp-uniform) nothing of this tile is left in tensor memory for this thread
+        tc_fence_before();
+        mbar_arrive(release_bar);
+      }
       // parity of every accumulator (integer-valued fp32 < 2^23: adding 2^23 leaves it in the
       // mantissa LSB).  Column c = 4*j + k2 goes to bit k2*8 + j of this lane's word: one funnel
       // shift per accumulator pushes the LSB into the top of one of four 8-deep chains (chain k2
@@ -573,15 +588,21 @@ OB2_D void epilogue_tile(uint32_t tm, uint32_t acc_col, uint32_t warp, uint32_t 
   // 8x8 bit transposes across the 8 lanes (bit planes) of a row: lane bit i <-> index bit i, all
   // chunks of the tile together (independent shuffles).  Afterwards lane (row rr, gc) holds bytes
   // Y[rr][4*gc .. 4*gc+3] (bit a = plane a).
+  // Per stage a lane keeps the bits `km` of its word and takes the others from its partner (lane ^ d), shifted by
+  // d: down for the upper lane, up for the lower one.  The SENDER rotates (one funnel shift; the bits that wrap
+  // around fall outside the receiver's take mask), so a word costs rotate + shuffle + one LOP3 select per stage
+  // instead of two masks, a shift, an OR and a select -- the ALU pipe is what the read-out runs out of.
 #pragma unroll
   for (int i2 = 0; i2 < 3; i2++) {
     const uint32_t d = 1u << i2;
     const uint32_t m0 = (i2 == 0) ? 0x55555555u : (i2 == 1) ? 0x33333333u : 0x0f0f0f0fu;
     const bool up = (lane & d) != 0;
+    const uint32_t km = up ? ~m0 : m0;        // the bits this lane keeps
+    const uint32_t amt = up ? 32u - d : d;    // upper lane sends its word rotated LEFT by d, lower lane RIGHT by d
 #pragma unroll
     for (int k = 0; k < kC0; k++) {
-      const uint32_t tw = __shfl_xor_sync(0xffffffffu, w[k], d);
-      w[k] = up ? ((w[k] & ~m0) | ((tw & ~m0) >> d)) : ((w[k] & m0) | ((tw & m0) << d));
+      const uint32_t tw = __shfl_xor_sync(0xffffffffu, __funnelshift_r(w[k], w[k], amt), d);
+      w[k] = (w[k] & km) | (tw & ~km);
     }
   }
   const long long q1 = pc ? clock64() : 0;
@@ -990,6 +1011,9 @@ static_assert(kUSteps == kUSPS * kUStages, "one trip around the B ring per colum
 #ifndef OB2_U_PRODUCERS
 #define OB2_U_PRODUCERS 2
 #endif
+#ifndef OB2_U_EARLY_RELEASE
+#define OB2_U_EARLY_RELEASE 0
+#endif
 #ifndef OB2_U_WARPARRIVE
 #define OB2_U_WARPARRIVE 0
 #endif
@@ -1335,9 +1359,13 @@ __global__ void __launch_bounds__(kUThreads, 1) update_tc_kernel(const ApplyTcAr
       if (!mbar_wait(tmem_full(ab), use & 1u, p.status)) break;
       const long long w1 = prof ? clock64() : 0;
       tc_fence_after();
-      if (!(p.dbg & 4)) epilogue_tile<kHalfN, kUEpiParts>(tm, ab * kHalfN, warp, lane, cur, old_cur, prof ? pc : nullptr);
+      constexpr bool kEarly = OB2_U_EARLY_RELEASE != 0 && !kUWarpArrive;
+      if (!(p.dbg & 4)) epilogue_tile<kHalfN, kUEpiParts>(tm, ab * kHalfN, warp, lane, cur, old_cur, prof ? pc : nullptr,
+                                                          kEarly ? tmem_empty(ab) : 0u);
       tc_fence_before();
-      if (kUWarpArrive) {
+      if (kEarly && !(p.dbg & 4)) {
+        // handed back inside epilogue_tile
+      } else if (kUWarpArrive) {
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty(ab));
       } else {
