@@ -386,8 +386,17 @@ def run_b200_arm(args):
                     "algorithmic_bytes_per_launch": sys_per_launch * 2 * K * (trailing / nouter),
                     "gf256_macs_per_system": upd_macs / nsys,
                     "note": "fp4 e2m1 0/1 operands, fp32 accumulation in TMEM, parity in the epilogue; inner dimension "
-                            "128 coefficients = 16 K-steps per tile: per 2000 clk of MMAs one epilogue (2 instructions "
+                            "128 coefficients = 16 K-steps per tile: per 2000 clk of MMAs one epilogue (1.5 instructions "
                             "per accumulator) and, per row tile, one rebuild of the coefficient operand"}
+        # The peak is a burst figure at the maximum SM clock (the bare MMA loop of tools/peaks.cu holds it for seconds:
+        # profiles/r02_peaks_sustained_b200.jsonl -- it moves no data).  This kernel, inside a long step, runs under
+        # the board's power cap: the same fraction against the peak AT THE CLOCK SAMPLED DURING THE TIMED REGION
+        # says how busy the tensor pipe is kept, `frac` how far the whole step is from the burst figure.
+        if clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz"):
+            scale = float(clocks["sm_mhz"]) / float(clocks["sm_max_mhz"])
+            roofline["frac_at_sampled_clock"] = ach / (fp4_peak * scale)
+            roofline["sampled_clock_note"] = ("sm %d of %d MHz under load (%s)" % (
+                int(clocks["sm_mhz"]), int(clocks["sm_max_mhz"]), ",".join(clocks.get("reasons") or []) or "no throttle reason"))
         # outer-panel factorisation: shared-memory look-up bound.  Per 16-column step it streams ONE
         # combined 128-byte tile of every row (the live right part of the 128-column window and the
         # live left part of E are complementary): 22 LDS.128 per 16 bytes x 16 pivots

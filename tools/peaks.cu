@@ -358,6 +358,47 @@ static void run_umma(const char *name, int kdim, int sms, int n_mma, int sts_war
   cudaFree(cyc); cudaFree(stsb); cudaFree(status);
 }
 
+// The same MMA loop back to back for `seconds` on all SMs: what the tensor pipe sustains under the board's power cap
+// (the burst figure above is reached for a few ms; a kernel timed inside a long step has to be held against this one).
+// Reports the rate over the whole run and over its second half.
+template <int KIND>
+static void run_umma_sustained(const char *name, int kdim, int sms, double seconds) {
+  unsigned long long *cyc, *stsb;
+  int *status;
+  CK(cudaMalloc(&cyc, 8));
+  CK(cudaMalloc(&stsb, 8));
+  CK(cudaMalloc(&status, 4));
+  CK(cudaMemset(cyc, 0, 8));
+  CK(cudaMemset(stsb, 0, 8));
+  CK(cudaMemset(status, 0, 4));
+  auto k = umma_kernel<KIND>;
+  CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  const int n_mma = 131072;                       // ~9 ms per launch
+  const double est_ms = 131072.0 * 131.0 / 1.9e6;
+  const int launches = (int)(seconds * 1e3 / est_ms) + 2;
+  cudaEvent_t e0, em, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&em));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0));
+  for (int i = 0; i < launches; i++) {
+    if (i == launches / 2) CK(cudaEventRecord(em));
+    k<<<sms, 128, 65536>>>(n_mma, 0, cyc, stsb, status);
+  }
+  CK(cudaEventRecord(e1));
+  CK(cudaDeviceSynchronize());
+  float ms_all, ms_half;
+  CK(cudaEventElapsedTime(&ms_all, e0, e1));
+  CK(cudaEventElapsedTime(&ms_half, em, e1));
+  const double macs = 128.0 * 256.0 * kdim * n_mma * sms;
+  printf("{\"what\": \"umma_sustained\", \"kind\": \"%s\", \"M\": 128, \"N\": 256, \"K\": %d, \"ctas\": %d, \"launches\": %d, "
+         "\"seconds\": %.2f, \"chip_Tmac_per_s\": %.1f, \"chip_Tmac_per_s_second_half\": %.1f, \"chip_TFLOPs_second_half\": %.1f}\n",
+         name, kdim, sms, launches, ms_all / 1e3, macs * launches / (ms_all * 1e-3) / 1e12,
+         macs * (launches - launches / 2) / (ms_half * 1e-3) / 1e12, 2.0 * macs * (launches - launches / 2) / (ms_half * 1e-3) / 1e12);
+  fflush(stdout);
+  cudaFree(cyc); cudaFree(stsb); cudaFree(status);
+}
+
 template <int OP>
 static void run_alu(const char *name, int sms) {
   uint32_t *out;
@@ -432,6 +473,14 @@ int main(int argc, char **argv) {
   for (int i = 1; i < argc; i++) {
     if (!strcmp(argv[i], "--no-umma")) do_umma = false;
     if (!strcmp(argv[i], "--mxf4")) do_mxf4 = true;
+    if (!strcmp(argv[i], "--sustained") && i + 1 < argc) {   // only the sustained mxf4 / bf16 rates, for that many seconds each
+      const double sec = atof(argv[i + 1]);
+      run_umma<3>("mxf4(e2m1,ue8m0)", 64, sms, 16384, 0, sms);
+      run_umma_sustained<3>("mxf4(e2m1,ue8m0)", 64, sms, sec);
+      run_umma<3>("mxf4(e2m1,ue8m0)", 64, sms, 16384, 0, sms);
+      run_umma_sustained<2>("f16(bf16)", 16, sms, sec);
+      return 0;
+    }
   }
   run_alu<0>("LOP3", sms);
   run_alu<1>("PRMT", sms);
