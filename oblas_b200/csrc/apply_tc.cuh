@@ -983,14 +983,20 @@ constexpr int kUABuf = kUSteps * kATile;          // resident A operand of one r
 //   the copy size (15 KB / 7.5 KB stages: the kernel slows down in proportion to the number of copies, so
 //   kRSPS stays 4); one producer serving the four slots in turn put up to four of those in front of a refill
 //   (MMA warp waiting 680 clk per tile for B).  kUProducers warps share the slots (s % kUProducers): 240 clk.
-// * What remains is the read-out: the 8 epilogue warps are busy ~2470 clk per tile (1660 TMEM read + parity
+// * The read-out: in the role counters the 8 epilogue warps are busy ~2470 clk per tile (1660 TMEM read + parity
 //   packing + transposes + stores, ~800 addressing / prefetch of the old words) and hold an accumulator set
-//   meanwhile -- 2640 clk per tile now against 1870 clk of MMAs (0.78 of the fp4 peak on this kernel).  Measured
-//   and NOT faster: 12 epilogue warps (the per-warp time does not shrink), one tmem_empty arrive per warp,
-//   token passing between the issuers (tiles issued strictly in turn), testing the next barrier before
-//   issuing (the extra try_wait costs the issuing thread more than it hides), back-off in the producers' and
-//   builders' waits, accumulators biased by 2^23 so that the parity needs no add (not exact: dropped), and
+//   meanwhile, against 1870 clk of MMAs.  Measured and NOT faster: 12 epilogue warps (the per-warp time does not
+//   shrink), two epilogue groups (one per accumulator set), one tmem_empty arrive per warp, handing the set back right
+//   after the last tcgen05.ld, token passing between the issuers (tiles issued strictly in turn), testing the next
+//   barrier before issuing (the extra try_wait costs the issuing thread more than it hides), back-off or tighter
+//   poll loops in the waits, accumulators biased by 2^23 so that the parity needs no add (not exact: dropped), and
 //   mbarrier.try_wait with a suspend-time hint (parked warps are not woken: the kernel takes seconds).
+// * What DID help once the above was in place (second half of round 2): the parity bias as packed add.rn.f32x2
+//   (1.5 instead of 2 instructions per accumulator: 20.05 -> 19.3 ms per 592 systems) and EVEN column tiles
+//   (TileGeo: no narrow rest tile, whose 16 MMAs of N = 16 cost the issuing thread as much as a full tile's:
+//   19.42 -> 18.80 ms; tensor pipe 83 % active per launch, 85 % where it was 86 % only on the one panel whose range
+//   240 divides).  With cheaper addressing and transposes changing nothing (18.9 ms), what is left between the kernel
+//   and the bare MMA time (15.3 ms) sits in the issue / barrier structure of the MMA stream itself.
 #ifndef OB2_U_SPS
 #define OB2_U_SPS 4
 #endif
