@@ -124,6 +124,14 @@ int emu_solve(int field, uint8_t *A, size_t a_rs, size_t a_ss, uint32_t rows, ui
     static const unsigned kPoly[4] = {3, 7, 19, 285}, kB[4] = {1, 2, 4, 8};
     p.red = field_red(kB[field], kPoly[field]);
   }
+  if (force_nbw == 40) {   // tall-system variant: 128-bit panels, per-row state in a "global" workspace (solve_kernel<.., GROWS>)
+    const int ggeo = geo == 4 ? 4 : 1;
+    if (!solve_grows_fits(rows, ggeo)) return -1;
+    std::vector<uint8_t> ws(solve_row_ws_bytes<4>(rows) * (size_t)grid + 256);
+    p.row_ws = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(ws.data()) + 255) & ~(uintptr_t)255);
+    p.row_ws_cta = solve_row_ws_bytes<4>(rows);
+    return launch_solve_grows(field, ggeo, p, grid, threads, smem_limit, nullptr);
+  }
   if (force_nbw == 2) {
     switch (field) {
     case OB2_GF256: return launch_solve_geo<8, 2>(geo, p, grid, threads, smem_limit, nullptr);

@@ -148,6 +148,22 @@ def test_solve(args, geo):
 
 
 @pytest.mark.parametrize("args", [
+    dict(field=GF256, rows=40, cols=40, b_bytes=64, seed=130),
+    dict(field=GF256, rows=150, cols=150, b_bytes=528, seed=131, threads=128, deficient=1),
+    dict(field=GF16, rows=70, cols=70, b_bytes=48, seed=132, deficient=2),
+    dict(field=GF4, rows=150, cols=150, b_bytes=16, seed=133, nsys=3, grid=2),
+    dict(field=GF2, rows=200, cols=200, b_bytes=32, seed=134, threads=128),
+    dict(field=GF2, rows=300, cols=100, b_bytes=0, seed=135, deficient=1),
+])
+@pytest.mark.parametrize("geo", [1, 4])
+@pytest.mark.parametrize("no_fast", [0, 1], ids=["fast_panel", "general_panel"])
+def test_solve_tall_variant_rows_in_global_memory(args, geo, no_fast):
+    """solve_kernel<.., NBW=4, GROWS>: the per-row state (panel chunk, coefficient vector, row map, candidate flags)
+    in a per-CTA block of a workspace outside shared memory; every field, 6- and 5-bit tables, both panel paths"""
+    _solve(nbw=40, geo=geo, no_fast=no_fast, **args)
+
+
+@pytest.mark.parametrize("args", [
     dict(field=GF256, rows=100, cols=100, b_bytes=272, seed=201, threads=64),
     dict(field=GF256, rows=100, cols=100, b_bytes=64, seed=202, threads=64, deficient=1),
     dict(field=GF256, rows=100, cols=100, b_bytes=64, seed=203, threads=64, deficient=2),
