@@ -318,3 +318,9 @@ print("pair ok")
     env = dict(os.environ, OBLAS_B200_TC_PAIR="1")
     r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert r.returncode == 0 and "pair ok" in r.stdout, r.stdout[-2000:]
+    # the same child with OBLAS_B200_TC_EVEN=0: the single-CTA update kernel on the FIXED tile geometry (240-column
+    # tiles + a rest tile, processed second) instead of the evenly dealt tiles every other test runs on
+    env = dict(os.environ, OBLAS_B200_TC_EVEN="0")
+    env.pop("OBLAS_B200_TC_PAIR", None)
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0 and "pair ok" in r.stdout, r.stdout[-2000:]
