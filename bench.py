@@ -727,7 +727,9 @@ def bench_e2e(L_, capi, torch, A0, B0, K, L, nsys, world, dist, ranks_gpu):
     # both directions run at once: the call cannot finish before the larger direction has moved its bytes
     # at the rate one direction gets while both are busy
     floor_s = max(h2d, d2h) / (raw["bidirectional_each_GBs"] * 1e9)
-    floor_skip_s = max(h2d / (raw["bidirectional_each_GBs"] * 1e9), d2h_skip / (raw["bidirectional_each_GBs"] * 1e9))
+    # skip variant: the directions are unequal (9.7 GB in, 5.4 GB out), so the lower bound is each direction at the
+    # rate it gets ALONE (the call can finish before h2d / bidirectional rate)
+    floor_skip_s = max(h2d / (raw["h2d_GBs"] * 1e9), d2h_skip / (raw["d2h_GBs"] * 1e9))
     return {"value": world * n / dt, "unit": "solves/s", "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h, "systems_per_gpu": n, "s_per_call": dt,
             "api": "oblas_b200_solve_batch_host (pinned host A,B in; A,B,rank out; 3-lane chunked copy/compute overlap)",
@@ -741,7 +743,9 @@ def bench_e2e(L_, capi, torch, A0, B0, K, L, nsys, world, dist, ranks_gpu):
             "skip_identity_A": {"value": world * n / dt_skip, "unit": "solves/s", "s_per_call": dt_skip,
                                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_skip, "frac_of_copy_floor": floor_skip_s / dt_skip,
                                 "api": "oblas_b200_solve_batch_host_ex(..., OBLAS_B200_SOLVE_SKIP_IDENTITY_A): A of the %d "
-                                       "full-rank systems (= I) is not copied back" % (n - deficient)}}
+                                       "full-rank systems (= I) is not copied back; the A of the other %d is written into the "
+                                       "pinned host buffer by a kernel (no host-side wait for the ranks)" % (n - deficient, deficient),
+                                "floor": "max(h2d bytes / unidirectional h2d rate, d2h bytes / unidirectional d2h rate)"}}
 
 
 # ------------------------------------------------------------------ the other BASELINE configs

@@ -241,7 +241,10 @@ int oblas_b200_solve_batch_host(int field, void *A_host, size_t a_row_stride, si
  * full-rank system is the identity matrix -- known in advance -- so it is NOT copied back: A_host
  * keeps the input for systems with rank_out[s] == rows and receives the reduced form only for the
  * rank-deficient ones.  Saves rows*cols of the (rows*cols + rows*b_row_bytes) bytes returned per
- * system (44 % at K=1024 with 1280-byte symbols). */
+ * system (44 % at K=1024 with 1280-byte symbols).  With A_host in pinned (cudaHostAlloc / cudaHostRegister)
+ * memory a kernel writes the rank-deficient systems' A straight into the host buffer, so the host never waits
+ * for the ranks of a chunk: 19.8 k against 17.7 k solves/s for the full copy-back on the same B200 box
+ * (K=1024, 1280-byte symbols); pageable memory takes a deferred cudaMemcpyAsync per deficient system. */
 #define OBLAS_B200_SOLVE_SKIP_IDENTITY_A 1u
 int oblas_b200_solve_batch_host_ex(int field, void *A_host, size_t a_row_stride, size_t a_sys_stride,
                                    uint32_t rows, uint32_t cols, size_t a_row_bytes,

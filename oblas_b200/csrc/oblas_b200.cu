@@ -278,6 +278,19 @@ int queue_push(int field, int op, uint8_t *a, size_t a_stride, const uint8_t *b,
   return 0;
 }
 
+// host streaming with OBLAS_B200_SOLVE_SKIP_IDENTITY_A and a pinned (device-visible) A_host: the A of the systems
+// that are NOT of full rank goes straight from the lane buffer into host memory -- a handful of systems per chunk,
+// decided on the device, so the host never has to wait for the ranks before it can reuse the lane
+__global__ void copy_deficient_kernel(const uint8_t *src, uint8_t *dst, const int32_t *rank, uint32_t rows,
+                                      uint32_t nsys, size_t sys_bytes) {
+  for (uint32_t s = blockIdx.x; s < nsys; s += gridDim.x) {
+    if ((uint32_t)rank[s] == rows) continue;
+    const uint4 *a = reinterpret_cast<const uint4 *>(src + (size_t)s * sys_bytes);
+    uint4 *d = reinterpret_cast<uint4 *>(dst + (size_t)s * sys_bytes);
+    for (size_t i = threadIdx.x; i < sys_bytes / 16; i += blockDim.x) d[i] = a[i];
+  }
+}
+
 __global__ void fill_random_kernel(uint64_t *dst, size_t nwords, uint64_t seed, uint64_t word0) {
   for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < nwords;
        n += (size_t)gridDim.x * blockDim.x) {
@@ -915,6 +928,16 @@ int oblas_b200_solve_batch_host_ex(int field, void *A_host, size_t a_row_stride,
   int32_t *pin_r = (int32_t *)cx().pin;
   uint32_t *pin_p = (uint32_t *)((uint8_t *)cx().pin + pin_rank);
 
+  // skip_ident with pinned host memory: a kernel copies the A of the rank-deficient systems back (no host wait);
+  // pageable host memory takes the deferred cudaMemcpyAsync path below
+  uint8_t *A_host_dev = nullptr;
+  if (skip_ident && (reinterpret_cast<uintptr_t>(A_host) & 15) == 0) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, A_host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+      A_host_dev = (uint8_t *)at.devicePointer;
+    else
+      cudaGetLastError();
+  }
   const bool trace = getenv("OBLAS_B200_TRACE") != nullptr;
   std::vector<cudaEvent_t> ev;
   cudaEvent_t ev_start = nullptr;
@@ -954,7 +977,7 @@ int oblas_b200_solve_batch_host_ex(int field, void *A_host, size_t a_row_stride,
   for (size_t first = 0; first < nsys && rc == 0; first += chunk_systems, c++) {
     HostLane &L = cx().lane[c % kLanes];
     size_t cnt = nsys - first < chunk_systems ? nsys - first : chunk_systems;
-    if (skip_ident && flush_lane((int)(c % kLanes))) { rc = -1; break; }
+    if (skip_ident && !A_host_dev && flush_lane((int)(c % kLanes))) { rc = -1; break; }
     cudaError_t e = cudaMemcpyAsync(L.A, (uint8_t *)A_host + first * a_sys_stride, cnt * a_sys_stride,
                                     cudaMemcpyHostToDevice, L.s);
     if (e == cudaSuccess && B_host)
@@ -986,7 +1009,11 @@ int oblas_b200_solve_batch_host_ex(int field, void *A_host, size_t a_row_stride,
     if (e == cudaSuccess && pivcols_out)
       e = cudaMemcpyAsync(pin_p + first * rows, L.piv, cnt * (size_t)rows * 4, cudaMemcpyDeviceToHost, L.s);
     if (e != cudaSuccess) { rc = fail("solve_host: copy to host failed: %s", cudaGetErrorString(e)); break; }
-    if (skip_ident) {
+    if (skip_ident && A_host_dev) {
+      const uint32_t g = cnt < 64 ? (uint32_t)cnt : 64u;
+      copy_deficient_kernel<<<g, 256, 0, L.s>>>(L.A, A_host_dev + first * a_sys_stride, L.rank, rows, (uint32_t)cnt, a_sys_stride);
+      if (after_launch("solve_host (copy-back of the rank-deficient systems)")) { rc = -1; break; }
+    } else if (skip_ident) {
       Pending &pd = pend[c % kLanes];
       if (!pd.done && cudaEventCreateWithFlags(&pd.done, cudaEventDisableTiming) != cudaSuccess) { rc = fail("solve_host: event"); break; }
       cudaEventRecord(pd.done, L.s);

@@ -296,6 +296,32 @@ def test_host_streaming_on_the_tensor_core_path(cuda_lib):
     assert np.array_equal(rank2, rank) and np.array_equal(B2, B)
     for s in range(nsys):
         assert np.array_equal(A2[s], A0[s] if rank[s] == K else want[s][2]), s
+    # the same from PINNED host memory: a kernel writes the A of the rank-deficient systems straight into the
+    # host buffer (no host-side wait for the ranks); two deficient systems in different chunks
+    pa = cuda_lib.oblas_b200_host_alloc(A0.nbytes)
+    pb = cuda_lib.oblas_b200_host_alloc(B0.nbytes)
+    try:
+        A3 = np.frombuffer((C.c_uint8 * A0.nbytes).from_address(pa), dtype=np.uint8).reshape(A0.shape)
+        B3 = np.frombuffer((C.c_uint8 * B0.nbytes).from_address(pb), dtype=np.uint8).reshape(B0.shape)
+        A3[:], B3[:] = A0, B0
+        A3[5, 7] = A3[5, 8]
+        w5 = ref_solve(GF256, A3[5].copy(), B3[5].copy(), K)
+        in5 = A3[5].copy()
+        rank3 = np.zeros(nsys, dtype=np.int32)
+        capi.check(cuda_lib.oblas_b200_solve_batch_host_ex(
+            GF256, A3.ctypes.data, A3.strides[1], A3.strides[0], K, K, K, B3.ctypes.data, B3.strides[1], B3.strides[0], L,
+            rank3.ctypes.data, None, nsys, 2, 1))
+        assert rank3[5] == w5[0] == K - 1 and rank3[2] == K - 1
+        for s in range(nsys):
+            if s == 5:
+                assert np.array_equal(A3[5], w5[2]) and np.array_equal(B3[5], w5[3])
+            else:
+                assert rank3[s] == rank[s] and np.array_equal(B3[s], B[s]), s
+                assert np.array_equal(A3[s], A0[s] if rank[s] == K else want[s][2]), s
+        assert not np.array_equal(A3[5], in5)
+    finally:
+        cuda_lib.oblas_b200_host_free(pa)
+        cuda_lib.oblas_b200_host_free(pb)
 
 
 def test_barrier_time_limit_is_reported_and_the_device_recovers(cuda_lib):
