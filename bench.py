@@ -688,9 +688,11 @@ def bench_e2e(L_, capi, torch, A0, B0, K, L, nsys, world, dist, ranks_gpu):
             return {"value": None, "unit": "solves/s", "error": "pinned host allocation failed"}
     rank = np.zeros(n, dtype=np.int32)
 
+    all_calls = {}
+
     def run(flags):
         times = []
-        for it in range(3):  # 1 warm-up + 2 timed calls
+        for it in range(6):  # 1 warm-up + 5 timed calls; the MEDIAN is reported (single calls vary by +-8 % on these boxes)
             torch.cuda.synchronize()
             capi.check(L_.oblas_b200_copy(hA, A0.data_ptr(), a_bytes))   # refill host inputs (untimed)
             capi.check(L_.oblas_b200_copy(hB, B0.data_ptr(), b_bytes))
@@ -704,7 +706,8 @@ def bench_e2e(L_, capi, torch, A0, B0, K, L, nsys, world, dist, ranks_gpu):
             dt = time.perf_counter() - t0
             if it:
                 times.append(dt)
-        dt = sum(times) / len(times)
+        dt = sorted(times)[len(times) // 2]
+        all_calls[flags] = [round(x, 4) for x in times]
         t = torch.tensor([dt], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -732,6 +735,7 @@ def bench_e2e(L_, capi, torch, A0, B0, K, L, nsys, world, dist, ranks_gpu):
     floor_skip_s = max(h2d / (raw["h2d_GBs"] * 1e9), d2h_skip / (raw["d2h_GBs"] * 1e9))
     return {"value": world * n / dt, "unit": "solves/s", "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h, "systems_per_gpu": n, "s_per_call": dt,
+            "s_per_call_all": all_calls.get(0), "statistic": "median of 5 timed calls after 1 warm-up call (rank 0's calls listed; max over ranks of the medians)",
             "api": "oblas_b200_solve_batch_host (pinned host A,B in; A,B,rank out; 3-lane chunked copy/compute overlap)",
             "first_system_identity": ok, "ranks_equal_device_resident_run": ranks_ok,
             "roofline": {"bound": "host<->device copies (PCIe / host memory), both directions busy", "unit": "GB/s",
@@ -740,7 +744,7 @@ def bench_e2e(L_, capi, torch, A0, B0, K, L, nsys, world, dist, ranks_gpu):
                          "note": "achieved = bytes of the larger direction / call time; peak = what one direction of a plain "
                                  "pinned cudaMemcpyAsync gets on this rank while the other direction and the other ranks "
                                  "copy too, measured in this run"},
-            "skip_identity_A": {"value": world * n / dt_skip, "unit": "solves/s", "s_per_call": dt_skip,
+            "skip_identity_A": {"value": world * n / dt_skip, "unit": "solves/s", "s_per_call": dt_skip, "s_per_call_all": all_calls.get(1),
                                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_skip, "frac_of_copy_floor": floor_skip_s / dt_skip,
                                 "api": "oblas_b200_solve_batch_host_ex(..., OBLAS_B200_SOLVE_SKIP_IDENTITY_A): A of the %d "
                                        "full-rank systems (= I) is not copied back; the A of the other %d is written into the "
