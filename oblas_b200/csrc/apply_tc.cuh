@@ -48,11 +48,12 @@
 // Only the product build sees this file (no host-thread emulation of tcgen05).
 #pragma once
 #include "gf_device.cuh"
+#include "tile_geo.h"
 
 namespace ob2 {
 namespace tc {
 
-constexpr int kHalfN = 240;                  // N of one MMA = columns of a half tile
+constexpr int kHalfN = kTileCols;            // N of one MMA = columns of a half tile (240, tile_geo.h)
 constexpr int kRowsI = 16;                   // C/Y rows per CTA tile (x 8 bit planes = 128 lanes)
 constexpr int kStepJ = 8;                    // coefficient columns per step (x 8 bits = K 64)
 constexpr int kHBlock = kHalfN * 32;         // bytes of one B-operand block: half tile x one step (7680)
@@ -110,35 +111,6 @@ struct TcRegion {
   uint32_t col0;       // first byte column of the range inside a row
   uint32_t ncols;      // bytes per row in the range (multiple of 16)
   uint32_t v0;         // first virtual column of the region (0 for region 0, region 0's ncols for region 1)
-};
-
-// Column tiles of a virtual column range [0, vend) (vend a multiple of 16), ntiles = ceil(vend / 240) of them.
-// FIXED geometry: tile t = columns [240 t, 240 t + 240), the last one takes the rest.  EVEN geometry (the rank-128
-// update of the elimination): the range is dealt out in groups of 16 columns as evenly as possible, every tile is
-// 16 * (q / ntiles) or 16 more columns wide.  The rest tile of the fixed geometry can be tiny (K = 1024, L = 1280,
-// outer panel 0: 2176 = 9 x 240 + 16) and costs its issuing thread the same ~1800 clk of waits, issues and commits as
-// a full tile for 1/15 of the tensor work -- ncu, tensor pipe active per outer panel: 85.8 % where 240 divides
-// the range (panel 2), 74-79 % with a narrow rest tile (panels 7, 0).
-struct TileGeo {
-  uint32_t b, x, vend;   // even: groups of 16 columns per tile, tiles with one group more; the end of the range
-  int even;
-  OB2_D void init(uint32_t vend_, uint32_t ntiles, int even_) {
-    vend = vend_;
-    even = even_ && ntiles > 0;
-    const uint32_t q = vend_ >> 4;
-    b = even ? q / ntiles : 0u;
-    x = even ? q - b * ntiles : 0u;
-  }
-  OB2_D void span(uint32_t t, uint32_t &v0, uint32_t &w) const {
-    if (even) {
-      v0 = 16u * (t * b + (t < x ? t : x));
-      w = 16u * (b + (t < x ? 1u : 0u));
-    } else {
-      v0 = t * (uint32_t)kHalfN;
-      const uint32_t rest = vend > v0 ? vend - v0 : 0u;
-      w = rest >= (uint32_t)kHalfN ? (uint32_t)kHalfN : ((rest + 15u) & ~15u);
-    }
-  }
 };
 
 struct ExpandArgs {

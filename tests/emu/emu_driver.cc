@@ -9,6 +9,7 @@
 #include "rowops.cuh"
 #include "solve.cuh"
 #include "tables_host.h"
+#include "tile_geo.h"
 
 using namespace ob2;
 
@@ -32,6 +33,16 @@ const uint8_t *emu_table(int ts, int which, unsigned *len) {
   }
   *len = 0;
   return nullptr;
+}
+// Column tiles of the tensor-core update launches (tile_geo.h): the tiles of [0, vend) in the fixed or the even
+// geometry -- start and width of tile t; returns the number of tiles (ceil(vend / 240)) or -1
+int emu_tile_geo(uint32_t vend, int even, uint32_t *starts, uint32_t *widths, uint32_t cap) {
+  const uint32_t ntiles = (vend + ob2::tc::kTileCols - 1) / ob2::tc::kTileCols;
+  if (ntiles > cap) return -1;
+  ob2::tc::TileGeo g;
+  g.init(vend, ntiles, even);
+  for (uint32_t t = 0; t < ntiles; t++) g.span(t, starts[t], widths[t]);
+  return (int)ntiles;
 }
 int emu_table_linear(int ts) {
   ensure_sets();

@@ -2,6 +2,8 @@
 (tests/emu): row ops, blocked elimination, apply -- bit-exact against the oracle.
 This is not the product path (the GPU tests are); it lets the GPU-less build
 container catch indexing / pivoting / table-build mistakes."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -16,6 +18,30 @@ def test_fastdiv_exact():
     e = emu()
     for d in (1, 2, 3, 5, 16, 80, 81, 640, 1000, 4096, 65536, 12345, 0x7FFFFFF):
         assert e.emu_fastdiv_check(d, 2_000_000, 7) == 1, d
+
+
+def test_update_tile_geometry():
+    """tile_geo.h: the column tiles of the tensor-core update launches.  Both geometries cover the range exactly once
+    with widths that are multiples of 16 and at most 240; the even one (the default) has no narrow rest tile: widths
+    differ by at most 16 columns.  All ranges of K = 1024 / L = 1280 and a sweep."""
+    e = emu()
+    cap = 512
+    starts, widths = (C.c_uint32 * cap)(), (C.c_uint32 * cap)()
+    for vend in [2176, 2048, 1920, 1792, 1664, 1536, 1408, 1280] + list(range(16, 4000, 16)) + [65536, 100000 // 16 * 16]:
+        for even in (0, 1):
+            n = e.emu_tile_geo(vend, even, starts, widths, cap)
+            assert n == (vend + 239) // 240
+            pos = 0
+            for t in range(n):
+                assert starts[t] == pos and widths[t] % 16 == 0 and 16 <= widths[t] <= 240, (vend, even, t)
+                pos += widths[t]
+            assert pos == vend
+            if even:
+                assert max(widths[:n]) - min(widths[:n]) <= 16 and list(widths[:n]) == sorted(widths[:n], reverse=True)
+            else:
+                assert all(w == 240 for w in widths[:n - 1])
+    n = e.emu_tile_geo(2176, 1, starts, widths, cap)
+    assert list(widths[:n]) == [224] * 6 + [208] * 4
 
 
 def test_table_linearity_flags():
