@@ -992,6 +992,9 @@ static_assert(kUSteps == kUSPS * kUStages, "one trip around the B ring per colum
 #ifndef OB2_U_EARLY_RELEASE
 #define OB2_U_EARLY_RELEASE 0
 #endif
+#ifndef OB2_U_ROLEMAP
+#define OB2_U_ROLEMAP 1
+#endif
 #ifndef OB2_U_WARPARRIVE
 #define OB2_U_WARPARRIVE 0
 #endif
@@ -1101,6 +1104,36 @@ __global__ void __launch_bounds__(kUThreads, 1) update_tc_kernel(const ApplyTcAr
   __syncthreads();
   tc_fence_after();
 
+  // Roles.  OB2_U_ROLEMAP = 0: warp 0 issuer, 1 producer, 2-5 builders, 6-13 epilogue, 14 issuer, 15 producer -- each
+  // issuing warp shares its scheduler (warp % 4) with a builder.  OB2_U_ROLEMAP = 1 (two issuers, two producers, one
+  // epilogue group): issuers 0 and 2 share their schedulers with the producers 4 and 14, the builders 1, 5, 3, 15 sit
+  // on the other two schedulers; the epilogue warps 6-13 (two per scheduler: the TMEM lane quarter is warp % 4) stay.
+  uint32_t role, ridx;   // 0 issuer, 1 producer, 2 builder, 3 epilogue; index within the role
+  if (OB2_U_ROLEMAP && kUIssuers == 2 && kUProducers == 2 && kUEpiGroups == 1) {
+    switch (warp) {
+    case 0: role = 0; ridx = 0; break;
+    case 2: role = 0; ridx = 1; break;
+    case 4: role = 1; ridx = 0; break;
+    case 14: role = 1; ridx = 1; break;
+    case 1: role = 2; ridx = 0; break;
+    case 5: role = 2; ridx = 1; break;
+    case 3: role = 2; ridx = 2; break;
+    case 15: role = 2; ridx = 3; break;
+    default: role = 3; ridx = warp - (uint32_t)kEpi0; break;
+    }
+  } else if (warp == kProdWarp || (kUProducers > 1 && warp >= (uint32_t)kProd2Warp)) {
+    role = 1;
+    ridx = (warp == kProdWarp) ? 0u : warp - (uint32_t)kProd2Warp + 1u;
+  } else if (warp == kMmaWarp || (kUIssuers > 1 && warp == (uint32_t)kMma2Warp)) {
+    role = 0;
+    ridx = (warp == kMmaWarp) ? 0u : 1u;
+  } else if (warp >= (uint32_t)kBuild0 && warp < (uint32_t)(kBuild0 + kBuilderWarps)) {
+    role = 2;
+    ridx = warp - kBuild0;
+  } else {
+    role = 3;
+    ridx = warp - (uint32_t)kEpi0;
+  }
   const uint32_t itiles = p.itiles, ntiles = p.ntiles;
   // units = (system, row tile): all pairs, or the list the outer-panel kernel left (lazy elimination)
   const uint32_t nunits = p.units ? *p.nunits_dev : p.nsys * itiles;
@@ -1115,9 +1148,9 @@ __global__ void __launch_bounds__(kUThreads, 1) update_tc_kernel(const ApplyTcAr
     }
   };
 
-  if (warp == kProdWarp || (kUProducers > 1 && warp >= (uint32_t)kProd2Warp)) {
+  if (role == 1) {
     // ------------------------------------------------------------ producers: B blocks of every column tile
-    const uint32_t pwi = (warp == kProdWarp) ? 0u : warp - (uint32_t)kProd2Warp + 1u;   // producer index
+    const uint32_t pwi = ridx;   // producer index
     const bool leader = elect_one();
     const uint32_t b_dst0 = smem_addr(smB);
     uint32_t ph = 0, tile_iter = 0;
@@ -1152,9 +1185,9 @@ __global__ void __launch_bounds__(kUThreads, 1) update_tc_kernel(const ApplyTcAr
       atomicAdd(p.prof + 7, (unsigned long long)pw);
       atomicAdd(p.prof + 8, (unsigned long long)(clock64() - pt0));
     }
-  } else if (warp == kMmaWarp || (kUIssuers > 1 && warp == (uint32_t)kMma2Warp)) {
+  } else if (role == 0) {
     // ------------------------------------------------------------ MMA issuers (see kMma2Warp)
-    const uint32_t me = (warp == kMmaWarp) ? 0u : 1u;   // two issuers: = accumulator set = parity of the tiles this warp issues
+    const uint32_t me = ridx;   // two issuers: = accumulator set = parity of the tiles this warp issues
     const bool leader = elect_one();
     // A,B = E2M1 (1), K-major, scales UE8M0, M = 128, K = 64; N is set per tile: 240, or the
     // 16-aligned rest of the virtual column range for the last tile (MMA time is proportional to N)
@@ -1240,9 +1273,9 @@ __global__ void __launch_bounds__(kUThreads, 1) update_tc_kernel(const ApplyTcAr
       atomicAdd(p.prof + 3, (unsigned long long)(clock64() - pt0));
       atomicAdd(p.prof + 12, (unsigned long long)tile_iter);   // all column tiles (this warp issued every other one)
     }
-  } else if (warp >= (uint32_t)kBuild0 && warp < (uint32_t)(kBuild0 + kBuilderWarps)) {
+  } else if (role == 2) {
     // ------------------------------------------------------------ A builders: once per (system, row tile)
-    const uint32_t b = warp - kBuild0;
+    const uint32_t b = ridx;
     const uint32_t i = lane >> 1, q = lane & 1u;
     const uint4 *lutc = lut_copy(lut, lane);
     uint32_t unit_iter = 0;
