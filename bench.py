@@ -322,6 +322,7 @@ def run_b200_arm(args):
     for _ in range(args.warmup):
         step()
     barrier()
+    L_.oblas_b200_lazy_stats((C.c_uint64 * 2)(), 1)    # reset: count the timed steps only
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -336,10 +337,13 @@ def run_b200_arm(args):
     ev1.record()
     barrier()
     launches = L_.oblas_b200_launch_count() - launches0
-    cls_ms, cls_n = (C.c_double * 4)(), (C.c_uint64 * 4)()
-    L_.oblas_b200_solve_tc_times(0, cls_ms, cls_n)
+    cls_ms, cls_n = (C.c_double * 5)(), (C.c_uint64 * 5)()
+    L_.oblas_b200_solve_tc_times_ex(0, cls_ms, cls_n, 5)   # 0 outer panel (lazy: compact pass), 1 expansion, 2 update, 3 permutation, 4 lazy: redo
     cls_ms = [float(x) / args.steps for x in cls_ms]   # per step
     cls_n = [int(x) // args.steps for x in cls_n]
+    lazy_st = (C.c_uint64 * 2)()
+    L_.oblas_b200_lazy_stats(lazy_st, 1)
+    lazy_pairs = [int(lazy_st[0]), int(lazy_st[1])]     # (system, outer panel) pairs: compact pass / given up, all steps incl. warm-up
     clocks = sampler.stop() if rank == 0 else None
     total_ms = ev0.elapsed_time(ev1)
     kern_ms = sum(a.elapsed_time(b) for a, b in kern_events) / len(kern_events)
@@ -400,19 +404,59 @@ def run_b200_arm(args):
         # outer-panel factorisation: shared-memory look-up bound.  Per 16-column step it streams ONE
         # combined 128-byte tile of every row (the live right part of the 128-column window and the
         # live left part of E are complementary): 22 LDS.128 per 16 bytes x 16 pivots
-        macs_per_clk_sm = 256.0 * 8.0 / 22.0
-        pan_macs = nsys * K * (K / 16.0) * 16 * 128            # rows x 16-col steps x 16 pivots x 128 bytes
+        lazy = cls_n[4] > 0
+        cmax = 144                                              # compact set of the lazy outer panels (library default)
+        panel_ms = cls_ms[0] + cls_ms[4]
+        if lazy:
+            # lazy flow: the compact pass streams the tile of cmax rows per step (4-bit tables: 32 look-ups per 16 bytes),
+            # the full kernel only the panels the compact pass gave up.  The compact pass is NOT look-up bound: per
+            # 16-column step its look-ahead runs a chain of 16 dependent column eliminations (~25 k clk) against ~6 k clk
+            # of look-ups, which is why two CTAs share an SM.
+            pairs_c, pairs_g = lazy_pairs[0] / args.steps, lazy_pairs[1] / args.steps
+            macs_per_clk_sm = 256.0 * 8.0 / 32.0
+            pan_macs = (pairs_c * cmax + pairs_g * K) * 8 * 16 * 128
+            kname = "ob2::panel_kernel<4,128,COMPACT> (2 CTAs of 256 threads per SM) + ob2::panel_kernel<6,128> for the panels it gives up"
+            bound = ("latency of the look-ahead chain (16 dependent column eliminations per 16-column step); the look-up work "
+                     "(compact sets of %d rows, 4-bit tables: %.1f GF(256) MAC/clk/SM) is what `frac` measures" % (cmax, macs_per_clk_sm))
+        else:
+            macs_per_clk_sm = 256.0 * 8.0 / 22.0
+            pan_macs = nsys * K * (K / 16.0) * 16 * 128            # rows x 16-col steps x 16 pivots x 128 bytes
+            kname = "ob2::panel_kernel<6,128>"
+            bound = "shared-memory LUT bandwidth (6-bit Four-Russians tables: %.1f GF(256) MAC/clk/SM)" % macs_per_clk_sm
         lut_peak = macs_per_clk_sm * sms * sm_mhz * 1e6
-        binding = {"kernel": "ob2::panel_kernel<6,128>",
-                   "bound": "shared-memory LUT bandwidth (6-bit Four-Russians tables: %.1f GF(256) MAC/clk/SM)" % macs_per_clk_sm,
-                   "achieved": pan_macs / (cls_ms[0] / 1e3) / 1e12, "peak": lut_peak / 1e12, "unit": "T GF-MAC/s",
-                   "frac": pan_macs / (cls_ms[0] / 1e3) / lut_peak, "sm_mhz_used": sm_mhz,
-                   "ms_per_step": {"panel_kernel": cls_ms[0], "expand_d_kernel": cls_ms[1],
+        binding = {"kernel": kname, "bound": bound,
+                   "achieved": pan_macs / (panel_ms / 1e3) / 1e12, "peak": lut_peak / 1e12, "unit": "T GF-MAC/s",
+                   "frac": pan_macs / (panel_ms / 1e3) / lut_peak, "sm_mhz_used": sm_mhz,
+                   "ms_per_step": {"panel_kernel": panel_ms, "expand_d_kernel": cls_ms[1],
                                    "update_tc_kernel": cls_ms[2], "permute_kernel": cls_ms[3]},
-                   "launches_per_step": {"panel_kernel": cls_n[0], "expand_d_kernel": cls_n[1],
+                   "launches_per_step": {"panel_kernel": cls_n[0] + cls_n[4], "expand_d_kernel": cls_n[1],
                                          "update_tc_kernel": cls_n[2], "permute_kernel": cls_n[3]},
                    "algorithmic_min_gmacs_per_system": macs_min / nsys / 1e9,
                    "executed_gmacs_per_system": macs / nsys / 1e9}
+        if lazy:
+            binding["lazy_outer_panels"] = {"compact_rows": cmax, "pairs_per_step_compact": pairs_c, "pairs_per_step_given_up": pairs_g,
+                                            "ms_per_step_compact_pass": cls_ms[0], "ms_per_step_redo": cls_ms[4]}
+            # the same batch with the FULL outer-panel kernel (every row in every 16-column step), for the A/B in this run
+            L_.oblas_b200_set_lazy_panels(0)
+            for _ in range(2):
+                step()
+            barrier()
+            L_.oblas_b200_solve_tc_times(1, None, None)
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(3):
+                step()
+            f1.record()
+            barrier()
+            fms, fn_ = (C.c_double * 5)(), (C.c_uint64 * 5)()
+            L_.oblas_b200_solve_tc_times_ex(0, fms, fn_, 5)
+            L_.oblas_b200_set_lazy_panels(-1)
+            fpan = float(fms[0]) / 3
+            binding["full_outer_panels"] = {
+                "value": world * nsys * 3 / (f0.elapsed_time(f1) / 1e3), "unit": "solves/s (this rank x world)",
+                "ms_per_step": {"panel_kernel": fpan, "expand_d_kernel": float(fms[1]) / 3, "update_tc_kernel": float(fms[2]) / 3},
+                "panel_kernel_frac_of_6bit_lut_ceiling": nsys * K * (K / 16.0) * 16 * 128 / (fpan / 1e3) / (256.0 * 8.0 / 22.0 * sms * sm_mhz * 1e6),
+                "note": "oblas_b200_set_lazy_panels(0): 3 steps right after the timed region, same inputs"}
     else:
         # shared-memory look-up ceiling of the table kernel: a row update of 16 bytes x 16 pivots
         # (256 byte-MACs) costs 22 LDS.128, the crossbar delivers 8 x 16 B per clk per SM

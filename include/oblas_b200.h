@@ -157,10 +157,13 @@ int oblas_b200_solve_tc_times_ex(int enable, double *ms_out, uint64_t *launches_
  * its own 128-byte window as the coefficient row -- the rows x 128 x 128 products of the coefficient matrix
  * disappear.  A system whose panel has a column without a pivot among the compact rows (rank deficiency, pivots
  * far down) is redone by the kernel that looks at all rows; results are identical either way.
- * compact_rows: rounded up to a multiple of 16, at least 128; 0 = off; < 0 = default (off).
- * Measured on B200 (K = 1024, 1280-byte symbols, 592 systems): the outer-panel kernel drops from 7.10 to 5.51 ms, but
- * the second expansion of the pivot rows (+1.38 ms) and the two update launches (+0.65 ms) cost more than that
- * (20 506 against 20 930 solves/s), so the default is off; bit-exact either way (pytest -m gpu runs both). */
+ * compact_rows: rounded up to a multiple of 16, at least 128; 0 = off; < 0 = default (144, and only for batches of at
+ * least 2 x (SM count) systems: smaller batches cannot put two compact CTAs on every SM and take the full kernel).
+ * The compact pass is bound by the chain of dependent column eliminations of its look-ahead, not by table look-ups,
+ * so it runs with the small 4-bit tables as two CTAs of 256 threads per SM.  Measured on B200 (K = 1024, 1280-byte
+ * symbols, 592 systems): outer-panel kernel 7.11 -> 3.68 ms, second expansion of the pivot rows +1.40 ms, update
+ * launches +0.4 ms: 21 520 -> 22 780 solves/s with compact sets of 144 rows (192: 22 390; 128: 21 670, the compact
+ * pass then gives up 48 of 4736 panels); bit-exact either way (pytest -m gpu runs both). */
 void oblas_b200_set_lazy_panels(int compact_rows);
 /* out[0] = (system, outer panel) pairs factorised by the compact pass so far, out[1] = pairs it gave up;
  * reset != 0 clears the counters */

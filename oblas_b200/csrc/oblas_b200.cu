@@ -90,7 +90,8 @@ struct Ctx {
   int no_fast_panel = 0;               // diagnostics: general panel path only
   int solve_tall = 1;                  // table kernel: per-row state in a global workspace when 128-bit panels do not fit shared memory (oblas_b200_set_tall_mode)
   unsigned long long *d_lazy_stats = nullptr;   // {compact, given up} (system, outer panel) pairs
-  int tc_lazy_rows = 0;                // tensor-core elimination: rows of the compact set of the lazy outer panels, 0 = off (the default: measured 2 % slower than the full outer-panel kernel)
+  int tc_lazy_rows = 144;              // tensor-core elimination: rows of the compact set of the lazy outer panels (0 = off); 144 measured best
+  bool tc_lazy_auto = true;            // default setting: lazy only for chunks of at least 2 x (SM count) systems (two compact CTAs per SM)
   unsigned long long *d_phase = nullptr;  // solve-kernel phase counters (diagnostics)
   unsigned long long *d_uprof = nullptr;  // update_tc_kernel role counters (diagnostics)
   DevTableSet *d_sets = nullptr;  // [TS_COUNT] in device memory
@@ -501,9 +502,10 @@ void oblas_b200_queue_stats(uint64_t *batches, uint64_t *ops) {
 }
 void oblas_b200_set_panel_path(int general_only) { cx().no_fast_panel = general_only & 3; }
 // Lazy outer panels of the tensor-core elimination (solve_tc_run): compact_rows = rows of the compact set
-// (rounded up to a multiple of 16, at least 128), 0 = off (every outer panel factorised over all rows), < 0 = default
+// (rounded up to a multiple of 16, at least 128), 0 = off (every outer panel factorised over all rows), < 0 = default (144)
 void oblas_b200_set_lazy_panels(int compact_rows) {
-  if (compact_rows < 0) compact_rows = 0;
+  cx().tc_lazy_auto = compact_rows < 0;
+  if (compact_rows < 0) compact_rows = 144;
   if (compact_rows > 0) {
     if (compact_rows < 128) compact_rows = 128;
     if (compact_rows > 1024) compact_rows = 1024;
@@ -1432,7 +1434,10 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
   const size_t map_per_sys = ((size_t)rows * 2 + 15) / 16 * 16;
   const size_t small_per_sys = 2 * kOuterBytes + 16;   // piv_all (u16 x 128) + tcount + npiv + pad
   // lazy outer panels (header of panel_kernel, solve.cuh): compact set of cmax rows per system
-  const uint32_t cmax = (rows >= (uint32_t)kOuterBytes) ? (uint32_t)cx().tc_lazy_rows : 0u;
+  // (default setting: only for batches of at least 2 x (SM count) systems -- the compact pass needs two CTAs per SM
+  // to overlap their look-ahead chains; the 148-system chunks of the host-streaming call take the full kernel)
+  const uint32_t cmax = (rows >= (uint32_t)kOuterBytes && (!cx().tc_lazy_auto || nsys >= 2 * (size_t)cx().sm_count))
+                            ? (uint32_t)cx().tc_lazy_rows : 0u;
   const bool lazy = cmax != 0;
   const size_t wc_per_sys = (size_t)cmax * kOuterBytes;
   const size_t lazy_per_sys = solve_tc_lazy_ws_per_system(rows);
@@ -1516,7 +1521,15 @@ int solve_tc_run(SolveArgs &p, size_t nsys) {
         pc.stats = cx().d_lazy_stats;
         {
           TcTimer tt(0);
-          int rc = launch_panel_t<6, 128>(pc, grid, cx().smem_optin, cx().stream);
+          // The compact pass is bound by the look-ahead chain (16 dependent column eliminations per step on two
+          // warps: ~25 k clk per step, against ~6 k clk of tile pass over 192 rows), not by table look-ups: with
+          // the 4-bit tables (64 KB) and 256 threads two CTAs share an SM and their chains overlap.
+          // OBLAS_B200_LAZY_GEO=6: one CTA of 512 threads per SM with the 6-bit tables (A/B runs).
+          static const bool geo6 = getenv("OBLAS_B200_LAZY_GEO") && atoi(getenv("OBLAS_B200_LAZY_GEO")) == 6;
+          // (measured: 256 threads x 2 CTAs per SM 3.73 ms per 592 systems; 192 x 2: 3.78; 160 x 3: 4.03; 128 x 4: 4.14)
+          const uint32_t grid2 = cnt < 2u * (uint32_t)cx().sm_count ? cnt : 2u * (uint32_t)cx().sm_count;
+          int rc = geo6 ? launch_panel_t<6, 128>(pc, grid, cx().smem_optin, cx().stream)
+                        : launch_panel_t<4, 128>(pc, grid2, cx().smem_optin, cx().stream, 256);
           if (rc) return fail("solve (tensor-core path): compact panel kernel launch configuration failed (%d)", rc);
         }
         if (after_launch("solve (compact outer panel)")) return -1;

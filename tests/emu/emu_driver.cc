@@ -237,6 +237,11 @@ int emu_solve_outer(uint8_t *A, size_t a_rs, size_t a_ss, uint32_t rows, uint32_
 // kernel, then two updates -- launch A: the compact rows with their coefficient rows against the OLD pivot
 // rows (row tiles through crow), launch B: every other row with its own window as the coefficient row against
 // the NEW pivot rows.  Both updates are CPU loops here that walk the unit lists exactly as update_tc_kernel does.
+// table geometry of the COMPACT pass of the lazy flow: 6 = 6-bit groups (as the full kernel), 4 = 4-bit groups (what
+// the product launches: two CTAs of 256 threads per SM)
+static int g_lazy_kb = 6;
+void emu_set_lazy_kb(int kb) { g_lazy_kb = kb == 4 ? 4 : 6; }
+
 int emu_solve_outer_lazy(uint8_t *A, size_t a_rs, size_t a_ss, uint32_t rows, uint32_t cols, uint32_t a_bytes,
                          uint8_t *B, size_t b_rs, size_t b_ss, uint32_t b_bytes, int32_t *rank,
                          uint32_t *pivcols, uint32_t nsys, uint32_t grid, uint32_t threads, size_t smem_limit,
@@ -265,7 +270,8 @@ int emu_solve_outer_lazy(uint8_t *A, size_t a_rs, size_t a_ss, uint32_t rows, ui
     pa.unitsA = unitsA.data(); pa.unitsB = unitsB.data(); pa.nunitsA = &ncount[0]; pa.nunitsB = &ncount[1];
     ncount[0] = ncount[1] = 0;
     pa.cmax = cmax;
-    int rc = launch_panel_t<6, 128>(pa, grid, smem_limit, nullptr, threads);
+    int rc = g_lazy_kb == 4 ? launch_panel_t<4, 128>(pa, grid, smem_limit, nullptr, threads)
+                            : launch_panel_t<6, 128>(pa, grid, smem_limit, nullptr, threads);
     if (rc) return rc;
     pa.cmax = 0; pa.only_flagged = 1;
     rc = launch_panel_t<6, 128>(pa, grid, smem_limit, nullptr, threads);

@@ -358,7 +358,8 @@ def test_outer_panel_elimination(args):
     dict(rows=300, cols=256, b_bytes=32, seed=508, cmax=144, antidiag=True, flagged=1),  # panel 0: pivots far below the compact set (redone); panel 1: right at its top
     dict(rows=300, cols=256, b_bytes=32, seed=509, cmax=144, swap_far=True, flagged=None),
 ])
-def test_lazy_outer_panel_elimination(args):
+@pytest.mark.parametrize("kb", [4, 6], ids=["compact_pass_4bit_tables", "compact_pass_6bit_tables"])
+def test_lazy_outer_panel_elimination(args, kb):
     """the LAZY tensor-core elimination: compact outer-panel factorisation (windows of the first cmax unpivoted
     rows only), full kernel for the panels it gives up, update launch A (compact rows, old pivot rows) and
     launch B (all other rows with their own window as coefficients, NEW pivot rows) walked through the unit
@@ -385,6 +386,7 @@ def test_lazy_outer_panel_elimination(args):
     rank = np.zeros(nsys, dtype=np.int32)
     piv = np.full((nsys, rows), 0xFFFFFFFF, dtype=np.uint32)
     stats = np.zeros(3, dtype=np.uint32)
+    e.emu_set_lazy_kb(kb)   # the product launches the compact pass with the 4-bit tables (two CTAs per SM)
     rc = e.emu_solve_outer_lazy(ptr(A), A.strides[1], A.strides[0], rows, cols, A.shape[2],
                                 ptr(B) if B is not None else None, B.strides[1] if B is not None else 0,
                                 B.strides[0] if B is not None else 0, B.shape[2] if B is not None else 0,

@@ -223,7 +223,7 @@ def test_elimination_in_several_chunks_of_systems(cuda_lib):
     B = np.stack([splitmix_bytes(9300 + s, K * L).reshape(K, L) for s in range(nsys)]).copy()
     per_sys = 4 * 16 * 7680 + K * 128 + K * 2 + 272
     per_sys += 2 * 192 * 128 + 192 * 2 + 16 + (192 // 16 + K // 16) * 4    # lazy outer panels, compact sets of 192 rows
-    cuda_lib.oblas_b200_set_lazy_panels(192)   # (off by default: the lazy flow has the bigger workspace and more launch classes)
+    cuda_lib.oblas_b200_set_lazy_panels(192)   # (the lazy flow has the bigger workspace and more launch classes)
     old = cuda_lib.oblas_b200_set_workspace_budget(2 * per_sys + 4096)
     try:
         cuda_lib.oblas_b200_set_tuning(3, -1)
@@ -239,10 +239,11 @@ def test_elimination_in_several_chunks_of_systems(cuda_lib):
         cuda_lib.oblas_b200_set_workspace_budget(old)
         cuda_lib.oblas_b200_set_tuning(-1, -1)
         cuda_lib.oblas_b200_set_lazy_panels(-1)
-    # the same batch with the default flow (full outer panels), also in chunks of two systems
+    # the same batch with full outer panels, also in chunks of two systems
     per_sys0 = 4 * 16 * 7680 + K * 128 + K * 2 + 272
     old = cuda_lib.oblas_b200_set_workspace_budget(2 * per_sys0 + 4096)
     try:
+        cuda_lib.oblas_b200_set_lazy_panels(0)
         cuda_lib.oblas_b200_set_tuning(3, -1)
         cuda_lib.oblas_b200_solve_tc_times(1, None, None)
         fA, fB = dev(A), dev(B)
@@ -255,6 +256,7 @@ def test_elimination_in_several_chunks_of_systems(cuda_lib):
     finally:
         cuda_lib.oblas_b200_set_workspace_budget(old)
         cuda_lib.oblas_b200_set_tuning(-1, -1)
+        cuda_lib.oblas_b200_set_lazy_panels(-1)
     cuda_lib.oblas_b200_set_tuning(1, -1)
     tA, tB = dev(A), dev(B)
     trank, tpiv = device.solve_batch(GF256, tA, K, tB, want_pivcols=True)
@@ -553,3 +555,44 @@ def test_tall_systems_on_the_table_kernel(cuda_lib, field, rows, cols, bbytes):
     finally:
         cuda_lib.oblas_b200_set_tall_mode(1)
         cuda_lib.oblas_b200_set_tuning(-1, -1)
+
+
+def test_default_flow_of_a_big_batch_is_the_lazy_one(cuda_lib):
+    """default settings: a GF(256) batch of at least 2 x (SM count) systems takes the lazy outer panels (compact sets
+    of 144 rows, two compact CTAs per SM); the same batch with the full outer-panel kernel must give the same bytes,
+    ranks and pivot columns, and a few systems (two of them rank deficient) must equal the oracle's result"""
+    K, L = 512, 64
+    nsys = 2 * cuda_lib.oblas_b200_sm_count() + 3
+    dA0 = torch.empty((nsys, K, K), dtype=torch.uint8, device="cuda")
+    dB0 = torch.empty((nsys, K, L), dtype=torch.uint8, device="cuda")
+    device.fill_random(dA0, 9850)
+    device.fill_random(dB0, 9851)
+    dA0[7, 100] = dA0[7, 3]
+    dA0[nsys - 2, :, 300] = 0
+    out = {}
+    try:
+        for lazy in (-1, 0):
+            cuda_lib.oblas_b200_set_lazy_panels(lazy)
+            st = (C.c_uint64 * 2)()
+            cuda_lib.oblas_b200_lazy_stats(st, 1)
+            dA, dB = dA0.clone(), dB0.clone()
+            rank, piv = device.solve_batch(GF256, dA, K, dB, want_pivcols=True)
+            device.sync()
+            cuda_lib.oblas_b200_lazy_stats(st, 1)
+            out[lazy] = (dA, dB, rank, piv, (int(st[0]), int(st[1])))
+    finally:
+        cuda_lib.oblas_b200_set_lazy_panels(-1)
+    assert out[0][4] == (0, 0)
+    compact, given_up = out[-1][4]
+    assert compact + given_up == nsys * 4 and compact >= (nsys - 2) * 4 and given_up >= 1
+    for k in range(4):
+        assert torch.equal(out[-1][k], out[0][k]), k
+    rank = host(out[-1][2])
+    assert rank[7] == K - 1 and rank[nsys - 2] == K - 1
+    A0, B0 = host(dA0), host(dB0)
+    gA, gB, gp = host(out[-1][0]), host(out[-1][1]), host(out[-1][3])
+    for s in (0, 7, nsys // 2, nsys - 2, nsys - 1):
+        a, b = A0[s].copy(), B0[s].copy()
+        rk, pv = oracle_solve(GF256, a, b, K)
+        assert rank[s] == rk and np.array_equal(gA[s], a) and np.array_equal(gB[s], b), s
+        assert np.array_equal(gp[s][:rk].astype(np.uint32), pv[:rk]), s

@@ -22,14 +22,15 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module", autouse=True,
                 params=[(-1, 0, -1), (0, 0, -1), (1, 0, -1), (2, 0, -1), (4, 0, -1), (-1, 1, -1), (3, 0, -1), (3, 1, -1),
-                        (3, 0, 192), (3, 0, 128), (3, 1, 144)],
+                        (3, 0, 0), (3, 0, 192), (3, 0, 128), (3, 1, 144)],
                 ids=["auto", "geo4x256", "geo6x128", "geo7x64", "geo5x128", "general_panel_path", "tcgen05", "tcgen05_general_panel",
-                     "tcgen05_lazy192", "tcgen05_lazy128", "tcgen05_lazy144_general_panel"])
+                     "tcgen05_full_panels", "tcgen05_lazy192", "tcgen05_lazy128", "tcgen05_lazy144_general_panel"])
 def _bind(cuda_lib, request):
     """every test of this module runs once per Four-Russians table geometry, once with the
     register-resident fast panel factorisation disabled, and (GF(256)) on the tensor-core path
-    (outer panels of 128 columns + tcgen05 rank-128 updates) with both panel factorisations, with the full
-    outer panels (the default) and with the lazy outer panels (compact sets of 192, 128 and 144 rows)"""
+    (outer panels of 128 columns + tcgen05 rank-128 updates) with both panel factorisations, with the full outer
+    panels (what batches of this size get by default, and forced) and with the lazy outer panels (compact sets of 192,
+    128 and 144 rows; the default for batches of at least 2 x (SM count) systems)"""
     device.bind(0)
     geo, general, lazy = request.param
     cuda_lib.oblas_b200_set_tuning(geo, geo)
