@@ -55,16 +55,19 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 K_DEFAULT, L_DEFAULT, NSYS_DEFAULT = 1024, 1280, 4096
 
 
-def ncu_update_traffic_per_system():
+def ncu_update_traffic_per_system(lazy=False):
     """dram__bytes_read.sum + dram__bytes_write.sum per system and update_tc_kernel launch, AVERAGED over
-    the 8 launches (outer panels) of one K=1024/L=1280 elimination, from the committed ncu --set full
-    capture of all 8 (profiles/r02_ncu_update_tc_all_panels.json, written by tools/summarize_profiles.py).
-    Falls back to the round-1 capture of outer panel 0 scaled by the modelled bytes (Y read + write,
-    E, fp4 operand blocks) of the average panel over panel 0."""
+    the launches of one K=1024/L=1280 elimination, from the committed ncu --set full captures of all of them:
+    profiles/r02_ncu_update_tc_all_panels.json (full outer panels: 8 launches) or, for the lazy flow (two
+    launches per outer panel, each over all systems), profiles/r02_ncu_update_tc_lazy.json (16 launches,
+    tools/ncu_launch_table.py).  Falls back to the round-1 capture of outer panel 0 scaled by the modelled
+    bytes (Y read + write, E, fp4 operand blocks) of the average panel over panel 0."""
+    name = "r02_ncu_update_tc_lazy.json" if lazy else "r02_ncu_update_tc_all_panels.json"
     try:
-        with open(os.path.join(ROOT, "profiles", "r02_ncu_update_tc_all_panels.json")) as f:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
             d = json.load(f)
-        return float(d["dram_bytes_per_system_per_launch"]), d.get("source", "profiles/r02_ncu_update_tc_all_panels.json")
+        src = d.get("source", "")
+        return float(d["dram_bytes_per_system_per_launch"]), src if src.startswith("profiles/") else "profiles/%s: %s" % (name, src)
     except Exception:
         def model(p):
             trailing = max(1024 - 128 * (p + 1), 0) + 1280
@@ -380,10 +383,15 @@ def run_b200_arm(args):
         # (profiles/r01_ncu_update_tc.json: dram read + write of one launch on 296 systems)
         # (outer panel 0, the widest), scaled to the systems of one launch of this run
         sys_per_launch = nsys * nouter / max(cls_n[2], 1)
+        lazy_flow = cls_n[4] > 0
         traffic, traffic_src = None, None
         if (K, L) == (K_DEFAULT, L_DEFAULT):
-            per_sys, traffic_src = ncu_update_traffic_per_system()   # same panel mix as algorithmic_bytes_per_launch
-            traffic = per_sys * sys_per_launch
+            # same panel mix as algorithmic_bytes_per_launch.  The lazy flow updates every outer panel with TWO
+            # launches that each cover all systems of the chunk (sys_per_launch above is then half a chunk: the
+            # algorithmic bytes -- Y read and written once per panel -- are spread over both), so its capture's
+            # per-launch average is taken x 2 per system.
+            per_sys, traffic_src = ncu_update_traffic_per_system(lazy_flow)
+            traffic = per_sys * sys_per_launch * (2 if lazy_flow else 1)
         roofline = {"kernel": "ob2::tc::update_tc_kernel", "bound": "tensor", "achieved": ach, "peak": fp4_peak,
                     "unit": "TFLOP/s", "frac": ach / fp4_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": fp4_src,
                     "launches_per_step": cls_n[2], "ms_per_step": upd_ms, "share_of_step": upd_ms / kern_ms,
